@@ -1,0 +1,51 @@
+// TEST HARNESS (CPU): compiles the product's device math (chain_dynamics.cuh) for the host so the
+// link-frame formulation can be compared with the oracle without a GPU.  Not a product path.
+#include <cstddef>
+#include "../../mjmpc_b200/csrc/chain_dynamics.cuh"
+
+using namespace mjb;
+struct PtrParams { const double* p; double operator[](int i) const { return p[i]; } };
+
+template <class T>
+static void run(const double* P, const double* qpos, const double* qvel, const double* target, int K, int H,
+                const double* mean, const double* noise, double* costs, double* qv, int* iters) {
+    PtrParams prm{P};
+    const int fs = (int)P[CS_FRAME_SKIP];
+    for (int k = 0; k < K; k++) {
+        double q[7], v[7], u[7], sn[7], cs[7];
+        for (int j = 0; j < 7; j++) { q[j] = qpos[j]; v[j] = qvel[j]; }
+        for (int t = 0; t < H; t++) {
+            for (int j = 0; j < 7; j++) u[j] = mean[t * 7 + j] + noise[((size_t)k * H + t) * 7 + j];
+            V3 hand{0, 0, 0};
+            for (int s = 0; s < fs; s++) {
+                for (int j = 0; j < 7; j++) sincos(q[j], &sn[j], &cs[j]);
+                if (s == fs - 1) hand = chain_point_world<T>(prm, sn, cs, V3{P[CS_HAND], P[CS_HAND + 1], P[CS_HAND + 2]});
+                chain_substep<T>(prm, q, v, sn, cs, u);
+            }
+            costs[(size_t)k * H + t] = reach_cost(hand, V3{target[0], target[1], target[2]});
+            for (int j = 0; j < 7; j++) { qv[((size_t)k * H + t) * 14 + j] = q[j]; qv[((size_t)k * H + t) * 14 + 7 + j] = v[j]; }
+        }
+    }
+    (void)iters;
+}
+
+extern "C" void hostcheck_rollout(const double* P166, int dense, const double* qpos, const double* qvel,
+                                  const double* target, int K, int H, const double* mean, const double* noise,
+                                  double* costs, double* qv) {
+    double P[CH_NDEV];
+    for (int i = 0; i < CH_NPARAM; i++) P[i] = P166[i];
+    mjb_derive_params(P);
+    if (dense) run<DenseTraits>(P, qpos, qvel, target, K, H, mean, noise, costs, qv, nullptr);
+    else run<SawyerTraits>(P, qpos, qvel, target, K, H, mean, noise, costs, qv, nullptr);
+}
+extern "C" int hostcheck_fits_sawyer(const double* P166) { return mjb_params_fit_sawyer(P166); }
+extern "C" void hostcheck_mass_bias(const double* P166, const double* q, const double* v, double* M, double* bias) {
+    double P[CH_NDEV];
+    for (int i = 0; i < CH_NPARAM; i++) P[i] = P166[i];
+    mjb_derive_params(P);
+    PtrParams prm{P};
+    double sn[7], cs[7], qd[7], Mm[7][7], b[7];
+    for (int j = 0; j < 7; j++) { sincos(q[j], &sn[j], &cs[j]); qd[j] = v[j]; }
+    chain_mass_bias<SawyerTraits>(prm, sn, cs, qd, Mm, b);
+    for (int i = 0; i < 7; i++) { bias[i] = b[i]; for (int j = 0; j <= i; j++) { M[i * 7 + j] = Mm[i][j]; M[j * 7 + i] = Mm[i][j]; } }
+}
