@@ -415,7 +415,7 @@ MJB_HD void solve_constraints(const double (&M)[7][7], const double (&f)[7], con
             break;
         }
         // exact line search on phi(t) = obj(a + t p), p = x - a:  phi'(t) piecewise linear, increasing
-        double p[7], Mp[7], g0 = 0.0, h0 = 0.0;
+        double p[7], g0 = 0.0, h0 = 0.0;
 #pragma unroll
         for (int j = 0; j < 7; j++) p[j] = x[j] - a[j];
 #pragma unroll
@@ -426,9 +426,8 @@ MJB_HD void solve_constraints(const double (&M)[7][7], const double (&f)[7], con
                 const double mik = k <= i ? M[i][k] : M[k][i];
                 s += mik * p[k]; ga += mik * a[k];
             }
-            Mp[i] = s; g0 += p[i] * ga; h0 += p[i] * s;
+            g0 += p[i] * ga; h0 += p[i] * s;
         }
-        (void)Mp;
         double jar[8], jp[8], Dr[8];
 #pragma unroll
         for (int j = 0; j < 7; j++) { jar[j] = R.sg[j] * a[j] - R.aref[j]; jp[j] = R.sg[j] * p[j]; Dr[j] = R.D[j]; }

@@ -1,0 +1,249 @@
+"""GPU stand-in for the reference's rollout stack.
+
+Mirrors the public surface of ``SubprocVecEnv`` that the MPC hot path uses
+(reference: ``mjmpc/envs/vec_env/subproc_vec_env.py:128-135`` rollout, ``:235-251``
+set_env_state, ``:304-312`` randomize_dynamics, ``:188-190`` reset, ``:192-204`` close) on top
+of the batched CUDA rollout (``csrc/rollout_reacher.cu``), so the reference driver's
+
+    policy.controller.set_sim_state_fn = sim_env.set_env_state
+    policy.controller.rollout_fn = rollout_fn          # examples/example_mpc.py:112-133,154-155
+
+keeps working: :meth:`rollout` returns the reference's 6-tuple of numpy arrays, and
+:meth:`rollout_fn` is the closure of ``examples/example_mpc.py:112-133`` returning the
+trajectories dict -- as device tensors for this package's controllers, as numpy arrays when
+the caller passed numpy noise (i.e. an unmodified reference controller).
+
+``n_workers`` plays the role of ``num_cpu``: particle k is simulated with model instance
+``k // (K / n_workers)`` -- the reference's contiguous-block split -- which only matters after
+``randomize_dynamics`` gave every worker its own model.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .model import CompiledModel, compile_model, randomized_copy, reacher7dof_spec
+
+
+class DeviceModel:
+    """Owns one ``mjb_model`` (n_instances parameter blocks in HBM)."""
+
+    def __init__(self, params: np.ndarray, device: int = 0):
+        params = np.ascontiguousarray(params, np.float64).reshape(-1, _lib.MODEL_NPARAM)
+        self.n_instances = params.shape[0]
+        self.device = device
+        h = C.c_void_p()
+        _lib.check(_lib.lib().mjb_model_create(
+            params.ctypes.data_as(_lib.c_double_p), C.c_int(self.n_instances), C.c_int(device), C.byref(h)))
+        self.handle = h
+
+    def update(self, first: int, params: np.ndarray):
+        params = np.ascontiguousarray(params, np.float64).reshape(-1, _lib.MODEL_NPARAM)
+        _lib.check(_lib.lib().mjb_model_update(
+            self.handle, C.c_int(first), C.c_int(params.shape[0]),
+            params.ctypes.data_as(_lib.c_double_p), _lib.stream_ptr()))
+
+    def close(self):
+        if self.handle is not None:
+            _lib.lib().mjb_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _state_vector(state) -> np.ndarray:
+    """Reacher env state dict (reacher_env.py:81-85) -> qpos, qvel, target (17,).
+    ``qa`` only seeds MuJoCo's solver warm start and ``timestep`` only drives timed events of
+    the continual variant; neither influences the rollout."""
+    if isinstance(state, dict):
+        return np.concatenate([np.asarray(state["qp"], float).reshape(7),
+                               np.asarray(state["qv"], float).reshape(7),
+                               np.asarray(state["target_pos"], float).reshape(3)])
+    s = np.asarray(state, float).reshape(-1)
+    if s.size != _lib.STATE_DIM:
+        raise ValueError("state must be a reacher state dict or a (17,) vector")
+    return s
+
+
+class GpuReacherVecEnv:
+    d_action = 7
+    d_obs = 20          # gym_env_wrapper.py:16-28 measures 7+7+3+3 on this env
+    d_state = 25        # gym_env_wrapper.py:29-39: qp,qv,qa (7 each) + target (3) + timestep (1)
+
+    def __init__(self, model: Optional[CompiledModel] = None, n_workers: int = 1, device: int = 0,
+                 return_observations: bool = False):
+        if not torch.cuda.is_available():
+            raise _lib.MjbError("GpuReacherVecEnv needs a CUDA device (there is no CPU fallback)")
+        self.compiled = model if model is not None else compile_model(reacher7dof_spec())
+        self.n_workers = int(n_workers)
+        self.device = torch.device("cuda", device)
+        self.return_observations = return_observations
+        self._worker_models = [self.compiled] * self.n_workers
+        self._defaults = [dict() for _ in range(self.n_workers)]
+        self.model = DeviceModel(np.stack([m.chain.params for m in self._worker_models]), device)
+        self._state_host = torch.zeros(1, _lib.STATE_DIM, dtype=torch.float64).pin_memory()
+        self._state = torch.zeros(1, _lib.STATE_DIM, dtype=torch.float64, device=self.device)
+        self.action_lows = -np.ones(7)
+        self.action_highs = np.ones(7)
+
+    # ---- SubprocVecEnv surface -------------------------------------------------------------
+    def set_env_state(self, state_dicts):
+        """One state for every particle, or a list with one state per batched controller."""
+        if isinstance(state_dicts, (list, tuple)):
+            rows = np.stack([_state_vector(s) for s in state_dicts])
+        else:
+            rows = _state_vector(state_dicts)[None]
+        if self._state_host.shape[0] != rows.shape[0]:
+            self._state_host = torch.zeros(rows.shape[0], _lib.STATE_DIM, dtype=torch.float64).pin_memory()
+            self._state = torch.zeros(rows.shape[0], _lib.STATE_DIM, dtype=torch.float64, device=self.device)
+        self._state_host.copy_(torch.from_numpy(rows))
+        self._state.copy_(self._state_host, non_blocking=True)
+
+    def set_env_state_device(self, state: torch.Tensor):
+        """Device-resident (n_ctrl, 17) states (no host round trip)."""
+        self._state = state.reshape(-1, _lib.STATE_DIM).contiguous()
+
+    def reset(self):
+        pass
+
+    def close(self):
+        self.model.close()
+
+    def randomize_dynamics(self, param_dict, base_seed):
+        """Per-worker model perturbation, worker i seeded with base_seed + i*12345
+        (subproc_vec_env.py:304-312 -> gym_env_wrapper.py:367-416)."""
+        defaults, randomized = [], []
+        for i in range(self.n_workers):
+            rng = np.random.RandomState(base_seed + i * 12345)
+            m, d, r = randomized_copy(self.compiled, param_dict, rng, self._defaults[i])
+            self._worker_models[i] = m
+            defaults.append(d)
+            randomized.append(r)
+        self.model.update(0, np.stack([m.chain.params for m in self._worker_models]))
+        return defaults, randomized
+
+    # ---- rollouts ----------------------------------------------------------------------------
+    def rollout_device(self, num_particles: int, horizon: int, mean: torch.Tensor, noise: Optional[torch.Tensor],
+                       costs: Optional[torch.Tensor] = None, actions: Optional[torch.Tensor] = None,
+                       want_traj: bool = False, want_obs: bool = False, want_ncon: bool = False):
+        """Launch K1.  ``mean`` (n_ctrl,H,7) or (H,7); ``noise`` logical shape (K,H,7) with any
+        strides.  Outputs use the particle-minor layout (H,[7,]K) viewed as (K,H[,7])."""
+        K, H = int(num_particles), int(horizon)
+        n_ctrl = self._state.shape[0]
+        if K % self.n_workers != 0:
+            raise AssertionError("Number of particles must be divisible by number of cpus")
+        mean = mean.reshape(-1, H, 7)
+        if mean.shape[0] != n_ctrl:
+            raise ValueError("mean has %d controller rows but %d states are set" % (mean.shape[0], n_ctrl))
+        if not mean.is_contiguous():
+            mean = mean.contiguous()
+        dev = self.device
+        if costs is None:
+            costs = torch.empty((H, K), dtype=torch.float64, device=dev).t()
+        if actions is None:
+            actions = torch.empty((H, 7, K), dtype=torch.float64, device=dev).permute(2, 0, 1)
+        a = _lib.RolloutArgs()
+        a.K, a.H = K, H
+        a.particles_per_ctrl = K // n_ctrl
+        a.particles_per_model = K // self.n_workers
+        a.state = self._state.data_ptr()
+        a.mean = mean.data_ptr()
+        if noise is not None:
+            if tuple(noise.shape) != (K, H, 7):
+                raise ValueError("noise must have shape (K,H,7)")
+            a.noise = noise.data_ptr()
+            a.noise_sk, a.noise_st, a.noise_sj = noise.stride()
+        a.costs = costs.data_ptr()
+        a.costs_sk, a.costs_st = costs.stride()
+        a.actions = actions.data_ptr()
+        a.act_sk, a.act_st, a.act_sj = actions.stride()
+        out = dict(costs=costs, actions=actions)
+        if want_traj:
+            out["qv"] = torch.empty((K, H, 14), dtype=torch.float64, device=dev)
+            a.qv_traj = out["qv"].data_ptr()
+        if want_obs:
+            out["next_observations"] = torch.empty((K, H, _lib.OBS_DIM), dtype=torch.float64, device=dev)
+            a.next_obs = out["next_observations"].data_ptr()
+        if want_ncon:
+            out["ncon"] = torch.empty((K,), dtype=torch.int32, device=dev)
+            a.ncon = out["ncon"].data_ptr()
+        _lib.check(_lib.lib().mjb_rollout_reacher(self.model.handle, C.byref(a), _lib.stream_ptr()))
+        return out
+
+    def _to_device(self, x):
+        if x is None or isinstance(x, torch.Tensor):
+            return x
+        return torch.from_numpy(np.ascontiguousarray(x, np.float64)).to(self.device)
+
+    def rollout(self, num_particles, horizon, mean, noise, mode="open_loop"):
+        """Reference signature and return value (subproc_vec_env.py:128-135, :170-186): numpy
+        ``(obs, rew, act, done, info, next_obs)``.  ``obs[:, t]`` is the observation before
+        step t, ``rew = -cost``."""
+        if mode != "open_loop":
+            raise NotImplementedError("only mode='open_loop' runs on the GPU rollout")
+        start_t = time.time()
+        out = self.rollout_device(num_particles, horizon, self._to_device(mean), self._to_device(noise),
+                                  want_obs=True)
+        nobs = out["next_observations"].cpu().numpy()
+        rew = -out["costs"].cpu().numpy()
+        act = np.ascontiguousarray(out["actions"].cpu().numpy())
+        K, H = rew.shape
+        obs = np.empty_like(nobs)
+        obs[:, 1:] = nobs[:, :-1]
+        obs[:, 0] = self._first_obs(K)
+        done = np.zeros((K, H))
+        info = [{"total_time": time.time() - start_t}] * self.n_workers
+        return obs, np.ascontiguousarray(rew), act, done, info, nobs
+
+    def _first_obs(self, K):
+        # observation at the set state: forward kinematics on the host (FK only, no dynamics)
+        from .model import _rot_axis
+        st = self._state.cpu().numpy()
+        rows = []
+        tree = self.compiled.tree
+        for s in st:
+            q = s[:7]
+            R = np.eye(3); p = np.zeros(3); j = 0
+            dof = {int(b): k for k, b in enumerate(tree.jnt_body)}
+            Rs, ps = {}, {}
+            for b in range(tree.nb):
+                pa = int(tree.parent[b])
+                Rp = np.eye(3) if pa < 0 else Rs[pa]
+                pp = np.zeros(3) if pa < 0 else ps[pa]
+                ps[b] = pp + Rp @ tree.pos[b]
+                Rs[b] = Rp @ _rot_axis(tree.jnt_axis[dof[b]], q[dof[b]]) if b in dof else Rp
+            hand = ps[tree.hand_body] + Rs[tree.hand_body] @ tree.hand_pos
+            rows.append(np.concatenate([s[:14], hand, hand - s[14:17]]))
+        rows = np.stack(rows)
+        return np.repeat(rows, K // rows.shape[0], axis=0)
+
+    @property
+    def rollout_fn(self):
+        """The closure of examples/example_mpc.py:112-133: (K, H, mean, noise, mode) -> dict."""
+        def fn(num_particles, horizon, mean, noise, mode="open_loop"):
+            if mode != "open_loop":
+                raise NotImplementedError("only mode='open_loop' runs on the GPU rollout")
+            host = not isinstance(noise, torch.Tensor) and not isinstance(mean, torch.Tensor)
+            out = self.rollout_device(num_particles, horizon, self._to_device(mean), self._to_device(noise),
+                                      want_obs=self.return_observations or host)
+            if not host:
+                return out
+            # unmodified reference controllers: numpy in, numpy out, reference dict keys
+            nobs = out["next_observations"].cpu().numpy()
+            K = nobs.shape[0]
+            obs = np.empty_like(nobs)
+            obs[:, 1:] = nobs[:, :-1]
+            obs[:, 0] = self._first_obs(K)
+            return dict(observations=obs, actions=np.ascontiguousarray(out["actions"].cpu().numpy()),
+                        costs=np.ascontiguousarray(out["costs"].cpu().numpy()), dones=np.zeros(nobs.shape[:2]),
+                        next_observations=nobs, infos={})
+        return fn

@@ -1,0 +1,42 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def compiled_model():
+    from mjmpc_b200.envs.model import compile_model, reacher7dof_spec
+    return compile_model(reacher7dof_spec())
+
+
+@pytest.fixture(scope="session")
+def oracle_model(compiled_model):
+    from oracle import mjstep
+    return mjstep.OracleModel(compiled_model.tree)
+
+
+def reference_noise(K, H, d, seed, cov=1.0, filt=(0.25, 0.8, 0.0)):
+    """The reference's generate_noise (control_utils.py:24-34) for a scalar diagonal cov --
+    restated in oracle/control_np.py; used to feed identical noise to both sides."""
+    from oracle import control_np
+    return control_np.generate_noise(np.diag([cov] * d), filt, (K, H), seed)
+
+
+def synthetic_state(compiled_model, seed=0):
+    """SURVEY 8(d) synthetic start state: joints inside 10%..90% of their range, qvel~N(0,.5^2)."""
+    rng = np.random.default_rng(seed)
+    lo, hi = compiled_model.tree.jnt_range[:, 0], compiled_model.tree.jnt_range[:, 1]
+    qp = rng.uniform(lo + 0.1 * (hi - lo), hi - 0.1 * (hi - lo))
+    qv = rng.normal(0, 0.5, 7)
+    tgt = rng.uniform([-.3, -.2, -.25], [.3, .2, .25])
+    return dict(qp=qp, qv=qv, qa=np.zeros(7), target_pos=tgt, timestep=0)
