@@ -22,7 +22,7 @@ extern "C" {
 #define MJB_ECUDA 2    /* CUDA runtime failure */
 #define MJB_ENOTIMPL 3 /* unsupported option (maps to NotImplementedError) */
 
-#define MJB_MODEL_NPARAM 166 /* doubles per model instance, layout in mjmpc_b200/csrc/chain_model.h */
+#define MJB_MODEL_NPARAM 167 /* doubles per model instance, layout in mjmpc_b200/csrc/chain_model.h */
 #define MJB_STATE_DIM 17     /* qpos(7) qvel(7) target_pos(3) */
 #define MJB_OBS_DIM 20       /* reacher_env.py:41-47: qpos, qvel, hand, hand-target */
 

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmjmpc_b200.so")
 
 MJB_OK, MJB_EINVAL, MJB_ECUDA, MJB_ENOTIMPL = 0, 1, 2, 3
-MODEL_NPARAM = 166
+MODEL_NPARAM = 167
 STATE_DIM = 17
 OBS_DIM = 20
 

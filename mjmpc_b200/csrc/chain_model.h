@@ -19,12 +19,12 @@ enum {
     CH_RANGE_HI = CH_RANGE_LO + 7, // 7
     CH_INVW0 = CH_RANGE_HI + 7,    // 7    dof_invweight0
     CH_SCALARS = CH_INVW0 + 7,     // 20 scalars, see below
-    CH_NPARAM = CH_SCALARS + 20,   // host block ends here (166)
+    CH_NPARAM = CH_SCALARS + 20,   // host block ends here (167)
     // derived on upload (mjb_model_create): first moment h = m*com and inertia about the link origin
     CH_H = CH_NPARAM,              // 7*3
     CH_IO = CH_H + 21,             // 7*6 (xx,yy,zz,xy,xz,yz)
     CH_HDAMP = CH_IO + 42,         // 7    timestep * damping
-    CH_NDEV = CH_HDAMP + 7         // 236
+    CH_NDEV = CH_HDAMP + 7         // 237
 };
 
 enum {

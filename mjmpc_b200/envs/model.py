@@ -245,7 +245,7 @@ CH_SCALARS = CH_INVW0 + 7       # see below
 #   +11 con sphere x, +12 y, +13 z (last link frame), +14 radius (<0: none)
 #   +15 plane z, +16 margin, +17 contact invweight
 #   +18 limited mask (bit j set = joint j limited), +19 frame_skip
-CH_NPARAM = CH_SCALARS + 20     # = 166
+CH_NPARAM = CH_SCALARS + 20     # = 167
 
 
 @dataclass

@@ -29,19 +29,19 @@ static void run(const double* P, const double* qpos, const double* qvel, const d
     (void)iters;
 }
 
-extern "C" void hostcheck_rollout(const double* P166, int dense, const double* qpos, const double* qvel,
+extern "C" void hostcheck_rollout(const double* P167, int dense, const double* qpos, const double* qvel,
                                   const double* target, int K, int H, const double* mean, const double* noise,
                                   double* costs, double* qv) {
     double P[CH_NDEV];
-    for (int i = 0; i < CH_NPARAM; i++) P[i] = P166[i];
+    for (int i = 0; i < CH_NPARAM; i++) P[i] = P167[i];
     mjb_derive_params(P);
     if (dense) run<DenseTraits>(P, qpos, qvel, target, K, H, mean, noise, costs, qv, nullptr);
     else run<SawyerTraits>(P, qpos, qvel, target, K, H, mean, noise, costs, qv, nullptr);
 }
-extern "C" int hostcheck_fits_sawyer(const double* P166) { return mjb_params_fit_sawyer(P166); }
-extern "C" void hostcheck_mass_bias(const double* P166, const double* q, const double* v, double* M, double* bias) {
+extern "C" int hostcheck_fits_sawyer(const double* P167) { return mjb_params_fit_sawyer(P167); }
+extern "C" void hostcheck_mass_bias(const double* P167, const double* q, const double* v, double* M, double* bias) {
     double P[CH_NDEV];
-    for (int i = 0; i < CH_NPARAM; i++) P[i] = P166[i];
+    for (int i = 0; i < CH_NPARAM; i++) P[i] = P167[i];
     mjb_derive_params(P);
     PtrParams prm{P};
     double sn[7], cs[7], qd[7], Mm[7][7], b[7];
