@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Headline benchmark: MPPI on reacher_7dof, K=65536 particles (global), H=32, n_iters=1
+(BASELINE.json configs[2]); a "step" is one MPC iteration = noise + rollout + update + shift.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Own arm prints one JSON line with
+  value        particle-steps/s, device-timed (CUDA events), state resident in HBM, no host sync
+  e2e          the same metric through MPCPolicy.get_action(state_dict): host state in (pinned H2D),
+               host action out (D2H) every step
+  mpc_hz       1 / time of one e2e get_action call
+  roofline     rollout kernel (K1) against the FP64 FMA peak measured live by mjb_fp64_peak
+  cpu_baseline the CPU oracle (C restatement of the reference rollout + numpy controller math) on all
+               host cores, bounded sample of the same workload
+`--impl reference` times that CPU path alone (the reference's own path is Python + mujoco_py, which
+cannot run here: no MuJoCo).  For N > 1 launch with torchrun; particles are sharded K/N per rank.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_GLOBAL, HORIZON, D_ACTION = 65536, 32, 7
+FLOP_PER_PARTICLE_STEP = 5340.0          # BASELINE.md section 4 / SURVEY 8(d): the contract figure
+MPPI_PARAMS = dict(horizon=HORIZON, init_cov=1.0, filter_coeffs=[0.25, 0.8, 0.0], gamma=1.0, n_iters=1,
+                   step_size=1.0, lam=0.2, alpha=1, base_action='null')     # reacher_7dof-v0.yml:20-30 + :5
+KERNELS_PER_STEP = 9     # noise, rollout, softmax {prep, traj_cost, weighted_reduce, decode_min, chunk_sum}, combine, shift
+
+
+def synthetic_states(compiled, n, seed=0):
+    """joints inside 10%..90% of their range, qvel ~ N(0,.5^2), random target."""
+    rng = np.random.default_rng(seed)
+    lo, hi = compiled.tree.jnt_range[:, 0], compiled.tree.jnt_range[:, 1]
+    out = []
+    for _ in range(n):
+        out.append(dict(qp=rng.uniform(lo + 0.1 * (hi - lo), hi - 0.1 * (hi - lo)), qv=rng.normal(0, .5, 7),
+                        qa=np.zeros(7), target_pos=rng.uniform([-.3, -.2, -.25], [.3, .2, .25]), timestep=0))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline: oracle rollout (C, all cores, contiguous particle blocks like SubprocVecEnv) + numpy
+# controller math restated from the reference.  One call = one MPC iteration on K_sample particles.
+# --------------------------------------------------------------------------------------------------
+class CpuBaseline:
+    def __init__(self, k_sample):
+        from mjmpc_b200.envs.model import compile_model, reacher7dof_spec
+        from oracle import control_np, mjstep
+        self.np_ctrl, self.mjstep = control_np, mjstep
+        self.compiled = compile_model(reacher7dof_spec())
+        self.om = mjstep.OracleModel(self.compiled.tree)
+        self.cores = os.cpu_count() or 1
+        self.K = k_sample
+        self.mean = np.zeros((HORIZON, D_ACTION))
+        self.cov = np.diag([MPPI_PARAMS["init_cov"]] * D_ACTION)
+        self.gseq = control_np.gamma_seq(MPPI_PARAMS["gamma"], HORIZON)
+        self.num_steps = 0
+        self.states = synthetic_states(self.compiled, 16, seed=0)
+
+    def step(self):
+        st = self.states[self.num_steps % len(self.states)]
+        noise = self.np_ctrl.generate_noise(self.cov, MPPI_PARAMS["filter_coeffs"], (self.K, HORIZON), 123 + self.num_steps)
+        out = self.mjstep.rollout(self.om, st["qp"], st["qv"], st["target_pos"], self.mean, noise, nthreads=self.cores)
+        self.mean, _ = self.np_ctrl.mppi_update(self.mean, self.cov, out["costs"], out["actions"], self.gseq,
+                                                MPPI_PARAMS["lam"], MPPI_PARAMS["alpha"], MPPI_PARAMS["step_size"])
+        action = self.mean[0].copy()
+        self.mean = self.np_ctrl.shift_mean(self.mean, 'null')
+        self.num_steps += 1
+        return action
+
+    def measure(self, steps, warmup):
+        for _ in range(warmup):
+            self.step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step()
+        dt = time.perf_counter() - t0
+        return self.K * HORIZON * steps / dt, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    k_sample = 2048
+    cb = CpuBaseline(k_sample)
+    value, s_per_step = cb.measure(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "particle_steps_per_s", "value": value, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "mpc_hz_at_full_K": value / (K_GLOBAL * HORIZON),
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cb.cores, "kind": "port",
+                         "sample": "%d of %d particles x H=%d per MPC iteration (numpy generate_noise + C oracle "
+                                   "rollout on %d threads + numpy MPPI update); mujoco_py itself cannot run here"
+                                   % (k_sample, K_GLOBAL, HORIZON, cb.cores)},
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "MPPI reacher_7dof-v0 K=65536 H=32 n_iters=1 (BASELINE.json configs[2])",
+            "num_particles": K_GLOBAL, "horizon": HORIZON, "d_action": D_ACTION,
+            "particles_per_gpu": K_GLOBAL // n_gpus, "sharding": "particles, contiguous blocks, %d rank(s)" % n_gpus,
+            "noise": "in-kernel Philox4x32-10 + AR filter", "start_states": "synthetic, SURVEY 8(d), new state every step",
+            "l2": "per-step working set (noise+actions+costs = 251 MB at N=1) exceeds the 126 MB L2; no explicit flush"}
+
+
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    from mjmpc_b200 import _lib
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    from mjmpc_b200.envs.model import compile_model, reacher7dof_spec
+    from mjmpc_b200.policies import MPCPolicy
+    from mjmpc_b200.utils.shard import ShardContext
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    shard = ShardContext(rank, world)
+    L = _lib.lib()
+    compiled = compile_model(reacher7dof_spec())
+    env = GpuReacherVecEnv(compiled, device=local_rank)
+    params = dict(MPPI_PARAMS)
+    params.update(d_state=env.d_state, d_obs=env.d_obs, d_action=env.d_action, action_lows=env.action_lows,
+                  action_highs=env.action_highs, num_particles=K_GLOBAL, seed=123, device=local_rank, shard=shard)
+    policy = MPCPolicy("mppi", params)
+    ctrl = policy.controller
+    ctrl.set_sim_state_fn = env.set_env_state
+    ctrl.rollout_fn = env.rollout_fn
+    states = synthetic_states(compiled, 64, seed=0)
+    states_dev = torch.stack([torch.from_numpy(np.concatenate([s["qp"], s["qv"], s["target_pos"]])) for s in states]).cuda()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput (value) -----------------------------------------------------------
+    def device_step(i):
+        env.set_env_state_device(states_dev[i % len(states)][None])
+        return ctrl.step_device(None)
+
+    for i in range(args.warmup):
+        device_step(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        device_step(args.warmup + i)
+    e1.record()
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    value = K_GLOBAL * HORIZON * args.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the public API: host state dict in, host action out ------------------------
+    ctrl.reset()
+    for i in range(args.warmup):
+        policy.get_action(states[i % len(states)])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        action, _ = policy.get_action(states[(args.warmup + i) % len(states)])
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = K_GLOBAL * HORIZON * args.steps / e2e_s
+    mpc_hz = args.steps / e2e_s
+
+    # ---- rollout kernel alone (roofline), CUDA events on the launching stream ---------------------------
+    kl = K_GLOBAL // world
+    noise = ctrl.sample_noise()
+    out = env.rollout_device(kl, HORIZON, ctrl._mean, noise)
+    torch.cuda.synchronize()
+    ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(5, min(args.steps, 20))
+    ks.record()
+    for _ in range(reps):
+        env.rollout_device(kl, HORIZON, ctrl._mean, noise, costs=out["costs"], actions=out["actions"])
+    ke.record()
+    torch.cuda.synchronize()
+    k1_ms = ks.elapsed_time(ke) / reps
+    tf, pms = C.c_double(), C.c_double()
+    _lib.check(L.mjb_fp64_peak(local_rank, 8, 2048, C.byref(tf), C.byref(pms)))
+    achieved = kl * HORIZON * FLOP_PER_PARTICLE_STEP / (k1_ms * 1e-3) / 1e12
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on the host cores (rank 0, N=1 only, bounded sample) --------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = CpuBaseline(2048)
+        v, _ = cb.measure(steps=3, warmup=1)
+        cpu = {"value": v, "unit": "particle-steps/s", "cores": cb.cores, "kind": "port",
+               "sample": "3 MPC iterations of 2048 of %d particles x H=%d: numpy generate_noise + C oracle rollout on %d "
+                         "threads + numpy MPPI update (restatement of the reference path; mujoco_py cannot run here)"
+                         % (K_GLOBAL, HORIZON, cb.cores)}
+    line = {
+        "metric": "particle_steps_per_s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world),
+        "mpc_hz": mpc_hz, "mpc_hz_device_resident": args.steps / (dev_ms * 1e-3),
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "ms_per_step": e2e_s / args.steps * 1e3,
+                "h2d_bytes_per_step": 17 * 8, "d2h_bytes_per_step": 7 * 8,
+                "api": "MPCPolicy.get_action(state_dict) -> (action ndarray, value)"},
+        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "roofline": {"kernel": "rollout_reacher_kernel (K1)", "bound": "fp64", "achieved": achieved, "peak": tf.value,
+                     "unit": "TFLOP/s", "frac": achieved / tf.value, "traffic": None,
+                     "ms_per_launch": k1_ms, "particles_per_launch": kl,
+                     "flop_per_particle_step": FLOP_PER_PARTICLE_STEP,
+                     "peak_source": "mjb_fp64_peak microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)"},
+        "clocks": clocks,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

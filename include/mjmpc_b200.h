@@ -66,6 +66,164 @@ typedef struct {
 } mjb_rollout_args;
 int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a, void* stream);
 
+/* ---- K9 pendulum rollout: replaces PendulumEnv.step (mjmpc/envs/basic/pendulum.py:33-50) under
+ * GymEnvWrapper.rollout.  state: (n_ctrl, 2) theta, thetadot; mean (n_ctrl, H, 1); d_action = 1.
+ * states_out (K,H,2) row-major or NULL. */
+typedef struct {
+    int K, H, particles_per_ctrl;
+    const double* state;
+    const double* mean;
+    const double* noise; long long noise_sk, noise_st;
+    double* costs; long long costs_sk, costs_st;
+    double* actions; long long act_sk, act_st;
+    double* states_out;
+} mjb_pendulum_args;
+int mjb_rollout_pendulum(const mjb_pendulum_args* a, void* stream);
+
+/* ---- K2 noise: replaces generate_noise (mjmpc/utils/control_utils.py:24-34) and the
+ * use_zero_control_seq overwrite (mjmpc/control/olgaussian_mpc.py:110-111).  Philox4x32-10 keyed by
+ * `seed`, counters (k_offset + k, low32(offset), t, high32(offset) << 8 | pair): results do not
+ * depend on how particles are sharded.  All pointers are device pointers. */
+typedef struct {
+    int K, H, d;
+    long long k_offset;          /* global index of this shard's first particle */
+    long long K_global;          /* total particles over all shards (zero_last targets K_global-1) */
+    unsigned long long seed;     /* controller seed_val */
+    unsigned long long offset;   /* low 32 bits: num_steps-like counter; high 32 bits: stream id */
+    const double* cov;           /* (d,d) covariance, Cholesky-factorised inside the kernel */
+    double beta0, beta1, beta2;  /* filter_coeffs */
+    int zero_last;               /* 1: particle K_global-1 gets noise = -mean (zero control sequence) */
+    const double* neg_mean;      /* (H,d) mean sequence, needed when zero_last */
+    double* out;                 /* (K,H,d) by strides */
+    long long out_sk, out_st, out_sj;
+} mjb_noise_args;
+int mjb_generate_noise(const mjb_noise_args* a, void* stream);
+
+/* ---- K3 cost-to-go: replaces cost_to_go (mjmpc/utils/control_utils.py:37-46), bit-exact:
+ * x_t = gamma_t*c_t, reverse sequential sum, divide by gamma_t; returns costs unchanged if any
+ * gamma_t == 0.  gamma_seq is a HOST pointer (H,). */
+int mjb_cost_to_go(const double* costs, long long sk, long long st, const double* gamma_seq_host, int K, int H,
+                   double* out, long long out_sk, long long out_st, void* stream);
+
+/* ---- K4/K6 exponential-utility reductions: MPPI._update_distribution/_exp_util/_control_costs
+ * (mjmpc/control/mppi.py:69-111), DMDMPC._update_distribution/_exp_util
+ * (mjmpc/control/gaussian_dmd.py:65-104), PFMPC._exp_util (particle_filter_controller.py:104-113).
+ * Phase 1 reduces this GPU's particles to a partial vector
+ *     [ m[T] | acc[H][NACC] ],  T = time_based ? H : 1,  NACC = 1 + d + ncov,
+ *     acc[t] = ( sum_k w, sum_k w a[k,t,0..d), sum_k w delta delta' (diag: d, full: d(d+1)/2) ),
+ *     w = exp(-(total_k - m)/lam), m = min_k total_k
+ * phase 2 combines the partial vectors of all shards (rank order, deterministic) and writes the
+ * smoothed mean / covariance.  With one GPU, n_shards = 1. */
+#define MJB_COV_NONE 0
+#define MJB_COV_DIAG 1
+#define MJB_COV_FULL 2
+typedef struct {
+    int K, H, d;
+    const double* costs; long long costs_sk, costs_st;
+    const double* actions; long long act_sk, act_st, act_sj;
+    const double* mean;          /* (H,d) device */
+    const double* cov;           /* (d,d) device; only read when control_cost */
+    const double* gamma_seq;     /* (H,) HOST */
+    double lam;
+    int control_cost;            /* MPPI alpha == 0 */
+    int time_based;              /* MPPI time_based_weights */
+    int cov_mode;                /* MJB_COV_* (DMD update_cov) */
+    double* total;               /* (T,K) out: trajectory cost the weights are computed from */
+    double* scratch;             /* >= mjb_softmax_scratch_doubles(K,H,d,cov_mode) */
+    double* partials;            /* out: mjb_softmax_partial_doubles(H,d,time_based,cov_mode) */
+} mjb_softmax_args;
+long long mjb_softmax_scratch_doubles(int K, int H, int d, int cov_mode);
+int mjb_softmax_partial_doubles(int H, int d, int time_based, int cov_mode);
+int mjb_softmax_partials(const mjb_softmax_args* a, void* stream);
+
+typedef struct {
+    int H, d, n_shards;
+    long long K_global;
+    const double* partials;      /* (n_shards, P) device, rank order */
+    double lam, step_size;
+    int time_based, cov_mode;
+    double* mean;                /* (H,d) in/out: (1-step)*mean + step*sum_k w a; NULL = statistics only */
+    double* cov;                 /* (d,d) in/out when cov_mode != NONE, else may be NULL */
+    double* stats;               /* out (2+2T): [0] = -lam*logsumexp(-total/lam, b=1/K) (the _calc_val value,
+                                    mppi.py:113-131, gaussian_dmd.py:126-139), [1] = global min m[0],
+                                    [2..2+T) = normaliser S[t] w.r.t. the global min, [2+T..2+2T) = global min m[t] */
+} mjb_combine_args;
+int mjb_softmax_combine(const mjb_combine_args* a, void* stream);
+/* normalised weights w_k = exp(-(total_k - m)/lam)/S for one t-row of `total`; m,S from stats. */
+int mjb_softmax_weights(const double* total, int K, const double* stats, int t, double lam, double* w_out,
+                        void* stream);
+
+/* ---- K5 elite selection + moments: CEM._update_distribution (mjmpc/control/cem.py:65-86) and
+ * RandomShooting._update_distribution (mjmpc/control/random_shooting.py:52-62).
+ * mjb_select_elites: the num_elite smallest keys of ctg0 (K_global,), ties broken by LOWER index
+ * (np.argsort's tie order is unspecified; this is the contract SURVEY 7-H4 fixes).  Writes
+ * flags (K_global,) uint8, and ids (num_elite,) int64 ascending by index (NULL ok). */
+int mjb_select_elites(const double* ctg0, long long K_global, long long num_elite, unsigned char* flags,
+                      long long* ids, void* scratch /* >= 4096 bytes */, void* stream);
+/* first index of the minimum of ctg0 (np.argmin): out_index (1,) int64 device */
+int mjb_argmin(const double* ctg0, long long K, long long* out_index, double* out_value, void* stream);
+/* Elite moments of this shard: partial = [ n | sum_a (H,d) | sum_delta (d) ]  (pass 1)
+ * and [ sum (delta-mu)(delta-mu)' lower-triangular d(d+1)/2 ] (pass 2, mu = pooled mean of delta
+ * over all shards, device pointer (d,)). */
+typedef struct {
+    int K, H, d;
+    const unsigned char* flags;  /* (K,) elite flags of THIS shard's particles */
+    const double* actions; long long act_sk, act_st, act_sj;
+    const double* mean;          /* (H,d) */
+    const double* mu;            /* (d,) pooled mean of elite deltas (pass 2 only) */
+    double* scratch;             /* >= mjb_elite_scratch_doubles(K,H,d) */
+    double* partial;             /* out */
+} mjb_elite_args;
+long long mjb_elite_scratch_doubles(int K, int H, int d);
+int mjb_elite_moments1(const mjb_elite_args* a, void* stream);
+int mjb_elite_moments2(const mjb_elite_args* a, void* stream);
+typedef struct {
+    int H, d, n_shards, full_cov;          /* full_cov: 1 = np.cov (ddof 1), 0 = diag(np.var) (ddof 0) */
+    const double* partial1;      /* (n_shards, 1 + H*d + d) */
+    const double* partial2;      /* (n_shards, d(d+1)/2) or NULL when only the pooled mean is wanted */
+    double step_size;
+    double* mu;                  /* out (d,): pooled mean of elite deltas */
+    double* mean;                /* (H,d) in/out (only touched when partial2 != NULL) */
+    double* cov;                 /* (d,d) in/out (only touched when partial2 != NULL) */
+} mjb_elite_combine_args;
+int mjb_elite_combine(const mjb_elite_combine_args* a, void* stream);
+/* mean <- (1-step)*mean + step*actions[best] (random_shooting.py:61-62); best_index device (1,) */
+int mjb_blend_best(const double* actions, long long sk, long long st, long long sj, const long long* best_index,
+                   long long k_offset, int K, int H, int d, double step_size, double* mean, void* stream);
+
+/* ---- K7 systematic resampling: PFMPC._resampling (particle_filter_controller.py:159-174).
+ * Sequential FP64 prefix sum c_i (the reference's accumulation order, so indices are bit-exact),
+ * idx[m] = first i with c_i >= r + m/M (clamped to M-1).  r = random.uniform(0, 1/M) from the host. */
+int mjb_resample_indices(const double* weights, long long M, double r, double* cumsum_scratch /* (M,) */,
+                         long long* idx_out, void* stream);
+/* out[m] = in[idx[m]] for (K,H,d) tensors by strides */
+int mjb_gather_particles(const double* in, long long in_sk, long long in_st, long long in_sj, const long long* idx,
+                         int K, int H, int d, double* out, long long out_sk, long long out_st, long long out_sj,
+                         void* stream);
+/* mean over particles: out (H,d) = mean_k x[k] (PFMPC mean_action, particle_filter_controller.py:102,124) */
+int mjb_particle_mean(const double* x, long long sk, long long st, long long sj, int K, int H, int d,
+                      double* scratch, double* out, void* stream);
+
+/* out = x - mean[None]: the deviation PFMPC.generate_rollouts hands to rollout_fn
+ * (particle_filter_controller.py:87) */
+int mjb_particle_sub_mean(const double* x, long long sk, long long st, long long sj, const double* mean, int K, int H,
+                          int d, double* out, long long out_sk, long long out_st, long long out_sj, void* stream);
+
+/* ---- K8 shift: OLGaussianMPC._shift (mjmpc/control/olgaussian_mpc.py:116-129), CEM._shift
+ * (cem.py:89-95), DMDMPC._shift (gaussian_dmd.py:106-113), PFMPC._shift
+ * (particle_filter_controller.py:127-150). */
+#define MJB_BASE_NULL 0
+#define MJB_BASE_REPEAT 1
+#define MJB_BASE_RANDOM 2
+/* mean[:-1] = mean[1:]; last row per base_action; `random_row` (d,) device, used for MJB_BASE_RANDOM */
+int mjb_shift_mean(double* mean, int H, int d, int base_action, const double* random_row, void* stream);
+/* cov += beta * diag(v)   (v (d,) device, or NULL for the identity) */
+int mjb_cov_add_diag(double* cov, int d, double beta, const double* v, void* stream);
+/* samples[:, :-1] = samples[:, 1:]; samples += delta; last column per base_action */
+int mjb_pf_shift(double* samples, long long sk, long long st, long long sj, const double* delta, long long dk,
+                 long long dt, long long dj, int K, int H, int d, int base_action, const double* random_row,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

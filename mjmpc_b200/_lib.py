@@ -50,6 +50,7 @@ def lib():
         L.mjb_last_error.restype = C.c_char_p
         for name in EXPORTS:
             getattr(L, name)        # AttributeError if the build is stale
+        _setup_restypes(L)
         _lib = L
     return _lib
 
@@ -81,3 +82,82 @@ def ptr(t):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---- argument structs of include/mjmpc_b200.h ---------------------------------------------------
+class PendulumArgs(C.Structure):
+    _fields_ = [
+        ("K", C.c_int), ("H", C.c_int), ("particles_per_ctrl", C.c_int),
+        ("state", C.c_void_p), ("mean", C.c_void_p),
+        ("noise", C.c_void_p), ("noise_sk", c_ll), ("noise_st", c_ll),
+        ("costs", C.c_void_p), ("costs_sk", c_ll), ("costs_st", c_ll),
+        ("actions", C.c_void_p), ("act_sk", c_ll), ("act_st", c_ll),
+        ("states_out", C.c_void_p),
+    ]
+
+
+class NoiseArgs(C.Structure):
+    _fields_ = [
+        ("K", C.c_int), ("H", C.c_int), ("d", C.c_int),
+        ("k_offset", c_ll), ("K_global", c_ll),
+        ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
+        ("cov", C.c_void_p), ("beta0", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
+        ("zero_last", C.c_int), ("neg_mean", C.c_void_p),
+        ("out", C.c_void_p), ("out_sk", c_ll), ("out_st", c_ll), ("out_sj", c_ll),
+    ]
+
+
+class SoftmaxArgs(C.Structure):
+    _fields_ = [
+        ("K", C.c_int), ("H", C.c_int), ("d", C.c_int),
+        ("costs", C.c_void_p), ("costs_sk", c_ll), ("costs_st", c_ll),
+        ("actions", C.c_void_p), ("act_sk", c_ll), ("act_st", c_ll), ("act_sj", c_ll),
+        ("mean", C.c_void_p), ("cov", C.c_void_p), ("gamma_seq", C.c_void_p),
+        ("lam", C.c_double), ("control_cost", C.c_int), ("time_based", C.c_int), ("cov_mode", C.c_int),
+        ("total", C.c_void_p), ("scratch", C.c_void_p), ("partials", C.c_void_p),
+    ]
+
+
+class CombineArgs(C.Structure):
+    _fields_ = [
+        ("H", C.c_int), ("d", C.c_int), ("n_shards", C.c_int), ("K_global", c_ll),
+        ("partials", C.c_void_p), ("lam", C.c_double), ("step_size", C.c_double),
+        ("time_based", C.c_int), ("cov_mode", C.c_int),
+        ("mean", C.c_void_p), ("cov", C.c_void_p), ("stats", C.c_void_p),
+    ]
+
+
+class EliteArgs(C.Structure):
+    _fields_ = [
+        ("K", C.c_int), ("H", C.c_int), ("d", C.c_int),
+        ("flags", C.c_void_p),
+        ("actions", C.c_void_p), ("act_sk", c_ll), ("act_st", c_ll), ("act_sj", c_ll),
+        ("mean", C.c_void_p), ("mu", C.c_void_p), ("scratch", C.c_void_p), ("partial", C.c_void_p),
+    ]
+
+
+class EliteCombineArgs(C.Structure):
+    _fields_ = [
+        ("H", C.c_int), ("d", C.c_int), ("n_shards", C.c_int), ("full_cov", C.c_int),
+        ("partial1", C.c_void_p), ("partial2", C.c_void_p), ("step_size", C.c_double),
+        ("mu", C.c_void_p), ("mean", C.c_void_p), ("cov", C.c_void_p),
+    ]
+
+
+COV_NONE, COV_DIAG, COV_FULL = 0, 1, 2
+BASE_ACTIONS = {"null": 0, "repeat": 1, "random": 2}
+
+EXPORTS += [
+    "mjb_rollout_pendulum", "mjb_generate_noise", "mjb_cost_to_go",
+    "mjb_softmax_scratch_doubles", "mjb_softmax_partial_doubles", "mjb_softmax_partials",
+    "mjb_softmax_combine", "mjb_softmax_weights",
+    "mjb_select_elites", "mjb_argmin", "mjb_elite_scratch_doubles", "mjb_elite_moments1",
+    "mjb_elite_moments2", "mjb_elite_combine", "mjb_blend_best",
+    "mjb_resample_indices", "mjb_gather_particles", "mjb_particle_mean", "mjb_particle_sub_mean",
+    "mjb_shift_mean", "mjb_cov_add_diag", "mjb_pf_shift",
+]
+
+
+def _setup_restypes(L):
+    L.mjb_softmax_scratch_doubles.restype = c_ll
+    L.mjb_elite_scratch_doubles.restype = c_ll

@@ -1,0 +1,183 @@
+"""Base class for controllers -- same surface as the reference's ``Controller``
+(``mjmpc/control/controller.py:13-279``): constructor arguments, ``optimize`` control flow
+(:207-257), ``get_optimal_value`` (:259-275), the ``rollout_fn`` / ``set_sim_state_fn``
+injection points (:152-175) and ``seed`` (:277-279).  Distribution parameters live in HBM as
+FP64 tensors; ``mean_action`` / ``cov_action`` read them back as numpy arrays like the
+reference's attributes.
+"""
+from __future__ import annotations
+
+import copy
+import os
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..utils.shard import ShardContext
+
+
+class Controller(ABC):
+    def __init__(self,
+                 d_state,
+                 d_obs,
+                 d_action,
+                 action_lows,
+                 action_highs,
+                 horizon,
+                 gamma,
+                 n_iters,
+                 set_sim_state_fn=None,
+                 rollout_fn=None,
+                 sample_mode='mean',
+                 batch_size=1,
+                 seed=0,
+                 device=None,
+                 shard=None):
+        """Parameters as in the reference (controller.py:28-63) plus
+        device : torch.device or int, the GPU this controller lives on (default: current)
+        shard  : ShardContext, this process's slice of the particles (default: all of them)
+        """
+        if not torch.cuda.is_available():
+            raise _lib.MjbError("mjmpc_b200 controllers need a CUDA device (there is no CPU fallback)")
+        _lib.lib()
+        self.d_state = d_state
+        self.d_obs = d_obs
+        self.d_action = int(d_action)
+        self.action_lows = action_lows
+        self.action_highs = action_highs
+        self.horizon = int(horizon)
+        self.gamma = gamma
+        self.gamma_seq = np.cumprod([1.0] + [self.gamma] * (self.horizon - 1)).reshape(1, self.horizon)
+        self.n_iters = n_iters
+        self._set_sim_state_fn = set_sim_state_fn
+        self._rollout_fn = rollout_fn
+        self.sample_mode = sample_mode
+        self.batch_size = batch_size
+        self.num_steps = 0
+        self.seed_val = self.seed(seed)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.shard = shard if shard is not None else ShardContext()
+
+    # ---- abstract surface (controller.py:80-143,203-205) -----------------------------------
+    @abstractmethod
+    def _get_next_action(self, state, mode='mean'):
+        pass
+
+    def sample_actions(self):
+        raise NotImplementedError('sample_actions funtion not implemented')
+
+    @abstractmethod
+    def _update_distribution(self, trajectories):
+        pass
+
+    @abstractmethod
+    def _shift(self):
+        pass
+
+    @abstractmethod
+    def reset(self):
+        pass
+
+    @abstractmethod
+    def _calc_val(self, trajectories):
+        pass
+
+    @abstractmethod
+    def generate_rollouts(self, state):
+        pass
+
+    def check_convergence(self):
+        """Returns False by default (controller.py:145-150)."""
+        return False
+
+    # ---- injection points (controller.py:152-175) --------------------------------------------
+    @property
+    def set_sim_state_fn(self):
+        return self._set_sim_state_fn
+
+    @set_sim_state_fn.setter
+    def set_sim_state_fn(self, fn):
+        self._set_sim_state_fn = fn
+
+    @property
+    def rollout_fn(self):
+        return self._rollout_fn
+
+    @rollout_fn.setter
+    def rollout_fn(self, fn):
+        self._rollout_fn = fn
+
+    # ---- the MPC step (controller.py:207-257) ------------------------------------------------
+    def optimize(self, state, calc_val=False, hotstart=True):
+        for _ in range(self.n_iters):
+            trajectory = self.generate_rollouts(copy.deepcopy(state))
+            self._update_distribution(trajectory)
+            if self.check_convergence():
+                break
+        curr_action = self._get_next_action(state, mode=self.sample_mode)
+        value = 0.0
+        if calc_val:
+            trajectories = self.generate_rollouts(copy.deepcopy(state))
+            value = self._calc_val(trajectories)
+        self.num_steps += 1
+        if hotstart:
+            self._shift()
+        return curr_action, value
+
+    def step_device(self, state=None, hotstart=True):
+        """One MPC step with no host round trip: same sequence as :meth:`optimize` but the action stays
+        on the device (returned as a (d_action,) tensor) and nothing synchronises.  ``state=None`` keeps
+        the state the rollout backend already holds in HBM.  For pipelines whose plant is on the GPU too;
+        not part of the reference API."""
+        for _ in range(self.n_iters):
+            trajectory = self.generate_rollouts(state)
+            self._update_distribution(trajectory)
+        action = self._mean[0].clone()
+        self.num_steps += 1
+        if hotstart:
+            self._shift()
+        return action
+
+    def get_optimal_value(self, state):
+        """controller.py:259-275."""
+        self.reset()
+        _, value = self.optimize(state, calc_val=True, hotstart=False)
+        return value
+
+    def seed(self, seed=None):
+        """controller.py:277-279 (gym.utils.seeding.np_random: RandomState + the integer seed)."""
+        if seed is None:
+            seed = int.from_bytes(os.urandom(4), "little")
+        self.np_random = np.random.RandomState(int(seed) % (2 ** 32))
+        return seed
+
+    def set_params(self, **params):
+        """Update constructor-level parameters in place (not in the reference, which rebuilds the
+        controller per episode -- examples/example_mpc.py:152-153).  Shape-changing parameters
+        (horizon, num_particles) reset the distribution."""
+        reshape = False
+        for k, v in params.items():
+            if not hasattr(self, k):
+                raise ValueError("unknown controller parameter %r" % k)
+            if k in ("horizon", "num_particles", "d_action") and getattr(self, k) != v:
+                reshape = True
+            setattr(self, k, v)
+        if "gamma" in params or "horizon" in params:
+            self.gamma_seq = np.cumprod([1.0] + [self.gamma] * (self.horizon - 1)).reshape(1, self.horizon)
+        if "seed" in params:
+            self.seed_val = self.seed(params["seed"])
+        self._on_params_changed(reshape)
+
+    def _on_params_changed(self, reshape):
+        if reshape:
+            self.reset()
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def _to_device(self, x):
+        if isinstance(x, torch.Tensor):
+            return x.to(device=self.device, dtype=torch.float64)
+        return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=self.device)

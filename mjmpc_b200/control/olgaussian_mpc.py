@@ -1,0 +1,208 @@
+"""MPC with open-loop Gaussian policies -- the reference's ``OLGaussianMPC``
+(``mjmpc/control/olgaussian_mpc.py:10-139``) with its numeric bodies on the GPU: ``sample_noise``
+(:88-93) is the Philox kernel, ``_shift`` (:116-129) a device kernel, and the softmax /
+elite reductions used by the subclasses go through the C ABI.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..utils import control_utils
+from ..utils.control_utils import generate_noise
+from .controller import Controller
+
+
+class OLGaussianMPC(Controller):
+    def __init__(self,
+                 d_state,
+                 d_obs,
+                 d_action,
+                 action_lows,
+                 action_highs,
+                 horizon,
+                 init_cov,
+                 init_mean,
+                 base_action,
+                 num_particles,
+                 gamma,
+                 n_iters,
+                 step_size,
+                 filter_coeffs,
+                 set_sim_state_fn=None,
+                 rollout_fn=None,
+                 cov_type='diagonal',
+                 sample_mode='mean',
+                 batch_size=1,
+                 seed=0,
+                 use_zero_control_seq=False,
+                 device=None,
+                 shard=None):
+        super(OLGaussianMPC, self).__init__(d_state, d_obs, d_action, action_lows, action_highs, horizon,
+                                            gamma, n_iters, set_sim_state_fn, rollout_fn, sample_mode,
+                                            batch_size, seed, device, shard)
+        # reference: np.array([init_cov] * d_action) (olgaussian_mpc.py:58); a length-d sequence (as some
+        # shipped configs give, reacher_7dof-v0.yml:34) is taken as the per-dimension variances.
+        ic = np.asarray(init_cov, dtype=np.float64).reshape(-1)
+        if ic.size == 1:
+            ic = np.array([float(ic[0])] * self.d_action)
+        elif ic.size != self.d_action:
+            raise ValueError("init_cov must be a scalar or have d_action entries")
+        self.init_cov = ic
+        self.init_mean = np.array(init_mean, dtype=np.float64).copy()
+        self.base_action = base_action
+        self.num_particles = int(num_particles)
+        if cov_type == 'diag':          # README spelling (README.md:103); the code tests 'diagonal'
+            cov_type = 'diagonal'
+        self.cov_type = cov_type
+        self.step_size = step_size
+        self.filter_coeffs = filter_coeffs
+        self.use_zero_control_seq = use_zero_control_seq
+        self._mean = self._to_device(self.init_mean).reshape(self.horizon, self.d_action).contiguous()
+        self._cov = self._to_device(np.diag(self.init_cov)).contiguous()
+        self._init_cov_d = self._to_device(self.init_cov)
+        self._buffers = {}
+
+    # ---- numpy views of the distribution (public attributes in the reference) ----------------
+    @property
+    def mean_action(self):
+        return self._mean.cpu().numpy()
+
+    @mean_action.setter
+    def mean_action(self, value):
+        self._mean = self._to_device(value).reshape(self.horizon, self.d_action).contiguous()
+
+    @property
+    def cov_action(self):
+        return self._cov.cpu().numpy()
+
+    @cov_action.setter
+    def cov_action(self, value):
+        self._cov = self._to_device(value).reshape(self.d_action, self.d_action).contiguous()
+
+    # ---- sharding ----------------------------------------------------------------------------------
+    @property
+    def local_particles(self):
+        return self.shard.local_range(self.num_particles)[1]
+
+    def _buf(self, name, shape, dtype=torch.float64):
+        key = (name, tuple(shape), dtype)
+        b = self._buffers.get(key)
+        if b is None:
+            b = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._buffers[key] = b
+        return b
+
+    # ---- olgaussian_mpc.py:69-78 ---------------------------------------------------------------------
+    def _get_next_action(self, state, mode='mean'):
+        if mode == 'mean':
+            next_action = self._mean[0].cpu().numpy().copy()
+        elif mode == 'sample':
+            delta = generate_noise(self._cov, self.filter_coeffs, shape=(1, 1), base_seed=self.seed_val,
+                                   step=123 * self.num_steps, stream_id=control_utils.NOISE_STREAM_ACTION,
+                                   device=self.device)
+            next_action = self._mean[0].cpu().numpy().copy() + delta.reshape(self.d_action).cpu().numpy().copy()
+        else:
+            raise ValueError('Unidentified sampling mode in get_next_action')
+        return next_action
+
+    # ---- olgaussian_mpc.py:88-93 ---------------------------------------------------------------------
+    def sample_noise(self):
+        k0, kl = self.shard.local_range(self.num_particles)
+        out = self._buf("noise", (self.horizon, self.d_action, kl)).permute(2, 0, 1)
+        delta = generate_noise(self._cov, self.filter_coeffs, shape=(kl, self.horizon), base_seed=self.seed_val,
+                               step=self.num_steps, k_offset=k0, K_global=self.num_particles,
+                               zero_last_mean=self._mean if self.use_zero_control_seq else None,
+                               out=out, device=self.device)
+        return delta
+
+    # ---- olgaussian_mpc.py:95-114 --------------------------------------------------------------------
+    def generate_rollouts(self, state):
+        if state is not None:             # None: the backend already holds the (device-resident) state
+            self._set_sim_state_fn(copy.deepcopy(state))
+        delta = self.sample_noise()       # use_zero_control_seq is applied inside the kernel
+        trajectories = self._rollout_fn(self.local_particles, self.horizon, self._mean, delta, mode="open_loop")
+        return trajectories
+
+    # ---- olgaussian_mpc.py:116-129 -------------------------------------------------------------------
+    def _shift(self):
+        if self.base_action not in _lib.BASE_ACTIONS:
+            raise NotImplementedError("invalid option for base action during shift")
+        rnd = None
+        if self.base_action == 'random':
+            # np.random.normal(0, self.init_cov, d): the reference passes the variances as std devs
+            rnd = generate_noise(torch.diag(self._init_cov_d ** 2), [1.0, 0.0, 0.0], shape=(1, 1),
+                                 base_seed=self.seed_val, step=self.num_steps,
+                                 stream_id=control_utils.NOISE_STREAM_BASE, device=self.device).reshape(-1).contiguous()
+        _lib.check(_lib.lib().mjb_shift_mean(_lib.ptr(self._mean), C.c_int(self.horizon), C.c_int(self.d_action),
+                                             C.c_int(_lib.BASE_ACTIONS[self.base_action]), _lib.ptr(rnd),
+                                             _lib.stream_ptr()))
+
+    # ---- olgaussian_mpc.py:131-135 -------------------------------------------------------------------
+    def reset(self):
+        self.num_steps = 0
+        self._mean = torch.zeros((self.horizon, self.d_action), dtype=torch.float64, device=self.device)
+        self._cov = self._to_device(np.diag(self.init_cov)).contiguous()
+        self.gamma_seq = np.cumprod([1.0] + [self.gamma] * (self.horizon - 1)).reshape(1, self.horizon)
+        self._buffers = {}
+
+    def _calc_val(self, trajectories):
+        raise NotImplementedError("_calc_val not implemented")
+
+    # ---- shared GPU reductions -----------------------------------------------------------------------
+    def _traj(self, trajectories):
+        costs = self._to_device(trajectories["costs"])
+        actions = self._to_device(trajectories["actions"])
+        kl = self.local_particles
+        if tuple(costs.shape) != (kl, self.horizon) or tuple(actions.shape) != (kl, self.horizon, self.d_action):
+            raise ValueError("rollout_fn returned costs %s / actions %s for K=%d H=%d d=%d" % (
+                tuple(costs.shape), tuple(actions.shape), kl, self.horizon, self.d_action))
+        return costs, actions
+
+    def _softmax_update(self, costs, actions, lam, control_cost=False, time_based=False, cov_mode=_lib.COV_NONE,
+                        apply=True):
+        """Phase 1 (local partials) -> all-gather over shards -> phase 2 (combine, smooth).
+        Returns the (2+2T,) stats tensor: value, global min, normalisers, minima."""
+        L = _lib.lib()
+        kl, H, d = self.local_particles, self.horizon, self.d_action
+        T = H if time_based else 1
+        P = L.mjb_softmax_partial_doubles(H, d, int(time_based), cov_mode)
+        a = _lib.SoftmaxArgs()
+        a.K, a.H, a.d = kl, H, d
+        a.costs = costs.data_ptr(); a.costs_sk, a.costs_st = costs.stride()
+        a.actions = actions.data_ptr(); a.act_sk, a.act_st, a.act_sj = actions.stride()
+        a.mean = self._mean.data_ptr()
+        a.cov = self._cov.data_ptr()
+        g = np.ascontiguousarray(self.gamma_seq.reshape(-1))
+        a.gamma_seq = g.ctypes.data
+        a.lam = float(lam)
+        a.control_cost, a.time_based, a.cov_mode = int(control_cost), int(time_based), int(cov_mode)
+        total = self._buf("total", (T, kl))
+        scratch = self._buf("sm_scratch", (int(L.mjb_softmax_scratch_doubles(kl, H, d, cov_mode)),))
+        partials = self._buf("sm_partials", (P,))
+        a.total, a.scratch, a.partials = total.data_ptr(), scratch.data_ptr(), partials.data_ptr()
+        _lib.check(L.mjb_softmax_partials(C.byref(a), _lib.stream_ptr()))
+        allp = self.shard.all_gather(partials)
+        stats = self._buf("sm_stats", (2 + 2 * T,))
+        c = _lib.CombineArgs()
+        c.H, c.d, c.n_shards, c.K_global = H, d, self.shard.world_size, self.num_particles
+        c.partials = allp.data_ptr()
+        c.lam, c.step_size = float(lam), float(self.step_size)
+        c.time_based, c.cov_mode = int(time_based), int(cov_mode)
+        c.mean = self._mean.data_ptr() if apply else None
+        c.cov = self._cov.data_ptr() if (apply and cov_mode != _lib.COV_NONE) else None
+        c.stats = stats.data_ptr()
+        _lib.check(L.mjb_softmax_combine(C.byref(c), _lib.stream_ptr()))
+        self._last_total = total
+        return stats
+
+    def _ctg0(self, costs):
+        """cost_to_go(costs, gamma_seq)[:, 0] for the local particles (device, contiguous)."""
+        kl = self.local_particles
+        out = self._buf("ctg", (self.horizon, kl)).t()
+        control_utils.cost_to_go(costs, self.gamma_seq, out=out)
+        return out[:, 0]

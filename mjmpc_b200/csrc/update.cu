@@ -1,0 +1,770 @@
+// K3-K8: everything the controllers do with a finished rollout -- discounted cost-to-go, the
+// exponential-utility (softmax) reductions of MPPI / DMD-MPC / PFMPC, CEM elite selection and
+// moments, RandomShooting argmin, PFMPC systematic resampling and the hot-start shifts.
+// Reference sites are cited per entry point in include/mjmpc_b200.h.  All reductions are
+// two-stage and ordered (per-block partials, then a fixed-order sum), so results are
+// deterministic and independent of scheduling; shards combine in rank order.
+#include <math.h>
+#include "common.h"
+
+#define MJB_MAXD 8
+#define MJB_MAXH 128
+#define MJB_CHUNK 2048        // particles per block in the (chunk, t) reductions
+#define MJB_RB 256            // threads per reduction block
+
+namespace mjb {
+
+struct GammaSeq { double g[MJB_MAXH]; int raw; };
+
+static int load_gamma(GammaSeq& G, const double* host, int H) {
+    if (H > MJB_MAXH) return set_error(MJB_EINVAL, "horizon %d exceeds the supported maximum %d", H, MJB_MAXH);
+    G.raw = 0;
+    for (int t = 0; t < H; t++) { G.g[t] = host[t]; if (host[t] == 0.0) G.raw = 1; }
+    return MJB_OK;
+}
+
+__device__ __forceinline__ unsigned long long enc_key(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_key(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------ cost_to_go
+// control_utils.py:37-46 with numpy's operation order: multiply, sequential reverse add, divide.
+__global__ void cost_to_go_kernel(const double* __restrict__ c, long long sk, long long st, GammaSeq G, int K, int H,
+                                  double* __restrict__ out, long long osk, long long ost) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double S = 0.0;
+    for (int t = H - 1; t >= 0; t--) {
+        const double x = c[k * sk + t * st];
+        if (G.raw) { out[k * osk + t * ost] = x; continue; }
+        S = __dadd_rn(S, __dmul_rn(G.g[t], x));
+        out[k * osk + t * ost] = __ddiv_rn(S, G.g[t]);
+    }
+}
+
+// ------------------------------------------------------------------------------ softmax phase 1
+// scratch layout (doubles): [0, MAXH) encoded minima | [MAXH, MAXH + H*d) u_n | then block partials
+__global__ void softmax_prep_kernel(mjb_softmax_args a, int T) {
+    unsigned long long* menc = (unsigned long long*)a.scratch;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) menc[i] = enc_key(INFINITY);
+    if (!a.control_cost) return;
+    // u_n = mean @ inv(cov)   (mppi.py:106); inverse by Gauss-Jordan with partial pivoting on a d x 2d tableau
+    __shared__ double A[MJB_MAXD][2 * MJB_MAXD];
+    const int d = a.d;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < d; i++)
+            for (int j = 0; j < d; j++) { A[i][j] = a.cov[i * d + j]; A[i][d + j] = i == j ? 1.0 : 0.0; }
+        for (int c = 0; c < d; c++) {
+            int p = c;
+            for (int r = c + 1; r < d; r++) if (fabs(A[r][c]) > fabs(A[p][c])) p = r;
+            if (p != c) for (int j = 0; j < 2 * d; j++) { const double t = A[c][j]; A[c][j] = A[p][j]; A[p][j] = t; }
+            const double inv = 1.0 / A[c][c];
+            for (int j = 0; j < 2 * d; j++) A[c][j] *= inv;
+            for (int r = 0; r < d; r++) if (r != c) {
+                const double f = A[r][c];
+                for (int j = 0; j < 2 * d; j++) A[r][j] -= f * A[c][j];
+            }
+        }
+    }
+    __syncthreads();
+    double* un = a.scratch + MJB_MAXH;
+    for (int i = threadIdx.x; i < a.H * d; i += blockDim.x) {
+        const int t = i / d, j = i % d;
+        double s = 0.0;
+        for (int l = 0; l < d; l++) s += a.mean[t * d + l] * A[l][d + j];
+        un[i] = s;
+    }
+}
+
+// per-particle trajectory cost (mppi.py:84-97 / gaussian_dmd.py:94-104) and its minimum over particles
+template <int D>
+__global__ void __launch_bounds__(MJB_RB) traj_cost_kernel(mjb_softmax_args a, GammaSeq G, int T) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long* menc = (unsigned long long*)a.scratch;
+    const double* __restrict__ un = a.scratch + MJB_MAXH;
+    const bool live = k < a.K;
+    double S = 0.0, Sc = 0.0, tot0 = INFINITY;
+    for (int t = a.H - 1; t >= 0; t--) {
+        double tot = INFINITY;
+        if (live) {
+            const double c = a.costs[k * a.costs_sk + t * a.costs_st];
+            double ctg;
+            if (G.raw) ctg = c;
+            else { S = __dadd_rn(S, __dmul_rn(G.g[t], c)); ctg = __ddiv_rn(S, G.g[t]); }
+            double ccg = 0.0;
+            if (a.control_cost) {
+                double cc = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    const double m = a.mean[t * D + j];
+                    const double dl = a.actions[k * a.act_sk + t * a.act_st + j * a.act_sj] - m;
+                    cc += 0.5 * un[t * D + j] * (m + 2.0 * dl);
+                }
+                if (G.raw) ccg = cc;
+                else { Sc = __dadd_rn(Sc, __dmul_rn(G.g[t], cc)); ccg = __ddiv_rn(Sc, G.g[t]); }
+            }
+            tot = ctg + a.lam * ccg;
+            if (T > 1) a.total[(long long)t * a.K + k] = tot;
+            tot0 = tot;
+        }
+        if (T > 1) {
+            double mn = tot;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            if ((threadIdx.x & 31) == 0 && mn < INFINITY) atomicMin(&menc[t], enc_key(mn));
+        }
+    }
+    if (T == 1) {
+        if (live) a.total[k] = tot0;
+        double mn = tot0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if ((threadIdx.x & 31) == 0 && mn < INFINITY) atomicMin(&menc[0], enc_key(mn));
+    }
+}
+
+// Generic weighted reduction over particles for one (chunk, t) tile.
+//   WMODE 0: w = exp(ninv*total - ninv*m)   1: w = flag (0/1)   2: w = 1
+//   CMODE 0: none  1: diag  2: full lower triangle of  w (delta-mu)(delta-mu)',  delta = a - mean[t]
+// block partial -> out[(t*nchunks + chunk)*NACC + c],  NACC = 1 + D + ncov
+template <int D, int WMODE, int CMODE>
+__global__ void __launch_bounds__(MJB_RB) weighted_reduce_kernel(
+    int K, int H, const double* __restrict__ total, int T, const unsigned long long* __restrict__ menc, double ninv,
+    const unsigned char* __restrict__ flags, const double* __restrict__ actions, long long sk, long long st, long long sj,
+    const double* __restrict__ mean, const double* __restrict__ mu, double* __restrict__ out) {
+    constexpr int NC = CMODE == 0 ? 0 : (CMODE == 1 ? D : D * (D + 1) / 2);
+    constexpr int NACC = 1 + D + NC;
+    const int t = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+    double acc[NACC];
+#pragma unroll
+    for (int c = 0; c < NACC; c++) acc[c] = 0.0;
+    double xmax = 0.0;
+    const double* trow = nullptr;
+    if (WMODE == 0) { const int tr = T > 1 ? t : 0; xmax = ninv * dec_key(menc[tr]); trow = total + (long long)tr * K; }
+    double mrow[D], murow[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) { mrow[j] = (CMODE != 0) ? mean[t * D + j] : 0.0; murow[j] = (CMODE != 0 && mu) ? mu[j] : 0.0; }
+    const long long k0 = (long long)chunk * MJB_CHUNK;
+    for (int i = threadIdx.x; i < MJB_CHUNK; i += MJB_RB) {
+        const long long k = k0 + i;
+        if (k >= K) break;
+        double w;
+        if (WMODE == 0) w = exp(ninv * trow[k] - xmax);
+        else if (WMODE == 1) w = flags[k] ? 1.0 : 0.0;
+        else w = 1.0;
+        if (WMODE == 1 && w == 0.0) continue;
+        acc[0] += w;
+        double dl[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            const double av = actions[k * sk + t * st + j * sj];
+            acc[1 + j] += w * av;
+            dl[j] = av - mrow[j] - murow[j];
+        }
+        if (CMODE == 1) {
+#pragma unroll
+            for (int j = 0; j < D; j++) acc[1 + D + j] += w * (dl[j] * dl[j]);
+        } else if (CMODE == 2) {
+            int c = 1 + D;
+#pragma unroll
+            for (int i2 = 0; i2 < D; i2++)
+#pragma unroll
+                for (int j = 0; j <= i2; j++) acc[c++] += w * (dl[i2] * dl[j]);
+        }
+    }
+    __shared__ double sm[MJB_RB / 32][NACC];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < NACC; c++) {
+        const double v = warp_sum(acc[c]);
+        if (lane == 0) sm[wid][c] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < NACC; c += MJB_RB) {
+        double s = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < MJB_RB / 32; w2++) s += sm[w2][c];
+        out[((long long)t * nchunks + chunk) * NACC + c] = s;
+    }
+}
+
+// fixed-order sum over chunks: part[t*NACC + c] = sum_chunk blockpart[(t*nchunks+chunk)*NACC + c]
+__global__ void chunk_sum_kernel(const double* __restrict__ bp, int nchunks, int NACC, double* __restrict__ part) {
+    const int t = blockIdx.x;
+    for (int c = threadIdx.x; c < NACC; c += blockDim.x) {
+        double s = 0.0;
+        for (int ch = 0; ch < nchunks; ch++) s += bp[((long long)t * nchunks + ch) * NACC + c];
+        part[t * NACC + c] = s;
+    }
+}
+__global__ void decode_min_kernel(const unsigned long long* menc, int T, double* out) {
+    for (int i = threadIdx.x; i < T; i += blockDim.x) out[i] = dec_key(menc[i]);
+}
+
+// ------------------------------------------------------------------------------ softmax phase 2
+__global__ void softmax_combine_kernel(mjb_combine_args a) {
+    const int H = a.H, d = a.d, T = a.time_based ? H : 1;
+    const int nc = a.cov_mode == MJB_COV_NONE ? 0 : (a.cov_mode == MJB_COV_DIAG ? d : d * (d + 1) / 2);
+    const int NACC = 1 + d + nc, P = T + H * NACC;
+    const double ninv = -1.0 / a.lam;
+    __shared__ double mstar[MJB_MAXH];
+    __shared__ double comb[MJB_MAXH][1 + MJB_MAXD + MJB_MAXD * (MJB_MAXD + 1) / 2];
+    for (int tr = threadIdx.x; tr < T; tr += blockDim.x) {
+        double m = INFINITY;
+        for (int r = 0; r < a.n_shards; r++) m = fmin(m, a.partials[(long long)r * P + tr]);
+        mstar[tr] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * NACC; i += blockDim.x) {
+        const int t = i / NACC, tr = T > 1 ? t : 0;
+        double s = 0.0;
+        for (int r = 0; r < a.n_shards; r++) {
+            const double* p = a.partials + (long long)r * P;
+            const double scale = exp(ninv * p[tr] - ninv * mstar[tr]);   // <= 1: shard minimum vs global minimum
+            s += p[T + i] * scale;
+        }
+        comb[t][i % NACC] = s;
+    }
+    __syncthreads();
+    // a.mean == NULL: statistics only (the _calc_val pass leaves the distribution untouched)
+    for (int i = threadIdx.x; a.mean && i < H * d; i += blockDim.x) {
+        const int t = i / d, j = i % d;
+        a.mean[i] = (1.0 - a.step_size) * a.mean[i] + a.step_size * (comb[t][1 + j] / comb[t][0]);
+    }
+    if (a.mean && a.cov_mode != MJB_COV_NONE) {
+        for (int i = threadIdx.x; i < d * d; i += blockDim.x) {
+            const int r = i / d, c = i % d;
+            double upd = 0.0;
+            if (a.cov_mode == MJB_COV_DIAG) {
+                if (r == c) { for (int t = 0; t < H; t++) upd += comb[t][1 + d + r] / comb[t][0]; upd /= H; }
+            } else {
+                const int hi = r > c ? r : c, lo = r > c ? c : r;
+                const int idx = 1 + d + hi * (hi + 1) / 2 + lo;
+                for (int t = 0; t < H; t++) upd += comb[t][idx] / comb[t][0];
+                upd /= H;
+            }
+            a.cov[i] = (1.0 - a.step_size) * a.cov[i] + a.step_size * upd;
+        }
+    }
+    if (a.stats) {
+        if (threadIdx.x == 0) {
+            a.stats[0] = -a.lam * (ninv * mstar[0] + log(comb[0][0] / (double)a.K_global));
+            a.stats[1] = mstar[0];
+        }
+        for (int tr = threadIdx.x; tr < T; tr += blockDim.x) a.stats[2 + tr] = comb[tr][0];
+        // minima for the other rows of a time-based weighting live after the normalisers
+        for (int tr = threadIdx.x; tr < T; tr += blockDim.x) a.stats[2 + T + tr] = mstar[tr];
+    }
+}
+
+__global__ void softmax_weights_kernel(const double* __restrict__ total, int K, const double* __restrict__ stats, int T,
+                                       int t, double ninv, double* __restrict__ w) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const double m = stats[2 + T + t], S = stats[2 + t];
+    w[k] = exp(ninv * total[(long long)t * K + k] - ninv * m) / S;
+}
+
+// ------------------------------------------------------------------------------ elite selection
+// 8-pass MSB radix select on order-preserving keys, one block; ties at the threshold resolved by index.
+__global__ void __launch_bounds__(1024) select_elites_kernel(const double* __restrict__ v, long long K, long long E,
+                                                            unsigned char* __restrict__ flags, long long* __restrict__ ids) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned long long s_prefix, s_want;
+    __shared__ long long s_scan[1024];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) { s_prefix = 0; s_want = (unsigned long long)E; }
+    __syncthreads();
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        for (int b = tid; b < 256; b += nt) hist[b] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        for (long long i = tid; i < K; i += nt) {
+            const unsigned long long key = enc_key(v[i]);
+            if ((key & himask) == prefix) {
+                // warp-aggregate: costs share their exponent byte, so whole warps hit one bin
+                const unsigned b = (unsigned)(key >> shift) & 255u;
+                const unsigned peers = __match_any_sync(__activemask(), b);
+                if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[b], (unsigned)__popc(peers));
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long want = s_want, cum = 0;
+            int b = 0;
+            for (; b < 256; b++) { if (cum + hist[b] >= want) break; cum += hist[b]; }
+            s_want = want - cum;
+            s_prefix = prefix | ((unsigned long long)b << shift);
+        }
+        __syncthreads();
+    }
+    const unsigned long long thr = s_prefix;      // key of the E-th smallest value
+    const long long need_eq = (long long)s_want;  // how many keys equal to it are elite (lowest indices first)
+    // ordered pass over contiguous index ranges
+    const long long per = (K + nt - 1) / nt, lo = (long long)tid * per, hi = lo + per < K ? lo + per : K;
+    long long neq = 0;
+    for (long long i = lo; i < hi; i++) neq += enc_key(v[i]) == thr;
+    s_scan[tid] = neq;
+    __syncthreads();
+    if (tid == 0) { long long c = 0; for (int i = 0; i < nt; i++) { const long long x = s_scan[i]; s_scan[i] = c; c += x; } }
+    __syncthreads();
+    long long eq_before = s_scan[tid], nel = 0;
+    __syncthreads();
+    for (long long i = lo; i < hi; i++) {
+        const unsigned long long key = enc_key(v[i]);
+        bool e = key < thr;
+        if (key == thr) { e = eq_before < need_eq; eq_before++; }
+        flags[i] = e ? 1 : 0;
+        nel += e;
+    }
+    if (ids) {
+        s_scan[tid] = nel;
+        __syncthreads();
+        if (tid == 0) { long long c = 0; for (int i = 0; i < nt; i++) { const long long x = s_scan[i]; s_scan[i] = c; c += x; } }
+        __syncthreads();
+        long long o = s_scan[tid];
+        for (long long i = lo; i < hi; i++) if (flags[i]) ids[o++] = i;
+    }
+}
+
+__global__ void __launch_bounds__(1024) argmin_kernel(const double* __restrict__ v, long long K, long long* out_idx,
+                                                     double* out_val) {
+    __shared__ unsigned long long sk[1024];
+    __shared__ long long si[1024];
+    unsigned long long bk = ~0ull;
+    long long bi = -1;
+    for (long long i = threadIdx.x; i < K; i += blockDim.x) {
+        const unsigned long long key = enc_key(v[i]);
+        if (key < bk) { bk = key; bi = i; }          // strided ascending i: first occurrence wins within a thread
+    }
+    sk[threadIdx.x] = bk; si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const unsigned long long ok = sk[threadIdx.x + s];
+            const long long oi = si[threadIdx.x + s];
+            if (oi >= 0 && (ok < sk[threadIdx.x] || (ok == sk[threadIdx.x] && (si[threadIdx.x] < 0 || oi < si[threadIdx.x])))) {
+                sk[threadIdx.x] = ok; si[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out_idx[0] = si[0]; if (out_val) out_val[0] = si[0] >= 0 ? v[si[0]] : INFINITY; }
+}
+
+// pass-1 / pass-2 combine of elite moments (cem.py:71-86)
+__global__ void elite_combine_kernel(mjb_elite_combine_args a) {
+    const int H = a.H, d = a.d, P1 = 1 + H * d + d, P2 = d * (d + 1) / 2;
+    __shared__ double n_s, mu_s[MJB_MAXD];
+    if (threadIdx.x == 0) {
+        double n = 0.0;
+        for (int r = 0; r < a.n_shards; r++) n += a.partial1[(long long)r * P1];
+        n_s = n;
+    }
+    __syncthreads();
+    const double n = n_s;
+    if (threadIdx.x < d) {
+        double s = 0.0;
+        for (int r = 0; r < a.n_shards; r++) s += a.partial1[(long long)r * P1 + 1 + H * d + threadIdx.x];
+        mu_s[threadIdx.x] = s / (n * H);
+        a.mu[threadIdx.x] = mu_s[threadIdx.x];
+    }
+    __syncthreads();
+    if (!a.partial2) return;
+    for (int i = threadIdx.x; i < d * d; i += blockDim.x) {
+        const int r = i / d, c = i % d;
+        const int hi = r > c ? r : c, lo = r > c ? c : r;
+        double s = 0.0;
+        for (int q = 0; q < a.n_shards; q++) s += a.partial2[(long long)q * P2 + hi * (hi + 1) / 2 + lo];
+        double upd;
+        if (a.full_cov) upd = s / (n * H - 1.0);           // np.cov, ddof = 1
+        else upd = r == c ? s / (n * H) : 0.0;             // np.diag(np.var), ddof = 0
+        a.cov[i] = (1.0 - a.step_size) * a.cov[i] + a.step_size * upd;
+    }
+    for (int i = threadIdx.x; i < H * d; i += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < a.n_shards; q++) s += a.partial1[(long long)q * P1 + 1 + i];
+        a.mean[i] = (1.0 - a.step_size) * a.mean[i] + a.step_size * (s / n);
+    }
+}
+
+// partial1 = [ n | sum_a (H,d) | sum_delta (d) ] from the per-t reduced block (NACC = 1 + d)
+__global__ void elite_pack1_kernel(const double* __restrict__ part, const double* __restrict__ mean, int H, int d,
+                                   double* __restrict__ out) {
+    const int NACC = 1 + d;
+    if (threadIdx.x == 0) out[0] = part[0];
+    for (int i = threadIdx.x; i < H * d; i += blockDim.x) out[1 + i] = part[(i / d) * NACC + 1 + i % d];
+    __syncthreads();
+    if (threadIdx.x < d) {
+        double s = 0.0;
+        for (int t = 0; t < H; t++) s += part[t * NACC + 1 + threadIdx.x] - part[t * NACC] * mean[t * d + threadIdx.x];
+        out[1 + H * d + threadIdx.x] = s;
+    }
+}
+// partial2 = sum over t of the lower-triangular second moments (NACC = 1 + d + d(d+1)/2)
+__global__ void elite_pack2_kernel(const double* __restrict__ part, int H, int d, double* __restrict__ out) {
+    const int P2 = d * (d + 1) / 2, NACC = 1 + d + P2;
+    for (int c = threadIdx.x; c < P2; c += blockDim.x) {
+        double s = 0.0;
+        for (int t = 0; t < H; t++) s += part[t * NACC + 1 + d + c];
+        out[c] = s;
+    }
+}
+
+__global__ void blend_best_kernel(const double* __restrict__ actions, long long sk, long long st, long long sj,
+                                  const long long* best, long long k_offset, int K, int H, int d, double step,
+                                  double* mean) {
+    const long long b = best[0] - k_offset;
+    if (b < 0 || b >= K) return;
+    for (int i = threadIdx.x; i < H * d; i += blockDim.x)
+        mean[i] = (1.0 - step) * mean[i] + step * actions[b * sk + (i / d) * st + (i % d) * sj];
+}
+
+// ------------------------------------------------------------------------------ PFMPC resampling
+__global__ void __launch_bounds__(256) seq_cumsum_kernel(const double* __restrict__ w, long long M, double* __restrict__ cs) {
+    __shared__ double tile[2048];
+    __shared__ double carry;
+    if (threadIdx.x == 0) carry = 0.0;
+    for (long long base = 0; base < M; base += 2048) {
+        const int n = (int)(M - base < 2048 ? M - base : 2048);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = w[base + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double c = carry;
+            for (int i = 0; i < n; i++) { c = __dadd_rn(c, tile[i]); tile[i] = c; }   // reference order: c += w[i]
+            carry = c;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) cs[base + i] = tile[i];
+    }
+}
+__global__ void resample_search_kernel(const double* __restrict__ cs, long long M, double r, long long* __restrict__ idx) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const double u = __dadd_rn(r, __ddiv_rn((double)m, (double)M));       // r + m*1.0/M*1.0
+    long long res;
+    if (!(0.0 < u)) res = M - 1;                                          // loop never runs: act_seq[-1]
+    else {
+        long long lo = 0, hi = M;                                         // first i with cs[i] >= u
+        while (lo < hi) { const long long mid = (lo + hi) >> 1; if (cs[mid] >= u) hi = mid; else lo = mid + 1; }
+        res = lo < M ? lo : M - 1;
+    }
+    idx[m] = res;
+}
+__global__ void gather_kernel(const double* __restrict__ in, long long isk, long long ist, long long isj,
+                              const long long* __restrict__ idx, int K, int H, int d, double* __restrict__ out,
+                              long long osk, long long ost, long long osj) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tj = blockIdx.y;
+    if (k >= K) return;
+    const int t = tj / d, j = tj % d;
+    out[k * osk + t * ost + j * osj] = in[idx[k] * isk + t * ist + j * isj];
+}
+
+__global__ void sub_mean_kernel(const double* __restrict__ x, long long sk, long long st, long long sj,
+                                const double* __restrict__ mean, int K, int H, int d, double* __restrict__ out,
+                                long long osk, long long ost, long long osj) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tj = blockIdx.y;
+    if (k >= K) return;
+    const int t = tj / d, j = tj % d;
+    out[k * osk + t * ost + j * osj] = x[k * sk + t * st + j * sj] - mean[tj];
+}
+
+// ------------------------------------------------------------------------------ shifts
+__global__ void shift_mean_kernel(double* mean, int H, int d, int base, const double* rnd) {
+    // single block: read everything, sync, write (rows overlap)
+    extern __shared__ double buf[];
+    for (int i = threadIdx.x; i < H * d; i += blockDim.x) buf[i] = mean[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < H * d; i += blockDim.x) {
+        const int t = i / d, j = i % d;
+        double v;
+        if (t < H - 1) v = buf[(t + 1) * d + j];
+        else if (base == MJB_BASE_NULL) v = 0.0;
+        else if (base == MJB_BASE_REPEAT) v = H >= 2 ? buf[(H - 1) * d + j] : buf[j];   // mean[-2] after the shift
+        else v = rnd[j];
+        mean[i] = v;
+    }
+}
+__global__ void cov_add_diag_kernel(double* cov, int d, double beta, const double* v) {
+    if (threadIdx.x < d) cov[threadIdx.x * d + threadIdx.x] += beta * (v ? v[threadIdx.x] : 1.0);
+}
+__global__ void pf_shift_kernel(double* s, long long sk, long long st, long long sj, const double* dl, long long dk,
+                                long long dt, long long dj, int K, int H, int d, int base, const double* rnd) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    for (int j = 0; j < d; j++) {
+        double prev = 0.0;
+        for (int t = 0; t < H; t++) {
+            // particle_filter_controller.py:133-139: roll left (last column keeps its value), then add noise
+            const double src = t < H - 1 ? s[k * sk + (t + 1) * st + j * sj] : s[k * sk + t * st + j * sj];
+            double v = src + dl[k * dk + t * dt + j * dj];
+            if (t == H - 1) {
+                if (base == MJB_BASE_NULL) v = 0.0;
+                else if (base == MJB_BASE_REPEAT) v = H >= 2 ? prev : v;
+                else v = rnd[j];
+            }
+            s[k * sk + t * st + j * sj] = v;
+            prev = v;
+        }
+    }
+}
+
+template <int D>
+static int launch_reduce(int wmode, int cmode, dim3 grid, cudaStream_t s, int K, int H, const double* total, int T,
+                         const unsigned long long* menc, double ninv, const unsigned char* flags, const double* actions,
+                         long long sk, long long st, long long sj, const double* mean, const double* mu, double* out) {
+#define MJB_L(W, C) weighted_reduce_kernel<D, W, C><<<grid, MJB_RB, 0, s>>>(K, H, total, T, menc, ninv, flags, actions, sk, st, sj, mean, mu, out)
+    if (wmode == 0 && cmode == 0) MJB_L(0, 0);
+    else if (wmode == 0 && cmode == 1) MJB_L(0, 1);
+    else if (wmode == 0 && cmode == 2) MJB_L(0, 2);
+    else if (wmode == 1 && cmode == 0) MJB_L(1, 0);
+    else if (wmode == 1 && cmode == 2) MJB_L(1, 2);
+    else if (wmode == 2 && cmode == 0) MJB_L(2, 0);
+    else return set_error(MJB_EINVAL, "unsupported reduction mode %d/%d", wmode, cmode);
+#undef MJB_L
+    return MJB_OK;
+}
+static int dispatch_reduce(int d, int wmode, int cmode, dim3 grid, cudaStream_t s, int K, int H, const double* total, int T,
+                           const unsigned long long* menc, double ninv, const unsigned char* flags, const double* actions,
+                           long long sk, long long st, long long sj, const double* mean, const double* mu, double* out) {
+    switch (d) {
+#define MJB_CASE(D) case D: return launch_reduce<D>(wmode, cmode, grid, s, K, H, total, T, menc, ninv, flags, actions, sk, st, sj, mean, mu, out);
+        MJB_CASE(1) MJB_CASE(2) MJB_CASE(3) MJB_CASE(4) MJB_CASE(5) MJB_CASE(6) MJB_CASE(7) MJB_CASE(8)
+#undef MJB_CASE
+    }
+    return set_error(MJB_EINVAL, "d_action=%d not in 1..%d", d, MJB_MAXD);
+}
+static int ncov_of(int d, int cov_mode) { return cov_mode == MJB_COV_NONE ? 0 : (cov_mode == MJB_COV_DIAG ? d : d * (d + 1) / 2); }
+static int nchunks_of(int K) { return (K + MJB_CHUNK - 1) / MJB_CHUNK; }
+
+}  // namespace mjb
+
+using namespace mjb;
+
+extern "C" int mjb_cost_to_go(const double* costs, long long sk, long long st, const double* gamma_seq_host, int K, int H,
+                              double* out, long long osk, long long ost, void* stream) {
+    MJB_REQUIRE(costs && out && gamma_seq_host, "mjb_cost_to_go: null pointer");
+    MJB_REQUIRE(K >= 0 && H >= 1, "mjb_cost_to_go: bad shape");
+    GammaSeq G;
+    int rc = load_gamma(G, gamma_seq_host, H);
+    if (rc) return rc;
+    if (K == 0) return MJB_OK;
+    cost_to_go_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(costs, sk, st, G, K, H, out, osk, ost);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" long long mjb_softmax_scratch_doubles(int K, int H, int d, int cov_mode) {
+    const long long NACC = 1 + d + ncov_of(d, cov_mode);
+    return MJB_MAXH + (long long)H * d + (long long)H * nchunks_of(K) * NACC + 64;
+}
+extern "C" int mjb_softmax_partial_doubles(int H, int d, int time_based, int cov_mode) {
+    return (time_based ? H : 1) + H * (1 + d + ncov_of(d, cov_mode));
+}
+
+extern "C" int mjb_softmax_partials(const mjb_softmax_args* a, void* stream) {
+    MJB_REQUIRE(a && a->costs && a->actions && a->mean && a->gamma_seq && a->total && a->scratch && a->partials,
+                "mjb_softmax_partials: null pointer");
+    MJB_REQUIRE(a->K >= 1 && a->H >= 1, "mjb_softmax_partials: bad shape K=%d H=%d", a->K, a->H);
+    MJB_REQUIRE(a->d >= 1 && a->d <= MJB_MAXD, "d_action=%d not in 1..%d", a->d, MJB_MAXD);
+    MJB_REQUIRE(a->lam > 0.0, "lam must be positive");
+    MJB_REQUIRE(!a->control_cost || a->cov, "control cost needs cov");
+    MJB_REQUIRE(!(a->time_based && a->cov_mode != MJB_COV_NONE), "time-based weights have no covariance update");
+    if (a->cov_mode < 0 || a->cov_mode > 2)
+        return set_error(MJB_EINVAL, "Unidentified covariance type in update_distribution");   // gaussian_dmd.py:85
+    GammaSeq G;
+    int rc = load_gamma(G, a->gamma_seq, a->H);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int T = a->time_based ? a->H : 1;
+    const int NACC = 1 + a->d + ncov_of(a->d, a->cov_mode);
+    const int nch = nchunks_of(a->K);
+    softmax_prep_kernel<<<1, 128, 0, s>>>(*a, T);
+    switch (a->d) {
+#define MJB_CASE(D) case D: traj_cost_kernel<D><<<(a->K + MJB_RB - 1) / MJB_RB, MJB_RB, 0, s>>>(*a, G, T); break;
+        MJB_CASE(1) MJB_CASE(2) MJB_CASE(3) MJB_CASE(4) MJB_CASE(5) MJB_CASE(6) MJB_CASE(7) MJB_CASE(8)
+#undef MJB_CASE
+    }
+    double* bp = a->scratch + MJB_MAXH + (long long)a->H * a->d;
+    rc = dispatch_reduce(a->d, 0, a->cov_mode, dim3(nch, a->H), s, a->K, a->H, a->total, T,
+                         (const unsigned long long*)a->scratch, -1.0 / a->lam, nullptr, a->actions, a->act_sk, a->act_st,
+                         a->act_sj, a->mean, nullptr, bp);
+    if (rc) return rc;
+    decode_min_kernel<<<1, 128, 0, s>>>((const unsigned long long*)a->scratch, T, a->partials);
+    chunk_sum_kernel<<<a->H, 64, 0, s>>>(bp, nch, NACC, a->partials + T);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_softmax_combine(const mjb_combine_args* a, void* stream) {
+    MJB_REQUIRE(a && a->partials && (a->mean || a->stats), "mjb_softmax_combine: null pointer");
+    MJB_REQUIRE(a->H >= 1 && a->H <= MJB_MAXH && a->d >= 1 && a->d <= MJB_MAXD && a->n_shards >= 1, "mjb_softmax_combine: bad shape");
+    MJB_REQUIRE(a->cov_mode == MJB_COV_NONE || a->cov || !a->mean, "covariance update needs cov");
+    softmax_combine_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*a);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_softmax_weights(const double* total, int K, const double* stats, int t, double lam, double* w_out,
+                                   void* stream) {
+    MJB_REQUIRE(total && stats && w_out && K >= 1 && lam > 0.0, "mjb_softmax_weights: bad argument");
+    // T is implied by the caller's stats layout: this entry point serves the non-time-based case (T = 1)
+    softmax_weights_kernel<<<(K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(total, K, stats, 1, t, -1.0 / lam, w_out);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_select_elites(const double* ctg0, long long K_global, long long num_elite, unsigned char* flags,
+                                 long long* ids, void* scratch, void* stream) {
+    (void)scratch;
+    MJB_REQUIRE(ctg0 && flags, "mjb_select_elites: null pointer");
+    MJB_REQUIRE(K_global >= 1 && num_elite >= 1 && num_elite <= K_global, "num_elite=%lld must be in 1..K=%lld", num_elite, K_global);
+    select_elites_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ctg0, K_global, num_elite, flags, ids);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_argmin(const double* ctg0, long long K, long long* out_index, double* out_value, void* stream) {
+    MJB_REQUIRE(ctg0 && out_index && K >= 1, "mjb_argmin: bad argument");
+    argmin_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ctg0, K, out_index, out_value);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" long long mjb_elite_scratch_doubles(int K, int H, int d) {
+    const long long NACC = 1 + d + d * (d + 1) / 2;
+    return (long long)H * nchunks_of(K) * NACC + (long long)H * NACC + 64;
+}
+
+static int elite_moments(const mjb_elite_args* a, int pass, void* stream) {
+    MJB_REQUIRE(a && a->flags && a->actions && a->mean && a->scratch && a->partial, "mjb_elite_moments: null pointer");
+    MJB_REQUIRE(a->K >= 1 && a->H >= 1 && a->H <= MJB_MAXH && a->d >= 1 && a->d <= MJB_MAXD, "mjb_elite_moments: bad shape");
+    MJB_REQUIRE(pass == 1 || a->mu, "mjb_elite_moments2 needs the pooled mean");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nch = nchunks_of(a->K);
+    const int cmode = pass == 1 ? 0 : 2;
+    const int NACC = 1 + a->d + (pass == 1 ? 0 : a->d * (a->d + 1) / 2);
+    double* bp = a->scratch;
+    double* part = a->scratch + (long long)a->H * nch * NACC;
+    int rc = dispatch_reduce(a->d, 1, cmode, dim3(nch, a->H), s, a->K, a->H, nullptr, 1, nullptr, 0.0, a->flags, a->actions,
+                             a->act_sk, a->act_st, a->act_sj, a->mean, a->mu, bp);
+    if (rc) return rc;
+    chunk_sum_kernel<<<a->H, 64, 0, s>>>(bp, nch, NACC, part);
+    if (pass == 1) elite_pack1_kernel<<<1, 256, 0, s>>>(part, a->mean, a->H, a->d, a->partial);
+    else elite_pack2_kernel<<<1, 64, 0, s>>>(part, a->H, a->d, a->partial);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+extern "C" int mjb_elite_moments1(const mjb_elite_args* a, void* stream) { return elite_moments(a, 1, stream); }
+extern "C" int mjb_elite_moments2(const mjb_elite_args* a, void* stream) { return elite_moments(a, 2, stream); }
+
+extern "C" int mjb_elite_combine(const mjb_elite_combine_args* a, void* stream) {
+    MJB_REQUIRE(a && a->partial1 && a->mu, "mjb_elite_combine: null pointer");
+    MJB_REQUIRE(!a->partial2 || (a->mean && a->cov), "mjb_elite_combine: mean and cov are required with partial2");
+    MJB_REQUIRE(a->H >= 1 && a->d >= 1 && a->d <= MJB_MAXD && a->n_shards >= 1, "mjb_elite_combine: bad shape");
+    elite_combine_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*a);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_blend_best(const double* actions, long long sk, long long st, long long sj, const long long* best_index,
+                              long long k_offset, int K, int H, int d, double step_size, double* mean, void* stream) {
+    MJB_REQUIRE(actions && best_index && mean, "mjb_blend_best: null pointer");
+    blend_best_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(actions, sk, st, sj, best_index, k_offset, K, H, d, step_size, mean);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_resample_indices(const double* weights, long long M, double r, double* cumsum_scratch,
+                                    long long* idx_out, void* stream) {
+    MJB_REQUIRE(weights && cumsum_scratch && idx_out && M >= 1, "mjb_resample_indices: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    seq_cumsum_kernel<<<1, 256, 0, s>>>(weights, M, cumsum_scratch);
+    resample_search_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(cumsum_scratch, M, r, idx_out);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_gather_particles(const double* in, long long isk, long long ist, long long isj, const long long* idx,
+                                    int K, int H, int d, double* out, long long osk, long long ost, long long osj,
+                                    void* stream) {
+    MJB_REQUIRE(in && idx && out && K >= 1 && H >= 1 && d >= 1, "mjb_gather_particles: bad argument");
+    MJB_REQUIRE(in != out, "mjb_gather_particles: in-place gather is not supported");
+    gather_kernel<<<dim3((K + 255) / 256, H * d), 256, 0, (cudaStream_t)stream>>>(in, isk, ist, isj, idx, K, H, d, out, osk, ost, osj);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_particle_mean(const double* x, long long sk, long long st, long long sj, int K, int H, int d,
+                                 double* scratch, double* out, void* stream);
+namespace mjb {
+__global__ void particle_mean_pack_kernel(const double* part, int H, int d, int K, double* out) {
+    for (int i = threadIdx.x; i < H * d; i += blockDim.x) out[i] = part[(i / d) * (1 + d) + 1 + i % d] / (double)K;
+}
+}
+extern "C" int mjb_particle_mean(const double* x, long long sk, long long st, long long sj, int K, int H, int d,
+                                 double* scratch, double* out, void* stream) {
+    MJB_REQUIRE(x && scratch && out && K >= 1 && H >= 1 && d >= 1 && d <= MJB_MAXD, "mjb_particle_mean: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nch = nchunks_of(K), NACC = 1 + d;
+    double* bp = scratch;
+    double* part = scratch + (long long)H * nch * NACC;
+    int rc = dispatch_reduce(d, 2, 0, dim3(nch, H), s, K, H, nullptr, 1, nullptr, 0.0, nullptr, x, sk, st, sj, nullptr, nullptr, bp);
+    if (rc) return rc;
+    chunk_sum_kernel<<<H, 64, 0, s>>>(bp, nch, NACC, part);
+    particle_mean_pack_kernel<<<1, 256, 0, s>>>(part, H, d, K, out);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_shift_mean(double* mean, int H, int d, int base_action, const double* random_row, void* stream) {
+    MJB_REQUIRE(mean && H >= 1 && d >= 1, "mjb_shift_mean: bad argument");
+    if (base_action < 0 || base_action > 2)
+        return set_error(MJB_ENOTIMPL, "invalid option for base action during shift");   // olgaussian_mpc.py:129
+    MJB_REQUIRE(base_action != MJB_BASE_RANDOM || random_row, "base_action 'random' needs a random row");
+    shift_mean_kernel<<<1, 256, sizeof(double) * H * d, (cudaStream_t)stream>>>(mean, H, d, base_action, random_row);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_cov_add_diag(double* cov, int d, double beta, const double* v, void* stream) {
+    MJB_REQUIRE(cov && d >= 1 && d <= 32, "mjb_cov_add_diag: bad argument");
+    cov_add_diag_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(cov, d, beta, v);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_pf_shift(double* samples, long long sk, long long st, long long sj, const double* delta, long long dk,
+                            long long dt, long long dj, int K, int H, int d, int base_action, const double* random_row,
+                            void* stream) {
+    MJB_REQUIRE(samples && delta && K >= 1 && H >= 1 && d >= 1, "mjb_pf_shift: bad argument");
+    if (base_action < 0 || base_action > 2)
+        return set_error(MJB_ENOTIMPL, "invalid option for base action during shift");   // particle_filter_controller.py:148
+    MJB_REQUIRE(base_action != MJB_BASE_RANDOM || random_row, "base_action 'random' needs a random row");
+    pf_shift_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(samples, sk, st, sj, delta, dk, dt, dj, K, H, d, base_action, random_row);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_particle_sub_mean(const double* x, long long sk, long long st, long long sj, const double* mean, int K,
+                                     int H, int d, double* out, long long osk, long long ost, long long osj, void* stream) {
+    MJB_REQUIRE(x && mean && out && K >= 1 && H >= 1 && d >= 1, "mjb_particle_sub_mean: bad argument");
+    sub_mean_kernel<<<dim3((K + 255) / 256, H * d), 256, 0, (cudaStream_t)stream>>>(x, sk, st, sj, mean, K, H, d, out, osk, ost, osj);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}

@@ -1,0 +1,89 @@
+"""GPU counterparts of the reference's ``mjmpc/utils/control_utils.py`` hot-path helpers
+(``generate_noise`` :24-34, ``cost_to_go`` :37-46, ``scale_ctrl`` :3-12), same names and
+argument meaning, operating on CUDA tensors through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+NOISE_STREAM_ROLLOUT = 0      # stream ids (high 32 bits of the Philox offset)
+NOISE_STREAM_ACTION = 1
+NOISE_STREAM_SHIFT = 2
+NOISE_STREAM_BASE = 3
+
+
+def _dev(x, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float64)
+    return torch.as_tensor(np.asarray(x, np.float64), device=device)
+
+
+def particle_minor(K, H, d, device):
+    """(K,H,d)-shaped view of a freshly allocated (H,d,K) buffer: the layout every kernel
+    reads/writes coalesced across particles."""
+    return torch.empty((H, d, K), dtype=torch.float64, device=device).permute(2, 0, 1)
+
+
+def generate_noise(cov, filter_coeffs, shape, base_seed, *, step=0, stream_id=NOISE_STREAM_ROLLOUT,
+                   k_offset=0, K_global=None, zero_last_mean=None, out=None, device="cuda"):
+    """Correlated noise samples eps (K,H,d): N(0,cov) draws filtered along the horizon by
+    eps[:,i] = b0*eps[:,i] + b1*eps[:,i-1] + b2*eps[:,i-2], i >= 2 (control_utils.py:24-34).
+
+    ``base_seed`` keys the Philox generator and ``step`` plays the role of the reference's
+    ``+ num_steps`` reseeding (the same (seed, step) gives the same samples, as all n_iters of
+    one MPC step do in the reference).  ``k_offset``/``K_global`` place a shard inside the
+    global particle range; ``zero_last_mean`` applies olgaussian_mpc.py:110-111."""
+    K, H = int(shape[0]), int(shape[1])
+    cov = _dev(cov, device).contiguous()
+    d = cov.shape[0]
+    if out is None:
+        out = particle_minor(K, H, d, cov.device)
+    a = _lib.NoiseArgs()
+    a.K, a.H, a.d = K, H, d
+    a.k_offset = int(k_offset)
+    a.K_global = int(K_global if K_global is not None else k_offset + K)
+    a.seed = int(base_seed) & 0xFFFFFFFFFFFFFFFF
+    a.offset = ((int(stream_id) & 0xFFFFFFFF) << 32) | (int(step) & 0xFFFFFFFF)
+    a.cov = cov.data_ptr()
+    a.beta0, a.beta1, a.beta2 = [float(b) for b in filter_coeffs]
+    if zero_last_mean is not None:
+        zm = _dev(zero_last_mean, cov.device).contiguous()
+        a.zero_last, a.neg_mean = 1, zm.data_ptr()
+    a.out = out.data_ptr()
+    a.out_sk, a.out_st, a.out_sj = out.stride()
+    _lib.check(_lib.lib().mjb_generate_noise(C.byref(a), _lib.stream_ptr()))
+    return out
+
+
+def cost_to_go(cost_seq, gamma_seq, out=None):
+    """Discounted cost-to-go (control_utils.py:37-46), bit-identical to the reference's numpy
+    evaluation order.  cost_seq (K,H) CUDA tensor (any strides), gamma_seq (1,H) or (H,) host array."""
+    g = np.ascontiguousarray(np.asarray(gamma_seq, np.float64).reshape(-1))
+    K, H = cost_seq.shape
+    if g.shape[0] != H:
+        raise ValueError("gamma_seq has %d entries for horizon %d" % (g.shape[0], H))
+    if out is None:
+        out = torch.empty((H, K), dtype=torch.float64, device=cost_seq.device).t()
+    _lib.check(_lib.lib().mjb_cost_to_go(
+        _lib.ptr(cost_seq), _lib.c_ll(cost_seq.stride(0)), _lib.c_ll(cost_seq.stride(1)),
+        g.ctypes.data_as(_lib.c_double_p), C.c_int(K), C.c_int(H),
+        _lib.ptr(out), _lib.c_ll(out.stride(0)), _lib.c_ll(out.stride(1)), _lib.stream_ptr()))
+    return out
+
+
+def scale_ctrl(ctrl, action_low_limit, action_up_limit, squash_fn='clip'):
+    """control_utils.py:3-12 (no live caller on the hot path; kept for API parity)."""
+    if len(ctrl.shape) == 1:
+        ctrl = ctrl[None, :, None]
+    act_half_range = (action_up_limit - action_low_limit) / 2.0
+    act_mid_range = (action_up_limit + action_low_limit) / 2.0
+    if squash_fn == 'clip':
+        ctrl = ctrl.clip(-1.0, 1.0)
+    elif squash_fn == 'tanh':
+        ctrl = ctrl.tanh() if isinstance(ctrl, torch.Tensor) else np.tanh(ctrl)
+    return act_mid_range[None, :] + ctrl * act_half_range[None, :]

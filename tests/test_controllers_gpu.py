@@ -1,0 +1,286 @@
+"""Controller-update parity on the GPU (through the C ABI) against the reference's own outputs
+(golden vectors generated from /root/reference) on identical costs / actions.
+
+Tolerances: cost-to-go bit-exact; softmax weights, updated mean / covariance and values
+1e-10 relative (numpy sums pairwise, the GPU sums in a fixed two-stage order); elite index set,
+argmin index and resampling indices bit-exact."""
+import numpy as np
+import pytest
+
+from golden_util import load
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def _common(d=7):
+    return dict(d_state=25, d_obs=20, d_action=d, action_lows=-np.ones(d), action_highs=np.ones(d))
+
+
+def _traj(g):
+    import torch
+    K = g["costs"].shape[0]
+    # hand the controller what the GPU rollout returns: particle-minor device tensors
+    costs = torch.from_numpy(g["costs"]).cuda().t().contiguous().t()
+    actions = torch.from_numpy(g["actions"]).cuda().permute(1, 2, 0).contiguous().permute(2, 0, 1)
+    return dict(costs=costs, actions=actions)
+
+
+@pytest.mark.parametrize("name", ["ctg_g1", "ctg_g099", "ctg_g05", "ctg_g0"])
+def test_cost_to_go_bit_exact(name):
+    import torch
+    from mjmpc_b200.utils.control_utils import cost_to_go
+    g = load(name)
+    for layout in ("row", "particle_minor"):
+        c = torch.from_numpy(g["costs"]).cuda()
+        if layout == "particle_minor":
+            c = c.t().contiguous().t()
+        out = cost_to_go(c, g["gamma_seq"])
+        np.testing.assert_array_equal(out.cpu().numpy(), g["ctg"])
+
+
+@pytest.mark.parametrize("name", ["mppi_basic", "mppi_ctrlcost", "mppi_timebased", "mppi_tb_ctrlcost"])
+def test_mppi_update(name):
+    from mjmpc_b200.control import MPPI
+    g = load(name)
+    H = g["mean0"].shape[0]
+    K = g["costs"].shape[0]
+    c = MPPI(horizon=H, init_cov=0.8, base_action='null', lam=g["lam"], num_particles=K, step_size=g["step_size"],
+             alpha=int(g["alpha"]), gamma=g["gamma"], n_iters=1, time_based_weights=bool(g["time_based"]),
+             filter_coeffs=[0.25, 0.8, 0.0], seed=3, **_common())
+    c.mean_action = g["mean0"]
+    traj = _traj(g)
+    if not g["time_based"]:
+        assert c._calc_val(traj) == pytest.approx(g["value"], rel=RTOL)
+        np.testing.assert_array_equal(c.mean_action, g["mean0"])      # _calc_val leaves the distribution alone
+    c._update_distribution(traj)
+    np.testing.assert_allclose(c.mean_action, g["mean1"], rtol=RTOL, atol=1e-13)
+    c._shift()
+    np.testing.assert_allclose(c.mean_action, g["shifted"], rtol=RTOL, atol=1e-13)
+    assert np.all(c.mean_action[-1] == 0.0)
+
+
+def test_mppi_weights_match_reference():
+    import ctypes as C
+    import torch
+    from mjmpc_b200 import _lib
+    from mjmpc_b200.control import MPPI
+    g = load("mppi_ctrlcost")
+    H, K = g["mean0"].shape[0], g["costs"].shape[0]
+    c = MPPI(horizon=H, init_cov=0.8, base_action='null', lam=g["lam"], num_particles=K, step_size=g["step_size"],
+             alpha=0, gamma=g["gamma"], n_iters=1, **_common())
+    c.mean_action = g["mean0"]
+    traj = _traj(g)
+    stats = c._softmax_update(traj["costs"], traj["actions"], c.lam, control_cost=True, apply=False)
+    w = torch.empty(K, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().mjb_softmax_weights(_lib.ptr(c._last_total), C.c_int(K), _lib.ptr(stats), C.c_int(0),
+                                              C.c_double(c.lam), _lib.ptr(w), _lib.stream_ptr()))
+    np.testing.assert_allclose(w.cpu().numpy(), g["w"], rtol=RTOL, atol=1e-300)
+    assert abs(w.sum().item() - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["cem_diag", "cem_full"])
+def test_cem_update(name):
+    from mjmpc_b200.control import CEM
+    g = load(name)
+    H, K = g["mean0"].shape[0], g["costs"].shape[0]
+    c = CEM(horizon=H, init_cov=1.0, base_action='repeat', elite_frac=0.2, num_particles=K, step_size=g["step_size"],
+            gamma=g["gamma"], n_iters=1, beta=g["beta"], cov_type='full' if g["full"] else 'diagonal',
+            filter_coeffs=[0.25, 0.8, 0.0], seed=3, **_common())
+    assert c.num_elite == int(g["num_elite"])
+    c.mean_action = g["mean0"]
+    traj = _traj(g)
+    assert c._calc_val(traj) == pytest.approx(g["value"], rel=RTOL)
+    c._update_distribution(traj)
+    np.testing.assert_array_equal(c.elite_ids.cpu().numpy(), g["elite_ids"])     # bit-exact elite set
+    np.testing.assert_allclose(c.mean_action, g["mean1"], rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(c.cov_action, g["cov1"], rtol=RTOL, atol=1e-13)
+    c._shift()
+    np.testing.assert_allclose(c.mean_action, g["shifted"], rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(c.cov_action, g["cov_shifted"], rtol=RTOL, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["dmd_nocov", "dmd_diag", "dmd_full"])
+def test_dmd_update(name):
+    from mjmpc_b200.control import DMDMPC
+    g = load(name)
+    H, K = g["mean0"].shape[0], g["costs"].shape[0]
+    c = DMDMPC(horizon=H, init_cov=0.1, beta=g["beta"], base_action='null', lam=g["lam"], num_particles=K,
+               step_size=g["step_size"], gamma=g["gamma"], n_iters=1, update_cov=bool(g["update_cov"]),
+               cov_type='full' if g["full"] else 'diagonal', filter_coeffs=[0.25, 0.8, 0.0], seed=3, **_common())
+    c.mean_action = g["mean0"]
+    traj = _traj(g)
+    assert c._calc_val(traj) == pytest.approx(g["value"], rel=RTOL)
+    c._update_distribution(traj)
+    np.testing.assert_allclose(c.mean_action, g["mean1"], rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(c.cov_action, g["cov1"], rtol=RTOL, atol=1e-13)
+    c._shift()
+    np.testing.assert_allclose(c.mean_action, g["shifted"], rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(c.cov_action, g["cov_shifted"], rtol=RTOL, atol=1e-13)
+
+
+def test_random_shooting_update():
+    from mjmpc_b200.control import RandomShooting
+    g = load("rs")
+    H, K = g["mean0"].shape[0], g["costs"].shape[0]
+    c = RandomShooting(horizon=H, init_cov=1.0, base_action='null', num_particles=K, step_size=g["step_size"],
+                       gamma=g["gamma"], n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=3, **_common())
+    c.mean_action = g["mean0"]
+    c._update_distribution(_traj(g))
+    assert int(c.best_id.item()) == int(g["best_id"])                            # bit-exact argmin
+    np.testing.assert_allclose(c.mean_action, g["mean1"], rtol=RTOL, atol=1e-13)
+
+
+def test_argmin_first_occurrence_and_elite_ties():
+    """Ties: np.argmin returns the first minimum; the elite contract breaks ties by lower index."""
+    import torch
+    from mjmpc_b200 import _lib
+    v = np.array([3.0, 1.0, 2.0, 1.0, 5.0, 1.0, 2.0, 0.5, 0.5, 7.0] * 300)
+    t = torch.from_numpy(v).cuda()
+    idx = torch.empty(1, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.lib().mjb_argmin(_lib.ptr(t), _lib.c_ll(len(v)), _lib.ptr(idx), None, _lib.stream_ptr()))
+    assert idx.item() == int(np.argmin(v)) == 7
+    for E in (1, 2, 299, 600, 601, 950, 1500, len(v)):
+        flags = torch.empty(len(v), dtype=torch.uint8, device="cuda")
+        ids = torch.empty(E, dtype=torch.int64, device="cuda")
+        _lib.check(_lib.lib().mjb_select_elites(_lib.ptr(t), _lib.c_ll(len(v)), _lib.c_ll(E), _lib.ptr(flags),
+                                                _lib.ptr(ids), None, _lib.stream_ptr()))
+        want = np.sort(np.argsort(v, kind="stable")[:E])                         # stable sort = lower index first
+        np.testing.assert_array_equal(ids.cpu().numpy(), want)
+        assert flags.sum().item() == E
+
+
+def test_elite_select_negative_and_large():
+    import torch
+    from mjmpc_b200 import _lib
+    rng = np.random.default_rng(5)
+    v = np.concatenate([rng.normal(0, 100, 70000), [-np.inf, np.inf, 0.0, -0.0]])
+    t = torch.from_numpy(v).cuda()
+    E = 13107
+    flags = torch.empty(len(v), dtype=torch.uint8, device="cuda")
+    ids = torch.empty(E, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.lib().mjb_select_elites(_lib.ptr(t), _lib.c_ll(len(v)), _lib.c_ll(E), _lib.ptr(flags), _lib.ptr(ids),
+                                            None, _lib.stream_ptr()))
+    np.testing.assert_array_equal(ids.cpu().numpy(), np.sort(np.argsort(v, kind="stable")[:E]))
+
+
+def test_pfmpc_resampling_bit_exact():
+    from mjmpc_b200.control import PFMPC
+    import torch
+    g = load("pf")
+    Kp, H, d = g["samples0"].shape
+    c = PFMPC(horizon=H, cov_shift=0.1, cov_resample=1.0, base_action='null', lam=g["lam"], num_particles=Kp,
+              gamma=1.0, n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=int(g["seed"]), **_common())
+    c.action_samples = g["samples0"]
+    c.num_steps = int(g["num_steps"])
+    # weights from the same costs must agree to 1e-10 ...
+    w = c._weights(torch.from_numpy(g["costs"]).cuda())
+    np.testing.assert_allclose(w.cpu().numpy(), g["w"], rtol=RTOL)
+    # ... and bit-identical weights must give bit-identical indices (index tests are not driven through
+    # exp() whose last ulp differs between libraries -- SURVEY 8c)
+    import random
+    random.seed(int(g["seed"]) + int(g["num_steps"]))
+    new = c._resampling(c._samples, torch.from_numpy(g["w"]).cuda())
+    np.testing.assert_array_equal(c.resample_ids.cpu().numpy(), g["ids"])
+    np.testing.assert_array_equal(new.cpu().numpy(), g["samples1"])
+    c._samples = new
+    c._update_mean()
+    np.testing.assert_allclose(c.mean_action, g["mean1"], rtol=RTOL, atol=1e-14)
+
+
+def test_resample_skewed_weights():
+    import ctypes as C
+    import torch
+    from mjmpc_b200 import _lib
+    g = load("pf_skewed")
+    M = len(g["w"])
+    w = torch.from_numpy(g["w"]).cuda()
+    cs = torch.empty(M, dtype=torch.float64, device="cuda")
+    idx = torch.empty(M, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.lib().mjb_resample_indices(_lib.ptr(w), _lib.c_ll(M), C.c_double(float(g["r"])), _lib.ptr(cs),
+                                               _lib.ptr(idx), _lib.stream_ptr()))
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["ids"])
+    np.testing.assert_array_equal(cs.cpu().numpy(), np.cumsum(g["w"]))           # sequential order
+
+
+def test_pfmpc_shift():
+    from mjmpc_b200.control import PFMPC
+    H, d, K = 8, 7, 64
+    for base in ("null", "repeat"):
+        c = PFMPC(horizon=H, cov_shift=0.1, cov_resample=1.0, base_action=base, lam=0.5, num_particles=K, gamma=1.0,
+                  n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=1, **_common())
+        s0 = c.action_samples
+        c.num_steps = 3
+        c._shift()
+        s1 = c.action_samples
+        delta = c._buffers[("delta", (H, d, K), __import__("torch").float64)].permute(2, 0, 1).cpu().numpy()
+        np.testing.assert_array_equal(s1[:, :-2], s0[:, 1:-1] + delta[:, :-2])
+        if base == "null":
+            assert np.all(s1[:, -1] == 0.0)
+        else:
+            np.testing.assert_array_equal(s1[:, -1], s1[:, -2])
+    with pytest.raises(NotImplementedError):
+        c.base_action = "bogus"
+        c._shift()
+
+
+def test_sharded_updates_equal_unsharded():
+    """N logical shards on one device: phase-1 partials per slice, combined in rank order, must reproduce
+    the unsharded update (the multi-GPU path without a cluster)."""
+    import ctypes as C
+    import torch
+    from mjmpc_b200 import _lib
+    from mjmpc_b200.control import MPPI
+    from mjmpc_b200.utils.shard import ShardContext
+    g = load("mppi_ctrlcost")
+    H, K = g["mean0"].shape[0], g["costs"].shape[0]
+    traj = _traj(g)
+
+    class FakeShard(ShardContext):
+        """Rank r of N; all_gather returns the partials every rank computed (recorded by the test)."""
+        bank = {}
+
+        def all_gather(self, t):
+            key = tuple(t.shape)
+            FakeShard.bank.setdefault(key, {})[self.rank] = t.clone()
+            if len(FakeShard.bank[key]) < self.world_size:
+                return torch.stack([t] * self.world_size)          # placeholder until all ranks have run
+            return torch.stack([FakeShard.bank[key][r] for r in range(self.world_size)])
+
+    for N in (2, 4):
+        FakeShard.bank = {}
+        ctrls = []
+        for pass_ in range(2):          # pass 0 fills the bank, pass 1 combines real partials
+            ctrls = []
+            for r in range(N):
+                c = MPPI(horizon=H, init_cov=0.8, base_action='null', lam=g["lam"], num_particles=K,
+                         step_size=g["step_size"], alpha=0, gamma=g["gamma"], n_iters=1, shard=FakeShard(r, N),
+                         **_common())
+                c.mean_action = g["mean0"]
+                per = K // N
+                sl = dict(costs=traj["costs"][r * per:(r + 1) * per], actions=traj["actions"][r * per:(r + 1) * per])
+                c._update_distribution(sl)
+                ctrls.append(c)
+        for c in ctrls:
+            np.testing.assert_allclose(c.mean_action, g["mean1"], rtol=RTOL, atol=1e-13)
+        for c in ctrls[1:]:
+            np.testing.assert_array_equal(c.mean_action, ctrls[0].mean_action)   # identical on every rank
+
+
+def test_bad_options_raise():
+    from mjmpc_b200.control import MPPI, DMDMPC
+    from mjmpc_b200.policies import MPCPolicy
+    g = load("mppi_basic")
+    H, K = g["mean0"].shape[0], g["costs"].shape[0]
+    c = MPPI(horizon=H, init_cov=0.8, base_action='bogus', lam=0.2, num_particles=K, step_size=1.0, alpha=1,
+             gamma=1.0, n_iters=1, **_common())
+    with pytest.raises(NotImplementedError):
+        c._shift()
+    with pytest.raises(ValueError):
+        c._get_next_action(None, mode='bogus')
+    dm = DMDMPC(horizon=H, init_cov=0.1, beta=0.1, base_action='null', lam=0.2, num_particles=K, step_size=1.0,
+                gamma=1.0, n_iters=1, update_cov=True, cov_type='bogus', **_common())
+    with pytest.raises(ValueError):
+        dm._update_distribution(_traj(g))
+    with pytest.raises(NotImplementedError):
+        MPCPolicy("ilqr", {})

@@ -1,0 +1,195 @@
+"""CPU-only checks (-m "not gpu"): the model compiler, the oracle's physics, the product's device math
+compiled for the host against the oracle, and that the C-ABI library loads and exports every symbol the
+header declares."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, reference_noise, synthetic_state
+
+
+# ---- model compiler -----------------------------------------------------------------------------------
+def test_model_matches_survey_data_sheet(compiled_model):
+    """SURVEY Appendix A (derived independently at survey time from sawyer.xml)."""
+    t = compiled_model.tree
+    np.testing.assert_allclose(t.mass, [24.3117, 10.4720, 0.2848, 5.4287, 1.3572, 0.2848, 2.8091, 0.0168, 2.1447], atol=6e-5)
+    np.testing.assert_allclose(t.ipos[0], [0, 0.00299, -0.08429], atol=1e-5)
+    np.testing.assert_allclose(t.ipos[3], [0.2, 0, 0], atol=1e-12)
+    np.testing.assert_allclose(t.ipos[6], [0.1455, 0, 0], atol=1e-12)
+    np.testing.assert_allclose(np.diag(t.inertia[1]), [0.126711, 0.048171, 0.126711], atol=1e-6)
+    np.testing.assert_allclose(np.diag(t.inertia[3]), [0.009446, 0.110027, 0.110027], atol=1e-6)
+    np.testing.assert_allclose(np.diag(t.inertia[8]), [0.005490] * 3, atol=1e-6)
+    assert compiled_model.chain.axes == (2, 1, 0, 1, 0, 1, 0)
+    np.testing.assert_allclose(t.gear, [20, 10, 10, 10, 10, 10, 10])
+    np.testing.assert_allclose(t.damping, [2, 2, .8, .8, .8, .8, .8])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/mjmpc/envs/assets/xml/sawyer.xml"),
+                    reason="reference tree not mounted (GPU box)")
+def test_builtin_spec_equals_reference_mjcf(compiled_model):
+    """The built-in reacher spec is pinned to the reference's MJCF: parsing sawyer.xml gives the same block."""
+    from mjmpc_b200.envs.mjcf import load_mjcf
+    from mjmpc_b200.envs.model import compile_model
+    ref = compile_model(load_mjcf("/root/reference/mjmpc/envs/assets/xml/sawyer.xml"))
+    np.testing.assert_array_equal(ref.chain.params, compiled_model.chain.params)
+    assert ref.chain.axes == compiled_model.chain.axes
+    np.testing.assert_array_equal(ref.tree.dof_invweight0, compiled_model.tree.dof_invweight0)
+
+
+def test_param_layout_matches_header():
+    """The Python CH_* offsets mirror csrc/chain_model.h."""
+    from mjmpc_b200.envs import model as M
+    from mjmpc_b200 import _lib
+    src = r'''
+    #include <stdio.h>
+    #include "mjmpc_b200/csrc/chain_model.h"
+    #include "include/mjmpc_b200.h"
+    int main(){printf("%d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d %d\n", CH_OFF, CH_MASS, CH_COM, CH_INERTIA,
+      CH_ARMATURE, CH_DAMPING, CH_GEAR, CH_CTRL_LO, CH_CTRL_HI, CH_RANGE_LO, CH_RANGE_HI, CH_INVW0, CH_SCALARS,
+      CH_NPARAM, MJB_MODEL_NPARAM, MJB_STATE_DIM, MJB_OBS_DIM); return 0;}'''
+    exe = os.path.join(ROOT, "tests", "hostcheck", "layout_probe")
+    subprocess.run(["gcc", "-x", "c", "-", "-I", ROOT, "-o", exe], input=src.encode(), cwd=ROOT, check=True)
+    vals = [int(x) for x in subprocess.check_output([exe]).split()]
+    want = [M.CH_OFF, M.CH_MASS, M.CH_COM, M.CH_INERTIA, M.CH_ARMATURE, M.CH_DAMPING, M.CH_GEAR, M.CH_CTRL_LO,
+            M.CH_CTRL_HI, M.CH_RANGE_LO, M.CH_RANGE_HI, M.CH_INVW0, M.CH_SCALARS, M.CH_NPARAM, _lib.MODEL_NPARAM,
+            _lib.STATE_DIM, _lib.OBS_DIM]
+    assert vals == want
+
+
+def test_randomized_copy_follows_reference_rule(compiled_model):
+    """gym_env_wrapper.py:408-410: U(biased*(1-noise), biased*(1+noise)), defaults cached, repeated calls
+    re-randomise around the original."""
+    from mjmpc_b200.envs.model import randomized_copy
+    rng = np.random.RandomState(3)
+    pd = dict(body_mass={"r_forearm_link": [0.3, 0.1]}, dof_damping={"r_elbow_flex_joint": [0.0, -0.5]})
+    m1, defaults, rnd = randomized_copy(compiled_model, pd, rng)
+    base = compiled_model.tree.mass[6]
+    assert defaults["body_mass"]["r_forearm_link"] == base
+    assert 1.1 * base * 0.7 <= rnd["body_mass"]["r_forearm_link"] <= 1.1 * base * 1.3
+    assert rnd["dof_damping"]["r_elbow_flex_joint"] == pytest.approx(0.4)
+    m2, defaults2, rnd2 = randomized_copy(m1, pd, rng, defaults)
+    assert defaults2["body_mass"]["r_forearm_link"] == base               # not overwritten
+    assert 1.1 * base * 0.7 <= rnd2["body_mass"]["r_forearm_link"] <= 1.1 * base * 1.3
+    np.testing.assert_array_equal(m1.tree.dof_invweight0, compiled_model.tree.dof_invweight0)
+    with pytest.raises(ValueError):
+        randomized_copy(compiled_model, dict(bogus={"x": [0.1, 0.1]}), rng)
+
+
+# ---- oracle physics (no MuJoCo available: two independent derivations + invariants) ----------------------
+def test_oracle_matches_lagrangian_derivation(compiled_model, oracle_model):
+    from oracle import lagrange
+    rng = np.random.default_rng(1)
+    for _ in range(4):
+        q = rng.uniform(-2, 2, 7); v = rng.normal(0, 3, 7)
+        M, b, _ = oracle_model.mass_bias(q, v)
+        M2, c2 = lagrange.mass_bias(compiled_model.tree, q, v)
+        np.testing.assert_allclose(M, M2, atol=1e-13)
+        np.testing.assert_allclose(b, c2, atol=1e-12 * max(1.0, np.abs(c2).max()))
+        assert np.linalg.eigvalsh(M).min() > 0
+        np.testing.assert_allclose(M, M.T, atol=0)
+
+
+def test_oracle_energy_conservation(compiled_model):
+    """damping=0, ctrl=0, gravity=0, limits off: kinetic energy is conserved to O(h)."""
+    import copy
+    from oracle import mjstep
+    tree = copy.deepcopy(compiled_model.tree)
+    tree.damping[:] = 0.0
+    tree.jnt_limited[:] = 0
+    tree.con_radius = -1.0
+    om = mjstep.OracleModel(tree)
+    q = np.array([0.1, 0.2, -0.3, -0.5, 0.4, -0.2, 0.3]); v = np.array([0.5, -0.4, 0.8, 0.6, -0.7, 0.9, -0.5])
+    M, _, _ = om.mass_bias(q, v)
+    e0 = 0.5 * v @ M @ v
+    for _ in range(50):
+        q, v, _, n = om.substep(q, v, np.zeros(7))
+        assert n == 0
+    M, _, _ = om.mass_bias(q, v)
+    assert abs(0.5 * v @ M @ v - e0) / e0 < 0.02
+
+
+def test_oracle_limits_and_contact_hold(compiled_model, oracle_model):
+    from oracle import mjstep
+    K, H = 256, 32
+    noise = reference_noise(K, H, 7, 1)
+    out = mjstep.rollout(oracle_model, np.zeros(7), np.zeros(7), np.array([.1, .1, .1]), np.zeros((H, 7)), noise,
+                         want_traj=True, nthreads=4)
+    q = out["qv"][:, :, :7]
+    lo, hi = compiled_model.tree.jnt_range[:, 0], compiled_model.tree.jnt_range[:, 1]
+    assert (q - hi).max() < 0.3 and (lo - q).max() < 0.3                   # soft limits: bounded violation
+    assert (out["ncon"] > 0).mean() > 0.5
+    # pushing down onto the table: the soft contact stops the sphere near the plane
+    mean = np.zeros((H, 7)); mean[:, 1] = 1.0
+    out = mjstep.rollout(oracle_model, np.array([0.0, 0.45, 0, -0.2, 0, -0.3, 0.0]), np.zeros(7),
+                         np.array([.1, .1, .1]), mean, 0.3 * noise, want_obs=True)
+    hz = out["next_observations"][:, :, 16]
+    assert hz.min() < -0.345 and hz.min() > -0.40
+
+
+# ---- the product's device math, compiled for the host, against the oracle ---------------------------------
+@pytest.fixture(scope="module")
+def hostcheck():
+    so = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
+    src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src, "-lm"])
+    return C.CDLL(so)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.mark.parametrize("case", ["interior", "reset", "table"])
+def test_device_math_on_host_matches_oracle(case, compiled_model, oracle_model, hostcheck):
+    from oracle import mjstep
+    P = compiled_model.chain.params
+    assert hostcheck.hostcheck_fits_sawyer(_p(P)) == 1
+    K, H = 192, 32
+    noise = reference_noise(K, H, 7, 5)
+    mean = np.zeros((H, 7))
+    if case == "interior":
+        st = synthetic_state(compiled_model, 3)
+        q0, v0 = st["qp"], st["qv"]
+    elif case == "reset":
+        q0, v0 = np.zeros(7), np.zeros(7)
+    else:
+        q0, v0 = np.array([0.0, 0.45, 0, -0.2, 0, -0.3, 0.0]), np.zeros(7)
+        mean[:, 1] = 1.0
+        noise = 0.3 * noise
+    tgt = np.array([0.1, 0.1, 0.1])
+    ref = mjstep.rollout(oracle_model, q0, v0, tgt, mean, noise, want_traj=True, nthreads=4)
+    for dense in (0, 1):
+        costs = np.zeros((K, H)); qv = np.zeros((K, H, 14))
+        hostcheck.hostcheck_rollout(_p(P), dense, _p(q0), _p(v0), _p(tgt), K, H, _p(mean), _p(noise), _p(costs), _p(qv))
+        scale = np.abs(ref["qv"]).max(axis=(0, 1))
+        assert (np.abs(qv - ref["qv"]).max(axis=(0, 1)) / scale).max() < 1e-9
+        np.testing.assert_allclose(costs, ref["costs"], rtol=1e-10)
+
+
+# ---- C ABI ------------------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    from mjmpc_b200 import _lib, build
+    build.build()
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "mjmpc_b200.h")).read()
+    declared = set(re.findall(r"\b(mjb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert declared == set(_lib.EXPORTS)
+    assert L.mjb_version() >= 100
+    assert L.mjb_softmax_partial_doubles(32, 7, 0, 0) == 1 + 32 * 8
+    assert L.mjb_softmax_partial_doubles(32, 7, 1, 0) == 32 + 32 * 8
+    assert L.mjb_softmax_partial_doubles(16, 7, 0, 2) == 1 + 16 * (8 + 28)
+
+
+def test_product_never_imports_the_oracle():
+    for dp, _, files in os.walk(os.path.join(ROOT, "mjmpc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
