@@ -1,6 +1,6 @@
 // Articulated-body step for a serial chain of 7 axis-aligned hinge joints, one particle per
-// thread, every loop unrolled at compile time so q, v, M and the recursion state live in
-// registers.  Replaces, for the reacher_7dof model, what the reference reaches through
+// thread, the kinematic recursions unrolled at compile time so q, v, M and the recursion state
+// live in registers.  Replaces, for the reacher_7dof model, what the reference reaches through
 //   GymEnvWrapper.rollout          mjmpc/envs/gym_env_wrapper.py:125-153
 //   Reacher7DOFEnv.step            mjmpc/envs/basic/reacher_env.py:29-39
 //   -> mjrl do_simulation -> mujoco_py MjSim.step -> MuJoCo mj_step   (not in the reference tree)
@@ -11,8 +11,14 @@
 //   * soft joint limits / sphere-plane contact: exact minimiser of MuJoCo's convex
 //     constraint objective by Newton steps on the active set (M + diag(D) + Dc Jc Jc'),
 //   * semi-implicit Euler with implicit joint damping: (M + h B) a = f + f_constraint.
-// Joint axes are template constants, rotations are 2x2 Givens updates, and structurally
-// zero offsets / centre-of-mass components are skipped through the Traits masks.
+// Joint axes are template constants, rotations are 2x2 Givens updates, and structurally zero
+// offsets / centre-of-mass components / inertia products are skipped through the Traits masks.
+//
+// Code size matters as much as FLOPs here: with 255 registers per thread only 8 warps share an
+// SM, so the loop body has to stay inside the instruction cache (the first version of this file
+// inlined 140 KB of SASS and spent 7 of every 8 issue slots waiting for instructions).  Hence one
+// shared factor/solve site for the Newton and Euler solves, a rolled line search, and a compact
+// sincos for the bounded joint angles.
 #pragma once
 #include <math.h>
 #include <utility>
@@ -20,11 +26,21 @@
 
 #if defined(__CUDACC__)
 #define MJB_HD __host__ __device__ __forceinline__
+#define MJB_NOINLINE static __host__ __device__ __noinline__
 #else
 #define MJB_HD inline
+#define MJB_NOINLINE __attribute__((noinline)) inline
 #endif
 
 namespace mjb {
+
+#if defined(MJB_HOST_STATS)
+// host test harness only: solver statistics [substeps, substeps with rows, factor/solve passes, line searches]
+static long long g_stats[4] = {0, 0, 0, 0};
+#define MJB_STAT(i) (g_stats[i]++)
+#else
+#define MJB_STAT(i) ((void)0)
+#endif
 
 struct V3 { double x, y, z; };
 struct S3 { double xx, yy, zz, xy, xz, yz; };
@@ -33,12 +49,24 @@ MJB_HD V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
 MJB_HD V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 MJB_HD V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
 MJB_HD V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
-MJB_HD double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-MJB_HD V3 mul(const S3& I, V3 w) {
-    return {I.xx * w.x + I.xy * w.y + I.xz * w.z, I.xy * w.x + I.yy * w.y + I.yz * w.z,
-            I.xz * w.x + I.yz * w.y + I.zz * w.z};
-}
 template <int AX> MJB_HD double comp(V3 v) { return AX == 0 ? v.x : (AX == 1 ? v.y : v.z); }
+
+// a x b where b's components outside MASK are structurally zero (bit k = component k)
+template <int MASK> MJB_HD V3 cross_m(V3 a, V3 b) {
+    V3 r = {0.0, 0.0, 0.0};
+    if constexpr (MASK & 1) { r.y += a.z * b.x; r.z -= a.y * b.x; }
+    if constexpr (MASK & 2) { r.x -= a.z * b.y; r.z += a.x * b.y; }
+    if constexpr (MASK & 4) { r.x += a.y * b.z; r.y -= a.x * b.z; }
+    return r;
+}
+// I w for a symmetric 3x3; FULL = false: diagonal only
+template <bool FULL> MJB_HD V3 mul_s(const S3& I, V3 w) {
+    if constexpr (FULL)
+        return {I.xx * w.x + I.xy * w.y + I.xz * w.z, I.xy * w.x + I.yy * w.y + I.yz * w.z,
+                I.xz * w.x + I.yz * w.y + I.zz * w.z};
+    else
+        return {I.xx * w.x, I.yy * w.y, I.zz * w.z};
+}
 
 // v <- R v, R = rotation by angle (s = sin, c = cos) about coordinate axis AX (child -> parent frame)
 template <int AX> MJB_HD V3 rot(V3 v, double s, double c) {
@@ -74,6 +102,28 @@ template <class F, int... Is> MJB_HD void static_for_impl(F&& f, std::integer_se
 }
 template <int N, class F> MJB_HD void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
 
+// sin and cos of a joint angle.  Joint angles are bounded by the (soft) joint limits, so a two-term
+// Cody-Waite reduction by pi/2 and the fdlibm kernel polynomials on [-pi/4, pi/4] are accurate to
+// ~1 ulp for |x| < 1e5 rad; there is no huge-argument path.
+MJB_HD void sincos_joint(double x, double& s, double& c) {
+    const double kd = rint(x * 6.36619772367581382433e-01);          // x * 2/pi
+    double r = fma(kd, -1.57079632673412561417e+00, x);              // pi/2, first 33 bits
+    r = fma(kd, -6.07710050650619224932e-11, r);                     // pi/2 tail
+    const double z = r * r;
+    const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08),
+                                                2.75573137070700676789e-06), -1.98412698298579493134e-04),
+                                 8.33333333332248946124e-03), -1.66666666666666324348e-01);
+    const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09),
+                                                -2.75573143513906633035e-07), 2.48015872894767294178e-05),
+                                 -1.38888888888741095749e-03), 4.16666666666666019037e-02);
+    const double sr = fma(z * r, ps, r);
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const int k = (int)kd;
+    const double a = (k & 1) ? cr : sr, b = (k & 1) ? sr : cr;
+    s = (k & 2) ? -a : a;
+    c = ((k + 1) & 2) ? -b : b;
+}
+
 // Structure of the reference's arm (sawyer.xml:15-59): axes z,y,x,y,x,y,x; after merging the two
 // welded bodies, link offsets are (x,0,0) or 0 and COMs are on the link x axis (or at the origin),
 // so inertias about the link origin stay diagonal for links 1..6.  Bit k of a mask = component k.
@@ -96,15 +146,6 @@ template <class T, int I, class P> MJB_HD V3 link_offset(const P& prm) {
     return {(m & 1) ? prm[CH_OFF + 3 * I] : 0.0, (m & 2) ? prm[CH_OFF + 3 * I + 1] : 0.0,
             (m & 4) ? prm[CH_OFF + 3 * I + 2] : 0.0};
 }
-// o x f with masked offset components
-template <class T, int I, class P> MJB_HD V3 off_cross(const P& prm, V3 f) {
-    constexpr int m = T::off_mask(I);
-    V3 r = {0.0, 0.0, 0.0};
-    if constexpr (m & 1) { const double ox = prm[CH_OFF + 3 * I]; r.y -= ox * f.z; r.z += ox * f.y; }
-    if constexpr (m & 2) { const double oy = prm[CH_OFF + 3 * I + 1]; r.x += oy * f.z; r.z -= oy * f.x; }
-    if constexpr (m & 4) { const double oz = prm[CH_OFF + 3 * I + 2]; r.x -= oz * f.y; r.y += oz * f.x; }
-    return r;
-}
 template <class T, int I, class P> MJB_HD V3 link_h(const P& prm) {
     constexpr int m = T::com_mask(I);
     return {(m & 1) ? prm[CH_H + 3 * I] : 0.0, (m & 2) ? prm[CH_H + 3 * I + 1] : 0.0,
@@ -117,39 +158,52 @@ template <class T, int I, class P> MJB_HD S3 link_inertia_o(const P& prm) {
     else { s.xy = 0.0; s.xz = 0.0; s.yz = 0.0; }
     return s;
 }
-// a x h and w x (w x h) with masked h
-template <class T, int I> MJB_HD V3 cross_h(V3 a, V3 h) {
-    constexpr int m = T::com_mask(I);
-    V3 r = {0.0, 0.0, 0.0};
-    if constexpr (m & 1) { r.y += a.z * h.x; r.z -= a.y * h.x; }
-    if constexpr (m & 2) { r.x -= a.z * h.y; r.z += a.x * h.y; }
-    if constexpr (m & 4) { r.x += a.y * h.z; r.y -= a.x * h.z; }
-    return r;
+// p + o with masked o
+template <int MASK> MJB_HD V3 add_m(V3 p, V3 o) {
+    if constexpr (MASK & 1) p.x += o.x;
+    if constexpr (MASK & 2) p.y += o.y;
+    if constexpr (MASK & 4) p.z += o.z;
+    return p;
 }
 
+// Per-particle scratch outside the register file.  Values with a long life and a single use (the
+// link wrenches between the two Newton-Euler passes, M between its construction and the solves, the
+// contact Jacobian, the control held over both substeps) are parked here explicitly instead of
+// being spilled by the compiler: on the device a slot is one column of shared memory
+// (slot * BLOCK + thread: conflict-free), on the host a plain array.
+enum { SC_LF = 0, SC_LN = 18, SC_M = 36, SC_JC = 64, SC_U = 71, SC_NSLOT = 78 };
+MJB_HD constexpr int sc_m(int i, int j) { return SC_M + i * (i + 1) / 2 + j; }   // lower triangle, i >= j
+
+struct HostScratch {
+    double buf[SC_NSLOT];
+    double ld(int slot) const { return buf[slot]; }
+    void st(int slot, double v) { buf[slot] = v; }
+};
+
 // ---------------------------------------------------------------------------------------------
-// M(q) lower triangle (with armature) and bias(q,v).  sn/cs = sin/cos of the joint angles.
+// M(q) lower triangle (with armature) -> scratch, and bias(q,v).  sn/cs = sin/cos of the joint angles.
 // ---------------------------------------------------------------------------------------------
-template <class T, class P>
-MJB_HD void chain_mass_bias(const P& prm, const double (&sn)[7], const double (&cs)[7], const double (&qd)[7],
-                            double (&M)[7][7], double (&bias)[7]) {
-    // ---- recursive Newton-Euler, outward pass: link velocities / bias accelerations -> link wrenches
-    V3 lf[7], ln[7];
+template <class T, class P, class S>
+MJB_HD void chain_mass_bias(const P& prm, S& sc, const double (&sn)[7], const double (&cs)[7], const double (&qd)[7],
+                            double (&bias)[7]) {
+    // ---- recursive Newton-Euler, outward pass: link velocities / bias accelerations -> link wrenches.
+    // Link 0 hangs off the fixed base: its own wrench never reaches a joint axis (its z torque is
+    // zero and it has no parent), so only its angular velocity is carried on.
     {
         V3 w = {0, 0, 0}, al = {0, 0, 0}, ac = {0, 0, 0};
         static_for<7>([&](auto Ic) {
             constexpr int i = decltype(Ic)::value;
             constexpr int AX = T::axis(i);
+            constexpr int OM = T::off_mask(i), CM = T::com_mask(i);
             if constexpr (i == 0) {
-                // fixed base: only the joint's own rate
                 w = {AX == 0 ? qd[0] : 0.0, AX == 1 ? qd[0] : 0.0, AX == 2 ? qd[0] : 0.0};
             } else {
-                const V3 o = link_offset<T, i>(prm);
                 // acceleration of this joint's origin, parent frame: a + al x o + w x (w x o)
                 V3 ao = ac;
-                if constexpr (T::off_mask(i) != 0) {
-                    const V3 wxo = cross(w, o);
-                    ao = ao + cross(al, o) + cross(w, wxo);
+                if constexpr (OM != 0) {
+                    const V3 o = link_offset<T, i>(prm);
+                    const V3 wxo = cross_m<OM>(w, o);
+                    ao = ao + cross_m<OM>(al, o) + cross(w, wxo);
                 }
                 const V3 wp = rotT<AX>(w, sn[i], cs[i]);
                 const V3 alp = rotT<AX>(al, sn[i], cs[i]);
@@ -159,19 +213,20 @@ MJB_HD void chain_mass_bias(const P& prm, const double (&sn)[7], const double (&
                 if constexpr (AX == 0) { al = {alp.x, alp.y + wp.z * r, alp.z - wp.y * r}; w = {wp.x + r, wp.y, wp.z}; }
                 else if constexpr (AX == 1) { al = {alp.x - wp.z * r, alp.y, alp.z + wp.x * r}; w = {wp.x, wp.y + r, wp.z}; }
                 else { al = {alp.x + wp.y * r, alp.y - wp.x * r, alp.z}; w = {wp.x, wp.y, wp.z + r}; }
+                // wrench about the link origin: f = m a + al x h + w x (w x h); n = I al + w x (I w) + h x a
+                const S3 Io = link_inertia_o<T, i>(prm);
+                const double m = prm[CH_MASS + i];
+                V3 f = m * ac;
+                V3 n = mul_s<T::full_inertia(i)>(Io, al) + cross(w, mul_s<T::full_inertia(i)>(Io, w));
+                if constexpr (CM != 0) {
+                    const V3 h = link_h<T, i>(prm);
+                    const V3 wxh = cross_m<CM>(w, h);
+                    f = f + cross_m<CM>(al, h) + cross(w, wxh);
+                    n = n - cross_m<CM>(ac, h);   // h x a = -(a x h)
+                }
+                sc.st(SC_LF + 3 * (i - 1), f.x); sc.st(SC_LF + 3 * (i - 1) + 1, f.y); sc.st(SC_LF + 3 * (i - 1) + 2, f.z);
+                sc.st(SC_LN + 3 * (i - 1), n.x); sc.st(SC_LN + 3 * (i - 1) + 1, n.y); sc.st(SC_LN + 3 * (i - 1) + 2, n.z);
             }
-            // wrench about the link origin: f = m a + al x h + w x (w x h); n = I al + w x (I w) + h x a
-            const V3 h = link_h<T, i>(prm);
-            const S3 Io = link_inertia_o<T, i>(prm);
-            const double m = prm[CH_MASS + i];
-            V3 f = m * ac;
-            V3 n = mul(Io, al) + cross(w, mul(Io, w));
-            if constexpr (T::com_mask(i) != 0) {
-                const V3 wxh = cross_h<T, i>(w, h);
-                f = f + cross_h<T, i>(al, h) + cross(w, wxh);
-                n = n - cross_h<T, i>(ac, h);   // h x a = -(a x h)
-            }
-            lf[i] = f; ln[i] = n;
         });
     }
     // ---- inward pass: accumulate child wrenches, project on the joint axis
@@ -180,12 +235,15 @@ MJB_HD void chain_mass_bias(const P& prm, const double (&sn)[7], const double (&
         static_for<7>([&](auto Ic) {
             constexpr int i = 6 - decltype(Ic)::value;
             constexpr int AX = T::axis(i);
-            fa = fa + lf[i];
-            na = na + ln[i];
+            if constexpr (i > 0) {
+                fa = fa + V3{sc.ld(SC_LF + 3 * (i - 1)), sc.ld(SC_LF + 3 * (i - 1) + 1), sc.ld(SC_LF + 3 * (i - 1) + 2)};
+                na = na + V3{sc.ld(SC_LN + 3 * (i - 1)), sc.ld(SC_LN + 3 * (i - 1) + 1), sc.ld(SC_LN + 3 * (i - 1) + 2)};
+            }
             bias[i] = comp<AX>(na);
             if constexpr (i > 0) {
                 fa = rot<AX>(fa, sn[i], cs[i]);
-                na = rot<AX>(na, sn[i], cs[i]) + off_cross<T, i>(prm, fa);
+                na = rot<AX>(na, sn[i], cs[i]);
+                if constexpr (T::off_mask(i) != 0) na = na - cross_m<T::off_mask(i)>(fa, link_offset<T, i>(prm));   // o x f
             }
         });
     }
@@ -199,48 +257,78 @@ MJB_HD void chain_mass_bias(const P& prm, const double (&sn)[7], const double (&
             constexpr int AX = T::axis(i);
             // add link i's own inertia (composite is expressed in frame i here)
             {
-                const V3 h = link_h<T, i>(prm);
                 const S3 Io = link_inertia_o<T, i>(prm);
                 cm += prm[CH_MASS + i];
-                ch = ch + h;
-                cI.xx += Io.xx; cI.yy += Io.yy; cI.zz += Io.zz; cI.xy += Io.xy; cI.xz += Io.xz; cI.yz += Io.yz;
+                if constexpr (T::com_mask(i) != 0) ch = add_m<T::com_mask(i)>(ch, link_h<T, i>(prm));
+                cI.xx += Io.xx; cI.yy += Io.yy; cI.zz += Io.zz;
+                if constexpr (T::full_inertia(i)) { cI.xy += Io.xy; cI.xz += Io.xz; cI.yz += Io.yz; }
             }
             // unit acceleration about the joint axis: F = e x ch, N = cI e
             V3 F, N;
             if constexpr (AX == 0) { F = {0.0, -ch.z, ch.y}; N = {cI.xx, cI.xy, cI.xz}; }
             else if constexpr (AX == 1) { F = {ch.z, 0.0, -ch.x}; N = {cI.xy, cI.yy, cI.yz}; }
             else { F = {-ch.y, ch.x, 0.0}; N = {cI.xz, cI.yz, cI.zz}; }
-            M[i][i] = comp<AX>(N) + prm[CH_ARMATURE + i];
+            sc.st(sc_m(i, i), comp<AX>(N) + prm[CH_ARMATURE + i]);
             // carry the wrench down to every ancestor joint
             static_for<i>([&](auto Jc) {
                 constexpr int j = i - decltype(Jc)::value;      // hop through joint j: frame j -> j-1
                 constexpr int AJ = T::axis(j);
                 F = rot<AJ>(F, sn[j], cs[j]);
-                N = rot<AJ>(N, sn[j], cs[j]) + off_cross<T, j>(prm, F);
-                M[i][j - 1] = comp<T::axis(j - 1)>(N);
+                N = rot<AJ>(N, sn[j], cs[j]);
+                if constexpr (T::off_mask(j) != 0) N = N - cross_m<T::off_mask(j)>(F, link_offset<T, j>(prm));
+                sc.st(sc_m(i, j - 1), comp<T::axis(j - 1)>(N));
             });
             // move the composite to the parent frame
             if constexpr (i > 0) {
+                constexpr int OM = T::off_mask(i);
                 const V3 hr = rot<AX>(ch, sn[i], cs[i]);
                 cI = rotS<AX>(cI, sn[i], cs[i]);
-                if constexpr (T::off_mask(i) != 0) {
+                if constexpr (OM != 0) {
                     const V3 o = link_offset<T, i>(prm);
                     // reference point moves by -o: I += (2 h.o + m o.o) 1 - (h o' + o h') - m o o'
                     const V3 mo = cm * o;
                     const V3 g = hr + hr + mo;                  // 2h + m o
-                    const double tr = dot(g, o);
-                    cI.xx += tr - g.x * o.x; cI.yy += tr - g.y * o.y; cI.zz += tr - g.z * o.z;
+                    double tr = 0.0;
+                    if constexpr (OM & 1) tr += g.x * o.x;
+                    if constexpr (OM & 2) tr += g.y * o.y;
+                    if constexpr (OM & 4) tr += g.z * o.z;
+                    if constexpr (OM & 1) cI.xx -= g.x * o.x;
+                    if constexpr (OM & 2) cI.yy -= g.y * o.y;
+                    if constexpr (OM & 4) cI.zz -= g.z * o.z;
+                    cI.xx += tr; cI.yy += tr; cI.zz += tr;
                     // off-diagonals: -(h_a o_b + o_a h_b) - m o_a o_b
-                    cI.xy -= hr.x * o.y + o.x * hr.y + mo.x * o.y;
-                    cI.xz -= hr.x * o.z + o.x * hr.z + mo.x * o.z;
-                    cI.yz -= hr.y * o.z + o.y * hr.z + mo.y * o.z;
-                    ch = hr + mo;
+                    if constexpr (OM & 2) cI.xy -= hr.x * o.y;
+                    if constexpr (OM & 1) cI.xy -= o.x * hr.y;
+                    if constexpr ((OM & 3) == 3) cI.xy -= mo.x * o.y;
+                    if constexpr (OM & 4) cI.xz -= hr.x * o.z;
+                    if constexpr (OM & 1) cI.xz -= o.x * hr.z;
+                    if constexpr ((OM & 5) == 5) cI.xz -= mo.x * o.z;
+                    if constexpr (OM & 4) cI.yz -= hr.y * o.z;
+                    if constexpr (OM & 2) cI.yz -= o.y * hr.z;
+                    if constexpr ((OM & 6) == 6) cI.yz -= mo.y * o.z;
+                    ch = add_m<OM>(hr, mo);
                 } else {
                     ch = hr;
                 }
             }
         });
     }
+}
+
+// Reciprocal of a well-scaled positive number (mass-matrix pivots, regularisers): hardware seed
+// (rcp.approx.ftz.f64 = MUFU.RCP64H, ~20 bits) + two Newton steps in FP64 (2^-20 -> 2^-40 -> below
+// 1 ulp).  No denormal / special-case path: 5 straight-line instructions instead of the ~30 (with a
+// slow-path call) of an IEEE division.
+MJB_HD double rcp_pos(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = r * fma(-x, r, 2.0);
+    r = r * fma(-x, r, 2.0);
+    return r;
+#else
+    return 1.0 / x;
+#endif
 }
 
 // In-place LDL' of the lower triangle of a 7x7 SPD matrix: A[i][j] (i>j) <- L[i][j], dinv[j] = 1/D[j].
@@ -252,7 +340,7 @@ MJB_HD void ldl7(double (&A)[7][7], double (&dinv)[7]) {
 #pragma unroll
         for (int k = 0; k < j; k++) { w[k] = A[j][k] * A[k][k]; dj -= A[j][k] * w[k]; }
         A[j][j] = dj;
-        const double inv = 1.0 / dj;
+        const double inv = rcp_pos(dj);
         dinv[j] = inv;
 #pragma unroll
         for (int i = j + 1; i < 7; i++) {
@@ -278,19 +366,34 @@ MJB_HD void ldl7_solve(const double (&L)[7][7], const double (&dinv)[7], double 
     }
 }
 
-// MuJoCo's constraint impedance as a function of penetration (solimp d0,dwidth,width,midpoint,power)
-template <class P> MJB_HD double impedance(const P& prm, double dist_minus_margin) {
+// MuJoCo's constraint impedance / regulariser / reference acceleration of one soft row
+// (mj_makeImpedance + mj_referenceConstraint): generic form, out of line.  The hot path below uses a
+// branch-free specialisation for the default power-2 impedance and falls back to this one otherwise.
+struct RowParams { double D, aref; };
+template <class P> MJB_NOINLINE RowParams soft_row(P prm, double pos_minus_margin, double vel, double invweight) {
     const double d0 = prm[CS_IMP_D0], dw = prm[CS_IMP_DW], width = prm[CS_IMP_WIDTH];
-    if (d0 == dw || width <= 1e-15) return 0.5 * (d0 + dw);
-    const double x = fabs(dist_minus_margin / width);
-    if (x >= 1.0) return dw;
-    if (x <= 0.0) return d0;
-    const double mid = prm[CS_IMP_MID], pw = prm[CS_IMP_POWER];
-    double y;
-    if (pw == 1.0) y = x;
-    else if (x <= mid) y = pow(x, pw) / pow(mid, pw - 1.0);
-    else y = 1.0 - pow(1.0 - x, pw) / pow(1.0 - mid, pw - 1.0);
-    return d0 + y * (dw - d0);
+    double imp;
+    if (d0 == dw || width <= 1e-15) imp = 0.5 * (d0 + dw);
+    else {
+        const double x = fabs(pos_minus_margin / width);
+        if (x >= 1.0) imp = dw;
+        else if (x <= 0.0) imp = d0;
+        else {
+            const double mid = prm[CS_IMP_MID], pw = prm[CS_IMP_POWER];
+            double y;
+            if (pw == 1.0) y = x;
+            else if (pw == 2.0) y = x <= mid ? (x * x) / mid : 1.0 - ((1.0 - x) * (1.0 - x)) / (1.0 - mid);
+            else if (x <= mid) y = pow(x, pw) / pow(mid, pw - 1.0);
+            else y = 1.0 - pow(1.0 - x, pw) / pow(1.0 - mid, pw - 1.0);
+            imp = d0 + y * (dw - d0);
+        }
+    }
+    double r = (1.0 - imp) * invweight / imp;      // regulariser R; D = 1/R
+    r = r < 1e-15 ? 1e-15 : r;
+    RowParams o;
+    o.D = 1.0 / r;
+    o.aref = -prm[CS_SOLB] * vel - prm[CS_SOLK] * imp * pos_minus_margin;
+    return o;
 }
 
 // World position of a point given in the last link's frame (nested evaluation, no matrices).
@@ -299,212 +402,278 @@ MJB_HD V3 chain_point_world(const P& prm, const double (&sn)[7], const double (&
     static_for<7>([&](auto Ic) {
         constexpr int i = 6 - decltype(Ic)::value;
         p = rot<T::axis(i)>(p, sn[i], cs[i]);
-        if constexpr (T::off_mask(i) != 0) p = p + link_offset<T, i>(prm);
+        if constexpr (T::off_mask(i) != 0) p = add_m<T::off_mask(i)>(p, link_offset<T, i>(prm));
     });
     return p;
 }
 
-// Constraint rows of one particle: 7 joint-limit rows (at most one side of a joint can be violated;
-// row j acts on dof j with Jacobian entry sg[j] = -side) and one frictionless contact row.
-struct Rows {
-    double D[7], aref[7], sg[7];   // D == 0: row absent
-    double Dc, arefc, Jc[7];       // Dc == 0: no contact
-    bool any;
-};
-
+// Jacobian row of the sphere-plane contact: the contact point and the plane normal are carried into
+// every link frame, Jc[j] = n_j . (e_j x r_j).  Rare path, kept out of line; it works on a packed copy
+// (io[0..7) sin, [7..14) cos, [14..21) qvel in; [0..7) Jc, [7] D, [8] aref out) so that the caller's
+// register-resident arrays never have their address taken.
 template <class T, class P>
-MJB_HD void make_rows(const P& prm, const double (&q)[7], const double (&qd)[7], const double (&sn)[7],
-                      const double (&cs)[7], Rows& R) {
-    R.any = false;
-    const double K = prm[CS_SOLK], B = prm[CS_SOLB];
-    const int limited = (int)prm[CS_LIMITED_MASK];
+MJB_NOINLINE void contact_row(P prm, double* io, double cx, double cy, double cz, double dist) {
+    const double radius = prm[CS_CON_RADIUS], margin = prm[CS_CON_MARGIN];
+    V3 n = {0.0, 0.0, 1.0};
+    V3 r = {cx, cy, cz - (radius + 0.5 * dist)};
+    double vel = 0.0, J[7];
+    static_for<7>([&](auto Ic) {
+        constexpr int i = decltype(Ic)::value;
+        constexpr int AX = T::axis(i);
+        if constexpr (T::off_mask(i) != 0) r = r - link_offset<T, i>(prm);
+        r = rotT<AX>(r, io[i], io[7 + i]);
+        n = rotT<AX>(n, io[i], io[7 + i]);
+        double j;
+        if constexpr (AX == 0) j = n.z * r.y - n.y * r.z;
+        else if constexpr (AX == 1) j = n.x * r.z - n.z * r.x;
+        else j = n.y * r.x - n.x * r.y;
+        J[i] = j;
+        vel += j * io[14 + i];
+    });
+    const RowParams rp = soft_row(prm, dist - margin, vel, prm[CS_CON_INVW]);
 #pragma unroll
-    for (int j = 0; j < 7; j++) {
-        const double lo = prm[CH_RANGE_LO + j], hi = prm[CH_RANGE_HI + j];
-        double dist = 0.0, side = 0.0;
-        if (q[j] < lo) { dist = q[j] - lo; side = -1.0; }          // side * (range - q), side = -1
-        else if (q[j] > hi) { dist = hi - q[j]; side = 1.0; }
-        R.D[j] = 0.0; R.aref[j] = 0.0; R.sg[j] = -side;
-        if (dist < 0.0 && ((limited >> j) & 1)) {
-            const double imp = impedance(prm, dist);
-            double r = (1.0 - imp) * prm[CH_INVW0 + j] / imp;
-            r = r < 1e-15 ? 1e-15 : r;
-            R.D[j] = 1.0 / r;
-            R.aref[j] = -B * (-side * qd[j]) - K * imp * dist;
-            R.any = true;
+    for (int i = 0; i < 7; i++) io[i] = J[i];
+    io[7] = rp.D;
+    io[8] = rp.aref;
+}
+
+// Constraint rows of one particle.  Limit row j acts on dof j alone with Jacobian entry sg = +1 below
+// the range, -1 above it (at most one side can be violated); D == 0 marks an absent row.  The
+// contact row's Jacobian lives in the scratch (SC_JC) and is only touched when Dc != 0.
+struct Rows {
+    double D[7], aref[7];
+    unsigned below;            // bit j: joint j is below its range (sg = +1)
+    double Dc, arefc;
+};
+MJB_HD double row_sg(const Rows& R, int j) { return ((R.below >> j) & 1u) ? 1.0 : -1.0; }
+
+template <class T, class P, class S>
+MJB_HD bool make_rows(const P& prm, S& sc, const double (&q)[7], const double (&qd)[7], const double (&sn)[7],
+                      const double (&cs)[7], Rows& R) {
+    bool any = false;
+    const int limited = (int)prm[CS_LIMITED_MASK];
+    const double d0 = prm[CS_IMP_D0], dw = prm[CS_IMP_DW], width = prm[CS_IMP_WIDTH];
+    const double mid = prm[CS_IMP_MID];
+    const double K = prm[CS_SOLK], B = prm[CS_SOLB];
+    R.below = 0;
+    if (prm[CS_IMP_POWER] == 2.0 && d0 != dw && width > 1e-15) {
+        // default impedance shape (power 2): branch-free over the 7 joints, every lane does the same work
+        const double iw = 1.0 / width, imid = 1.0 / mid, i1mid = 1.0 / (1.0 - mid);
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const double lo = prm[CH_RANGE_LO + j], hi = prm[CH_RANGE_HI + j];
+            const bool below = q[j] < lo;
+            const double dist = below ? q[j] - lo : hi - q[j];     // side * (range - q): < 0 when violated
+            const bool viol = dist < 0.0 && ((limited >> j) & 1);
+            const double x = fabs(dist) * iw;
+            const double xm = 1.0 - x;
+            const double y = x <= mid ? (x * x) * imid : 1.0 - (xm * xm) * i1mid;
+            const double imp = x >= 1.0 ? dw : d0 + y * (dw - d0);
+            // D = 1 / max(1e-15, (1-imp)*invweight/imp)
+            const double den = fmax((1.0 - imp) * prm[CH_INVW0 + j], 1e-15 * imp);
+            const double sg = below ? 1.0 : -1.0;
+            R.D[j] = viol ? imp * rcp_pos(den) : 0.0;
+            R.aref[j] = viol ? -B * (sg * qd[j]) - K * imp * dist : 0.0;
+            R.below |= below ? (1u << j) : 0u;
+            any |= viol;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const double lo = prm[CH_RANGE_LO + j], hi = prm[CH_RANGE_HI + j];
+            const bool below = q[j] < lo;
+            const double dist = below ? q[j] - lo : hi - q[j];
+            R.D[j] = 0.0; R.aref[j] = 0.0;
+            R.below |= below ? (1u << j) : 0u;
+            if (dist < 0.0 && ((limited >> j) & 1)) {
+                const RowParams rp = soft_row(prm, dist, (below ? 1.0 : -1.0) * qd[j], prm[CH_INVW0 + j]);
+                R.D[j] = rp.D; R.aref[j] = rp.aref;
+                any = true;
+            }
         }
     }
     R.Dc = 0.0; R.arefc = 0.0;
-#pragma unroll
-    for (int j = 0; j < 7; j++) R.Jc[j] = 0.0;
     const double radius = prm[CS_CON_RADIUS];
     if (radius > 0.0) {
         const V3 c = chain_point_world<T>(prm, sn, cs, V3{prm[CS_CON_POS], prm[CS_CON_POS + 1], prm[CS_CON_POS + 2]});
-        const double margin = prm[CS_CON_MARGIN];
         const double dist = c.z - prm[CS_CON_PLANE_Z] - radius;
-        if (dist < margin) {
-            // contact point (mid-surface) and plane normal carried into each link frame:
-            // Jc[j] = n_j . (e_j x r_j), r_j = contact point relative to joint j, link-j coordinates
-            V3 n = {0.0, 0.0, 1.0};
-            V3 r = {c.x, c.y, c.z - (radius + 0.5 * dist)};
-            static_for<7>([&](auto Ic) {
-                constexpr int i = decltype(Ic)::value;
-                constexpr int AX = T::axis(i);
-                r = r - link_offset<T, i>(prm);
-                r = rotT<AX>(r, sn[i], cs[i]);
-                n = rotT<AX>(n, sn[i], cs[i]);
-                // n . (e x r)
-                if constexpr (AX == 0) R.Jc[i] = n.z * r.y - n.y * r.z;
-                else if constexpr (AX == 1) R.Jc[i] = n.x * r.z - n.z * r.x;
-                else R.Jc[i] = n.y * r.x - n.x * r.y;
-            });
-            const double imp = impedance(prm, dist - margin);
-            double rr = (1.0 - imp) * prm[CS_CON_INVW] / imp;
-            rr = rr < 1e-15 ? 1e-15 : rr;
-            R.Dc = 1.0 / rr;
-            double vel = 0.0;
+        if (dist < prm[CS_CON_MARGIN]) {
+            double io[21];
 #pragma unroll
-            for (int j = 0; j < 7; j++) vel += R.Jc[j] * qd[j];
-            R.arefc = -B * vel - K * imp * (dist - margin);
-            R.any = true;
+            for (int j = 0; j < 7; j++) { io[j] = sn[j]; io[7 + j] = cs[j]; io[14 + j] = qd[j]; }
+            contact_row<T>(prm, io, c.x, c.y, c.z, dist);
+#pragma unroll
+            for (int j = 0; j < 7; j++) sc.st(SC_JC + j, io[j]);
+            R.Dc = io[7]; R.arefc = io[8];
+            any = true;
         }
     }
+    return any;
 }
 
-// Exact minimiser over a of  1/2 a'Ma - f'a + sum_r 1/2 D_r min(0, J_r a - aref_r)^2 ; returns the
-// constraint force J' lambda in fc.  Newton on the active set with an exact line search (each
-// piece of the objective is quadratic, so a step that keeps its active set lands on the optimum).
-MJB_HD void solve_constraints(const double (&M)[7][7], const double (&f)[7], const Rows& R, double (&fc)[7]) {
-    double a[7];
+// active-set bit mask at acceleration a (bit j: limit row j, bit 7: contact); jc = Jc.a - arefc
+template <class S>
+MJB_HD unsigned active_set(const Rows& R, const S& sc, const double (&a)[7], double& jc) {
+    unsigned act = 0;
 #pragma unroll
-    for (int j = 0; j < 7; j++) a[j] = 0.0;
-    unsigned act = 0;            // bit j: limit row j active, bit 7: contact
-    for (int it = 0; it < 64; it++) {
-        // active set at the current point
-        double jc = -R.arefc;
+    for (int j = 0; j < 7; j++) if (R.D[j] > 0.0 && row_sg(R, j) * a[j] - R.aref[j] < 0.0) act |= 1u << j;
+    jc = 0.0;
+    if (R.Dc > 0.0) {
+        jc = -R.arefc;
 #pragma unroll
-        for (int j = 0; j < 7; j++) jc += R.Jc[j] * a[j];
-        act = 0;
-#pragma unroll
-        for (int j = 0; j < 7; j++) if (R.D[j] > 0.0 && R.sg[j] * a[j] - R.aref[j] < 0.0) act |= 1u << j;
-        if (R.Dc > 0.0 && jc < 0.0) act |= 128u;
-        // minimiser of the current quadratic piece
-        double H[7][7], dinv[7], x[7];
-        const double dc = (act & 128u) ? R.Dc : 0.0;
-#pragma unroll
-        for (int i = 0; i < 7; i++) {
-            const double di = ((act >> i) & 1u) ? R.D[i] : 0.0;
-#pragma unroll
-            for (int j = 0; j <= i; j++) H[i][j] = M[i][j] + dc * R.Jc[i] * R.Jc[j];
-            H[i][i] += di;
-            x[i] = f[i] + di * R.aref[i] * R.sg[i] + dc * R.arefc * R.Jc[i];
+        for (int j = 0; j < 7; j++) jc += sc.ld(SC_JC + j) * a[j];
+        if (jc < 0.0) act |= 128u;
+    }
+    return act;
+}
+
+// Exact line search on phi(t) = obj(a + t p): phi'(t) is piecewise linear and increasing; bracket the
+// root between consecutive breakpoints, then solve the linear piece.  Rare path (the active set
+// changed along a Newton step), so it is rolled, out of line, and fed through one packed buffer:
+// w = [ M (49, lower triangle valid) | f 7 | a 7 | p 7 | jar 8 | jp 8 | D 8 ].
+MJB_NOINLINE double line_search(const double* w) {
+    const double *M49 = w, *f = w + 49, *a = w + 56, *p = w + 63, *jar = w + 70, *jp = w + 78, *Dr = w + 86;
+    double g0 = 0.0, h0 = 0.0;
+    for (int i = 0; i < 7; i++) {
+        double s = 0.0, ga = -f[i];
+        for (int k = 0; k < 7; k++) {
+            const double mik = k <= i ? M49[i * 7 + k] : M49[k * 7 + i];
+            s += mik * p[k]; ga += mik * a[k];
         }
-        ldl7(H, dinv);
-        ldl7_solve(H, dinv, x);
-        // active set at the candidate
-        double jcx = -R.arefc;
-#pragma unroll
-        for (int j = 0; j < 7; j++) jcx += R.Jc[j] * x[j];
-        unsigned actx = 0;
-#pragma unroll
-        for (int j = 0; j < 7; j++) if (R.D[j] > 0.0 && R.sg[j] * x[j] - R.aref[j] < 0.0) actx |= 1u << j;
-        if (R.Dc > 0.0 && jcx < 0.0) actx |= 128u;
-        if (actx == act) {
-#pragma unroll
-            for (int j = 0; j < 7; j++) a[j] = x[j];
-            break;
-        }
-        // exact line search on phi(t) = obj(a + t p), p = x - a:  phi'(t) piecewise linear, increasing
-        double p[7], g0 = 0.0, h0 = 0.0;
-#pragma unroll
-        for (int j = 0; j < 7; j++) p[j] = x[j] - a[j];
-#pragma unroll
-        for (int i = 0; i < 7; i++) {
-            double s = 0.0, ga = -f[i];
-#pragma unroll
-            for (int k = 0; k < 7; k++) {
-                const double mik = k <= i ? M[i][k] : M[k][i];
-                s += mik * p[k]; ga += mik * a[k];
-            }
-            g0 += p[i] * ga; h0 += p[i] * s;
-        }
-        double jar[8], jp[8], Dr[8];
-#pragma unroll
-        for (int j = 0; j < 7; j++) { jar[j] = R.sg[j] * a[j] - R.aref[j]; jp[j] = R.sg[j] * p[j]; Dr[j] = R.D[j]; }
-        jar[7] = jc; jp[7] = jcx - jc; Dr[7] = R.Dc;
-        // bracket the root between consecutive breakpoints: lo = largest breakpoint with phi' <= 0
-        double lo = 0.0, hi = INFINITY;
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            if (Dr[r] > 0.0 && jp[r] != 0.0) {
-                const double t = -jar[r] / jp[r];
-                if (t > 0.0) {
-                    double d = g0 + t * h0;
-#pragma unroll
-                    for (int s = 0; s < 8; s++) {
-                        const double js = jar[s] + t * jp[s];
-                        if (Dr[s] > 0.0 && js < 0.0) d += Dr[s] * js * jp[s];
-                    }
-                    if (d <= 0.0) { if (t > lo) lo = t; }
-                    else if (t < hi) hi = t;
+        g0 += p[i] * ga; h0 += p[i] * s;
+    }
+    double lo = 0.0, hi = INFINITY;
+    for (int r = 0; r < 8; r++) {
+        if (Dr[r] > 0.0 && jp[r] != 0.0) {
+            const double t = -jar[r] / jp[r];
+            if (t > 0.0) {
+                double d = g0 + t * h0;
+                for (int s = 0; s < 8; s++) {
+                    const double js = jar[s] + t * jp[s];
+                    if (Dr[s] > 0.0 && js < 0.0) d += Dr[s] * js * jp[s];
                 }
+                if (d <= 0.0) { if (t > lo) lo = t; }
+                else if (t < hi) hi = t;
             }
         }
-        const double mid = (hi == INFINITY) ? lo + 1.0 : 0.5 * (lo + hi);
-        double c0 = g0, c1 = h0;
-#pragma unroll
-        for (int s = 0; s < 8; s++) {
-            if (Dr[s] > 0.0 && jar[s] + mid * jp[s] < 0.0) { c0 += Dr[s] * jar[s] * jp[s]; c1 += Dr[s] * jp[s] * jp[s]; }
-        }
-        double t = -c0 / c1;
-        t = t < lo ? lo : (t > hi ? hi : t);
-#pragma unroll
-        for (int j = 0; j < 7; j++) a[j] += t * p[j];
     }
-    // constraint force at the optimum: lambda_r = -D_r (J_r a - aref_r) on active rows
-    double jc = -R.arefc;
-#pragma unroll
-    for (int j = 0; j < 7; j++) jc += R.Jc[j] * a[j];
-    const double lc = (R.Dc > 0.0 && jc < 0.0) ? -R.Dc * jc : 0.0;
-#pragma unroll
-    for (int j = 0; j < 7; j++) {
-        const double jr = R.sg[j] * a[j] - R.aref[j];
-        const double lam = (R.D[j] > 0.0 && jr < 0.0) ? -R.D[j] * jr : 0.0;
-        fc[j] = R.sg[j] * lam + lc * R.Jc[j];
-    }
+    const double mid = (hi == INFINITY) ? lo + 1.0 : 0.5 * (lo + hi);
+    double c0 = g0, c1 = h0;
+    for (int s = 0; s < 8; s++)
+        if (Dr[s] > 0.0 && jar[s] + mid * jp[s] < 0.0) { c0 += Dr[s] * jar[s] * jp[s]; c1 += Dr[s] * jp[s] * jp[s]; }
+    double t = -c0 / c1;
+    t = t < lo ? lo : (t > hi ? hi : t);
+    return t;
 }
 
-// One mj_step of the chain: forward dynamics at (q, qd) under control u, then Euler advance.
-// sn/cs must hold sin/cos of q on entry.  Returns true when a constraint row was present.
-template <class T, class P>
-MJB_HD bool chain_substep(const P& prm, double (&q)[7], double (&qd)[7], const double (&sn)[7],
-                          const double (&cs)[7], const double (&u)[7]) {
-    double M[7][7], f[7];
-    chain_mass_bias<T>(prm, sn, cs, qd, M, f);
+// One mj_step of the chain: forward dynamics at (q, qd) under the control held in the scratch
+// (SC_U), then Euler advance.  sn/cs must hold sin/cos of q on entry.  Returns true when a
+// constraint row was present.
+//
+// Constraint forces: exact minimiser over a of 1/2 a'Ma - f'a + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
+// by Newton on the active set (each piece of the objective is quadratic, so a step that keeps its
+// active set lands on the optimum).  The Newton solves and the final implicit-damping Euler solve
+// (M + hB) a = f + J'lambda share ONE factor/solve site: phase 0 = Newton iterations, phase 1 = Euler.
+template <class T, class P, class S>
+MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], const double (&sn)[7],
+                          const double (&cs)[7]) {
+    double f[7];
+    chain_mass_bias<T>(prm, sc, sn, cs, qd, f);
 #pragma unroll
     for (int j = 0; j < 7; j++) {
-        double c = u[j];
-        c = c < prm[CH_CTRL_LO + j] ? prm[CH_CTRL_LO + j] : c;
-        c = c > prm[CH_CTRL_HI + j] ? prm[CH_CTRL_HI + j] : c;
+        double c = sc.ld(SC_U + j);
+        c = fmin(fmax(c, prm[CH_CTRL_LO + j]), prm[CH_CTRL_HI + j]);
         f[j] = prm[CH_GEAR + j] * c - prm[CH_DAMPING + j] * qd[j] - f[j];
     }
     Rows R;
-    make_rows<T>(prm, q, qd, sn, cs, R);
-    if (R.any) {
-        double fc[7];
-        solve_constraints(M, f, R, fc);
+    const bool any = make_rows<T>(prm, sc, q, qd, sn, cs, R);
+    double a[7], fc[7], x[7];
+    // First active-set guess from the decoupled accelerations f_j / M_jj (the contact row from its
+    // reference acceleration alone).  Any guess is admissible: a solve whose own active set equals the
+    // set it was built from satisfies the optimality conditions of the strictly convex problem.
+    unsigned act = 0;
 #pragma unroll
-        for (int j = 0; j < 7; j++) f[j] += fc[j];
+    for (int j = 0; j < 7; j++) {
+        a[j] = 0.0; fc[j] = 0.0;
+        if (R.D[j] > 0.0 && row_sg(R, j) * f[j] < R.aref[j] * sc.ld(sc_m(j, j))) act |= 1u << j;
     }
-    double dinv[7];
+    if (R.Dc > 0.0 && R.arefc > 0.0) act |= 128u;
+    double jc = 0.0;
+    int phase = any ? 0 : 1;
+    MJB_STAT(0); if (any) MJB_STAT(1);
+    for (int it = 0;; it++) {
+        double H[7][7], dinv[7];
+        MJB_STAT(2);
+        const unsigned use = phase == 0 ? act : 0u;
 #pragma unroll
-    for (int j = 0; j < 7; j++) M[j][j] += prm[CH_HDAMP + j];
-    ldl7(M, dinv);
-    ldl7_solve(M, dinv, f);
+        for (int i = 0; i < 7; i++) {
+#pragma unroll
+            for (int j = 0; j <= i; j++) H[i][j] = sc.ld(sc_m(i, j));
+            const double di = ((use >> i) & 1u) ? R.D[i] : 0.0;
+            H[i][i] += phase == 0 ? di : prm[CH_HDAMP + i];
+            x[i] = f[i] + (phase == 0 ? di * R.aref[i] * row_sg(R, i) : fc[i]);
+        }
+        if (use & 128u) {
+            double Jc[7];
+#pragma unroll
+            for (int i = 0; i < 7; i++) Jc[i] = sc.ld(SC_JC + i);
+#pragma unroll
+            for (int i = 0; i < 7; i++) {
+#pragma unroll
+                for (int j = 0; j <= i; j++) H[i][j] += R.Dc * Jc[i] * Jc[j];
+                x[i] += R.Dc * R.arefc * Jc[i];
+            }
+        }
+        ldl7(H, dinv);
+        ldl7_solve(H, dinv, x);
+        if (phase == 1) break;
+        double jcx;
+        const unsigned actx = active_set(R, sc, x, jcx);
+        if (actx == act || it >= 48) {
+            // optimum reached: constraint force lambda_r = -D_r (J_r a - aref_r) on the active rows
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                const double sg = row_sg(R, j);
+                const double lam = ((actx >> j) & 1u) ? -R.D[j] * (sg * x[j] - R.aref[j]) : 0.0;
+                fc[j] = sg * lam;
+            }
+            if (actx & 128u) {
+                const double lc = -R.Dc * jcx;
+#pragma unroll
+                for (int j = 0; j < 7; j++) fc[j] += lc * sc.ld(SC_JC + j);
+            }
+            phase = 1;
+            continue;
+        }
+        if (it < 4) {
+            // plain active-set (unit Newton) step: adopt the candidate and its active set
+#pragma unroll
+            for (int j = 0; j < 7; j++) a[j] = x[j];
+            act = actx; jc = jcx;
+            continue;
+        }
+        // safety net (the unit steps did not settle): globally convergent Newton with an exact line search
+        // from the current point a, whose active set is `act` by construction
+        double w[94];
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const double pj = x[j] - a[j], sg = row_sg(R, j);
+            w[49 + j] = f[j]; w[56 + j] = a[j]; w[63 + j] = pj;
+            w[70 + j] = sg * a[j] - R.aref[j]; w[78 + j] = sg * pj; w[86 + j] = R.D[j];
+#pragma unroll
+            for (int k = 0; k <= j; k++) w[j * 7 + k] = sc.ld(sc_m(j, k));
+        }
+        w[77] = jc; w[85] = jcx - jc; w[93] = R.Dc;
+        MJB_STAT(3);
+        const double t = line_search(w);
+#pragma unroll
+        for (int j = 0; j < 7; j++) a[j] += t * (x[j] - a[j]);
+        act = active_set(R, sc, a, jc);
+    }
     const double h = prm[CS_TIMESTEP];
 #pragma unroll
-    for (int j = 0; j < 7; j++) { qd[j] += h * f[j]; q[j] += h * qd[j]; }
-    return R.any;
+    for (int j = 0; j < 7; j++) { qd[j] += h * x[j]; q[j] += h * qd[j]; }
+    return any;
 }
 
 // The reference's step cost (reacher_env.py:31-35): -reward = |h-g|_1 + 5 |h-g|_2

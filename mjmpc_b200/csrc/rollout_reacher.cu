@@ -3,59 +3,95 @@
 // env-copy loop: GymEnvWrapper.rollout (mjmpc/envs/gym_env_wrapper.py:125-153) ->
 // Reacher7DOFEnv.step (mjmpc/envs/basic/reacher_env.py:29-39) -> MuJoCo mj_step x frame_skip,
 // fanned out by SubprocVecEnv.rollout (mjmpc/envs/vec_env/subproc_vec_env.py:161-186).
+#include <type_traits>
 #include "chain_dynamics.cuh"
 #include "common.h"
 
 namespace mjb {
 
 struct GlobalParams {
-    const double* __restrict__ p;
+    const double* p;
     __device__ __forceinline__ double operator[](int i) const { return __ldg(p + i); }
+};
+
+// Single-model launches (the common case) read the model from constant memory: every parameter
+// index is a compile-time constant after unrolling, so it becomes a c[bank][offset] operand of the
+// FP64 instruction itself -- no load, no register.  Per-worker models (dynamics randomisation) read
+// their instance's block from global memory instead.
+__constant__ double c_params[CH_NDEV];
+struct ConstParams {
+    __device__ __forceinline__ double operator[](int i) const { return c_params[i]; }
+};
+
+#define MJB_ROLLOUT_BLOCK 64
+// one shared-memory column per scratch slot: slot * BLOCK + thread (no bank conflicts)
+struct SmemScratch {
+    double* base;
+    __device__ __forceinline__ double ld(int slot) const { return base[slot * MJB_ROLLOUT_BLOCK]; }
+    __device__ __forceinline__ void st(int slot, double v) { base[slot * MJB_ROLLOUT_BLOCK] = v; }
 };
 
 // 64-thread blocks, 4 per SM: 256 resident particles per SM at up to 255 registers each; the
 // small block keeps the second wave of a K=65536 launch evenly spread over the 148 SMs.
-template <class T>
-__global__ void __launch_bounds__(64, 4) rollout_reacher_kernel(const double* __restrict__ params, int n_inst,
+// EXTRA: also write the per-step state trajectory / observations / constraint counters (tests, adaptors
+// that hand observations back); the production instantiation carries none of that code.
+template <class T, class P, bool EXTRA>
+__global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, 4) rollout_reacher_kernel(const double* __restrict__ params, int n_inst,
                                                                 mjb_rollout_args a) {
+    __shared__ double smem[SC_NSLOT * MJB_ROLLOUT_BLOCK];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.K) return;
+    SmemScratch sc{smem + threadIdx.x};
     const int ctrl = k / a.particles_per_ctrl;
-    const int inst = (k / a.particles_per_model) % n_inst;
-    GlobalParams prm{params + (size_t)inst * CH_NDEV};
+    P prm;
+    if constexpr (std::is_same<P, GlobalParams>::value) {
+        const int inst = (k / a.particles_per_model) % n_inst;
+        prm.p = params + (size_t)inst * CH_NDEV;
+    }
     const double* __restrict__ st = a.state + (size_t)ctrl * MJB_STATE_DIM;
     const double* __restrict__ mean = a.mean + (size_t)ctrl * a.H * 7;
-    double q[7], v[7], u[7], sn[7], cs[7];
+    double q[7], v[7], sn[7], cs[7];
 #pragma unroll
     for (int j = 0; j < 7; j++) { q[j] = __ldg(st + j); v[j] = __ldg(st + 7 + j); }
     const V3 target = {__ldg(st + 14), __ldg(st + 15), __ldg(st + 16)};
     const V3 hand_local = {prm[CS_HAND], prm[CS_HAND + 1], prm[CS_HAND + 2]};
     const int fs = (int)prm[CS_FRAME_SKIP];
     int nc = 0;
+    const double* __restrict__ np = a.noise ? a.noise + k * a.noise_sk : nullptr;
+    double* __restrict__ ap = a.actions ? a.actions + k * a.act_sk : nullptr;
+    double* __restrict__ cp = a.costs + k * a.costs_sk;
     for (int t = 0; t < a.H; t++) {
+        {
+            const double* nj = np;
+            double* aj = ap;
 #pragma unroll
-        for (int j = 0; j < 7; j++) {
-            double x = __ldg(mean + t * 7 + j);
-            if (a.noise) x += __ldg(a.noise + k * a.noise_sk + t * a.noise_st + j * a.noise_sj);
-            u[j] = x;
-            if (a.actions) a.actions[k * a.act_sk + t * a.act_st + j * a.act_sj] = x;
+            for (int j = 0; j < 7; j++) {
+                double x = __ldg(mean + t * 7 + j);
+                if (np) { x += __ldg(nj); nj += a.noise_sj; }
+                sc.st(SC_U + j, x);
+                if (ap) { *aj = x; aj += a.act_sj; }
+            }
+            if (np) np += a.noise_st;
+            if (ap) ap += a.act_st;
         }
         V3 hand = {0.0, 0.0, 0.0};
         for (int s = 0; s < fs; s++) {
 #pragma unroll
-            for (int j = 0; j < 7; j++) sincos(q[j], &sn[j], &cs[j]);
+            for (int j = 0; j < 7; j++) sincos_joint(q[j], sn[j], cs[j]);
             // data.site_xpos read after mj_step is the one computed by the LAST forward pass, i.e. at
             // the state before the last substep's integration (reacher_env.py:31-35).
             if (s == fs - 1) hand = chain_point_world<T>(prm, sn, cs, hand_local);
-            nc += chain_substep<T>(prm, q, v, sn, cs, u) ? 1 : 0;
+            const bool any = chain_substep<T>(prm, sc, q, v, sn, cs);
+            if (EXTRA) nc += any ? 1 : 0;
         }
-        a.costs[k * a.costs_sk + t * a.costs_st] = reach_cost(hand, target);
-        if (a.qv_traj) {
+        *cp = reach_cost(hand, target);
+        cp += a.costs_st;
+        if (EXTRA && a.qv_traj) {
             double* o = a.qv_traj + ((size_t)k * a.H + t) * 14;
 #pragma unroll
             for (int j = 0; j < 7; j++) { o[j] = q[j]; o[7 + j] = v[j]; }
         }
-        if (a.next_obs) {
+        if (EXTRA && a.next_obs) {
             double* o = a.next_obs + ((size_t)k * a.H + t) * MJB_OBS_DIM;
 #pragma unroll
             for (int j = 0; j < 7; j++) { o[j] = q[j]; o[7 + j] = v[j]; }
@@ -63,7 +99,7 @@ __global__ void __launch_bounds__(64, 4) rollout_reacher_kernel(const double* __
             o[17] = hand.x - target.x; o[18] = hand.y - target.y; o[19] = hand.z - target.z;
         }
     }
-    if (a.ncon) a.ncon[k] = nc;
+    if (EXTRA && a.ncon) a.ncon[k] = nc;
 }
 
 }  // namespace mjb
@@ -77,13 +113,30 @@ extern "C" int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a
                 "Number of particles must be divisible by number of cpus");  // subproc_vec_env.py:162
     MJB_REQUIRE(a->state && a->mean && a->costs, "mjb_rollout_reacher: state, mean and costs are required");
     MJB_CUDA(cudaSetDevice(m->device));
-    const int block = 64;
+    const int block = MJB_ROLLOUT_BLOCK;
     const int grid = (a->K + block - 1) / block;
     cudaStream_t s = (cudaStream_t)stream;
-    if (m->fits_sawyer)
-        mjb::rollout_reacher_kernel<mjb::SawyerTraits><<<grid, block, 0, s>>>(m->d_params, m->n_instances, *a);
-    else
-        mjb::rollout_reacher_kernel<mjb::DenseTraits><<<grid, block, 0, s>>>(m->d_params, m->n_instances, *a);
+    const bool extra = a->qv_traj || a->next_obs || a->ncon;
+    const bool use_const = m->n_instances == 1;
+    if (use_const) {
+        // constant bank is per device; re-upload only when another model (or an updated one) was there
+        static unsigned long long owner[64] = {0};
+        const int dev = m->device & 63;
+        if (owner[dev] != m->serial) {
+            if (owner[dev] != 0) MJB_CUDA(cudaDeviceSynchronize());   // kernels of the previous owner may still read it
+            MJB_CUDA(cudaMemcpyToSymbolAsync(mjb::c_params, m->h_params, sizeof(double) * CH_NDEV, 0, cudaMemcpyHostToDevice, s));
+            owner[dev] = m->serial;
+        }
+    }
+#define MJB_LAUNCH(T, P, E) mjb::rollout_reacher_kernel<mjb::T, mjb::P, E><<<grid, block, 0, s>>>(m->d_params, m->n_instances, *a)
+    if (m->fits_sawyer) {
+        if (use_const) { if (extra) MJB_LAUNCH(SawyerTraits, ConstParams, true); else MJB_LAUNCH(SawyerTraits, ConstParams, false); }
+        else { if (extra) MJB_LAUNCH(SawyerTraits, GlobalParams, true); else MJB_LAUNCH(SawyerTraits, GlobalParams, false); }
+    } else {
+        // arbitrary offsets / COMs / inertias on the same axis pattern: dense variant, global parameters
+        if (extra) MJB_LAUNCH(DenseTraits, GlobalParams, true); else MJB_LAUNCH(DenseTraits, GlobalParams, false);
+    }
+#undef MJB_LAUNCH
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;
 }

@@ -1,6 +1,7 @@
 // TEST HARNESS (CPU): compiles the product's device math (chain_dynamics.cuh) for the host so the
 // link-frame formulation can be compared with the oracle without a GPU.  Not a product path.
 #include <cstddef>
+#define MJB_HOST_STATS 1
 #include "../../mjmpc_b200/csrc/chain_dynamics.cuh"
 
 using namespace mjb;
@@ -12,15 +13,16 @@ static void run(const double* P, const double* qpos, const double* qvel, const d
     PtrParams prm{P};
     const int fs = (int)P[CS_FRAME_SKIP];
     for (int k = 0; k < K; k++) {
-        double q[7], v[7], u[7], sn[7], cs[7];
+        double q[7], v[7], sn[7], cs[7];
+        HostScratch sc;
         for (int j = 0; j < 7; j++) { q[j] = qpos[j]; v[j] = qvel[j]; }
         for (int t = 0; t < H; t++) {
-            for (int j = 0; j < 7; j++) u[j] = mean[t * 7 + j] + noise[((size_t)k * H + t) * 7 + j];
+            for (int j = 0; j < 7; j++) sc.st(SC_U + j, mean[t * 7 + j] + noise[((size_t)k * H + t) * 7 + j]);
             V3 hand{0, 0, 0};
             for (int s = 0; s < fs; s++) {
-                for (int j = 0; j < 7; j++) sincos(q[j], &sn[j], &cs[j]);
+                for (int j = 0; j < 7; j++) sincos_joint(q[j], sn[j], cs[j]);
                 if (s == fs - 1) hand = chain_point_world<T>(prm, sn, cs, V3{P[CS_HAND], P[CS_HAND + 1], P[CS_HAND + 2]});
-                chain_substep<T>(prm, q, v, sn, cs, u);
+                chain_substep<T>(prm, sc, q, v, sn, cs);
             }
             costs[(size_t)k * H + t] = reach_cost(hand, V3{target[0], target[1], target[2]});
             for (int j = 0; j < 7; j++) { qv[((size_t)k * H + t) * 14 + j] = q[j]; qv[((size_t)k * H + t) * 14 + 7 + j] = v[j]; }
@@ -44,8 +46,15 @@ extern "C" void hostcheck_mass_bias(const double* P167, const double* q, const d
     for (int i = 0; i < CH_NPARAM; i++) P[i] = P167[i];
     mjb_derive_params(P);
     PtrParams prm{P};
-    double sn[7], cs[7], qd[7], Mm[7][7], b[7];
-    for (int j = 0; j < 7; j++) { sincos(q[j], &sn[j], &cs[j]); qd[j] = v[j]; }
-    chain_mass_bias<SawyerTraits>(prm, sn, cs, qd, Mm, b);
-    for (int i = 0; i < 7; i++) { bias[i] = b[i]; for (int j = 0; j <= i; j++) { M[i * 7 + j] = Mm[i][j]; M[j * 7 + i] = Mm[i][j]; } }
+    double sn[7], cs[7], qd[7], b[7];
+    HostScratch sc;
+    for (int j = 0; j < 7; j++) { sincos_joint(q[j], sn[j], cs[j]); qd[j] = v[j]; }
+    chain_mass_bias<SawyerTraits>(prm, sc, sn, cs, qd, b);
+    for (int i = 0; i < 7; i++) { bias[i] = b[i]; for (int j = 0; j <= i; j++) { M[i * 7 + j] = sc.ld(sc_m(i, j)); M[j * 7 + i] = M[i * 7 + j]; } }
+}
+
+extern "C" void hostcheck_sincos(double x, double* s, double* c) { mjb::sincos_joint(x, *s, *c); }
+
+extern "C" void hostcheck_stats(long long* out, int reset) {
+    for (int i = 0; i < 4; i++) { out[i] = mjb::g_stats[i]; if (reset) mjb::g_stats[i] = 0; }
 }

@@ -14,7 +14,7 @@ def test_moments_and_filter():
     assert eps.shape == (K, H, d)
     # steps 0,1 are unfiltered N(0, cov)
     for t in (0, 1):
-        np.testing.assert_allclose(eps[:, t].mean(0), 0, atol=5 * np.sqrt(np.diag(cov) / K))
+        assert np.all(np.abs(eps[:, t].mean(0)) < 5 * np.sqrt(np.diag(cov) / K))
         np.testing.assert_allclose(eps[:, t].var(0), np.diag(cov), rtol=0.02)
     # un-filter and recover white noise: z_i = (eps_i - b1 eps_{i-1} - b2 eps_{i-2}) / b0
     z = (eps[:, 2:] - b[1] * eps[:, 1:-1] - b[2] * eps[:, :-2]) / b[0]
