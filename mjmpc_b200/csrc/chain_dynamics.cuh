@@ -24,6 +24,14 @@
 #include <utility>
 #include "chain_model.h"
 
+// hide a value from constant propagation (keeps the compiler from cloning the factor/solve loop body
+// per phase: one copy of that code is the point)
+#if defined(__CUDA_ARCH__)
+#define MJB_OPAQUE(x) asm volatile("" : "+r"(x))
+#else
+#define MJB_OPAQUE(x) ((void)0)
+#endif
+
 #if defined(__CUDACC__)
 #define MJB_HD __host__ __device__ __forceinline__
 #define MJB_NOINLINE static __host__ __device__ __noinline__
@@ -438,59 +446,77 @@ MJB_NOINLINE void contact_row(P prm, double* io, double cx, double cy, double cz
 }
 
 // Constraint rows of one particle.  Limit row j acts on dof j alone with Jacobian entry sg = +1 below
-// the range, -1 above it (at most one side can be violated); D == 0 marks an absent row.  The
-// contact row's Jacobian lives in the scratch (SC_JC) and is only touched when Dc != 0.
+// the range, -1 above it (at most one side can be violated).  Stored in joint coordinates:
+//   D[j]  = 1/R_j, 0 when the row is absent
+//   b[j]  = sg * aref_j: the row is active at acceleration a iff sg (a_j - b_j) < 0, it then adds
+//           D_j to H_jj, D_j b_j to the right-hand side, and exerts the joint force D_j (b_j - a_j).
+// The contact row's Jacobian lives in the scratch (SC_JC) and is only touched when Dc != 0.
 struct Rows {
-    double D[7], aref[7];
+    double D[7], b[7];
     unsigned below;            // bit j: joint j is below its range (sg = +1)
     double Dc, arefc;
 };
-MJB_HD double row_sg(const Rows& R, int j) { return ((R.below >> j) & 1u) ? 1.0 : -1.0; }
+
+// generic-impedance fallback of make_rows (non-default solimp shapes): out of line
+template <class P>
+MJB_NOINLINE void limit_rows_generic(P prm, const double* qv, double* Db, unsigned* below_any) {
+    const int limited = (int)prm[CS_LIMITED_MASK];
+    unsigned below = 0, any = 0;
+    for (int j = 0; j < 7; j++) {
+        const double lo = prm[CH_RANGE_LO + j], hi = prm[CH_RANGE_HI + j];
+        const bool bl = qv[j] < lo;
+        const double dist = bl ? qv[j] - lo : hi - qv[j];
+        Db[j] = 0.0; Db[7 + j] = 0.0;
+        below |= bl ? (1u << j) : 0u;
+        if (dist < 0.0 && ((limited >> j) & 1)) {
+            const double sg = bl ? 1.0 : -1.0;
+            const RowParams rp = soft_row(prm, dist, sg * qv[7 + j], prm[CH_INVW0 + j]);
+            Db[j] = rp.D; Db[7 + j] = sg * rp.aref;
+            any = 1;
+        }
+    }
+    below_any[0] = below; below_any[1] = any;
+}
 
 template <class T, class P, class S>
 MJB_HD bool make_rows(const P& prm, S& sc, const double (&q)[7], const double (&qd)[7], const double (&sn)[7],
                       const double (&cs)[7], Rows& R) {
     bool any = false;
-    const int limited = (int)prm[CS_LIMITED_MASK];
     const double d0 = prm[CS_IMP_D0], dw = prm[CS_IMP_DW], width = prm[CS_IMP_WIDTH];
-    const double mid = prm[CS_IMP_MID];
-    const double K = prm[CS_SOLK], B = prm[CS_SOLB];
     R.below = 0;
     if (prm[CS_IMP_POWER] == 2.0 && d0 != dw && width > 1e-15) {
         // default impedance shape (power 2): branch-free over the 7 joints, every lane does the same work
-        const double iw = 1.0 / width, imid = 1.0 / mid, i1mid = 1.0 / (1.0 - mid);
+        const int limited = (int)prm[CS_LIMITED_MASK];
+        const double mid = prm[CS_IMP_MID];
+        const double K = prm[CS_SOLK], B = prm[CS_SOLB];
+        const double niw = -1.0 / width, imid = 1.0 / mid, i1mid = 1.0 / (1.0 - mid), dd = dw - d0;
 #pragma unroll
         for (int j = 0; j < 7; j++) {
-            const double lo = prm[CH_RANGE_LO + j], hi = prm[CH_RANGE_HI + j];
-            const bool below = q[j] < lo;
-            const double dist = below ? q[j] - lo : hi - q[j];     // side * (range - q): < 0 when violated
+            const double dlo = q[j] - prm[CH_RANGE_LO + j], dhi = prm[CH_RANGE_HI + j] - q[j];
+            const bool below = dlo < 0.0;
+            const double dist = fmin(dlo, dhi);                    // side * (range - q): < 0 when violated
             const bool viol = dist < 0.0 && ((limited >> j) & 1);
-            const double x = fabs(dist) * iw;
+            const double x = fmin(dist * niw, 1.0);                // penetration / width, saturating (imp = dw at 1)
             const double xm = 1.0 - x;
-            const double y = x <= mid ? (x * x) * imid : 1.0 - (xm * xm) * i1mid;
-            const double imp = x >= 1.0 ? dw : d0 + y * (dw - d0);
+            const double y = x <= mid ? (x * x) * imid : fma(-(xm * xm), i1mid, 1.0);
+            const double imp = fma(y, dd, d0);
             // D = 1 / max(1e-15, (1-imp)*invweight/imp)
             const double den = fmax((1.0 - imp) * prm[CH_INVW0 + j], 1e-15 * imp);
-            const double sg = below ? 1.0 : -1.0;
+            const double kd = K * imp * dist;
             R.D[j] = viol ? imp * rcp_pos(den) : 0.0;
-            R.aref[j] = viol ? -B * (sg * qd[j]) - K * imp * dist : 0.0;
+            R.b[j] = -B * qd[j] - (below ? kd : -kd);              // sg * (-B sg qd - K imp dist)
             R.below |= below ? (1u << j) : 0u;
             any |= viol;
         }
     } else {
+        double qv[14], Db[14];
+        unsigned ba[2];
 #pragma unroll
-        for (int j = 0; j < 7; j++) {
-            const double lo = prm[CH_RANGE_LO + j], hi = prm[CH_RANGE_HI + j];
-            const bool below = q[j] < lo;
-            const double dist = below ? q[j] - lo : hi - q[j];
-            R.D[j] = 0.0; R.aref[j] = 0.0;
-            R.below |= below ? (1u << j) : 0u;
-            if (dist < 0.0 && ((limited >> j) & 1)) {
-                const RowParams rp = soft_row(prm, dist, (below ? 1.0 : -1.0) * qd[j], prm[CH_INVW0 + j]);
-                R.D[j] = rp.D; R.aref[j] = rp.aref;
-                any = true;
-            }
-        }
+        for (int j = 0; j < 7; j++) { qv[j] = q[j]; qv[7 + j] = qd[j]; }
+        limit_rows_generic(prm, qv, Db, ba);
+#pragma unroll
+        for (int j = 0; j < 7; j++) { R.D[j] = Db[j]; R.b[j] = Db[7 + j]; }
+        R.below = ba[0]; any = ba[1] != 0;
     }
     R.Dc = 0.0; R.arefc = 0.0;
     const double radius = prm[CS_CON_RADIUS];
@@ -511,169 +537,253 @@ MJB_HD bool make_rows(const P& prm, S& sc, const double (&q)[7], const double (&
     return any;
 }
 
-// active-set bit mask at acceleration a (bit j: limit row j, bit 7: contact); jc = Jc.a - arefc
-template <class S>
-MJB_HD unsigned active_set(const Rows& R, const S& sc, const double (&a)[7], double& jc) {
-    unsigned act = 0;
-#pragma unroll
-    for (int j = 0; j < 7; j++) if (R.D[j] > 0.0 && row_sg(R, j) * a[j] - R.aref[j] < 0.0) act |= 1u << j;
-    jc = 0.0;
-    if (R.Dc > 0.0) {
-        jc = -R.arefc;
-#pragma unroll
-        for (int j = 0; j < 7; j++) jc += sc.ld(SC_JC + j) * a[j];
-        if (jc < 0.0) act |= 128u;
+// --------------------------------------------------------------------------------------------------
+// Slow path of the constraint solve, out of line and rolled: used when the sphere-plane contact row
+// exists or when the unit active-set steps of the fast path did not settle.  Same problem, solved
+// robustly: Newton on the active set from a = 0 with an exact line search (phi'(t) is piecewise
+// linear and increasing: bracket the root between breakpoints, solve the linear piece), then the
+// implicit-damping Euler solve.  Packed buffer (doubles):
+//   w[0..49)   M (lower triangle valid)      w[49..56)  f            w[56..63) h*damping
+//   w[63..70)  D (limit rows)                w[70..77)  b            w[77..84) sg (+1 below / -1 above)
+//   w[84..91)  Jc                            w[91] Dc   w[92] arefc
+//   out: w[49..56) = qacc of the Euler solve
+// --------------------------------------------------------------------------------------------------
+MJB_NOINLINE void chol_solve7(double (*A)[7], double* x) {      // SPD solve, lower triangle of A, in place
+    #pragma unroll 1
+    for (int j = 0; j < 7; j++) {
+        double d = A[j][j];
+        #pragma unroll 1
+        for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
+        d = sqrt(d);
+        A[j][j] = d;
+        #pragma unroll 1
+        for (int i = j + 1; i < 7; i++) {
+            double t = A[i][j];
+            #pragma unroll 1
+            for (int k = 0; k < j; k++) t -= A[i][k] * A[j][k];
+            A[i][j] = t / d;
+        }
     }
-    return act;
+#pragma unroll 1
+    for (int i = 0; i < 7; i++) { double t = x[i];
+#pragma unroll 1
+        for (int k = 0; k < i; k++) t -= A[i][k] * x[k]; x[i] = t / A[i][i]; }
+#pragma unroll 1
+    for (int i = 6; i >= 0; i--) { double t = x[i];
+#pragma unroll 1
+        for (int k = i + 1; k < 7; k++) t -= A[k][i] * x[k]; x[i] = t / A[i][i]; }
 }
 
-// Exact line search on phi(t) = obj(a + t p): phi'(t) is piecewise linear and increasing; bracket the
-// root between consecutive breakpoints, then solve the linear piece.  Rare path (the active set
-// changed along a Newton step), so it is rolled, out of line, and fed through one packed buffer:
-// w = [ M (49, lower triangle valid) | f 7 | a 7 | p 7 | jar 8 | jp 8 | D 8 ].
-MJB_NOINLINE double line_search(const double* w) {
-    const double *M49 = w, *f = w + 49, *a = w + 56, *p = w + 63, *jar = w + 70, *jp = w + 78, *Dr = w + 86;
-    double g0 = 0.0, h0 = 0.0;
-    for (int i = 0; i < 7; i++) {
-        double s = 0.0, ga = -f[i];
-        for (int k = 0; k < 7; k++) {
-            const double mik = k <= i ? M49[i * 7 + k] : M49[k * 7 + i];
-            s += mik * p[k]; ga += mik * a[k];
+MJB_NOINLINE void constrained_solve_slow(double* w) {
+    const double *M49 = w, *f = w + 49, *hd = w + 56, *D = w + 63, *b = w + 70, *sg = w + 77, *Jc = w + 84;
+    const double Dc = w[91], arefc = w[92];
+    double a[7], A[7][7], x[7], jar[8], jp[8], Dr[8];
+    #pragma unroll 1
+    for (int j = 0; j < 7; j++) { a[j] = 0.0; Dr[j] = D[j]; }
+    Dr[7] = Dc;
+    #pragma unroll 1
+    for (int it = 0; it < 60; it++) {
+        // residuals J_r a - aref_r and active set at a
+        #pragma unroll 1
+        for (int j = 0; j < 7; j++) jar[j] = sg[j] * (a[j] - b[j]);
+        jar[7] = -arefc;
+        #pragma unroll 1
+        for (int j = 0; j < 7; j++) jar[7] += Jc[j] * a[j];
+        #pragma unroll 1
+        for (int i = 0; i < 7; i++) {
+            #pragma unroll 1
+            for (int j = 0; j <= i; j++) A[i][j] = M49[i * 7 + j] + ((Dc > 0.0 && jar[7] < 0.0) ? Dc * Jc[i] * Jc[j] : 0.0);
+            const bool on = D[i] > 0.0 && jar[i] < 0.0;
+            if (on) A[i][i] += D[i];
+            x[i] = f[i] + (on ? D[i] * b[i] : 0.0) + ((Dc > 0.0 && jar[7] < 0.0) ? Dc * arefc * Jc[i] : 0.0);
         }
-        g0 += p[i] * ga; h0 += p[i] * s;
-    }
-    double lo = 0.0, hi = INFINITY;
-    for (int r = 0; r < 8; r++) {
-        if (Dr[r] > 0.0 && jp[r] != 0.0) {
-            const double t = -jar[r] / jp[r];
-            if (t > 0.0) {
-                double d = g0 + t * h0;
-                for (int s = 0; s < 8; s++) {
-                    const double js = jar[s] + t * jp[s];
-                    if (Dr[s] > 0.0 && js < 0.0) d += Dr[s] * js * jp[s];
+        chol_solve7(A, x);
+        // same active set at the candidate -> optimum
+        bool same = true;
+        double jcx = -arefc;
+        #pragma unroll 1
+        for (int j = 0; j < 7; j++) jcx += Jc[j] * x[j];
+        #pragma unroll 1
+        for (int j = 0; j < 7; j++) same = same && ((D[j] > 0.0 && sg[j] * (x[j] - b[j]) < 0.0) == (D[j] > 0.0 && jar[j] < 0.0));
+        same = same && ((Dc > 0.0 && jcx < 0.0) == (Dc > 0.0 && jar[7] < 0.0));
+        if (same) { for (int j = 0; j < 7; j++) a[j] = x[j]; break; }
+        // exact line search along p = x - a
+        double g0 = 0.0, h0 = 0.0;
+        #pragma unroll 1
+        for (int i = 0; i < 7; i++) {
+            double s = 0.0, ga = -f[i];
+            #pragma unroll 1
+            for (int k = 0; k < 7; k++) {
+                const double mik = k <= i ? M49[i * 7 + k] : M49[k * 7 + i];
+                s += mik * (x[k] - a[k]); ga += mik * a[k];
+            }
+            g0 += (x[i] - a[i]) * ga; h0 += (x[i] - a[i]) * s;
+        }
+        #pragma unroll 1
+        for (int j = 0; j < 7; j++) jp[j] = sg[j] * (x[j] - a[j]);
+        jp[7] = jcx - jar[7];
+        double lo = 0.0, hi = INFINITY;
+        #pragma unroll 1
+        for (int r = 0; r < 8; r++) {
+            if (Dr[r] > 0.0 && jp[r] != 0.0) {
+                const double t = -jar[r] / jp[r];
+                if (t > 0.0) {
+                    double d = g0 + t * h0;
+                    #pragma unroll 1
+                    for (int q = 0; q < 8; q++) {
+                        const double js = jar[q] + t * jp[q];
+                        if (Dr[q] > 0.0 && js < 0.0) d += Dr[q] * js * jp[q];
+                    }
+                    if (d <= 0.0) { if (t > lo) lo = t; }
+                    else if (t < hi) hi = t;
                 }
-                if (d <= 0.0) { if (t > lo) lo = t; }
-                else if (t < hi) hi = t;
             }
         }
+        const double mid = (hi == INFINITY) ? lo + 1.0 : 0.5 * (lo + hi);
+        double c0 = g0, c1 = h0;
+        #pragma unroll 1
+        for (int q = 0; q < 8; q++)
+            if (Dr[q] > 0.0 && jar[q] + mid * jp[q] < 0.0) { c0 += Dr[q] * jar[q] * jp[q]; c1 += Dr[q] * jp[q] * jp[q]; }
+        double t = -c0 / c1;
+        t = t < lo ? lo : (t > hi ? hi : t);
+        #pragma unroll 1
+        for (int j = 0; j < 7; j++) a[j] += t * (x[j] - a[j]);
     }
-    const double mid = (hi == INFINITY) ? lo + 1.0 : 0.5 * (lo + hi);
-    double c0 = g0, c1 = h0;
-    for (int s = 0; s < 8; s++)
-        if (Dr[s] > 0.0 && jar[s] + mid * jp[s] < 0.0) { c0 += Dr[s] * jar[s] * jp[s]; c1 += Dr[s] * jp[s] * jp[s]; }
-    double t = -c0 / c1;
-    t = t < lo ? lo : (t > hi ? hi : t);
-    return t;
+    // constraint force at the optimum, then (M + hB) qacc = f + J'lambda
+    double jc = -arefc;
+    #pragma unroll 1
+    for (int j = 0; j < 7; j++) jc += Jc[j] * a[j];
+    const double lc = (Dc > 0.0 && jc < 0.0) ? -Dc * jc : 0.0;
+    #pragma unroll 1
+    for (int i = 0; i < 7; i++) {
+        const double r = sg[i] * (a[i] - b[i]);
+        x[i] = f[i] + ((D[i] > 0.0 && r < 0.0) ? D[i] * (b[i] - a[i]) : 0.0) + lc * Jc[i];
+        #pragma unroll 1
+        for (int j = 0; j <= i; j++) A[i][j] = M49[i * 7 + j];
+        A[i][i] += hd[i];
+    }
+    chol_solve7(A, x);
+    #pragma unroll 1
+    for (int j = 0; j < 7; j++) w[49 + j] = x[j];
 }
 
-// One mj_step of the chain: forward dynamics at (q, qd) under the control held in the scratch
-// (SC_U), then Euler advance.  sn/cs must hold sin/cos of q on entry.  Returns true when a
-// constraint row was present.
+// One mj_step of the chain: forward dynamics at (q, qd) under the actuator torques held in the scratch
+// (SC_U = gear * clip(ctrl), computed once per env step), then Euler advance.  sn/cs must hold sin/cos
+// of q on entry.  Returns true when a constraint row was present.
 //
 // Constraint forces: exact minimiser over a of 1/2 a'Ma - f'a + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
-// by Newton on the active set (each piece of the objective is quadratic, so a step that keeps its
-// active set lands on the optimum).  The Newton solves and the final implicit-damping Euler solve
-// (M + hB) a = f + J'lambda share ONE factor/solve site: phase 0 = Newton iterations, phase 1 = Euler.
+// by Newton on the active set (each piece of the objective is quadratic, so a solve whose own active
+// set equals the set it was built from satisfies the optimality conditions).  Fast path (limit rows
+// only -- they act on single dofs, so H = M + diagonal): the Newton solves and the final
+// implicit-damping Euler solve (M + hB) a = f + J'lambda share ONE factor/solve site fed by a diagonal
+// increment and a right-hand-side increment:
+//     Newton:  H = M + diag(dadd),  rhs = f + radd,   dadd = D on the active rows, radd = D b
+//     Euler:   H = M + diag(h B),   rhs = f + fc,     fc = D (b - a) on the active rows
 template <class T, class P, class S>
 MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], const double (&sn)[7],
                           const double (&cs)[7]) {
     double f[7];
     chain_mass_bias<T>(prm, sc, sn, cs, qd, f);
 #pragma unroll
-    for (int j = 0; j < 7; j++) {
-        double c = sc.ld(SC_U + j);
-        c = fmin(fmax(c, prm[CH_CTRL_LO + j]), prm[CH_CTRL_HI + j]);
-        f[j] = prm[CH_GEAR + j] * c - prm[CH_DAMPING + j] * qd[j] - f[j];
-    }
+    for (int j = 0; j < 7; j++) f[j] = sc.ld(SC_U + j) - prm[CH_DAMPING + j] * qd[j] - f[j];
     Rows R;
     const bool any = make_rows<T>(prm, sc, q, qd, sn, cs, R);
-    double a[7], fc[7], x[7];
-    // First active-set guess from the decoupled accelerations f_j / M_jj (the contact row from its
-    // reference acceleration alone).  Any guess is admissible: a solve whose own active set equals the
-    // set it was built from satisfies the optimality conditions of the strictly convex problem.
+    double dadd[7], radd[7], x[7];
     unsigned act = 0;
+    bool slow = R.Dc > 0.0;
+    int phase = 1;
+    if (!any) {
 #pragma unroll
-    for (int j = 0; j < 7; j++) {
-        a[j] = 0.0; fc[j] = 0.0;
-        if (R.D[j] > 0.0 && row_sg(R, j) * f[j] < R.aref[j] * sc.ld(sc_m(j, j))) act |= 1u << j;
-    }
-    if (R.Dc > 0.0 && R.arefc > 0.0) act |= 128u;
-    double jc = 0.0;
-    int phase = any ? 0 : 1;
-    MJB_STAT(0); if (any) MJB_STAT(1);
-    for (int it = 0;; it++) {
-        double H[7][7], dinv[7];
-        MJB_STAT(2);
-        const unsigned use = phase == 0 ? act : 0u;
+        for (int j = 0; j < 7; j++) { dadd[j] = prm[CH_HDAMP + j]; radd[j] = 0.0; }
+    } else {
+        // first active-set guess from the decoupled accelerations f_j / M_jj; any guess is admissible,
+        // it only has to be confirmed by its own solve
+        phase = 0;
 #pragma unroll
-        for (int i = 0; i < 7; i++) {
-#pragma unroll
-            for (int j = 0; j <= i; j++) H[i][j] = sc.ld(sc_m(i, j));
-            const double di = ((use >> i) & 1u) ? R.D[i] : 0.0;
-            H[i][i] += phase == 0 ? di : prm[CH_HDAMP + i];
-            x[i] = f[i] + (phase == 0 ? di * R.aref[i] * row_sg(R, i) : fc[i]);
+        for (int j = 0; j < 7; j++) {
+            const double bm = R.b[j] * sc.ld(sc_m(j, j));
+            const bool on = (R.D[j] > 0.0) & (((R.below >> j) & 1u) ? f[j] < bm : f[j] > bm);
+            act |= on ? (1u << j) : 0u;
+            dadd[j] = on ? R.D[j] : 0.0;
+            radd[j] = dadd[j] * R.b[j];
         }
-        if (use & 128u) {
-            double Jc[7];
-#pragma unroll
-            for (int i = 0; i < 7; i++) Jc[i] = sc.ld(SC_JC + i);
+    }
+    MJB_STAT(0); if (any) MJB_STAT(1);
+    if (!slow) {
+        // Straight-line, bottom-tested loop: every trip is one factor/solve followed by the (branch-free)
+        // active-set check that prepares the next trip's increments.  On the final (Euler) trip the check
+        // is dead work (~70 instructions), but with no exit in the middle of the body the compiler keeps
+        // ONE copy of the factor/solve instead of rotating the loop into "solve; while (..) { check; solve }",
+        // which doubled its instruction-cache footprint.
+        int iters = 0;
+        bool done;
+#pragma unroll 1
+        do {
+            double H[7][7], dinv[7];
+            MJB_OPAQUE(phase);
+            MJB_STAT(2);
 #pragma unroll
             for (int i = 0; i < 7; i++) {
 #pragma unroll
-                for (int j = 0; j <= i; j++) H[i][j] += R.Dc * Jc[i] * Jc[j];
-                x[i] += R.Dc * R.arefc * Jc[i];
+                for (int j = 0; j < i; j++) H[i][j] = sc.ld(sc_m(i, j));
+                H[i][i] = sc.ld(sc_m(i, i)) + dadd[i];
+                x[i] = f[i] + radd[i];
             }
-        }
-        ldl7(H, dinv);
-        ldl7_solve(H, dinv, x);
-        if (phase == 1) break;
-        double jcx;
-        const unsigned actx = active_set(R, sc, x, jcx);
-        if (actx == act || it >= 48) {
-            // optimum reached: constraint force lambda_r = -D_r (J_r a - aref_r) on the active rows
+            ldl7(H, dinv);
+            ldl7_solve(H, dinv, x);
+            done = phase == 1;
+            unsigned actx = 0;
 #pragma unroll
             for (int j = 0; j < 7; j++) {
-                const double sg = row_sg(R, j);
-                const double lam = ((actx >> j) & 1u) ? -R.D[j] * (sg * x[j] - R.aref[j]) : 0.0;
-                fc[j] = sg * lam;
+                const bool on = (R.D[j] > 0.0) & (((R.below >> j) & 1u) ? x[j] < R.b[j] : x[j] > R.b[j]);
+                actx |= on ? (1u << j) : 0u;
             }
-            if (actx & 128u) {
-                const double lc = -R.Dc * jcx;
+            // same set as the one the solve was built from: optimum, next trip is the Euler solve with the
+            // joint-space constraint force D_j (b_j - a_j); otherwise a plain active-set (unit Newton) step
+            const bool ok = actx == act;
 #pragma unroll
-                for (int j = 0; j < 7; j++) fc[j] += lc * sc.ld(SC_JC + j);
+            for (int j = 0; j < 7; j++) {
+                const bool on = (actx >> j) & 1u;
+                dadd[j] = ok ? prm[CH_HDAMP + j] : (on ? R.D[j] : 0.0);
+                radd[j] = on ? R.D[j] * (R.b[j] - (ok ? x[j] : 0.0)) : 0.0;
             }
-            phase = 1;
-            continue;
-        }
-        if (it < 4) {
-            // plain active-set (unit Newton) step: adopt the candidate and its active set
-#pragma unroll
-            for (int j = 0; j < 7; j++) a[j] = x[j];
-            act = actx; jc = jcx;
-            continue;
-        }
-        // safety net (the unit steps did not settle): globally convergent Newton with an exact line search
-        // from the current point a, whose active set is `act` by construction
-        double w[94];
+            act = actx;
+            iters++;
+            if (!done) {
+                phase = ok ? 1 : 0;
+                if (!ok && iters > 5) { slow = true; done = true; }    // unit steps did not settle (never seen)
+            }
+        } while (!done);
+    }
+    if (slow) {
+        double w[93];
+        MJB_STAT(3);
 #pragma unroll
         for (int j = 0; j < 7; j++) {
-            const double pj = x[j] - a[j], sg = row_sg(R, j);
-            w[49 + j] = f[j]; w[56 + j] = a[j]; w[63 + j] = pj;
-            w[70 + j] = sg * a[j] - R.aref[j]; w[78 + j] = sg * pj; w[86 + j] = R.D[j];
 #pragma unroll
             for (int k = 0; k <= j; k++) w[j * 7 + k] = sc.ld(sc_m(j, k));
+            w[49 + j] = f[j]; w[56 + j] = prm[CH_HDAMP + j];
+            w[63 + j] = R.D[j]; w[70 + j] = R.b[j]; w[77 + j] = ((R.below >> j) & 1u) ? 1.0 : -1.0;
+            w[84 + j] = R.Dc > 0.0 ? sc.ld(SC_JC + j) : 0.0;
         }
-        w[77] = jc; w[85] = jcx - jc; w[93] = R.Dc;
-        MJB_STAT(3);
-        const double t = line_search(w);
+        w[91] = R.Dc; w[92] = R.arefc;
+        constrained_solve_slow(w);
 #pragma unroll
-        for (int j = 0; j < 7; j++) a[j] += t * (x[j] - a[j]);
-        act = active_set(R, sc, a, jc);
+        for (int j = 0; j < 7; j++) x[j] = w[49 + j];
     }
     const double h = prm[CS_TIMESTEP];
 #pragma unroll
     for (int j = 0; j < 7; j++) { qd[j] += h * x[j]; q[j] += h * qd[j]; }
     return any;
+}
+
+// Motor torque of joint j under control u: gear * clip(u, ctrlrange) (MuJoCo mj_fwdActuation with
+// ctrllimited motors, sawyer.xml:101-109).  The control is held over the frame_skip substeps.
+template <class P> MJB_HD double actuator_torque(const P& prm, int j, double u) {
+    const double lo = prm[CH_CTRL_LO + j], hi = prm[CH_CTRL_HI + j];
+    u = u < lo ? lo : u;
+    u = u > hi ? hi : u;
+    return prm[CH_GEAR + j] * u;
 }
 
 // The reference's step cost (reacher_env.py:31-35): -reward = |h-g|_1 + 5 |h-g|_2

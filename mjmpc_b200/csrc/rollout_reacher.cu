@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, 4) rollout_reacher_kernel(c
             for (int j = 0; j < 7; j++) {
                 double x = __ldg(mean + t * 7 + j);
                 if (np) { x += __ldg(nj); nj += a.noise_sj; }
-                sc.st(SC_U + j, x);
+                sc.st(SC_U + j, actuator_torque(prm, j, x));   // held over the frame_skip substeps
                 if (ap) { *aj = x; aj += a.act_sj; }
             }
             if (np) np += a.noise_st;

@@ -17,7 +17,7 @@ static void run(const double* P, const double* qpos, const double* qvel, const d
         HostScratch sc;
         for (int j = 0; j < 7; j++) { q[j] = qpos[j]; v[j] = qvel[j]; }
         for (int t = 0; t < H; t++) {
-            for (int j = 0; j < 7; j++) sc.st(SC_U + j, mean[t * 7 + j] + noise[((size_t)k * H + t) * 7 + j]);
+            for (int j = 0; j < 7; j++) sc.st(SC_U + j, actuator_torque(prm, j, mean[t * 7 + j] + noise[((size_t)k * H + t) * 7 + j]));
             V3 hand{0, 0, 0};
             for (int s = 0; s < fs; s++) {
                 for (int j = 0; j < 7; j++) sincos_joint(q[j], sn[j], cs[j]);

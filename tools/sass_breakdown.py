@@ -33,3 +33,24 @@ for s in tot:
         print(s[:110], tot[s])
         if want in s:
             for k, v in per[s].most_common(): print("    %-28s %d" % (k, v))
+
+# opcode histogram of the hot part (cold out-of-line helpers excluded)
+cold = {"soft_row", "line_search", "contact_row"}
+sec = None; cur = None
+ops = collections.Counter(); byfn = collections.defaultdict(collections.Counter)
+for l in txt:
+    if l.startswith(".text."):
+        sec = l.strip(); continue
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+    if m:
+        f = os.path.basename(m.group(1)); cur = fn_of(int(m.group(2))) if f == "chain_dynamics.cuh" else f; continue
+    m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(@!?U?P\d+\s+)?(\S+)", l)
+    if m and sec and want in sec and cur not in cold:
+        op = m.group(2).split(".")[0].rstrip(";")
+        ops[op] += 1; byfn[cur][op] += 1
+print("hot opcode histogram:", sum(ops.values()))
+print("  ", ops.most_common(30))
+fp64 = sum(v for k, v in ops.items() if k in ("DFMA", "DMUL", "DADD", "DSETP", "MUFU"))
+print("   fp64-pipe-ish:", fp64)
+for fn in ("chain_substep", "make_rows", "rollout_reacher.cu", "rot", "sincos_joint", "?"):
+    print("  ", fn, byfn[fn].most_common(12))
