@@ -57,6 +57,9 @@ MJB_HD V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
 MJB_HD V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 MJB_HD V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
 MJB_HD V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+// min / max without the NaN-propagation fix-ups of fmin/fmax (9 instructions each in FP64 on sm_100a)
+MJB_HD double dmin(double a, double b) { return a < b ? a : b; }
+MJB_HD double dmax(double a, double b) { return a > b ? a : b; }
 template <int AX> MJB_HD double comp(V3 v) { return AX == 0 ? v.x : (AX == 1 ? v.y : v.z); }
 
 // a x b where b's components outside MASK are structurally zero (bit k = component k)
@@ -494,16 +497,17 @@ MJB_HD bool make_rows(const P& prm, S& sc, const double (&q)[7], const double (&
         for (int j = 0; j < 7; j++) {
             const double dlo = q[j] - prm[CH_RANGE_LO + j], dhi = prm[CH_RANGE_HI + j] - q[j];
             const bool below = dlo < 0.0;
-            const double dist = fmin(dlo, dhi);                    // side * (range - q): < 0 when violated
+            const double dist = dmin(dlo, dhi);                    // side * (range - q): < 0 when violated
             const bool viol = dist < 0.0 && ((limited >> j) & 1);
-            const double x = fmin(dist * niw, 1.0);                // penetration / width, saturating (imp = dw at 1)
+            const double x = dmin(dist * niw, 1.0);                // penetration / width, saturating (imp = dw at 1)
             const double xm = 1.0 - x;
             const double y = x <= mid ? (x * x) * imid : fma(-(xm * xm), i1mid, 1.0);
             const double imp = fma(y, dd, d0);
             // D = 1 / max(1e-15, (1-imp)*invweight/imp)
-            const double den = fmax((1.0 - imp) * prm[CH_INVW0 + j], 1e-15 * imp);
+            const double den = dmax((1.0 - imp) * prm[CH_INVW0 + j], 1e-15 * imp);
             const double kd = K * imp * dist;
-            R.D[j] = viol ? imp * rcp_pos(den) : 0.0;
+            const double dj = imp * rcp_pos(den);
+            R.D[j] = viol ? dj : 0.0;
             R.b[j] = -B * qd[j] - (below ? kd : -kd);              // sg * (-B sg qd - K imp dist)
             R.below |= below ? (1u << j) : 0u;
             any |= viol;
@@ -710,13 +714,12 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
     }
     MJB_STAT(0); if (any) MJB_STAT(1);
     if (!slow) {
-        // Straight-line, bottom-tested loop: every trip is one factor/solve followed by the (branch-free)
-        // active-set check that prepares the next trip's increments.  On the final (Euler) trip the check
-        // is dead work (~70 instructions), but with no exit in the middle of the body the compiler keeps
-        // ONE copy of the factor/solve instead of rotating the loop into "solve; while (..) { check; solve }",
-        // which doubled its instruction-cache footprint.
+        // Every trip is one factor/solve; a Newton trip then checks its active set and prepares the next
+        // trip's increments.  The loop condition is laundered (MJB_OPAQUE) so the compiler cannot thread the
+        // "skip the check on the Euler trip" branch into a mid-body exit and rotate the loop into
+        // "solve; while (..) { check; solve }" -- that doubled the instruction-cache footprint of the solve.
         int iters = 0;
-        bool done;
+        int again;
 #pragma unroll 1
         do {
             double H[7][7], dinv[7];
@@ -731,29 +734,30 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
             }
             ldl7(H, dinv);
             ldl7_solve(H, dinv, x);
-            done = phase == 1;
-            unsigned actx = 0;
+            again = 0;
+            if (phase == 0) {
+                unsigned actx = 0;
 #pragma unroll
-            for (int j = 0; j < 7; j++) {
-                const bool on = (R.D[j] > 0.0) & (((R.below >> j) & 1u) ? x[j] < R.b[j] : x[j] > R.b[j]);
-                actx |= on ? (1u << j) : 0u;
-            }
-            // same set as the one the solve was built from: optimum, next trip is the Euler solve with the
-            // joint-space constraint force D_j (b_j - a_j); otherwise a plain active-set (unit Newton) step
-            const bool ok = actx == act;
+                for (int j = 0; j < 7; j++) {
+                    const bool on = (R.D[j] > 0.0) & (((R.below >> j) & 1u) ? x[j] < R.b[j] : x[j] > R.b[j]);
+                    actx |= on ? (1u << j) : 0u;
+                }
+                // same set as the one the solve was built from: optimum, next trip is the Euler solve with
+                // the joint-space constraint force D_j (b_j - a_j); otherwise a plain active-set (unit Newton) step
+                const bool ok = actx == act;
 #pragma unroll
-            for (int j = 0; j < 7; j++) {
-                const bool on = (actx >> j) & 1u;
-                dadd[j] = ok ? prm[CH_HDAMP + j] : (on ? R.D[j] : 0.0);
-                radd[j] = on ? R.D[j] * (R.b[j] - (ok ? x[j] : 0.0)) : 0.0;
-            }
-            act = actx;
-            iters++;
-            if (!done) {
+                for (int j = 0; j < 7; j++) {
+                    const bool on = (actx >> j) & 1u;
+                    dadd[j] = ok ? prm[CH_HDAMP + j] : (on ? R.D[j] : 0.0);
+                    radd[j] = on ? R.D[j] * (R.b[j] - (ok ? x[j] : 0.0)) : 0.0;
+                }
+                act = actx;
                 phase = ok ? 1 : 0;
-                if (!ok && iters > 5) { slow = true; done = true; }    // unit steps did not settle (never seen)
+                again = 1;
+                if (!ok && ++iters > 5) { slow = true; again = 0; }    // unit steps did not settle (never seen)
             }
-        } while (!done);
+            MJB_OPAQUE(again);
+        } while (again);
     }
     if (slow) {
         double w[93];
