@@ -154,7 +154,7 @@ def workload_config(n_gpus):
     return {"workload": "MPPI reacher_7dof-v0 K=65536 H=32 n_iters=1 (BASELINE.json configs[2])",
             "num_particles": K_GLOBAL, "horizon": HORIZON, "d_action": D_ACTION,
             "particles_per_gpu": K_GLOBAL // n_gpus, "sharding": "particles, contiguous blocks, %d rank(s)" % n_gpus,
-            "noise": "in-kernel Philox4x32-10 + AR filter", "start_states": "synthetic, SURVEY 8(d), new state every step",
+            "noise": "Philox4x32-10 + AR filter kernel (K2), regenerated every step", "start_states": "synthetic, SURVEY 8(d), new state every step",
             "l2": "per-step working set (noise+actions+costs = 251 MB at N=1) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -207,6 +207,9 @@ def run_own(args):
         env.set_env_state_device(states_dev[i % len(states)][None])
         return ctrl.step_device(None)
 
+    graphed = False
+    if not args.no_graph:
+        graphed = ctrl.enable_cuda_graph(states[0])
     for i in range(args.warmup):
         device_step(i)
     sampler = ClockSampler(local_rank)
@@ -224,6 +227,8 @@ def run_own(args):
 
     # ---- end to end through the public API: host state dict in, host action out ------------------------
     ctrl.reset()
+    if not args.no_graph:
+        ctrl.enable_cuda_graph(states[0])
     for i in range(args.warmup):
         policy.get_action(states[i % len(states)])
     barrier()
@@ -277,7 +282,7 @@ def run_own(args):
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "ms_per_step": e2e_s / args.steps * 1e3,
                 "h2d_bytes_per_step": 17 * 8, "d2h_bytes_per_step": 7 * 8,
                 "api": "MPCPolicy.get_action(state_dict) -> (action ndarray, value)"},
-        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "gpu_launches": KERNELS_PER_STEP * args.steps, "cuda_graph": bool(graphed),
         "roofline": {"kernel": "rollout_reacher_kernel (K1)", "bound": "fp64", "achieved": achieved, "peak": tf.value,
                      "unit": "TFLOP/s", "frac": achieved / tf.value, "traffic": None,
                      "ms_per_launch": k1_ms, "particles_per_launch": kl,
@@ -294,10 +299,11 @@ def run_own(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

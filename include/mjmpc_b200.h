@@ -90,6 +90,8 @@ typedef struct {
     long long K_global;          /* total particles over all shards (zero_last targets K_global-1) */
     unsigned long long seed;     /* controller seed_val */
     unsigned long long offset;   /* low 32 bits: num_steps-like counter; high 32 bits: stream id */
+    const long long* step_ptr;   /* optional DEVICE counter replacing the low 32 bits of offset (lets a captured
+                                    CUDA graph advance the noise stream without re-recording), or NULL */
     const double* cov;           /* (d,d) covariance, Cholesky-factorised inside the kernel */
     double beta0, beta1, beta2;  /* filter_coeffs */
     int zero_last;               /* 1: particle K_global-1 gets noise = -mean (zero control sequence) */

@@ -100,7 +100,7 @@ class NoiseArgs(C.Structure):
     _fields_ = [
         ("K", C.c_int), ("H", C.c_int), ("d", C.c_int),
         ("k_offset", c_ll), ("K_global", c_ll),
-        ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
+        ("seed", C.c_ulonglong), ("offset", C.c_ulonglong), ("step_ptr", C.c_void_p),
         ("cov", C.c_void_p), ("beta0", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
         ("zero_last", C.c_int), ("neg_mean", C.c_void_p),
         ("out", C.c_void_p), ("out_sk", c_ll), ("out_st", c_ll), ("out_sj", c_ll),

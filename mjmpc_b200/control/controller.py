@@ -61,6 +61,8 @@ class Controller(ABC):
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         self.shard = shard if shard is not None else ShardContext()
+        self._graph = None            # captured CUDA graph of one MPC step (enable_cuda_graph)
+        self._step_d = torch.zeros(1, dtype=torch.int64, device=self.device)   # device mirror of num_steps
 
     # ---- abstract surface (controller.py:80-143,203-205) -----------------------------------
     @abstractmethod
@@ -113,6 +115,8 @@ class Controller(ABC):
 
     # ---- the MPC step (controller.py:207-257) ------------------------------------------------
     def optimize(self, state, calc_val=False, hotstart=True):
+        if self._graph is not None and not calc_val and hotstart:
+            return self._optimize_graphed(state), 0.0
         for _ in range(self.n_iters):
             trajectory = self.generate_rollouts(copy.deepcopy(state))
             self._update_distribution(trajectory)
@@ -133,6 +137,9 @@ class Controller(ABC):
         on the device (returned as a (d_action,) tensor) and nothing synchronises.  ``state=None`` keeps
         the state the rollout backend already holds in HBM.  For pipelines whose plant is on the GPU too;
         not part of the reference API."""
+        if self._graph is not None and hotstart:
+            self._replay(state)
+            return self._graph_action
         for _ in range(self.n_iters):
             trajectory = self.generate_rollouts(state)
             self._update_distribution(trajectory)
@@ -141,6 +148,62 @@ class Controller(ABC):
         if hotstart:
             self._shift()
         return action
+
+    # ---- CUDA-graph replay of the step (launch-bound at small K per GPU) --------------------------
+    def _graph_body(self):
+        for _ in range(self.n_iters):
+            trajectory = self.generate_rollouts(None)
+            self._update_distribution(trajectory)
+        action = self._mean[0].clone()
+        self._shift()
+        return action
+
+    def _graphable(self):
+        return self.sample_mode == 'mean' and getattr(self, "base_action", "null") != 'random'
+
+    def enable_cuda_graph(self, state):
+        """Capture one whole MPC step (noise, rollout, update, shift; n_iters included) into a CUDA
+        graph; `optimize` / `step_device` then replay it.  The noise stream advances through a device
+        counter, the state is written into the backend's persistent buffer before every replay.  The
+        controller's distribution is left exactly as it was.  Falls back to eager execution (returns
+        False) for options that need host work inside the step."""
+        if not self._graphable():
+            return False
+        self._graph = None
+        saved = {k: getattr(self, k).clone() for k in ("_mean", "_cov") if hasattr(self, k)}
+        steps = self.num_steps
+        self._set_sim_state_fn(copy.deepcopy(state))
+        self._step_d.fill_(self.num_steps)
+        self._noise_step = self._step_d
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._graph_body()
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._graph_action = self._graph_body()
+        for k, v in saved.items():
+            getattr(self, k).copy_(v)
+        self.num_steps = steps
+        self._graph = g
+        return True
+
+    def disable_cuda_graph(self):
+        self._graph = None
+        self._noise_step = None
+
+    def _replay(self, state):
+        if state is not None:
+            self._set_sim_state_fn(copy.deepcopy(state))
+        self._step_d.fill_(self.num_steps)
+        self._graph.replay()
+        self.num_steps += 1
+
+    def _optimize_graphed(self, state):
+        self._replay(state)
+        return self._graph_action.cpu().numpy()
 
     def get_optimal_value(self, state):
         """controller.py:259-275."""
@@ -173,6 +236,7 @@ class Controller(ABC):
         self._on_params_changed(reshape)
 
     def _on_params_changed(self, reshape):
+        self.disable_cuda_graph()
         if reshape:
             self.reset()
 

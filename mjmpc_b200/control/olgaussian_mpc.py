@@ -66,6 +66,7 @@ class OLGaussianMPC(Controller):
         self._cov = self._to_device(np.diag(self.init_cov)).contiguous()
         self._init_cov_d = self._to_device(self.init_cov)
         self._buffers = {}
+        self._noise_step = None       # device step counter while a CUDA graph is active
 
     # ---- numpy views of the distribution (public attributes in the reference) ----------------
     @property
@@ -74,6 +75,7 @@ class OLGaussianMPC(Controller):
 
     @mean_action.setter
     def mean_action(self, value):
+        self.disable_cuda_graph()
         self._mean = self._to_device(value).reshape(self.horizon, self.d_action).contiguous()
 
     @property
@@ -82,6 +84,7 @@ class OLGaussianMPC(Controller):
 
     @cov_action.setter
     def cov_action(self, value):
+        self.disable_cuda_graph()
         self._cov = self._to_device(value).reshape(self.d_action, self.d_action).contiguous()
 
     # ---- sharding ----------------------------------------------------------------------------------
@@ -115,7 +118,8 @@ class OLGaussianMPC(Controller):
         k0, kl = self.shard.local_range(self.num_particles)
         out = self._buf("noise", (self.horizon, self.d_action, kl)).permute(2, 0, 1)
         delta = generate_noise(self._cov, self.filter_coeffs, shape=(kl, self.horizon), base_seed=self.seed_val,
-                               step=self.num_steps, k_offset=k0, K_global=self.num_particles,
+                               step=self._noise_step if self._noise_step is not None else self.num_steps,
+                               k_offset=k0, K_global=self.num_particles,
                                zero_last_mean=self._mean if self.use_zero_control_seq else None,
                                out=out, device=self.device)
         return delta
@@ -144,6 +148,7 @@ class OLGaussianMPC(Controller):
 
     # ---- olgaussian_mpc.py:131-135 -------------------------------------------------------------------
     def reset(self):
+        self.disable_cuda_graph()
         self.num_steps = 0
         self._mean = torch.zeros((self.horizon, self.d_action), dtype=torch.float64, device=self.device)
         self._cov = self._to_device(np.diag(self.init_cov)).contiguous()

@@ -62,6 +62,9 @@ class PFMPC(Controller):
                                        base_seed=self.seed_val, step=0, k_offset=k0, K_global=self.num_particles,
                                        device=self.device)
 
+    def _graphable(self):
+        return False          # the resampler's r comes from Python's random module every step
+
     def _buf(self, name, shape, dtype=torch.float64):
         key = (name, tuple(shape), dtype)
         b = self._buffers.get(key)

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) noise_kernel(mjb_noise_args a) {
     const unsigned long long gk = (unsigned long long)(a.k_offset + k);
     Philox ph{(unsigned)a.seed, (unsigned)(a.seed >> 32)};
     // counter = (global particle, step counter, t, stream id << 8 | pair index); key = seed
-    const unsigned step_ctr = (unsigned)a.offset;
+    const unsigned step_ctr = a.step_ptr ? (unsigned)(*a.step_ptr) : (unsigned)a.offset;
     const unsigned tag_hi = (unsigned)(a.offset >> 32) << 8;
     double e1[D], e2[D];   // filtered history t-1, t-2
 #pragma unroll

@@ -109,8 +109,12 @@ class GpuReacherVecEnv:
         self._state.copy_(self._state_host, non_blocking=True)
 
     def set_env_state_device(self, state: torch.Tensor):
-        """Device-resident (n_ctrl, 17) states (no host round trip)."""
-        self._state = state.reshape(-1, _lib.STATE_DIM).contiguous()
+        """Device-resident (n_ctrl, 17) states (no host round trip).  Copied into the persistent state
+        buffer so that a captured CUDA graph of the MPC step keeps reading the right address."""
+        state = state.reshape(-1, _lib.STATE_DIM)
+        if state.shape[0] != self._state.shape[0]:
+            self._state = torch.zeros(state.shape[0], _lib.STATE_DIM, dtype=torch.float64, device=self.device)
+        self._state.copy_(state)
 
     def reset(self):
         pass

@@ -34,8 +34,8 @@ def generate_noise(cov, filter_coeffs, shape, base_seed, *, step=0, stream_id=NO
     """Correlated noise samples eps (K,H,d): N(0,cov) draws filtered along the horizon by
     eps[:,i] = b0*eps[:,i] + b1*eps[:,i-1] + b2*eps[:,i-2], i >= 2 (control_utils.py:24-34).
 
-    ``base_seed`` keys the Philox generator and ``step`` plays the role of the reference's
-    ``+ num_steps`` reseeding (the same (seed, step) gives the same samples, as all n_iters of
+    ``base_seed`` keys the Philox generator and ``step`` (an int, or a 1-element int64 CUDA tensor read
+    by the kernel) plays the role of the reference's ``+ num_steps`` reseeding (the same (seed, step) gives the same samples, as all n_iters of
     one MPC step do in the reference).  ``k_offset``/``K_global`` place a shard inside the
     global particle range; ``zero_last_mean`` applies olgaussian_mpc.py:110-111."""
     K, H = int(shape[0]), int(shape[1])
@@ -48,7 +48,11 @@ def generate_noise(cov, filter_coeffs, shape, base_seed, *, step=0, stream_id=NO
     a.k_offset = int(k_offset)
     a.K_global = int(K_global if K_global is not None else k_offset + K)
     a.seed = int(base_seed) & 0xFFFFFFFFFFFFFFFF
-    a.offset = ((int(stream_id) & 0xFFFFFFFF) << 32) | (int(step) & 0xFFFFFFFF)
+    if isinstance(step, torch.Tensor):      # device-resident step counter (CUDA-graph replay)
+        a.offset = (int(stream_id) & 0xFFFFFFFF) << 32
+        a.step_ptr = step.data_ptr()
+    else:
+        a.offset = ((int(stream_id) & 0xFFFFFFFF) << 32) | (int(step) & 0xFFFFFFFF)
     a.cov = cov.data_ptr()
     a.beta0, a.beta1, a.beta2 = [float(b) for b in filter_coeffs]
     if zero_last_mean is not None:

@@ -38,9 +38,9 @@ class ShardContext:
             return t.reshape((1,) + tuple(t.shape))
         import torch.distributed as dist
         t = t.contiguous()
-        out = torch.empty((self.world_size,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t, group=self.group)
-        return out
+        flat = torch.empty(self.world_size * t.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(flat, t.reshape(-1), group=self.group)
+        return flat.reshape((self.world_size,) + tuple(t.shape))
 
 
 SINGLE = ShardContext()

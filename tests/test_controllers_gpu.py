@@ -284,3 +284,64 @@ def test_bad_options_raise():
         dm._update_distribution(_traj(g))
     with pytest.raises(NotImplementedError):
         MPCPolicy("ilqr", {})
+
+
+@pytest.mark.parametrize("name", ["mppi", "cem", "dmd"])
+def test_cuda_graph_step_equals_eager(name, compiled_model):
+    """A captured CUDA graph of the whole MPC step must replay to exactly the eager result, step after step
+    (same kernels, same counters), and leave the distribution untouched at capture time."""
+    from conftest import synthetic_state
+    from mjmpc_b200.control import CEM, DMDMPC, MPPI
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    K, H = 1024, 12
+    kw = dict(horizon=H, num_particles=K, gamma=0.99, n_iters=2, filter_coeffs=[0.25, 0.8, 0.0], seed=9, **_common())
+    mk = {"mppi": lambda: MPPI(init_cov=1.0, base_action='null', lam=0.2, step_size=0.9, alpha=1, **kw),
+          "cem": lambda: CEM(init_cov=1.0, base_action='repeat', elite_frac=0.2, step_size=0.8, beta=0.1, cov_type='full', **kw),
+          "dmd": lambda: DMDMPC(init_cov=0.5, beta=0.1, base_action='null', lam=0.2, step_size=0.8, update_cov=True,
+                                cov_type='diagonal', **kw)}[name]
+    states = [synthetic_state(compiled_model, s) for s in range(4)]
+    outs = []
+    for graphed in (False, True):
+        env = GpuReacherVecEnv(compiled_model)
+        c = mk()
+        c.set_sim_state_fn = env.set_env_state
+        c.rollout_fn = env.rollout_fn
+        if graphed:
+            m0 = c.mean_action.copy()
+            assert c.enable_cuda_graph(states[0])
+            np.testing.assert_array_equal(c.mean_action, m0)
+            assert c.num_steps == 0
+        acts = [c.optimize(st)[0] for st in states]
+        outs.append((np.stack(acts), c.mean_action, c.cov_action, c.num_steps))
+        env.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    np.testing.assert_array_equal(outs[0][2], outs[1][2])
+    assert outs[0][3] == outs[1][3] == 4
+
+
+def test_full_optimize_matches_numpy_oracle_end_to_end(compiled_model, oracle_model):
+    """Whole optimize() against the CPU oracle chain: GPU-generated noise -> oracle rollout -> numpy MPPI
+    update -> shift, three consecutive MPC steps with hot start."""
+    from conftest import synthetic_state
+    from mjmpc_b200.control import MPPI
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    from oracle import control_np as O, mjstep
+    K, H = 256, 10
+    env = GpuReacherVecEnv(compiled_model)
+    c = MPPI(horizon=H, init_cov=0.6, base_action='null', lam=0.3, num_particles=K, step_size=0.8, alpha=0, gamma=0.97,
+             n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=4, **_common())
+    c.set_sim_state_fn = env.set_env_state
+    c.rollout_fn = env.rollout_fn
+    mean = np.zeros((H, 7)); cov = np.diag([0.6] * 7); gs = O.gamma_seq(0.97, H)
+    for step in range(3):
+        st = synthetic_state(compiled_model, 30 + step)
+        noise = np.ascontiguousarray(c.sample_noise().cpu().numpy())          # what optimize() will draw
+        ref = mjstep.rollout(oracle_model, st["qp"], st["qv"], st["target_pos"], mean, noise)
+        mean, _ = O.mppi_update(mean, cov, ref["costs"], ref["actions"], gs, 0.3, 0, 0.8)
+        want_action = mean[0].copy()
+        mean = O.shift_mean(mean, 'null')
+        action, _ = c.optimize(st)
+        np.testing.assert_allclose(action, want_action, rtol=1e-7, atol=1e-10)
+        np.testing.assert_allclose(c.mean_action, mean, rtol=1e-7, atol=1e-10)
+    env.close()
