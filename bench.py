@@ -39,13 +39,19 @@ KERNELS_PER_STEP = 9     # noise, rollout, softmax {prep, traj_cost, weighted_re
 
 
 def synthetic_states(compiled, n, seed=0):
-    """joints inside 10%..90% of their range, qvel ~ N(0,.5^2), random target."""
+    """joints inside 10%..90% of their range, qvel ~ N(0,.5^2), random target.  Joint samples
+    that would put the end-effector sphere inside (or within 2 cm of) the table are redrawn: no episode
+    of the reference can start there."""
+    from mjmpc_b200.envs.model import table_clearance
     rng = np.random.default_rng(seed)
     lo, hi = compiled.tree.jnt_range[:, 0], compiled.tree.jnt_range[:, 1]
     out = []
-    for _ in range(n):
-        out.append(dict(qp=rng.uniform(lo + 0.1 * (hi - lo), hi - 0.1 * (hi - lo)), qv=rng.normal(0, .5, 7),
-                        qa=np.zeros(7), target_pos=rng.uniform([-.3, -.2, -.25], [.3, .2, .25]), timestep=0))
+    while len(out) < n:
+        qp = rng.uniform(lo + 0.1 * (hi - lo), hi - 0.1 * (hi - lo))
+        if table_clearance(compiled.tree, qp) < 0.02:
+            continue
+        out.append(dict(qp=qp, qv=rng.normal(0, .5, 7), qa=np.zeros(7),
+                        target_pos=rng.uniform([-.3, -.2, -.25], [.3, .2, .25]), timestep=0))
     return out
 
 
@@ -154,7 +160,7 @@ def workload_config(n_gpus):
     return {"workload": "MPPI reacher_7dof-v0 K=65536 H=32 n_iters=1 (BASELINE.json configs[2])",
             "num_particles": K_GLOBAL, "horizon": HORIZON, "d_action": D_ACTION,
             "particles_per_gpu": K_GLOBAL // n_gpus, "sharding": "particles, contiguous blocks, %d rank(s)" % n_gpus,
-            "noise": "Philox4x32-10 + AR filter kernel (K2), regenerated every step", "start_states": "synthetic, SURVEY 8(d), new state every step",
+            "noise": "Philox4x32-10 + AR filter kernel (K2), regenerated every step", "start_states": "synthetic, SURVEY 8(d), sphere >= 2 cm above the table, new state every step",
             "l2": "per-step working set (noise+actions+costs = 251 MB at N=1) exceeds the 126 MB L2; no explicit flush"}
 
 

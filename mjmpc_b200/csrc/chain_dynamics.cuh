@@ -182,7 +182,9 @@ template <int MASK> MJB_HD V3 add_m(V3 p, V3 o) {
 // contact Jacobian, the control held over both substeps) are parked here explicitly instead of
 // being spilled by the compiler: on the device a slot is one column of shared memory
 // (slot * BLOCK + thread: conflict-free), on the host a plain array.
-enum { SC_LF = 0, SC_LN = 18, SC_M = 36, SC_JC = 64, SC_U = 71, SC_NSLOT = 78 };
+// SC_M2 (M + Dc Jc Jc', only while a contact row exists) reuses the link-wrench slots, which are dead once
+// the bias forces are known.
+enum { SC_LF = 0, SC_LN = 18, SC_M = 36, SC_JC = 64, SC_U = 71, SC_NSLOT = 78, SC_M2 = 0 };
 MJB_HD constexpr int sc_m(int i, int j) { return SC_M + i * (i + 1) / 2 + j; }   // lower triangle, i >= j
 
 struct HostScratch {
@@ -694,7 +696,7 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
     const bool any = make_rows<T>(prm, sc, q, qd, sn, cs, R);
     double dadd[7], radd[7], x[7];
     unsigned act = 0;
-    bool slow = R.Dc > 0.0;
+    bool slow = false;
     int phase = 1;
     if (!any) {
 #pragma unroll
@@ -712,8 +714,28 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
             radd[j] = dadd[j] * R.b[j];
         }
     }
+    // Contact row (rare): its rank-one term is not diagonal, so the matrix with the term added is kept
+    // as a second copy in the scratch (M2 = M + Dc Jc Jc') and the Newton passes read M or M2 through
+    // a slot offset; all contact bookkeeping sits in cold branches around the shared factor/solve.
+    int moff = 0;
+    bool con_on = false;
+    if (R.Dc > 0.0) {
+#pragma unroll 1
+        for (int i = 0; i < 7; i++) {
+            const double ji = R.Dc * sc.ld(SC_JC + i);
+#pragma unroll 1
+            for (int j = 0; j <= i; j++)
+                sc.st(SC_M2 + i * (i + 1) / 2 + j, sc.ld(SC_M + i * (i + 1) / 2 + j) + ji * sc.ld(SC_JC + j));
+        }
+        con_on = R.arefc > 0.0;          // guess: the reference acceleration alone pushes out of the plane
+        if (con_on) {
+            moff = SC_M2 - SC_M;
+#pragma unroll
+            for (int j = 0; j < 7; j++) radd[j] += R.Dc * R.arefc * sc.ld(SC_JC + j);
+        }
+    }
     MJB_STAT(0); if (any) MJB_STAT(1);
-    if (!slow) {
+    {
         // Every trip is one factor/solve; a Newton trip then checks its active set and prepares the next
         // trip's increments.  The loop condition is laundered (MJB_OPAQUE) so the compiler cannot thread the
         // "skip the check on the Euler trip" branch into a mid-body exit and rotate the loop into
@@ -728,8 +750,8 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
 #pragma unroll
             for (int i = 0; i < 7; i++) {
 #pragma unroll
-                for (int j = 0; j < i; j++) H[i][j] = sc.ld(sc_m(i, j));
-                H[i][i] = sc.ld(sc_m(i, i)) + dadd[i];
+                for (int j = 0; j < i; j++) H[i][j] = sc.ld(moff + sc_m(i, j));
+                H[i][i] = sc.ld(moff + sc_m(i, i)) + dadd[i];
                 x[i] = f[i] + radd[i];
             }
             ldl7(H, dinv);
@@ -742,19 +764,35 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
                     const bool on = (R.D[j] > 0.0) & (((R.below >> j) & 1u) ? x[j] < R.b[j] : x[j] > R.b[j]);
                     actx |= on ? (1u << j) : 0u;
                 }
+                bool con_x = false;
+                double jcx = 0.0;
+                if (R.Dc > 0.0) {
+                    jcx = -R.arefc;
+#pragma unroll
+                    for (int j = 0; j < 7; j++) jcx += sc.ld(SC_JC + j) * x[j];
+                    con_x = jcx < 0.0;
+                }
                 // same set as the one the solve was built from: optimum, next trip is the Euler solve with
                 // the joint-space constraint force D_j (b_j - a_j); otherwise a plain active-set (unit Newton) step
-                const bool ok = actx == act;
+                const bool ok = (actx == act) & (con_x == con_on);
 #pragma unroll
                 for (int j = 0; j < 7; j++) {
                     const bool on = (actx >> j) & 1u;
                     dadd[j] = ok ? prm[CH_HDAMP + j] : (on ? R.D[j] : 0.0);
                     radd[j] = on ? R.D[j] * (R.b[j] - (ok ? x[j] : 0.0)) : 0.0;
                 }
+                if (con_x) {
+                    // contact force -Dc (Jc.a - arefc) Jc at the optimum, or the row's right-hand side Dc arefc Jc
+                    const double lc = ok ? -R.Dc * jcx : R.Dc * R.arefc;
+#pragma unroll
+                    for (int j = 0; j < 7; j++) radd[j] += lc * sc.ld(SC_JC + j);
+                }
                 act = actx;
+                con_on = con_x;
+                moff = (!ok && con_on) ? SC_M2 - SC_M : 0;
                 phase = ok ? 1 : 0;
                 again = 1;
-                if (!ok && ++iters > 5) { slow = true; again = 0; }    // unit steps did not settle (never seen)
+                if (!ok && ++iters > 6) { slow = true; again = 0; }    // unit steps did not settle: robust path
             }
             MJB_OPAQUE(again);
         } while (again);

@@ -210,22 +210,10 @@ class GpuReacherVecEnv:
 
     def _first_obs(self, K):
         # observation at the set state: forward kinematics on the host (FK only, no dynamics)
-        from .model import _rot_axis
-        st = self._state.cpu().numpy()
+        from .model import forward_kinematics
         rows = []
-        tree = self.compiled.tree
-        for s in st:
-            q = s[:7]
-            R = np.eye(3); p = np.zeros(3); j = 0
-            dof = {int(b): k for k, b in enumerate(tree.jnt_body)}
-            Rs, ps = {}, {}
-            for b in range(tree.nb):
-                pa = int(tree.parent[b])
-                Rp = np.eye(3) if pa < 0 else Rs[pa]
-                pp = np.zeros(3) if pa < 0 else ps[pa]
-                ps[b] = pp + Rp @ tree.pos[b]
-                Rs[b] = Rp @ _rot_axis(tree.jnt_axis[dof[b]], q[dof[b]]) if b in dof else Rp
-            hand = ps[tree.hand_body] + Rs[tree.hand_body] @ tree.hand_pos
+        for s in self._state.cpu().numpy():
+            hand = forward_kinematics(self.compiled.tree, s[:7])["hand"]
             rows.append(np.concatenate([s[:14], hand, hand - s[14:17]]))
         rows = np.stack(rows)
         return np.repeat(rows, K // rows.shape[0], axis=0)

@@ -275,6 +275,30 @@ def _rot_axis(axis, q):
     return np.eye(3) + math.sin(q) * K + (1 - math.cos(q)) * (K @ K)
 
 
+def forward_kinematics(tree: "TreeModel", q):
+    """World positions / rotations of every body, the hand site and the contact sphere centre
+    (host-side helper for observations at the set state and for validating start states)."""
+    nb = tree.nb
+    dof = {int(b): j for j, b in enumerate(tree.jnt_body)}
+    R, p = [None] * nb, [None] * nb
+    for b in range(nb):
+        pa = int(tree.parent[b])
+        Rp = np.eye(3) if pa < 0 else R[pa]
+        pp = np.zeros(3) if pa < 0 else p[pa]
+        p[b] = pp + Rp @ tree.pos[b]
+        R[b] = Rp @ _rot_axis(tree.jnt_axis[dof[b]], q[dof[b]]) if b in dof else Rp
+    hand = p[tree.hand_body] + R[tree.hand_body] @ tree.hand_pos
+    sphere = p[tree.con_body] + R[tree.con_body] @ tree.con_pos if tree.con_radius > 0 else None
+    return dict(pos=p, rot=R, hand=hand, sphere=sphere)
+
+
+def table_clearance(tree: "TreeModel", q):
+    """Distance between the end-effector sphere and the table plane (inf without a contact pair)."""
+    if tree.con_radius <= 0:
+        return float("inf")
+    return float(forward_kinematics(tree, q)["sphere"][2] - tree.con_plane_z - tree.con_radius)
+
+
 def tree_mass_matrix(tree: "TreeModel", q: np.ndarray) -> np.ndarray:
     """Dense joint-space inertia (with armature) from geometric Jacobians.
     Host-side helper for the qpos0 constants; NOT used by the rollout."""
