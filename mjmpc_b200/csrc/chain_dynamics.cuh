@@ -184,7 +184,8 @@ template <int MASK> MJB_HD V3 add_m(V3 p, V3 o) {
 // (slot * BLOCK + thread: conflict-free), on the host a plain array.
 // SC_M2 (M + Dc Jc Jc', only while a contact row exists) reuses the link-wrench slots, which are dead once
 // the bias forces are known.
-enum { SC_LF = 0, SC_LN = 18, SC_M = 36, SC_JC = 64, SC_U = 71, SC_NSLOT = 78, SC_M2 = 0 };
+// SC_NZ: landing zone of the asynchronous copy of the NEXT env step's noise row (kernel wrapper only).
+enum { SC_LF = 0, SC_LN = 18, SC_M = 36, SC_JC = 64, SC_U = 71, SC_NZ = 78, SC_NSLOT = 85, SC_M2 = 0 };
 MJB_HD constexpr int sc_m(int i, int j) { return SC_M + i * (i + 1) / 2 + j; }   // lower triangle, i >= j
 
 struct HostScratch {
@@ -329,38 +330,39 @@ MJB_HD void chain_mass_bias(const P& prm, S& sc, const double (&sn)[7], const do
 }
 
 // Reciprocal of a well-scaled positive number (mass-matrix pivots, regularisers): hardware seed
-// (rcp.approx.ftz.f64 = MUFU.RCP64H, ~20 bits) + two Newton steps in FP64 (2^-20 -> 2^-40 -> below
-// 1 ulp).  No denormal / special-case path: 5 straight-line instructions instead of the ~30 (with a
-// slow-path call) of an IEEE division.
+// (rcp.approx.ftz.f64 = MUFU.RCP64H, ~20 bits) refined by one third-order step
+// r = r0 (1 + e + e^2), e = 1 - x r0  (error e^3, below 1 ulp) -- three dependent FP64 operations on the
+// critical path of every pivot instead of the ~30 instructions (with a slow-path call) of an IEEE
+// division.  No denormal / special-case handling: callers pass well-scaled positive values only.
 MJB_HD double rcp_pos(double x) {
 #if defined(__CUDA_ARCH__)
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = r * fma(-x, r, 2.0);
-    r = r * fma(-x, r, 2.0);
-    return r;
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    const double e = fma(-x, r0, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r0, t, r0);
 #else
     return 1.0 / x;
 #endif
 }
 
 // In-place LDL' of the lower triangle of a 7x7 SPD matrix: A[i][j] (i>j) <- L[i][j], dinv[j] = 1/D[j].
+// Right-looking (outer-product) order: as soon as a pivot's reciprocal is known its column is scaled
+// and the trailing block updated with independent FMAs, so the dependency chain from one pivot to the
+// next is reciprocal -> scale -> one FMA (the left-looking form chains up to six FMAs in front of
+// every reciprocal).  With two warps per scheduler this chain length is what the solve costs.
 MJB_HD void ldl7(double (&A)[7][7], double (&dinv)[7]) {
 #pragma unroll
     for (int j = 0; j < 7; j++) {
-        double w[7];
-        double dj = A[j][j];
-#pragma unroll
-        for (int k = 0; k < j; k++) { w[k] = A[j][k] * A[k][k]; dj -= A[j][k] * w[k]; }
-        A[j][j] = dj;
-        const double inv = rcp_pos(dj);
+        const double inv = rcp_pos(A[j][j]);
         dinv[j] = inv;
+        double c[7];
+#pragma unroll
+        for (int i = j + 1; i < 7; i++) { c[i] = A[i][j]; A[i][j] = c[i] * inv; }
 #pragma unroll
         for (int i = j + 1; i < 7; i++) {
-            double t = A[i][j];
 #pragma unroll
-            for (int k = 0; k < j; k++) t -= A[i][k] * w[k];
-            A[i][j] = t * inv;
+            for (int k = j + 1; k <= i; k++) A[i][k] = fma(-A[i][j], c[k], A[i][k]);
         }
     }
 }

@@ -33,16 +33,18 @@ struct Philox {
     }
 };
 
-// two standard normals from four 32-bit words (53-bit uniforms, Box-Muller in FP64)
-__device__ __forceinline__ void normal_pair(const unsigned (&r)[4], double& z0, double& z1) {
-    const unsigned long long a = ((unsigned long long)r[0] << 21) | (r[1] >> 11);
-    const unsigned long long b = ((unsigned long long)r[2] << 21) | (r[3] >> 11);
-    const double u1 = ((double)a + 0.5) * 1.1102230246251565e-16;   // 2^-53, in (0,1)
-    const double u2 = ((double)b + 0.5) * 1.1102230246251565e-16;
-    const double rad = sqrt(-2.0 * log(u1));
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    z0 = rad * c; z1 = rad * s;
+// Four standard normals from the four 32-bit words of one Philox call.  The Gaussian variates are
+// formed in FP32 (Box-Muller on 32-/24-bit uniforms with the SFU log / sincos: 24-bit resolution,
+// |z| <= 6.7 sigma) and promoted to FP64; the covariance transform and the filter below run in FP64.
+// Exploration noise does not need 53-bit variates, and the kernel is instruction-bound on the Philox
+// rounds, so every generated word is used.
+__device__ __forceinline__ void normal_pair32(unsigned a, unsigned b, double& z0, double& z1) {
+    const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;    // (0,1], 2^-32
+    const float u2 = (float)(b >> 8) * 5.9604644775390625e-08f;      // [0,1), 2^-24: exact in FP32
+    const float rad = sqrtf(-2.0f * logf(fminf(u1, 1.0f)));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    z0 = (double)(rad * c); z1 = (double)(rad * s);
 }
 
 template <int D>
@@ -76,12 +78,13 @@ __global__ void __launch_bounds__(128) noise_kernel(mjb_noise_args a) {
     for (int j = 0; j < D; j++) { e1[j] = 0.0; e2[j] = 0.0; }
     const bool zero_seq = a.zero_last && (long long)gk == a.K_global - 1;
     for (int t = 0; t < a.H; t++) {
-        double z[(D + 1) / 2 * 2];
+        double z[(D + 3) / 4 * 4];
 #pragma unroll
-        for (int p = 0; p < (D + 1) / 2; p++) {
+        for (int p = 0; p < (D + 3) / 4; p++) {
             unsigned r[4];
             ph((unsigned)gk, step_ctr, (unsigned)t, tag_hi | (unsigned)p, r);
-            normal_pair(r, z[2 * p], z[2 * p + 1]);
+            normal_pair32(r[0], r[1], z[4 * p], z[4 * p + 1]);
+            normal_pair32(r[2], r[3], z[4 * p + 2], z[4 * p + 3]);
         }
         double e[D];
 #pragma unroll

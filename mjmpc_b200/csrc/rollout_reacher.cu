@@ -27,6 +27,12 @@ struct ConstParams {
 // one shared-memory column per scratch slot: slot * BLOCK + thread (no bank conflicts)
 struct SmemScratch {
     double* base;
+    // asynchronous 8-byte global -> shared copy into a slot (LDGSTS: no register, no stall until waited for)
+    __device__ __forceinline__ void fetch(int slot, const double* g) const {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(base + slot * MJB_ROLLOUT_BLOCK);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g) : "memory");
+    }
+    __device__ __forceinline__ static void fetch_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
     __device__ __forceinline__ double ld(int slot) const { return base[slot * MJB_ROLLOUT_BLOCK]; }
     __device__ __forceinline__ void st(int slot, double v) { base[slot * MJB_ROLLOUT_BLOCK] = v; }
 };
@@ -60,18 +66,35 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, 4) rollout_reacher_kernel(c
     const double* __restrict__ np = a.noise ? a.noise + k * a.noise_sk : nullptr;
     double* __restrict__ ap = a.actions ? a.actions + k * a.act_sk : nullptr;
     double* __restrict__ cp = a.costs + k * a.costs_sk;
+    // The noise row of env step t+1 is copied global -> shared asynchronously while step t is simulated,
+    // so its HBM latency (the only long-latency load of the loop) is never waited for.
+    if (np) {
+        const double* nj = np;
+#pragma unroll
+        for (int j = 0; j < 7; j++) { sc.fetch(SC_NZ + j, nj); nj += a.noise_sj; }
+        np += a.noise_st;
+    }
     for (int t = 0; t < a.H; t++) {
         {
-            const double* nj = np;
             double* aj = ap;
+            double x[7];
+            if (np) SmemScratch::fetch_wait();
 #pragma unroll
             for (int j = 0; j < 7; j++) {
-                double x = __ldg(mean + t * 7 + j);
-                if (np) { x += __ldg(nj); nj += a.noise_sj; }
-                sc.st(SC_U + j, actuator_torque(prm, j, x));   // held over the frame_skip substeps
-                if (ap) { *aj = x; aj += a.act_sj; }
+                x[j] = __ldg(mean + t * 7 + j);
+                if (np) x[j] += sc.ld(SC_NZ + j);
             }
-            if (np) np += a.noise_st;
+            if (np && t + 1 < a.H) {
+                const double* nj = np;
+#pragma unroll
+                for (int j = 0; j < 7; j++) { sc.fetch(SC_NZ + j, nj); nj += a.noise_sj; }
+                np += a.noise_st;
+            }
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                sc.st(SC_U + j, actuator_torque(prm, j, x[j]));   // held over the frame_skip substeps
+                if (ap) { *aj = x[j]; aj += a.act_sj; }
+            }
             if (ap) ap += a.act_st;
         }
         V3 hand = {0.0, 0.0, 0.0};

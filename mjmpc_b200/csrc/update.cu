@@ -94,34 +94,46 @@ __global__ void __launch_bounds__(MJB_RB) traj_cost_kernel(mjb_softmax_args a, G
     const double* __restrict__ un = a.scratch + MJB_MAXH;
     const bool live = k < a.K;
     double S = 0.0, Sc = 0.0, tot0 = INFINITY;
-    for (int t = a.H - 1; t >= 0; t--) {
-        double tot = INFINITY;
-        if (live) {
-            const double c = a.costs[k * a.costs_sk + t * a.costs_st];
-            double ctg;
-            if (G.raw) ctg = c;
-            else { S = __dadd_rn(S, __dmul_rn(G.g[t], c)); ctg = __ddiv_rn(S, G.g[t]); }
-            double ccg = 0.0;
-            if (a.control_cost) {
-                double cc = 0.0;
+    // costs are read 8 steps at a time ahead of the (sequential, reference-ordered) accumulation
+    for (int tb = a.H - 1; tb >= 0; tb -= 8) {
+        double cbuf[8];
 #pragma unroll
-                for (int j = 0; j < D; j++) {
-                    const double m = a.mean[t * D + j];
-                    const double dl = a.actions[k * a.act_sk + t * a.act_st + j * a.act_sj] - m;
-                    cc += 0.5 * un[t * D + j] * (m + 2.0 * dl);
-                }
-                if (G.raw) ccg = cc;
-                else { Sc = __dadd_rn(Sc, __dmul_rn(G.g[t], cc)); ccg = __ddiv_rn(Sc, G.g[t]); }
-            }
-            tot = ctg + a.lam * ccg;
-            if (T > 1) a.total[(long long)t * a.K + k] = tot;
-            tot0 = tot;
+        for (int u = 0; u < 8; u++) {
+            const int t = tb - u;
+            cbuf[u] = (live && t >= 0) ? a.costs[k * a.costs_sk + t * a.costs_st] : 0.0;
         }
-        if (T > 1) {
-            double mn = tot;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            if ((threadIdx.x & 31) == 0 && mn < INFINITY) atomicMin(&menc[t], enc_key(mn));
+        for (int u = 0; u < 8; u++) {
+            const int t = tb - u;
+            if (t < 0) break;
+            double tot = INFINITY;
+            if (live) {
+                const double c = cbuf[u];
+                double ctg;
+                if (G.raw) ctg = c;
+                else { S = __dadd_rn(S, __dmul_rn(G.g[t], c)); ctg = __ddiv_rn(S, G.g[t]); }
+                double ccg = 0.0;
+                if (a.control_cost) {
+                    double cc = 0.0;
+#pragma unroll
+                    for (int j = 0; j < D; j++) {
+                        const double m = a.mean[t * D + j];
+                        const double dl = a.actions[k * a.act_sk + t * a.act_st + j * a.act_sj] - m;
+                        cc += 0.5 * un[t * D + j] * (m + 2.0 * dl);
+                    }
+                    if (G.raw) ccg = cc;
+                    else { Sc = __dadd_rn(Sc, __dmul_rn(G.g[t], cc)); ccg = __ddiv_rn(Sc, G.g[t]); }
+                }
+                tot = ctg + a.lam * ccg;
+                if (T > 1) a.total[(long long)t * a.K + k] = tot;
+                tot0 = tot;
+            }
+            if (T > 1) {
+                double mn = tot;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                if ((threadIdx.x & 31) == 0 && mn < INFINITY) atomicMin(&menc[t], enc_key(mn));
+            }
         }
     }
     if (T == 1) {
@@ -155,31 +167,44 @@ __global__ void __launch_bounds__(MJB_RB) weighted_reduce_kernel(
 #pragma unroll
     for (int j = 0; j < D; j++) { mrow[j] = (CMODE != 0) ? mean[t * D + j] : 0.0; murow[j] = (CMODE != 0 && mu) ? mu[j] : 0.0; }
     const long long k0 = (long long)chunk * MJB_CHUNK;
-    for (int i = threadIdx.x; i < MJB_CHUNK; i += MJB_RB) {
-        const long long k = k0 + i;
-        if (k >= K) break;
-        double w;
-        if (WMODE == 0) w = exp(ninv * trow[k] - xmax);
-        else if (WMODE == 1) w = flags[k] ? 1.0 : 0.0;
-        else w = 1.0;
-        if (WMODE == 1 && w == 0.0) continue;
-        acc[0] += w;
-        double dl[D];
+    // 4 particles per trip with every load issued before the first use: 32 independent loads in flight
+    // per thread (the one-particle-per-trip form sat on the load latency at a quarter of HBM speed)
+    constexpr int U = 4;
+    for (int i0 = threadIdx.x; i0 < MJB_CHUNK; i0 += MJB_RB * U) {
+        double av[U][D], tw[U];
+        bool ok[U];
 #pragma unroll
-        for (int j = 0; j < D; j++) {
-            const double av = actions[k * sk + t * st + j * sj];
-            acc[1 + j] += w * av;
-            dl[j] = av - mrow[j] - murow[j];
+        for (int u = 0; u < U; u++) {
+            const long long k = k0 + i0 + u * MJB_RB;
+            ok[u] = k < K;
+            const long long kk = ok[u] ? k : k0;
+            if (WMODE == 0) tw[u] = trow[kk];
+            else if (WMODE == 1) tw[u] = flags[kk] ? 1.0 : 0.0;
+            else tw[u] = 1.0;
+#pragma unroll
+            for (int j = 0; j < D; j++) av[u][j] = actions[kk * sk + t * st + j * sj];
         }
-        if (CMODE == 1) {
 #pragma unroll
-            for (int j = 0; j < D; j++) acc[1 + D + j] += w * (dl[j] * dl[j]);
-        } else if (CMODE == 2) {
-            int c = 1 + D;
+        for (int u = 0; u < U; u++) {
+            double w = WMODE == 0 ? exp(ninv * tw[u] - xmax) : tw[u];
+            w = ok[u] ? w : 0.0;
+            acc[0] += w;
+            double dl[D];
 #pragma unroll
-            for (int i2 = 0; i2 < D; i2++)
+            for (int j = 0; j < D; j++) {
+                acc[1 + j] += w * av[u][j];
+                dl[j] = av[u][j] - mrow[j] - murow[j];
+            }
+            if (CMODE == 1) {
 #pragma unroll
-                for (int j = 0; j <= i2; j++) acc[c++] += w * (dl[i2] * dl[j]);
+                for (int j = 0; j < D; j++) acc[1 + D + j] += w * (dl[j] * dl[j]);
+            } else if (CMODE == 2) {
+                int c = 1 + D;
+#pragma unroll
+                for (int i2 = 0; i2 < D; i2++)
+#pragma unroll
+                    for (int j = 0; j <= i2; j++) acc[c++] += w * (dl[i2] * dl[j]);
+            }
         }
     }
     __shared__ double sm[MJB_RB / 32][NACC];
