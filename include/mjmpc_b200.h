@@ -155,6 +155,22 @@ int mjb_softmax_combine(const mjb_combine_args* a, void* stream);
 int mjb_softmax_weights(const double* total, int K, const double* stats, int t, double lam, double* w_out,
                         void* stream);
 
+/* Batched MPPI update for many small independent controllers (sweeps, dynamics-randomisation batches:
+ * BASELINE config 5): controller c owns particles [c*K, (c+1)*K) and mean row c; one thread block per
+ * controller does cost-to-go, softmax and the weighted mean of mppi.py:69-111.  No collective. */
+typedef struct {
+    int n_ctrl, K, H, d;         /* K particles per controller (K*8 bytes of shared memory, K <= 4096) */
+    const double* costs; long long costs_sk, costs_st;      /* (n_ctrl*K, H) */
+    const double* actions; long long act_sk, act_st, act_sj; /* (n_ctrl*K, H, d) */
+    double* mean;                /* (n_ctrl, H, d) in/out */
+    const double* cov;           /* (d,d), read when control_cost */
+    const double* gamma_seq;     /* (H,) HOST */
+    double lam, step_size;
+    int control_cost;
+    double* value;               /* out (n_ctrl,): -lam*logsumexp(-total/lam, b=1/K), or NULL */
+} mjb_mppi_batched_args;
+int mjb_mppi_update_batched(const mjb_mppi_batched_args* a, void* stream);
+
 /* ---- K5 elite selection + moments: CEM._update_distribution (mjmpc/control/cem.py:65-86) and
  * RandomShooting._update_distribution (mjmpc/control/random_shooting.py:52-62).
  * mjb_select_elites: the num_elite smallest keys of ctg0 (K_global,), ties broken by LOWER index
@@ -219,6 +235,8 @@ int mjb_particle_sub_mean(const double* x, long long sk, long long st, long long
 #define MJB_BASE_RANDOM 2
 /* mean[:-1] = mean[1:]; last row per base_action; `random_row` (d,) device, used for MJB_BASE_RANDOM */
 int mjb_shift_mean(double* mean, int H, int d, int base_action, const double* random_row, void* stream);
+/* the same for n stacked (H,d) means; random_rows (n,d) */
+int mjb_shift_mean_batched(double* mean, int n, int H, int d, int base_action, const double* random_rows, void* stream);
 /* cov += beta * diag(v)   (v (d,) device, or NULL for the identity) */
 int mjb_cov_add_diag(double* cov, int d, double beta, const double* v, void* stream);
 /* samples[:, :-1] = samples[:, 1:]; samples += delta; last column per base_action */

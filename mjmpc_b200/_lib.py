@@ -144,6 +144,16 @@ class EliteCombineArgs(C.Structure):
     ]
 
 
+class MppiBatchedArgs(C.Structure):
+    _fields_ = [
+        ("n_ctrl", C.c_int), ("K", C.c_int), ("H", C.c_int), ("d", C.c_int),
+        ("costs", C.c_void_p), ("costs_sk", c_ll), ("costs_st", c_ll),
+        ("actions", C.c_void_p), ("act_sk", c_ll), ("act_st", c_ll), ("act_sj", c_ll),
+        ("mean", C.c_void_p), ("cov", C.c_void_p), ("gamma_seq", C.c_void_p),
+        ("lam", C.c_double), ("step_size", C.c_double), ("control_cost", C.c_int), ("value", C.c_void_p),
+    ]
+
+
 COV_NONE, COV_DIAG, COV_FULL = 0, 1, 2
 BASE_ACTIONS = {"null": 0, "repeat": 1, "random": 2}
 
@@ -154,7 +164,7 @@ EXPORTS += [
     "mjb_select_elites", "mjb_argmin", "mjb_elite_scratch_doubles", "mjb_elite_moments1",
     "mjb_elite_moments2", "mjb_elite_combine", "mjb_blend_best",
     "mjb_resample_indices", "mjb_gather_particles", "mjb_particle_mean", "mjb_particle_sub_mean",
-    "mjb_shift_mean", "mjb_cov_add_diag", "mjb_pf_shift",
+    "mjb_shift_mean", "mjb_shift_mean_batched", "mjb_cov_add_diag", "mjb_pf_shift", "mjb_mppi_update_batched",
 ]
 
 

@@ -143,7 +143,7 @@ class Controller(ABC):
         for _ in range(self.n_iters):
             trajectory = self.generate_rollouts(state)
             self._update_distribution(trajectory)
-        action = self._mean[0].clone()
+        action = self._first_action()
         self.num_steps += 1
         if hotstart:
             self._shift()
@@ -154,7 +154,7 @@ class Controller(ABC):
         for _ in range(self.n_iters):
             trajectory = self.generate_rollouts(None)
             self._update_distribution(trajectory)
-        action = self._mean[0].clone()
+        action = self._first_action()
         self._shift()
         return action
 
@@ -241,6 +241,9 @@ class Controller(ABC):
             self.reset()
 
     # ---- helpers ------------------------------------------------------------------------------
+    def _first_action(self):
+        return self._mean[0].clone()
+
     def _to_device(self, x):
         if isinstance(x, torch.Tensor):
             return x.to(device=self.device, dtype=torch.float64)

@@ -62,7 +62,17 @@ class OLGaussianMPC(Controller):
         self.step_size = step_size
         self.filter_coeffs = filter_coeffs
         self.use_zero_control_seq = use_zero_control_seq
-        self._mean = self._to_device(self.init_mean).reshape(self.horizon, self.d_action).contiguous()
+        # batch_size > 1: that many INDEPENDENT controller instances (sweeps, dynamics-randomisation batches)
+        # advance in lock step -- instance b owns particles [b*K, (b+1)*K), mean row b, state row b and (with
+        # an n_workers = batch_size backend) its own model; there is no reduction across instances
+        self.batch_size = int(batch_size)
+        if self.batch_size > 1:
+            if self.shard.world_size != 1:
+                raise ValueError("independent instances are partitioned by the caller, not sharded (no collective)")
+            if use_zero_control_seq:
+                raise NotImplementedError("use_zero_control_seq is not available for batched instances")
+        self._particle_id_offset = 0       # first global Philox particle index of this controller's block
+        self._mean = self._mean_from(self.init_mean)
         self._cov = self._to_device(np.diag(self.init_cov)).contiguous()
         self._init_cov_d = self._to_device(self.init_cov)
         self._buffers = {}
@@ -76,7 +86,19 @@ class OLGaussianMPC(Controller):
     @mean_action.setter
     def mean_action(self, value):
         self.disable_cuda_graph()
-        self._mean = self._to_device(value).reshape(self.horizon, self.d_action).contiguous()
+        self._mean = self._mean_from(value)
+
+    def _mean_from(self, value):
+        m = self._to_device(value)
+        if self.batch_size > 1:
+            if m.numel() == self.horizon * self.d_action:
+                m = m.reshape(1, self.horizon, self.d_action).expand(self.batch_size, -1, -1)
+            return m.reshape(self.batch_size, self.horizon, self.d_action).contiguous().clone()
+        return m.reshape(self.horizon, self.d_action).contiguous().clone()
+
+    def _first_action(self):
+        """mean_action[0] (per instance when batched), device tensor."""
+        return self._mean[:, 0].clone() if self.batch_size > 1 else self._mean[0].clone()
 
     @property
     def cov_action(self):
@@ -90,7 +112,7 @@ class OLGaussianMPC(Controller):
     # ---- sharding ----------------------------------------------------------------------------------
     @property
     def local_particles(self):
-        return self.shard.local_range(self.num_particles)[1]
+        return self.shard.local_range(self.num_particles)[1] * self.batch_size
 
     def _buf(self, name, shape, dtype=torch.float64):
         key = (name, tuple(shape), dtype)
@@ -103,12 +125,14 @@ class OLGaussianMPC(Controller):
     # ---- olgaussian_mpc.py:69-78 ---------------------------------------------------------------------
     def _get_next_action(self, state, mode='mean'):
         if mode == 'mean':
-            next_action = self._mean[0].cpu().numpy().copy()
+            next_action = self._first_action().cpu().numpy()
         elif mode == 'sample':
-            delta = generate_noise(self._cov, self.filter_coeffs, shape=(1, 1), base_seed=self.seed_val,
+            B = self.batch_size
+            delta = generate_noise(self._cov, self.filter_coeffs, shape=(B, 1), base_seed=self.seed_val,
                                    step=123 * self.num_steps, stream_id=control_utils.NOISE_STREAM_ACTION,
                                    device=self.device)
-            next_action = self._mean[0].cpu().numpy().copy() + delta.reshape(self.d_action).cpu().numpy().copy()
+            shape = (B, self.d_action) if B > 1 else (self.d_action,)
+            next_action = self._first_action().cpu().numpy() + delta.reshape(shape).cpu().numpy().copy()
         else:
             raise ValueError('Unidentified sampling mode in get_next_action')
         return next_action
@@ -116,10 +140,12 @@ class OLGaussianMPC(Controller):
     # ---- olgaussian_mpc.py:88-93 ---------------------------------------------------------------------
     def sample_noise(self):
         k0, kl = self.shard.local_range(self.num_particles)
+        kl *= self.batch_size
+        k0 += self._particle_id_offset
         out = self._buf("noise", (self.horizon, self.d_action, kl)).permute(2, 0, 1)
         delta = generate_noise(self._cov, self.filter_coeffs, shape=(kl, self.horizon), base_seed=self.seed_val,
                                step=self._noise_step if self._noise_step is not None else self.num_steps,
-                               k_offset=k0, K_global=self.num_particles,
+                               k_offset=k0, K_global=self._particle_id_offset + self.num_particles * self.batch_size,
                                zero_last_mean=self._mean if self.use_zero_control_seq else None,
                                out=out, device=self.device)
         return delta
@@ -127,6 +153,8 @@ class OLGaussianMPC(Controller):
     # ---- olgaussian_mpc.py:95-114 --------------------------------------------------------------------
     def generate_rollouts(self, state):
         if state is not None:             # None: the backend already holds the (device-resident) state
+            if self.batch_size > 1 and isinstance(state, dict):
+                state = [state] * self.batch_size          # one state for every instance
             self._set_sim_state_fn(copy.deepcopy(state))
         delta = self.sample_noise()       # use_zero_control_seq is applied inside the kernel
         trajectories = self._rollout_fn(self.local_particles, self.horizon, self._mean, delta, mode="open_loop")
@@ -137,11 +165,17 @@ class OLGaussianMPC(Controller):
         if self.base_action not in _lib.BASE_ACTIONS:
             raise NotImplementedError("invalid option for base action during shift")
         rnd = None
+        B = self.batch_size
         if self.base_action == 'random':
             # np.random.normal(0, self.init_cov, d): the reference passes the variances as std devs
-            rnd = generate_noise(torch.diag(self._init_cov_d ** 2), [1.0, 0.0, 0.0], shape=(1, 1),
+            rnd = generate_noise(torch.diag(self._init_cov_d ** 2), [1.0, 0.0, 0.0], shape=(B, 1),
                                  base_seed=self.seed_val, step=self.num_steps,
-                                 stream_id=control_utils.NOISE_STREAM_BASE, device=self.device).reshape(-1).contiguous()
+                                 stream_id=control_utils.NOISE_STREAM_BASE, device=self.device).reshape(B, -1).contiguous()
+        if B > 1:
+            _lib.check(_lib.lib().mjb_shift_mean_batched(_lib.ptr(self._mean), C.c_int(B), C.c_int(self.horizon),
+                                                         C.c_int(self.d_action), C.c_int(_lib.BASE_ACTIONS[self.base_action]),
+                                                         _lib.ptr(rnd), _lib.stream_ptr()))
+            return
         _lib.check(_lib.lib().mjb_shift_mean(_lib.ptr(self._mean), C.c_int(self.horizon), C.c_int(self.d_action),
                                              C.c_int(_lib.BASE_ACTIONS[self.base_action]), _lib.ptr(rnd),
                                              _lib.stream_ptr()))
@@ -150,7 +184,7 @@ class OLGaussianMPC(Controller):
     def reset(self):
         self.disable_cuda_graph()
         self.num_steps = 0
-        self._mean = torch.zeros((self.horizon, self.d_action), dtype=torch.float64, device=self.device)
+        self._mean = self._mean_from(np.zeros((self.horizon, self.d_action)))
         self._cov = self._to_device(np.diag(self.init_cov)).contiguous()
         self.gamma_seq = np.cumprod([1.0] + [self.gamma] * (self.horizon - 1)).reshape(1, self.horizon)
         self._buffers = {}
@@ -172,6 +206,8 @@ class OLGaussianMPC(Controller):
                         apply=True):
         """Phase 1 (local partials) -> all-gather over shards -> phase 2 (combine, smooth).
         Returns the (2+2T,) stats tensor: value, global min, normalisers, minima."""
+        if self.batch_size > 1:
+            raise NotImplementedError("batched instances are implemented for MPPI without time-based weights")
         L = _lib.lib()
         kl, H, d = self.local_particles, self.horizon, self.d_action
         T = H if time_based else 1

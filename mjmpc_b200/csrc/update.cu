@@ -300,6 +300,101 @@ __global__ void softmax_weights_kernel(const double* __restrict__ total, int K, 
     w[k] = exp(ninv * total[(long long)t * K + k] - ninv * m) / S;
 }
 
+// ------------------------------------------------------------------------------ batched small MPPI
+// one block per controller; sh[0..K) holds the trajectory costs, then the un-normalised weights
+template <int D>
+__global__ void __launch_bounds__(256) mppi_batched_kernel(mjb_mppi_batched_args a, GammaSeq G) {
+    extern __shared__ double sh[];
+    __shared__ double un[MJB_MAXH * MJB_MAXD];
+    __shared__ double Ainv[MJB_MAXD][2 * MJB_MAXD];
+    __shared__ double red[256];
+    const int c = blockIdx.x, K = a.K, H = a.H;
+    double* mean = a.mean + (long long)c * H * D;
+    const long long kbase = (long long)c * K;
+    if (a.control_cost) {
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < D; i++)
+                for (int j = 0; j < D; j++) { Ainv[i][j] = a.cov[i * D + j]; Ainv[i][D + j] = i == j ? 1.0 : 0.0; }
+            for (int col = 0; col < D; col++) {
+                int p = col;
+                for (int r = col + 1; r < D; r++) if (fabs(Ainv[r][col]) > fabs(Ainv[p][col])) p = r;
+                if (p != col) for (int j = 0; j < 2 * D; j++) { const double t = Ainv[col][j]; Ainv[col][j] = Ainv[p][j]; Ainv[p][j] = t; }
+                const double inv = 1.0 / Ainv[col][col];
+                for (int j = 0; j < 2 * D; j++) Ainv[col][j] *= inv;
+                for (int r = 0; r < D; r++) if (r != col) {
+                    const double f = Ainv[r][col];
+                    for (int j = 0; j < 2 * D; j++) Ainv[r][j] -= f * Ainv[col][j];
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < H * D; i += blockDim.x) {
+            const int t = i / D, j = i % D;
+            double s = 0.0;
+            for (int l = 0; l < D; l++) s += mean[t * D + l] * Ainv[l][D + j];
+            un[i] = s;
+        }
+        __syncthreads();
+    }
+    // trajectory cost per particle (reference order), block minimum
+    double mn = INFINITY;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const long long gk = kbase + k;
+        double S = 0.0, Sc = 0.0, ctg = 0.0, ccg = 0.0;
+        for (int t = H - 1; t >= 0; t--) {
+            const double cst = a.costs[gk * a.costs_sk + t * a.costs_st];
+            if (G.raw) ctg = cst;
+            else { S = __dadd_rn(S, __dmul_rn(G.g[t], cst)); ctg = __ddiv_rn(S, G.g[t]); }
+            if (a.control_cost) {
+                double cc = 0.0;
+                for (int j = 0; j < D; j++) {
+                    const double m = mean[t * D + j];
+                    const double dl = a.actions[gk * a.act_sk + t * a.act_st + j * a.act_sj] - m;
+                    cc += 0.5 * un[t * D + j] * (m + 2.0 * dl);
+                }
+                if (G.raw) ccg = cc;
+                else { Sc = __dadd_rn(Sc, __dmul_rn(G.g[t], cc)); ccg = __ddiv_rn(Sc, G.g[t]); }
+            }
+        }
+        const double tot = ctg + a.lam * ccg;
+        sh[k] = tot;
+        mn = fmin(mn, tot);
+    }
+    red[threadIdx.x] = mn;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmin(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+    const double ninv = -1.0 / a.lam, xmax = ninv * red[0];
+    __syncthreads();
+    double ws = 0.0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) { const double w = exp(ninv * sh[k] - xmax); sh[k] = w; ws += w; }
+    red[threadIdx.x] = ws;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s]; __syncthreads(); }
+    const double Ssum = red[0];
+    // weighted mean: one (t,j) entry per thread, particles in index order
+    for (int i = threadIdx.x; i < H * D; i += blockDim.x) {
+        const int t = i / D, j = i % D;
+        double s = 0.0;
+        for (int k = 0; k < K; k++) s += sh[k] * a.actions[(kbase + k) * a.act_sk + t * a.act_st + j * a.act_sj];
+        mean[i] = (1.0 - a.step_size) * mean[i] + a.step_size * (s / Ssum);
+    }
+    if (a.value && threadIdx.x == 0) a.value[c] = -a.lam * (xmax + log(Ssum / (double)K));
+}
+
+__global__ void shift_mean_batched_kernel(double* mean, int n, int H, int d, int base, const double* rnd) {
+    // grid.x = controller; rows move up by one, so walk forward in t
+    double* m = mean + (long long)blockIdx.x * H * d;
+    for (int j = threadIdx.x; j < d; j += blockDim.x) {
+        const double last = m[(H - 1) * d + j];
+        for (int t = 0; t < H - 1; t++) m[t * d + j] = m[(t + 1) * d + j];
+        double v;
+        if (base == MJB_BASE_NULL) v = 0.0;
+        else if (base == MJB_BASE_REPEAT) v = last;
+        else v = rnd[(long long)blockIdx.x * d + j];
+        m[(H - 1) * d + j] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------ elite selection
 // 8-pass MSB radix select on order-preserving keys, one block; ties at the threshold resolved by index.
 __global__ void __launch_bounds__(1024) select_elites_kernel(const double* __restrict__ v, long long K, long long E,
@@ -790,6 +885,36 @@ extern "C" int mjb_particle_sub_mean(const double* x, long long sk, long long st
                                      int H, int d, double* out, long long osk, long long ost, long long osj, void* stream) {
     MJB_REQUIRE(x && mean && out && K >= 1 && H >= 1 && d >= 1, "mjb_particle_sub_mean: bad argument");
     sub_mean_kernel<<<dim3((K + 255) / 256, H * d), 256, 0, (cudaStream_t)stream>>>(x, sk, st, sj, mean, K, H, d, out, osk, ost, osj);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_mppi_update_batched(const mjb_mppi_batched_args* a, void* stream) {
+    MJB_REQUIRE(a && a->costs && a->actions && a->mean && a->gamma_seq, "mjb_mppi_update_batched: null pointer");
+    MJB_REQUIRE(a->n_ctrl >= 1 && a->K >= 1 && a->K <= 4096 && a->H >= 1, "mjb_mppi_update_batched: bad shape (K per controller must be <= 4096)");
+    MJB_REQUIRE(a->d >= 1 && a->d <= MJB_MAXD, "d_action=%d not in 1..%d", a->d, MJB_MAXD);
+    MJB_REQUIRE(a->lam > 0.0, "lam must be positive");
+    MJB_REQUIRE(!a->control_cost || a->cov, "control cost needs cov");
+    GammaSeq G;
+    int rc = load_gamma(G, a->gamma_seq, a->H);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = sizeof(double) * a->K;
+    switch (a->d) {
+#define MJB_CASE(D) case D: mppi_batched_kernel<D><<<a->n_ctrl, 256, smem, s>>>(*a, G); break;
+        MJB_CASE(1) MJB_CASE(2) MJB_CASE(3) MJB_CASE(4) MJB_CASE(5) MJB_CASE(6) MJB_CASE(7) MJB_CASE(8)
+#undef MJB_CASE
+    }
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_shift_mean_batched(double* mean, int n, int H, int d, int base_action, const double* random_rows, void* stream) {
+    MJB_REQUIRE(mean && n >= 1 && H >= 1 && d >= 1, "mjb_shift_mean_batched: bad argument");
+    if (base_action < 0 || base_action > 2)
+        return set_error(MJB_ENOTIMPL, "invalid option for base action during shift");
+    MJB_REQUIRE(base_action != MJB_BASE_RANDOM || random_rows, "base_action 'random' needs random rows");
+    shift_mean_batched_kernel<<<n, 32, 0, (cudaStream_t)stream>>>(mean, n, H, d, base_action, random_rows);
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;
 }

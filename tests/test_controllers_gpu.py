@@ -345,3 +345,38 @@ def test_full_optimize_matches_numpy_oracle_end_to_end(compiled_model, oracle_mo
         np.testing.assert_allclose(action, want_action, rtol=1e-7, atol=1e-10)
         np.testing.assert_allclose(c.mean_action, mean, rtol=1e-7, atol=1e-10)
     env.close()
+
+
+def test_batched_independent_instances_match_single_controllers(compiled_model):
+    """BASELINE config 5 in miniature: batch_size independent MPPI instances (shipped sizes K=32, H=16), each
+    with its own start state and its own randomised model, in one launch -- against separate controllers."""
+    from conftest import synthetic_state
+    from mjmpc_b200.control import MPPI
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    B, K, H = 12, 32, 16
+    rand = dict(body_mass={"r_forearm_link": [0.3, 0.0], "r_wrist_roll_link": [0.3, 0.0]},
+                dof_damping={"r_elbow_flex_joint": [0.2, 0.1]})
+    kw = dict(horizon=H, init_cov=1.0, base_action='null', lam=0.2, num_particles=K, step_size=0.9, alpha=0, gamma=0.98,
+              n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=77, **_common())
+    states = [[synthetic_state(compiled_model, 100 * s + b) for b in range(B)] for s in range(3)]
+    env = GpuReacherVecEnv(compiled_model, n_workers=B)
+    env.randomize_dynamics(rand, base_seed=3)
+    cb = MPPI(batch_size=B, **kw)
+    cb.set_sim_state_fn = env.set_env_state
+    cb.rollout_fn = env.rollout_fn
+    acts_b = np.stack([cb.optimize(st)[0] for st in states])                  # (steps, B, 7)
+    assert acts_b.shape == (3, B, 7)
+    vals = cb._calc_val(cb.generate_rollouts(states[0]))
+    assert vals.shape == (B,) and np.all(np.isfinite(vals))
+    for b in (0, 5, B - 1):
+        single_env = GpuReacherVecEnv(env._worker_models[b], n_workers=1)
+        c = MPPI(batch_size=1, **kw)
+        c._particle_id_offset = b * K                                         # same Philox block as instance b
+        c.set_sim_state_fn = single_env.set_env_state
+        c.rollout_fn = single_env.rollout_fn
+        acts = np.stack([c.optimize(st[b])[0] for st in states])
+        np.testing.assert_allclose(acts_b[:, b], acts, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(cb.mean_action[b], c.mean_action, rtol=1e-9, atol=1e-12)
+        single_env.close()
+    assert np.abs(acts_b[:, 0] - acts_b[:, 1]).max() > 1e-3                     # instances really differ
+    env.close()
