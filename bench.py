@@ -302,6 +302,17 @@ def run_own(args):
         dist.destroy_process_group()
 
 
+def _watchdog(seconds):
+    """A hung collective must not hang the driver: abort the process group after `seconds`."""
+    def fire():
+        sys.stderr.write("bench.py: watchdog fired after %d s, aborting\n" % seconds)
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -309,10 +320,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--watchdog", type=int, default=600, help="abort if the whole run exceeds this many seconds")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    _watchdog(args.watchdog)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -159,7 +159,10 @@ class Controller(ABC):
         return action
 
     def _graphable(self):
-        return self.sample_mode == 'mean' and getattr(self, "base_action", "null") != 'random'
+        # sharded controllers launch eagerly: a collective inside a captured graph needs every rank to
+        # capture and replay in lock step with the process group's watchdog, which is not validated here
+        return (self.sample_mode == 'mean' and getattr(self, "base_action", "null") != 'random'
+                and self.shard.world_size == 1)
 
     def enable_cuda_graph(self, state):
         """Capture one whole MPC step (noise, rollout, update, shift; n_iters included) into a CUDA
