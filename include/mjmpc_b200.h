@@ -151,6 +151,13 @@ typedef struct {
                                     [2..2+T) = normaliser S[t] w.r.t. the global min, [2+T..2+2T) = global min m[t] */
 } mjb_combine_args;
 int mjb_softmax_combine(const mjb_combine_args* a, void* stream);
+/* Fused multi-GPU variant of the combine: pushes `local_partial` (P doubles) into every peer's symmetric
+ * buffer over NVLink peer memory, waits for all peers' sequence flags, then combines in rank order (one
+ * kernel, no NCCL call).  peer_bufs_dev: DEVICE array of n_shards pointers to the peers' buffers, each
+ * 2*n_shards*P doubles followed by 2*n_shards 64-bit flags (zero-initialised); a->partials is ignored;
+ * seq = 1, 2, 3, ... must advance identically on every rank. */
+int mjb_softmax_exchange_combine(const mjb_combine_args* a, const double* local_partial, void* const* peer_bufs_dev,
+                                 int rank, unsigned long long seq, void* stream);
 /* normalised weights w_k = exp(-(total_k - m)/lam)/S for one t-row of `total`; m,S from stats. */
 int mjb_softmax_weights(const double* total, int K, const double* stats, int t, double lam, double* w_out,
                         void* stream);

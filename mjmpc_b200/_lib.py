@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmjmpc_b200.so")
+LIB_PATH = os.environ.get("MJB_LIB_PATH") or os.path.join(_HERE, "libmjmpc_b200.so")   # override: kernel-variant experiments
 
 MJB_OK, MJB_EINVAL, MJB_ECUDA, MJB_ENOTIMPL = 0, 1, 2, 3
 MODEL_NPARAM = 167
@@ -160,7 +160,7 @@ BASE_ACTIONS = {"null": 0, "repeat": 1, "random": 2}
 EXPORTS += [
     "mjb_rollout_pendulum", "mjb_generate_noise", "mjb_cost_to_go",
     "mjb_softmax_scratch_doubles", "mjb_softmax_partial_doubles", "mjb_softmax_partials",
-    "mjb_softmax_combine", "mjb_softmax_weights",
+    "mjb_softmax_combine", "mjb_softmax_exchange_combine", "mjb_softmax_weights",
     "mjb_select_elites", "mjb_argmin", "mjb_elite_scratch_doubles", "mjb_elite_moments1",
     "mjb_elite_moments2", "mjb_elite_combine", "mjb_blend_best",
     "mjb_resample_indices", "mjb_gather_particles", "mjb_particle_mean", "mjb_particle_sub_mean",

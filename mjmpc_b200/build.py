@@ -33,17 +33,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:
+    """out / defines: build a kernel variant next to the default library (experiments; see tools/)."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    target = out or LIB
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + sources()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import copy
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -227,19 +228,48 @@ class OLGaussianMPC(Controller):
         partials = self._buf("sm_partials", (P,))
         a.total, a.scratch, a.partials = total.data_ptr(), scratch.data_ptr(), partials.data_ptr()
         _lib.check(L.mjb_softmax_partials(C.byref(a), _lib.stream_ptr()))
-        allp = self.shard.all_gather(partials)
         stats = self._buf("sm_stats", (2 + 2 * T,))
         c = _lib.CombineArgs()
         c.H, c.d, c.n_shards, c.K_global = H, d, self.shard.world_size, self.num_particles
-        c.partials = allp.data_ptr()
         c.lam, c.step_size = float(lam), float(self.step_size)
         c.time_based, c.cov_mode = int(time_based), int(cov_mode)
         c.mean = self._mean.data_ptr() if apply else None
         c.cov = self._cov.data_ptr() if (apply and cov_mode != _lib.COV_NONE) else None
         c.stats = stats.data_ptr()
-        _lib.check(L.mjb_softmax_combine(C.byref(c), _lib.stream_ptr()))
+        px = self._peer_exchange(P)
+        if px is not None:
+            # fused: P2P stores into every peer's buffer + flag wait + rank-ordered combine in ONE kernel
+            _lib.check(L.mjb_softmax_exchange_combine(C.byref(c), _lib.ptr(partials), C.c_void_p(px.peer_ptrs_dev),
+                                                      C.c_int(self.shard.rank), C.c_ulonglong(px.next_seq()),
+                                                      _lib.stream_ptr()))
+        else:
+            allp = self.shard.all_gather(partials)
+            c.partials = allp.data_ptr()
+            _lib.check(L.mjb_softmax_combine(C.byref(c), _lib.stream_ptr()))
         self._last_total = total
         return stats
+
+    def _peer_exchange(self, P):
+        """Symmetric-memory exchange buffer for partial vectors of P doubles (None: single GPU, disabled
+        with MJB_P2P=0, or symmetric memory unavailable -> NCCL all-gather).  Creation is collective and
+        happens at the same call on every rank."""
+        if self.shard.world_size == 1 or os.environ.get("MJB_P2P", "1") == "0":
+            return None
+        cache = self.__dict__.setdefault("_px", {})
+        if P not in cache:
+            px = None
+            try:
+                from ..utils.shard import PeerExchange
+                px = PeerExchange(self.shard, P, self.device)
+            except Exception as e:            # pragma: no cover - depends on the box
+                import warnings
+                warnings.warn("NVLink peer exchange unavailable (%r); using NCCL all-gather" % (e,))
+            # all ranks must take the same path: agree on the minimum
+            ok = torch.tensor([1.0 if px is not None else 0.0], dtype=torch.float64, device=self.device)
+            if self.shard.all_gather(ok).min().item() < 1.0:
+                px = None
+            cache[P] = px
+        return cache[P]
 
     def _ctg0(self, costs):
         """cost_to_go(costs, gamma_seq)[:, 0] for the local particles (device, contiguous)."""

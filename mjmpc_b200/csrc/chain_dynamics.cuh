@@ -184,8 +184,14 @@ template <int MASK> MJB_HD V3 add_m(V3 p, V3 o) {
 // (slot * BLOCK + thread: conflict-free), on the host a plain array.
 // SC_M2 (M + Dc Jc Jc', only while a contact row exists) reuses the link-wrench slots, which are dead once
 // the bias forces are known.
-// SC_NZ: landing zone of the asynchronous copy of the NEXT env step's noise row (kernel wrapper only).
-enum { SC_LF = 0, SC_LN = 18, SC_M = 36, SC_JC = 64, SC_U = 71, SC_NZ = 78, SC_NSLOT = 85, SC_M2 = 0 };
+// SC_JC (contact Jacobian, only while a contact row exists) sits in the tail of the link-wrench region
+// that M2 leaves free.  SC_NZ: landing zone of the asynchronous copy of the NEXT env step's noise row
+// (kernel wrapper only; compiled out with MJB_NO_PREFETCH to fit one more block per SM).
+#ifdef MJB_NO_PREFETCH
+enum { SC_LF = 0, SC_LN = 18, SC_M = 36, SC_JC = 28, SC_U = 64, SC_NZ = 71, SC_NSLOT = 71, SC_M2 = 0 };
+#else
+enum { SC_LF = 0, SC_LN = 18, SC_M = 36, SC_JC = 28, SC_U = 64, SC_NZ = 71, SC_NSLOT = 78, SC_M2 = 0 };
+#endif
 MJB_HD constexpr int sc_m(int i, int j) { return SC_M + i * (i + 1) / 2 + j; }   // lower triangle, i >= j
 
 struct HostScratch {

@@ -24,6 +24,9 @@ struct ConstParams {
 };
 
 #define MJB_ROLLOUT_BLOCK 64
+#ifndef MJB_OCC
+#define MJB_OCC 4          // resident blocks per SM the register allocation is bounded for
+#endif
 // one shared-memory column per scratch slot: slot * BLOCK + thread (no bank conflicts)
 struct SmemScratch {
     double* base;
@@ -42,7 +45,7 @@ struct SmemScratch {
 // EXTRA: also write the per-step state trajectory / observations / constraint counters (tests, adaptors
 // that hand observations back); the production instantiation carries none of that code.
 template <class T, class P, bool EXTRA>
-__global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, 4) rollout_reacher_kernel(const double* __restrict__ params, int n_inst,
+__global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_kernel(const double* __restrict__ params, int n_inst,
                                                                 mjb_rollout_args a) {
     __shared__ double smem[SC_NSLOT * MJB_ROLLOUT_BLOCK];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,16 +71,19 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, 4) rollout_reacher_kernel(c
     double* __restrict__ cp = a.costs + k * a.costs_sk;
     // The noise row of env step t+1 is copied global -> shared asynchronously while step t is simulated,
     // so its HBM latency (the only long-latency load of the loop) is never waited for.
+#ifndef MJB_NO_PREFETCH
     if (np) {
         const double* nj = np;
 #pragma unroll
         for (int j = 0; j < 7; j++) { sc.fetch(SC_NZ + j, nj); nj += a.noise_sj; }
         np += a.noise_st;
     }
+#endif
     for (int t = 0; t < a.H; t++) {
         {
             double* aj = ap;
             double x[7];
+#ifndef MJB_NO_PREFETCH
             if (np) SmemScratch::fetch_wait();
 #pragma unroll
             for (int j = 0; j < 7; j++) {
@@ -90,6 +96,17 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, 4) rollout_reacher_kernel(c
                 for (int j = 0; j < 7; j++) { sc.fetch(SC_NZ + j, nj); nj += a.noise_sj; }
                 np += a.noise_st;
             }
+#else
+            {
+                const double* nj = np;
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    x[j] = __ldg(mean + t * 7 + j);
+                    if (np) { x[j] += __ldg(nj); nj += a.noise_sj; }
+                }
+                if (np) np += a.noise_st;
+            }
+#endif
 #pragma unroll
             for (int j = 0; j < 7; j++) {
                 sc.st(SC_U + j, actuator_torque(prm, j, x[j]));   // held over the frame_skip substeps

@@ -237,7 +237,7 @@ __global__ void decode_min_kernel(const unsigned long long* menc, int T, double*
 }
 
 // ------------------------------------------------------------------------------ softmax phase 2
-__global__ void softmax_combine_kernel(mjb_combine_args a) {
+__device__ void softmax_combine_body(const mjb_combine_args& a) {
     const int H = a.H, d = a.d, T = a.time_based ? H : 1;
     const int nc = a.cov_mode == MJB_COV_NONE ? 0 : (a.cov_mode == MJB_COV_DIAG ? d : d * (d + 1) / 2);
     const int NACC = 1 + d + nc, P = T + H * NACC;
@@ -290,6 +290,42 @@ __global__ void softmax_combine_kernel(mjb_combine_args a) {
         // minima for the other rows of a time-based weighting live after the normalisers
         for (int tr = threadIdx.x; tr < T; tr += blockDim.x) a.stats[2 + T + tr] = mstar[tr];
     }
+}
+
+__global__ void softmax_combine_kernel(mjb_combine_args a) { softmax_combine_body(a); }
+
+// Fused exchange + combine over NVLink peer memory (one block per GPU).  Every rank owns a symmetric
+// buffer [2][world][P] doubles + [2][world] sequence flags, mapped into all peers.  The kernel
+//   1. stores its partial vector straight into slot [parity][rank] of EVERY peer's buffer (P2P stores),
+//   2. publishes its sequence number in every peer's flag word (system-scope fence before it),
+//   3. spins until all `world` flags of its own buffer carry this sequence number,
+//   4. combines the `world` partial vectors in rank order -- the same code as the single-GPU combine --
+// so the 2 KB exchange costs one NVLink round trip inside the reduction epilogue instead of a separate
+// NCCL launch.  Two parity halves: a rank can be at most one exchange ahead of the slowest peer.
+__global__ void __launch_bounds__(256) softmax_exchange_combine_kernel(mjb_combine_args a, const double* __restrict__ local,
+                                                                        int P, void* const* __restrict__ peers, int rank,
+                                                                        unsigned long long seq) {
+    const int world = a.n_shards, parity = (int)(seq & 1ull);
+    for (int r = 0; r < world; r++) {
+        double* dst = (double*)peers[r] + ((long long)parity * world + rank) * P;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) dst[i] = local[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        volatile unsigned long long* flag =
+            (volatile unsigned long long*)((double*)peers[threadIdx.x] + 2ll * world * P) + parity * world + rank;
+        *flag = seq;
+    }
+    double* mine = (double*)peers[rank];
+    if (threadIdx.x < world) {
+        volatile unsigned long long* flag = (volatile unsigned long long*)(mine + 2ll * world * P) + parity * world + threadIdx.x;
+        while (*flag < seq) { __nanosleep(64); }
+    }
+    __threadfence_system();
+    __syncthreads();
+    a.partials = mine + (long long)parity * world * P;
+    softmax_combine_body(a);
 }
 
 __global__ void softmax_weights_kernel(const double* __restrict__ total, int K, const double* __restrict__ stats, int T,
@@ -915,6 +951,18 @@ extern "C" int mjb_shift_mean_batched(double* mean, int n, int H, int d, int bas
         return set_error(MJB_ENOTIMPL, "invalid option for base action during shift");
     MJB_REQUIRE(base_action != MJB_BASE_RANDOM || random_rows, "base_action 'random' needs random rows");
     shift_mean_batched_kernel<<<n, 32, 0, (cudaStream_t)stream>>>(mean, n, H, d, base_action, random_rows);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_softmax_exchange_combine(const mjb_combine_args* a, const double* local_partial, void* const* peer_bufs_dev,
+                                            int rank, unsigned long long seq, void* stream) {
+    MJB_REQUIRE(a && local_partial && peer_bufs_dev && (a->mean || a->stats), "mjb_softmax_exchange_combine: null pointer");
+    MJB_REQUIRE(a->H >= 1 && a->H <= MJB_MAXH && a->d >= 1 && a->d <= MJB_MAXD && a->n_shards >= 1 && a->n_shards <= 64,
+                "mjb_softmax_exchange_combine: bad shape");
+    MJB_REQUIRE(rank >= 0 && rank < a->n_shards && seq >= 1, "mjb_softmax_exchange_combine: bad rank / sequence number");
+    const int P = mjb_softmax_partial_doubles(a->H, a->d, a->time_based, a->cov_mode);
+    softmax_exchange_combine_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*a, local_partial, P, peer_bufs_dev, rank, seq);
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;
 }

@@ -43,4 +43,30 @@ class ShardContext:
         return flat.reshape((self.world_size,) + tuple(t.shape))
 
 
+class PeerExchange:
+    """Symmetric NVLink peer-memory buffer for the fused exchange+combine kernel
+    (``mjb_softmax_exchange_combine``): ``[2][world][P]`` doubles + ``[2][world]`` sequence flags on every
+    rank, mapped into every peer through ``torch.distributed._symmetric_memory`` (plumbing only -- the
+    loads / stores over NVLink are issued by our kernel).  Construction is collective."""
+
+    def __init__(self, shard: "ShardContext", P: int, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.P, self.world, self.rank = int(P), shard.world_size, shard.rank
+        n = 2 * self.world * self.P + 2 * self.world
+        self.buf = symm_mem.empty(n, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        group = shard.group if shard.group is not None else dist.group.WORLD
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        ptrs = self.handle.buffer_ptrs_dev
+        self.peer_ptrs_dev = int(ptrs)                       # device array of `world` buffer pointers
+        self.seq = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)                            # every rank has zeroed its flags before first use
+
+    def next_seq(self) -> int:
+        self.seq += 1
+        return self.seq
+
+
 SINGLE = ShardContext()

@@ -9,7 +9,8 @@ from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
 from mjmpc_b200.envs.model import compile_model, reacher7dof_spec
 
 L = _lib.lib()
-for bps, iters in [(2, 2048), (4, 2048), (8, 2048)]:
+KS = [int(x) for x in os.environ.get("PROBE_K", "8192,65536,262144").split(",")]
+for bps, iters in ([(8, 2048)] if "PROBE_K" not in os.environ else []):
     tf = C.c_double(); ms = C.c_double()
     _lib.check(L.mjb_fp64_peak(0, bps, iters, C.byref(tf), C.byref(ms)))
     print("fp64 peak blocks/SM=%d: %.2f TFLOP/s (%.3f ms)" % (bps, tf.value, ms.value))
@@ -21,7 +22,7 @@ lo, hi = cm.tree.jnt_range[:, 0], cm.tree.jnt_range[:, 1]
 st = dict(qp=rng.uniform(lo + 0.1 * (hi - lo), hi - 0.1 * (hi - lo)), qv=rng.normal(0, .5, 7), qa=np.zeros(7),
           target_pos=rng.uniform([-.3, -.2, -.25], [.3, .2, .25]), timestep=0)
 env.set_env_state(st)
-for K in (8192, 65536, 262144):
+for K in KS:
     H = 32
     g = torch.Generator(device="cuda"); g.manual_seed(0)
     noise = torch.randn((H, 7, K), dtype=torch.float64, device="cuda", generator=g)
@@ -30,6 +31,8 @@ for K in (8192, 65536, 262144):
     noise = noise.permute(2, 0, 1)
     mean = torch.zeros(H, 7, dtype=torch.float64, device="cuda")
     out = env.rollout_device(K, H, mean, noise, want_ncon=True)
+    ncon = out['ncon'].double().mean().item() / (2 * H)
+    out = env.rollout_device(K, H, mean, noise)      # production instantiation (no EXTRA outputs)
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     ts = []
@@ -39,4 +42,4 @@ for K in (8192, 65536, 262144):
     ms = min(ts)
     ps = K * H / (ms * 1e-3)
     print("K=%d H=%d rollout %.3f ms  %.3e particle-steps/s  alg %.2f TFLOP/s  ncon frac %.3f"
-          % (K, H, ms, ps, ps * 5340 / 1e12, out["ncon"].double().mean().item() / (2 * H)))
+          % (K, H, ms, ps, ps * 5340 / 1e12, ncon))
