@@ -264,6 +264,19 @@ def run_own(args):
     tf, pms = C.c_double(), C.c_double()
     _lib.check(L.mjb_fp64_peak(local_rank, 8, 2048, C.byref(tf), C.byref(pms)))
     achieved = kl * HORIZON * FLOP_PER_PARTICLE_STEP / (k1_ms * 1e-3) / 1e12
+    # DRAM traffic of that kernel from the committed `ncu --set full` capture (per launch, K=65536, one GPU)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            tj = json.load(f)
+        if world == 1:
+            traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+    except Exception:
+        pass
+    px = getattr(ctrl, "_px", {})
+    exchange = ("none (single GPU)" if world == 1 else
+                "nvlink peer-memory exchange fused into the combine kernel" if any(v is not None for v in px.values())
+                else "nccl all_gather + combine kernel")
 
     if rank != 0:
         if world > 1:
@@ -288,9 +301,10 @@ def run_own(args):
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "ms_per_step": e2e_s / args.steps * 1e3,
                 "h2d_bytes_per_step": 17 * 8, "d2h_bytes_per_step": 7 * 8,
                 "api": "MPCPolicy.get_action(state_dict) -> (action ndarray, value)"},
-        "gpu_launches": KERNELS_PER_STEP * args.steps, "cuda_graph": bool(graphed),
+        "gpu_launches": KERNELS_PER_STEP * args.steps, "cuda_graph": bool(graphed), "exchange": exchange,
         "roofline": {"kernel": "rollout_reacher_kernel (K1)", "bound": "fp64", "achieved": achieved, "peak": tf.value,
-                     "unit": "TFLOP/s", "frac": achieved / tf.value, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / tf.value, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_hbm_bytes": kl * HORIZON * 120,
                      "ms_per_launch": k1_ms, "particles_per_launch": kl,
                      "flop_per_particle_step": FLOP_PER_PARTICLE_STEP,
                      "peak_source": "mjb_fp64_peak microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)"},

@@ -70,6 +70,19 @@ template <int MASK> MJB_HD V3 cross_m(V3 a, V3 b) {
     if constexpr (MASK & 4) { r.x += a.y * b.z; r.y -= a.x * b.z; }
     return r;
 }
+// acc + a x b  and  acc - a x b  as two FMAs per component (a bare cross product followed by a vector
+// add costs three FP64 operations per component)
+MJB_HD V3 cross_acc(V3 acc, V3 a, V3 b) {
+    return {fma(a.y, b.z, fma(-a.z, b.y, acc.x)), fma(a.z, b.x, fma(-a.x, b.z, acc.y)), fma(a.x, b.y, fma(-a.y, b.x, acc.z))};
+}
+// acc + SIGN * (a x b), b's components outside MASK structurally zero
+template <int MASK, int SIGN> MJB_HD V3 cross_m_acc(V3 acc, V3 a, V3 b) {
+    const double sx = SIGN > 0 ? b.x : -b.x, sy = SIGN > 0 ? b.y : -b.y, sz = SIGN > 0 ? b.z : -b.z;
+    if constexpr (MASK & 1) { acc.y = fma(a.z, sx, acc.y); acc.z = fma(-a.y, sx, acc.z); }
+    if constexpr (MASK & 2) { acc.x = fma(-a.z, sy, acc.x); acc.z = fma(a.x, sy, acc.z); }
+    if constexpr (MASK & 4) { acc.x = fma(a.y, sz, acc.x); acc.y = fma(-a.x, sz, acc.y); }
+    return acc;
+}
 // I w for a symmetric 3x3; FULL = false: diagonal only
 template <bool FULL> MJB_HD V3 mul_s(const S3& I, V3 w) {
     if constexpr (FULL)
@@ -223,7 +236,7 @@ MJB_HD void chain_mass_bias(const P& prm, S& sc, const double (&sn)[7], const do
                 if constexpr (OM != 0) {
                     const V3 o = link_offset<T, i>(prm);
                     const V3 wxo = cross_m<OM>(w, o);
-                    ao = ao + cross_m<OM>(al, o) + cross(w, wxo);
+                    ao = cross_acc(cross_m_acc<OM, 1>(ac, al, o), w, wxo);
                 }
                 const V3 wp = rotT<AX>(w, sn[i], cs[i]);
                 const V3 alp = rotT<AX>(al, sn[i], cs[i]);
@@ -237,12 +250,12 @@ MJB_HD void chain_mass_bias(const P& prm, S& sc, const double (&sn)[7], const do
                 const S3 Io = link_inertia_o<T, i>(prm);
                 const double m = prm[CH_MASS + i];
                 V3 f = m * ac;
-                V3 n = mul_s<T::full_inertia(i)>(Io, al) + cross(w, mul_s<T::full_inertia(i)>(Io, w));
+                V3 n = cross_acc(mul_s<T::full_inertia(i)>(Io, al), w, mul_s<T::full_inertia(i)>(Io, w));
                 if constexpr (CM != 0) {
                     const V3 h = link_h<T, i>(prm);
                     const V3 wxh = cross_m<CM>(w, h);
-                    f = f + cross_m<CM>(al, h) + cross(w, wxh);
-                    n = n - cross_m<CM>(ac, h);   // h x a = -(a x h)
+                    f = cross_acc(cross_m_acc<CM, 1>(f, al, h), w, wxh);
+                    n = cross_m_acc<CM, -1>(n, ac, h);   // h x a = -(a x h)
                 }
                 sc.st(SC_LF + 3 * (i - 1), f.x); sc.st(SC_LF + 3 * (i - 1) + 1, f.y); sc.st(SC_LF + 3 * (i - 1) + 2, f.z);
                 sc.st(SC_LN + 3 * (i - 1), n.x); sc.st(SC_LN + 3 * (i - 1) + 1, n.y); sc.st(SC_LN + 3 * (i - 1) + 2, n.z);
@@ -263,7 +276,7 @@ MJB_HD void chain_mass_bias(const P& prm, S& sc, const double (&sn)[7], const do
             if constexpr (i > 0) {
                 fa = rot<AX>(fa, sn[i], cs[i]);
                 na = rot<AX>(na, sn[i], cs[i]);
-                if constexpr (T::off_mask(i) != 0) na = na - cross_m<T::off_mask(i)>(fa, link_offset<T, i>(prm));   // o x f
+                if constexpr (T::off_mask(i) != 0) na = cross_m_acc<T::off_mask(i), -1>(na, fa, link_offset<T, i>(prm));   // + o x f
             }
         });
     }
@@ -295,7 +308,7 @@ MJB_HD void chain_mass_bias(const P& prm, S& sc, const double (&sn)[7], const do
                 constexpr int AJ = T::axis(j);
                 F = rot<AJ>(F, sn[j], cs[j]);
                 N = rot<AJ>(N, sn[j], cs[j]);
-                if constexpr (T::off_mask(j) != 0) N = N - cross_m<T::off_mask(j)>(F, link_offset<T, j>(prm));
+                if constexpr (T::off_mask(j) != 0) N = cross_m_acc<T::off_mask(j), -1>(N, F, link_offset<T, j>(prm));
                 sc.st(sc_m(i, j - 1), comp<T::axis(j - 1)>(N));
             });
             // move the composite to the parent frame
