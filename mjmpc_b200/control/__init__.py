@@ -1,9 +1,10 @@
+"""Controllers of the sampling-MPC hot path (same class names as ``mjmpc.control``)."""
 from .controller import Controller
 from .olgaussian_mpc import OLGaussianMPC
+from .mppi import MPPI
 from .cem import CEM
 from .gaussian_dmd import DMDMPC
-from .mppi import MPPI
-from .particle_filter_controller import PFMPC
 from .random_shooting import RandomShooting
+from .particle_filter_controller import PFMPC
 
-__all__ = ["Controller", "OLGaussianMPC", "CEM", "DMDMPC", "MPPI", "PFMPC", "RandomShooting"]
+__all__ = [c.__name__ for c in (Controller, OLGaussianMPC, MPPI, CEM, DMDMPC, RandomShooting, PFMPC)]

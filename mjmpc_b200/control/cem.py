@@ -14,30 +14,10 @@ from .olgaussian_mpc import OLGaussianMPC
 
 
 class CEM(OLGaussianMPC):
-    def __init__(self,
-                 d_state,
-                 d_obs,
-                 d_action,
-                 horizon,
-                 init_cov,
-                 base_action,
-                 elite_frac,
-                 num_particles,
-                 step_size,
-                 gamma,
-                 n_iters,
-                 action_lows,
-                 action_highs,
-                 set_sim_state_fn=None,
-                 rollout_fn=None,
-                 beta=0.0,
-                 cov_type='diagonal',
-                 sample_mode='mean',
-                 batch_size=1,
-                 filter_coeffs=[1., 0., 0.],
-                 seed=0,
-                 device=None,
-                 shard=None):
+    def __init__(self, d_state, d_obs, d_action, horizon, init_cov, base_action, elite_frac, num_particles,
+                 step_size, gamma, n_iters, action_lows, action_highs, set_sim_state_fn=None,
+                 rollout_fn=None, beta=0.0, cov_type='diagonal', sample_mode='mean', batch_size=1,
+                 filter_coeffs=[1., 0., 0.], seed=0, device=None, shard=None):
         super(CEM, self).__init__(d_state, d_obs, d_action, action_lows, action_highs, horizon, init_cov,
                                   np.zeros(shape=(horizon, d_action)), base_action, num_particles, gamma,
                                   n_iters, step_size, filter_coeffs, set_sim_state_fn, rollout_fn, cov_type,

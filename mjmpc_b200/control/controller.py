@@ -19,22 +19,9 @@ from ..utils.shard import ShardContext
 
 
 class Controller(ABC):
-    def __init__(self,
-                 d_state,
-                 d_obs,
-                 d_action,
-                 action_lows,
-                 action_highs,
-                 horizon,
-                 gamma,
-                 n_iters,
-                 set_sim_state_fn=None,
-                 rollout_fn=None,
-                 sample_mode='mean',
-                 batch_size=1,
-                 seed=0,
-                 device=None,
-                 shard=None):
+    def __init__(self, d_state, d_obs, d_action, action_lows, action_highs, horizon, gamma, n_iters,
+                 set_sim_state_fn=None, rollout_fn=None, sample_mode='mean', batch_size=1, seed=0,
+                 device=None, shard=None):
         """Parameters as in the reference (controller.py:28-63) plus
         device : torch.device or int, the GPU this controller lives on (default: current)
         shard  : ShardContext, this process's slice of the particles (default: all of them)

@@ -12,34 +12,11 @@ from .olgaussian_mpc import OLGaussianMPC
 
 
 class MPPI(OLGaussianMPC):
-    def __init__(self,
-                 d_state,
-                 d_obs,
-                 d_action,
-                 horizon,
-                 init_cov,
-                 base_action,
-                 lam,
-                 num_particles,
-                 step_size,
-                 alpha,
-                 gamma,
-                 n_iters,
-                 action_lows,
-                 action_highs,
-                 time_based_weights=False,
-                 set_sim_state_fn=None,
-                 get_sim_state_fn=None,
-                 sim_step_fn=None,
-                 sim_reset_fn=None,
-                 rollout_fn=None,
-                 sample_mode='mean',
-                 batch_size=1,
-                 filter_coeffs=[1., 0., 0.],
-                 seed=0,
-                 use_zero_control_seq=False,
-                 device=None,
-                 shard=None):
+    def __init__(self, d_state, d_obs, d_action, horizon, init_cov, base_action, lam, num_particles,
+                 step_size, alpha, gamma, n_iters, action_lows, action_highs, time_based_weights=False,
+                 set_sim_state_fn=None, get_sim_state_fn=None, sim_step_fn=None, sim_reset_fn=None,
+                 rollout_fn=None, sample_mode='mean', batch_size=1, filter_coeffs=[1., 0., 0.], seed=0,
+                 use_zero_control_seq=False, device=None, shard=None):
         # get_sim_state_fn / sim_step_fn / sim_reset_fn are accepted and ignored, like mppi.py:34-36
         super(MPPI, self).__init__(d_state, d_obs, d_action, action_lows, action_highs, horizon, init_cov,
                                    np.zeros(shape=(horizon, d_action)), base_action, num_particles, gamma,

@@ -19,30 +19,10 @@ from .controller import Controller
 
 
 class OLGaussianMPC(Controller):
-    def __init__(self,
-                 d_state,
-                 d_obs,
-                 d_action,
-                 action_lows,
-                 action_highs,
-                 horizon,
-                 init_cov,
-                 init_mean,
-                 base_action,
-                 num_particles,
-                 gamma,
-                 n_iters,
-                 step_size,
-                 filter_coeffs,
-                 set_sim_state_fn=None,
-                 rollout_fn=None,
-                 cov_type='diagonal',
-                 sample_mode='mean',
-                 batch_size=1,
-                 seed=0,
-                 use_zero_control_seq=False,
-                 device=None,
-                 shard=None):
+    def __init__(self, d_state, d_obs, d_action, action_lows, action_highs, horizon, init_cov, init_mean,
+                 base_action, num_particles, gamma, n_iters, step_size, filter_coeffs, set_sim_state_fn=None,
+                 rollout_fn=None, cov_type='diagonal', sample_mode='mean', batch_size=1, seed=0,
+                 use_zero_control_seq=False, device=None, shard=None):
         super(OLGaussianMPC, self).__init__(d_state, d_obs, d_action, action_lows, action_highs, horizon,
                                             gamma, n_iters, set_sim_state_fn, rollout_fn, sample_mode,
                                             batch_size, seed, device, shard)

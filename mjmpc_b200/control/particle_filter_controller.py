@@ -17,28 +17,10 @@ from .controller import Controller
 
 
 class PFMPC(Controller):
-    def __init__(self,
-                 d_state,
-                 d_obs,
-                 d_action,
-                 horizon,
-                 cov_shift,
-                 cov_resample,
-                 base_action,
-                 lam,
-                 num_particles,
-                 gamma,
-                 n_iters,
-                 action_lows,
-                 action_highs,
-                 set_sim_state_fn=None,
-                 rollout_fn=None,
-                 sample_mode="mean",
-                 batch_size=1,
-                 filter_coeffs=[1., 0., 0.],
-                 seed=0,
-                 device=None,
-                 shard=None):
+    def __init__(self, d_state, d_obs, d_action, horizon, cov_shift, cov_resample, base_action, lam,
+                 num_particles, gamma, n_iters, action_lows, action_highs, set_sim_state_fn=None,
+                 rollout_fn=None, sample_mode="mean", batch_size=1, filter_coeffs=[1., 0., 0.], seed=0,
+                 device=None, shard=None):
         super(PFMPC, self).__init__(d_state, d_obs, d_action, action_lows, action_highs, horizon, gamma, n_iters,
                                     set_sim_state_fn, rollout_fn, sample_mode, batch_size, seed, device, shard)
         self.lam = lam

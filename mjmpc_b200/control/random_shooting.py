@@ -13,26 +13,9 @@ from .olgaussian_mpc import OLGaussianMPC
 
 
 class RandomShooting(OLGaussianMPC):
-    def __init__(self,
-                 d_state,
-                 d_obs,
-                 d_action,
-                 horizon,
-                 init_cov,
-                 base_action,
-                 num_particles,
-                 step_size,
-                 gamma,
-                 n_iters,
-                 action_lows,
-                 action_highs,
-                 set_sim_state_fn=None,
-                 rollout_fn=None,
-                 sample_mode='mean',
-                 filter_coeffs=[1.0, 0.0, 0.0],
-                 batch_size=1,
-                 seed=0,
-                 device=None,
+    def __init__(self, d_state, d_obs, d_action, horizon, init_cov, base_action, num_particles, step_size,
+                 gamma, n_iters, action_lows, action_highs, set_sim_state_fn=None, rollout_fn=None,
+                 sample_mode='mean', filter_coeffs=[1.0, 0.0, 0.0], batch_size=1, seed=0, device=None,
                  shard=None):
         super(RandomShooting, self).__init__(d_state, d_obs, d_action, action_lows, action_highs, horizon, init_cov,
                                              np.zeros(shape=(horizon, d_action)), base_action, num_particles,

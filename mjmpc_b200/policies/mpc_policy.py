@@ -1,31 +1,32 @@
-"""``MPCPolicy`` -- the reference's policy facade (``mjmpc/policies/mpc_policy.py:7-40``):
-controller name -> class, ``get_action`` -> ``controller.optimize``.
+"""``MPCPolicy`` -- the reference's policy facade (``mjmpc/policies/mpc_policy.py:7-40``): controller name
+-> class built from the YAML block splatted as keyword arguments, ``get_action`` -> ``controller.optimize``.
 """
 from __future__ import annotations
 
 from .. import control
 
+# the sampling-MPC controllers on the GPU path; the reference's other names (ilqr, mppiq,
+# random_shooting_nn, softq, reinforce) are outside it and raise like an unknown name does there
+_CONTROLLERS = {
+    "mppi": control.MPPI,
+    "cem": control.CEM,
+    "dmd": control.DMDMPC,
+    "pfmpc": control.PFMPC,
+    "random_shooting": control.RandomShooting,
+}
+
 
 class MPCPolicy(object):
     def __init__(self, controller_type, param_dict, batch_size=1):
-        self.batch_size = batch_size      # policies/policy.py:8-10
-        if controller_type == "cem":
-            self.controller = control.CEM(**param_dict)
-        elif controller_type == "dmd":
-            self.controller = control.DMDMPC(**param_dict)
-        elif controller_type == "mppi":
-            self.controller = control.MPPI(**param_dict)
-        elif controller_type == "pfmpc":
-            self.controller = control.PFMPC(**param_dict)
-        elif controller_type == "random_shooting":
-            self.controller = control.RandomShooting(**param_dict)
-        else:
-            # ilqr / mppiq / random_shooting_nn / softq / reinforce are outside the sampling-MPC hot path
-            raise NotImplementedError("Controller type does not exist")
+        self.batch_size = batch_size
+        try:
+            cls = _CONTROLLERS[controller_type]
+        except KeyError:
+            raise NotImplementedError("Controller type does not exist") from None
+        self.controller = cls(**param_dict)
 
     def get_action(self, state, calc_val=False, hotstart=True):
-        action, value = self.controller.optimize(state, calc_val, hotstart)
-        return action, value
+        return self.controller.optimize(state, calc_val, hotstart)
 
     def reset(self):
         self.controller.reset()

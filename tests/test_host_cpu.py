@@ -206,3 +206,61 @@ def test_sincos_joint_accuracy(hostcheck):
         hostcheck.hostcheck_sincos(float(x), C.byref(s), C.byref(c))
         err = max(err, abs(s.value - np.sin(x)), abs(c.value - np.cos(x)))
     assert err < 4e-16
+
+
+# ---- driver / config glue --------------------------------------------------------------------------------
+def test_example_config_loads_like_the_reference_file():
+    import yaml
+    mine = yaml.safe_load(open(os.path.join(ROOT, "examples", "configs", "reacher_7dof-v0.yml")))
+    for name in ("mppi", "cem", "dmd", "pfmpc", "random_shooting"):
+        assert name in mine and mine[name]["horizon"] == 16 and mine[name]["num_cpu"] * mine[name]["particles_per_cpu"] == 32
+    ref_path = "/root/reference/examples/configs/reacher_7dof-v0.yml"
+    if os.path.exists(ref_path):
+        ref = yaml.safe_load(open(ref_path))
+        for name in ("mppi", "cem", "dmd", "pfmpc"):       # the reference's random_shooting block has a malformed init_cov
+            assert mine[name] == ref[name], name
+        for key in ("env_name", "n_episodes", "max_ep_length", "seed", "base_action"):
+            assert mine[key] == ref[key]
+
+
+def test_load_policy_params_follows_the_reference_driver():
+    """examples/example_mpc.py:71-79,135-136: env dims injected, num_particles = num_cpu * particles_per_cpu,
+    both popped; plus the top-level base_action fallback."""
+    import sys
+    import types
+    import yaml
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    from run_mpc import load_policy_params
+    exp = yaml.safe_load(open(os.path.join(ROOT, "examples", "configs", "reacher_7dof-v0.yml")))
+    env = types.SimpleNamespace(d_obs=20, d_state=25, d_action=7, action_lows=-np.ones(7), action_highs=np.ones(7))
+    p, num_cpu = load_policy_params(exp, "mppi", env)
+    assert num_cpu == 8 and p["num_particles"] == 32 and "num_cpu" not in p and "particles_per_cpu" not in p
+    assert p["base_action"] == "null" and p["d_action"] == 7 and p["lam"] == 0.2
+    assert "num_cpu" in exp["mppi"]              # the loaded YAML itself is left untouched
+
+
+def test_mjcf_reader_rejects_unsupported_models(tmp_path):
+    from mjmpc_b200.envs.mjcf import load_mjcf
+    bad = tmp_path / "bad.xml"
+    bad.write_text('<mujoco><compiler inertiafromgeom="true" angle="radian" coordinate="local"/>'
+                   '<option timestep="0.01" gravity="0 0 -9.81"/><worldbody/></mujoco>')
+    with pytest.raises(ValueError):
+        load_mjcf(str(bad))
+    bad.write_text('<mujoco><compiler inertiafromgeom="false" angle="radian"/><option/><worldbody/></mujoco>')
+    with pytest.raises(ValueError):
+        load_mjcf(str(bad))
+
+
+def test_controllers_refuse_to_run_without_cuda():
+    """No CPU fallback: on a machine without a GPU the product path raises instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mjmpc_b200 import _lib
+    from mjmpc_b200.control import MPPI
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    with pytest.raises(_lib.MjbError):
+        GpuReacherVecEnv()
+    with pytest.raises(_lib.MjbError):
+        MPPI(d_state=25, d_obs=20, d_action=7, horizon=4, init_cov=1.0, base_action='null', lam=0.2, num_particles=8,
+             step_size=1.0, alpha=1, gamma=1.0, n_iters=1, action_lows=-np.ones(7), action_highs=np.ones(7))
