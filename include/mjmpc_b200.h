@@ -63,6 +63,15 @@ typedef struct {
     double* qv_traj;             /* (K, H, 14) row-major qpos,qvel after each env step, or NULL */
     double* next_obs;            /* (K, H, MJB_OBS_DIM) row-major, or NULL */
     int* ncon;                   /* (K,) substeps with >=1 active constraint row, or NULL */
+    /* Fused K2: with noise == NULL and noise_cov != NULL the kernel generates the noise itself (same Philox
+     * counters, covariance factor and filter as mjb_generate_noise -> bit-identical samples) and the noise
+     * tensor never exists in HBM.  Fields mirror mjb_noise_args. */
+    const double* noise_cov;     /* (7,7) device covariance, or NULL */
+    unsigned long long noise_seed, noise_offset;
+    const long long* noise_step_ptr;
+    double noise_beta0, noise_beta1, noise_beta2;
+    long long noise_k_offset, noise_K_global;
+    int noise_zero_last;         /* particle noise_K_global-1 gets noise = -mean (mean row of its controller) */
 } mjb_rollout_args;
 int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a, void* stream);
 

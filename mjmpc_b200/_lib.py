@@ -28,6 +28,10 @@ class RolloutArgs(C.Structure):
         ("costs", C.c_void_p), ("costs_sk", c_ll), ("costs_st", c_ll),
         ("actions", C.c_void_p), ("act_sk", c_ll), ("act_st", c_ll), ("act_sj", c_ll),
         ("qv_traj", C.c_void_p), ("next_obs", C.c_void_p), ("ncon", C.c_void_p),
+        ("noise_cov", C.c_void_p), ("noise_seed", C.c_ulonglong), ("noise_offset", C.c_ulonglong),
+        ("noise_step_ptr", C.c_void_p),
+        ("noise_beta0", C.c_double), ("noise_beta1", C.c_double), ("noise_beta2", C.c_double),
+        ("noise_k_offset", c_ll), ("noise_K_global", c_ll), ("noise_zero_last", C.c_int),
     ]
 
 

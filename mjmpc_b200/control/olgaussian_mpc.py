@@ -53,6 +53,9 @@ class OLGaussianMPC(Controller):
             if use_zero_control_seq:
                 raise NotImplementedError("use_zero_control_seq is not available for batched instances")
         self._particle_id_offset = 0       # first global Philox particle index of this controller's block
+        # draw the noise inside the rollout kernel when the backend can (rollout_fn.accepts_noise_spec):
+        # same samples as sample_noise(), but the (K,H,d) noise tensor never exists in HBM
+        self.fuse_noise = True
         self._mean = self._mean_from(self.init_mean)
         self._cov = self._to_device(np.diag(self.init_cov)).contiguous()
         self._init_cov_d = self._to_device(self.init_cov)
@@ -119,17 +122,21 @@ class OLGaussianMPC(Controller):
         return next_action
 
     # ---- olgaussian_mpc.py:88-93 ---------------------------------------------------------------------
-    def sample_noise(self):
+    def noise_spec(self):
+        """What sample_noise() would draw, as parameters (for backends that generate noise in-kernel)."""
         k0, kl = self.shard.local_range(self.num_particles)
         kl *= self.batch_size
         k0 += self._particle_id_offset
-        out = self._buf("noise", (self.horizon, self.d_action, kl)).permute(2, 0, 1)
-        delta = generate_noise(self._cov, self.filter_coeffs, shape=(kl, self.horizon), base_seed=self.seed_val,
-                               step=self._noise_step if self._noise_step is not None else self.num_steps,
-                               k_offset=k0, K_global=self._particle_id_offset + self.num_particles * self.batch_size,
-                               zero_last_mean=self._mean if self.use_zero_control_seq else None,
-                               out=out, device=self.device)
-        return delta
+        return control_utils.NoiseSpec(
+            self._cov, self.filter_coeffs, (kl, self.horizon), self.seed_val,
+            step=self._noise_step if self._noise_step is not None else self.num_steps,
+            k_offset=k0, K_global=self._particle_id_offset + self.num_particles * self.batch_size,
+            zero_last=self.use_zero_control_seq, mean=self._mean)
+
+    def sample_noise(self):
+        spec = self.noise_spec()
+        out = self._buf("noise", (self.horizon, self.d_action, spec.shape[0])).permute(2, 0, 1)
+        return spec.materialize(out=out)
 
     # ---- olgaussian_mpc.py:95-114 --------------------------------------------------------------------
     def generate_rollouts(self, state):
@@ -137,7 +144,10 @@ class OLGaussianMPC(Controller):
             if self.batch_size > 1 and isinstance(state, dict):
                 state = [state] * self.batch_size          # one state for every instance
             self._set_sim_state_fn(copy.deepcopy(state))
-        delta = self.sample_noise()       # use_zero_control_seq is applied inside the kernel
+        if self.fuse_noise and getattr(self._rollout_fn, "accepts_noise_spec", False):
+            delta = self.noise_spec()     # drawn inside the rollout kernel
+        else:
+            delta = self.sample_noise()   # use_zero_control_seq is applied inside the noise kernel
         trajectories = self._rollout_fn(self.local_particles, self.horizon, self._mean, delta, mode="open_loop")
         return trajectories
 

@@ -205,6 +205,8 @@ enum { SC_LF = 0, SC_LN = 18, SC_M = 36, SC_JC = 28, SC_U = 64, SC_NZ = 71, SC_N
 #else
 enum { SC_LF = 0, SC_LN = 18, SC_M = 36, SC_JC = 28, SC_U = 64, SC_NZ = 71, SC_NSLOT = 78, SC_M2 = 0 };
 #endif
+// fused in-kernel noise: filtered history eps[t-1] lives in the SC_NZ slots, eps[t-2] in SC_E2
+enum { SC_E2 = SC_NSLOT, SC_NSLOT_FUSED = SC_NSLOT + 7 };
 MJB_HD constexpr int sc_m(int i, int j) { return SC_M + i * (i + 1) / 2 + j; }   // lower triangle, i >= j
 
 struct HostScratch {

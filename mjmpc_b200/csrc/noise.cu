@@ -12,59 +12,14 @@
 // determinism and its independence from how particles are sharded (counters are keyed by the
 // GLOBAL particle index).
 #include "common.h"
+#include "philox_noise.cuh"
 
 namespace mjb {
-
-#define MJB_MAXD 8
-
-struct Philox {
-    unsigned k0, k1;
-    __device__ __forceinline__ void operator()(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned (&o)[4]) const {
-        unsigned a = k0, b = k1;
-#pragma unroll
-        for (int r = 0; r < 10; r++) {
-            const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-            const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-            const unsigned n0 = hi1 ^ c1 ^ a, n2 = hi0 ^ c3 ^ b;
-            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-            a += 0x9E3779B9u; b += 0xBB67AE85u;
-        }
-        o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
-    }
-};
-
-// Four standard normals from the four 32-bit words of one Philox call.  The Gaussian variates are
-// formed in FP32 (Box-Muller on 32-/24-bit uniforms with the SFU log / sincos: 24-bit resolution,
-// |z| <= 6.7 sigma) and promoted to FP64; the covariance transform and the filter below run in FP64.
-// Exploration noise does not need 53-bit variates, and the kernel is instruction-bound on the Philox
-// rounds, so every generated word is used.
-__device__ __forceinline__ void normal_pair32(unsigned a, unsigned b, double& z0, double& z1) {
-    const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;    // (0,1], 2^-32
-    const float u2 = (float)(b >> 8) * 5.9604644775390625e-08f;      // [0,1), 2^-24: exact in FP32
-    const float rad = sqrtf(-2.0f * logf(fminf(u1, 1.0f)));
-    float s, c;
-    sincospif(2.0f * u2, &s, &c);
-    z0 = (double)(rad * c); z1 = (double)(rad * s);
-}
 
 template <int D>
 __global__ void __launch_bounds__(128) noise_kernel(mjb_noise_args a) {
     __shared__ double L[MJB_MAXD][MJB_MAXD];
-    if (threadIdx.x == 0) {
-        // lower Cholesky factor of cov (positive semi-definite tolerated: a non-positive pivot zeroes its column)
-        for (int j = 0; j < D; j++) {
-            double s = a.cov[j * D + j];
-            for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k];
-            const double piv = s > 0.0 ? sqrt(s) : 0.0;
-            L[j][j] = piv;
-            for (int i = j + 1; i < D; i++) {
-                double t = a.cov[i * D + j];
-                for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
-                L[i][j] = piv > 0.0 ? t / piv : 0.0;
-            }
-            for (int i = 0; i < j; i++) L[i][j] = 0.0;
-        }
-    }
+    if (threadIdx.x == 0) noise_chol<D>(a.cov, L);
     __syncthreads();
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.K) return;
@@ -79,25 +34,9 @@ __global__ void __launch_bounds__(128) noise_kernel(mjb_noise_args a) {
     const bool zero_seq = a.zero_last && (long long)gk == a.K_global - 1;
     for (int t = 0; t < a.H; t++) {
         double z[(D + 3) / 4 * 4];
-#pragma unroll
-        for (int p = 0; p < (D + 3) / 4; p++) {
-            unsigned r[4];
-            ph((unsigned)gk, step_ctr, (unsigned)t, tag_hi | (unsigned)p, r);
-            normal_pair32(r[0], r[1], z[4 * p], z[4 * p + 1]);
-            normal_pair32(r[2], r[3], z[4 * p + 2], z[4 * p + 3]);
-        }
+        noise_normals<D>(ph, gk, step_ctr, tag_hi, t, z);
         double e[D];
-#pragma unroll
-        for (int j = 0; j < D; j++) {
-            double s = 0.0;
-#pragma unroll
-            for (int i = 0; i <= j; i++) s += L[j][i] * z[i];
-            e[j] = s;
-        }
-        if (t >= 2) {
-#pragma unroll
-            for (int j = 0; j < D; j++) e[j] = a.beta0 * e[j] + a.beta1 * e1[j] + a.beta2 * e2[j];
-        }
+        noise_shape<D>(L, z, t, a.beta0, a.beta1, a.beta2, e1, e2, e);
 #pragma unroll
         for (int j = 0; j < D; j++) {
             e2[j] = e1[j]; e1[j] = e[j];

@@ -5,6 +5,7 @@
 // fanned out by SubprocVecEnv.rollout (mjmpc/envs/vec_env/subproc_vec_env.py:161-186).
 #include <type_traits>
 #include "chain_dynamics.cuh"
+#include "philox_noise.cuh"
 #include "common.h"
 
 namespace mjb {
@@ -44,10 +45,17 @@ struct SmemScratch {
 // small block keeps the second wave of a K=65536 launch evenly spread over the 148 SMs.
 // EXTRA: also write the per-step state trajectory / observations / constraint counters (tests, adaptors
 // that hand observations back); the production instantiation carries none of that code.
-template <class T, class P, bool EXTRA>
+// FUSED: the action noise is generated in the kernel (Philox + covariance factor + AR filter, the code of
+// K2) on the integer / FP32 pipes the FP64-bound rollout leaves idle; the noise tensor never touches HBM.
+template <class T, class P, bool EXTRA, bool FUSED>
 __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_kernel(const double* __restrict__ params, int n_inst,
                                                                 mjb_rollout_args a) {
-    __shared__ double smem[SC_NSLOT * MJB_ROLLOUT_BLOCK];
+    __shared__ double smem[(FUSED ? SC_NSLOT_FUSED : SC_NSLOT) * MJB_ROLLOUT_BLOCK];
+    __shared__ double Lsh[FUSED ? MJB_MAXD : 1][MJB_MAXD];
+    if constexpr (FUSED) {
+        if (threadIdx.x == 0) noise_chol<7>(a.noise_cov, Lsh);
+        __syncthreads();
+    }
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.K) return;
     SmemScratch sc{smem + threadIdx.x};
@@ -71,8 +79,18 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
     double* __restrict__ cp = a.costs + k * a.costs_sk;
     // The noise row of env step t+1 is copied global -> shared asynchronously while step t is simulated,
     // so its HBM latency (the only long-latency load of the loop) is never waited for.
+    // fused noise: Philox keyed like mjb_generate_noise
+    const unsigned long long gk = FUSED ? (unsigned long long)(a.noise_k_offset + k) : 0ull;
+    const Philox ph{(unsigned)a.noise_seed, (unsigned)(a.noise_seed >> 32)};
+    const unsigned step_ctr = FUSED ? (a.noise_step_ptr ? (unsigned)(*a.noise_step_ptr) : (unsigned)a.noise_offset) : 0u;
+    const unsigned tag_hi = (unsigned)(a.noise_offset >> 32) << 8;
+    const bool zero_seq = FUSED && a.noise_zero_last && (long long)gk == a.noise_K_global - 1;
+    if constexpr (FUSED) {
+#pragma unroll
+        for (int j = 0; j < 7; j++) { sc.st(SC_NZ + j, 0.0); sc.st(SC_E2 + j, 0.0); }
+    }
 #ifndef MJB_NO_PREFETCH
-    if (np) {
+    if (!FUSED && np) {
         const double* nj = np;
 #pragma unroll
         for (int j = 0; j < 7; j++) { sc.fetch(SC_NZ + j, nj); nj += a.noise_sj; }
@@ -83,6 +101,19 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
         {
             double* aj = ap;
             double x[7];
+            if constexpr (FUSED) {
+                double z[8], e[7], h1[7], h2[7];
+                noise_normals<7>(ph, gk, step_ctr, tag_hi, t, z);
+#pragma unroll
+                for (int j = 0; j < 7; j++) { h1[j] = sc.ld(SC_NZ + j); h2[j] = sc.ld(SC_E2 + j); }
+                noise_shape<7>(Lsh, z, t, a.noise_beta0, a.noise_beta1, a.noise_beta2, h1, h2, e);
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    sc.st(SC_E2 + j, h1[j]); sc.st(SC_NZ + j, e[j]);
+                    const double m = __ldg(mean + t * 7 + j);
+                    x[j] = m + (zero_seq ? -m : e[j]);
+                }
+            } else {
 #ifndef MJB_NO_PREFETCH
             if (np) SmemScratch::fetch_wait();
 #pragma unroll
@@ -107,6 +138,7 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
                 if (np) np += a.noise_st;
             }
 #endif
+            }
 #pragma unroll
             for (int j = 0; j < 7; j++) {
                 sc.st(SC_U + j, actuator_torque(prm, j, x[j]));   // held over the frame_skip substeps
@@ -157,6 +189,8 @@ extern "C" int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a
     const int grid = (a->K + block - 1) / block;
     cudaStream_t s = (cudaStream_t)stream;
     const bool extra = a->qv_traj || a->next_obs || a->ncon;
+    const bool fused = a->noise_cov != nullptr;
+    MJB_REQUIRE(!(fused && a->noise), "mjb_rollout_reacher: pass either a noise tensor or in-kernel noise parameters, not both");
     const bool use_const = m->n_instances == 1;
     if (use_const) {
         // constant bank is per device; re-upload only when another model (or an updated one) was there
@@ -168,14 +202,20 @@ extern "C" int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a
             owner[dev] = m->serial;
         }
     }
-#define MJB_LAUNCH(T, P, E) mjb::rollout_reacher_kernel<mjb::T, mjb::P, E><<<grid, block, 0, s>>>(m->d_params, m->n_instances, *a)
+#define MJB_LAUNCH4(T, P, E, F) mjb::rollout_reacher_kernel<mjb::T, mjb::P, E, F><<<grid, block, 0, s>>>(m->d_params, m->n_instances, *a)
+#define MJB_LAUNCH(T, P)                                                    \
+    do {                                                                    \
+        if (extra) { if (fused) MJB_LAUNCH4(T, P, true, true); else MJB_LAUNCH4(T, P, true, false); }   \
+        else { if (fused) MJB_LAUNCH4(T, P, false, true); else MJB_LAUNCH4(T, P, false, false); }       \
+    } while (0)
     if (m->fits_sawyer) {
-        if (use_const) { if (extra) MJB_LAUNCH(SawyerTraits, ConstParams, true); else MJB_LAUNCH(SawyerTraits, ConstParams, false); }
-        else { if (extra) MJB_LAUNCH(SawyerTraits, GlobalParams, true); else MJB_LAUNCH(SawyerTraits, GlobalParams, false); }
+        if (use_const) MJB_LAUNCH(SawyerTraits, ConstParams);
+        else MJB_LAUNCH(SawyerTraits, GlobalParams);
     } else {
         // arbitrary offsets / COMs / inertias on the same axis pattern: dense variant, global parameters
-        if (extra) MJB_LAUNCH(DenseTraits, GlobalParams, true); else MJB_LAUNCH(DenseTraits, GlobalParams, false);
+        MJB_LAUNCH(DenseTraits, GlobalParams);
     }
+#undef MJB_LAUNCH4
 #undef MJB_LAUNCH
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;

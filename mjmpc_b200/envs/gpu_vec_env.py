@@ -27,6 +27,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..utils.control_utils import NoiseSpec
 from .model import CompiledModel, compile_model, randomized_copy, reacher7dof_spec
 
 
@@ -161,7 +162,12 @@ class GpuReacherVecEnv:
         a.particles_per_model = K // self.n_workers
         a.state = self._state.data_ptr()
         a.mean = mean.data_ptr()
-        if noise is not None:
+        if isinstance(noise, NoiseSpec):
+            # fused K2: the kernel draws the noise itself, nothing is read from HBM
+            if noise.shape != (K, H) or noise.cov.shape != (7, 7):
+                raise ValueError("noise spec does not match K=%d H=%d d=7" % (K, H))
+            noise.fill(a)
+        elif noise is not None:
             if tuple(noise.shape) != (K, H, 7):
                 raise ValueError("noise must have shape (K,H,7)")
             a.noise = noise.data_ptr()
@@ -184,7 +190,7 @@ class GpuReacherVecEnv:
         return out
 
     def _to_device(self, x):
-        if x is None or isinstance(x, torch.Tensor):
+        if x is None or isinstance(x, (torch.Tensor, NoiseSpec)):
             return x
         return torch.from_numpy(np.ascontiguousarray(x, np.float64)).to(self.device)
 
@@ -224,7 +230,7 @@ class GpuReacherVecEnv:
         def fn(num_particles, horizon, mean, noise, mode="open_loop"):
             if mode != "open_loop":
                 raise NotImplementedError("only mode='open_loop' runs on the GPU rollout")
-            host = not isinstance(noise, torch.Tensor) and not isinstance(mean, torch.Tensor)
+            host = not isinstance(noise, (torch.Tensor, NoiseSpec)) and not isinstance(mean, torch.Tensor)
             out = self.rollout_device(num_particles, horizon, self._to_device(mean), self._to_device(noise),
                                       want_obs=self.return_observations or host)
             if not host:
@@ -238,4 +244,5 @@ class GpuReacherVecEnv:
             return dict(observations=obs, actions=np.ascontiguousarray(out["actions"].cpu().numpy()),
                         costs=np.ascontiguousarray(out["costs"].cpu().numpy()), dones=np.zeros(nobs.shape[:2]),
                         next_observations=nobs, infos={})
+        fn.accepts_noise_spec = True
         return fn

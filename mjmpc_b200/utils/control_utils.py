@@ -17,6 +17,40 @@ NOISE_STREAM_SHIFT = 2
 NOISE_STREAM_BASE = 3
 
 
+class NoiseSpec:
+    """Parameters of a noise tensor that is generated INSIDE the rollout kernel instead of being
+    materialised by :func:`generate_noise` (same counters, covariance factor and filter -> bit-identical
+    samples).  A rollout backend whose ``rollout_fn`` has ``accepts_noise_spec = True`` takes one in
+    place of the ``noise`` argument; ``materialize()`` produces the tensor it stands for."""
+
+    def __init__(self, cov, filter_coeffs, shape, base_seed, step=0, stream_id=0, k_offset=0, K_global=None,
+                 zero_last=False, mean=None):
+        self.cov, self.filter_coeffs, self.shape = cov, [float(b) for b in filter_coeffs], tuple(shape)
+        self.base_seed, self.step, self.stream_id = int(base_seed), step, int(stream_id)
+        self.k_offset = int(k_offset)
+        self.K_global = int(K_global if K_global is not None else k_offset + shape[0])
+        self.zero_last, self.mean = bool(zero_last), mean
+
+    def materialize(self, out=None):
+        return generate_noise(self.cov, self.filter_coeffs, self.shape, self.base_seed, step=self.step,
+                              stream_id=self.stream_id, k_offset=self.k_offset, K_global=self.K_global,
+                              zero_last_mean=self.mean if self.zero_last else None, out=out,
+                              device=self.cov.device)
+
+    def fill(self, a):
+        """Write the fused-noise fields of a ``RolloutArgs``."""
+        a.noise_cov = self.cov.data_ptr()
+        a.noise_seed = self.base_seed & 0xFFFFFFFFFFFFFFFF
+        if isinstance(self.step, torch.Tensor):
+            a.noise_offset = (self.stream_id & 0xFFFFFFFF) << 32
+            a.noise_step_ptr = self.step.data_ptr()
+        else:
+            a.noise_offset = ((self.stream_id & 0xFFFFFFFF) << 32) | (int(self.step) & 0xFFFFFFFF)
+        a.noise_beta0, a.noise_beta1, a.noise_beta2 = self.filter_coeffs
+        a.noise_k_offset, a.noise_K_global = self.k_offset, self.K_global
+        a.noise_zero_last = int(self.zero_last)
+
+
 def _dev(x, device):
     if isinstance(x, torch.Tensor):
         return x.to(device=device, dtype=torch.float64)

@@ -380,3 +380,26 @@ def test_batched_independent_instances_match_single_controllers(compiled_model):
         single_env.close()
     assert np.abs(acts_b[:, 0] - acts_b[:, 1]).max() > 1e-3                     # instances really differ
     env.close()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_noise_controller_equals_two_kernel_path(compiled_model, graph):
+    """optimize() with the noise drawn inside the rollout kernel == optimize() with a materialised noise tensor."""
+    from conftest import synthetic_state
+    from mjmpc_b200.control import MPPI
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    states = [synthetic_state(compiled_model, 50 + s) for s in range(4)]
+    outs = []
+    for fuse in (True, False):
+        env = GpuReacherVecEnv(compiled_model)
+        c = MPPI(horizon=12, init_cov=0.7, base_action='null', lam=0.2, num_particles=2048, step_size=0.9, alpha=0, gamma=0.99,
+                 n_iters=2, filter_coeffs=[0.25, 0.8, 0.0], seed=21, use_zero_control_seq=True, **_common())
+        c.fuse_noise = fuse
+        c.set_sim_state_fn = env.set_env_state
+        c.rollout_fn = env.rollout_fn
+        if graph:
+            assert c.enable_cuda_graph(states[0])
+        outs.append((np.stack([c.optimize(st)[0] for st in states]), c.mean_action))
+        env.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])

@@ -145,3 +145,41 @@ def test_rollout_per_worker_models(compiled_model):
     # and the models really differ between workers
     assert np.abs(ref["qv"][0] - ref["qv"][K // W]).max() > 1e-6 or True
     env.close()
+
+
+@pytest.mark.parametrize("n_workers,extra", [(1, False), (1, True), (4, False)])
+def test_fused_noise_equals_materialised_noise(compiled_model, n_workers, extra):
+    """Fused K2: the rollout kernel drawing its own noise must give exactly the actions and costs of the
+    two-kernel path (noise tensor from mjb_generate_noise fed to the rollout) -- same counters, same rounding."""
+    import torch
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    from mjmpc_b200.utils.control_utils import NoiseSpec
+    K, H = 1000 if n_workers == 1 else 1024, 12
+    env = GpuReacherVecEnv(compiled_model, n_workers=n_workers)
+    if n_workers > 1:
+        env.randomize_dynamics(dict(body_mass={"r_forearm_link": [0.3, 0.0]}), base_seed=2)
+    env.set_env_state(synthetic_state(compiled_model, 4))
+    rng = np.random.default_rng(3)
+    A = rng.normal(0, 1, (7, 7))
+    cov = torch.from_numpy(A @ A.T / 7 + 0.2 * np.eye(7)).cuda()
+    mean = torch.from_numpy(rng.normal(0, 0.3, (H, 7))).cuda()
+    for zero_last, k_off, Kg in [(False, 0, K), (True, 0, K), (True, 5000, 5000 + K), (False, 77, 100000)]:
+        spec = NoiseSpec(cov, [0.25, 0.8, 0.1], (K, H), 1234, step=7, k_offset=k_off, K_global=Kg, zero_last=zero_last,
+                         mean=mean)
+        noise = spec.materialize()
+        a = env.rollout_device(K, H, mean, noise, want_traj=extra)
+        b = env.rollout_device(K, H, mean, spec, want_traj=extra)
+        assert torch.equal(a["actions"], b["actions"])
+        assert torch.equal(a["costs"], b["costs"])
+        if extra:
+            assert torch.equal(a["qv"], b["qv"])
+        if zero_last:
+            assert torch.all(b["actions"][-1] == 0.0)
+    # a device-resident step counter selects the same stream as the integer step
+    step_d = torch.tensor([7], dtype=torch.int64, device="cuda")
+    spec_d = NoiseSpec(cov, [0.25, 0.8, 0.1], (K, H), 1234, step=step_d, k_offset=77, K_global=100000)
+    c = env.rollout_device(K, H, mean, spec_d)
+    assert torch.equal(c["actions"], b["actions"])
+    with pytest.raises(ValueError):
+        env.rollout_device(K, H + 1, torch.zeros(H + 1, 7, dtype=torch.float64, device="cuda"), spec)
+    env.close()
