@@ -35,7 +35,7 @@ K_GLOBAL, HORIZON, D_ACTION = 65536, 32, 7
 FLOP_PER_PARTICLE_STEP = 5340.0          # BASELINE.md section 4 / SURVEY 8(d): the contract figure
 MPPI_PARAMS = dict(horizon=HORIZON, init_cov=1.0, filter_coeffs=[0.25, 0.8, 0.0], gamma=1.0, n_iters=1,
                    step_size=1.0, lam=0.2, alpha=1, base_action='null')     # reacher_7dof-v0.yml:20-30 + :5
-KERNELS_PER_STEP = 8     # rollout (noise drawn in-kernel), softmax {prep, traj_cost, weighted_reduce, decode_min, chunk_sum}, combine, shift
+KERNELS_PER_STEP = 9     # noise, rollout, softmax {prep, traj_cost, weighted_reduce, decode_min, chunk_sum}, combine, shift
 
 
 def synthetic_states(compiled, n, seed=0):
@@ -160,8 +160,8 @@ def workload_config(n_gpus):
     return {"workload": "MPPI reacher_7dof-v0 K=65536 H=32 n_iters=1 (BASELINE.json configs[2])",
             "num_particles": K_GLOBAL, "horizon": HORIZON, "d_action": D_ACTION,
             "particles_per_gpu": K_GLOBAL // n_gpus, "sharding": "particles, contiguous blocks, %d rank(s)" % n_gpus,
-            "noise": "Philox4x32-10 + covariance factor + AR filter drawn inside the rollout kernel (fused K2), new stream every step", "start_states": "synthetic, SURVEY 8(d), sphere >= 2 cm above the table, new state every step",
-            "l2": "per-step working set (actions + costs = 134 MB at N=1) exceeds the 126 MB L2; no explicit flush"}
+            "noise": "Philox4x32-10 + covariance factor + AR filter kernel (K2), new stream every step", "start_states": "synthetic, SURVEY 8(d), sphere >= 2 cm above the table, new state every step",
+            "l2": "per-step working set (noise + actions + costs = 251 MB at N=1) exceeds the 126 MB L2; no explicit flush"}
 
 
 def run_own(args):
@@ -250,7 +250,7 @@ def run_own(args):
 
     # ---- rollout kernel alone (roofline), CUDA events on the launching stream ---------------------------
     kl = K_GLOBAL // world
-    noise = ctrl.noise_spec()            # what optimize() passes: noise drawn inside the kernel
+    noise = ctrl.sample_noise()
     out = env.rollout_device(kl, HORIZON, ctrl._mean, noise)
     torch.cuda.synchronize()
     ks, ke = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -304,7 +304,7 @@ def run_own(args):
         "gpu_launches": KERNELS_PER_STEP * args.steps, "cuda_graph": bool(graphed), "exchange": exchange,
         "roofline": {"kernel": "rollout_reacher_kernel (K1)", "bound": "fp64", "achieved": achieved, "peak": tf.value,
                      "unit": "TFLOP/s", "frac": achieved / tf.value, "traffic": traffic, "traffic_source": traffic_src,
-                     "algorithmic_hbm_bytes": kl * HORIZON * 64,
+                     "algorithmic_hbm_bytes": kl * HORIZON * 120,
                      "ms_per_launch": k1_ms, "particles_per_launch": kl,
                      "flop_per_particle_step": FLOP_PER_PARTICLE_STEP,
                      "peak_source": "mjb_fp64_peak microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)"},

@@ -53,9 +53,12 @@ class OLGaussianMPC(Controller):
             if use_zero_control_seq:
                 raise NotImplementedError("use_zero_control_seq is not available for batched instances")
         self._particle_id_offset = 0       # first global Philox particle index of this controller's block
-        # draw the noise inside the rollout kernel when the backend can (rollout_fn.accepts_noise_spec):
-        # same samples as sample_noise(), but the (K,H,d) noise tensor never exists in HBM
-        self.fuse_noise = True
+        # fuse_noise = True draws the noise inside the rollout kernel when the backend can
+        # (rollout_fn.accepts_noise_spec): same samples as sample_noise(), and the (K,H,d) noise tensor never
+        # exists in HBM (-117 MB at K=65536).  Off by default: measured on B200 the extra Philox / Box-Muller
+        # instructions lengthen the latency-bound rollout by more (+0.09 ms) than the separate, fully
+        # occupied noise kernel costs (0.065 ms).
+        self.fuse_noise = False
         self._mean = self._mean_from(self.init_mean)
         self._cov = self._to_device(np.diag(self.init_cov)).contiguous()
         self._init_cov_d = self._to_device(self.init_cov)
