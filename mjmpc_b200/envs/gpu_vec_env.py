@@ -93,6 +93,7 @@ class GpuReacherVecEnv:
         self.model = DeviceModel(np.stack([m.chain.params for m in self._worker_models]), device)
         self._state_host = torch.zeros(1, _lib.STATE_DIM, dtype=torch.float64).pin_memory()
         self._state = torch.zeros(1, _lib.STATE_DIM, dtype=torch.float64, device=self.device)
+        self._h2d_done = None
         self.action_lows = -np.ones(7)
         self.action_highs = np.ones(7)
 
@@ -100,14 +101,26 @@ class GpuReacherVecEnv:
     def set_env_state(self, state_dicts):
         """One state for every particle, or a list with one state per batched controller."""
         if isinstance(state_dicts, (list, tuple)):
-            rows = np.stack([_state_vector(s) for s in state_dicts])
+            if len(state_dicts) > 1 and all(isinstance(s, dict) for s in state_dicts):
+                rows = np.empty((len(state_dicts), _lib.STATE_DIM))          # batched instances: one pass per key
+                rows[:, 0:7] = [s["qp"] for s in state_dicts]
+                rows[:, 7:14] = [s["qv"] for s in state_dicts]
+                rows[:, 14:17] = [s["target_pos"] for s in state_dicts]
+            else:
+                rows = np.stack([_state_vector(s) for s in state_dicts])
         else:
             rows = _state_vector(state_dicts)[None]
         if self._state_host.shape[0] != rows.shape[0]:
             self._state_host = torch.zeros(rows.shape[0], _lib.STATE_DIM, dtype=torch.float64).pin_memory()
             self._state = torch.zeros(rows.shape[0], _lib.STATE_DIM, dtype=torch.float64, device=self.device)
+            self._h2d_done = None
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()       # the previous asynchronous copy must have left the pinned buffer
         self._state_host.copy_(torch.from_numpy(rows))
         self._state.copy_(self._state_host, non_blocking=True)
+        if self._h2d_done is None:
+            self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record()
 
     def set_env_state_device(self, state: torch.Tensor):
         """Device-resident (n_ctrl, 17) states (no host round trip).  Copied into the persistent state
