@@ -264,3 +264,22 @@ def test_controllers_refuse_to_run_without_cuda():
     with pytest.raises(_lib.MjbError):
         MPPI(d_state=25, d_obs=20, d_action=7, horizon=4, init_cov=1.0, base_action='null', lam=0.2, num_particles=8,
              step_size=1.0, alpha=1, gamma=1.0, n_iters=1, action_lows=-np.ones(7), action_highs=np.ones(7))
+
+
+def test_ctypes_structs_match_header_layout():
+    """sizeof and the offset of the last field of every argument struct, C compiler vs ctypes mirror."""
+    import ctypes
+    from mjmpc_b200 import _lib
+    pairs = [("mjb_rollout_args", _lib.RolloutArgs, "noise_zero_last"), ("mjb_pendulum_args", _lib.PendulumArgs, "states_out"),
+             ("mjb_noise_args", _lib.NoiseArgs, "out_sj"), ("mjb_softmax_args", _lib.SoftmaxArgs, "partials"),
+             ("mjb_combine_args", _lib.CombineArgs, "stats"), ("mjb_elite_args", _lib.EliteArgs, "partial"),
+             ("mjb_elite_combine_args", _lib.EliteCombineArgs, "cov"), ("mjb_mppi_batched_args", _lib.MppiBatchedArgs, "value")]
+    body = "".join('printf("%%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));' % (c, c, last) for c, _, last in pairs)
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "include/mjmpc_b200.h"\nint main(){%s return 0;}' % body
+    exe = os.path.join(ROOT, "tests", "hostcheck", "layout_probe")
+    subprocess.run(["gcc", "-x", "c", "-", "-I", ROOT, "-o", exe], input=src.encode(), cwd=ROOT, check=True)
+    lines = subprocess.check_output([exe]).decode().split("\n")
+    for (cname, cls, last), line in zip(pairs, lines):
+        size, off = [int(x) for x in line.split()]
+        assert ctypes.sizeof(cls) == size, cname
+        assert getattr(cls, last).offset == off, cname
