@@ -128,6 +128,8 @@ int mjb_cost_to_go(const double* costs, long long sk, long long st, const double
 #define MJB_COV_NONE 0
 #define MJB_COV_DIAG 1
 #define MJB_COV_FULL 2
+#define MJB_RETURNS_CTG 0
+#define MJB_RETURNS_TD_LAMBDA 1
 typedef struct {
     int K, H, d;
     const double* costs; long long costs_sk, costs_st;
@@ -142,6 +144,17 @@ typedef struct {
     double* total;               /* (T,K) out: trajectory cost the weights are computed from */
     double* scratch;             /* >= mjb_softmax_scratch_doubles(K,H,d,cov_mode) */
     double* partials;            /* out: mjb_softmax_partial_doubles(H,d,time_based,cov_mode) */
+    /* MPPIQ (mjmpc/control/mppiq.py:76-126): returns == MJB_RETURNS_TD_LAMBDA replaces the discounted
+     * cost-to-go by the TD(lambda) return of calculate_returns (mppiq.py:104-126) over the per-step total
+     * cost c_t + lam * control_cost_t (mppiq.py:96-97; `lam` carries MPPIQ's beta):
+     *     q_hat_t = q_t + td_lam * cost_to_go(c_t + gamma q_{t+1} - q_t, td_weight_seq)_t  (t < H-1),
+     *     q_hat_{H-1} = q_{H-1},   q = qvals, or (0, ..., 0, c_{H-1}) when qvals == NULL (mppiq.py:109-111)
+     * in the reference's operation order (bit-exact given bit-identical per-step costs). */
+    int returns;                 /* MJB_RETURNS_* */
+    double td_lam, td_gamma;
+    const double* td_weight_seq; /* (H-1,) HOST: cumprod([1, gamma*td_lam, ...]) (mppiq.py:117-119); H == 1: unused */
+    const double* qvals;         /* (K,H) device by strides, or NULL */
+    long long q_sk, q_st;
 } mjb_softmax_args;
 long long mjb_softmax_scratch_doubles(int K, int H, int d, int cov_mode);
 int mjb_softmax_partial_doubles(int H, int d, int time_based, int cov_mode);

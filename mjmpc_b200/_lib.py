@@ -119,6 +119,8 @@ class SoftmaxArgs(C.Structure):
         ("mean", C.c_void_p), ("cov", C.c_void_p), ("gamma_seq", C.c_void_p),
         ("lam", C.c_double), ("control_cost", C.c_int), ("time_based", C.c_int), ("cov_mode", C.c_int),
         ("total", C.c_void_p), ("scratch", C.c_void_p), ("partials", C.c_void_p),
+        ("returns", C.c_int), ("td_lam", C.c_double), ("td_gamma", C.c_double),
+        ("td_weight_seq", C.c_void_p), ("qvals", C.c_void_p), ("q_sk", c_ll), ("q_st", c_ll),
     ]
 
 
@@ -159,6 +161,7 @@ class MppiBatchedArgs(C.Structure):
 
 
 COV_NONE, COV_DIAG, COV_FULL = 0, 1, 2
+RETURNS_CTG, RETURNS_TD_LAMBDA = 0, 1
 BASE_ACTIONS = {"null": 0, "repeat": 1, "random": 2}
 
 EXPORTS += [

@@ -2,9 +2,10 @@
 from .controller import Controller
 from .olgaussian_mpc import OLGaussianMPC
 from .mppi import MPPI
+from .mppiq import MPPIQ
 from .cem import CEM
 from .gaussian_dmd import DMDMPC
 from .random_shooting import RandomShooting
 from .particle_filter_controller import PFMPC
 
-__all__ = [c.__name__ for c in (Controller, OLGaussianMPC, MPPI, CEM, DMDMPC, RandomShooting, PFMPC)]
+__all__ = [c.__name__ for c in (Controller, OLGaussianMPC, MPPI, MPPIQ, CEM, DMDMPC, RandomShooting, PFMPC)]

@@ -197,9 +197,11 @@ class OLGaussianMPC(Controller):
         return costs, actions
 
     def _softmax_update(self, costs, actions, lam, control_cost=False, time_based=False, cov_mode=_lib.COV_NONE,
-                        apply=True):
+                        apply=True, td=None):
         """Phase 1 (local partials) -> all-gather over shards -> phase 2 (combine, smooth).
-        Returns the (2+2T,) stats tensor: value, global min, normalisers, minima."""
+        Returns the (2+2T,) stats tensor: value, global min, normalisers, minima.
+        td = (td_lam, gamma, weight_seq, qvals or None): weights from MPPIQ's TD(lambda) returns instead of
+        the discounted cost-to-go."""
         if self.batch_size > 1:
             raise NotImplementedError("batched instances are implemented for MPPI without time-based weights")
         L = _lib.lib()
@@ -216,6 +218,13 @@ class OLGaussianMPC(Controller):
         a.gamma_seq = g.ctypes.data
         a.lam = float(lam)
         a.control_cost, a.time_based, a.cov_mode = int(control_cost), int(time_based), int(cov_mode)
+        if td is not None:
+            td_lam, td_gamma, wseq, qvals = td
+            wseq = np.ascontiguousarray(wseq, dtype=np.float64)     # host array, kept alive until the call returns
+            a.returns, a.td_lam, a.td_gamma = _lib.RETURNS_TD_LAMBDA, float(td_lam), float(td_gamma)
+            a.td_weight_seq = wseq.ctypes.data
+            if qvals is not None:
+                a.qvals = qvals.data_ptr(); a.q_sk, a.q_st = qvals.stride()
         total = self._buf("total", (T, kl))
         scratch = self._buf("sm_scratch", (int(L.mjb_softmax_scratch_doubles(kl, H, d, cov_mode)),))
         partials = self._buf("sm_partials", (P,))

@@ -86,21 +86,24 @@ __global__ void softmax_prep_kernel(mjb_softmax_args a, int T) {
     }
 }
 
-// per-particle trajectory cost (mppi.py:84-97 / gaussian_dmd.py:94-104) and its minimum over particles
-template <int D>
-__global__ void __launch_bounds__(MJB_RB) traj_cost_kernel(mjb_softmax_args a, GammaSeq G, int T) {
+// per-particle trajectory cost (mppi.py:84-97 / gaussian_dmd.py:94-104) and its minimum over particles.
+// TD = true: MPPIQ's TD(lambda) return (mppiq.py:92-126) instead of the discounted cost-to-go; W is then
+// the (H-1)-entry weight sequence cumprod([1, gamma*td_lam, ...]) and G is unused.
+template <int D, bool TD>
+__global__ void __launch_bounds__(MJB_RB) traj_cost_kernel(mjb_softmax_args a, GammaSeq G, GammaSeq W, int T) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long* menc = (unsigned long long*)a.scratch;
     const double* __restrict__ un = a.scratch + MJB_MAXH;
     const bool live = k < a.K;
-    double S = 0.0, Sc = 0.0, tot0 = INFINITY;
+    double S = 0.0, Sc = 0.0, tot0 = INFINITY, qnext = 0.0;
     // costs are read 8 steps at a time ahead of the (sequential, reference-ordered) accumulation
     for (int tb = a.H - 1; tb >= 0; tb -= 8) {
-        double cbuf[8];
+        double cbuf[8], qbuf[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             const int t = tb - u;
             cbuf[u] = (live && t >= 0) ? a.costs[k * a.costs_sk + t * a.costs_st] : 0.0;
+            if (TD) qbuf[u] = (live && t >= 0 && a.qvals) ? a.qvals[k * a.q_sk + t * a.q_st] : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
@@ -109,22 +112,39 @@ __global__ void __launch_bounds__(MJB_RB) traj_cost_kernel(mjb_softmax_args a, G
             double tot = INFINITY;
             if (live) {
                 const double c = cbuf[u];
-                double ctg;
-                if (G.raw) ctg = c;
-                else { S = __dadd_rn(S, __dmul_rn(G.g[t], c)); ctg = __ddiv_rn(S, G.g[t]); }
-                double ccg = 0.0;
+                double cc = 0.0;
                 if (a.control_cost) {
-                    double cc = 0.0;
 #pragma unroll
                     for (int j = 0; j < D; j++) {
                         const double m = a.mean[t * D + j];
                         const double dl = a.actions[k * a.act_sk + t * a.act_st + j * a.act_sj] - m;
                         cc += 0.5 * un[t * D + j] * (m + 2.0 * dl);
                     }
-                    if (G.raw) ccg = cc;
-                    else { Sc = __dadd_rn(Sc, __dmul_rn(G.g[t], cc)); ccg = __ddiv_rn(Sc, G.g[t]); }
                 }
-                tot = ctg + a.lam * ccg;
+                if constexpr (TD) {
+                    // mppiq.py:96-97 total per-step cost, then calculate_returns (:104-126), reverse order
+                    const double ct = a.control_cost ? __dadd_rn(c, __dmul_rn(a.lam, cc)) : c;
+                    const double q = a.qvals ? qbuf[u] : (t == a.H - 1 ? ct : 0.0);
+                    if (t == a.H - 1) tot = q;
+                    else {
+                        const double td = __dsub_rn(__dadd_rn(ct, __dmul_rn(a.td_gamma, qnext)), q);
+                        double ctg;
+                        if (W.raw) ctg = td;
+                        else { S = __dadd_rn(S, __dmul_rn(W.g[t], td)); ctg = __ddiv_rn(S, W.g[t]); }
+                        tot = __dadd_rn(q, __dmul_rn(a.td_lam, ctg));
+                    }
+                    qnext = q;
+                } else {
+                    double ctg;
+                    if (G.raw) ctg = c;
+                    else { S = __dadd_rn(S, __dmul_rn(G.g[t], c)); ctg = __ddiv_rn(S, G.g[t]); }
+                    double ccg = 0.0;
+                    if (a.control_cost) {
+                        if (G.raw) ccg = cc;
+                        else { Sc = __dadd_rn(Sc, __dmul_rn(G.g[t], cc)); ccg = __ddiv_rn(Sc, G.g[t]); }
+                    }
+                    tot = ctg + a.lam * ccg;
+                }
                 if (T > 1) a.total[(long long)t * a.K + k] = tot;
                 tot0 = tot;
             }
@@ -743,16 +763,24 @@ extern "C" int mjb_softmax_partials(const mjb_softmax_args* a, void* stream) {
     MJB_REQUIRE(!(a->time_based && a->cov_mode != MJB_COV_NONE), "time-based weights have no covariance update");
     if (a->cov_mode < 0 || a->cov_mode > 2)
         return set_error(MJB_EINVAL, "Unidentified covariance type in update_distribution");   // gaussian_dmd.py:85
-    GammaSeq G;
+    MJB_REQUIRE(a->returns == MJB_RETURNS_CTG || a->returns == MJB_RETURNS_TD_LAMBDA, "mjb_softmax_partials: unknown returns mode %d", a->returns);
+    const bool td = a->returns == MJB_RETURNS_TD_LAMBDA;
+    MJB_REQUIRE(!td || a->H == 1 || a->td_weight_seq, "TD(lambda) returns need td_weight_seq");
+    MJB_REQUIRE(!(td && a->cov_mode != MJB_COV_NONE), "TD(lambda) returns have no covariance update");
+    GammaSeq G, W;
     int rc = load_gamma(G, a->gamma_seq, a->H);
     if (rc) return rc;
+    W.raw = 0;
+    if (td && a->H > 1) { rc = load_gamma(W, a->td_weight_seq, a->H - 1); if (rc) return rc; }
     cudaStream_t s = (cudaStream_t)stream;
     const int T = a->time_based ? a->H : 1;
     const int NACC = 1 + a->d + ncov_of(a->d, a->cov_mode);
     const int nch = nchunks_of(a->K);
     softmax_prep_kernel<<<1, 128, 0, s>>>(*a, T);
+    const int tgrid = (a->K + MJB_RB - 1) / MJB_RB;
     switch (a->d) {
-#define MJB_CASE(D) case D: traj_cost_kernel<D><<<(a->K + MJB_RB - 1) / MJB_RB, MJB_RB, 0, s>>>(*a, G, T); break;
+#define MJB_CASE(D) case D: if (td) traj_cost_kernel<D, true><<<tgrid, MJB_RB, 0, s>>>(*a, G, W, T); \
+                            else traj_cost_kernel<D, false><<<tgrid, MJB_RB, 0, s>>>(*a, G, W, T); break;
         MJB_CASE(1) MJB_CASE(2) MJB_CASE(3) MJB_CASE(4) MJB_CASE(5) MJB_CASE(6) MJB_CASE(7) MJB_CASE(8)
 #undef MJB_CASE
     }

@@ -5,10 +5,11 @@ from __future__ import annotations
 
 from .. import control
 
-# the sampling-MPC controllers on the GPU path; the reference's other names (ilqr, mppiq,
+# the sampling-MPC controllers on the GPU path; the reference's other names (ilqr,
 # random_shooting_nn, softq, reinforce) are outside it and raise like an unknown name does there
 _CONTROLLERS = {
     "mppi": control.MPPI,
+    "mppiq": control.MPPIQ,
     "cem": control.CEM,
     "dmd": control.DMDMPC,
     "pfmpc": control.PFMPC,

@@ -77,6 +77,57 @@ def mppi_value(mean, cov, costs, actions, gseq, lam, alpha):
     return -lam * scipy.special.logsumexp((-1.0 / lam) * total_costs, b=(1.0 / total_costs.shape[0]))
 
 
+def mppiq_control_costs(mean, cov, delta, alpha):
+    """mjmpc/control/mppiq.py:128-136 (per-step control cost, no cost-to-go)."""
+    if alpha == 1:
+        return np.zeros((delta.shape[0], delta.shape[1]))
+    u_normalized = mean.dot(np.linalg.inv(cov))[np.newaxis, :, :]
+    control_costs = 0.5 * u_normalized * (mean[np.newaxis, :, :] + 2.0 * delta)
+    return np.sum(control_costs, axis=-1)
+
+
+def mppiq_returns(costs, qvals, gamma, td_lam, horizon):
+    """mjmpc/control/mppiq.py:104-126 (calculate_returns): TD(lambda) estimate of the cost-to-go."""
+    if qvals is None:
+        qvals = np.zeros(costs.shape)
+        qvals[:, -1] = costs[:, -1]
+    td_errors = costs[:, 0:-1] + gamma * qvals[:, 1:] - qvals[:, 0:-1]
+    if horizon == 1:
+        weight_seq = np.array([1.0])
+    else:
+        weight_seq = np.cumprod([1.0] + [gamma * td_lam] * (horizon - 2)).reshape(1, horizon - 1)
+    q_lam_minus_q = cost_to_go(td_errors, weight_seq)
+    q_lam = qvals[:, 0:-1] + td_lam * q_lam_minus_q
+    q_lam = np.hstack([q_lam, qvals[:, [-1]]])
+    return q_lam
+
+
+def mppiq_update(mean, cov, costs, actions, qvals, gamma, td_lam, beta, alpha, step_size, time_based_weights=True):
+    """mjmpc/control/mppiq.py:73-102.  Returns (new_mean, w, q_hat)."""
+    costs = costs.copy(); actions = actions.copy()
+    qvals = None if qvals is None else qvals.copy()
+    delta = actions - mean[None, :, :]
+    control_costs = mppiq_control_costs(mean, cov, delta, alpha)
+    total_costs = costs + beta * control_costs
+    q_hat = mppiq_returns(total_costs, qvals, gamma, td_lam, mean.shape[0])
+    q_full = q_hat
+    if not time_based_weights:
+        q_hat = q_hat[:, 0]
+    w = scipy.special.softmax((-1.0 / beta) * q_hat, axis=0)
+    weighted_seq = w.T * actions.T
+    new_mean = (1.0 - step_size) * mean + step_size * np.sum(weighted_seq.T, axis=0)
+    return new_mean, w, q_full
+
+
+def mppiq_value(mean, cov, costs, actions, qvals, gamma, td_lam, beta, alpha):
+    """mjmpc/control/mppiq.py:138-160."""
+    delta = actions - mean[None, :, :]
+    control_costs = mppiq_control_costs(mean, cov, delta, alpha)
+    total_costs = costs + beta * control_costs
+    q_hat = mppiq_returns(total_costs, None if qvals is None else qvals.copy(), gamma, td_lam, mean.shape[0])[:, 0]
+    return -beta * scipy.special.logsumexp((-1.0 / beta) * q_hat, b=(1.0 / q_hat.shape[0]))
+
+
 def cem_update(mean, cov, costs, actions, gseq, num_elite, step_size, cov_type):
     """mjmpc/control/cem.py:65-86.  Returns (new_mean, new_cov, elite_ids)."""
     H, d = mean.shape

@@ -71,6 +71,31 @@ def main():
         out[name] = dict(mean0=mean, cov0=cov0, costs=costs, actions=actions, w=w, mean1=new_mean, value=val,
                          shifted=ctrl.mean_action.copy(), gamma=kw["gamma"], lam=kw["lam"], alpha=kw["alpha"],
                          step_size=kw["step_size"], time_based=int(kw.get("time_based_weights", False)))
+    # ---- MPPIQ (TD(lambda) returns, optional Q estimates from the rollout) ----------------------------
+    qv = np.abs(np.random.RandomState(21).normal(25.0, 4.0, (K, H)))
+    for name, kw, use_q in (("mppiq_basic", dict(beta=0.3, alpha=1, step_size=1.0, gamma=1.0, td_lam=1.0), False),
+                            ("mppiq_td", dict(beta=0.4, alpha=1, step_size=0.9, gamma=0.97, td_lam=0.8), False),
+                            ("mppiq_qvals", dict(beta=0.5, alpha=0, step_size=0.8, gamma=0.95, td_lam=0.7), True),
+                            ("mppiq_q_notb", dict(beta=0.6, alpha=0, step_size=0.7, gamma=0.9, td_lam=0.5,
+                                                  time_based_weights=False), True),
+                            ("mppiq_lam0", dict(beta=0.5, alpha=1, step_size=1.0, gamma=0.9, td_lam=0.0), True)):
+        ctrl = R.mppiq.MPPIQ(d_action=d, horizon=H, init_cov=0.8, base_action='null', num_particles=K, n_iters=1,
+                             filter_coeffs=[0.25, 0.8, 0.0], seed=3, **kw, **COMMON)
+        cov0 = ctrl.cov_action.copy()
+        ctrl.mean_action = mean.copy()
+        traj = dict(costs=costs.copy(), actions=actions.copy())
+        if use_q:
+            traj["qvals"] = qv.copy()
+        val = ctrl._calc_val({k: v.copy() for k, v in traj.items()})
+        delta = actions - mean[None]
+        w = ctrl._exp_util(costs.copy(), qv.copy() if use_q else None, delta)
+        q_hat = ctrl.calculate_returns(costs + ctrl.beta * ctrl._control_costs(delta), qv.copy() if use_q else None,
+                                       ctrl.gamma, ctrl.td_lam)
+        ctrl._update_distribution({k: v.copy() for k, v in traj.items()})
+        out[name] = dict(mean0=mean, cov0=cov0, costs=costs, actions=actions, qvals=qv if use_q else np.zeros(0),
+                         w=w, q_hat=q_hat, mean1=ctrl.mean_action.copy(), value=val, gamma=kw["gamma"],
+                         beta=kw["beta"], alpha=kw["alpha"], step_size=kw["step_size"], td_lam=kw["td_lam"],
+                         time_based=int(kw.get("time_based_weights", True)))
     # ---- CEM -----------------------------------------------------------------------------------------
     for name, kw in (("cem_diag", dict(cov_type='diagonal', step_size=1.0, gamma=1.0, beta=0.0)),
                      ("cem_full", dict(cov_type='full', step_size=0.6, gamma=0.98, beta=0.3))):
@@ -155,10 +180,13 @@ def main():
 
     # the MPPI/CEM/DMD/RS cases share one synthetic rollout: store it once
     out["common"] = dict(mean0=mean, costs=costs, actions=actions)
+    only = sys.argv[1] if len(sys.argv) > 1 else ""      # optional name prefix: regenerate those files only
     for name, dct in out.items():
         if name != "common" and "actions" in dct and dct["actions"] is actions:
             for k in ("mean0", "costs", "actions"):
                 dct.pop(k)
+        if not name.startswith(only):
+            continue
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: np.asarray(v) for k, v in dct.items()})
     print("wrote", len(out), "golden files to", HERE)
 

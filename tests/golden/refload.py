@@ -48,6 +48,7 @@ def load():
     mods = types.SimpleNamespace()
     mods.control_utils = importlib.import_module("mjmpc.utils.control_utils")
     mods.mppi = importlib.import_module("mjmpc.control.mppi")
+    mods.mppiq = importlib.import_module("mjmpc.control.mppiq")
     mods.cem = importlib.import_module("mjmpc.control.cem")
     mods.dmd = importlib.import_module("mjmpc.control.gaussian_dmd")
     mods.rs = importlib.import_module("mjmpc.control.random_shooting")

@@ -60,6 +60,55 @@ def test_mppi_update(name):
     assert np.all(c.mean_action[-1] == 0.0)
 
 
+@pytest.mark.parametrize("name", ["mppiq_basic", "mppiq_td", "mppiq_qvals", "mppiq_q_notb", "mppiq_lam0"])
+def test_mppiq_update(name):
+    """MPPIQ (mppiq.py:73-160): TD(lambda) returns bit-exact when the per-step cost is (no control cost),
+    1e-10 otherwise; weighted mean and log-sum-exp value 1e-10."""
+    import torch
+    from mjmpc_b200.control import MPPIQ
+    g = load(name)
+    H, K = g["mean0"].shape[0], g["costs"].shape[0]
+    c = MPPIQ(horizon=H, init_cov=0.8, base_action='null', beta=g["beta"], num_particles=K, step_size=g["step_size"],
+              alpha=int(g["alpha"]), gamma=g["gamma"], n_iters=1, td_lam=g["td_lam"],
+              time_based_weights=bool(g["time_based"]), filter_coeffs=[0.25, 0.8, 0.0], seed=3, **_common())
+    c.mean_action = g["mean0"]
+    traj = _traj(g)
+    if g["qvals"].size:
+        traj["qvals"] = torch.from_numpy(g["qvals"]).cuda().t().contiguous().t()
+    assert c._calc_val(traj) == pytest.approx(g["value"], rel=RTOL)
+    q0 = c._last_total.cpu().numpy()[0]                                 # q_hat[:, 0] from the value pass
+    if int(g["alpha"]) == 1:
+        np.testing.assert_array_equal(q0, g["q_hat"][:, 0])
+    else:
+        np.testing.assert_allclose(q0, g["q_hat"][:, 0], rtol=RTOL)
+    np.testing.assert_array_equal(c.mean_action, g["mean0"])            # _calc_val leaves the distribution alone
+    c._update_distribution(traj)
+    if g["time_based"]:
+        q = c._last_total.cpu().numpy().T                               # (K, H)
+        if int(g["alpha"]) == 1:
+            np.testing.assert_array_equal(q, g["q_hat"])
+        else:
+            np.testing.assert_allclose(q, g["q_hat"], rtol=RTOL)
+    np.testing.assert_allclose(c.mean_action, g["mean1"], rtol=RTOL, atol=1e-13)
+
+
+def test_mppiq_numpy_qvals_and_policy_name():
+    """qvals handed over as a row-major numpy array (what a reference-style rollout_fn returns) and the
+    'mppiq' policy name (mpc_policy.py:18-19)."""
+    from mjmpc_b200.policies.mpc_policy import MPCPolicy
+    g = load("mppiq_qvals")
+    H, K = g["mean0"].shape[0], g["costs"].shape[0]
+    p = MPCPolicy("mppiq", dict(horizon=H, init_cov=0.8, base_action='null', beta=g["beta"], num_particles=K,
+                                step_size=g["step_size"], alpha=int(g["alpha"]), gamma=g["gamma"], n_iters=1,
+                                td_lam=g["td_lam"], filter_coeffs=[0.25, 0.8, 0.0], seed=3, **_common()))
+    c = p.controller
+    c.mean_action = g["mean0"]
+    c._update_distribution(dict(costs=g["costs"], actions=g["actions"], qvals=g["qvals"]))
+    np.testing.assert_allclose(c.mean_action, g["mean1"], rtol=RTOL, atol=1e-13)
+    with pytest.raises(ValueError):
+        c._update_distribution(dict(costs=g["costs"], actions=g["actions"], qvals=g["qvals"][:, :-1]))
+
+
 def test_mppi_weights_match_reference():
     import ctypes as C
     import torch

@@ -40,6 +40,31 @@ def test_mppi_golden(name):
     np.testing.assert_array_equal(O.shift_mean(m1, 'null'), g["shifted"])
 
 
+MPPIQ_CASES = ["mppiq_basic", "mppiq_td", "mppiq_qvals", "mppiq_q_notb", "mppiq_lam0"]
+
+
+@pytest.mark.parametrize("name", MPPIQ_CASES)
+def test_mppiq_golden(name):
+    g = load(name)
+    q = g["qvals"] if g["qvals"].size else None
+    m1, w, q_hat = O.mppiq_update(g["mean0"], g["cov0"], g["costs"], g["actions"], q, g["gamma"], g["td_lam"],
+                                  g["beta"], g["alpha"], g["step_size"], bool(g["time_based"]))
+    np.testing.assert_array_equal(q_hat, g["q_hat"])
+    np.testing.assert_array_equal(w, g["w"])
+    np.testing.assert_array_equal(m1, g["mean1"])
+    assert O.mppiq_value(g["mean0"], g["cov0"], g["costs"], g["actions"], q, g["gamma"], g["td_lam"], g["beta"],
+                         g["alpha"]) == g["value"]
+
+
+def test_mppiq_td1_equals_discounted_cost_to_go():
+    """With td_lam = 1 and no Q estimates the TD(lambda) return telescopes to the discounted cost-to-go."""
+    g = load("mppiq_td")
+    H = g["costs"].shape[1]
+    q_hat = O.mppiq_returns(g["costs"], None, g["gamma"], 1.0, H)
+    ctg = O.cost_to_go(g["costs"].copy(), O.gamma_seq(g["gamma"], H))
+    np.testing.assert_allclose(q_hat, ctg, rtol=1e-12)
+
+
 @pytest.mark.parametrize("name", ["cem_diag", "cem_full"])
 def test_cem_golden(name):
     g = load(name)
