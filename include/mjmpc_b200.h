@@ -200,6 +200,29 @@ typedef struct {
 } mjb_mppi_batched_args;
 int mjb_mppi_update_batched(const mjb_mppi_batched_args* a, void* stream);
 
+/* Batched PFMPC update for many small independent particle filters (BASELINE config 5): controller c owns
+ * particles [c*K, (c+1)*K); one thread block per controller does PFMPC._exp_util
+ * (particle_filter_controller.py:104-113), the systematic resampler (:159-174, sequential cumulative sum
+ * in the reference's order; idx[m] = first i with c_i >= r_c + m/K) and mean_action = mean of the
+ * resampled set (:102).  No collective. */
+typedef struct {
+    int n_ctrl, K, H, d;         /* K particles per controller (K <= 4096) */
+    const double* costs; long long costs_sk, costs_st;       /* (n_ctrl*K, H) */
+    const double* samples; long long s_sk, s_st, s_sj;        /* (n_ctrl*K, H, d) current particle sets */
+    const double* gamma_seq;     /* (H,) HOST */
+    double lam;
+    const double* r;             /* (n_ctrl,) device: r_c = random.uniform(0, 1/K) of each controller */
+    double* weights;             /* out (n_ctrl*K,) normalised weights, or NULL */
+    long long* idx;              /* out (n_ctrl*K,) resampled indices, local to the controller, or NULL */
+    double* out; long long o_sk, o_st, o_sj;                  /* out (n_ctrl*K, H, d): out[c,m] = samples[c, idx[c,m]] */
+    double* mean;                /* out (n_ctrl, H, d) */
+} mjb_pf_batched_args;
+int mjb_pf_update_batched(const mjb_pf_batched_args* a, void* stream);
+/* out[k] = x[k] - mean[k / K] for n_ctrl stacked particle sets (PFMPC.generate_rollouts, :87) */
+int mjb_particle_sub_mean_batched(const double* x, long long sk, long long st, long long sj, const double* mean,
+                                  int n_ctrl, int K, int H, int d, double* out, long long out_sk, long long out_st,
+                                  long long out_sj, void* stream);
+
 /* ---- K5 elite selection + moments: CEM._update_distribution (mjmpc/control/cem.py:65-86) and
  * RandomShooting._update_distribution (mjmpc/control/random_shooting.py:52-62).
  * mjb_select_elites: the num_elite smallest keys of ctg0 (K_global,), ties broken by LOWER index

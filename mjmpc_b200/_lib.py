@@ -160,6 +160,18 @@ class MppiBatchedArgs(C.Structure):
     ]
 
 
+class PfBatchedArgs(C.Structure):
+    _fields_ = [
+        ("n_ctrl", C.c_int), ("K", C.c_int), ("H", C.c_int), ("d", C.c_int),
+        ("costs", C.c_void_p), ("costs_sk", c_ll), ("costs_st", c_ll),
+        ("samples", C.c_void_p), ("s_sk", c_ll), ("s_st", c_ll), ("s_sj", c_ll),
+        ("gamma_seq", C.c_void_p), ("lam", C.c_double), ("r", C.c_void_p),
+        ("weights", C.c_void_p), ("idx", C.c_void_p),
+        ("out", C.c_void_p), ("o_sk", c_ll), ("o_st", c_ll), ("o_sj", c_ll),
+        ("mean", C.c_void_p),
+    ]
+
+
 COV_NONE, COV_DIAG, COV_FULL = 0, 1, 2
 RETURNS_CTG, RETURNS_TD_LAMBDA = 0, 1
 BASE_ACTIONS = {"null": 0, "repeat": 1, "random": 2}
@@ -172,6 +184,7 @@ EXPORTS += [
     "mjb_elite_moments2", "mjb_elite_combine", "mjb_blend_best",
     "mjb_resample_indices", "mjb_gather_particles", "mjb_particle_mean", "mjb_particle_sub_mean",
     "mjb_shift_mean", "mjb_shift_mean_batched", "mjb_cov_add_diag", "mjb_pf_shift", "mjb_mppi_update_batched",
+    "mjb_pf_update_batched", "mjb_particle_sub_mean_batched",
 ]
 
 

@@ -34,15 +34,24 @@ class PFMPC(Controller):
         self._cov_shift_d = self._to_device(self.cov_shift)
         self._cov_resample_d = self._to_device(self.cov_resample)
         self.resample_ids = None
+        # batch_size > 1: that many INDEPENDENT particle filters advance in lock step (sweeps, dynamics-
+        # randomisation batches): instance b owns particles [b*K, (b+1)*K), mean row b and state row b; one
+        # thread block per instance does the update (mjb_pf_update_batched), nothing crosses instances
+        self.batch_size = int(batch_size)
+        if self.batch_size > 1 and self.shard.world_size != 1:
+            raise ValueError("independent instances are partitioned by the caller, not sharded (no collective)")
+        self._particle_id_offset = 0       # first global Philox particle index of this controller's block
         self._init_particles()
 
     def _init_particles(self):
         k0, kl = self.shard.local_range(self.num_particles)
-        self._mean = torch.zeros((self.horizon, self.d_action), dtype=torch.float64, device=self.device)
+        B = self.batch_size
+        shape = (B, self.horizon, self.d_action) if B > 1 else (self.horizon, self.d_action)
+        self._mean = torch.zeros(shape, dtype=torch.float64, device=self.device)
         # particle_filter_controller.py:69-71 (base_seed = seed_val)
-        self._samples = generate_noise(self._cov_resample_d, self.filter_coeffs, shape=(kl, self.horizon),
-                                       base_seed=self.seed_val, step=0, k_offset=k0, K_global=self.num_particles,
-                                       device=self.device)
+        self._samples = generate_noise(self._cov_resample_d, self.filter_coeffs, shape=(kl * B, self.horizon),
+                                       base_seed=self.seed_val, step=0, k_offset=k0 + self._particle_id_offset,
+                                       K_global=self._particle_id_offset + self.num_particles * B, device=self.device)
 
     def _graphable(self):
         return False          # the resampler's r comes from Python's random module every step
@@ -57,7 +66,10 @@ class PFMPC(Controller):
 
     @property
     def local_particles(self):
-        return self.shard.local_range(self.num_particles)[1]
+        return self.shard.local_range(self.num_particles)[1] * self.batch_size
+
+    def _first_action(self):
+        return self._mean[:, 0].clone() if self.batch_size > 1 else self._mean[0].clone()
 
     @property
     def mean_action(self):
@@ -65,7 +77,8 @@ class PFMPC(Controller):
 
     @mean_action.setter
     def mean_action(self, value):
-        self._mean = self._to_device(value).reshape(self.horizon, self.d_action).contiguous()
+        shape = (self.batch_size, self.horizon, self.d_action) if self.batch_size > 1 else (self.horizon, self.d_action)
+        self._mean = self._to_device(value).reshape(shape).contiguous()
 
     @property
     def action_samples(self):
@@ -80,13 +93,16 @@ class PFMPC(Controller):
     # ---- particle_filter_controller.py:74-90 -----------------------------------------------------------
     def generate_rollouts(self, state):
         if state is not None:             # None: the backend already holds the (device-resident) state
+            if self.batch_size > 1 and isinstance(state, dict):
+                state = [state] * self.batch_size          # one state for every instance
             self._set_sim_state_fn(copy.deepcopy(state))
         kl, H, d = self.local_particles, self.horizon, self.d_action
         delta = self._buf("delta", (H, d, kl)).permute(2, 0, 1)
         s = self._samples
-        _lib.check(_lib.lib().mjb_particle_sub_mean(
-            _lib.ptr(s), *[_lib.c_ll(x) for x in s.stride()], _lib.ptr(self._mean), C.c_int(kl), C.c_int(H),
-            C.c_int(d), _lib.ptr(delta), *[_lib.c_ll(x) for x in delta.stride()], _lib.stream_ptr()))
+        _lib.check(_lib.lib().mjb_particle_sub_mean_batched(
+            _lib.ptr(s), *[_lib.c_ll(x) for x in s.stride()], _lib.ptr(self._mean), C.c_int(self.batch_size),
+            C.c_int(kl // self.batch_size), C.c_int(H), C.c_int(d), _lib.ptr(delta),
+            *[_lib.c_ll(x) for x in delta.stride()], _lib.stream_ptr()))
         return self._rollout_fn(kl, H, self._mean, delta, mode="open_loop")
 
     def _weights(self, costs):
@@ -124,11 +140,45 @@ class PFMPC(Controller):
     # ---- particle_filter_controller.py:92-102 ----------------------------------------------------------
     def _update_distribution(self, trajectories):
         costs = self._to_device(trajectories["costs"])
-        w = self._weights(costs)
+        if tuple(costs.shape) != (self.local_particles, self.horizon):
+            raise ValueError("rollout_fn returned costs %s for K=%d H=%d" % (tuple(costs.shape), self.local_particles,
+                                                                             self.horizon))
         random.seed(self.seed_val + self.num_steps)
         np.random.seed((self.seed_val + self.num_steps) % (2 ** 32))
+        if self.batch_size > 1:
+            self._batched_update(costs)
+            return
+        w = self._weights(costs)
         self._samples = self._resampling(self._samples, w, low_variance=True)
         self._update_mean()
+
+    def _batched_update(self, costs):
+        """batch_size independent filters: weights, resampling and mean of every instance in one launch.
+        Every instance draws r = random.uniform(0, 1/M) after the same random.seed(seed_val + num_steps)
+        (particle_filter_controller.py:99,163), i.e. the same r."""
+        B, K, H, d = self.batch_size, self.num_particles, self.horizon, self.d_action
+        r = random.uniform(0.0, 1.0 / K * 1.0)
+        a = _lib.PfBatchedArgs()
+        a.n_ctrl, a.K, a.H, a.d = B, K, H, d
+        a.costs = costs.data_ptr(); a.costs_sk, a.costs_st = costs.stride()
+        s = self._samples
+        a.samples = s.data_ptr(); a.s_sk, a.s_st, a.s_sj = s.stride()
+        g = np.ascontiguousarray(self.gamma_seq.reshape(-1))
+        a.gamma_seq = g.ctypes.data
+        a.lam = float(self.lam)
+        rd = self._buf("pf_r", (B,))
+        rd.fill_(r)
+        w = self._buf("weights", (B * K,))
+        idx = self._buf("resample_idx", (B * K,), torch.int64)
+        out = torch.empty((H, d, B * K), dtype=torch.float64, device=self.device).permute(2, 0, 1)
+        a.r, a.weights, a.idx = rd.data_ptr(), w.data_ptr(), idx.data_ptr()
+        a.out = out.data_ptr(); a.o_sk, a.o_st, a.o_sj = out.stride()
+        a.mean = self._mean.data_ptr()
+        _lib.check(_lib.lib().mjb_pf_update_batched(C.byref(a), _lib.stream_ptr()))
+        self._samples = out
+        self.resample_ids = idx.reshape(B, K)
+        self._last_weights = w.reshape(B, K)
+        self._last_r = r
 
     def _update_mean(self):
         """mean_action = np.mean(action_samples, axis=0) over all shards."""
@@ -149,20 +199,24 @@ class PFMPC(Controller):
 
     # ---- particle_filter_controller.py:118-125 ---------------------------------------------------------
     def _get_next_action(self, state, mode='mean'):
-        return self._mean[0].cpu().numpy().copy()
+        return self._first_action().cpu().numpy().copy()
 
     # ---- particle_filter_controller.py:127-150 ---------------------------------------------------------
     def _shift(self):
         if self.base_action not in _lib.BASE_ACTIONS:
             raise NotImplementedError("invalid option for base action during shift")
         k0, kl = self.shard.local_range(self.num_particles)
+        kl *= self.batch_size
         H, d = self.horizon, self.d_action
         delta = generate_noise(self._cov_shift_d, self.filter_coeffs, shape=(kl, H), base_seed=self.seed_val,
-                               step=self.num_steps, stream_id=control_utils.NOISE_STREAM_SHIFT, k_offset=k0,
-                               K_global=self.num_particles, out=self._buf("delta", (H, d, kl)).permute(2, 0, 1),
-                               device=self.device)
+                               step=self.num_steps, stream_id=control_utils.NOISE_STREAM_SHIFT,
+                               k_offset=k0 + self._particle_id_offset,
+                               K_global=self._particle_id_offset + self.num_particles * self.batch_size,
+                               out=self._buf("delta", (H, d, kl)).permute(2, 0, 1), device=self.device)
         rnd = None
         if self.base_action == 'random':
+            if self.batch_size > 1:
+                raise NotImplementedError("base_action 'random' is not available for batched instances")
             # np.random.normal(0, self.cov_resample, d) broadcasts one (d,) row (the matrix diagonal as std)
             rnd = generate_noise(self._cov_resample_d ** 2, [1.0, 0.0, 0.0], shape=(1, 1), base_seed=self.seed_val,
                                  step=self.num_steps, stream_id=control_utils.NOISE_STREAM_BASE,

@@ -660,6 +660,88 @@ __global__ void sub_mean_kernel(const double* __restrict__ x, long long sk, long
     out[k * osk + t * ost + j * osj] = x[k * sk + t * st + j * sj] - mean[tj];
 }
 
+// ------------------------------------------------------------------------------ batched small PFMPC
+// One block per independent PFMPC instance (BASELINE config 5): cost-to-go, softmax weights, the reference's
+// sequential cumulative sum, the systematic-resampling searches, the gather into the new particle set and
+// its mean -- particle_filter_controller.py:92-113,159-174 per instance.  sh[0..K): trajectory costs ->
+// weights -> cumulative sums; ish[0..K): resampled indices.
+__global__ void __launch_bounds__(256) pf_batched_kernel(mjb_pf_batched_args a, GammaSeq G) {
+    extern __shared__ double sh[];
+    __shared__ double red[256];
+    const int c = blockIdx.x, K = a.K, H = a.H, d = a.d;
+    int* ish = (int*)(sh + K);
+    const long long kbase = (long long)c * K;
+    double mn = INFINITY;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const long long gk = kbase + k;
+        double S = 0.0, ctg = 0.0;
+        for (int t = H - 1; t >= 0; t--) {
+            const double cst = a.costs[gk * a.costs_sk + t * a.costs_st];
+            if (G.raw) ctg = cst;
+            else { S = __dadd_rn(S, __dmul_rn(G.g[t], cst)); ctg = __ddiv_rn(S, G.g[t]); }
+        }
+        sh[k] = ctg;
+        mn = fmin(mn, ctg);
+    }
+    red[threadIdx.x] = mn;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] = fmin(red[threadIdx.x], red[threadIdx.x + s]); __syncthreads(); }
+    const double ninv = -1.0 / a.lam, xmax = ninv * red[0];
+    __syncthreads();
+    double ws = 0.0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) { const double w = exp(ninv * sh[k] - xmax); sh[k] = w; ws += w; }
+    red[threadIdx.x] = ws;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s]; __syncthreads(); }
+    const double Ssum = red[0];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const double w = sh[k] / Ssum;
+        sh[k] = w;
+        if (a.weights) a.weights[kbase + k] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                       // reference order: c += w[i]
+        double cs = 0.0;
+        for (int i = 0; i < K; i++) { cs = __dadd_rn(cs, sh[i]); sh[i] = cs; }
+    }
+    __syncthreads();
+    const double r = a.r[c];
+    for (int m = threadIdx.x; m < K; m += blockDim.x) {
+        const double u = __dadd_rn(r, __ddiv_rn((double)m, (double)K));    // r + m*1.0/M*1.0
+        int res;
+        if (!(0.0 < u)) res = K - 1;                                       // loop never runs: act_seq[-1]
+        else {
+            int lo = 0, hi = K;                                            // first i with cs[i] >= u
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (sh[mid] >= u) hi = mid; else lo = mid + 1; }
+            res = lo < K ? lo : K - 1;
+        }
+        ish[m] = res;
+        if (a.idx) a.idx[kbase + m] = res;
+    }
+    __syncthreads();
+    // gather + mean of the resampled set: one (t,j) column per thread, particles in index order
+    for (int i = threadIdx.x; i < H * d; i += blockDim.x) {
+        const int t = i / d, j = i % d;
+        double s = 0.0;
+        for (int m = 0; m < K; m++) {
+            const double v = a.samples[(kbase + ish[m]) * a.s_sk + t * a.s_st + j * a.s_sj];
+            a.out[(kbase + m) * a.o_sk + t * a.o_st + j * a.o_sj] = v;
+            s += v;
+        }
+        a.mean[(long long)c * H * d + i] = s / (double)K;
+    }
+}
+
+__global__ void sub_mean_batched_kernel(const double* __restrict__ x, long long sk, long long st, long long sj,
+                                        const double* __restrict__ mean, int K, int ppc, int H, int d,
+                                        double* __restrict__ out, long long osk, long long ost, long long osj) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tj = blockIdx.y;
+    if (k >= K) return;
+    const int t = tj / d, j = tj % d;
+    out[k * osk + t * ost + j * osj] = x[k * sk + t * st + j * sj] - mean[(k / ppc) * (long long)H * d + tj];
+}
+
 // ------------------------------------------------------------------------------ shifts
 __global__ void shift_mean_kernel(double* mean, int H, int d, int base, const double* rnd) {
     // single block: read everything, sync, write (rows overlap)
@@ -969,6 +1051,32 @@ extern "C" int mjb_mppi_update_batched(const mjb_mppi_batched_args* a, void* str
         MJB_CASE(1) MJB_CASE(2) MJB_CASE(3) MJB_CASE(4) MJB_CASE(5) MJB_CASE(6) MJB_CASE(7) MJB_CASE(8)
 #undef MJB_CASE
     }
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_pf_update_batched(const mjb_pf_batched_args* a, void* stream) {
+    MJB_REQUIRE(a && a->costs && a->samples && a->gamma_seq && a->r && a->out && a->mean, "mjb_pf_update_batched: null pointer");
+    MJB_REQUIRE(a->n_ctrl >= 1 && a->K >= 1 && a->K <= 4096 && a->H >= 1, "mjb_pf_update_batched: bad shape (K per controller must be <= 4096)");
+    MJB_REQUIRE(a->d >= 1 && a->d <= MJB_MAXD, "d_action=%d not in 1..%d", a->d, MJB_MAXD);
+    MJB_REQUIRE(a->lam > 0.0, "lam must be positive");
+    MJB_REQUIRE(a->samples != a->out, "mjb_pf_update_batched: in-place resampling is not supported");
+    GammaSeq G;
+    int rc = load_gamma(G, a->gamma_seq, a->H);
+    if (rc) return rc;
+    const size_t smem = (sizeof(double) + sizeof(int)) * (size_t)a->K;
+    pf_batched_kernel<<<a->n_ctrl, 256, smem, (cudaStream_t)stream>>>(*a, G);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_particle_sub_mean_batched(const double* x, long long sk, long long st, long long sj, const double* mean,
+                                             int n_ctrl, int K, int H, int d, double* out, long long osk, long long ost,
+                                             long long osj, void* stream) {
+    MJB_REQUIRE(x && mean && out && n_ctrl >= 1 && K >= 1 && H >= 1 && d >= 1, "mjb_particle_sub_mean_batched: bad argument");
+    const long long Kt = (long long)n_ctrl * K;
+    sub_mean_batched_kernel<<<dim3((unsigned)((Kt + 255) / 256), H * d), 256, 0, (cudaStream_t)stream>>>(
+        x, sk, st, sj, mean, (int)Kt, K, H, d, out, osk, ost, osj);
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;
 }

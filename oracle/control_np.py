@@ -200,8 +200,14 @@ def pf_resample_indices(weights, seed):
     random.seed(seed_val + num_steps) (:99)."""
     random.seed(seed)
     M = weights.shape[0]
-    idx = np.zeros(M, np.int64)
     r = random.uniform(0.0, 1.0 / M * 1.0)
+    return pf_resample_with_r(weights, r), r
+
+
+def pf_resample_with_r(weights, r):
+    """The loop of particle_filter_controller.py:164-170 for a given offset r."""
+    M = weights.shape[0]
+    idx = np.zeros(M, np.int64)
     c = 0.0
     i = 0
     for m in range(M):
@@ -210,7 +216,7 @@ def pf_resample_indices(weights, seed):
             c += weights[i]
             i += 1
         idx[m] = i - 1
-    return idx, r
+    return idx
 
 
 def shift_mean(mean, base_action, init_cov=None, rng_normal=None):

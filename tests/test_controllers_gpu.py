@@ -252,6 +252,95 @@ def test_resample_skewed_weights():
     np.testing.assert_array_equal(cs.cpu().numpy(), np.cumsum(g["w"]))           # sequential order
 
 
+@pytest.mark.parametrize("K,gamma", [(32, 1.0), (257, 0.97), (4096, 0.9)])
+def test_pf_update_batched_kernel(K, gamma):
+    """mjb_pf_update_batched per instance against the numpy restatement: weights 1e-10, resampling indices
+    bit-exact for the kernel's own weights, gathered set and its mean."""
+    import ctypes as C
+    import torch
+    from mjmpc_b200 import _lib
+    from oracle import control_np as O
+    B, H, d, lam = 5, 9, 7, 0.4
+    rng = np.random.RandomState(K)
+    costs = np.abs(rng.normal(2, 1, (B * K, H)))
+    samples = rng.normal(0, 1, (B * K, H, d))
+    r = rng.uniform(0, 1.0 / K, B)
+    r[1] = 0.0                                               # the loop never runs for m = 0: act_seq[-1]
+    gs = O.gamma_seq(gamma, H)
+    ct = torch.from_numpy(costs).cuda().t().contiguous().t()
+    st = torch.from_numpy(samples).cuda().permute(1, 2, 0).contiguous().permute(2, 0, 1)
+    out = torch.empty((H, d, B * K), dtype=torch.float64, device="cuda").permute(2, 0, 1)
+    w = torch.empty(B * K, dtype=torch.float64, device="cuda")
+    idx = torch.empty(B * K, dtype=torch.int64, device="cuda")
+    mean = torch.empty((B, H, d), dtype=torch.float64, device="cuda")
+    rd = torch.from_numpy(r).cuda()
+    a = _lib.PfBatchedArgs()
+    a.n_ctrl, a.K, a.H, a.d = B, K, H, d
+    a.costs = ct.data_ptr(); a.costs_sk, a.costs_st = ct.stride()
+    a.samples = st.data_ptr(); a.s_sk, a.s_st, a.s_sj = st.stride()
+    g = np.ascontiguousarray(gs.reshape(-1))
+    a.gamma_seq, a.lam, a.r = g.ctypes.data, lam, rd.data_ptr()
+    a.weights, a.idx = w.data_ptr(), idx.data_ptr()
+    a.out = out.data_ptr(); a.o_sk, a.o_st, a.o_sj = out.stride()
+    a.mean = mean.data_ptr()
+    _lib.check(_lib.lib().mjb_pf_update_batched(C.byref(a), _lib.stream_ptr()))
+    wh, ih, oh, mh = w.cpu().numpy().reshape(B, K), idx.cpu().numpy().reshape(B, K), out.cpu().numpy(), mean.cpu().numpy()
+    for b in range(B):
+        sl = slice(b * K, (b + 1) * K)
+        np.testing.assert_allclose(wh[b], O.pf_weights(costs[sl], gs, lam), rtol=RTOL, atol=1e-300)
+        np.testing.assert_array_equal(ih[b], O.pf_resample_with_r(wh[b], r[b]))
+        np.testing.assert_array_equal(oh[sl], samples[sl][ih[b]])
+        np.testing.assert_allclose(mh[b], samples[sl][ih[b]].mean(0), rtol=RTOL, atol=1e-14)
+    assert ih[1][0] == K - 1
+    a.K = 5000
+    with pytest.raises(ValueError):
+        _lib.check(_lib.lib().mjb_pf_update_batched(C.byref(a), _lib.stream_ptr()))
+
+
+def test_batched_pfmpc_instances_match_single_controllers(compiled_model):
+    """BASELINE config 5, PFMPC half: batch_size independent particle filters (shipped sizes K=32, H=16) with
+    their own start states and randomised models in one launch -- against separate controllers."""
+    from conftest import synthetic_state
+    from mjmpc_b200.control import PFMPC
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    B, K, H = 6, 32, 16
+    rand = dict(body_mass={"r_forearm_link": [0.3, 0.0]}, dof_damping={"r_elbow_flex_joint": [0.2, 0.1]})
+    kw = dict(horizon=H, cov_shift=0.05, cov_resample=0.8, base_action='null', lam=0.5, num_particles=K, gamma=0.98,
+              n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=31, **_common())
+    states = [[synthetic_state(compiled_model, 100 * s + b) for b in range(B)] for s in range(3)]
+    env = GpuReacherVecEnv(compiled_model, n_workers=B)
+    env.randomize_dynamics(rand, base_seed=3)
+    cb = PFMPC(batch_size=B, **kw)
+    cb.set_sim_state_fn = env.set_env_state
+    cb.rollout_fn = env.rollout_fn
+    assert cb.action_samples.shape == (B * K, H, 7) and cb.mean_action.shape == (B, H, 7)
+    acts_b, ids_b = [], []
+    for st in states:
+        acts_b.append(cb.optimize(st)[0])
+        ids_b.append(cb.resample_ids.cpu().numpy().copy())
+    acts_b = np.stack(acts_b)                                                   # (steps, B, 7)
+    assert acts_b.shape == (3, B, 7)
+    for b in (0, 3, B - 1):
+        single_env = GpuReacherVecEnv(env._worker_models[b], n_workers=1)
+        c = PFMPC(batch_size=1, **kw)
+        c._particle_id_offset = b * K                                           # same Philox block as instance b
+        c.reset()
+        c.set_sim_state_fn = single_env.set_env_state
+        c.rollout_fn = single_env.rollout_fn
+        np.testing.assert_array_equal(c.action_samples, PFMPC(batch_size=B, **kw).action_samples[b * K:(b + 1) * K])
+        for s, st in enumerate(states):
+            act = c.optimize(st[b])[0]
+            np.testing.assert_array_equal(c.resample_ids.cpu().numpy(), ids_b[s][b])
+            np.testing.assert_allclose(acts_b[s, b], act, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(cb.action_samples[b * K:(b + 1) * K], c.action_samples, rtol=1e-9, atol=1e-12)
+        single_env.close()
+    assert np.abs(acts_b[:, 0] - acts_b[:, 1]).max() > 1e-3                     # instances really differ
+    with pytest.raises(NotImplementedError):
+        cb.base_action = 'random'
+        cb._shift()
+    env.close()
+
+
 def test_pfmpc_shift():
     from mjmpc_b200.control import PFMPC
     H, d, K = 8, 7, 64

@@ -273,7 +273,8 @@ def test_ctypes_structs_match_header_layout():
     pairs = [("mjb_rollout_args", _lib.RolloutArgs, "noise_zero_last"), ("mjb_pendulum_args", _lib.PendulumArgs, "states_out"),
              ("mjb_noise_args", _lib.NoiseArgs, "out_sj"), ("mjb_softmax_args", _lib.SoftmaxArgs, "q_st"),
              ("mjb_combine_args", _lib.CombineArgs, "stats"), ("mjb_elite_args", _lib.EliteArgs, "partial"),
-             ("mjb_elite_combine_args", _lib.EliteCombineArgs, "cov"), ("mjb_mppi_batched_args", _lib.MppiBatchedArgs, "value")]
+             ("mjb_elite_combine_args", _lib.EliteCombineArgs, "cov"), ("mjb_mppi_batched_args", _lib.MppiBatchedArgs, "value"),
+             ("mjb_pf_batched_args", _lib.PfBatchedArgs, "mean")]
     body = "".join('printf("%%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));' % (c, c, last) for c, _, last in pairs)
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "include/mjmpc_b200.h"\nint main(){%s return 0;}' % body
     exe = os.path.join(ROOT, "tests", "hostcheck", "layout_probe")

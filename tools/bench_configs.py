@@ -4,7 +4,7 @@ line per config, device-timed MPC steps through the public controller API on one
   configs[0]  MPPI reacher_7dof, shipped sizes K=32 H=16
   configs[1]  CEM diag-cov, SimplePendulum, K=4096 H=64
   configs[3]  DMD-MPC full covariance, 7-DOF arm, K=65536 H=32
-  configs[4]  1024 independent MPPI instances (K=32, H=16) with per-instance randomised dynamics, one launch
+  configs[4]  1024 independent MPPI / PFMPC instances (K=32, H=16) with per-instance randomised dynamics, one launch
 """
 import json
 import os
@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from bench import synthetic_states
-from mjmpc_b200.control import CEM, DMDMPC, MPPI
+from mjmpc_b200.control import CEM, DMDMPC, MPPI, PFMPC
 from mjmpc_b200.envs.gpu_pendulum import GpuPendulumVecEnv
 from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
 from mjmpc_b200.envs.model import compile_model, reacher7dof_spec
@@ -77,4 +77,9 @@ c.set_sim_state_fn, c.rollout_fn = env.set_env_state, env.rollout_fn
 bstates = [synthetic_states(compiled, B, seed=10 + s) for s in range(2)]
 emit("configs[4] 1024 independent MPPI instances, randomised dynamics, one GPU", timed(c, bstates, steps=100), 32, 16, n_ctrl=B,
      note="mpc_hz = controller-steps per second summed over the 1024 instances; host->device copy of 1024 states included")
+c = PFMPC(horizon=16, cov_shift=0.05, cov_resample=1.0, base_action='null', lam=0.2, num_particles=32, gamma=1.0, n_iters=1,
+          filter_coeffs=[0.25, 0.8, 0.0], seed=123, batch_size=B, **R7)
+c.set_sim_state_fn, c.rollout_fn = env.set_env_state, env.rollout_fn
+emit("configs[4] 1024 independent PFMPC instances, randomised dynamics, one GPU", timed(c, bstates, steps=100, graph=False), 32, 16,
+     n_ctrl=B, note="eager launches (the resampler's r comes from Python's random module every step)")
 env.close()
