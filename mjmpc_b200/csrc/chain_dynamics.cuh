@@ -45,9 +45,13 @@ namespace mjb {
 #if defined(MJB_HOST_STATS)
 // host test harness only: solver statistics [substeps, substeps with rows, factor/solve passes, line searches]
 static long long g_stats[4] = {0, 0, 0, 0};
+static int* g_trips = nullptr;      // optional: factor/solve passes of every substep, in call order
+static long long g_ntrips = 0;
 #define MJB_STAT(i) (g_stats[i]++)
+#define MJB_STAT_TRIPS(n) do { if (g_trips) g_trips[g_ntrips++] = (n); } while (0)
 #else
 #define MJB_STAT(i) ((void)0)
+#define MJB_STAT_TRIPS(n) ((void)0)
 #endif
 
 struct V3 { double x, y, z; };
@@ -60,6 +64,15 @@ MJB_HD V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b
 // min / max without the NaN-propagation fix-ups of fmin/fmax (9 instructions each in FP64 on sm_100a)
 MJB_HD double dmin(double a, double b) { return a < b ? a : b; }
 MJB_HD double dmax(double a, double b) { return a > b ? a : b; }
+// v with its sign bit XOR-ed with `mask` (0 or 0x80000000): multiplication by +-1 as one integer
+// instruction on the high word
+MJB_HD double sflip(double v, unsigned mask) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(v) ^ (int)mask, __double2loint(v));
+#else
+    return mask ? -v : v;
+#endif
+}
 template <int AX> MJB_HD double comp(V3 v) { return AX == 0 ? v.x : (AX == 1 ? v.y : v.z); }
 
 // a x b where b's components outside MASK are structurally zero (bit k = component k)
@@ -474,16 +487,21 @@ MJB_NOINLINE void contact_row(P prm, double* io, double cx, double cy, double cz
 }
 
 // Constraint rows of one particle.  Limit row j acts on dof j alone with Jacobian entry sg = +1 below
-// the range, -1 above it (at most one side can be violated).  Stored in joint coordinates:
-//   D[j]  = 1/R_j, 0 when the row is absent
-//   b[j]  = sg * aref_j: the row is active at acceleration a iff sg (a_j - b_j) < 0, it then adds
-//           D_j to H_jj, D_j b_j to the right-hand side, and exerts the joint force D_j (b_j - a_j).
+// the range, -1 above it (at most one side can be violated).  Stored in the row's own sign convention
+// so that one comparison decides activity:
+//   D[j]   = 1/R_j, 0 when the row is absent
+//   bs[j]  = aref_j (= sg * b_j with b_j the joint-space reference acceleration), -DBL_MAX when the row
+//            is absent: the row is active at acceleration a iff sg a_j < bs_j; it then adds D_j to H_jj,
+//            sg D_j bs_j to the right-hand side, and exerts the joint force sg D_j (bs_j - sg a_j).
+//   below  = bit j: joint j is below its range (sg = +1); sgn(j) is the sign mask of sg
 // The contact row's Jacobian lives in the scratch (SC_JC) and is only touched when Dc != 0.
 struct Rows {
-    double D[7], b[7];
-    unsigned below;            // bit j: joint j is below its range (sg = +1)
+    double D[7], bs[7];
+    unsigned below;
     double Dc, arefc;
+    MJB_HD unsigned sgn(int j) const { return (~below << (31 - j)) & 0x80000000u; }
 };
+#define MJB_ROW_ABSENT (-1.7976931348623157e308)
 
 // generic-impedance fallback of make_rows (non-default solimp shapes): out of line
 template <class P>
@@ -513,7 +531,7 @@ MJB_HD bool make_rows(const P& prm, S& sc, const double (&q)[7], const double (&
     const double d0 = prm[CS_IMP_D0], dw = prm[CS_IMP_DW], width = prm[CS_IMP_WIDTH];
     R.below = 0;
     if (prm[CS_IMP_POWER] == 2.0 && d0 != dw && width > 1e-15) {
-        // default impedance shape (power 2): branch-free over the 7 joints, every lane does the same work
+        // default impedance shape (power 2)
         const int limited = (int)prm[CS_LIMITED_MASK];
         const double mid = prm[CS_IMP_MID];
         const double K = prm[CS_SOLK], B = prm[CS_SOLB];
@@ -524,18 +542,31 @@ MJB_HD bool make_rows(const P& prm, S& sc, const double (&q)[7], const double (&
             const bool below = dlo < 0.0;
             const double dist = dmin(dlo, dhi);                    // side * (range - q): < 0 when violated
             const bool viol = dist < 0.0 && ((limited >> j) & 1);
-            const double x = dmin(dist * niw, 1.0);                // penetration / width, saturating (imp = dw at 1)
-            const double xm = 1.0 - x;
-            const double y = x <= mid ? (x * x) * imid : fma(-(xm * xm), i1mid, 1.0);
-            const double imp = fma(y, dd, d0);
-            // D = 1 / max(1e-15, (1-imp)*invweight/imp)
-            const double den = dmax((1.0 - imp) * prm[CH_INVW0 + j], 1e-15 * imp);
-            const double kd = K * imp * dist;
-            const double dj = imp * rcp_pos(den);
-            R.D[j] = viol ? dj : 0.0;
-            R.b[j] = -B * qd[j] - (below ? kd : -kd);              // sg * (-B sg qd - K imp dist)
             R.below |= below ? (1u << j) : 0u;
             any |= viol;
+#ifdef MJB_ROWS_BRANCH
+            // variant: the row's impedance / regulariser / reference acceleration only where a limit is
+            // violated (a warp skips the block for joints none of its particles violates)
+            R.D[j] = 0.0; R.bs[j] = MJB_ROW_ABSENT;
+            if (viol)
+#endif
+            {
+                const double x = dmin(dist * niw, 1.0);            // penetration / width, saturating (imp = dw at 1)
+                const double xm = 1.0 - x;
+                const double y = x <= mid ? (x * x) * imid : fma(-(xm * xm), i1mid, 1.0);
+                const double imp = fma(y, dd, d0);
+                // D = 1 / max(1e-15, (1-imp)*invweight/imp)
+                const double den = dmax((1.0 - imp) * prm[CH_INVW0 + j], 1e-15 * imp);
+                const double kd = K * imp * dist;
+                const double dj = imp * rcp_pos(den);
+                const double bsj = -B * sflip(qd[j], below ? 0u : 0x80000000u) - kd;     // aref = -B sg qd - K imp dist
+#ifdef MJB_ROWS_BRANCH
+                R.D[j] = dj; R.bs[j] = bsj;
+#else
+                R.D[j] = viol ? dj : 0.0;                          // branch-free: every lane does the same work
+                R.bs[j] = viol ? bsj : MJB_ROW_ABSENT;
+#endif
+            }
         }
     } else {
         double qv[14], Db[14];
@@ -544,8 +575,9 @@ MJB_HD bool make_rows(const P& prm, S& sc, const double (&q)[7], const double (&
         for (int j = 0; j < 7; j++) { qv[j] = q[j]; qv[7 + j] = qd[j]; }
         limit_rows_generic(prm, qv, Db, ba);
 #pragma unroll
-        for (int j = 0; j < 7; j++) { R.D[j] = Db[j]; R.b[j] = Db[7 + j]; }
         R.below = ba[0]; any = ba[1] != 0;
+#pragma unroll
+        for (int j = 0; j < 7; j++) { R.D[j] = Db[j]; R.bs[j] = Db[j] > 0.0 ? sflip(Db[7 + j], R.sgn(j)) : MJB_ROW_ABSENT; }
     }
     R.Dc = 0.0; R.arefc = 0.0;
     const double radius = prm[CS_CON_RADIUS];
@@ -730,11 +762,11 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
         phase = 0;
 #pragma unroll
         for (int j = 0; j < 7; j++) {
-            const double bm = R.b[j] * sc.ld(sc_m(j, j));
-            const bool on = (R.D[j] > 0.0) & (((R.below >> j) & 1u) ? f[j] < bm : f[j] > bm);
+            const double bm = R.bs[j] * sc.ld(sc_m(j, j));
+            const bool on = sflip(f[j], R.sgn(j)) < bm;            // absent rows (bs = -DBL_MAX) are never on
             act |= on ? (1u << j) : 0u;
             dadd[j] = on ? R.D[j] : 0.0;
-            radd[j] = dadd[j] * R.b[j];
+            radd[j] = sflip(dadd[j] * R.bs[j], R.sgn(j));
         }
     }
     // Contact row (rare): its rank-one term is not diagonal, so the matrix with the term added is kept
@@ -758,6 +790,9 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
         }
     }
     MJB_STAT(0); if (any) MJB_STAT(1);
+#if defined(MJB_HOST_STATS)
+    int ntrip = 0;
+#endif
     {
         // Every trip is one factor/solve; a Newton trip then checks its active set and prepares the next
         // trip's increments.  The loop condition is laundered (MJB_OPAQUE) so the compiler cannot thread the
@@ -770,6 +805,9 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
             double H[7][7], dinv[7];
             MJB_OPAQUE(phase);
             MJB_STAT(2);
+#if defined(MJB_HOST_STATS)
+            ntrip++;
+#endif
 #pragma unroll
             for (int i = 0; i < 7; i++) {
 #pragma unroll
@@ -783,10 +821,7 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
             if (phase == 0) {
                 unsigned actx = 0;
 #pragma unroll
-                for (int j = 0; j < 7; j++) {
-                    const bool on = (R.D[j] > 0.0) & (((R.below >> j) & 1u) ? x[j] < R.b[j] : x[j] > R.b[j]);
-                    actx |= on ? (1u << j) : 0u;
-                }
+                for (int j = 0; j < 7; j++) actx |= (sflip(x[j], R.sgn(j)) < R.bs[j]) ? (1u << j) : 0u;
                 bool con_x = false;
                 double jcx = 0.0;
                 if (R.Dc > 0.0) {
@@ -800,9 +835,9 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
                 const bool ok = (actx == act) & (con_x == con_on);
 #pragma unroll
                 for (int j = 0; j < 7; j++) {
-                    const bool on = (actx >> j) & 1u;
-                    dadd[j] = ok ? prm[CH_HDAMP + j] : (on ? R.D[j] : 0.0);
-                    radd[j] = on ? R.D[j] * (R.b[j] - (ok ? x[j] : 0.0)) : 0.0;
+                    const double De = ((actx >> j) & 1u) ? R.D[j] : 0.0;
+                    dadd[j] = ok ? prm[CH_HDAMP + j] : De;
+                    radd[j] = sflip(De * (R.bs[j] - (ok ? sflip(x[j], R.sgn(j)) : 0.0)), R.sgn(j));
                 }
                 if (con_x) {
                     // contact force -Dc (Jc.a - arefc) Jc at the optimum, or the row's right-hand side Dc arefc Jc
@@ -828,7 +863,8 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
 #pragma unroll
             for (int k = 0; k <= j; k++) w[j * 7 + k] = sc.ld(sc_m(j, k));
             w[49 + j] = f[j]; w[56 + j] = prm[CH_HDAMP + j];
-            w[63 + j] = R.D[j]; w[70 + j] = R.b[j]; w[77 + j] = ((R.below >> j) & 1u) ? 1.0 : -1.0;
+            w[63 + j] = R.D[j]; w[70 + j] = R.D[j] > 0.0 ? sflip(R.bs[j], R.sgn(j)) : 0.0;
+            w[77 + j] = ((R.below >> j) & 1u) ? 1.0 : -1.0;
             w[84 + j] = R.Dc > 0.0 ? sc.ld(SC_JC + j) : 0.0;
         }
         w[91] = R.Dc; w[92] = R.arefc;
@@ -836,6 +872,7 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
 #pragma unroll
         for (int j = 0; j < 7; j++) x[j] = w[49 + j];
     }
+    MJB_STAT_TRIPS(ntrip);
     const double h = prm[CS_TIMESTEP];
 #pragma unroll
     for (int j = 0; j < 7; j++) { qd[j] += h * x[j]; q[j] += h * qd[j]; }

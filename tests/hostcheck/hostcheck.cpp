@@ -55,6 +55,8 @@ extern "C" void hostcheck_mass_bias(const double* P167, const double* q, const d
 
 extern "C" void hostcheck_sincos(double x, double* s, double* c) { mjb::sincos_joint(x, *s, *c); }
 
+// record the factor/solve passes of every following substep into buf (call order: particle, step, substep)
+extern "C" void hostcheck_record_trips(int* buf) { mjb::g_trips = buf; mjb::g_ntrips = 0; }
 extern "C" void hostcheck_stats(long long* out, int reset) {
     for (int i = 0; i < 4; i++) { out[i] = mjb::g_stats[i]; if (reset) mjb::g_stats[i] = 0; }
 }
