@@ -288,7 +288,7 @@ def test_pf_update_batched_kernel(K, gamma):
     for b in range(B):
         sl = slice(b * K, (b + 1) * K)
         np.testing.assert_allclose(wh[b], O.pf_weights(costs[sl], gs, lam), rtol=RTOL, atol=1e-300)
-        np.testing.assert_array_equal(ih[b], O.pf_resample_with_r(wh[b], r[b]))
+        np.testing.assert_array_equal(ih[b], O.pf_resample_with_r(wh[b], r[b]) % K)   # -1 (r = 0) is act_seq[-1]
         np.testing.assert_array_equal(oh[sl], samples[sl][ih[b]])
         np.testing.assert_allclose(mh[b], samples[sl][ih[b]].mean(0), rtol=RTOL, atol=1e-14)
     assert ih[1][0] == K - 1
