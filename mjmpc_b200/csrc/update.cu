@@ -1065,6 +1065,9 @@ extern "C" int mjb_pf_update_batched(const mjb_pf_batched_args* a, void* stream)
     int rc = load_gamma(G, a->gamma_seq, a->H);
     if (rc) return rc;
     const size_t smem = (sizeof(double) + sizeof(int)) * (size_t)a->K;
+    // K = 4096 needs 48 KB of dynamic shared memory on top of the kernel's static 2 KB: above the default limit
+    if (smem > 40 * 1024)
+        MJB_CUDA(cudaFuncSetAttribute(pf_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pf_batched_kernel<<<a->n_ctrl, 256, smem, (cudaStream_t)stream>>>(*a, G);
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;
