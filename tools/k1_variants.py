@@ -18,9 +18,12 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "gpurun_variants")
 VARIANTS = {
     "default": [],
-    "rows_branch": ["MJB_ROWS_BRANCH"],
-    "no_prefetch": ["MJB_NO_PREFETCH"],
-    "occ5": ["MJB_OCC=5", "MJB_NO_PREFETCH"],
+    "sincos": ["MJB_SINCOS_INCR"],
+    "back": ["MJB_BACK_ORDER"],
+    "pivot": ["MJB_PIVOT_SQ"],
+    "fwd": ["MJB_LDL_FUSED_RHS"],
+    "sincos_back": ["MJB_SINCOS_INCR", "MJB_BACK_ORDER"],
+    "all4": ["MJB_SINCOS_INCR", "MJB_BACK_ORDER", "MJB_PIVOT_SQ", "MJB_LDL_FUSED_RHS"],
 }
 
 
