@@ -161,32 +161,6 @@ MJB_HD void sincos_joint(double x, double& s, double& c) {
     c = ((k + 1) & 2) ? -b : b;
 }
 
-// (s, c) = (sin q, cos q) advanced to q + d for a small step d (|d| <= 0.25 rad: one Euler substep of a joint
-// slower than 25 rad/s): angle addition with Taylor polynomials of sin d and cos d - 1 (truncation error
-// d^13/13! and d^14/14!, below 1e-17), written as corrections to s and c so each update rounds at the ulp of the
-// result.  15 FP64 operations instead of the 42 (+ range-reduction selects) of a fresh sincos; the caller
-// re-evaluates sincos_joint when a step is larger than the bound.
-#define MJB_SINCOS_STEP_MAX2 0.0625
-MJB_HD void sincos_advance(double& s, double& c, double d, double z) {
-    const double ps = fma(z, fma(z, fma(z, fma(z, -2.50521083854417187751e-08, 2.75573192239858906526e-06),
-                                       -1.98412698412698412698e-04), 8.33333333333333333333e-03), -1.66666666666666666667e-01);
-    const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, 2.08767569878680989792e-09, -2.75573192239858906526e-07),
-                                              2.48015873015873015873e-05), -1.38888888888888888889e-03),
-                                 4.16666666666666666667e-02), -0.5);
-    const double sd = fma(z * d, ps, d);          // sin d
-    const double cm = z * pc;                     // cos d - 1
-    const double s1 = fma(c, sd, fma(s, cm, s));
-    const double c1 = fma(-s, sd, fma(c, cm, c));
-    s = s1; c = c1;
-}
-
-// fresh sin/cos of all joints (io[0..7) q in, io[7..14) sin, io[14..21) cos out): the rare path behind
-// sincos_advance, out of line and rolled so it costs the hot loop no instruction-cache space
-MJB_NOINLINE void sincos_refresh(double* io) {
-#pragma unroll 1
-    for (int j = 0; j < 7; j++) sincos_joint(io[j], io[7 + j], io[14 + j]);
-}
-
 // Structure of the reference's arm (sawyer.xml:15-59): axes z,y,x,y,x,y,x; after merging the two
 // welded bodies, link offsets are (x,0,0) or 0 and COMs are on the link x axis (or at the origin),
 // so inertias about the link origin stay diagonal for links 1..6.  Bit k of a mask = component k.
@@ -411,68 +385,38 @@ MJB_HD double rcp_pos(double x) {
 // and the trailing block updated with independent FMAs, so the dependency chain from one pivot to the
 // next is reciprocal -> scale -> one FMA (the left-looking form chains up to six FMAs in front of
 // every reciprocal).  With two warps per scheduler this chain length is what the solve costs.
-// One step of the right-looking elimination, shared by ldl7 / ldl7_fwd.
-#ifdef MJB_PIVOT_SQ
-// The next pivot comes straight from the reciprocal: A[j+1][j+1] - c^2 inv, with c^2 formed while the
-// reciprocal is in flight -- one FMA instead of scale-then-FMA on the pivot-to-pivot chain.
-#define MJB_LDL_COLUMN(j)                                                                        \
-    const double inv = rcp_pos(A[j][j]);                                                         \
-    dinv[j] = inv;                                                                               \
-    double c[7];                                                                                 \
-    _Pragma("unroll") for (int i = j + 1; i < 7; i++) { c[i] = A[i][j]; A[i][j] = c[i] * inv; }  \
-    if (j < 6) A[j < 6 ? j + 1 : 6][j < 6 ? j + 1 : 6] = fma(-(c[j < 6 ? j + 1 : 6] * c[j < 6 ? j + 1 : 6]), inv, A[j < 6 ? j + 1 : 6][j < 6 ? j + 1 : 6]); \
-    _Pragma("unroll") for (int i = j + 2; i < 7; i++) {                                          \
-        _Pragma("unroll") for (int k = j + 1; k <= i; k++) A[i][k] = fma(-A[i][j], c[k], A[i][k]); \
-    }
-#else
-#define MJB_LDL_COLUMN(j)                                                                        \
-    const double inv = rcp_pos(A[j][j]);                                                         \
-    dinv[j] = inv;                                                                               \
-    double c[7];                                                                                 \
-    _Pragma("unroll") for (int i = j + 1; i < 7; i++) { c[i] = A[i][j]; A[i][j] = c[i] * inv; }  \
-    _Pragma("unroll") for (int i = j + 1; i < 7; i++) {                                          \
-        _Pragma("unroll") for (int k = j + 1; k <= i; k++) A[i][k] = fma(-A[i][j], c[k], A[i][k]); \
-    }
-#endif
 MJB_HD void ldl7(double (&A)[7][7], double (&dinv)[7]) {
 #pragma unroll
-    for (int j = 0; j < 7; j++) { MJB_LDL_COLUMN(j) }
-}
-// The same factorisation with the forward substitution L y = b carried along as one more row of the
-// trailing update (b[i] -= L[i][j] b[j] as soon as column j is known: the same operations in the same
-// order as ldl7_solve's first loop, so the result is bit-identical) -- the substitution's dependent chain
-// disappears into the factorisation's; ldl7_back finishes with the scaling and L' x = z.
-MJB_HD void ldl7_fwd(double (&A)[7][7], double (&dinv)[7], double (&b)[7]) {
-#pragma unroll
     for (int j = 0; j < 7; j++) {
-        MJB_LDL_COLUMN(j)
+        const double inv = rcp_pos(A[j][j]);
+        dinv[j] = inv;
+        double c[7];
 #pragma unroll
-        for (int i = j + 1; i < 7; i++) b[i] = fma(-A[i][j], b[j], b[i]);
+        for (int i = j + 1; i < 7; i++) { c[i] = A[i][j]; A[i][j] = c[i] * inv; }
+#pragma unroll
+        for (int i = j + 1; i < 7; i++) {
+#pragma unroll
+            for (int k = j + 1; k <= i; k++) A[i][k] = fma(-A[i][j], c[k], A[i][k]);
+        }
     }
 }
-MJB_HD void ldl7_back(const double (&L)[7][7], const double (&dinv)[7], double (&b)[7]) {
-#pragma unroll
-    for (int i = 0; i < 7; i++) b[i] *= dinv[i];
-#pragma unroll
-    for (int i = 5; i >= 0; i--) {
-#ifdef MJB_BACK_ORDER
-        // oldest unknown first: the unknown found last (b[i+1]) enters through the final FMA, so consecutive
-        // rows are one FMA apart on the dependency chain (ascending k chains 7 - i operations per row)
-#pragma unroll
-        for (int k = 6; k > i; k--) b[i] = fma(-L[k][i], b[k], b[i]);
-#else
-#pragma unroll
-        for (int k = i + 1; k < 7; k++) b[i] -= L[k][i] * b[k];
-#endif
-    }
-}
+// L y = b, z = D^-1 y, L' x = z.  Both substitutions apply the unknown found LAST through the final FMA of a
+// row (forward: k ascending; backward: k descending), so consecutive rows are one FMA apart on the
+// dependency chain; with k ascending the backward pass chained 7 - i operations per row (27 instead of 7
+// dependent FP64 operations at 8.2 cycles each: measured 3.5 % of the whole rollout kernel).
 MJB_HD void ldl7_solve(const double (&L)[7][7], const double (&dinv)[7], double (&b)[7]) {
 #pragma unroll
     for (int i = 1; i < 7; i++) {
 #pragma unroll
-        for (int k = 0; k < i; k++) b[i] -= L[i][k] * b[k];
+        for (int k = 0; k < i; k++) b[i] = fma(-L[i][k], b[k], b[i]);
     }
-    ldl7_back(L, dinv, b);
+#pragma unroll
+    for (int i = 0; i < 7; i++) b[i] *= dinv[i];
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+#pragma unroll
+        for (int k = 6; k > i; k--) b[i] = fma(-L[k][i], b[k], b[i]);
+    }
 }
 
 // MuJoCo's constraint impedance / regulariser / reference acceleration of one soft row
@@ -789,8 +733,7 @@ MJB_NOINLINE void constrained_solve_slow(double* w) {
 
 // One mj_step of the chain: forward dynamics at (q, qd) under the actuator torques held in the scratch
 // (SC_U = gear * clip(ctrl), computed once per env step), then Euler advance.  sn/cs must hold sin/cos
-// of q on entry (with MJB_SINCOS_INCR they are advanced with q and valid again on return).  Returns true
-// when a constraint row was present.
+// of q on entry.  Returns true when a constraint row was present.
 //
 // Constraint forces: exact minimiser over a of 1/2 a'Ma - f'a + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
 // by Newton on the active set (each piece of the objective is quadratic, so a solve whose own active
@@ -801,7 +744,8 @@ MJB_NOINLINE void constrained_solve_slow(double* w) {
 //     Newton:  H = M + diag(dadd),  rhs = f + radd,   dadd = D on the active rows, radd = D b
 //     Euler:   H = M + diag(h B),   rhs = f + fc,     fc = D (b - a) on the active rows
 template <class T, class P, class S>
-MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], double (&sn)[7], double (&cs)[7]) {
+MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], const double (&sn)[7],
+                          const double (&cs)[7]) {
     double f[7];
     chain_mass_bias<T>(prm, sc, sn, cs, qd, f);
 #pragma unroll
@@ -874,13 +818,8 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
                 H[i][i] = sc.ld(moff + sc_m(i, i)) + dadd[i];
                 x[i] = f[i] + radd[i];
             }
-#ifdef MJB_LDL_FUSED_RHS
-            ldl7_fwd(H, dinv, x);
-            ldl7_back(H, dinv, x);
-#else
             ldl7(H, dinv);
             ldl7_solve(H, dinv, x);
-#endif
             again = 0;
             if (phase == 0) {
                 unsigned actx = 0;
@@ -938,31 +877,8 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
     }
     MJB_STAT_TRIPS(ntrip);
     const double h = prm[CS_TIMESTEP];
-#ifdef MJB_SINCOS_INCR
-    // sin/cos follow the joint angles by angle addition (sincos_advance); a fresh evaluation only after a
-    // step beyond the polynomial's bound
-    bool big = false;
-#pragma unroll
-    for (int j = 0; j < 7; j++) {
-        qd[j] += h * x[j];
-        const double dq = h * qd[j];
-        q[j] += dq;
-        const double z = dq * dq;
-        big |= z > MJB_SINCOS_STEP_MAX2;
-        sincos_advance(sn[j], cs[j], dq, z);
-    }
-    if (big) {
-        double io[21];
-#pragma unroll
-        for (int j = 0; j < 7; j++) io[j] = q[j];
-        sincos_refresh(io);
-#pragma unroll
-        for (int j = 0; j < 7; j++) { sn[j] = io[7 + j]; cs[j] = io[14 + j]; }
-    }
-#else
 #pragma unroll
     for (int j = 0; j < 7; j++) { qd[j] += h * x[j]; q[j] += h * qd[j]; }
-#endif
     return any;
 }
 

@@ -70,10 +70,6 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
     double q[7], v[7], sn[7], cs[7];
 #pragma unroll
     for (int j = 0; j < 7; j++) { q[j] = __ldg(st + j); v[j] = __ldg(st + 7 + j); }
-#ifdef MJB_SINCOS_INCR
-#pragma unroll
-    for (int j = 0; j < 7; j++) sincos_joint(q[j], sn[j], cs[j]);     // kept current by chain_substep from here on
-#endif
     const V3 target = {__ldg(st + 14), __ldg(st + 15), __ldg(st + 16)};
     const V3 hand_local = {prm[CS_HAND], prm[CS_HAND + 1], prm[CS_HAND + 2]};
     const int fs = (int)prm[CS_FRAME_SKIP];
@@ -152,10 +148,8 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
         }
         V3 hand = {0.0, 0.0, 0.0};
         for (int s = 0; s < fs; s++) {
-#ifndef MJB_SINCOS_INCR
 #pragma unroll
             for (int j = 0; j < 7; j++) sincos_joint(q[j], sn[j], cs[j]);
-#endif
             // data.site_xpos read after mj_step is the one computed by the LAST forward pass, i.e. at
             // the state before the last substep's integration (reacher_env.py:31-35).
             if (s == fs - 1) hand = chain_point_world<T>(prm, sn, cs, hand_local);

@@ -16,16 +16,11 @@ static void run(const double* P, const double* qpos, const double* qvel, const d
         double q[7], v[7], sn[7], cs[7];
         HostScratch sc;
         for (int j = 0; j < 7; j++) { q[j] = qpos[j]; v[j] = qvel[j]; }
-#ifdef MJB_SINCOS_INCR
-        for (int j = 0; j < 7; j++) sincos_joint(q[j], sn[j], cs[j]);
-#endif
         for (int t = 0; t < H; t++) {
             for (int j = 0; j < 7; j++) sc.st(SC_U + j, actuator_torque(prm, j, mean[t * 7 + j] + noise[((size_t)k * H + t) * 7 + j]));
             V3 hand{0, 0, 0};
             for (int s = 0; s < fs; s++) {
-#ifndef MJB_SINCOS_INCR
                 for (int j = 0; j < 7; j++) sincos_joint(q[j], sn[j], cs[j]);
-#endif
                 if (s == fs - 1) hand = chain_point_world<T>(prm, sn, cs, V3{P[CS_HAND], P[CS_HAND + 1], P[CS_HAND + 2]});
                 chain_substep<T>(prm, sc, q, v, sn, cs);
             }
