@@ -5,7 +5,7 @@
 
 Variants are the default library built with extra -D flags (mjmpc_b200.build.build(out=, defines=)), plus
 `base`: the library of an older commit (VARIANT_BASE_REV, default HEAD~1) for before/after timing.
-All variant libraries are loaded side by side in one process.
+Every variant runs in its own process (MJB_LIB_PATH selects the library).
 """
 import json
 import os
@@ -18,12 +18,6 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "gpurun_variants")
 VARIANTS = {
     "default": [],
-    "sincos": ["MJB_SINCOS_INCR"],
-    "back": ["MJB_BACK_ORDER"],
-    "pivot": ["MJB_PIVOT_SQ"],
-    "fwd": ["MJB_LDL_FUSED_RHS"],
-    "sincos_back": ["MJB_SINCOS_INCR", "MJB_BACK_ORDER"],
-    "all4": ["MJB_SINCOS_INCR", "MJB_BACK_ORDER", "MJB_PIVOT_SQ", "MJB_LDL_FUSED_RHS"],
 }
 
 
@@ -45,8 +39,10 @@ def build_all():
     print(sorted(os.listdir(VDIR)))
 
 
-def run_all(K):
-    """All variants in one process: each library is loaded side by side (its own model handle and constant bank)."""
+def run_one(K):
+    """Parity vs the C oracle + device timing of the library MJB_LIB_PATH points to (one process per variant:
+    libraries loaded side by side share their template kernel symbols, so in one process every variant's
+    trajectory kernel came from the first library loaded -- seen as bit-identical checksums in round 1)."""
     import numpy as np
     import torch
     from bench import synthetic_states
@@ -64,47 +60,46 @@ def run_all(K):
     Kp = 512
     pnoise = generate_noise(cov, [0.25, 0.8, 0.0], (Kp, H), 7, device="cuda")
     pstates = (states[0], dict(qp=np.zeros(7), qv=np.zeros(7), target_pos=np.array([.1, .1, .1])))
-    refs = [mjstep.rollout(om, st["qp"], st["qv"], st["target_pos"], np.zeros((H, 7)),
-                           np.ascontiguousarray(pnoise.cpu().numpy()), want_traj=True, nthreads=8) for st in pstates]
+    env = GpuReacherVecEnv(cm)
+    name = os.path.basename(_lib.LIB_PATH)[4:-3]
+    r = dict(variant=name, K=K, H=H, ms_median=[], ms_min=[])
+    # parity on a small batch, injected noise: interior start + the env's reset state (limits bind at once)
+    err, chk = 0.0, 0.0
+    for st in pstates:
+        ref = mjstep.rollout(om, st["qp"], st["qv"], st["target_pos"], np.zeros((H, 7)),
+                             np.ascontiguousarray(pnoise.cpu().numpy()), want_traj=True, nthreads=8)
+        env.set_env_state(st)
+        out = env.rollout_device(Kp, H, mean, pnoise, want_traj=True)
+        scale = np.abs(ref["qv"]).max(axis=(0, 1))
+        err = max(err, float((np.abs(out["qv"].cpu().numpy() - ref["qv"]).max(axis=(0, 1)) / scale).max()))
+        chk += float(out["qv"].sum().item())
+    r["rel_err_vs_oracle"], r["traj_checksum"] = err, repr(chk)
+    # timing: the bench's K1 workload (new state every launch, noise resident in HBM), three passes
     noise = generate_noise(cov, [0.25, 0.8, 0.0], (K, H), 3, device="cuda")
-    libs = sorted(f for f in os.listdir(VDIR) if f.startswith("lib_") and f.endswith(".so"))
-    envs = {}
-    for f in libs:
-        _lib._lib, _lib.LIB_PATH = None, os.path.join(VDIR, f)
-        envs[f] = (GpuReacherVecEnv(cm), _lib.lib())
-    results = {}
-    for rep in range(3):                      # three passes: order effects / clock drift show up as disagreement
-        for f in libs:
-            env, _lib._lib = envs[f]
-            # parity on a small batch, injected noise: interior start + the env's reset state (limits bind at once)
-            err = 0.0
-            if rep == 0:
-                for st, ref in zip(pstates, refs):
-                    env.set_env_state(st)
-                    out = env.rollout_device(Kp, H, mean, pnoise, want_traj=True)
-                    scale = np.abs(ref["qv"]).max(axis=(0, 1))
-                    err = max(err, float((np.abs(out["qv"].cpu().numpy() - ref["qv"]).max(axis=(0, 1)) / scale).max()))
-            # timing: the bench's K1 workload (new state every launch, noise resident in HBM)
-            env.set_env_state(states[1])
-            out = env.rollout_device(K, H, mean, noise)
+    env.set_env_state(states[1])
+    out = env.rollout_device(K, H, mean, noise)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(3):
+        ts = []
+        for i in range(10):
+            env.set_env_state(states[i % 4])
+            e0.record()
+            env.rollout_device(K, H, mean, noise, costs=out["costs"], actions=out["actions"])
+            e1.record()
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ts = []
-            for i in range(10):
-                env.set_env_state(states[i % 4])
-                e0.record()
-                env.rollout_device(K, H, mean, noise, costs=out["costs"], actions=out["actions"])
-                e1.record()
-                torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1))
-            ts = sorted(ts[2:])
-            r = results.setdefault(f[4:-3], dict(variant=f[4:-3], K=K, H=H, ms_median=[], ms_min=[]))
-            r["ms_median"].append(round(ts[len(ts) // 2], 4)); r["ms_min"].append(round(ts[0], 4))
-            if rep == 0:
-                r["rel_err_vs_oracle"] = err
-    for r in results.values():
-        r["alg_tflops"] = K * H * 5340 / (min(r["ms_median"]) * 1e-3) / 1e12
-        print(json.dumps(r), flush=True)
+            ts.append(e0.elapsed_time(e1))
+        ts = sorted(ts[2:])
+        r["ms_median"].append(round(ts[len(ts) // 2], 4)); r["ms_min"].append(round(ts[0], 4))
+    r["alg_tflops"] = K * H * 5340 / (min(r["ms_median"]) * 1e-3) / 1e12
+    print(json.dumps(r), flush=True)
+
+
+def run_all(K):
+    libs = sorted(f for f in os.listdir(VDIR) if f.startswith("lib_") and f.endswith(".so"))
+    for f in libs:
+        env = dict(os.environ, MJB_LIB_PATH=os.path.join(VDIR, f))
+        subprocess.call([sys.executable, os.path.abspath(__file__), "one", str(K)], env=env, cwd=ROOT)
 
 
 if __name__ == "__main__":
@@ -112,5 +107,7 @@ if __name__ == "__main__":
     K = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
     if mode == "build":
         build_all()
+    elif mode == "one":
+        run_one(K)
     else:
         run_all(K)
