@@ -15,7 +15,7 @@ import numpy as np
 import yaml
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from mjmpc_b200.envs.gpu_reacher_env import GpuReacherEnv          # noqa: E402
+from mjmpc_b200.envs.gpu_reacher_env import GpuContinualReacherEnv, GpuReacherEnv          # noqa: E402
 from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv            # noqa: E402
 from mjmpc_b200.policies import MPCPolicy                           # noqa: E402
 
@@ -51,9 +51,10 @@ def main():
     if args.dyn_randomize_config is not None:
         with open(args.dyn_randomize_config) as file:
             dynamics_rand_params = yaml.load(file, Loader=yaml.FullLoader)
-    if exp_params['env_name'] != 'reacher_7dof-v0':
-        raise NotImplementedError("only reacher_7dof-v0 has a GPU plant; see DESIGN.md section 6")
-    env = GpuReacherEnv()
+    plants = {'reacher_7dof-v0': GpuReacherEnv, 'continual_reacher-v0': GpuContinualReacherEnv}   # mjmpc/envs/__init__.py:24-35
+    if exp_params['env_name'] not in plants:
+        raise NotImplementedError("only %s have a GPU plant; see DESIGN.md section 6" % sorted(plants))
+    env = plants[exp_params['env_name']]()
     policy_params, num_cpu = load_policy_params(exp_params, args.controller, env)
     n_episodes = args.n_episodes or exp_params['n_episodes']
     base_seed = exp_params['seed']

@@ -23,6 +23,7 @@ class GpuReacherEnv:
         self.action_lows, self.action_highs = self.sim.action_lows, self.sim.action_highs
         self.np_random = np.random.RandomState(seed)
         self.env_timestep = 0
+        self.real_step = True              # reacher_env.py:13: timed events fire on the plant, not in planning copies
         self.qp, self.qv, self.qa = np.zeros(7), np.zeros(7), np.zeros(7)
         self.target_pos = np.array([0.1, 0.1, 0.1])      # sawyer.xml:13
         self._hand = forward_kinematics(self.sim.compiled.tree, self.qp)["hand"]
@@ -32,12 +33,20 @@ class GpuReacherEnv:
         if seed is not None:
             self.np_random = np.random.RandomState(seed)
         self.qp, self.qv, self.qa = np.zeros(7), np.zeros(7), np.zeros(7)
-        self.target_pos = np.array([self.np_random.uniform(low=-0.3, high=0.3),
-                                    self.np_random.uniform(low=-0.2, high=0.2),
-                                    self.np_random.uniform(low=-0.25, high=0.25)])
+        self.target_reset()
         self.env_timestep = 0
         self._hand = forward_kinematics(self.sim.compiled.tree, self.qp)["hand"]
         return self.get_obs()
+
+    # reacher_env.py:56-62 (three draws in x, y, z order from the env's generator)
+    def target_reset(self):
+        self.target_pos = np.array([self.np_random.uniform(low=-0.3, high=0.3),
+                                    self.np_random.uniform(low=-0.2, high=0.2),
+                                    self.np_random.uniform(low=-0.25, high=0.25)])
+
+    # reacher_env.py:73-75
+    def trigger_timed_events(self):
+        pass
 
     # reacher_env.py:81-99
     def get_env_state(self):
@@ -63,7 +72,8 @@ class GpuReacherEnv:
         reward = -float(out["costs"][0, 0].item())
         self.qp, self.qv = ob[:7].copy(), ob[7:14].copy()
         self._hand = ob[14:17].copy()
-        self.env_timestep += 1
+        self.env_timestep += 1       # the observation is taken before the timed events, the infos after (:36-39)
+        self.trigger_timed_events()
         return ob, reward, False, self.get_env_infos()
 
     def get_env_infos(self):
@@ -80,3 +90,13 @@ class GpuReacherEnv:
 
     def close(self):
         self.sim.close()
+
+
+class GpuContinualReacherEnv(GpuReacherEnv):
+    """``continual_reacher-v0`` (reference ``reacher_env.py:128-132``, ``mjmpc/envs/__init__.py:31-35``): the
+    target is re-drawn every 50 plant steps."""
+    _max_episode_steps = 250
+
+    def trigger_timed_events(self):
+        if self.env_timestep % 50 == 0 and self.env_timestep > 0 and self.real_step is True:
+            self.target_reset()

@@ -284,3 +284,73 @@ def test_ctypes_structs_match_header_layout():
         size, off = [int(x) for x in line.split()]
         assert ctypes.sizeof(cls) == size, cname
         assert getattr(cls, last).offset == off, cname
+
+
+def test_c_abi_argument_validation_maps_to_reference_exceptions():
+    """Every entry point validates shapes before touching CUDA, returns MJB_EINVAL with a message, and the
+    ctypes shim raises the exception type the reference raises for the same mistake (ValueError / the
+    `K % num_cpu` assertion text of subproc_vec_env.py:162).  No compute call is made: the checks fail first."""
+    import ctypes
+    from mjmpc_b200 import _lib
+    L = _lib.lib()
+    D = 8            # any non-null address: never dereferenced, the shape checks fail first
+
+    def expect(rc, text):
+        assert rc == _lib.MJB_EINVAL
+        msg = L.mjb_last_error().decode()
+        assert text in msg, msg
+        with pytest.raises(ValueError):
+            _lib.check(rc)
+
+    a = _lib.RolloutArgs()
+    expect(L.mjb_rollout_reacher(None, ctypes.byref(a), None), "null handle")
+    n = _lib.NoiseArgs()
+    expect(L.mjb_generate_noise(ctypes.byref(n), None), "null pointer")
+    n.K, n.H, n.d, n.cov, n.out = 4, 4, 9, D, D
+    expect(L.mjb_generate_noise(ctypes.byref(n), None), "not in 1..8")
+    p = _lib.PfBatchedArgs()
+    p.n_ctrl, p.K, p.H, p.d = 1, 5000, 4, 7
+    p.costs = p.samples = p.gamma_seq = p.r = p.out = p.mean = D
+    expect(L.mjb_pf_update_batched(ctypes.byref(p), None), "<= 4096")
+    m = _lib.MppiBatchedArgs()
+    m.n_ctrl, m.K, m.H, m.d, m.lam = 1, 8, 4, 7, 0.0
+    m.costs = m.actions = m.mean = m.gamma_seq = D
+    expect(L.mjb_mppi_update_batched(ctypes.byref(m), None), "lam must be positive")
+    g = np.ones(200)
+    rc = L.mjb_cost_to_go(ctypes.c_void_p(D), 1, 1, g.ctypes.data_as(ctypes.c_void_p), 4, 200, ctypes.c_void_p(D), 1, 1, None)
+    expect(rc, "exceeds the supported maximum")
+    e = _lib.EliteArgs()
+    assert L.mjb_elite_moments1(ctypes.byref(e), None) == _lib.MJB_EINVAL
+    assert L.mjb_select_elites(None, 8, 2, None, None, None, None) == _lib.MJB_EINVAL
+    assert L.mjb_shift_mean(None, 4, 7, 0, None, None) == _lib.MJB_EINVAL
+    assert _lib.check(_lib.MJB_OK) is None
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.MJB_ENOTIMPL)
+
+
+def test_continual_reacher_timed_events_rule():
+    """reacher_env.py:128-132 on the host class (no device needed for the rule itself)."""
+    from mjmpc_b200.envs.gpu_reacher_env import GpuContinualReacherEnv, GpuReacherEnv
+    env = object.__new__(GpuContinualReacherEnv)
+    env.np_random = np.random.RandomState(3)
+    env.real_step, env.target_pos = True, np.array([0.1, 0.1, 0.1])
+    fired = []
+    for t in range(0, 151):
+        env.env_timestep = t
+        before = env.target_pos.copy()
+        env.trigger_timed_events()
+        if not np.array_equal(before, env.target_pos):
+            fired.append(t)
+    assert fired == [50, 100, 150]
+    rng = np.random.RandomState(3)
+    for _ in range(3):
+        want = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.2, 0.2), rng.uniform(-0.25, 0.25)])
+    np.testing.assert_array_equal(env.target_pos, want)
+    env.real_step = False
+    env.env_timestep = 200
+    env.trigger_timed_events()
+    np.testing.assert_array_equal(env.target_pos, want)
+    base = object.__new__(GpuReacherEnv)
+    base.env_timestep, base.real_step, base.target_pos = 50, True, want.copy()
+    base.trigger_timed_events()
+    np.testing.assert_array_equal(base.target_pos, want)
