@@ -38,8 +38,9 @@ __device__ __forceinline__ void normal_pair32(unsigned a, unsigned b, double& z0
     const float r2 = -1.3862943611198906f * __log2f(fminf(u1, 1.0f));   // -2 ln u1
     float rad;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(r2));
-    const float ang = fmaf(u2, 6.2831853071795865f, -3.1415926535897932f);   // uniform on [-pi, pi)
-    z0 = (double)(rad * __cosf(ang)); z1 = (double)(rad * __sinf(ang));
+    // cos(2 pi u2) = -cos(2 pi u2 - pi): the shifted angle is uniform on [-pi, pi)
+    const float ang = fmaf(u2, 6.2831853071795865f, -3.1415926535897932f);
+    z0 = (double)(-rad * __cosf(ang)); z1 = (double)(-rad * __sinf(ang));
 }
 
 
