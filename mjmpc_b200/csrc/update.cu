@@ -244,11 +244,21 @@ __global__ void __launch_bounds__(MJB_RB) weighted_reduce_kernel(
 }
 
 // fixed-order sum over chunks: part[t*NACC + c] = sum_chunk blockpart[(t*nchunks+chunk)*NACC + c]
+// (eight loads issued before the first add: the one-load-per-add form paid one L2 round trip per chunk)
 __global__ void chunk_sum_kernel(const double* __restrict__ bp, int nchunks, int NACC, double* __restrict__ part) {
     const int t = blockIdx.x;
     for (int c = threadIdx.x; c < NACC; c += blockDim.x) {
+        const double* __restrict__ p = bp + (long long)t * nchunks * NACC + c;
         double s = 0.0;
-        for (int ch = 0; ch < nchunks; ch++) s += bp[((long long)t * nchunks + ch) * NACC + c];
+        int ch = 0;
+        for (; ch + 8 <= nchunks; ch += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = p[(long long)(ch + u) * NACC];
+#pragma unroll
+            for (int u = 0; u < 8; u++) s += v[u];
+        }
+        for (; ch < nchunks; ch++) s += p[(long long)ch * NACC];
         part[t * NACC + c] = s;
     }
 }
