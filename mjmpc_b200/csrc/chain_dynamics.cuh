@@ -43,8 +43,9 @@
 namespace mjb {
 
 #if defined(MJB_HOST_STATS)
-// host test harness only: solver statistics [substeps, substeps with rows, factor/solve passes, line searches]
-static long long g_stats[4] = {0, 0, 0, 0};
+// host test harness only: solver statistics [substeps, substeps with rows, factor/solve passes, line searches,
+// rank-one repairs tried, repairs confirmed]
+static long long g_stats[6] = {0, 0, 0, 0, 0, 0};
 static int* g_trips = nullptr;      // optional: factor/solve passes of every substep, in call order
 static long long g_ntrips = 0;
 #define MJB_STAT(i) (g_stats[i]++)
@@ -534,7 +535,14 @@ MJB_HD bool make_rows(const P& prm, S& sc, const double (&q)[7], const double (&
     bool any = false;
     const double d0 = prm[CS_IMP_D0], dw = prm[CS_IMP_DW], width = prm[CS_IMP_WIDTH];
     R.below = 0;
+    // Centre of the contact sphere: a chain of 7 dependent rotations that nothing below depends on until the
+    // distance test.  It is evaluated inside the branch that computes the limit rows so that ptxas interleaves
+    // it with their independent per-joint work (as a basic block of its own it cost 128 cycles of exposed
+    // latency per substep for 42 instructions).
+    V3 c;
+    const V3 cpos = {prm[CS_CON_POS], prm[CS_CON_POS + 1], prm[CS_CON_POS + 2]};
     if (prm[CS_IMP_POWER] == 2.0 && d0 != dw && width > 1e-15) {
+        c = chain_point_world<T>(prm, sn, cs, cpos);
         // default impedance shape (power 2)
         const int limited = (int)prm[CS_LIMITED_MASK];
         const double mid = prm[CS_IMP_MID];
@@ -573,6 +581,7 @@ MJB_HD bool make_rows(const P& prm, S& sc, const double (&q)[7], const double (&
             }
         }
     } else {
+        c = chain_point_world<T>(prm, sn, cs, cpos);
         double qv[14], Db[14];
         unsigned ba[2];
 #pragma unroll
@@ -584,19 +593,16 @@ MJB_HD bool make_rows(const P& prm, S& sc, const double (&q)[7], const double (&
     }
     R.Dc = 0.0; R.arefc = 0.0;
     const double radius = prm[CS_CON_RADIUS];
-    if (radius > 0.0) {
-        const V3 c = chain_point_world<T>(prm, sn, cs, V3{prm[CS_CON_POS], prm[CS_CON_POS + 1], prm[CS_CON_POS + 2]});
-        const double dist = c.z - prm[CS_CON_PLANE_Z] - radius;
-        if (dist < prm[CS_CON_MARGIN]) {
-            double io[21];
+    const double dist = c.z - prm[CS_CON_PLANE_Z] - radius;
+    if (radius > 0.0 && dist < prm[CS_CON_MARGIN]) {
+        double io[21];
 #pragma unroll
-            for (int j = 0; j < 7; j++) { io[j] = sn[j]; io[7 + j] = cs[j]; io[14 + j] = qd[j]; }
-            contact_row<T>(prm, io, c.x, c.y, c.z, dist);
+        for (int j = 0; j < 7; j++) { io[j] = sn[j]; io[7 + j] = cs[j]; io[14 + j] = qd[j]; }
+        contact_row<T>(prm, io, c.x, c.y, c.z, dist);
 #pragma unroll
-            for (int j = 0; j < 7; j++) sc.st(SC_JC + j, io[j]);
-            R.Dc = io[7]; R.arefc = io[8];
-            any = true;
-        }
+        for (int j = 0; j < 7; j++) sc.st(SC_JC + j, io[j]);
+        R.Dc = io[7]; R.arefc = io[8];
+        any = true;
     }
     return any;
 }
@@ -835,7 +841,45 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
                 }
                 // same set as the one the solve was built from: optimum, next trip is the Euler solve with
                 // the joint-space constraint force D_j (b_j - a_j); otherwise a plain active-set (unit Newton) step
-                const bool ok = (actx == act) & (con_x == con_on);
+                bool ok = (actx == act) & (con_x == con_on);
+#ifndef MJB_NO_REPAIR
+                // One limit row misjudged (98 % of the wrong guesses; measured on the host): repair the solution
+                // by a rank-one update on the factor at hand instead of a new factor/solve trip.  With
+                // H z = e_j:  (H + s D_j e_j e_j') x' = rhs + s rho_j e_j  has  x' = x + alpha z,
+                // alpha = s (rho_j - D_j x_j) / (1 + s D_j z_j),  s = +1 row j turns on, -1 off.  MuJoCo's
+                // regulariser makes D_j (H^-1)_jj ~ imp/(1-imp) = 9..19, so the denominator of the "off" case
+                // (1 - D_j z_j = 1/(1 + D_j h)) loses one digit, not more.  The repaired solution is then checked
+                // like any other; a warp whose lanes all settle here skips the third trip the wrong guess cost
+                // (64 % of warp-substeps on the bench workload).
+                const unsigned fm = actx ^ act;
+                if (!ok && R.Dc == 0.0 && (fm & (fm - 1u)) == 0u) {
+                    MJB_STAT(4);
+                    double z[7];
+#pragma unroll
+                    for (int j = 0; j < 7; j++) z[j] = ((fm >> j) & 1u) ? 1.0 : 0.0;
+                    ldl7_solve(H, dinv, z);
+                    double Dj = 0.0, wj = 0.0, zj = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 7; j++) {
+                        const bool b = (fm >> j) & 1u;
+                        // rho_j - D_j x_j = D_j sg_j (bs_j - sg_j x_j)
+                        Dj = b ? R.D[j] : Dj;
+                        wj = b ? sflip(R.bs[j] - sflip(x[j], R.sgn(j)), R.sgn(j)) : wj;
+                        zj = b ? z[j] : zj;
+                    }
+                    const bool on = (actx & fm) != 0u;
+                    const double sD = on ? Dj : -Dj;
+                    const double alpha = sD * wj * rcp_pos(fma(sD, zj, 1.0));
+#pragma unroll
+                    for (int j = 0; j < 7; j++) x[j] = fma(alpha, z[j], x[j]);
+                    act ^= fm;
+                    actx = 0;
+#pragma unroll
+                    for (int j = 0; j < 7; j++) actx |= (sflip(x[j], R.sgn(j)) < R.bs[j]) ? (1u << j) : 0u;
+                    ok = actx == act;
+                    if (ok) MJB_STAT(5);
+                }
+#endif
 #pragma unroll
                 for (int j = 0; j < 7; j++) {
                     const double De = ((actx >> j) & 1u) ? R.D[j] : 0.0;

@@ -58,5 +58,6 @@ extern "C" void hostcheck_sincos(double x, double* s, double* c) { mjb::sincos_j
 // record the factor/solve passes of every following substep into buf (call order: particle, step, substep)
 extern "C" void hostcheck_record_trips(int* buf) { mjb::g_trips = buf; mjb::g_ntrips = 0; }
 extern "C" void hostcheck_stats(long long* out, int reset) {
-    for (int i = 0; i < 4; i++) { out[i] = mjb::g_stats[i]; if (reset) mjb::g_stats[i] = 0; }
+    for (int i = 0; i < 6; i++) { out[i] = mjb::g_stats[i]; if (reset) mjb::g_stats[i] = 0; }
 }
+

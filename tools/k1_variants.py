@@ -18,6 +18,7 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "gpurun_variants")
 VARIANTS = {
     "default": [],
+    "no_repair": ["MJB_NO_REPAIR"],      # without the rank-one repair of a misjudged limit row (chain_dynamics.cuh)
 }
 
 
