@@ -354,3 +354,32 @@ def test_continual_reacher_timed_events_rule():
     base.env_timestep, base.real_step, base.target_pos = 50, True, want.copy()
     base.trigger_timed_events()
     np.testing.assert_array_equal(base.target_pos, want)
+
+
+def test_rank_one_repair_settles_misjudged_rows_on_the_host(compiled_model, hostcheck):
+    """The solver's first active-set guess is wrong for a few percent of the constrained substeps, almost always
+    in one row; the rank-one repair (chain_dynamics.cuh) must settle those without a further factor/solve trip:
+    nearly every repair confirmed, a third trip the exception even at warp level (max over 32 lanes)."""
+    P = compiled_model.chain.params
+    K, H = 512, 24
+    st = synthetic_state(compiled_model, 1)
+    noise = reference_noise(K, H, 7, 11)
+    mean = np.zeros((H, 7))
+    trips = np.zeros(K * H * 2, dtype=np.int32)
+    stats = (C.c_longlong * 6)()
+    hostcheck.hostcheck_stats(stats, 1)
+    hostcheck.hostcheck_record_trips(trips.ctypes.data_as(C.POINTER(C.c_int)))
+    costs = np.zeros((K, H)); qv = np.zeros((K, H, 14))
+    hostcheck.hostcheck_rollout(_p(P), 0, _p(st["qp"]), _p(st["qv"]), _p(st["target_pos"]), K, H, _p(mean), _p(noise),
+                                _p(costs), _p(qv))
+    hostcheck.hostcheck_record_trips(None)
+    hostcheck.hostcheck_stats(stats, 0)
+    substeps, with_rows, passes, slow, tried, confirmed = list(stats)
+    assert substeps == K * H * 2 and with_rows > 0.2 * substeps          # the workload does exercise the limits
+    assert tried > 0.01 * with_rows and confirmed >= 0.99 * tried
+    assert slow == 0
+    t = trips.reshape(K, H * 2)
+    assert t.min() == 1 and t.max() <= 4
+    warp = t.reshape(K // 32, 32, H * 2).max(axis=1)
+    assert (warp >= 3).mean() < 0.10, (warp >= 3).mean()
+    assert np.isfinite(qv).all()
