@@ -53,7 +53,7 @@ typedef struct {
     int particles_per_ctrl;      /* K for one controller; K / n for n batched controllers */
     int particles_per_model;     /* K / n_workers in the reference's worker layout */
     const double* state;         /* (n_ctrl, MJB_STATE_DIM) */
-    const double* mean;          /* (n_ctrl, H, 7) row-major */
+    const double* mean;          /* (n_ctrl, H, 7) row-major (closed_loop: policy weights, see below) */
     const double* noise;         /* (K, H, 7) by strides, or NULL for the mean sequence only */
     long long noise_sk, noise_st, noise_sj;
     double* costs;               /* (K, H) = -reward */
@@ -72,6 +72,11 @@ typedef struct {
     double noise_beta0, noise_beta1, noise_beta2;
     long long noise_k_offset, noise_K_global;
     int noise_zero_last;         /* particle noise_K_global-1 gets noise = -mean (mean row of its controller) */
+    /* mode="closed_loop_linear" of GymEnvWrapper.rollout (gym_env_wrapper.py:135-136): with closed_loop != 0,
+     * `mean` is (n_ctrl, MJB_OBS_DIM + 1, 7) row-major -- the weights of a linear policy -- and the control of
+     * step t is mean' [obs_t; 1] + noise[k,t], obs_t the observation before the step (the first one from fresh
+     * kinematics at the set state, reacher_env.py:88-99). */
+    int closed_loop;
 } mjb_rollout_args;
 int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a, void* stream);
 

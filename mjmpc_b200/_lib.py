@@ -31,7 +31,7 @@ class RolloutArgs(C.Structure):
         ("noise_cov", C.c_void_p), ("noise_seed", C.c_ulonglong), ("noise_offset", C.c_ulonglong),
         ("noise_step_ptr", C.c_void_p),
         ("noise_beta0", C.c_double), ("noise_beta1", C.c_double), ("noise_beta2", C.c_double),
-        ("noise_k_offset", c_ll), ("noise_K_global", c_ll), ("noise_zero_last", C.c_int),
+        ("noise_k_offset", c_ll), ("noise_K_global", c_ll), ("noise_zero_last", C.c_int), ("closed_loop", C.c_int),
     ]
 
 

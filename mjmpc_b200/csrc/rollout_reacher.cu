@@ -66,7 +66,9 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
         prm.p = params + (size_t)inst * CH_NDEV;
     }
     const double* __restrict__ st = a.state + (size_t)ctrl * MJB_STATE_DIM;
-    const double* __restrict__ mean = a.mean + (size_t)ctrl * a.H * 7;
+    // closed_loop (EXTRA instantiations only): `mean` holds the (d_obs + 1, 7) weights of a linear policy
+    const bool closed = EXTRA && a.closed_loop;
+    const double* __restrict__ mean = a.mean + (size_t)ctrl * (closed ? (MJB_OBS_DIM + 1) * 7 : a.H * 7);
     double q[7], v[7], sn[7], cs[7];
 #pragma unroll
     for (int j = 0; j < 7; j++) { q[j] = __ldg(st + j); v[j] = __ldg(st + 7 + j); }
@@ -74,6 +76,14 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
     const V3 hand_local = {prm[CS_HAND], prm[CS_HAND + 1], prm[CS_HAND + 2]};
     const int fs = (int)prm[CS_FRAME_SKIP];
     int nc = 0;
+    // hand position of the current observation: fresh kinematics at the set state (set_env_state ends with
+    // sim.forward(), reacher_env.py:88-99), afterwards the stale one the last step's cost used
+    V3 hand_prev = {0.0, 0.0, 0.0};
+    if (closed) {
+#pragma unroll
+        for (int j = 0; j < 7; j++) sincos_joint(q[j], sn[j], cs[j]);
+        hand_prev = chain_point_world<T>(prm, sn, cs, hand_local);
+    }
     const double* __restrict__ np = a.noise ? a.noise + k * a.noise_sk : nullptr;
     double* __restrict__ ap = a.actions ? a.actions + k * a.act_sk : nullptr;
     double* __restrict__ cp = a.costs + k * a.costs_sk;
@@ -100,7 +110,22 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
     for (int t = 0; t < a.H; t++) {
         {
             double* aj = ap;
-            double x[7];
+            double x[7], ub[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            if (closed) {
+                // u = mean' [obs; 1] (gym_env_wrapper.py:135-136), obs = (qpos, qvel, hand, hand - target)
+                double ob[MJB_OBS_DIM];
+#pragma unroll
+                for (int j = 0; j < 7; j++) { ob[j] = q[j]; ob[7 + j] = v[j]; }
+                ob[14] = hand_prev.x; ob[15] = hand_prev.y; ob[16] = hand_prev.z;
+                ob[17] = hand_prev.x - target.x; ob[18] = hand_prev.y - target.y; ob[19] = hand_prev.z - target.z;
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    double s = __ldg(mean + MJB_OBS_DIM * 7 + j);
+#pragma unroll
+                    for (int i = 0; i < MJB_OBS_DIM; i++) s = fma(__ldg(mean + i * 7 + j), ob[i], s);
+                    ub[j] = s;
+                }
+            }
             if constexpr (FUSED) {
                 double z[8], e[7], h1[7], h2[7];
                 noise_normals<7>(ph, gk, step_ctr, tag_hi, t, z);
@@ -118,7 +143,7 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
             if (np) SmemScratch::fetch_wait();
 #pragma unroll
             for (int j = 0; j < 7; j++) {
-                x[j] = __ldg(mean + t * 7 + j);
+                x[j] = closed ? ub[j] : __ldg(mean + t * 7 + j);
                 if (np) x[j] += sc.ld(SC_NZ + j);
             }
             if (np && t + 1 < a.H) {
@@ -132,7 +157,7 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
                 const double* nj = np;
 #pragma unroll
                 for (int j = 0; j < 7; j++) {
-                    x[j] = __ldg(mean + t * 7 + j);
+                    x[j] = closed ? ub[j] : __ldg(mean + t * 7 + j);
                     if (np) { x[j] += __ldg(nj); nj += a.noise_sj; }
                 }
                 if (np) np += a.noise_st;
@@ -158,6 +183,7 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
         }
         *cp = reach_cost(hand, target);
         cp += a.costs_st;
+        if (EXTRA) hand_prev = hand;
         if (EXTRA && a.qv_traj) {
             double* o = a.qv_traj + ((size_t)k * a.H + t) * 14;
 #pragma unroll
@@ -188,8 +214,9 @@ extern "C" int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a
     const int block = MJB_ROLLOUT_BLOCK;
     const int grid = (a->K + block - 1) / block;
     cudaStream_t s = (cudaStream_t)stream;
-    const bool extra = a->qv_traj || a->next_obs || a->ncon;
+    const bool extra = a->qv_traj || a->next_obs || a->ncon || a->closed_loop;
     const bool fused = a->noise_cov != nullptr;
+    MJB_REQUIRE(!(fused && a->closed_loop), "mjb_rollout_reacher: closed-loop rollouts take an explicit noise tensor");
     MJB_REQUIRE(!(fused && a->noise), "mjb_rollout_reacher: pass either a noise tensor or in-kernel noise parameters, not both");
     const bool use_const = m->n_instances == 1;
     if (use_const) {

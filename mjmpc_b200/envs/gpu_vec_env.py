@@ -152,14 +152,19 @@ class GpuReacherVecEnv:
     # ---- rollouts ----------------------------------------------------------------------------
     def rollout_device(self, num_particles: int, horizon: int, mean: torch.Tensor, noise: Optional[torch.Tensor],
                        costs: Optional[torch.Tensor] = None, actions: Optional[torch.Tensor] = None,
-                       want_traj: bool = False, want_obs: bool = False, want_ncon: bool = False):
+                       want_traj: bool = False, want_obs: bool = False, want_ncon: bool = False,
+                       closed_loop: bool = False):
         """Launch K1.  ``mean`` (n_ctrl,H,7) or (H,7); ``noise`` logical shape (K,H,7) with any
-        strides.  Outputs use the particle-minor layout (H,[7,]K) viewed as (K,H[,7])."""
+        strides.  Outputs use the particle-minor layout (H,[7,]K) viewed as (K,H[,7]).
+        ``closed_loop``: ``mean`` is the (d_obs + 1, 7) weight matrix of a linear policy (one per controller),
+        the reference's mode="closed_loop_linear" (gym_env_wrapper.py:135-136)."""
         K, H = int(num_particles), int(horizon)
         n_ctrl = self._state.shape[0]
         if K % self.n_workers != 0:
             raise AssertionError("Number of particles must be divisible by number of cpus")
-        mean = mean.reshape(-1, H, 7)
+        if closed_loop and isinstance(noise, NoiseSpec):
+            raise ValueError("closed-loop rollouts take an explicit noise tensor")
+        mean = mean.reshape(-1, _lib.OBS_DIM + 1, 7) if closed_loop else mean.reshape(-1, H, 7)
         if mean.shape[0] != n_ctrl:
             raise ValueError("mean has %d controller rows but %d states are set" % (mean.shape[0], n_ctrl))
         if not mean.is_contiguous():
@@ -175,6 +180,7 @@ class GpuReacherVecEnv:
         a.particles_per_model = K // self.n_workers
         a.state = self._state.data_ptr()
         a.mean = mean.data_ptr()
+        a.closed_loop = 1 if closed_loop else 0
         if isinstance(noise, NoiseSpec):
             # fused K2: the kernel draws the noise itself, nothing is read from HBM
             if noise.shape != (K, H) or noise.cov.shape != (7, 7):
@@ -211,11 +217,11 @@ class GpuReacherVecEnv:
         """Reference signature and return value (subproc_vec_env.py:128-135, :170-186): numpy
         ``(obs, rew, act, done, info, next_obs)``.  ``obs[:, t]`` is the observation before
         step t, ``rew = -cost``."""
-        if mode != "open_loop":
-            raise NotImplementedError("only mode='open_loop' runs on the GPU rollout")
+        if mode not in ("open_loop", "closed_loop_linear"):
+            raise NotImplementedError("mode %r does not run on the GPU rollout" % (mode,))
         start_t = time.time()
         out = self.rollout_device(num_particles, horizon, self._to_device(mean), self._to_device(noise),
-                                  want_obs=True)
+                                  want_obs=True, closed_loop=(mode == "closed_loop_linear"))
         nobs = out["next_observations"].cpu().numpy()
         rew = -out["costs"].cpu().numpy()
         act = np.ascontiguousarray(out["actions"].cpu().numpy())
@@ -241,11 +247,12 @@ class GpuReacherVecEnv:
     def rollout_fn(self):
         """The closure of examples/example_mpc.py:112-133: (K, H, mean, noise, mode) -> dict."""
         def fn(num_particles, horizon, mean, noise, mode="open_loop"):
-            if mode != "open_loop":
-                raise NotImplementedError("only mode='open_loop' runs on the GPU rollout")
+            if mode not in ("open_loop", "closed_loop_linear"):
+                raise NotImplementedError("mode %r does not run on the GPU rollout" % (mode,))
             host = not isinstance(noise, (torch.Tensor, NoiseSpec)) and not isinstance(mean, torch.Tensor)
             out = self.rollout_device(num_particles, horizon, self._to_device(mean), self._to_device(noise),
-                                      want_obs=self.return_observations or host)
+                                      want_obs=self.return_observations or host,
+                                      closed_loop=(mode == "closed_loop_linear"))
             if not host:
                 return out
             # unmodified reference controllers: numpy in, numpy out, reference dict keys

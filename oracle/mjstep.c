@@ -454,6 +454,7 @@ int ora_substep(const ora_model* m, double* q, double* v, const double* u, doubl
 typedef struct {
     ora_model* const* models; int n_models; const double *qpos, *qvel, *target; int K, H;
     const double *mean, *noise; double *costs, *actions, *qv_traj, *next_obs; int* ncon; int k0, k1;
+    const double* policy_w;   /* mode="closed_loop_linear": (2nv+6+1, nv) weights; `mean` is then unused */
 } ora_job;
 
 static void* ora_rollout_range(void* arg) {
@@ -466,9 +467,26 @@ static void* ora_rollout_range(void* arg) {
         double q[MAXV], v[MAXV], u[MAXV];
         int nc = 0;
         for (int j = 0; j < nv; j++) { q[j] = J->qpos[j]; v[j] = J->qvel[j]; }
+        /* closed loop (gym_env_wrapper.py:129-136): curr_obs = get_obs() at the set state -- set_env_state ends
+         * with sim.forward() (reacher_env.py:88-99), so the first hand position is fresh -- then
+         * curr_obs = next_obs, whose hand position is the stale one of the step's last forward pass */
+        double obs[2 * MAXV + 6];
+        const int nobs = 2 * nv + 6;
+        if (J->policy_w) {
+            double qq[MAXV], vv[MAXV], zu[MAXV] = {0};
+            for (int j = 0; j < nv; j++) { qq[j] = q[j]; vv[j] = v[j]; }
+            ora_step(m, &d, qq, vv, zu);          /* d.hand: kinematics at (q, v) before the integration */
+            for (int j = 0; j < nv; j++) { obs[j] = q[j]; obs[nv + j] = v[j]; }
+            for (int c = 0; c < 3; c++) { obs[2 * nv + c] = d.hand[c]; obs[2 * nv + 3 + c] = d.hand[c] - J->target[c]; }
+        }
         for (int t = 0; t < H; t++) {
             for (int j = 0; j < nv; j++) {
-                u[j] = J->mean[t * nv + j] + (J->noise ? J->noise[((size_t)k * H + t) * nv + j] : 0.0);
+                double mu;
+                if (J->policy_w) {                /* mean.T @ np.append(curr_obs, 1.0) */
+                    mu = J->policy_w[nobs * nv + j];
+                    for (int i = 0; i < nobs; i++) mu += J->policy_w[i * nv + j] * obs[i];
+                } else mu = J->mean[t * nv + j];
+                u[j] = mu + (J->noise ? J->noise[((size_t)k * H + t) * nv + j] : 0.0);
                 if (J->actions) J->actions[((size_t)k * H + t) * nv + j] = u[j];
             }
             for (int s = 0; s < m->frame_skip; s++) { ora_step(m, &d, q, v, u); nc += d.nefc > 0; }
@@ -486,15 +504,31 @@ static void* ora_rollout_range(void* arg) {
                 o[2 * nv] = d.hand[0]; o[2 * nv + 1] = d.hand[1]; o[2 * nv + 2] = d.hand[2];
                 o[2 * nv + 3] = dx; o[2 * nv + 4] = dy; o[2 * nv + 5] = dz;
             }
+            if (J->policy_w) {
+                for (int j = 0; j < nv; j++) { obs[j] = q[j]; obs[nv + j] = v[j]; }
+                obs[2 * nv] = d.hand[0]; obs[2 * nv + 1] = d.hand[1]; obs[2 * nv + 2] = d.hand[2];
+                obs[2 * nv + 3] = dx; obs[2 * nv + 4] = dy; obs[2 * nv + 5] = dz;
+            }
         }
         if (J->ncon) J->ncon[k] = nc;
     }
     return NULL;
 }
 
+void ora_rollout_cl(ora_model* const* models, int n_models, const double* qpos, const double* qvel,
+                    const double* target, int K, int H, const double* mean, const double* noise,
+                    double* costs, double* actions, double* qv_traj, double* next_obs, int* ncon, int nthreads,
+                    const double* policy_w);
 void ora_rollout(ora_model* const* models, int n_models, const double* qpos, const double* qvel,
                  const double* target, int K, int H, const double* mean, const double* noise,
                  double* costs, double* actions, double* qv_traj, double* next_obs, int* ncon, int nthreads) {
+    ora_rollout_cl(models, n_models, qpos, qvel, target, K, H, mean, noise, costs, actions, qv_traj, next_obs, ncon,
+                   nthreads, NULL);
+}
+void ora_rollout_cl(ora_model* const* models, int n_models, const double* qpos, const double* qvel,
+                    const double* target, int K, int H, const double* mean, const double* noise,
+                    double* costs, double* actions, double* qv_traj, double* next_obs, int* ncon, int nthreads,
+                    const double* policy_w) {
     /* contiguous particle blocks per worker, like the reference's SubprocVecEnv (subproc_vec_env.py:161-168) */
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
@@ -503,7 +537,7 @@ void ora_rollout(ora_model* const* models, int n_models, const double* qpos, con
     pthread_t th[256];
     for (int i = 0; i < nthreads; i++) {
         ora_job j = {models, n_models, qpos, qvel, target, K, H, mean, noise, costs, actions, qv_traj, next_obs, ncon,
-                     (int)((long long)K * i / nthreads), (int)((long long)K * (i + 1) / nthreads)};
+                     (int)((long long)K * i / nthreads), (int)((long long)K * (i + 1) / nthreads), policy_w};
         jobs[i] = j;
     }
     if (nthreads == 1) { ora_rollout_range(&jobs[0]); return; }

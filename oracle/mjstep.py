@@ -87,15 +87,23 @@ def _solref_kb(tree):
     return (1.0 / max(1e-15, dmax * dmax * tc * tc * tree.solref[1] ** 2), 2.0 / max(1e-15, dmax * tc))
 
 
-def rollout(models, qpos, qvel, target, mean, noise, want_traj=False, want_obs=False, nthreads=1):
+def rollout(models, qpos, qvel, target, mean, noise, want_traj=False, want_obs=False, nthreads=1, policy_w=None,
+            horizon=None):
     """Reference rollout on the CPU.  ``models``: one OracleModel or a list (one per
-    contiguous particle block).  Returns dict(costs, actions[, qv, next_observations], ncon)."""
+    contiguous particle block).  Returns dict(costs, actions[, qv, next_observations], ncon).
+    ``policy_w`` (d_obs + 1, d_action): mode="closed_loop_linear" of gym_env_wrapper.py:135-136 (``mean`` is
+    then ignored and ``horizon`` gives H when there is no noise tensor to read it from)."""
     if isinstance(models, OracleModel):
         models = [models]
     nv = models[0].nv
+    noise = None if noise is None else np.ascontiguousarray(noise, np.float64)
+    if policy_w is not None:
+        policy_w = np.ascontiguousarray(policy_w, np.float64)
+        assert policy_w.shape == (2 * nv + 7, nv)
+        H = noise.shape[1] if noise is not None else int(horizon)
+        mean = np.zeros((H, nv))
     mean = np.ascontiguousarray(mean, np.float64)
     H = mean.shape[0]
-    noise = None if noise is None else np.ascontiguousarray(noise, np.float64)
     K = noise.shape[0] if noise is not None else 1
     assert K % len(models) == 0
     costs = np.zeros((K, H)); actions = np.zeros((K, H, nv))
@@ -106,10 +114,10 @@ def rollout(models, qpos, qvel, target, mean, noise, want_traj=False, want_obs=F
     qpos = np.ascontiguousarray(qpos, np.float64); qvel = np.ascontiguousarray(qvel, np.float64)
     target = np.ascontiguousarray(target, np.float64)
     nul = C.POINTER(C.c_double)()
-    lib().ora_rollout(arr, C.c_int(len(models)), _p(qpos), _p(qvel), _p(target), C.c_int(K), C.c_int(H),
-                      _p(mean), _p(noise) if noise is not None else nul, _p(costs), _p(actions),
-                      _p(qv) if qv is not None else nul, _p(nobs) if nobs is not None else nul,
-                      _p(ncon, C.c_int), C.c_int(nthreads))
+    lib().ora_rollout_cl(arr, C.c_int(len(models)), _p(qpos), _p(qvel), _p(target), C.c_int(K), C.c_int(H),
+                         _p(mean), _p(noise) if noise is not None else nul, _p(costs), _p(actions),
+                         _p(qv) if qv is not None else nul, _p(nobs) if nobs is not None else nul,
+                         _p(ncon, C.c_int), C.c_int(nthreads), _p(policy_w) if policy_w is not None else nul)
     out = dict(costs=costs, actions=actions, ncon=ncon)
     if qv is not None:
         out["qv"] = qv

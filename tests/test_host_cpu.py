@@ -270,7 +270,7 @@ def test_ctypes_structs_match_header_layout():
     """sizeof and the offset of the last field of every argument struct, C compiler vs ctypes mirror."""
     import ctypes
     from mjmpc_b200 import _lib
-    pairs = [("mjb_rollout_args", _lib.RolloutArgs, "noise_zero_last"), ("mjb_pendulum_args", _lib.PendulumArgs, "states_out"),
+    pairs = [("mjb_rollout_args", _lib.RolloutArgs, "closed_loop"), ("mjb_pendulum_args", _lib.PendulumArgs, "states_out"),
              ("mjb_noise_args", _lib.NoiseArgs, "out_sj"), ("mjb_softmax_args", _lib.SoftmaxArgs, "q_st"),
              ("mjb_combine_args", _lib.CombineArgs, "stats"), ("mjb_elite_args", _lib.EliteArgs, "partial"),
              ("mjb_elite_combine_args", _lib.EliteCombineArgs, "cov"), ("mjb_mppi_batched_args", _lib.MppiBatchedArgs, "value"),
@@ -383,3 +383,68 @@ def test_rank_one_repair_settles_misjudged_rows_on_the_host(compiled_model, host
     warp = t.reshape(K // 32, 32, H * 2).max(axis=1)
     assert (warp >= 3).mean() < 0.10, (warp >= 3).mean()
     assert np.isfinite(qv).all()
+
+
+# ---- closed-loop linear rollouts (gym_env_wrapper.py:129-136) --------------------------------------------------
+def _linear_policy(seed, scale=0.1):
+    """Random feedback gains, small enough that the closed loop does not amplify rounding differences between
+    two formulations of the dynamics by more than a few orders of magnitude over the horizon."""
+    rng = np.random.default_rng(seed)
+    W = scale * rng.normal(0, 1, (21, 7))
+    W[14:20] *= 2.0             # the hand / hand-target rows matter for reaching
+    return W
+
+
+def test_oracle_closed_loop_follows_the_reference_loop(compiled_model, oracle_model):
+    """ora_rollout_cl against the reference's loop written out in Python on top of the oracle's own single
+    steps: curr_obs = get_obs() at the set state (fresh kinematics), u = mean.T @ [obs; 1] + noise,
+    curr_obs = next_obs (stale hand position of the step's last forward pass)."""
+    from oracle import mjstep
+    K, H = 6, 10
+    st = synthetic_state(compiled_model, 2)
+    W = _linear_policy(0)
+    noise = 0.5 * reference_noise(K, H, 7, 3)
+    out = mjstep.rollout(oracle_model, st["qp"], st["qv"], st["target_pos"], None, noise, want_obs=True, policy_w=W)
+    tgt = st["target_pos"]
+    for k in range(K):
+        q, v = st["qp"].copy(), st["qv"].copy()
+        hand = oracle_model.mass_bias(q, v)[2]
+        obs = np.concatenate([q, v, hand, hand - tgt])
+        for t in range(H):
+            u = W.T @ np.append(obs, 1.0) + noise[k, t]
+            # BLAS and the C loop sum W'obs in different orders; the feedback loop amplifies the last-bit difference
+            np.testing.assert_allclose(out["actions"][k, t], u, rtol=1e-9, atol=1e-10)
+            for s in range(2):
+                hand = oracle_model.mass_bias(q, v)[2]          # kinematics before this substep's integration
+                q, v, _, _ = oracle_model.substep(q, v, u)
+            obs = np.concatenate([q, v, hand, hand - tgt])
+            np.testing.assert_allclose(out["next_observations"][k, t], obs, rtol=1e-9, atol=1e-10)
+            d = hand - tgt
+            np.testing.assert_allclose(out["costs"][k, t], np.abs(d).sum() + 5 * np.linalg.norm(d), rtol=1e-9)
+    # a policy with only the bias row is an open-loop rollout with a constant mean
+    Wb = np.zeros((21, 7)); Wb[20] = [0.3, -0.2, 0.1, 0.0, 0.2, -0.1, 0.05]
+    a = mjstep.rollout(oracle_model, st["qp"], st["qv"], tgt, None, noise, policy_w=Wb)
+    b = mjstep.rollout(oracle_model, st["qp"], st["qv"], tgt, np.tile(Wb[20], (H, 1)), noise)
+    np.testing.assert_array_equal(a["costs"], b["costs"])
+
+
+@pytest.mark.parametrize("case", ["interior", "reset"])
+def test_closed_loop_device_math_on_host_matches_oracle(case, compiled_model, oracle_model, hostcheck):
+    from oracle import mjstep
+    P = compiled_model.chain.params
+    K, H = 96, 24
+    st = synthetic_state(compiled_model, 5)
+    q0, v0 = (st["qp"], st["qv"]) if case == "interior" else (np.zeros(7), np.zeros(7))
+    tgt = st["target_pos"]
+    W = _linear_policy(1)
+    noise = np.ascontiguousarray(0.5 * reference_noise(K, H, 7, 9))
+    ref = mjstep.rollout(oracle_model, q0, v0, tgt, None, noise, want_traj=True, nthreads=4, policy_w=W)
+    costs = np.zeros((K, H)); qv = np.zeros((K, H, 14)); act = np.zeros((K, H, 7))
+    hostcheck.hostcheck_rollout_cl(_p(P), _p(np.ascontiguousarray(q0)), _p(np.ascontiguousarray(v0)), _p(tgt), K, H,
+                                   _p(np.ascontiguousarray(W)), _p(noise), _p(costs), _p(qv), _p(act))
+    # north-star tolerance: 1e-8 relative over the horizon (the feedback loop amplifies the ~1e-13 per-step
+    # difference between the link-frame and the world-frame formulation)
+    scale = np.abs(ref["qv"]).max(axis=(0, 1))
+    assert (np.abs(qv - ref["qv"]).max(axis=(0, 1)) / scale).max() < 1e-8
+    np.testing.assert_allclose(costs, ref["costs"], rtol=1e-8)
+    np.testing.assert_allclose(act, ref["actions"], rtol=1e-8, atol=1e-9)

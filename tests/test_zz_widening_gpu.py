@@ -35,3 +35,72 @@ def test_continual_reacher_redraws_target_every_50_plant_steps():
     env.step(np.zeros(7))
     np.testing.assert_array_equal(env.target_pos, old)
     env.close()
+
+
+def _linear_policy(seed, scale=0.1):
+    rng = np.random.default_rng(seed)
+    W = scale * rng.normal(0, 1, (21, 7))
+    W[14:20] *= 2.0
+    return W
+
+
+@pytest.mark.parametrize("case", ["interior", "reset"])
+def test_closed_loop_linear_rollout_matches_oracle(case):
+    """mode="closed_loop_linear" (gym_env_wrapper.py:129-136) through the C ABI against the CPU oracle on the same
+    noise: actions (= policy output + noise), trajectories and costs within the north-star 1e-8."""
+    import torch
+    from conftest import reference_noise, synthetic_state
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    from mjmpc_b200.envs.model import compile_model, reacher7dof_spec
+    from oracle import mjstep
+    cm = compile_model(reacher7dof_spec())
+    om = mjstep.OracleModel(cm.tree)
+    env = GpuReacherVecEnv(cm)
+    K, H = 256, 16
+    st = synthetic_state(cm, 5)
+    if case == "reset":
+        st = dict(st, qp=np.zeros(7), qv=np.zeros(7))
+    W = _linear_policy(1)
+    noise = np.ascontiguousarray(0.5 * reference_noise(K, H, 7, 9))
+    ref = mjstep.rollout(om, st["qp"], st["qv"], st["target_pos"], None, noise, want_traj=True, want_obs=True,
+                         nthreads=4, policy_w=W)
+    env.set_env_state(st)
+    out = env.rollout_device(K, H, torch.from_numpy(W).cuda(), torch.from_numpy(noise).cuda(), want_traj=True,
+                             want_obs=True, closed_loop=True)
+    scale = np.abs(ref["qv"]).max(axis=(0, 1))
+    assert (np.abs(out["qv"].cpu().numpy() - ref["qv"]).max(axis=(0, 1)) / scale).max() < 1e-8
+    np.testing.assert_allclose(out["actions"].cpu().numpy(), ref["actions"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(out["costs"].cpu().numpy(), ref["costs"], rtol=1e-8)
+    np.testing.assert_allclose(out["next_observations"].cpu().numpy(), ref["next_observations"], rtol=1e-8, atol=1e-9)
+    # a bias-only policy is the open-loop rollout with a constant mean: bit-identical through the same kernel
+    Wb = np.zeros((21, 7)); Wb[20] = [0.3, -0.2, 0.1, 0.0, 0.2, -0.1, 0.05]
+    a = env.rollout_device(K, H, torch.from_numpy(Wb).cuda(), torch.from_numpy(noise).cuda(), closed_loop=True)
+    b = env.rollout_device(K, H, torch.from_numpy(np.tile(Wb[20], (H, 1))).cuda(), torch.from_numpy(noise).cuda(),
+                           want_ncon=True)
+    assert torch.equal(a["costs"], b["costs"]) and torch.equal(a["actions"], b["actions"])
+    env.close()
+
+
+def test_closed_loop_linear_through_the_reference_rollout_fn():
+    """The closure contract (examples/example_mpc.py:112-133) with numpy in / numpy out, as CLGaussianMPC calls it
+    (clgaussian_mpc.py:104-106): observations[0, 0] is the observation at the set state."""
+    from conftest import reference_noise, synthetic_state
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    from mjmpc_b200.envs.model import compile_model, forward_kinematics, reacher7dof_spec
+    cm = compile_model(reacher7dof_spec())
+    env = GpuReacherVecEnv(cm)
+    st = synthetic_state(cm, 8)
+    env.set_env_state(st)
+    K, H = 64, 8
+    W = _linear_policy(2)
+    noise = 0.3 * reference_noise(K, H, 7, 4)
+    traj = env.rollout_fn(K, H, W, noise, mode="closed_loop_linear")
+    assert traj["observations"].shape == (K, H, 20) and traj["actions"].shape == (K, H, 7)
+    hand = forward_kinematics(cm.tree, st["qp"])["hand"]
+    obs0 = np.concatenate([st["qp"], st["qv"], hand, hand - st["target_pos"]])
+    np.testing.assert_allclose(traj["observations"][0, 0], obs0, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(traj["actions"][:, 0], (W.T @ np.append(obs0, 1.0))[None] + noise[:, 0], rtol=1e-10, atol=1e-12)
+    np.testing.assert_array_equal(traj["observations"][:, 1:], traj["next_observations"][:, :-1])
+    with pytest.raises(NotImplementedError):
+        env.rollout_fn(K, H, W, noise, mode="closed_loop_nn")
+    env.close()
