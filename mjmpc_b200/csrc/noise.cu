@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(128) noise_kernel(mjb_noise_args a) {
 
 }  // namespace mjb
 
+#ifndef MJB_HOST_EMU
 extern "C" int mjb_generate_noise(const mjb_noise_args* a, void* stream) {
     MJB_REQUIRE(a && a->cov && a->out, "mjb_generate_noise: null pointer");
     MJB_REQUIRE(a->K >= 0 && a->H >= 1, "mjb_generate_noise: bad shape K=%d H=%d", a->K, a->H);
@@ -64,3 +65,4 @@ extern "C" int mjb_generate_noise(const mjb_noise_args* a, void* stream) {
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;
 }
+#endif  // MJB_HOST_EMU

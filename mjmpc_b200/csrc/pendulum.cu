@@ -35,6 +35,7 @@ __global__ void rollout_pendulum_kernel(mjb_pendulum_args a) {
 }
 }  // namespace mjb
 
+#ifndef MJB_HOST_EMU
 extern "C" int mjb_rollout_pendulum(const mjb_pendulum_args* a, void* stream) {
     MJB_REQUIRE(a && a->state && a->mean && a->costs, "mjb_rollout_pendulum: null pointer");
     MJB_REQUIRE(a->K >= 1 && a->H >= 1, "mjb_rollout_pendulum: K and H must be positive");
@@ -44,3 +45,4 @@ extern "C" int mjb_rollout_pendulum(const mjb_pendulum_args* a, void* stream) {
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;
 }
+#endif  // MJB_HOST_EMU

@@ -37,7 +37,11 @@ __device__ __forceinline__ void normal_pair32(unsigned a, unsigned b, double& z0
     const float u2 = (float)(b >> 8) * 5.9604644775390625e-08f;      // [0,1), 2^-24: exact in FP32
     const float r2 = -1.3862943611198906f * __log2f(fminf(u1, 1.0f));   // -2 ln u1
     float rad;
+#if defined(__CUDA_ARCH__)
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(r2));
+#else
+    rad = sqrtf(r2);                   // host emulation of the kernels (tests/hostcheck/kernel_emu.cpp)
+#endif
     // cos(2 pi u2) = -cos(2 pi u2 - pi): the shifted angle is uniform on [-pi, pi)
     const float ang = fmaf(u2, 6.2831853071795865f, -3.1415926535897932f);
     z0 = (double)(-rad * __cosf(ang)); z1 = (double)(-rad * __sinf(ang));

@@ -32,11 +32,16 @@ struct ConstParams {
 struct SmemScratch {
     double* base;
     // asynchronous 8-byte global -> shared copy into a slot (LDGSTS: no register, no stall until waited for)
+#if defined(__CUDA_ARCH__)
     __device__ __forceinline__ void fetch(int slot, const double* g) const {
         const unsigned dst = (unsigned)__cvta_generic_to_shared(base + slot * MJB_ROLLOUT_BLOCK);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g) : "memory");
     }
     __device__ __forceinline__ static void fetch_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#else       // host pass of nvcc and the host emulation of the kernels (tests/hostcheck/kernel_emu.cpp): a plain copy
+    void fetch(int slot, const double* g) const { base[slot * MJB_ROLLOUT_BLOCK] = *g; }
+    static void fetch_wait() {}
+#endif
     __device__ __forceinline__ double ld(int slot) const { return base[slot * MJB_ROLLOUT_BLOCK]; }
     __device__ __forceinline__ void st(int slot, double v) { base[slot * MJB_ROLLOUT_BLOCK] = v; }
 };
@@ -202,6 +207,7 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
 
 }  // namespace mjb
 
+#ifndef MJB_HOST_EMU
 extern "C" int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a, void* stream) {
     MJB_REQUIRE(m && a, "mjb_rollout_reacher: null handle");
     MJB_REQUIRE(a->K >= 1 && a->H >= 1, "mjb_rollout_reacher: K and H must be positive (K=%d H=%d)", a->K, a->H);
@@ -247,3 +253,4 @@ extern "C" int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;
 }
+#endif  // MJB_HOST_EMU
