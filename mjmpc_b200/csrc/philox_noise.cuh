@@ -35,7 +35,9 @@ struct Philox {
 __device__ __forceinline__ void normal_pair32(unsigned a, unsigned b, double& z0, double& z1) {
     const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;    // (0,1], 2^-32
     const float u2 = (float)(b >> 8) * 5.9604644775390625e-08f;      // [0,1), 2^-24: exact in FP32
-    const float r2 = -1.3862943611198906f * __log2f(fminf(u1, 1.0f));   // -2 ln u1
+    // -2 ln u1; lg2.approx has an ABSOLUTE error of ~2^-22, so just below u1 = 1 its sign can be wrong:
+    // clamp, or the square root of a tiny negative number would put a NaN into one sample in ~10^7
+    const float r2 = fmaxf(-1.3862943611198906f * __log2f(fminf(u1, 1.0f)), 0.0f);
     float rad;
 #if defined(__CUDA_ARCH__)
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(r2));
