@@ -1,0 +1,27 @@
+"""The `-m gpu` test functions executed WITHOUT a GPU: a child pytest with MJB_TEST_EMU=1 runs them against
+tests/hostcheck/libmjmpc_b200_emu.so -- the product's .cu sources (kernels and launch code) built for the host --
+with torch handing out CPU tensors (tests/helpers/emu_device.py).  Whole episodes, BASELINE sizes, CUDA-graph
+replay and real NCCL ranks are skipped there (tests/conftest.py lists them); everything else -- rollout parity
+with the oracle, noise, all five controllers against the reference goldens, batched instances, logical shards,
+the VecEnv adaptor, closed-loop rollouts -- must pass before the suite ever reaches the GPU box.  A child
+process, because the shim patches torch globally."""
+import os
+import re
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def test_gpu_marked_tests_pass_on_the_host_emulation():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "helpers"))
+    import emu_device
+    emu_device.build_lib()                 # once, here: the xdist workers below must not race to build it
+    env = dict(os.environ, MJB_TEST_EMU="1")
+    env.pop("MJB_TEST_EMU_ALL", None)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-q", "-x",
+                        "-n", "4", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=1500)
+    tail = r.stdout[-3000:] + r.stderr[-1500:]
+    assert r.returncode == 0, tail
+    m = re.search(r"(\d+) passed", r.stdout)
+    assert m and int(m.group(1)) >= 55, tail          # the suite really ran (not everything skipped)

@@ -116,7 +116,7 @@ def test_rollout_bad_arguments(compiled_model):
     with pytest.raises(AssertionError):      # subproc_vec_env.py:162
         env.rollout_device(12, 4, mean, torch.zeros(12, 4, 7, dtype=torch.float64, device="cuda"))
     with pytest.raises(NotImplementedError):
-        env.rollout(8, 4, np.zeros((4, 7)), np.zeros((8, 4, 7)), mode="closed_loop_linear")
+        env.rollout(8, 4, np.zeros((4, 7)), np.zeros((8, 4, 7)), mode="closed_loop_nn")
     env.close()
 
 
