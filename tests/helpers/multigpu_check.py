@@ -17,15 +17,25 @@ sys.path.insert(0, ROOT)
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    emu = os.environ.get("MJB_TEST_EMU") == "1"
+    if emu:
+        # CPU dry run (tests/test_shard_gloo.py): the same controllers on the host build of the kernels
+        # (tests/helpers/emu_device.py), ranks connected by gloo, every rank on "device 0"
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import emu_device
+        emu_device.install()
+        local = 0
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from mjmpc_b200.control import CEM, DMDMPC, MPPI, PFMPC, RandomShooting
     from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
     from mjmpc_b200.envs.model import compile_model, reacher7dof_spec
     from mjmpc_b200.utils.shard import ShardContext
     compiled = compile_model(reacher7dof_spec())
     shard = ShardContext(rank, world)
-    K, H = 2048, 16
+    K, H = int(os.environ.get("MJB_CHECK_K", "2048")), 16
     common = dict(d_state=25, d_obs=20, d_action=7, action_lows=-np.ones(7), action_highs=np.ones(7), horizon=H,
                   num_particles=K, gamma=0.98, n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=5, device=local)
     cases = {

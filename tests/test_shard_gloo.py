@@ -79,6 +79,27 @@ def test_two_rank_gloo_sharded_softmax_update():
     assert res == {0: "ok", 1: "ok"}, res
 
 
+def test_two_rank_gloo_sharded_controllers_match_unsharded_on_the_host_emulation():
+    """The N > 1 path end to end on CPU: tests/helpers/multigpu_check.py (the script the 2-GPU test launches
+    with NCCL) under torchrun with two gloo ranks, the controllers running on the host build of the product's
+    kernels (tests/helpers/emu_device.py).  All five controllers: a sharded controller that owns K/2 particles
+    and exchanges partials / costs / elite moments / particles must reproduce the unsharded one -- actions,
+    mean and covariance to 1e-9, elite, argmin and resampling indices exactly -- and every rank must end with
+    bit-identical parameters."""
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tests", "helpers"))
+    import emu_device
+    emu_device.build_lib()
+    env = dict(os.environ, MJB_TEST_EMU="1", MJB_P2P="0", MJB_CHECK_K="512", OMP_NUM_THREADS="1")
+    port = 29600 + (os.getpid() % 300)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "helpers", "multigpu_check.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for name in ("mppi", "dmd", "cem", "rs", "pfmpc"):
+        assert "multigpu %-6s ok" % name in r.stdout, r.stdout[-2000:]
+
+
 def test_single_process_shard_context():
     from mjmpc_b200.utils.shard import ShardContext
     s = ShardContext()
