@@ -30,8 +30,7 @@ _EMU_IMPOSSIBLE = {
 }
 _EMU_SLOW = {
     "test_fullsize_gpu.py": "BASELINE sizes",
-    "test_cem_pendulum_config2_runs_and_improves": "K=4096 H=64 over a whole episode",
-    "test_closed_loop_reaches_target": "whole episodes",
+    "test_cem_pendulum_config2_runs_and_improves": "K=4096 H=64 over a whole episode (40 s)",
 }
 
 

@@ -1,81 +1,178 @@
-// TEST HARNESS (CPU): a minimal block-level emulation of CUDA for the product's reduction kernels (update.cu).
-// Every simulated CUDA thread of a block is an OS thread; blocks run one after another.  __syncthreads is a
-// std::barrier that exiting threads drop out of, warp shuffles exchange through a per-warp buffer behind a
-// per-warp barrier, atomics are real atomics.  Enough for kernels whose warps call shuffles uniformly (every
-// live lane of the warp together) -- which is what update.cu does; __match_any_sync degrades to "no peers"
-// (the warp-aggregated histogram update becomes one atomic per lane: same result).  Not a product path.
+// TEST HARNESS (CPU): a minimal block-level emulation of CUDA for the product's kernels and launch code.
+// Every simulated CUDA thread of a block is a FIBER (ucontext) on the OS thread that runs the block; a small
+// pool of OS threads runs the blocks of a launch side by side.  __syncthreads and the warp shuffles are
+// cooperative barriers (a fiber that reaches one yields; the barrier opens when every live thread of the block /
+// warp waits at it; exited threads drop out), __shared__ variables are thread_local (= one copy per running
+// block), atomics on global memory are real atomics because blocks run concurrently.  A barrier that can never
+// open (divergent __syncthreads) aborts with a message instead of hanging.  Enough for kernels whose warps call
+// shuffles uniformly (every live lane of the warp together) -- which is what the product's kernels do;
+// __match_any_sync degrades to "no peers" (the warp-aggregated histogram update becomes one atomic per lane:
+// same result).  Not a product path.
 #pragma once
 #include <atomic>
-#include <barrier>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
-#include <memory>
 #include <thread>
 #include <vector>
+#include <sys/mman.h>
+#include <ucontext.h>
 #include <cuda_runtime.h>          // dim3, cudaStream_t, error codes (host-side declarations only)
 
 namespace emu {
 struct Idx { unsigned x, y, z; };
-struct Warp { std::unique_ptr<std::barrier<>> bar; unsigned long long buf[32]; int lanes; };
-struct Block { std::unique_ptr<std::barrier<>> bar; std::vector<Warp> warps; };
-inline thread_local Idx t_thread;
-inline thread_local Block* t_block;
-inline Idx g_block, g_bdim, g_gdim;
-inline void* g_dyn_smem;
+enum { RUN = 0, AT_BLOCK = 1, AT_WARP = 2, DONE = 3 };
+struct Fiber { ucontext_t ctx; Idx tid; int state; };
+struct BlockCtx {
+    ucontext_t sched;
+    std::vector<Fiber> fib;
+    std::vector<int> warp_live, warp_wait;
+    std::vector<unsigned long long> wbuf;       // [warp][32] shuffle exchange
+    int n = 0, cur = 0, live = 0, block_wait = 0;
+    Idx block{0, 0, 0};
+    void* dyn = nullptr;
+    void (*call)(void*) = nullptr;
+    void* fobj = nullptr;
+    char* stacks = nullptr;
+    size_t stacks_bytes = 0;
+};
+constexpr size_t kStack = 256 * 1024;
+inline thread_local BlockCtx* t_ctx = nullptr;
+inline Idx g_bdim, g_gdim;
 
-template <class F> void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, F f) {
-    const unsigned n = block.x * block.y * block.z;
-    std::vector<unsigned long long> dyn(smem / 8 + 2);
-    g_bdim = {block.x, block.y, block.z}; g_gdim = {grid.x, grid.y, grid.z};
-    for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
-        g_block = {bx, by, bz}; g_dyn_smem = dyn.data();
-        Block ctx;
-        ctx.bar = std::make_unique<std::barrier<>>(n);
-        ctx.warps.resize((n + 31) / 32);
-        for (unsigned w = 0; w < ctx.warps.size(); w++) {
-            ctx.warps[w].lanes = (int)std::min(32u, n - 32 * w);
-            ctx.warps[w].bar = std::make_unique<std::barrier<>>(ctx.warps[w].lanes);
-        }
-        std::vector<std::thread> th;
-        th.reserve(n);
-        for (unsigned t = 0; t < n; t++)
-            th.emplace_back([&ctx, &f, t, block] {
-                t_thread = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-                t_block = &ctx;
-                f();
-                ctx.warps[t >> 5].bar->arrive_and_drop();       // exited lanes no longer take part
-                ctx.bar->arrive_and_drop();
-            });
-        for (auto& x : th) x.join();
+inline void release_if_complete(BlockCtx& c, int w) {
+    if (c.live > 0 && c.block_wait == c.live) {
+        for (auto& f : c.fib) if (f.state == AT_BLOCK) f.state = RUN;
+        c.block_wait = 0;
+    }
+    if (w >= 0 && c.warp_live[w] > 0 && c.warp_wait[w] == c.warp_live[w]) {
+        for (int l = 32 * w; l < 32 * w + 32 && l < c.n; l++) if (c.fib[l].state == AT_WARP) c.fib[l].state = RUN;
+        c.warp_wait[w] = 0;
     }
 }
-inline unsigned linear_tid() { return t_thread.x + g_bdim.x * (t_thread.y + g_bdim.y * t_thread.z); }
+inline void yield_at(int what) {
+    BlockCtx& c = *t_ctx;
+    Fiber& f = c.fib[c.cur];
+    f.state = what;
+    const int w = c.cur >> 5;
+    if (what == AT_BLOCK) c.block_wait++; else c.warp_wait[w]++;
+    release_if_complete(c, w);
+    if (f.state == RUN) return;                 // the barrier opened with this arrival
+    swapcontext(&f.ctx, &c.sched);
+}
+inline void fiber_main() {
+    BlockCtx& c = *t_ctx;
+    c.call(c.fobj);
+    Fiber& f = c.fib[c.cur];
+    f.state = DONE;
+    c.live--;
+    c.warp_live[c.cur >> 5]--;
+    release_if_complete(c, c.cur >> 5);         // exited threads no longer take part
+    swapcontext(&f.ctx, &c.sched);
+}
+inline void run_block(BlockCtx& c, dim3 block, unsigned bx, unsigned by, unsigned bz, size_t smem) {
+    const int n = (int)(block.x * block.y * block.z), nw = (n + 31) / 32;
+    c.n = n; c.live = n; c.block_wait = 0; c.block = {bx, by, bz};
+    if ((int)c.fib.size() < n) c.fib.resize(n);
+    c.warp_live.assign(nw, 0); c.warp_wait.assign(nw, 0); c.wbuf.assign((size_t)nw * 32, 0);
+    if (c.stacks_bytes < (size_t)n * kStack) {
+        if (c.stacks) munmap(c.stacks, c.stacks_bytes);
+        c.stacks_bytes = (size_t)n * kStack;
+        c.stacks = (char*)mmap(nullptr, c.stacks_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (c.stacks == MAP_FAILED) { std::fprintf(stderr, "block_emu: cannot map fiber stacks\n"); std::abort(); }
+    }
+    std::vector<unsigned long long> dyn(smem / 8 + 2);
+    c.dyn = dyn.data();
+    for (int t = 0; t < n; t++) {
+        Fiber& f = c.fib[t];
+        f.tid = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+        f.state = RUN;
+        c.warp_live[t >> 5]++;
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = c.stacks + (size_t)t * kStack;
+        f.ctx.uc_stack.ss_size = kStack;
+        f.ctx.uc_link = nullptr;
+        makecontext(&f.ctx, (void (*)())fiber_main, 0);
+    }
+    while (c.live > 0) {
+        bool progressed = false;
+        for (int t = 0; t < n; t++) {
+            if (c.fib[t].state != RUN) continue;
+            c.cur = t;
+            progressed = true;
+            swapcontext(&c.sched, &c.fib[t].ctx);
+        }
+        if (!progressed) {
+            std::fprintf(stderr, "block_emu: deadlock in block (%u,%u,%u): %d live threads, %d at __syncthreads -- "
+                                 "a barrier or warp shuffle is not reached by every live thread\n", bx, by, bz, c.live, c.block_wait);
+            std::abort();
+        }
+    }
+}
+
+template <class F> void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, F f) {
+    g_bdim = {block.x, block.y, block.z}; g_gdim = {grid.x, grid.y, grid.z};
+    const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+    std::atomic<unsigned long long> next{0};
+    auto worker = [&] {
+        BlockCtx c;
+        c.call = [](void* p) { (*(F*)p)(); };
+        c.fobj = (void*)&f;
+        t_ctx = &c;
+        for (;;) {
+            const unsigned long long b = next.fetch_add(1);
+            if (b >= nblocks) break;
+            run_block(c, block, (unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((unsigned long long)grid.x * grid.y)), smem);
+        }
+        if (c.stacks) munmap(c.stacks, c.stacks_bytes);
+        t_ctx = nullptr;
+    };
+    static const unsigned hw = [] { const char* e = std::getenv("MJB_EMU_THREADS"); unsigned n = e ? (unsigned)std::atoi(e) : std::thread::hardware_concurrency(); return n ? n : 1u; }();
+    const unsigned nthreads = (unsigned)std::min<unsigned long long>(nblocks, hw);
+    if (nthreads <= 1) {
+        BlockCtx* outer = t_ctx;
+        worker();
+        t_ctx = outer;
+        return;
+    }
+    std::vector<std::thread> th;
+    th.reserve(nthreads);
+    for (unsigned i = 0; i < nthreads; i++) th.emplace_back(worker);
+    for (auto& x : th) x.join();
+}
+inline void* dyn_smem() { return t_ctx->dyn; }
+inline const Idx& thread_idx() { return t_ctx->fib[t_ctx->cur].tid; }
+inline const Idx& block_idx() { return t_ctx->block; }
+inline unsigned linear_tid() { return (unsigned)t_ctx->cur; }
 template <class T, class S> T shfl(T v, S src_of_lane) {
-    Warp& w = t_block->warps[linear_tid() >> 5];
-    const int lane = (int)(linear_tid() & 31);
+    BlockCtx& c = *t_ctx;
+    const int w = c.cur >> 5, lane = c.cur & 31;
+    const int lanes = std::min(32, c.n - 32 * w);
     unsigned long long raw = 0;
     std::memcpy(&raw, &v, sizeof v);
-    w.buf[lane] = raw;
-    w.bar->arrive_and_wait();
+    c.wbuf[(size_t)w * 32 + lane] = raw;
+    yield_at(AT_WARP);
     const int s = src_of_lane(lane);
     T r = v;
-    if (s >= 0 && s < w.lanes) { raw = w.buf[s]; std::memcpy(&r, &raw, sizeof r); }
-    w.bar->arrive_and_wait();
+    if (s >= 0 && s < lanes) { raw = t_ctx->wbuf[(size_t)w * 32 + s]; std::memcpy(&r, &raw, sizeof r); }
+    yield_at(AT_WARP);
     return r;
 }
 }  // namespace emu
 
-#define threadIdx emu::t_thread
-#define blockIdx emu::g_block
+#define g_dyn_smem dyn_smem()          // emu::g_dyn_smem in generated code
+#define threadIdx emu::thread_idx()
+#define blockIdx emu::block_idx()
 #define blockDim emu::g_bdim
 #define gridDim emu::g_gdim
 #undef __shared__
-#define __shared__ static
+#define __shared__ static thread_local
 #ifndef __launch_bounds__
 #define __launch_bounds__(...)
 #endif
-static inline void __syncthreads() { emu::t_block->bar->arrive_and_wait(); }
+static inline void __syncthreads() { emu::yield_at(emu::AT_BLOCK); }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int o) { return emu::shfl(v, [o](int l) { return l + o; }); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int o) { return emu::shfl(v, [o](int l) { return l ^ o; }); }
 static inline unsigned __activemask() { return 1u << (emu::linear_tid() & 31); }
