@@ -301,6 +301,34 @@ int mjb_pf_shift(double* samples, long long sk, long long st, long long sj, cons
                  long long dt, long long dj, int K, int H, int d, int base_action, const double* random_row,
                  void* stream);
 
+/* ---- one whole MPC step of the softmax controllers (MPPI, DMD-MPC) in ONE host call: the loop of
+ * Controller.optimize (mjmpc/control/controller.py:207-257) = n_iters x { generate_rollouts
+ * (olgaussian_mpc.py:95-114), _update_distribution (mppi.py:69-97, gaussian_dmd.py:65-91) }, next action
+ * = mean[0] (olgaussian_mpc.py:69-78), _shift (:116-129; gaussian_dmd.py:106-113).  Launches exactly the
+ * kernels of mjb_generate_noise, mjb_rollout_reacher, mjb_softmax_partials, mjb_softmax_combine (or
+ * mjb_softmax_exchange_combine), mjb_shift_mean and mjb_cov_add_diag, in that order on `stream`: results are
+ * bit-identical to calling them one by one; the host time between launches goes away (it bounds the sharded
+ * multi-GPU step, which cannot replay a CUDA graph).  The argument blocks are the ones of the separate entry
+ * points and are read during the call only. */
+typedef struct {
+    int n_iters;
+    const mjb_noise_args* noise;       /* K2, re-run every iteration (same (seed, step): same samples; the zero
+                                          control sequence follows the updated mean); NULL = no noise kernel */
+    const mjb_model* model;
+    const mjb_rollout_args* rollout;
+    const mjb_softmax_args* softmax;
+    const mjb_combine_args* combine;   /* must apply the update (mean != NULL); n_shards == 1: partials ==
+                                          softmax->partials */
+    void* const* peer_bufs_dev;        /* n_shards > 1: buffers of mjb_softmax_exchange_combine */
+    int rank;
+    unsigned long long seq;            /* exchange sequence number of iteration 0; iteration i uses seq + i */
+    double* action_out;                /* (d,) device <- mean[0] after the last update, before the shift; or NULL */
+    int shift;                         /* hotstart: shift the mean sequence afterwards */
+    int base_action;                   /* MJB_BASE_NULL or MJB_BASE_REPEAT */
+    double cov_shift_beta;             /* != 0: cov += beta * I after the shift (DMD-MPC with update_cov) */
+} mjb_mpc_step_args;
+int mjb_softmax_mpc_step(const mjb_mpc_step_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

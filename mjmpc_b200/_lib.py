@@ -172,6 +172,16 @@ class PfBatchedArgs(C.Structure):
     ]
 
 
+class MpcStepArgs(C.Structure):
+    _fields_ = [
+        ("n_iters", C.c_int),
+        ("noise", C.POINTER(NoiseArgs)), ("model", C.c_void_p), ("rollout", C.POINTER(RolloutArgs)),
+        ("softmax", C.POINTER(SoftmaxArgs)), ("combine", C.POINTER(CombineArgs)),
+        ("peer_bufs_dev", C.c_void_p), ("rank", C.c_int), ("seq", C.c_ulonglong),
+        ("action_out", C.c_void_p), ("shift", C.c_int), ("base_action", C.c_int), ("cov_shift_beta", C.c_double),
+    ]
+
+
 COV_NONE, COV_DIAG, COV_FULL = 0, 1, 2
 RETURNS_CTG, RETURNS_TD_LAMBDA = 0, 1
 BASE_ACTIONS = {"null": 0, "repeat": 1, "random": 2}
@@ -184,7 +194,7 @@ EXPORTS += [
     "mjb_elite_moments2", "mjb_elite_combine", "mjb_blend_best",
     "mjb_resample_indices", "mjb_gather_particles", "mjb_particle_mean", "mjb_particle_sub_mean",
     "mjb_shift_mean", "mjb_shift_mean_batched", "mjb_cov_add_diag", "mjb_pf_shift", "mjb_mppi_update_batched",
-    "mjb_pf_update_batched", "mjb_particle_sub_mean_batched",
+    "mjb_pf_update_batched", "mjb_particle_sub_mean_batched", "mjb_softmax_mpc_step",
 ]
 
 

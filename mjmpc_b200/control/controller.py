@@ -104,6 +104,11 @@ class Controller(ABC):
     def optimize(self, state, calc_val=False, hotstart=True):
         if self._graph is not None and not calc_val and hotstart:
             return self._optimize_graphed(state), 0.0
+        if not calc_val:
+            action = self._fused_step(state, hotstart)       # the whole step in one native call, when it can be
+            if action is not None:
+                self.num_steps += 1
+                return action.cpu().numpy().copy(), 0.0
         for _ in range(self.n_iters):
             trajectory = self.generate_rollouts(copy.deepcopy(state))
             self._update_distribution(trajectory)
@@ -127,6 +132,10 @@ class Controller(ABC):
         if self._graph is not None and hotstart:
             self._replay(state)
             return self._graph_action
+        action = self._fused_step(state, hotstart)
+        if action is not None:
+            self.num_steps += 1
+            return action.clone()
         for _ in range(self.n_iters):
             trajectory = self.generate_rollouts(state)
             self._update_distribution(trajectory)
@@ -193,7 +202,7 @@ class Controller(ABC):
 
     def _optimize_graphed(self, state):
         self._replay(state)
-        return self._graph_action.cpu().numpy()
+        return self._graph_action.cpu().numpy().copy()
 
     def get_optimal_value(self, state):
         """controller.py:259-275."""
@@ -231,6 +240,10 @@ class Controller(ABC):
             self.reset()
 
     # ---- helpers ------------------------------------------------------------------------------
+    def _fused_step(self, state, hotstart=True):
+        """Subclasses whose whole step fits one native call return the device action; None = step by step."""
+        return None
+
     def _first_action(self):
         return self._mean[0].clone()
 

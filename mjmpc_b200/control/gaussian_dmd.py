@@ -28,18 +28,23 @@ class DMDMPC(OLGaussianMPC):
         self.beta = beta
         self.update_cov = update_cov
 
+    def _cov_mode(self):
+        if not self.update_cov:
+            return _lib.COV_NONE
+        if self.cov_type == 'diagonal':
+            return _lib.COV_DIAG
+        if self.cov_type == 'full':
+            return _lib.COV_FULL
+        raise ValueError('Unidentified covariance type in update_distribution')
+
     def _update_distribution(self, trajectories):
         """gaussian_dmd.py:65-91."""
         costs, actions = self._traj(trajectories)
-        cov_mode = _lib.COV_NONE
-        if self.update_cov:
-            if self.cov_type == 'diagonal':
-                cov_mode = _lib.COV_DIAG
-            elif self.cov_type == 'full':
-                cov_mode = _lib.COV_FULL
-            else:
-                raise ValueError('Unidentified covariance type in update_distribution')
-        self._softmax_update(costs, actions, self.lam, cov_mode=cov_mode)
+        self._softmax_update(costs, actions, self.lam, cov_mode=self._cov_mode())
+
+    def _softmax_spec(self):
+        return dict(lam=float(self.lam), control_cost=False, time_based=False, cov_mode=self._cov_mode(),
+                    cov_shift_beta=float(self.beta) if self.update_cov else 0.0)
 
     def _shift(self):
         """gaussian_dmd.py:106-113: shift the mean; grow the covariance by beta*I if it is adapted."""

@@ -36,6 +36,10 @@ class MPPI(OLGaussianMPC):
         self._softmax_update(costs, actions, self.lam, control_cost=(self.alpha != 1),
                              time_based=bool(self.time_based_weights))
 
+    def _softmax_spec(self):
+        return dict(lam=float(self.lam), control_cost=(self.alpha != 1), time_based=bool(self.time_based_weights),
+                    cov_mode=_lib.COV_NONE, cov_shift_beta=0.0)
+
     def _batched_update(self, costs, actions, apply):
         """batch_size independent instances: one thread block per instance, no cross-instance reduction."""
         if self.time_based_weights:

@@ -182,6 +182,7 @@ class OLGaussianMPC(Controller):
         self._cov = self._to_device(np.diag(self.init_cov)).contiguous()
         self.gamma_seq = np.cumprod([1.0] + [self.gamma] * (self.horizon - 1)).reshape(1, self.horizon)
         self._buffers = {}
+        self.__dict__.pop("_fused_blocks", None)
 
     def _calc_val(self, trajectories):
         raise NotImplementedError("_calc_val not implemented")
@@ -202,6 +203,27 @@ class OLGaussianMPC(Controller):
         Returns the (2+2T,) stats tensor: value, global min, normalisers, minima.
         td = (td_lam, gamma, weight_seq, qvals or None): weights from MPPIQ's TD(lambda) returns instead of
         the discounted cost-to-go."""
+        a, c, P, stats, _ = self._softmax_blocks(costs, actions, lam, control_cost, time_based, cov_mode, apply, td)
+        L = _lib.lib()
+        _lib.check(L.mjb_softmax_partials(C.byref(a), _lib.stream_ptr()))
+        partials = self._buf("sm_partials", (P,))
+        px = self._peer_exchange(P)
+        if px is not None:
+            # fused: P2P stores into every peer's buffer + flag wait + rank-ordered combine in ONE kernel
+            _lib.check(L.mjb_softmax_exchange_combine(C.byref(c), _lib.ptr(partials), C.c_void_p(px.peer_ptrs_dev),
+                                                      C.c_int(self.shard.rank), C.c_ulonglong(px.next_seq()),
+                                                      _lib.stream_ptr()))
+        else:
+            allp = self.shard.all_gather(partials)
+            c.partials = allp.data_ptr()
+            _lib.check(L.mjb_softmax_combine(C.byref(c), _lib.stream_ptr()))
+        return stats
+
+    def _softmax_blocks(self, costs, actions, lam, control_cost=False, time_based=False, cov_mode=_lib.COV_NONE,
+                        apply=True, td=None):
+        """The mjb_softmax_args / mjb_combine_args blocks of one update over this controller's persistent
+        buffers: (phase-1 block, phase-2 block, partial length P, stats tensor, host arrays the blocks point
+        into).  The phase-2 block reads this rank's own partial vector until a caller points it elsewhere."""
         if self.batch_size > 1:
             raise NotImplementedError("batched instances are implemented for MPPI without time-based weights")
         L = _lib.lib()
@@ -215,12 +237,14 @@ class OLGaussianMPC(Controller):
         a.mean = self._mean.data_ptr()
         a.cov = self._cov.data_ptr()
         g = np.ascontiguousarray(self.gamma_seq.reshape(-1))
+        keep = [g]
         a.gamma_seq = g.ctypes.data
         a.lam = float(lam)
         a.control_cost, a.time_based, a.cov_mode = int(control_cost), int(time_based), int(cov_mode)
         if td is not None:
             td_lam, td_gamma, wseq, qvals = td
             wseq = np.ascontiguousarray(wseq, dtype=np.float64)     # host array, kept alive until the call returns
+            keep.append(wseq)
             a.returns, a.td_lam, a.td_gamma = _lib.RETURNS_TD_LAMBDA, float(td_lam), float(td_gamma)
             a.td_weight_seq = wseq.ctypes.data
             if qvals is not None:
@@ -229,27 +253,86 @@ class OLGaussianMPC(Controller):
         scratch = self._buf("sm_scratch", (int(L.mjb_softmax_scratch_doubles(kl, H, d, cov_mode)),))
         partials = self._buf("sm_partials", (P,))
         a.total, a.scratch, a.partials = total.data_ptr(), scratch.data_ptr(), partials.data_ptr()
-        _lib.check(L.mjb_softmax_partials(C.byref(a), _lib.stream_ptr()))
         stats = self._buf("sm_stats", (2 + 2 * T,))
         c = _lib.CombineArgs()
         c.H, c.d, c.n_shards, c.K_global = H, d, self.shard.world_size, self.num_particles
         c.lam, c.step_size = float(lam), float(self.step_size)
         c.time_based, c.cov_mode = int(time_based), int(cov_mode)
+        c.partials = partials.data_ptr()
         c.mean = self._mean.data_ptr() if apply else None
         c.cov = self._cov.data_ptr() if (apply and cov_mode != _lib.COV_NONE) else None
         c.stats = stats.data_ptr()
-        px = self._peer_exchange(P)
-        if px is not None:
-            # fused: P2P stores into every peer's buffer + flag wait + rank-ordered combine in ONE kernel
-            _lib.check(L.mjb_softmax_exchange_combine(C.byref(c), _lib.ptr(partials), C.c_void_p(px.peer_ptrs_dev),
-                                                      C.c_int(self.shard.rank), C.c_ulonglong(px.next_seq()),
-                                                      _lib.stream_ptr()))
-        else:
-            allp = self.shard.all_gather(partials)
-            c.partials = allp.data_ptr()
-            _lib.check(L.mjb_softmax_combine(C.byref(c), _lib.stream_ptr()))
         self._last_total = total
-        return stats
+        return a, c, P, stats, keep
+
+    # ---- the whole MPC step behind one native call -----------------------------------------------------
+    def _softmax_spec(self):
+        """dict(lam, control_cost, time_based, cov_mode, cov_shift_beta) when this controller's update is the
+        plain softmax reduction (MPPI, DMD-MPC); None otherwise."""
+        return None
+
+    def _fused_step(self, state, hotstart=True):
+        """One MPC step -- n_iters x (noise, rollout, softmax update), next action, shift -- through
+        ``mjb_softmax_mpc_step``: the same kernels on the same buffers as the step-by-step path (bit-identical
+        results), launched from one native call instead of ~10 Python-level ones.  Returns the (d,) device
+        action (a persistent buffer, overwritten by the next step), or None -- with nothing done -- when this
+        controller / backend / option set needs the step-by-step path.  ``state=None`` keeps the state the
+        backend already holds."""
+        spec = self._softmax_spec()
+        backend = getattr(self._rollout_fn, "backend", None)
+        if (spec is None or backend is None or not hasattr(backend, "rollout_args") or self.batch_size > 1
+                or self.fuse_noise or self.base_action not in ("null", "repeat") or self.sample_mode != 'mean'
+                or type(self).check_convergence is not Controller.check_convergence
+                or os.environ.get("MJB_FUSED_STEP", "1") == "0"):
+            return None
+        L = _lib.lib()
+        kl, H, d = self.local_particles, self.horizon, self.d_action
+        P = L.mjb_softmax_partial_doubles(H, d, int(spec["time_based"]), spec["cov_mode"])
+        px = self._peer_exchange(P)
+        if self.shard.world_size > 1 and px is None:
+            return None                 # NCCL all-gather between the two phases: host work inside the step
+        if state is not None:
+            self._set_sim_state_fn(copy.deepcopy(state))
+        key = (self._mean.data_ptr(), self._cov.data_ptr(), backend._state.data_ptr(), backend.model.handle.value,
+               kl, H, self.n_iters, tuple(sorted(spec.items())), self.step_size, self.base_action, hotstart,
+               tuple(self.filter_coeffs), self.use_zero_control_seq, self.seed_val, self.gamma)
+        blk = self.__dict__.get("_fused_blocks")
+        if blk is None or blk["key"] != key:
+            ns = self.noise_spec()
+            noise = self._buf("noise", (H, d, kl)).permute(2, 0, 1)
+            na, nkeep = control_utils.noise_args(ns.cov, ns.filter_coeffs, ns.shape, ns.base_seed, step=0,
+                                                 stream_id=ns.stream_id, k_offset=ns.k_offset, K_global=ns.K_global,
+                                                 zero_last_mean=ns.mean if ns.zero_last else None, out=noise,
+                                                 device=self.device)
+            costs = self._buf("fused_costs", (H, kl)).t()
+            actions = self._buf("fused_actions", (H, d, kl)).permute(2, 0, 1)
+            ra, rout = backend.rollout_args(kl, H, self._mean, noise, costs=costs, actions=actions)
+            sa, ca, _, stats, skeep = self._softmax_blocks(costs, actions, spec["lam"], spec["control_cost"],
+                                                           spec["time_based"], spec["cov_mode"])
+            st = _lib.MpcStepArgs()
+            st.n_iters = int(self.n_iters)
+            st.noise, st.rollout, st.softmax, st.combine = C.pointer(na), C.pointer(ra), C.pointer(sa), C.pointer(ca)
+            st.model = backend.model.handle
+            st.rank = self.shard.rank
+            st.peer_bufs_dev = px.peer_ptrs_dev if px is not None else None
+            action = self._buf("fused_action", (d,))
+            st.action_out = action.data_ptr()
+            st.shift = int(bool(hotstart))
+            st.base_action = _lib.BASE_ACTIONS[self.base_action]
+            st.cov_shift_beta = float(spec["cov_shift_beta"])
+            blk = dict(key=key, st=st, na=na, action=action, keep=(ra, sa, ca, nkeep, rout, skeep, stats, noise))
+            self._fused_blocks = blk
+        na = blk["na"]
+        if self._noise_step is not None:
+            na.offset, na.step_ptr = control_utils.noise_offset(control_utils.NOISE_STREAM_ROLLOUT, 0), self._noise_step.data_ptr()
+        else:
+            na.offset, na.step_ptr = control_utils.noise_offset(control_utils.NOISE_STREAM_ROLLOUT, self.num_steps), None
+        st = blk["st"]
+        if px is not None:
+            st.seq = px.seq + 1
+            px.seq += self.n_iters
+        _lib.check(L.mjb_softmax_mpc_step(C.byref(st), _lib.stream_ptr()))
+        return blk["action"]
 
     def _peer_exchange(self, P):
         """Symmetric-memory exchange buffer for partial vectors of P doubles (None: single GPU, disabled

@@ -1,0 +1,48 @@
+// One whole MPC step of the softmax controllers (MPPI, DMD-MPC) behind ONE host call.
+// Replaces the host loop of Controller.optimize (mjmpc/control/controller.py:207-257):
+//   n_iters x { generate_rollouts (olgaussian_mpc.py:95-114) -> _update_distribution (mppi.py:69-97,
+//   gaussian_dmd.py:65-91) } -> next action = mean[0] (olgaussian_mpc.py:69-78) -> _shift (:116-129,
+//   gaussian_dmd.py:106-113).
+// It launches exactly the kernels the separate entry points launch, in the same order on the same stream, so
+// the results are bit-identical to calling them one by one; what goes away is the host time between the
+// launches (interpreter, ctypes marshalling, tensor bookkeeping: ~0.3 ms per step from Python against
+// ~0.04 ms here), which is what bounds a step that cannot replay a CUDA graph -- the sharded multi-GPU step,
+// whose exchange kernel waits on peers -- once a GPU's share of the particles is small.
+#include "common.h"
+
+extern "C" int mjb_softmax_mpc_step(const mjb_mpc_step_args* a, void* stream) {
+    MJB_REQUIRE(a && a->model && a->rollout && a->softmax && a->combine, "mjb_softmax_mpc_step: null argument block");
+    MJB_REQUIRE(a->n_iters >= 1, "mjb_softmax_mpc_step: n_iters must be >= 1");
+    MJB_REQUIRE(a->noise || a->rollout->noise_cov || !a->rollout->noise,
+                "mjb_softmax_mpc_step: the rollout reads a noise tensor that nothing in the step writes");
+    MJB_REQUIRE(a->base_action == MJB_BASE_NULL || a->base_action == MJB_BASE_REPEAT || !a->shift,
+                "mjb_softmax_mpc_step: base_action 'random' needs a host-drawn row; use the separate entry points");
+    const mjb_combine_args* c = a->combine;
+    MJB_REQUIRE(c->mean, "mjb_softmax_mpc_step: the combine must apply the update (mean is NULL)");
+    MJB_REQUIRE(c->n_shards >= 1 && (c->n_shards == 1 || a->peer_bufs_dev),
+                "mjb_softmax_mpc_step: %d shards need the peer-memory exchange buffers", c->n_shards);
+    MJB_REQUIRE(c->n_shards > 1 || c->partials == a->softmax->partials,
+                "mjb_softmax_mpc_step: with one shard the combine must read the partial vector phase 1 writes");
+    MJB_REQUIRE(c->H == a->rollout->H && a->softmax->H == c->H && a->softmax->K == a->rollout->K && a->softmax->d == c->d,
+                "mjb_softmax_mpc_step: rollout / softmax / combine shapes disagree");
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    for (int it = 0; it < a->n_iters; it++) {
+        if (a->noise && (rc = mjb_generate_noise(a->noise, stream)) != MJB_OK) return rc;
+        if ((rc = mjb_rollout_reacher(a->model, a->rollout, stream)) != MJB_OK) return rc;
+        if ((rc = mjb_softmax_partials(a->softmax, stream)) != MJB_OK) return rc;
+        if (c->n_shards == 1) rc = mjb_softmax_combine(c, stream);
+        else rc = mjb_softmax_exchange_combine(c, a->softmax->partials, a->peer_bufs_dev, a->rank, a->seq + (unsigned long long)it, stream);
+        if (rc != MJB_OK) return rc;
+    }
+    if (a->action_out)
+        MJB_CUDA(cudaMemcpyAsync(a->action_out, c->mean, sizeof(double) * c->d, cudaMemcpyDeviceToDevice, s));
+    if (a->shift) {
+        if ((rc = mjb_shift_mean(c->mean, c->H, c->d, a->base_action, nullptr, stream)) != MJB_OK) return rc;
+        if (a->cov_shift_beta != 0.0) {
+            MJB_REQUIRE(c->cov, "mjb_softmax_mpc_step: cov_shift_beta needs the covariance");
+            if ((rc = mjb_cov_add_diag(c->cov, c->d, a->cov_shift_beta, nullptr, stream)) != MJB_OK) return rc;
+        }
+    }
+    return MJB_OK;
+}

@@ -158,6 +158,18 @@ class GpuReacherVecEnv:
         strides.  Outputs use the particle-minor layout (H,[7,]K) viewed as (K,H[,7]).
         ``closed_loop``: ``mean`` is the (d_obs + 1, 7) weight matrix of a linear policy (one per controller),
         the reference's mode="closed_loop_linear" (gym_env_wrapper.py:135-136)."""
+        a, out = self.rollout_args(num_particles, horizon, mean, noise, costs, actions, want_traj, want_obs, want_ncon,
+                                   closed_loop)
+        _lib.check(_lib.lib().mjb_rollout_reacher(self.model.handle, C.byref(a), _lib.stream_ptr()))
+        return out
+
+    def rollout_args(self, num_particles: int, horizon: int, mean: torch.Tensor, noise: Optional[torch.Tensor],
+                     costs: Optional[torch.Tensor] = None, actions: Optional[torch.Tensor] = None,
+                     want_traj: bool = False, want_obs: bool = False, want_ncon: bool = False,
+                     closed_loop: bool = False):
+        """The ``mjb_rollout_args`` block of :meth:`rollout_device` without the launch, and the output dict it
+        points into (which also keeps ``mean`` alive as ``_mean``).  Used by callers that hand the block to a
+        larger native call (``mjb_softmax_mpc_step``)."""
         K, H = int(num_particles), int(horizon)
         n_ctrl = self._state.shape[0]
         if K % self.n_workers != 0:
@@ -205,8 +217,8 @@ class GpuReacherVecEnv:
         if want_ncon:
             out["ncon"] = torch.empty((K,), dtype=torch.int32, device=dev)
             a.ncon = out["ncon"].data_ptr()
-        _lib.check(_lib.lib().mjb_rollout_reacher(self.model.handle, C.byref(a), _lib.stream_ptr()))
-        return out
+        self._args_keepalive = (mean, noise)      # tensors the block points into, until the next block is built
+        return a, out
 
     def _to_device(self, x):
         if x is None or isinstance(x, (torch.Tensor, NoiseSpec)):
@@ -265,4 +277,5 @@ class GpuReacherVecEnv:
                         costs=np.ascontiguousarray(out["costs"].cpu().numpy()), dones=np.zeros(nobs.shape[:2]),
                         next_observations=nobs, infos={})
         fn.accepts_noise_spec = True
+        fn.backend = self          # lets a controller hand the whole MPC step to one native call (mjb_softmax_mpc_step)
         return fn

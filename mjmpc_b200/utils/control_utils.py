@@ -72,6 +72,16 @@ def generate_noise(cov, filter_coeffs, shape, base_seed, *, step=0, stream_id=NO
     by the kernel) plays the role of the reference's ``+ num_steps`` reseeding (the same (seed, step) gives the same samples, as all n_iters of
     one MPC step do in the reference).  ``k_offset``/``K_global`` place a shard inside the
     global particle range; ``zero_last_mean`` applies olgaussian_mpc.py:110-111."""
+    a, keep = noise_args(cov, filter_coeffs, shape, base_seed, step=step, stream_id=stream_id, k_offset=k_offset,
+                         K_global=K_global, zero_last_mean=zero_last_mean, out=out, device=device)
+    _lib.check(_lib.lib().mjb_generate_noise(C.byref(a), _lib.stream_ptr()))
+    return keep["out"]
+
+
+def noise_args(cov, filter_coeffs, shape, base_seed, *, step=0, stream_id=NOISE_STREAM_ROLLOUT, k_offset=0,
+               K_global=None, zero_last_mean=None, out=None, device="cuda"):
+    """The ``mjb_noise_args`` block :func:`generate_noise` launches with, and the tensors it points into
+    (``keep``: hold on to it for as long as the block is used)."""
     K, H = int(shape[0]), int(shape[1])
     cov = _dev(cov, device).contiguous()
     d = cov.shape[0]
@@ -86,16 +96,22 @@ def generate_noise(cov, filter_coeffs, shape, base_seed, *, step=0, stream_id=NO
         a.offset = (int(stream_id) & 0xFFFFFFFF) << 32
         a.step_ptr = step.data_ptr()
     else:
-        a.offset = ((int(stream_id) & 0xFFFFFFFF) << 32) | (int(step) & 0xFFFFFFFF)
+        a.offset = noise_offset(stream_id, step)
     a.cov = cov.data_ptr()
     a.beta0, a.beta1, a.beta2 = [float(b) for b in filter_coeffs]
+    keep = dict(cov=cov, out=out, step=step)
     if zero_last_mean is not None:
         zm = _dev(zero_last_mean, cov.device).contiguous()
         a.zero_last, a.neg_mean = 1, zm.data_ptr()
+        keep["neg_mean"] = zm
     a.out = out.data_ptr()
     a.out_sk, a.out_st, a.out_sj = out.stride()
-    _lib.check(_lib.lib().mjb_generate_noise(C.byref(a), _lib.stream_ptr()))
-    return out
+    return a, keep
+
+
+def noise_offset(stream_id, step):
+    """Philox offset word: stream id in the high 32 bits, the num_steps-like counter in the low 32."""
+    return ((int(stream_id) & 0xFFFFFFFF) << 32) | (int(step) & 0xFFFFFFFF)
 
 
 def cost_to_go(cost_seq, gamma_seq, out=None):

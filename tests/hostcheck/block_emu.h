@@ -31,7 +31,7 @@ struct BlockCtx {
     std::vector<int> warp_live, warp_wait;
     std::vector<unsigned long long> wbuf;       // [warp][32] shuffle exchange
     int n = 0, cur = 0, live = 0, block_wait = 0;
-    Idx block{0, 0, 0};
+    Idx block{0, 0, 0}, bdim{1, 1, 1}, gdim{1, 1, 1};
     void* dyn = nullptr;
     void (*call)(void*) = nullptr;
     void* fobj = nullptr;
@@ -40,7 +40,6 @@ struct BlockCtx {
 };
 constexpr size_t kStack = 256 * 1024;
 inline thread_local BlockCtx* t_ctx = nullptr;
-inline Idx g_bdim, g_gdim;
 
 inline void release_if_complete(BlockCtx& c, int w) {
     if (c.live > 0 && c.block_wait == c.live) {
@@ -113,13 +112,13 @@ inline void run_block(BlockCtx& c, dim3 block, unsigned bx, unsigned by, unsigne
 }
 
 template <class F> void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, F f) {
-    g_bdim = {block.x, block.y, block.z}; g_gdim = {grid.x, grid.y, grid.z};
     const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
     std::atomic<unsigned long long> next{0};
     auto worker = [&] {
         BlockCtx c;
         c.call = [](void* p) { (*(F*)p)(); };
         c.fobj = (void*)&f;
+        c.bdim = {block.x, block.y, block.z}; c.gdim = {grid.x, grid.y, grid.z};    // per worker: launches from several host threads may overlap
         t_ctx = &c;
         for (;;) {
             const unsigned long long b = next.fetch_add(1);
@@ -165,8 +164,8 @@ template <class T, class S> T shfl(T v, S src_of_lane) {
 #define g_dyn_smem dyn_smem()          // emu::g_dyn_smem in generated code
 #define threadIdx emu::thread_idx()
 #define blockIdx emu::block_idx()
-#define blockDim emu::g_bdim
-#define gridDim emu::g_gdim
+#define blockDim emu::t_ctx->bdim
+#define gridDim emu::t_ctx->gdim
 #undef __shared__
 #define __shared__ static thread_local
 #ifndef __launch_bounds__
