@@ -138,7 +138,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # bounded sample: as many particles per MPC iteration as keep the whole run near a minute on ~16 cores
+    # (one iteration costs ~40 us per particle: numpy noise + C rollout on all cores + numpy update); the full
+    # K = 65536 when the driver asks for few steps
+    budget = 60.0 / (40e-6 * max(1, args.steps + args.warmup))
     k_sample = 2048
+    while k_sample * 2 <= min(K_GLOBAL, budget):
+        k_sample *= 2
+    if args.cpu_particles:
+        k_sample = args.cpu_particles
     cb = CpuBaseline(k_sample)
     value, s_per_step = cb.measure(args.steps, args.warmup)
     line = {
@@ -286,12 +294,13 @@ def run_own(args):
     # ---- CPU baseline on the host cores (rank 0, N=1 only, bounded sample) --------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cb = CpuBaseline(2048)
-        v, _ = cb.measure(steps=3, warmup=1)
+        k_sample, cpu_steps = args.cpu_particles or 32768, 4          # ~10-15 s of CPU work on 16 cores
+        cb = CpuBaseline(k_sample)
+        v, _ = cb.measure(steps=cpu_steps, warmup=1)
         cpu = {"value": v, "unit": "particle-steps/s", "cores": cb.cores, "kind": "port",
-               "sample": "3 MPC iterations of 2048 of %d particles x H=%d: numpy generate_noise + C oracle rollout on %d "
+               "sample": "%d MPC iterations of %d of %d particles x H=%d: numpy generate_noise + C oracle rollout on %d "
                          "threads + numpy MPPI update (restatement of the reference path; mujoco_py cannot run here)"
-                         % (K_GLOBAL, HORIZON, cb.cores)}
+                         % (cpu_steps, k_sample, K_GLOBAL, HORIZON, cb.cores)}
     line = {
         "metric": "particle_steps_per_s", "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
@@ -334,6 +343,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-particles", type=int, default=0,
+                    help="particles per MPC iteration of the CPU sample (default: 32768 for cpu_baseline; sized to the step count for --impl reference)")
     ap.add_argument("--watchdog", type=int, default=600, help="abort if the whole run exceeds this many seconds")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -44,7 +44,8 @@ def test_bench_contract_keys_on_the_host_emulation():
 def test_bench_reference_arm_runs_on_cpu():
     """`bench.py --impl reference` needs no GPU at all: the C oracle rollout + numpy controller math, a bounded
     sample of the same workload; ranks other than 0 print nothing and exit 0."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "3",
+                        "--cpu-particles", "2048"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-3000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
