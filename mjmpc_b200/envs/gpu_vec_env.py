@@ -99,8 +99,16 @@ class GpuReacherVecEnv:
 
     # ---- SubprocVecEnv surface -------------------------------------------------------------
     def set_env_state(self, state_dicts):
-        """One state for every particle, or a list with one state per batched controller."""
-        if isinstance(state_dicts, (list, tuple)):
+        """One state for every particle, or a list with one state per batched controller.  Sweeps with many
+        instances can skip the per-dict Python work: an (n_ctrl, 17) array of [qpos | qvel | target_pos] rows (or
+        a device tensor of that shape, see :meth:`set_env_state_device`) is taken as it is."""
+        if isinstance(state_dicts, torch.Tensor):
+            return self.set_env_state_device(state_dicts.to(device=self.device, dtype=torch.float64))
+        if isinstance(state_dicts, np.ndarray) and state_dicts.ndim == 2:
+            if state_dicts.shape[1] != _lib.STATE_DIM:
+                raise ValueError("state rows must have %d entries (qpos, qvel, target_pos)" % _lib.STATE_DIM)
+            rows = np.asarray(state_dicts, np.float64)
+        elif isinstance(state_dicts, (list, tuple)):
             if len(state_dicts) > 1 and all(isinstance(s, dict) for s in state_dicts):
                 rows = np.empty((len(state_dicts), _lib.STATE_DIM))          # batched instances: one pass per key
                 rows[:, 0:7] = [s["qp"] for s in state_dicts]

@@ -193,6 +193,8 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+                # ... nor the host emulation the tests run it on
+                assert "emu_device" not in txt and "MJB_TEST_EMU" not in txt and "b200_emu" not in txt, f
 
 
 def test_sincos_joint_accuracy(hostcheck):

@@ -104,3 +104,33 @@ def test_closed_loop_linear_through_the_reference_rollout_fn():
     with pytest.raises(NotImplementedError):
         env.rollout_fn(K, H, W, noise, mode="closed_loop_nn")
     env.close()
+
+
+def test_batched_instances_take_state_rows():
+    """Sweeps of many instances: an (n_ctrl, 17) array (host or device) of [qpos | qvel | target] rows is accepted
+    in place of the list of state dicts and gives the same step, bit for bit."""
+    import torch
+    from conftest import synthetic_state
+    from mjmpc_b200.control import MPPI
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    from mjmpc_b200.envs.model import compile_model, reacher7dof_spec
+    cm = compile_model(reacher7dof_spec())
+    B, K, H = 6, 32, 8
+    dicts = [synthetic_state(cm, 40 + b) for b in range(B)]
+    rows = np.stack([np.concatenate([s["qp"], s["qv"], s["target_pos"]]) for s in dicts])
+    outs = []
+    for form in ("dicts", "rows", "device"):
+        env = GpuReacherVecEnv(cm, n_workers=B)
+        c = MPPI(d_state=25, d_obs=20, d_action=7, action_lows=-np.ones(7), action_highs=np.ones(7), horizon=H, init_cov=1.0,
+                 base_action='null', lam=0.2, num_particles=K, step_size=1.0, alpha=1, gamma=1.0, n_iters=1,
+                 filter_coeffs=[0.25, 0.8, 0.0], seed=3, batch_size=B)
+        c.set_sim_state_fn, c.rollout_fn = env.set_env_state, env.rollout_fn
+        st = {"dicts": dicts, "rows": rows, "device": torch.from_numpy(rows).cuda()}[form]
+        acts = [c.optimize(st)[0] for _ in range(2)]
+        outs.append((np.stack(acts), c.mean_action))
+        env.close()
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o[0], outs[0][0])
+        np.testing.assert_array_equal(o[1], outs[0][1])
+    with pytest.raises(ValueError):
+        GpuReacherVecEnv(cm).set_env_state(np.zeros((2, 5)))
