@@ -203,7 +203,8 @@ class OLGaussianMPC(Controller):
         Returns the (2+2T,) stats tensor: value, global min, normalisers, minima.
         td = (td_lam, gamma, weight_seq, qvals or None): weights from MPPIQ's TD(lambda) returns instead of
         the discounted cost-to-go."""
-        a, c, P, stats, _ = self._softmax_blocks(costs, actions, lam, control_cost, time_based, cov_mode, apply, td)
+        # `keep`: host arrays the phase-1 block points into (gamma_seq, TD weights) -- alive until the calls return
+        a, c, P, stats, keep = self._softmax_blocks(costs, actions, lam, control_cost, time_based, cov_mode, apply, td)
         L = _lib.lib()
         _lib.check(L.mjb_softmax_partials(C.byref(a), _lib.stream_ptr()))
         partials = self._buf("sm_partials", (P,))
@@ -217,6 +218,7 @@ class OLGaussianMPC(Controller):
             allp = self.shard.all_gather(partials)
             c.partials = allp.data_ptr()
             _lib.check(L.mjb_softmax_combine(C.byref(c), _lib.stream_ptr()))
+        del keep
         return stats
 
     def _softmax_blocks(self, costs, actions, lam, control_cost=False, time_based=False, cov_mode=_lib.COV_NONE,
