@@ -213,3 +213,51 @@ def test_fused_noise_equals_noise_kernel_then_rollout(emu, compiled_model):
     fused = _rollout(emu, P, st, K, H, mean, None, fused=(cov, 99, 4, b))
     np.testing.assert_array_equal(fused["actions"], two["actions"])
     np.testing.assert_array_equal(fused["costs"], two["costs"])
+
+
+def test_rollout_kernel_source_on_random_hard_states(emu, compiled_model):
+    """Randomised start states the bench never visits -- joints up to 0.2 rad beyond their limits, joint speeds up
+    to ~6 rad/s, torque-saturating noise, the arm driven towards the table, per-case randomised masses / inertias /
+    damping -- through the kernel source against the C oracle: every constraint path (several limit rows at once,
+    wrong first guesses, rank-one repairs, the contact row, the out-of-line robust solver) within the north-star
+    1e-8 on the whole trajectory."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as hst
+    from mjmpc_b200.envs.model import randomized_copy
+    from oracle import mjstep
+    lo, hi = compiled_model.tree.jnt_range[:, 0], compiled_model.tree.jnt_range[:, 1]
+    seen = dict(cases=0, constrained=0, contact=0)
+
+    @settings(deadline=None, max_examples=40, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(s=hst.integers(0, 2 ** 31 - 1), beyond=hst.sampled_from([0.0, 0.05, 0.2]), vstd=hst.sampled_from([0.5, 2.0, 6.0]),
+           nscale=hst.sampled_from([0.3, 1.0, 3.0]), table=hst.booleans(), rand_model=hst.booleans())
+    def run(s, beyond, vstd, nscale, table, rand_model):
+        rng = np.random.default_rng(s)
+        cm = compiled_model
+        if rand_model:
+            cm, _, _ = randomized_copy(compiled_model, dict(
+                body_mass={"r_forearm_link": [0.3, 0.0], "r_wrist_roll_link": [0.3, 0.0], "r_upper_arm_link": [0.3, 0.0]},
+                body_inertia={"r_upper_arm_link": [0.2, 0.0]},
+                dof_damping={"r_elbow_flex_joint": [0.3, 0.0], "r_shoulder_lift_joint": [0.3, 0.0]}),
+                np.random.RandomState(s % 100000), {})
+        qp = rng.uniform(lo - beyond, hi + beyond)
+        mean = np.zeros((10, 7))
+        if table:
+            qp[1] = rng.uniform(0.3, 0.5); qp[3] = rng.uniform(-0.4, 0.0); qp[5] = rng.uniform(-0.5, 0.0)
+            mean[:, 1] = 1.0
+        st = dict(qp=qp, qv=rng.normal(0, vstd, 7), target_pos=rng.uniform([-.3, -.2, -.25], [.3, .2, .25]))
+        K, H = 32, 10
+        noise = nscale * reference_noise(K, H, 7, s % 1000)
+        ref = mjstep.rollout(mjstep.OracleModel(cm.tree), st["qp"], st["qv"], st["target_pos"], mean, noise, want_traj=True,
+                             nthreads=2)
+        out = _rollout(emu, cm.chain.params, st, K, H, mean, noise, traj=True, ncon=True)
+        assert np.isfinite(out["qv"]).all()
+        scale = np.abs(ref["qv"]).max(axis=(0, 1))
+        assert (np.abs(out["qv"] - ref["qv"]).max(axis=(0, 1)) / scale).max() < 1e-8
+        np.testing.assert_allclose(out["costs"], ref["costs"], rtol=1e-8)
+        seen["cases"] += 1
+        seen["constrained"] += int((ref["ncon"] > 0).any())
+        seen["contact"] += int(table)
+
+    run()
+    assert seen["constrained"] >= seen["cases"] // 2 and seen["contact"] >= 5, seen
