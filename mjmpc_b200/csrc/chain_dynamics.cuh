@@ -231,14 +231,16 @@ struct HostScratch {
 
 // ---------------------------------------------------------------------------------------------
 // M(q) lower triangle (with armature) -> scratch, and bias(q,v).  sn/cs = sin/cos of the joint angles.
+// PARTS: bit 0 = the bias forces (the two Newton-Euler passes), bit 1 = the mass matrix (composite-rigid-body
+// recursion); the two halves are independent of each other (role-split experiments compile them apart).
 // ---------------------------------------------------------------------------------------------
-template <class T, class P, class S>
+template <class T, int PARTS = 3, class P, class S>
 MJB_HD void chain_mass_bias(const P& prm, S& sc, const double (&sn)[7], const double (&cs)[7], const double (&qd)[7],
                             double (&bias)[7]) {
     // ---- recursive Newton-Euler, outward pass: link velocities / bias accelerations -> link wrenches.
     // Link 0 hangs off the fixed base: its own wrench never reaches a joint axis (its z torque is
     // zero and it has no parent), so only its angular velocity is carried on.
-    {
+    if constexpr (PARTS & 1) {
         V3 w = {0, 0, 0}, al = {0, 0, 0}, ac = {0, 0, 0};
         static_for<7>([&](auto Ic) {
             constexpr int i = decltype(Ic)::value;
@@ -279,7 +281,7 @@ MJB_HD void chain_mass_bias(const P& prm, S& sc, const double (&sn)[7], const do
         });
     }
     // ---- inward pass: accumulate child wrenches, project on the joint axis
-    {
+    if constexpr (PARTS & 1) {
         V3 fa = {0, 0, 0}, na = {0, 0, 0};
         static_for<7>([&](auto Ic) {
             constexpr int i = 6 - decltype(Ic)::value;
@@ -297,7 +299,7 @@ MJB_HD void chain_mass_bias(const P& prm, S& sc, const double (&sn)[7], const do
         });
     }
     // ---- composite rigid body recursion (inward): composite (mass, first moment, inertia about origin)
-    {
+    if constexpr (PARTS & 2) {
         double cm = 0.0;
         V3 ch = {0, 0, 0};
         S3 cI = {0, 0, 0, 0, 0, 0};
