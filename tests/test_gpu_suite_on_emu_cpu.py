@@ -1,7 +1,7 @@
 """The `-m gpu` test functions executed WITHOUT a GPU: a child pytest with MJB_TEST_EMU=1 runs them against
 tests/hostcheck/libmjmpc_b200_emu.so -- the product's .cu sources (kernels and launch code) built for the host --
-with torch handing out CPU tensors (tests/helpers/emu_device.py).  Whole episodes, BASELINE sizes, CUDA-graph
-replay and real NCCL ranks are skipped there (tests/conftest.py lists them); everything else -- rollout parity
+with torch handing out CPU tensors (tests/helpers/emu_device.py).  CUDA-graph replay, real NCCL ranks and child
+processes are skipped there (tests/conftest.py lists them); everything else -- BASELINE sizes, whole episodes, rollout parity
 with the oracle, noise, all five controllers against the reference goldens, batched instances, logical shards,
 the VecEnv adaptor, closed-loop rollouts -- must pass before the suite ever reaches the GPU box.  A child
 process, because the shim patches torch globally."""
@@ -24,4 +24,4 @@ def test_gpu_marked_tests_pass_on_the_host_emulation():
     tail = r.stdout[-3000:] + r.stderr[-1500:]
     assert r.returncode == 0, tail
     m = re.search(r"(\d+) passed", r.stdout)
-    assert m and int(m.group(1)) >= 55, tail          # the suite really ran (not everything skipped)
+    assert m and int(m.group(1)) >= 80, tail          # the suite really ran (not everything skipped)

@@ -105,3 +105,23 @@ def test_cem_and_random_shooting_classes_random_shapes(K, H, d, layout, s, cov_t
     r._update_distribution(traj)
     assert int(r.best_id.cpu().numpy().reshape(-1)[0]) == int(np.argmin(O.cost_to_go(costs.copy(), gs)[:, 0]))
     np.testing.assert_allclose(r.mean_action, want if not isinstance(want, tuple) else want[0], rtol=RTOL, atol=1e-12)
+
+
+@settings(**SET)
+@given(lam=st.sampled_from([0.02, 0.3, 2.0]), nsteps=st.integers(0, 5), **shapes)
+def test_pfmpc_class_random_shapes(K, H, d, layout, s, lam, nsteps):
+    """Weights, the systematic resampler's indices (bit-exact, r drawn from Python's random after
+    random.seed(seed_val + num_steps) like the reference), the gathered particle set and its mean."""
+    from mjmpc_b200.control import PFMPC
+    from oracle import control_np as O
+    costs, _, samples, traj = _problem(s, K, H, d, layout)
+    c = PFMPC(horizon=H, cov_shift=0.1, cov_resample=1.0, base_action='null', lam=lam, num_particles=K, gamma=0.98, n_iters=1,
+              filter_coeffs=[0.25, 0.8, 0.0], seed=7, **_common(d))
+    c.action_samples = samples
+    c.num_steps = nsteps
+    w = O.pf_weights(costs, O.gamma_seq(0.98, H), lam)
+    ids, _ = O.pf_resample_indices(w, c.seed_val + nsteps)
+    c._update_distribution(dict(costs=traj["costs"]))
+    np.testing.assert_array_equal(c.resample_ids.cpu().numpy().reshape(-1), ids % K)
+    np.testing.assert_array_equal(c.action_samples, samples[ids])
+    np.testing.assert_allclose(c.mean_action, samples[ids].mean(0), rtol=1e-12, atol=1e-14)
