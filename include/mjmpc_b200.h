@@ -94,6 +94,24 @@ typedef struct {
 } mjb_pendulum_args;
 int mjb_rollout_pendulum(const mjb_pendulum_args* a, void* stream);
 
+/* ---- linear-quadratic toy env: replaces LQREnv.step (mjmpc/envs/basic/lqr.py:31-35) under
+ * GymEnvWrapper.rollout: cost_t = x'Qx + u'Ru on the pre-step state, x <- Ax + Bu, u = mean[t] + noise[k,t]
+ * (no clipping).  A (n,n), B (n,d), Q (n,n), R (d,d) row-major DEVICE; state (n_ctrl, n); mean (n_ctrl, H, d);
+ * states_out (K,H,n) row-major (the post-step states) or NULL. */
+#define MJB_LQR_MAXN 8
+#define MJB_LQR_MAXD 8
+typedef struct {
+    int K, H, n, d, particles_per_ctrl;
+    const double* A; const double* B; const double* Q; const double* R;
+    const double* state;
+    const double* mean;
+    const double* noise; long long noise_sk, noise_st, noise_sj;
+    double* costs; long long costs_sk, costs_st;
+    double* actions; long long act_sk, act_st, act_sj;
+    double* states_out;
+} mjb_lqr_args;
+int mjb_rollout_lqr(const mjb_lqr_args* a, void* stream);
+
 /* ---- K2 noise: replaces generate_noise (mjmpc/utils/control_utils.py:24-34) and the
  * use_zero_control_seq overwrite (mjmpc/control/olgaussian_mpc.py:110-111).  Philox4x32-10 keyed by
  * `seed`, counters (k_offset + k, low32(offset), t, high32(offset) << 8 | pair): results do not

@@ -100,6 +100,18 @@ class PendulumArgs(C.Structure):
     ]
 
 
+class LqrArgs(C.Structure):
+    _fields_ = [
+        ("K", C.c_int), ("H", C.c_int), ("n", C.c_int), ("d", C.c_int), ("particles_per_ctrl", C.c_int),
+        ("A", C.c_void_p), ("B", C.c_void_p), ("Q", C.c_void_p), ("R", C.c_void_p),
+        ("state", C.c_void_p), ("mean", C.c_void_p),
+        ("noise", C.c_void_p), ("noise_sk", c_ll), ("noise_st", c_ll), ("noise_sj", c_ll),
+        ("costs", C.c_void_p), ("costs_sk", c_ll), ("costs_st", c_ll),
+        ("actions", C.c_void_p), ("act_sk", c_ll), ("act_st", c_ll), ("act_sj", c_ll),
+        ("states_out", C.c_void_p),
+    ]
+
+
 class NoiseArgs(C.Structure):
     _fields_ = [
         ("K", C.c_int), ("H", C.c_int), ("d", C.c_int),
@@ -187,7 +199,7 @@ RETURNS_CTG, RETURNS_TD_LAMBDA = 0, 1
 BASE_ACTIONS = {"null": 0, "repeat": 1, "random": 2}
 
 EXPORTS += [
-    "mjb_rollout_pendulum", "mjb_generate_noise", "mjb_cost_to_go",
+    "mjb_rollout_pendulum", "mjb_rollout_lqr", "mjb_generate_noise", "mjb_cost_to_go",
     "mjb_softmax_scratch_doubles", "mjb_softmax_partial_doubles", "mjb_softmax_partials",
     "mjb_softmax_combine", "mjb_softmax_exchange_combine", "mjb_softmax_weights",
     "mjb_select_elites", "mjb_argmin", "mjb_elite_scratch_doubles", "mjb_elite_moments1",

@@ -178,6 +178,24 @@ def main():
             ps[b, t] = env.state
     out["pendulum"] = dict(state0=st0, mean=pmean, noise=pnoise, costs=pc, states=ps)
 
+    # ---- linear-quadratic toy env (mjmpc/envs/basic/lqr.py), driven like GymEnvWrapper.rollout drives it ------
+    rng = np.random.RandomState(4)
+    n, dl, Hl, Kl = 4, 2, 12, 16
+    Al = np.eye(n) + 0.1 * rng.normal(0, 1, (n, n)); Bl = rng.normal(0, 0.5, (n, dl))
+    Ql = rng.normal(0, 1, (n, n)); Ql = Ql @ Ql.T / n; Rl = np.diag([0.1, 0.3])
+    lenv = R.lqr.LQREnv(Al, Bl, Ql, Rl)
+    lmean = rng.normal(0, 0.5, (Hl, dl))
+    lnoise = R.control_utils.generate_noise(np.diag([1.0, 0.5]), [0.25, 0.8, 0.0], (Kl, Hl), 9)
+    lx0 = rng.normal(0, 2.0, (n, 1))
+    lc = np.zeros((Kl, Hl)); ls = np.zeros((Kl, Hl, n))
+    for b in range(Kl):
+        lenv.set_env_state(dict(state=lx0.copy()))
+        for t in range(Hl):
+            ob, rew, done, _ = lenv.step((lmean[t] + lnoise[b, t]).reshape(dl, 1))
+            lc[b, t] = -np.asarray(rew).item()
+            ls[b, t] = ob[:, 0]
+    out["lqr"] = dict(A=Al, B=Bl, Q=Ql, R=Rl, state0=lx0, mean=lmean, noise=lnoise, costs=lc, states=ls)
+
     # the MPPI/CEM/DMD/RS cases share one synthetic rollout: store it once
     out["common"] = dict(mean0=mean, costs=costs, actions=actions)
     only = sys.argv[1] if len(sys.argv) > 1 else ""      # optional name prefix: regenerate those files only

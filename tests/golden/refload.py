@@ -54,4 +54,5 @@ def load():
     mods.rs = importlib.import_module("mjmpc.control.random_shooting")
     mods.pf = importlib.import_module("mjmpc.control.particle_filter_controller")
     mods.pendulum = importlib.import_module("mjmpc.envs.basic.pendulum")
+    mods.lqr = importlib.import_module("mjmpc.envs.basic.lqr")
     return mods

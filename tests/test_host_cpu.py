@@ -276,7 +276,8 @@ def test_ctypes_structs_match_header_layout():
              ("mjb_noise_args", _lib.NoiseArgs, "out_sj"), ("mjb_softmax_args", _lib.SoftmaxArgs, "q_st"),
              ("mjb_combine_args", _lib.CombineArgs, "stats"), ("mjb_elite_args", _lib.EliteArgs, "partial"),
              ("mjb_elite_combine_args", _lib.EliteCombineArgs, "cov"), ("mjb_mppi_batched_args", _lib.MppiBatchedArgs, "value"),
-             ("mjb_pf_batched_args", _lib.PfBatchedArgs, "mean"), ("mjb_mpc_step_args", _lib.MpcStepArgs, "cov_shift_beta")]
+             ("mjb_pf_batched_args", _lib.PfBatchedArgs, "mean"), ("mjb_mpc_step_args", _lib.MpcStepArgs, "cov_shift_beta"),
+             ("mjb_lqr_args", _lib.LqrArgs, "states_out")]
     body = "".join('printf("%%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));' % (c, c, last) for c, _, last in pairs)
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "include/mjmpc_b200.h"\nint main(){%s return 0;}' % body
     exe = os.path.join(ROOT, "tests", "hostcheck", "layout_probe")

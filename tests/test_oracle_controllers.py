@@ -148,3 +148,13 @@ def test_oracle_matches_live_reference():
         m2, c2, _ = O.cem_update(mean, np.diag([1.0] * d), costs, actions, gs, e.num_elite, 0.5, 'full')
         np.testing.assert_array_equal(m2, e.mean_action)
         np.testing.assert_array_equal(c2, e.cov_action)
+
+
+def test_lqr_oracle_matches_reference_golden():
+    """oracle/lqr_np.py against trajectories of the unmodified LQREnv (mjmpc/envs/basic/lqr.py)."""
+    from golden_util import load
+    from oracle import lqr_np
+    g = load("lqr")
+    out = lqr_np.rollout(g["A"], g["B"], g["Q"], g["R"], g["state0"], g["mean"], g["noise"])
+    np.testing.assert_array_equal(out["costs"], g["costs"])
+    np.testing.assert_array_equal(out["states"], g["states"])
