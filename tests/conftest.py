@@ -30,6 +30,7 @@ _EMU_IMPOSSIBLE = {
 }
 _EMU_SLOW = {       # (BASELINE sizes, K = 65536, take ~10 s per test on the fiber emulator and stay in)
     "test_cem_pendulum_config2_runs_and_improves": "K=4096 H=64 over a whole episode (30 s)",
+    "test_closed_loop_reaches_target[cem]": "75 radix selections in one 1024-fiber block (35 s)",
 }
 
 
