@@ -95,9 +95,25 @@ inline void run_block(BlockCtx& c, dim3 block, unsigned bx, unsigned by, unsigne
         f.ctx.uc_link = nullptr;
         makecontext(&f.ctx, (void (*)())fiber_main, 0);
     }
+    // Fibers only switch at barriers, so the ORDER in which runnable fibers are resumed decides what a missing
+    // __syncthreads gets to see.  MJB_EMU_ORDER=reverse | shuffle (default: ascending thread index) lets the
+    // tests run the same kernels under adversarial orders: code that is correctly synchronised cannot tell.
+    static const int order_mode = [] { const char* e = std::getenv("MJB_EMU_ORDER"); return !e ? 0 : (e[0] == 'r' ? 1 : (e[0] == 's' ? 2 : 0)); }();
+    std::vector<int> order(n);
+    for (int t = 0; t < n; t++) order[t] = order_mode == 1 ? n - 1 - t : t;
+    unsigned long long lcg = 0x9E3779B97F4A7C15ull ^ ((unsigned long long)bx * 0x100000001B3ull + by * 7919ull + bz);
+    unsigned long long pass = 0;
     while (c.live > 0) {
         bool progressed = false;
-        for (int t = 0; t < n; t++) {
+        if (order_mode == 2) {                       // a fresh permutation for every scheduling pass
+            for (int i = n - 1; i > 0; i--) {
+                lcg = lcg * 6364136223846793005ull + 1442695040888963407ull + pass;
+                std::swap(order[i], order[(int)((lcg >> 33) % (unsigned long long)(i + 1))]);
+            }
+            pass++;
+        }
+        for (int oi = 0; oi < n; oi++) {
+            const int t = order[oi];
             if (c.fib[t].state != RUN) continue;
             c.cur = t;
             progressed = true;
