@@ -2,7 +2,7 @@
 # One GPU-box call that produces everything the next round needs first (tests, bench lines, A/B timings of the
 # changes made without a GPU, launch list, one full ncu capture of the rollout kernel).  Build the variant
 # libraries HERE first:   python tools/k1_variants.py build
-# then:   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'          (about 12 GPU-minutes)
+# then:   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh'          (about 15 GPU-minutes)
 # Everything lands in gpurun_out/session/; copy what should be judged into profiles/.
 set -u
 OUT=gpurun_out/session
@@ -28,5 +28,8 @@ ncu --set full --clock-control none --import-source on -k regex:rollout_reacher_
     python bench.py --steps 4 --warmup 3 --no-graph --no-cpu-baseline > $OUT/ncu_k1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:noise_kernel -s 3 -c 1 -o $OUT/k2_full \
     python bench.py --steps 4 --warmup 3 --no-graph --no-cpu-baseline > $OUT/ncu_k2.log 2>&1
+# memory and shared-memory race checks on small problems (the emulator cannot see either)
+compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py --smoke > $OUT/memcheck_smoke.log 2>&1; echo "memcheck smoke exit $?" >> $OUT/log.txt
+compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_controllers_gpu.py -m gpu -q -x -k "mppi_update or cem_update or dmd_update or pfmpc or random_shooting" > $OUT/racecheck_updates.log 2>&1; echo "racecheck updates exit $?" >> $OUT/log.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.csv 2>&1
 tail -5 $OUT/log.txt; head -c 600 $OUT/bench.json
