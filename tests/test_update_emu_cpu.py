@@ -43,27 +43,29 @@ def _problem(K, H, d, seed):
     return costs, mean, actions
 
 
-def _softmax(L, costs, actions, mean, cov, gseq, lam, step_size, control_cost=0, time_based=0, cov_mode=0, n_shards=1):
-    """mjb_softmax_partials per shard + mjb_softmax_combine, like OLGaussianMPC._softmax_update."""
+def _softmax(L, costs, actions, mean, cov, gseq, lam, step_size, control_cost=0, time_based=0, cov_mode=0, n_shards=1,
+             wrap=lambda a: a):
+    """mjb_softmax_partials per shard + mjb_softmax_combine, like OLGaussianMPC._softmax_update.
+    wrap: applied to every array handed to the library (the fuzz tests embed them in guard bands)."""
     K, H, d = actions.shape
     T = H if time_based else 1
     P = L.mjb_softmax_partial_doubles(H, d, time_based, cov_mode)
     g = np.ascontiguousarray(gseq.reshape(-1))
-    mean = mean.copy(); cov = cov.copy()
-    parts = np.zeros((n_shards, P))
+    mean = wrap(mean.copy()); cov = wrap(cov.copy())
+    parts = wrap(np.zeros((n_shards, P)))
     kl = K // n_shards
     for r in range(n_shards):
-        c = np.ascontiguousarray(costs[r * kl:(r + 1) * kl]); a_ = np.ascontiguousarray(actions[r * kl:(r + 1) * kl])
+        c = wrap(np.ascontiguousarray(costs[r * kl:(r + 1) * kl])); a_ = wrap(np.ascontiguousarray(actions[r * kl:(r + 1) * kl]))
         a = _lib.SoftmaxArgs()
         a.K, a.H, a.d = kl, H, d
         a.costs = c.ctypes.data; a.costs_sk, a.costs_st = H, 1
         a.actions = a_.ctypes.data; a.act_sk, a.act_st, a.act_sj = H * d, d, 1
         a.mean, a.cov, a.gamma_seq = mean.ctypes.data, cov.ctypes.data, g.ctypes.data
         a.lam, a.control_cost, a.time_based, a.cov_mode = lam, control_cost, time_based, cov_mode
-        total = np.zeros((T, kl)); scratch = np.zeros(int(L.mjb_softmax_scratch_doubles(kl, H, d, cov_mode)))
+        total = wrap(np.zeros((T, kl))); scratch = wrap(np.zeros(int(L.mjb_softmax_scratch_doubles(kl, H, d, cov_mode))))
         a.total, a.scratch, a.partials = total.ctypes.data, scratch.ctypes.data, parts[r].ctypes.data
         ok(L, L.mjb_softmax_partials(C.byref(a), None))
-    stats = np.zeros(2 + 2 * T)
+    stats = wrap(np.zeros(2 + 2 * T))
     cb = _lib.CombineArgs()
     cb.H, cb.d, cb.n_shards, cb.K_global = H, d, n_shards, K
     cb.partials, cb.lam, cb.step_size = parts.ctypes.data, lam, step_size

@@ -2,7 +2,9 @@
 numpy restatement of the reference: particle counts that are not multiples of the chunk / block / warp size down
 to a single particle, H from 1, every d_action the kernels are instantiated for, ties in the cost-to-go (elite
 set and argmin must break them towards the lower index, as numpy's stable order does), weights that underflow to
-zero (resampling), shards of ragged size.  hypothesis draws the cases; a fixed seed keeps the suite deterministic."""
+zero (resampling), shards of ragged size.  Every array handed to the kernels sits between bands of sentinels, so
+an out-of-bounds write (or a read that reaches a result) at a ragged tail fails the case.  hypothesis draws the
+cases; a fixed seed keeps the suite deterministic."""
 import ctypes as C
 
 import numpy as np
@@ -13,6 +15,28 @@ from hypothesis import strategies as st
 from mjmpc_b200 import _lib
 from oracle import control_np as O
 from test_update_emu_cpu import L, _softmax, ok, vp   # noqa: F401  (L is the fixture: the emulated library)
+
+class Guard:
+    """Embeds every array handed to the kernels in bands of sentinels: an out-of-bounds WRITE destroys a sentinel
+    (check()), an out-of-bounds READ of a float array pulls a NaN into a result the test compares."""
+
+    def __init__(self):
+        self.bufs = []
+
+    def __call__(self, a, pad=96):
+        a = np.ascontiguousarray(a)
+        sentinel = np.nan if a.dtype.kind == "f" else np.iinfo(a.dtype).min + 7
+        flat = np.full(a.size + 2 * pad, sentinel, dtype=a.dtype)
+        view = flat[pad:pad + a.size].reshape(a.shape)
+        view[...] = a
+        self.bufs.append((flat, pad, a.size, sentinel))
+        return view
+
+    def check(self):
+        for flat, pad, n, sentinel in self.bufs:
+            band = np.concatenate([flat[:pad], flat[pad + n:]])
+            assert (np.isnan(band).all() if flat.dtype.kind == "f" else (band == sentinel).all()), "out-of-bounds write"
+
 
 SETTINGS = dict(deadline=None, max_examples=25, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow],
                 derandomize=True)
@@ -38,8 +62,10 @@ def test_mppi_update_random_shapes(L, K, H, d, gamma, lam, alpha, time_based, sh
     cov = np.diag(rng.uniform(0.3, 2.0, d))
     gs = O.gamma_seq(gamma, H)
     want, _ = O.mppi_update(mean, cov, costs, actions, gs, lam, alpha, 0.8, time_based_weights=bool(time_based))
+    guard = Guard()
     got, _, stats = _softmax(L, costs, actions, mean, cov, gs, lam, 0.8, control_cost=int(alpha == 0),
-                             time_based=time_based, n_shards=shards)
+                             time_based=time_based, n_shards=shards, wrap=guard)
+    guard.check()
     np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
     if not time_based:
         np.testing.assert_allclose(stats[0], O.mppi_value(mean, cov, costs, actions, gs, lam, alpha), rtol=1e-10, atol=1e-12)
@@ -55,7 +81,9 @@ def test_dmd_update_random_shapes(L, K, H, d, mode, shards, s):
     cov = np.diag(rng.uniform(0.3, 2.0, d))
     gs = O.gamma_seq(0.99, H)
     wm, wc, _ = O.dmd_update(mean, cov, costs, actions, gs, 0.2, 0.6, mode != 0, "full" if mode == 2 else "diagonal")
-    gm, gc, _ = _softmax(L, costs, actions, mean, cov, gs, 0.2, 0.6, cov_mode=mode, n_shards=shards)
+    guard = Guard()
+    gm, gc, _ = _softmax(L, costs, actions, mean, cov, gs, 0.2, 0.6, cov_mode=mode, n_shards=shards, wrap=guard)
+    guard.check()
     np.testing.assert_allclose(gm, wm, rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(gc, wc, rtol=1e-10, atol=1e-12)
 
@@ -70,15 +98,17 @@ def test_elite_set_and_argmin_with_ties(L, K, frac, quantum, s):
         ctg0 = np.round(ctg0 / quantum) * quantum
     if K > 3 and s % 3 == 0:
         ctg0[rng.randint(K)] = -ctg0[rng.randint(K)]       # mixed signs: the order-preserving key must handle them
-    ctg0 = np.ascontiguousarray(ctg0)
+    guard = Guard()
+    ctg0 = guard(ctg0)
     E = min(K, max(1, int(K * frac)))
-    flags = np.zeros(K, np.uint8); sel = np.zeros(E, np.int64); scr = np.zeros(4096, np.uint8)
+    flags = guard(np.zeros(K, np.uint8)); sel = guard(np.zeros(E, np.int64)); scr = guard(np.zeros(4096, np.uint8))
     ok(L, L.mjb_select_elites(vp(ctg0), C.c_longlong(K), C.c_longlong(E), vp(flags), vp(sel), vp(scr), None))
     order = np.lexsort((np.arange(K), ctg0))[:E]           # == np.argsort(kind="stable")[:E]: ties -> lower index
     np.testing.assert_array_equal(np.flatnonzero(flags), np.sort(order))
     np.testing.assert_array_equal(np.sort(sel), np.sort(order))
-    idx = np.zeros(1, np.int64); val = np.zeros(1)
+    idx = guard(np.zeros(1, np.int64)); val = guard(np.zeros(1))
     ok(L, L.mjb_argmin(vp(ctg0), C.c_longlong(K), vp(idx), vp(val), None))
+    guard.check()
     assert idx[0] == np.argmin(ctg0) and val[0] == ctg0.min()
 
 
@@ -91,8 +121,10 @@ def test_systematic_resampling_indices_bit_exact(L, K, lam, rfrac, s):
     w = O.pf_weights(costs, O.gamma_seq(1.0, 3), lam)       # small lam: most weights underflow to exactly 0
     r = rfrac / K
     want = O.pf_resample_with_r(w, r)
-    cs = np.zeros(K); got = np.zeros(K, np.int64)
+    guard = Guard()
+    w = guard(w); cs = guard(np.zeros(K)); got = guard(np.zeros(K, np.int64))
     ok(L, L.mjb_resample_indices(vp(w), C.c_longlong(K), C.c_double(r), vp(cs), vp(got), None))
+    guard.check()
     np.testing.assert_array_equal(got, want % K)            # the reference's index -1 (r = 0) is the last particle
 
 
@@ -102,7 +134,9 @@ def test_systematic_resampling_indices_bit_exact(L, K, lam, rfrac, s):
 def test_cost_to_go_bit_exact_random_shapes(L, K, H, gamma, s):
     costs = np.abs(np.random.RandomState(s).normal(2, 1, (K, H)))
     gs = O.gamma_seq(gamma, H)
-    out = np.zeros((K, H))
+    guard = Guard()
+    costs = guard(costs); out = guard(np.zeros((K, H)))
     g = np.ascontiguousarray(gs.reshape(-1))
     ok(L, L.mjb_cost_to_go(vp(costs), C.c_longlong(H), C.c_longlong(1), vp(g), K, H, vp(out), C.c_longlong(H), C.c_longlong(1), None))
+    guard.check()
     np.testing.assert_array_equal(out, O.cost_to_go(costs.copy(), gs))
