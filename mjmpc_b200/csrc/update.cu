@@ -23,7 +23,11 @@ static int load_gamma(GammaSeq& G, const double* host, int H) {
     return MJB_OK;
 }
 
+// Order-preserving 64-bit key of a double.  -0.0 is folded onto +0.0 first: numpy compares them equal, so a tie
+// between the two must go to the lower index like any other tie (np.argmin / the stable sort order), not to the
+// one whose sign bit happens to be set (costs = -rewards turns a reward of 0.0 into a cost of -0.0).
 __device__ __forceinline__ unsigned long long enc_key(double x) {
+    x = (x == 0.0) ? 0.0 : x;
     const unsigned long long b = (unsigned long long)__double_as_longlong(x);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }

@@ -159,6 +159,14 @@ def test_argmin_blend_resample_gather_mean(L):
     idx = np.zeros(1, np.int64); val = np.zeros(1)
     ok(L, L.mjb_argmin(vp(ctg0), C.c_longlong(K), vp(idx), vp(val), None))
     assert idx[0] == 200 == np.argmin(ctg0) and val[0] == ctg0[200]
+    # -0.0 and +0.0 compare equal in numpy: the tie goes to the lower index (costs = -rewards makes -0.0 out of 0.0)
+    z = np.abs(ctg0) + 1.0; z[40] = 0.0; z[90] = -0.0; z[7] = 0.0
+    idx2 = np.zeros(1, np.int64); val2 = np.zeros(1)
+    ok(L, L.mjb_argmin(vp(z), C.c_longlong(K), vp(idx2), vp(val2), None))
+    assert idx2[0] == 7 == np.argmin(z)
+    flags = np.zeros(K, np.uint8); sel = np.zeros(2, np.int64); scr = np.zeros(4096, np.uint8)
+    ok(L, L.mjb_select_elites(vp(z), C.c_longlong(K), C.c_longlong(2), vp(flags), vp(sel), vp(scr), None))
+    np.testing.assert_array_equal(np.flatnonzero(flags), [7, 40])
     m = mean.copy()
     ok(L, L.mjb_blend_best(vp(actions), C.c_longlong(H * d), C.c_longlong(d), C.c_longlong(1), vp(idx), C.c_longlong(0),
                            K, H, d, C.c_double(0.6), vp(m), None))

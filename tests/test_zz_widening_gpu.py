@@ -134,3 +134,25 @@ def test_batched_instances_take_state_rows():
         np.testing.assert_array_equal(o[1], outs[0][1])
     with pytest.raises(ValueError):
         GpuReacherVecEnv(cm).set_env_state(np.zeros((2, 5)))
+
+
+def test_signed_zero_costs_tie_like_numpy():
+    """A reward of exactly 0.0 becomes a cost of -0.0 under `costs = -rewards`; numpy compares -0.0 == +0.0, so
+    argmin / the elite set break that tie by index, not by sign bit."""
+    import ctypes as C
+    import torch
+    from mjmpc_b200 import _lib
+    K = 3000
+    z = np.abs(np.random.RandomState(0).normal(2, 1, K)) + 1.0
+    z[40] = 0.0; z[90] = -0.0; z[7] = 0.0; z[2999] = -0.0
+    zt = torch.from_numpy(z).cuda()
+    idx = torch.zeros(1, dtype=torch.int64, device="cuda"); val = torch.zeros(1, dtype=torch.float64, device="cuda")
+    L = _lib.lib()
+    _lib.check(L.mjb_argmin(_lib.ptr(zt), C.c_longlong(K), _lib.ptr(idx), _lib.ptr(val), _lib.stream_ptr()))
+    assert int(idx.item()) == 7 == int(np.argmin(z))
+    flags = torch.zeros(K, dtype=torch.uint8, device="cuda"); sel = torch.zeros(3, dtype=torch.int64, device="cuda")
+    scr = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    _lib.check(L.mjb_select_elites(_lib.ptr(zt), C.c_longlong(K), C.c_longlong(3), _lib.ptr(flags), _lib.ptr(sel), _lib.ptr(scr),
+                                   _lib.stream_ptr()))
+    np.testing.assert_array_equal(np.flatnonzero(flags.cpu().numpy()), [7, 40, 90])
+    np.testing.assert_array_equal(np.sort(sel.cpu().numpy()), np.sort(np.argsort(z, kind="stable")[:3]))
