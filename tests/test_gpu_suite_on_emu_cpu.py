@@ -33,7 +33,7 @@ def test_update_kernels_do_not_depend_on_thread_order():
     and passes in descending order).  The controller / update / noise tests again, with a fresh random order on
     every scheduling pass: correctly synchronised kernels cannot tell the difference."""
     env = dict(os.environ, MJB_TEST_EMU="1", MJB_EMU_ORDER="shuffle")
-    files = [os.path.join(ROOT, "tests", f) for f in ("test_controllers_gpu.py", "test_native_step_gpu.py",
+    files = [os.path.join(ROOT, "tests", f) for f in ("test_controllers_gpu.py", "test_zz_native_step_gpu.py",
                                                       "test_zzz_controllers_fuzz_gpu.py", "test_noise_gpu.py")]
     r = subprocess.run([sys.executable, "-m", "pytest"] + files + ["-m", "gpu", "-q", "-x", "-n", "4", "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=1500)

@@ -1,6 +1,8 @@
 """mjb_softmax_mpc_step: the whole MPC step of MPPI / DMD-MPC behind one native call must be bit-identical to the
 step-by-step path (the same kernels launched one by one from Python, MJB_FUSED_STEP=0) -- actions, mean and
-covariance over several hot-started steps, for every option that changes the launch sequence."""
+covariance over several hot-started steps, for every option that changes the launch sequence.
+(Written without GPU access: sorts after the suites that have run on hardware, so that a surprise here cannot hide
+them behind `-x`.)"""
 import os
 import threading
 
