@@ -156,3 +156,19 @@ def test_signed_zero_costs_tie_like_numpy():
                                    _lib.stream_ptr()))
     np.testing.assert_array_equal(np.flatnonzero(flags.cpu().numpy()), [7, 40, 90])
     np.testing.assert_array_equal(np.sort(sel.cpu().numpy()), np.sort(np.argsort(z, kind="stable")[:3]))
+
+
+@pytest.mark.parametrize("d", [2, 3, 4, 5, 6, 8])
+def test_noise_kernel_every_action_dimension(d):
+    """K2 is instantiated for d_action = 1..8 (1 and 7 are covered in test_noise_gpu.py): full covariance and the
+    AR filter for the other sizes."""
+    from mjmpc_b200.utils.control_utils import generate_noise
+    rng = np.random.default_rng(d)
+    A = rng.normal(0, 1, (d, d))
+    cov = A @ A.T / d + 0.2 * np.eye(d)
+    b = (0.25, 0.8, 0.1)
+    eps = generate_noise(cov, b, (80000, 4), 3, step=1).cpu().numpy()
+    assert eps.shape == (80000, 4, d) and np.isfinite(eps).all()
+    np.testing.assert_allclose(np.cov(eps[:, 0].T), cov, atol=0.05)
+    z = (eps[:, 2:] - b[1] * eps[:, 1:-1] - b[2] * eps[:, :-2]) / b[0]
+    np.testing.assert_allclose(np.cov(z[:, 0].T), cov, atol=0.05)
