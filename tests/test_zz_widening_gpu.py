@@ -172,3 +172,53 @@ def test_noise_kernel_every_action_dimension(d):
     np.testing.assert_allclose(np.cov(eps[:, 0].T), cov, atol=0.05)
     z = (eps[:, 2:] - b[1] * eps[:, 1:-1] - b[2] * eps[:, :-2]) / b[0]
     np.testing.assert_allclose(np.cov(z[:, 0].T), cov, atol=0.05)
+
+
+@pytest.mark.parametrize("name", ["mppi", "cem", "dmd", "random_shooting"])
+def test_unmodified_reference_controller_on_this_rollout_backend(name, monkeypatch):
+    """SURVEY 8(f-1), from the other side: the reference's own controller class (imported read-only from
+    /root/reference, so this runs where that tree exists -- the container, under the host emulation -- and is
+    skipped on the GPU box) drives this package's rollout backend through the injected rollout_fn /
+    set_sim_state_fn with numpy arrays, exactly as examples/example_mpc.py:154-155 wires it.  Fed the same noise,
+    this package's controller must produce the same actions over several hot-started MPC steps."""
+    import os
+    import sys
+    import torch
+    from conftest import ROOT, synthetic_state
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import refload
+    if not refload.available():
+        pytest.skip("reference tree not present")
+    R = refload.load()
+    import mjmpc_b200.control as ctl
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    from mjmpc_b200.envs.model import compile_model, reacher7dof_spec
+    monkeypatch.setenv("MJB_FUSED_STEP", "0")          # the step-by-step path calls sample_noise(), patched below
+    cm = compile_model(reacher7dof_spec())
+    K, H = 128, 10
+    common = dict(d_state=25, d_obs=20, d_action=7, horizon=H, init_cov=0.8, base_action='null', num_particles=K,
+                  step_size=0.9, gamma=0.98, n_iters=1, action_lows=-np.ones(7), action_highs=np.ones(7),
+                  filter_coeffs=[0.25, 0.8, 0.0], seed=17)
+    extra = dict(mppi=dict(lam=0.3, alpha=0), cem=dict(elite_frac=0.25, beta=0.1, cov_type='diagonal'),
+                 dmd=dict(lam=0.3, beta=0.1, update_cov=True, cov_type='full'), random_shooting=dict())[name]
+    ref_cls = dict(mppi=R.mppi.MPPI, cem=R.cem.CEM, dmd=R.dmd.DMDMPC, random_shooting=R.rs.RandomShooting)[name]
+    own_cls = dict(mppi=ctl.MPPI, cem=ctl.CEM, dmd=ctl.DMDMPC, random_shooting=ctl.RandomShooting)[name]
+    states = [synthetic_state(cm, 60 + s) for s in range(4)]
+
+    env_r = GpuReacherVecEnv(cm)
+    ref = ref_cls(**common, **extra)
+    ref.set_sim_state_fn = env_r.set_env_state
+    ref.rollout_fn = env_r.rollout_fn
+    want = np.stack([ref.optimize(dict(s))[0] for s in states])
+
+    env_o = GpuReacherVecEnv(cm)
+    own = own_cls(**common, **extra)
+    own.set_sim_state_fn = env_o.set_env_state
+    own.rollout_fn = env_o.rollout_fn
+    own.sample_noise = lambda: torch.from_numpy(R.control_utils.generate_noise(
+        own.cov_action, own.filter_coeffs, (K, H), own.seed_val + own.num_steps)).cuda()
+    got = np.stack([own.optimize(dict(s))[0] for s in states])
+    np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(own.mean_action, ref.mean_action, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(own.cov_action, ref.cov_action, rtol=1e-8, atol=1e-10)
+    env_r.close(); env_o.close()
