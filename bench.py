@@ -36,6 +36,7 @@ FLOP_PER_PARTICLE_STEP = 5340.0          # BASELINE.md section 4 / SURVEY 8(d): 
 MPPI_PARAMS = dict(horizon=HORIZON, init_cov=1.0, filter_coeffs=[0.25, 0.8, 0.0], gamma=1.0, n_iters=1,
                    step_size=1.0, lam=0.2, alpha=1, base_action='null')     # reacher_7dof-v0.yml:20-30 + :5
 KERNELS_PER_STEP = 9     # noise, rollout, softmax {prep, traj_cost, weighted_reduce, decode_min, chunk_sum}, combine, shift
+#                          (counted inside the host emulation by tests/test_zz_native_step_gpu.py)
 
 
 def synthetic_states(compiled, n, seed=0):

@@ -127,7 +127,9 @@ inline void run_block(BlockCtx& c, dim3 block, unsigned bx, unsigned by, unsigne
     }
 }
 
+inline std::atomic<unsigned long long> g_launches{0};      // kernels launched so far (tests count launches per step)
 template <class F> void launch(dim3 grid, dim3 block, size_t smem, cudaStream_t, F f) {
+    g_launches.fetch_add(1);
     const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
     std::atomic<unsigned long long> next{0};
     auto worker = [&] {

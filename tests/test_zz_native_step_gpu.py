@@ -157,3 +157,34 @@ def test_native_step_with_peer_exchange_two_logical_ranks(compiled_model, cls, m
     for _, e in ranks:
         e.close()
     env0.close()
+
+
+def test_kernel_launches_per_mppi_step_match_the_bench_claim(compiled_model, monkeypatch):
+    """bench.py reports gpu_launches = KERNELS_PER_STEP x steps.  Host emulation only: count the kernel launches of
+    one hot-started MPPI step (n_iters = 1) on both the native and the step-by-step path."""
+    if os.environ.get("MJB_TEST_EMU") != "1":
+        pytest.skip("host emulation only (counts launches inside the emulator)")
+    import ctypes
+    import sys
+    from conftest import ROOT
+    from mjmpc_b200 import _lib
+    sys.path.insert(0, ROOT)
+    import bench
+    import mjmpc_b200.control as ctl
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    L = _lib.lib()
+    L.emu_launch_count.restype = ctypes.c_ulonglong
+    for fused in ("1", "0"):
+        monkeypatch.setenv("MJB_FUSED_STEP", fused)
+        env = GpuReacherVecEnv(compiled_model)
+        params = dict(bench.MPPI_PARAMS)
+        params.update(horizon=8)
+        c = ctl.MPPI(num_particles=256, seed=1, **params, **COMMON)
+        c.set_sim_state_fn, c.rollout_fn = env.set_env_state, env.rollout_fn
+        st = synthetic_state(compiled_model, 1)
+        c.optimize(st)                                   # first step: buffers, model upload
+        env.set_env_state(st)
+        n0 = L.emu_launch_count()
+        c.step_device(None)
+        assert L.emu_launch_count() - n0 == bench.KERNELS_PER_STEP, (fused, L.emu_launch_count() - n0)
+        env.close()
