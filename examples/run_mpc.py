@@ -17,6 +17,7 @@ import yaml
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mjmpc_b200.envs.gpu_reacher_env import GpuContinualReacherEnv, GpuReacherEnv          # noqa: E402
 from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv            # noqa: E402
+from mjmpc_b200.envs.gpu_pendulum import GpuPendulumEnv, GpuPendulumVecEnv    # noqa: E402
 from mjmpc_b200.policies import MPCPolicy                           # noqa: E402
 
 
@@ -38,7 +39,7 @@ def load_policy_params(exp_params, controller_name, env):
 
 
 def main():
-    parser = argparse.ArgumentParser(description='Run MPC algorithm on the GPU reacher')
+    parser = argparse.ArgumentParser(description='Run an MPC algorithm on the GPU backend (reacher_7dof-v0, continual_reacher-v0, SimplePendulum-v0)')
     parser.add_argument('--config', type=str, required=True, help='yaml file with experiment parameters')
     parser.add_argument('--dyn_randomize_config', type=str, help='yaml file with dynamics randomization parameters')
     parser.add_argument('--controller', type=str, default='mppi', help='controller to run')
@@ -51,17 +52,23 @@ def main():
     if args.dyn_randomize_config is not None:
         with open(args.dyn_randomize_config) as file:
             dynamics_rand_params = yaml.load(file, Loader=yaml.FullLoader)
-    plants = {'reacher_7dof-v0': GpuReacherEnv, 'continual_reacher-v0': GpuContinualReacherEnv}   # mjmpc/envs/__init__.py:24-35
+    # env name -> (plant, planner's rollout backend)                                mjmpc/envs/__init__.py:5-35
+    plants = {'reacher_7dof-v0': (GpuReacherEnv, GpuReacherVecEnv), 'continual_reacher-v0': (GpuContinualReacherEnv, GpuReacherVecEnv),
+              'SimplePendulum-v0': (GpuPendulumEnv, GpuPendulumVecEnv)}
     if exp_params['env_name'] not in plants:
         raise NotImplementedError("only %s have a GPU plant; see DESIGN.md section 6" % sorted(plants))
-    env = plants[exp_params['env_name']]()
+    plant_cls, sim_cls = plants[exp_params['env_name']]
+    reacher = sim_cls is GpuReacherVecEnv
+    env = plant_cls()
     policy_params, num_cpu = load_policy_params(exp_params, args.controller, env)
     n_episodes = args.n_episodes or exp_params['n_episodes']
     base_seed = exp_params['seed']
     ep_length = exp_params['max_ep_length']
 
-    sim_env = GpuReacherVecEnv(n_workers=num_cpu)
+    sim_env = GpuReacherVecEnv(n_workers=num_cpu) if reacher else sim_cls()
     if dynamics_rand_params is not None:
+        if not reacher:
+            raise NotImplementedError("dynamics randomisation is implemented for the reacher model")
         default_params, randomized_params = sim_env.randomize_dynamics(dynamics_rand_params, base_seed=base_seed)
         print('Randomized params (worker 0) = {}'.format(randomized_params[0]))
 
@@ -84,11 +91,14 @@ def main():
             action, value = policy.get_action(curr_state, calc_val=False)
             obs, reward, done, info = env.step(action)
             ep_rewards[i] += reward
-            infos.append(info['goal_achieved'])
-            dists.append(np.linalg.norm(obs[17:20]))
+            infos.append(info.get('goal_achieved', False))
+            dists.append(np.linalg.norm(obs[17:20]) if reacher else abs(np.arctan2(obs[1], obs[0])))
         trajectories.append(dict(env_infos=dict(goal_achieved=np.array(infos))))
-        print('episode %d: reward %.2f, hand-target distance %.3f -> %.3f, goal steps %d'
-              % (i, ep_rewards[i], dists[0], dists[-1], int(np.sum(infos))))
+        if reacher:
+            print('episode %d: reward %.2f, hand-target distance %.3f -> %.3f, goal steps %d'
+                  % (i, ep_rewards[i], dists[0], dists[-1], int(np.sum(infos))))
+        else:
+            print('episode %d: reward %.2f, |angle from upright| %.3f -> %.3f rad' % (i, ep_rewards[i], dists[0], dists[-1]))
     dt = time.time() - t0
     print('Avg. reward = {0}, Std. Reward = {1}, Success Metric = {2}'.format(
         np.average(ep_rewards), np.std(ep_rewards), env.evaluate_success(trajectories)))

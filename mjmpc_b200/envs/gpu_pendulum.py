@@ -77,3 +77,48 @@ class GpuPendulumVecEnv:
                 return {k: np.ascontiguousarray(v.cpu().numpy()) for k, v in out.items()}
             return out
         return fn
+
+
+class GpuPendulumEnv:
+    """The PLANT for ``SimplePendulum-v0`` (``mjmpc/envs/__init__.py:5-9``, ``pendulum.py:7-103``): one pendulum
+    advanced by the same kernel the planner rolls out (K = 1, H = 1), with the reference env's ``reset`` /
+    ``step`` / ``get_env_state`` / ``set_env_state`` / ``get_obs`` / ``evaluate_success`` surface."""
+    _max_episode_steps = 200
+    d_obs, d_state, d_action = GpuPendulumVecEnv.d_obs, GpuPendulumVecEnv.d_state, GpuPendulumVecEnv.d_action
+
+    def __init__(self, device: int = 0, seed=None):
+        self.sim = GpuPendulumVecEnv(device=device)
+        self.action_lows, self.action_highs = self.sim.action_lows, self.sim.action_highs
+        self.np_random = np.random.RandomState(seed)
+        self.state = np.zeros(2)
+
+    def reset(self, seed=None):
+        """pendulum.py:52-56: theta ~ U(-pi, pi), thetadot ~ U(-1, 1) from the env's generator."""
+        if seed is not None:
+            self.np_random = np.random.RandomState(seed)
+        high = np.array([np.pi, 1])
+        self.state = self.np_random.uniform(low=-high, high=high)
+        return self.get_obs()
+
+    def get_obs(self):
+        theta, thetadot = self.state
+        return np.array([np.cos(theta), np.sin(theta), thetadot])
+
+    def get_env_state(self):
+        return {'state': self.state.copy()}
+
+    def set_env_state(self, state_dict):
+        self.state = np.asarray(state_dict['state'], float).reshape(2).copy()
+
+    def step(self, u):
+        self.sim.set_env_state(self.get_env_state())
+        mean = torch.as_tensor(np.asarray(u, np.float64).reshape(1, 1), device=self.sim.device)
+        out = self.sim.rollout_device(1, 1, mean, None, want_states=True)
+        self.state = out["states"][0, 0].cpu().numpy().copy()
+        return self.get_obs(), -float(out["costs"][0, 0].item()), False, {}
+
+    def evaluate_success(self, trajectories):
+        return 0.0                      # pendulum.py:102-103
+
+    def close(self):
+        self.sim.close()

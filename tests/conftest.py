@@ -25,7 +25,7 @@ def pytest_configure(config):
 _EMU_IMPOSSIBLE = {
     "test_cuda_graph_step_equals_eager": "CUDA graphs are not emulated",
     "test_fused_noise_controller_equals_two_kernel_path[True]": "CUDA graphs are not emulated",
-    "test_example_driver_runs": "child process without the emulation shim",
+    "test_example_driver_runs": "child process without the emulation shim",      # (prefix: both driver tests)
     "test_multigpu_gpu.py": "needs real NCCL ranks",
 }
 _EMU_SLOW = {       # (BASELINE sizes, K = 65536, take ~10 s per test on the fiber emulator and stay in)

@@ -222,3 +222,36 @@ def test_unmodified_reference_controller_on_this_rollout_backend(name, monkeypat
     np.testing.assert_allclose(own.mean_action, ref.mean_action, rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(own.cov_action, ref.cov_action, rtol=1e-8, atol=1e-10)
     env_r.close(); env_o.close()
+
+
+def test_pendulum_plant_follows_the_reference_env():
+    """GpuPendulumEnv (the plant of SimplePendulum-v0) against the golden trajectory of the reference's PendulumEnv:
+    same states, rewards and observations step by step; reset draws like pendulum.py:52-56."""
+    from golden_util import load
+    from mjmpc_b200.envs.gpu_pendulum import GpuPendulumEnv
+    g = load("pendulum")
+    env = GpuPendulumEnv(seed=3)
+    ob = env.reset()
+    rng = np.random.RandomState(3)
+    high = np.array([np.pi, 1])
+    np.testing.assert_array_equal(env.get_env_state()["state"], rng.uniform(low=-high, high=high))
+    np.testing.assert_allclose(ob, [np.cos(env.state[0]), np.sin(env.state[0]), env.state[1]], rtol=0, atol=0)
+    env.set_env_state(dict(state=g["state0"]))
+    for t in range(g["mean"].shape[0]):
+        ob, rew, done, info = env.step(g["mean"][t] + g["noise"][0, t])
+        np.testing.assert_allclose(env.state, g["states"][0, t], rtol=1e-13, atol=1e-14)
+        assert rew == pytest.approx(-g["costs"][0, t], rel=1e-13, abs=1e-14) and done is False
+    assert env.evaluate_success([]) == 0.0 and env._max_episode_steps == 200
+    env.close()
+
+
+def test_example_driver_runs_the_pendulum_config():
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "run_mpc.py"), "--config",
+                        os.path.join(ROOT, "examples", "configs", "simple_pendulum-v0.yml"), "--controller", "cem",
+                        "--n_episodes", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "Avg. reward" in r.stdout
