@@ -97,6 +97,13 @@ class OLGaussianMPC(Controller):
         self._cov = self._to_device(value).reshape(self.d_action, self.d_action).contiguous()
 
     # ---- sharding ----------------------------------------------------------------------------------
+    def set_instance_offset(self, first_instance: int):
+        """Batched independent instances partitioned over several GPUs (no collective): this controller holds
+        instances [first_instance, first_instance + batch_size) of the sweep.  Only the Philox particle ids move,
+        so every instance draws the noise it would draw in the single-GPU sweep."""
+        self._particle_id_offset = int(first_instance) * self.num_particles
+        self.__dict__.pop("_fused_blocks", None)
+
     @property
     def local_particles(self):
         return self.shard.local_range(self.num_particles)[1] * self.batch_size

@@ -144,12 +144,14 @@ class GpuReacherVecEnv:
     def close(self):
         self.model.close()
 
-    def randomize_dynamics(self, param_dict, base_seed):
+    def randomize_dynamics(self, param_dict, base_seed, worker_offset=0):
         """Per-worker model perturbation, worker i seeded with base_seed + i*12345
-        (subproc_vec_env.py:304-312 -> gym_env_wrapper.py:367-416)."""
+        (subproc_vec_env.py:304-312 -> gym_env_wrapper.py:367-416).  ``worker_offset``: global index of this
+        backend's first worker when a sweep's instances are partitioned over several GPUs (each rank then draws
+        the models the single-GPU sweep would have drawn for its block)."""
         defaults, randomized = [], []
         for i in range(self.n_workers):
-            rng = np.random.RandomState(base_seed + i * 12345)
+            rng = np.random.RandomState(base_seed + (worker_offset + i) * 12345)
             m, d, r = randomized_copy(self.compiled, param_dict, rng, self._defaults[i])
             self._worker_models[i] = m
             defaults.append(d)

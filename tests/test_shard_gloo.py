@@ -100,6 +100,32 @@ def test_two_rank_gloo_sharded_controllers_match_unsharded_on_the_host_emulation
         assert "multigpu %-6s ok" % name in r.stdout, r.stdout[-2000:]
 
 
+def test_partitioned_sweep_is_independent_of_the_number_of_ranks():
+    """BASELINE configs[4] shape: examples/run_sweep.py (independent MPPI instances with per-instance randomised
+    dynamics, partitioned over ranks with no data-path collective) on the host emulation with one rank and with
+    two gloo ranks: models, start states and noise are keyed by the global instance index, so the gathered
+    results must be bit-identical."""
+    import json
+    import subprocess
+    sys.path.insert(0, os.path.join(ROOT, "tests", "helpers"))
+    import emu_device
+    emu_device.build_lib()
+    run = os.path.join(ROOT, "tests", "helpers", "run_on_emu.py")
+    script = [run, "script", os.path.join(ROOT, "examples", "run_sweep.py"), "--instances", "8", "--steps", "3"]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    one = subprocess.run([sys.executable] + script, env=env, capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0, one.stdout[-2000:] + one.stderr[-2000:]
+    port = 29650 + (os.getpid() % 300)
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port)] + script + ["--backend", "gloo"],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert two.returncode == 0, two.stdout[-2000:] + two.stderr[-2000:]
+    a = json.loads([l for l in one.stdout.splitlines() if l.startswith("{")][-1])
+    b = json.loads([l for l in two.stdout.splitlines() if l.startswith("{")][-1])
+    assert (a["n_gpus"], b["n_gpus"], b["instances_per_gpu"]) == (1, 2, 4)
+    assert a["result_sha1"] == b["result_sha1"]
+
+
 def test_single_process_shard_context():
     from mjmpc_b200.utils.shard import ShardContext
     s = ShardContext()

@@ -21,6 +21,7 @@ if [ -d gpurun_variants ]; then
   python tools/k1_variants.py run 8192 > $OUT/k1_variants_8192.jsonl 2>> $OUT/log.txt
 fi
 python tools/bench_configs.py > $OUT/configs.jsonl 2>> $OUT/log.txt
+python examples/run_sweep.py --instances 1024 --steps 100 > $OUT/sweep_1gpu.json 2>> $OUT/log.txt
 # per-kernel launch list of the bench command (cold-cache, serialised: shares, not absolutes) and one full capture
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
