@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""A sweep of independent MPPI controllers with per-instance randomised dynamics (BASELINE.json configs[4]; the
+"""A sweep of independent MPPI (or PFMPC) controllers with per-instance randomised dynamics (BASELINE.json configs[4]; the
 reference runs such sweeps as separate jobs, examples/job_script.py:186-217, and randomises per worker,
 subproc_vec_env.py:304-312), partitioned over the GPUs of one box WITHOUT any collective in the data path:
 
@@ -22,7 +22,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from mjmpc_b200.control import MPPI                                  # noqa: E402
+from mjmpc_b200.control import MPPI, PFMPC                           # noqa: E402
 from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv             # noqa: E402
 from mjmpc_b200.envs.model import compile_model, reacher7dof_spec    # noqa: E402
 
@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--horizon", type=int, default=16)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--seed", type=int, default=123)
+    ap.add_argument("--controller", default="mppi", choices=["mppi", "pfmpc"])
     ap.add_argument("--backend", default="nccl", help="torch.distributed backend when launched with torchrun")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -58,9 +59,13 @@ def main():
     compiled = compile_model(reacher7dof_spec())
     env = GpuReacherVecEnv(compiled, n_workers=B, device=local)
     env.randomize_dynamics(RANDOMIZE, base_seed=args.seed, worker_offset=first)
-    ctrl = MPPI(d_state=env.d_state, d_obs=env.d_obs, d_action=7, action_lows=env.action_lows, action_highs=env.action_highs,
-                horizon=args.horizon, init_cov=1.0, base_action='null', lam=0.2, num_particles=args.particles, step_size=1.0,
-                alpha=1, gamma=1.0, n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=args.seed, batch_size=B, device=local)
+    common = dict(d_state=env.d_state, d_obs=env.d_obs, d_action=7, action_lows=env.action_lows, action_highs=env.action_highs,
+                  horizon=args.horizon, base_action='null', num_particles=args.particles, gamma=1.0, n_iters=1,
+                  filter_coeffs=[0.25, 0.8, 0.0], seed=args.seed, batch_size=B, device=local)
+    if args.controller == "mppi":
+        ctrl = MPPI(init_cov=1.0, lam=0.2, step_size=1.0, alpha=1, **common)
+    else:
+        ctrl = PFMPC(cov_shift=0.05, cov_resample=1.0, lam=0.2, **common)
     ctrl.set_instance_offset(first)
     ctrl.set_sim_state_fn, ctrl.rollout_fn = env.set_env_state, env.rollout_fn
     states = [torch.from_numpy(np.stack([start_state(compiled, first + b, s) for b in range(B)])).cuda() for s in range(4)]
@@ -89,7 +94,7 @@ def main():
         rows = np.concatenate(gathered, axis=0)
     if rank == 0:
         t = float(ms.item()) * 1e-3
-        print(json.dumps(dict(config="independent MPPI instances, per-instance randomised dynamics, no collective",
+        print(json.dumps(dict(config="independent %s instances, per-instance randomised dynamics, no collective" % args.controller.upper(),
                               instances=args.instances, n_gpus=world, instances_per_gpu=B, num_particles=args.particles,
                               horizon=args.horizon, steps=args.steps, ms_per_sweep_step=t / args.steps * 1e3,
                               controller_steps_per_s=args.instances * args.steps / t,

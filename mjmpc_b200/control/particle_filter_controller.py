@@ -53,6 +53,14 @@ class PFMPC(Controller):
                                        base_seed=self.seed_val, step=0, k_offset=k0 + self._particle_id_offset,
                                        K_global=self._particle_id_offset + self.num_particles * B, device=self.device)
 
+    def set_instance_offset(self, first_instance: int):
+        """Batched independent filters partitioned over several GPUs (no collective): this controller holds
+        instances [first_instance, first_instance + batch_size) of the sweep.  Moves the Philox particle ids and
+        re-draws the particle sets, so every instance starts from (and keeps drawing) what it would in the
+        single-GPU sweep."""
+        self._particle_id_offset = int(first_instance) * self.num_particles
+        self.reset()
+
     def _graphable(self):
         return False          # the resampler's r comes from Python's random module every step
 

@@ -100,8 +100,9 @@ def test_two_rank_gloo_sharded_controllers_match_unsharded_on_the_host_emulation
         assert "multigpu %-6s ok" % name in r.stdout, r.stdout[-2000:]
 
 
-def test_partitioned_sweep_is_independent_of_the_number_of_ranks():
-    """BASELINE configs[4] shape: examples/run_sweep.py (independent MPPI instances with per-instance randomised
+@pytest.mark.parametrize("controller", ["mppi", "pfmpc"])
+def test_partitioned_sweep_is_independent_of_the_number_of_ranks(controller):
+    """BASELINE configs[4] shape: examples/run_sweep.py (independent MPPI / PFMPC instances with per-instance randomised
     dynamics, partitioned over ranks with no data-path collective) on the host emulation with one rank and with
     two gloo ranks: models, start states and noise are keyed by the global instance index, so the gathered
     results must be bit-identical."""
@@ -111,7 +112,8 @@ def test_partitioned_sweep_is_independent_of_the_number_of_ranks():
     import emu_device
     emu_device.build_lib()
     run = os.path.join(ROOT, "tests", "helpers", "run_on_emu.py")
-    script = [run, "script", os.path.join(ROOT, "examples", "run_sweep.py"), "--instances", "8", "--steps", "3"]
+    script = [run, "script", os.path.join(ROOT, "examples", "run_sweep.py"), "--instances", "8", "--steps", "3",
+              "--controller", controller]
     env = dict(os.environ, OMP_NUM_THREADS="1")
     one = subprocess.run([sys.executable] + script, env=env, capture_output=True, text=True, timeout=600)
     assert one.returncode == 0, one.stdout[-2000:] + one.stderr[-2000:]
