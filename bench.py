@@ -282,6 +282,35 @@ def run_own(args):
             traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
     except Exception:
         pass
+    # ---- fresh per-part timings of this build (the committed ncu lists predate the last kernel changes): the
+    # noise kernel alone, and the same MPC step launched eagerly through the one-call native step (no graph).
+    # Informative extras: never allowed to take the bench line down.
+    breakdown = {"step_ms": dev_ms / args.steps, "rollout_ms": k1_ms}
+    try:
+        ns, ne = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctrl.sample_noise()
+        torch.cuda.synchronize()
+        ns.record()
+        for _ in range(reps):
+            ctrl.sample_noise()
+        ne.record()
+        torch.cuda.synchronize()
+        breakdown["noise_ms"] = ns.elapsed_time(ne) / reps
+        ctrl.disable_cuda_graph()
+        for i in range(3):
+            device_step(i)
+        torch.cuda.synchronize()
+        ns.record()
+        for i in range(50):
+            device_step(i)
+        ne.record()
+        torch.cuda.synchronize()
+        # rank-local clock on purpose (no collective inside this try block: an exception on one rank must not
+        # leave the others waiting); sharded steps are kept in lock step by their exchange kernel anyway
+        breakdown["eager_native_step_ms"] = ns.elapsed_time(ne) / 50
+        breakdown["eager_path"] = "mjb_softmax_mpc_step" if getattr(ctrl, "_fused_blocks", None) else "step by step"
+    except Exception as e:          # pragma: no cover
+        breakdown["error"] = repr(e)[:200]
     px = getattr(ctrl, "_px", {})
     exchange = ("none (single GPU)" if world == 1 else
                 "nvlink peer-memory exchange fused into the combine kernel" if any(v is not None for v in px.values())
@@ -318,6 +347,7 @@ def run_own(args):
                      "ms_per_launch": k1_ms, "particles_per_launch": kl,
                      "flop_per_particle_step": FLOP_PER_PARTICLE_STEP,
                      "peak_source": "mjb_fp64_peak microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)"},
+        "breakdown": breakdown,
         "clocks": clocks,
         "cpu_baseline": cpu,
     }
