@@ -1,10 +1,9 @@
 """The reduction / selection / resampling kernels of update.cu (K3-K8) and their launch code executed on the
-host by the block emulator (tests/hostcheck/block_emu.h: one OS thread per CUDA thread, real barriers, warp
-shuffles and atomics), through the same extern "C" entry points and argument structs as the product library,
+host by the block emulator (tests/hostcheck/block_emu.h: CUDA threads as fibers, cooperative barriers, warp
+shuffles, real atomics across concurrently running blocks), through the same extern "C" entry points and argument structs as the product library,
 against the numpy restatement of the reference (oracle/control_np.py, itself pinned to the reference goldens).
 Sizes are small (thousands of OS threads per launch) but span two particle chunks and ragged tails."""
 import ctypes as C
-import importlib.util
 import os
 
 import numpy as np
@@ -17,10 +16,11 @@ from oracle import control_np as O
 
 @pytest.fixture(scope="module")
 def L():
-    spec = importlib.util.spec_from_file_location("gen_update_emu", os.path.join(ROOT, "tests", "hostcheck", "gen_update_emu.py"))
-    gen = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(gen)
-    lib = C.CDLL(gen.build())
+    """The whole C ABI built for the host (tests/hostcheck/gen_lib_emu.py); this module uses its update.cu part."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "helpers"))
+    import emu_device
+    lib = C.CDLL(emu_device.build_lib())
     lib.mjb_last_error.restype = C.c_char_p
     lib.mjb_softmax_scratch_doubles.restype = C.c_longlong
     lib.mjb_elite_scratch_doubles.restype = C.c_longlong
