@@ -29,6 +29,34 @@ def _vp(a):
     return a.ctypes.data
 
 
+class _Guard:
+    """Every array handed to the kernel sources sits between bands of NaN sentinels: an out-of-bounds write
+    destroys a sentinel (check()), an out-of-bounds read pulls a NaN into a result the tests compare."""
+    bufs = []
+
+    @classmethod
+    def full(cls, shape, fill, dtype=np.float64, pad=128):
+        n = int(np.prod(shape))
+        sentinel = np.nan if np.dtype(dtype).kind == "f" else np.iinfo(dtype).min + 7
+        flat = np.full(n + 2 * pad, sentinel, dtype=dtype)
+        view = flat[pad:pad + n].reshape(shape)
+        view[...] = fill
+        cls.bufs.append((flat, pad, n, sentinel))
+        return view
+
+    @classmethod
+    def copy(cls, a):
+        a = np.ascontiguousarray(a, np.float64)
+        return cls.full(a.shape, a)
+
+    @classmethod
+    def check(cls):
+        for flat, pad, n, sentinel in cls.bufs:
+            band = np.concatenate([flat[:pad], flat[pad + n:]])
+            assert (np.isnan(band).all() if flat.dtype.kind == "f" else (band == sentinel).all()), "out-of-bounds write"
+        cls.bufs.clear()
+
+
 def _noise(emu, cov, b, K, H, seed, step=0, k_offset=0, K_global=None, zero_last_mean=None, layout="row"):
     cov = np.ascontiguousarray(cov, np.float64)
     d = cov.shape[0]
@@ -41,15 +69,16 @@ def _noise(emu, cov, b, K, H, seed, step=0, k_offset=0, K_global=None, zero_last
         zl = np.ascontiguousarray(zero_last_mean, np.float64)
         a.zero_last, a.neg_mean = 1, _vp(zl)
     if layout == "row":
-        out = np.full((K, H, d), np.nan)
+        out = _Guard.full((K, H, d), np.nan)
         a.out_sk, a.out_st, a.out_sj = H * d, d, 1
         view = out
     else:                                   # the product's particle-minor layout (H, d, K) viewed as (K, H, d)
-        out = np.full((H, d, K), np.nan)
+        out = _Guard.full((H, d, K), np.nan)
         a.out_sk, a.out_st, a.out_sj = 1, d * K, K
         view = out.transpose(2, 0, 1)
     a.out = _vp(out)
     assert emu.emu_generate_noise(C.byref(a)) == 0
+    _Guard.check()
     return view
 
 
@@ -99,32 +128,32 @@ def _rollout(emu, P, st, K, H, mean, noise, n_inst=1, traj=False, obs=False, nco
              particle_minor=False):
     a = _lib.RolloutArgs()
     a.K, a.H, a.particles_per_ctrl, a.particles_per_model = K, H, K, K // n_inst
-    state = np.ascontiguousarray(np.concatenate([st["qp"], st["qv"], st["target_pos"]]))
-    mean = np.ascontiguousarray(mean, np.float64)
+    state = _Guard.copy(np.concatenate([st["qp"], st["qv"], st["target_pos"]]))
+    mean = _Guard.copy(mean)
     a.state, a.mean = _vp(state), _vp(mean)
     keep = [state, mean]
     if noise is not None:
-        noise = np.ascontiguousarray(noise, np.float64)
+        noise = _Guard.copy(noise)
         a.noise = _vp(noise)
         a.noise_sk, a.noise_st, a.noise_sj = H * 7, 7, 1
         keep.append(noise)
     if particle_minor:
-        costs = np.full((H, K), np.nan); actions = np.full((H, 7, K), np.nan)
+        costs = _Guard.full((H, K), np.nan); actions = _Guard.full((H, 7, K), np.nan)
         a.costs_sk, a.costs_st = 1, K
         a.act_sk, a.act_st, a.act_sj = 1, 7 * K, K
         out = dict(costs=costs.T, actions=actions.transpose(2, 0, 1))
     else:
-        costs = np.full((K, H), np.nan); actions = np.full((K, H, 7), np.nan)
+        costs = _Guard.full((K, H), np.nan); actions = _Guard.full((K, H, 7), np.nan)
         a.costs_sk, a.costs_st = H, 1
         a.act_sk, a.act_st, a.act_sj = H * 7, 7, 1
         out = dict(costs=costs, actions=actions)
     a.costs, a.actions = _vp(costs), _vp(actions)
     if traj:
-        out["qv"] = np.full((K, H, 14), np.nan); a.qv_traj = _vp(out["qv"])
+        out["qv"] = _Guard.full((K, H, 14), np.nan); a.qv_traj = _vp(out["qv"])
     if obs:
-        out["next_observations"] = np.full((K, H, 20), np.nan); a.next_obs = _vp(out["next_observations"])
+        out["next_observations"] = _Guard.full((K, H, 20), np.nan); a.next_obs = _vp(out["next_observations"])
     if ncon:
-        out["ncon"] = np.zeros(K, np.int32); a.ncon = _vp(out["ncon"])
+        out["ncon"] = _Guard.full((K,), 0, np.int32); a.ncon = _vp(out["ncon"])
     a.closed_loop = 1 if closed else 0
     if fused is not None:
         cov, seed, step, b = fused
@@ -134,6 +163,9 @@ def _rollout(emu, P, st, K, H, mean, noise, n_inst=1, traj=False, obs=False, nco
         a.noise_k_offset, a.noise_K_global = 0, K
     params = np.ascontiguousarray(np.tile(P, (n_inst, 1)))
     assert emu.emu_rollout_reacher(C.c_void_p(_vp(params)), n_inst, C.byref(a)) == 0
+    _Guard.check()
+    for k in ("costs", "actions", "qv", "next_observations"):
+        assert k not in out or np.isfinite(out[k]).all(), k            # every output element written, no sentinel read
     return out
 
 
