@@ -190,7 +190,10 @@ def run_own(args):
             raise SystemExit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if args.backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:                                   # CPU dry runs of this script on the host emulation (tests/)
+            dist.init_process_group(args.backend)
     shard = ShardContext(rank, world)
     L = _lib.lib()
     compiled = compile_model(reacher7dof_spec())
@@ -377,6 +380,7 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=0,
                     help="particles per MPC iteration of the CPU sample (default: 32768 for cpu_baseline; sized to the step count for --impl reference)")
     ap.add_argument("--watchdog", type=int, default=600, help="abort if the whole run exceeds this many seconds")
+    ap.add_argument("--backend", default="nccl", help="torch.distributed backend for N > 1 (the driver's runs: nccl)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:

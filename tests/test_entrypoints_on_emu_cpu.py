@@ -56,3 +56,22 @@ def test_bench_reference_arm_runs_on_cpu():
                        env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), capture_output=True, text=True,
                        timeout=600, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_two_ranks_on_the_host_emulation():
+    """The N > 1 control flow of bench.py (sharded controller, barriers, max over ranks, rank 0 prints, the other
+    ranks stay silent) under torchrun with two gloo ranks on the host emulation."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "helpers"))
+    import emu_device
+    emu_device.build_lib()
+    port = 29800 + (os.getpid() % 150)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), RUN, "bench", "--particles", "256", "--gpus", "2", "--steps", "3",
+                        "--warmup", "3", "--backend", "gloo"], env=dict(os.environ, MJB_P2P="0", OMP_NUM_THREADS="1"),
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, lines                       # rank 0 only
+    line = json.loads(lines[0])
+    assert line["n_gpus"] == 2 and line["config"]["particles_per_gpu"] == 128 and line["cpu_baseline"] is None
+    assert line["exchange"].startswith("nccl") and "error" not in line["breakdown"]
