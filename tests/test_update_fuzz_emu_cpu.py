@@ -140,3 +140,111 @@ def test_cost_to_go_bit_exact_random_shapes(L, K, H, gamma, s):
     ok(L, L.mjb_cost_to_go(vp(costs), C.c_longlong(H), C.c_longlong(1), vp(g), K, H, vp(out), C.c_longlong(H), C.c_longlong(1), None))
     guard.check()
     np.testing.assert_array_equal(out, O.cost_to_go(costs.copy(), gs))
+
+
+def _ll(*xs):
+    return [C.c_longlong(int(x)) for x in xs]
+
+
+@settings(**SETTINGS)
+@given(K=st.one_of(st.integers(1, 70), st.integers(1, 1500)), H=st.integers(1, 9), d=st.integers(1, 8),
+       base=st.integers(0, 2), layout=st.sampled_from(["row", "particle_minor"]), s=st.integers(0, 2 ** 31 - 1))
+def test_particle_set_kernels_random_shapes(L, K, H, d, base, layout, s):
+    """PFMPC's particle-set kernels (shift + noise, gather, mean, deviation) and RandomShooting's blend at random
+    shapes in both memory layouts, against numpy restatements of particle_filter_controller.py:87,102,127-150,168
+    and random_shooting.py:61-62."""
+    rng = np.random.RandomState(s)
+    guard = Guard()
+
+    def alloc(a):       # -> (logical (K,H,d) view, the physical array to point at, element strides), inside guard bands
+        if layout == "row":
+            phys = guard(a)
+            return phys, phys, (H * d, d, 1)
+        phys = guard(np.ascontiguousarray(a.transpose(1, 2, 0)))          # (H,d,K)
+        return phys.transpose(2, 0, 1), phys, (1, d * K, K)
+
+    samples0 = rng.normal(0, 1, (K, H, d)); delta0 = rng.normal(0, 0.3, (K, H, d)); row = guard(rng.normal(0, 1, d))
+    samples, samples_p, ss = alloc(samples0)
+    delta, delta_p, ds = alloc(delta0)
+    ok(L, L.mjb_pf_shift(vp(samples_p), *_ll(*ss), vp(delta_p), *_ll(*ds), K, H, d, base, vp(row), None))
+    want = samples0.copy()
+    want[:, :-1] = want[:, 1:]
+    want = want + delta0
+    if base == 0:
+        want[:, -1] = 0.0
+    elif base == 1:
+        if H >= 2:
+            want[:, -1] = want[:, -2]
+    else:
+        want[:, -1] = row
+    np.testing.assert_array_equal(samples, want)
+    # gather + mean + deviation
+    idx = guard(rng.randint(0, K, K).astype(np.int64))
+    out, out_p, os_ = alloc(np.zeros((K, H, d)))
+    ok(L, L.mjb_gather_particles(vp(samples_p), *_ll(*ss), vp(idx), K, H, d, vp(out_p), *_ll(*os_), None))
+    np.testing.assert_array_equal(out, want[idx])
+    pm = guard(np.zeros((H, d))); scratch = guard(np.zeros(int(L.mjb_elite_scratch_doubles(K, H, d))))
+    ok(L, L.mjb_particle_mean(vp(out_p), *_ll(*os_), K, H, d, vp(scratch), vp(pm), None))
+    np.testing.assert_allclose(pm, want[idx].mean(0), rtol=1e-12, atol=1e-14)
+    sub, sub_p, sub_s = alloc(np.zeros((K, H, d)))
+    ok(L, L.mjb_particle_sub_mean(vp(out_p), *_ll(*os_), vp(pm), K, H, d, vp(sub_p), *_ll(*sub_s), None))
+    np.testing.assert_array_equal(sub, want[idx] - pm[None])
+    # RandomShooting: mean <- (1-step)*mean + step*actions[best]
+    best = guard(np.array([rng.randint(K)], np.int64)); mean = guard(rng.normal(0, 1, (H, d))); m0 = mean.copy()
+    ok(L, L.mjb_blend_best(vp(samples_p), *_ll(*ss), vp(best), C.c_longlong(0), K, H, d, C.c_double(0.7), vp(mean), None))
+    np.testing.assert_allclose(mean, (1 - 0.7) * m0 + 0.7 * want[best[0]], rtol=1e-14, atol=1e-15)
+    guard.check()
+
+
+@settings(**SETTINGS)
+@given(B=st.integers(1, 6), K=st.one_of(st.integers(1, 40), st.integers(1, 700)), H=st.integers(1, 9), d=st.integers(1, 8),
+       alpha=st.integers(0, 1), base=st.integers(0, 1), s=st.integers(0, 2 ** 31 - 1))
+def test_batched_instance_kernels_random_shapes(L, B, K, H, d, alpha, base, s):
+    """One thread block per controller instance (mjb_mppi_update_batched, mjb_pf_update_batched, the batched shift
+    and deviation): every instance must equal the single-controller numpy restatement."""
+    rng = np.random.RandomState(s)
+    guard = Guard()
+    lam = 0.4
+    costs = guard(np.abs(rng.normal(2, 1, (B * K, H)))); samples = guard(rng.normal(0, 1, (B * K, H, d)))
+    means = rng.normal(0, 0.2, (B, H, d)); cov = guard(np.diag(rng.uniform(0.4, 1.5, d)))
+    gs = O.gamma_seq(0.97, H); g = np.ascontiguousarray(gs.reshape(-1))
+    a = _lib.MppiBatchedArgs()
+    a.n_ctrl, a.K, a.H, a.d = B, K, H, d
+    a.costs = costs.ctypes.data; a.costs_sk, a.costs_st = H, 1
+    a.actions = samples.ctypes.data; a.act_sk, a.act_st, a.act_sj = H * d, d, 1
+    m = guard(means.copy()); val = guard(np.zeros(B))
+    a.mean, a.cov, a.gamma_seq, a.lam, a.step_size, a.value = m.ctypes.data, cov.ctypes.data, g.ctypes.data, lam, 0.9, val.ctypes.data
+    a.control_cost = int(alpha == 0)
+    ok(L, L.mjb_mppi_update_batched(C.byref(a), None))
+    for b in range(B):
+        sl = slice(b * K, (b + 1) * K)
+        want, _ = O.mppi_update(means[b], cov, costs[sl], samples[sl], gs, lam, alpha, 0.9)
+        np.testing.assert_allclose(m[b], want, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(val[b], O.mppi_value(means[b], cov, costs[sl], samples[sl], gs, lam, alpha), rtol=1e-10, atol=1e-12)
+    m1 = m.copy()
+    ok(L, L.mjb_shift_mean_batched(vp(m), B, H, d, base, None, None))
+    for b in range(B):
+        want = m1[b].copy(); want[:-1] = m1[b][1:]
+        want[-1] = 0.0 if base == 0 else (m1[b][-1] if H >= 2 else m1[b][-1])
+        np.testing.assert_array_equal(m[b], want)
+    p = _lib.PfBatchedArgs()
+    p.n_ctrl, p.K, p.H, p.d = B, K, H, d
+    p.costs = costs.ctypes.data; p.costs_sk, p.costs_st = H, 1
+    p.samples = samples.ctypes.data; p.s_sk, p.s_st, p.s_sj = H * d, d, 1
+    r = guard(rng.uniform(0, 1.0 / K, B))
+    w = guard(np.zeros(B * K)); idx = guard(np.zeros(B * K, np.int64)); out = guard(np.zeros((B * K, H, d))); pmean = guard(np.zeros((B, H, d)))
+    p.gamma_seq, p.lam, p.r = g.ctypes.data, lam, r.ctypes.data
+    p.weights, p.idx, p.out, p.mean = w.ctypes.data, idx.ctypes.data, out.ctypes.data, pmean.ctypes.data
+    p.o_sk, p.o_st, p.o_sj = H * d, d, 1
+    ok(L, L.mjb_pf_update_batched(C.byref(p), None))
+    for b in range(B):
+        sl = slice(b * K, (b + 1) * K)
+        np.testing.assert_allclose(w[sl], O.pf_weights(costs[sl], gs, lam), rtol=1e-10, atol=1e-300)
+        want = O.pf_resample_with_r(w[sl], r[b]) % K
+        np.testing.assert_array_equal(idx[sl], want)
+        np.testing.assert_array_equal(out[sl], samples[sl][want])
+        np.testing.assert_allclose(pmean[b], out[sl].mean(0), rtol=1e-12, atol=1e-14)
+    sub = guard(np.zeros((B * K, H, d)))
+    ok(L, L.mjb_particle_sub_mean_batched(vp(out), *_ll(H * d, d, 1), vp(pmean), B, K, H, d, vp(sub), *_ll(H * d, d, 1), None))
+    np.testing.assert_array_equal(sub, out - np.repeat(pmean, K, axis=0))
+    guard.check()
