@@ -203,6 +203,7 @@ def run_own(args):
                   action_highs=env.action_highs, num_particles=K_GLOBAL, seed=123, device=local_rank, shard=shard)
     policy = MPCPolicy("mppi", params)
     ctrl = policy.controller
+    ctrl.overlap_noise = bool(args.overlap_noise)
     ctrl.set_sim_state_fn = env.set_env_state
     ctrl.rollout_fn = env.rollout_fn
     states = synthetic_states(compiled, 64, seed=0)
@@ -344,6 +345,7 @@ def run_own(args):
                 "h2d_bytes_per_step": 17 * 8, "d2h_bytes_per_step": 7 * 8,
                 "api": "MPCPolicy.get_action(state_dict) -> (action ndarray, value)"},
         "gpu_launches": KERNELS_PER_STEP * args.steps, "cuda_graph": bool(graphed), "exchange": exchange,
+        "overlap_noise": bool(args.overlap_noise),
         "roofline": {"kernel": "rollout_reacher_kernel (K1)", "bound": "fp64", "achieved": achieved, "peak": tf.value,
                      "unit": "TFLOP/s", "frac": achieved / tf.value, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_hbm_bytes": kl * HORIZON * 120,
@@ -380,6 +382,8 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=0,
                     help="particles per MPC iteration of the CPU sample (default: 32768 for cpu_baseline; sized to the step count for --impl reference)")
     ap.add_argument("--watchdog", type=int, default=600, help="abort if the whole run exceeds this many seconds")
+    ap.add_argument("--overlap-noise", action="store_true",
+                    help="eager native step only (use with --no-graph, or N > 1): draw the next step's noise on a side stream")
     ap.add_argument("--backend", default="nccl", help="torch.distributed backend for N > 1 (the driver's runs: nccl)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -331,7 +331,12 @@ int mjb_pf_shift(double* samples, long long sk, long long st, long long sj, cons
 typedef struct {
     int n_iters;
     const mjb_noise_args* noise;       /* K2, re-run every iteration (same (seed, step): same samples; the zero
-                                          control sequence follows the updated mean); NULL = no noise kernel */
+                                          control sequence follows the updated mean); NULL = no noise kernel (the
+                                          rollout reads a tensor an earlier call's noise_next has filled) */
+    const mjb_noise_args* noise_next;  /* optional: the NEXT step's noise (it depends on (seed, step) only) drawn on a
+                                          side stream while this step rolls out -- forked after the work already on
+                                          `stream`, joined back before the call returns its stream to the caller; must
+                                          write a different tensor than the one this step's rollout reads.  NULL = off */
     const mjb_model* model;
     const mjb_rollout_args* rollout;
     const mjb_softmax_args* softmax;

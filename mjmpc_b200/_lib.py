@@ -187,7 +187,8 @@ class PfBatchedArgs(C.Structure):
 class MpcStepArgs(C.Structure):
     _fields_ = [
         ("n_iters", C.c_int),
-        ("noise", C.POINTER(NoiseArgs)), ("model", C.c_void_p), ("rollout", C.POINTER(RolloutArgs)),
+        ("noise", C.POINTER(NoiseArgs)), ("noise_next", C.POINTER(NoiseArgs)), ("model", C.c_void_p),
+        ("rollout", C.POINTER(RolloutArgs)),
         ("softmax", C.POINTER(SoftmaxArgs)), ("combine", C.POINTER(CombineArgs)),
         ("peer_bufs_dev", C.c_void_p), ("rank", C.c_int), ("seq", C.c_ulonglong),
         ("action_out", C.c_void_p), ("shift", C.c_int), ("base_action", C.c_int), ("cov_shift_beta", C.c_double),

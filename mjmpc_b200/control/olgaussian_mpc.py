@@ -59,6 +59,11 @@ class OLGaussianMPC(Controller):
         # instructions lengthen the latency-bound rollout by more (+0.09 ms) than the separate, fully
         # occupied noise kernel costs (0.065 ms).
         self.fuse_noise = False
+        # overlap_noise = True (native step only): the NEXT step's noise -- a function of (seed, step) alone when
+        # the covariance is fixed and there is no zero control sequence -- is drawn on a side stream while this
+        # step rolls out, into the second of two noise tensors.  Same samples, same results; off by default until
+        # it has been timed on hardware.
+        self.overlap_noise = False
         self._mean = self._mean_from(self.init_mean)
         self._cov = self._to_device(np.diag(self.init_cov)).contiguous()
         self._init_cov_d = self._to_device(self.init_cov)
@@ -302,9 +307,11 @@ class OLGaussianMPC(Controller):
             return None                 # NCCL all-gather between the two phases: host work inside the step
         if state is not None:
             self._set_sim_state_fn(copy.deepcopy(state))
+        overlap = bool(self.overlap_noise) and spec["cov_mode"] == _lib.COV_NONE and not self.use_zero_control_seq \
+            and self._noise_step is None
         key = (self._mean.data_ptr(), self._cov.data_ptr(), backend._state.data_ptr(), backend.model.handle.value,
                kl, H, self.n_iters, tuple(sorted(spec.items())), self.step_size, self.base_action, hotstart,
-               tuple(self.filter_coeffs), self.use_zero_control_seq, self.seed_val, self.gamma)
+               tuple(self.filter_coeffs), self.use_zero_control_seq, self.seed_val, self.gamma, overlap)
         blk = self.__dict__.get("_fused_blocks")
         if blk is None or blk["key"] != key:
             ns = self.noise_spec()
@@ -329,14 +336,35 @@ class OLGaussianMPC(Controller):
             st.shift = int(bool(hotstart))
             st.base_action = _lib.BASE_ACTIONS[self.base_action]
             st.cov_shift_beta = float(spec["cov_shift_beta"])
-            blk = dict(key=key, st=st, na=na, action=action, keep=(ra, sa, ca, nkeep, rout, skeep, stats, noise))
+            blk = dict(key=key, st=st, na=na, ra=ra, action=action, keep=(sa, ca, nkeep, rout, skeep, stats, noise))
+            if overlap:
+                # second noise tensor + its argument block; `ready` = (tensor index, step) of noise already drawn
+                noise_b = self._buf("noise_b", (H, d, kl)).permute(2, 0, 1)
+                nb, nbkeep = control_utils.noise_args(ns.cov, ns.filter_coeffs, ns.shape, ns.base_seed, step=0,
+                                                      stream_id=ns.stream_id, k_offset=ns.k_offset, K_global=ns.K_global,
+                                                      out=noise_b, device=self.device)
+                blk.update(nargs=(na, nb), bufs=(noise, noise_b), ready=None, keep2=(nbkeep, noise_b))
             self._fused_blocks = blk
         na = blk["na"]
-        if self._noise_step is not None:
+        st = blk["st"]
+        if overlap:
+            ready = blk["ready"]
+            cur = ready[0] if (ready is not None and ready[1] == self.num_steps) else 0
+            n_cur, n_next = blk["nargs"][cur], blk["nargs"][1 - cur]
+            n_cur.offset = control_utils.noise_offset(control_utils.NOISE_STREAM_ROLLOUT, self.num_steps)
+            n_next.offset = control_utils.noise_offset(control_utils.NOISE_STREAM_ROLLOUT, self.num_steps + 1)
+            buf = blk["bufs"][cur]
+            ra = blk["ra"]
+            ra.noise = buf.data_ptr()
+            ra.noise_sk, ra.noise_st, ra.noise_sj = buf.stride()
+            # this step's noise: already there when the previous step drew it, otherwise drawn in line
+            st.noise = None if (ready is not None and ready == (cur, self.num_steps)) else C.pointer(n_cur)
+            st.noise_next = C.pointer(n_next)
+            blk["ready"] = (1 - cur, self.num_steps + 1)
+        elif self._noise_step is not None:
             na.offset, na.step_ptr = control_utils.noise_offset(control_utils.NOISE_STREAM_ROLLOUT, 0), self._noise_step.data_ptr()
         else:
             na.offset, na.step_ptr = control_utils.noise_offset(control_utils.NOISE_STREAM_ROLLOUT, self.num_steps), None
-        st = blk["st"]
         if px is not None:
             st.seq = px.seq + 1
             px.seq += self.n_iters

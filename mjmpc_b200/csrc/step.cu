@@ -13,8 +13,8 @@
 extern "C" int mjb_softmax_mpc_step(const mjb_mpc_step_args* a, void* stream) {
     MJB_REQUIRE(a && a->model && a->rollout && a->softmax && a->combine, "mjb_softmax_mpc_step: null argument block");
     MJB_REQUIRE(a->n_iters >= 1, "mjb_softmax_mpc_step: n_iters must be >= 1");
-    MJB_REQUIRE(a->noise || a->rollout->noise_cov || !a->rollout->noise,
-                "mjb_softmax_mpc_step: the rollout reads a noise tensor that nothing in the step writes");
+    MJB_REQUIRE(!a->noise_next || (!a->noise_next->zero_last && a->combine->cov_mode == MJB_COV_NONE),
+                "mjb_softmax_mpc_step: the next step's noise depends on this step's result (zero control sequence / adapted covariance)");
     MJB_REQUIRE(a->base_action == MJB_BASE_NULL || a->base_action == MJB_BASE_REPEAT || !a->shift,
                 "mjb_softmax_mpc_step: base_action 'random' needs a host-drawn row; use the separate entry points");
     const mjb_combine_args* c = a->combine;
@@ -27,6 +27,28 @@ extern "C" int mjb_softmax_mpc_step(const mjb_mpc_step_args* a, void* stream) {
                 "mjb_softmax_mpc_step: rollout / softmax / combine shapes disagree");
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
+    bool forked = false;
+    static cudaStream_t side[64] = {nullptr};
+    static cudaEvent_t ev_fork[64] = {nullptr}, ev_join[64] = {nullptr};
+    const int dev = a->model->device & 63;
+    if (a->noise_next) {
+        // The next step's noise needs neither this step's state nor its mean: draw it on a side stream while the
+        // FP64-bound rollout leaves the integer / SFU pipes (and, in its second wave, a quarter of the registers)
+        // idle.  Fork behind everything already queued on `s` (the previous step's rollout was the last reader of
+        // the tensor being overwritten), join before returning.
+        MJB_REQUIRE(a->noise_next->out != a->rollout->noise, "mjb_softmax_mpc_step: noise_next would overwrite the tensor this step reads");
+        if (!side[dev]) {
+            MJB_CUDA(cudaSetDevice(a->model->device));
+            MJB_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+            MJB_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+            MJB_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
+        }
+        MJB_CUDA(cudaEventRecord(ev_fork[dev], s));
+        MJB_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
+        if ((rc = mjb_generate_noise(a->noise_next, (void*)side[dev])) != MJB_OK) return rc;
+        MJB_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
+        forked = true;
+    }
     for (int it = 0; it < a->n_iters; it++) {
         if (a->noise && (rc = mjb_generate_noise(a->noise, stream)) != MJB_OK) return rc;
         if ((rc = mjb_rollout_reacher(a->model, a->rollout, stream)) != MJB_OK) return rc;
@@ -44,5 +66,6 @@ extern "C" int mjb_softmax_mpc_step(const mjb_mpc_step_args* a, void* stream) {
             if ((rc = mjb_cov_add_diag(c->cov, c->d, a->cov_shift_beta, nullptr, stream)) != MJB_OK) return rc;
         }
     }
+    if (forked) MJB_CUDA(cudaStreamWaitEvent(s, ev_join[dev], 0));
     return MJB_OK;
 }

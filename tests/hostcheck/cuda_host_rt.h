@@ -26,6 +26,11 @@ inline cudaError_t props_(cudaDeviceProp* p) {
 #define cudaGetDeviceProperties(p, d) emu::props_(p)
 #define cudaDeviceGetAttribute(v, a, d) (*(v) = ((a) == cudaDevAttrMultiProcessorCount ? 148 : 1965000), cudaSuccess)
 #define cudaGetErrorString(e) "emulated runtime"
+// streams are synchronous and in order here: a side stream is just more work done at once
+#define cudaStreamCreateWithFlags(ps, f) (*(ps) = (cudaStream_t)1, cudaSuccess)
+#define cudaEventCreateWithFlags(pe, f) (*(pe) = (cudaEvent_t)1, cudaSuccess)
+#define cudaEventRecord(e, s) ((void)(e), (void)(s), cudaSuccess)
+#define cudaStreamWaitEvent(s, e, f) ((void)(s), (void)(e), cudaSuccess)
 
 #undef __constant__
 #define __constant__ static

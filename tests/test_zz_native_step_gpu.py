@@ -115,6 +115,7 @@ def test_native_step_with_peer_exchange_two_logical_ranks(compiled_model, cls, m
         c = getattr(ctl, cls)(horizon=H, num_particles=K, filter_coeffs=[0.25, 0.8, 0.0], seed=5, shard=shard, **kw, **COMMON)
         c.set_sim_state_fn = env.set_env_state
         c.rollout_fn = env.rollout_fn
+        c.overlap_noise = shard.world_size > 1 and cls == "MPPI"       # the sharded MPPI ranks also prefetch their noise
         return c, env
 
     ref, env0 = make(ShardContext())
@@ -188,3 +189,49 @@ def test_kernel_launches_per_mppi_step_match_the_bench_claim(compiled_model, mon
         c.step_device(None)
         assert L.emu_launch_count() - n0 == bench.KERNELS_PER_STEP, (fused, L.emu_launch_count() - n0)
         env.close()
+
+
+@pytest.mark.parametrize("name", ["mppi", "mppi_ctrlcost_repeat", "mppi_time_based_2iters", "dmd_fixed_cov"])
+def test_overlapped_noise_is_bit_identical(compiled_model, name, monkeypatch):
+    """overlap_noise: the next step's noise drawn on a side stream during this step's rollout, into the second of
+    two noise tensors -- same Philox counters, so actions and distribution must not change by a bit; a jump in
+    num_steps (stale prefetch) and a step without hotstart are handled."""
+    import mjmpc_b200.control as ctl
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    monkeypatch.setenv("MJB_FUSED_STEP", "1")
+    cls, kw = CASES[name]
+    outs = []
+    for overlap in (False, True):
+        env = GpuReacherVecEnv(compiled_model)
+        c = getattr(ctl, cls)(horizon=10, num_particles=512, filter_coeffs=[0.25, 0.8, 0.0], seed=11, **kw, **COMMON)
+        c.set_sim_state_fn, c.rollout_fn = env.set_env_state, env.rollout_fn
+        c.overlap_noise = overlap
+        acts = [c.optimize(synthetic_state(compiled_model, 70 + s))[0] for s in range(3)]
+        c.num_steps += 5                                              # the prefetched tensor no longer matches
+        acts += [c.optimize(synthetic_state(compiled_model, 80 + s), hotstart=(s != 1))[0] for s in range(3)]
+        if overlap:
+            assert c._fused_blocks["ready"] == (c._fused_blocks["ready"][0], c.num_steps)
+        outs.append((np.stack(acts), c.mean_action, c.cov_action))
+        env.close()
+    for k in range(3):
+        np.testing.assert_array_equal(outs[0][k], outs[1][k])
+
+
+def test_overlapped_noise_is_refused_when_the_noise_depends_on_the_step(compiled_model, monkeypatch):
+    """Adapted covariance (DMD-MPC update_cov) or the zero control sequence make the next step's noise a function
+    of this step's result: the controller silently keeps the in-line noise kernel."""
+    import mjmpc_b200.control as ctl
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    monkeypatch.setenv("MJB_FUSED_STEP", "1")
+    for name in ("dmd_full_cov", "mppi_zero_seq_2iters"):
+        cls, kw = CASES[name]
+        outs = []
+        for overlap in (False, True):
+            env = GpuReacherVecEnv(compiled_model)
+            c = getattr(ctl, cls)(horizon=8, num_particles=256, filter_coeffs=[0.25, 0.8, 0.0], seed=11, **kw, **COMMON)
+            c.set_sim_state_fn, c.rollout_fn = env.set_env_state, env.rollout_fn
+            c.overlap_noise = overlap
+            outs.append(np.stack([c.optimize(synthetic_state(compiled_model, 70 + s))[0] for s in range(3)]))
+            assert "ready" not in c._fused_blocks
+            env.close()
+        np.testing.assert_array_equal(outs[0], outs[1])

@@ -15,6 +15,8 @@ python bench.py --steps 300 --warmup 10 --impl reference --cpu-particles 8192 > 
 # eager step through the one-call native step vs the step-by-step Python path (host time between launches)
 python bench.py --steps 300 --warmup 10 --no-graph --no-cpu-baseline > $OUT/bench_nograph_native.json 2>> $OUT/log.txt
 MJB_FUSED_STEP=0 python bench.py --steps 300 --warmup 10 --no-graph --no-cpu-baseline > $OUT/bench_nograph_stepwise.json 2>> $OUT/log.txt
+# ... and with the next step's noise drawn on a side stream during the rollout (results bit-identical; DESIGN 4.1 queue item 2)
+python bench.py --steps 300 --warmup 10 --no-graph --overlap-noise --no-cpu-baseline > $OUT/bench_nograph_native_overlap.json 2>> $OUT/log.txt
 # rollout kernel: current build vs without the rank-one repair vs the previous commit; also the under-filled sizes
 if [ -d gpurun_variants ]; then
   python tools/k1_variants.py run 65536 > $OUT/k1_variants_65536.jsonl 2>> $OUT/log.txt
