@@ -3,7 +3,6 @@ same adaptor surface as :class:`GpuReacherVecEnv` (set_env_state / rollout / rol
 from __future__ import annotations
 
 import ctypes as C
-import time
 
 import numpy as np
 import torch

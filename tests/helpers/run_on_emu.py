@@ -5,7 +5,6 @@
     python tests/helpers/run_on_emu.py script path/to/script.py [arguments]
 
 A dry run of the Python around the kernels: numbers printed by it are meaningless."""
-import ctypes as C
 import os
 import runpy
 import sys

@@ -8,8 +8,7 @@ cases; a fixed seed keeps the suite deterministic."""
 import ctypes as C
 
 import numpy as np
-import pytest
-from hypothesis import HealthCheck, given, seed, settings
+from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
 from mjmpc_b200 import _lib
