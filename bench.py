@@ -389,6 +389,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.overlap_noise:
+        args.no_graph = True          # the overlap lives in the eager native step; a replayed graph would ignore it
     _watchdog(args.watchdog)
     if args.impl == "reference":
         run_reference(args)
