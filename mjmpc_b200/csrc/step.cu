@@ -34,24 +34,30 @@ extern "C" int mjb_softmax_mpc_step(const mjb_mpc_step_args* a, void* stream) {
     if (a->noise_next) {
         // The next step's noise needs neither this step's state nor its mean: draw it on a side stream while the
         // FP64-bound rollout leaves the integer / SFU pipes (and, in its second wave, a quarter of the registers)
-        // idle.  Fork behind everything already queued on `s` (the previous step's rollout was the last reader of
-        // the tensor being overwritten), join before returning.
+        // idle.  The fork point is everything already queued on `s` (the previous step's rollout was the last
+        // reader of the tensor being overwritten); the kernel itself is launched right AFTER this step's rollout
+        // and on a lowest-priority stream, so that the rollout's blocks take the SMs first and the noise blocks
+        // fill what they leave; joined before returning.
         MJB_REQUIRE(a->noise_next->out != a->rollout->noise, "mjb_softmax_mpc_step: noise_next would overwrite the tensor this step reads");
         if (!side[dev]) {
             MJB_CUDA(cudaSetDevice(a->model->device));
-            MJB_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+            int lo = 0, hi = 0;
+            MJB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));       // lo = least priority
+            MJB_CUDA(cudaStreamCreateWithPriority(&side[dev], cudaStreamNonBlocking, lo));
             MJB_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
             MJB_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
         }
         MJB_CUDA(cudaEventRecord(ev_fork[dev], s));
         MJB_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
-        if ((rc = mjb_generate_noise(a->noise_next, (void*)side[dev])) != MJB_OK) return rc;
-        MJB_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
-        forked = true;
     }
     for (int it = 0; it < a->n_iters; it++) {
         if (a->noise && (rc = mjb_generate_noise(a->noise, stream)) != MJB_OK) return rc;
         if ((rc = mjb_rollout_reacher(a->model, a->rollout, stream)) != MJB_OK) return rc;
+        if (a->noise_next && it == 0) {
+            if ((rc = mjb_generate_noise(a->noise_next, (void*)side[dev])) != MJB_OK) return rc;
+            MJB_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
+            forked = true;
+        }
         if ((rc = mjb_softmax_partials(a->softmax, stream)) != MJB_OK) return rc;
         if (c->n_shards == 1) rc = mjb_softmax_combine(c, stream);
         else rc = mjb_softmax_exchange_combine(c, a->softmax->partials, a->peer_bufs_dev, a->rank, a->seq + (unsigned long long)it, stream);

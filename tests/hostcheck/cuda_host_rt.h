@@ -28,6 +28,8 @@ inline cudaError_t props_(cudaDeviceProp* p) {
 #define cudaGetErrorString(e) "emulated runtime"
 // streams are synchronous and in order here: a side stream is just more work done at once
 #define cudaStreamCreateWithFlags(ps, f) (*(ps) = (cudaStream_t)1, cudaSuccess)
+#define cudaStreamCreateWithPriority(ps, f, p) (*(ps) = (cudaStream_t)1, cudaSuccess)
+#define cudaDeviceGetStreamPriorityRange(lo, hi) (*(lo) = 0, *(hi) = -5, cudaSuccess)
 #define cudaEventCreateWithFlags(pe, f) (*(pe) = (cudaEvent_t)1, cudaSuccess)
 #define cudaEventRecord(e, s) ((void)(e), (void)(s), cudaSuccess)
 #define cudaStreamWaitEvent(s, e, f) ((void)(s), (void)(e), cudaSuccess)
