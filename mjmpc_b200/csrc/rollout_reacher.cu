@@ -61,7 +61,14 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
         if (threadIdx.x == 0) noise_chol<7>(a.noise_cov, Lsh);
         __syncthreads();
     }
+#ifdef MJB_HALFWARP
+    // experiment (tools/k1_variants.py): 16 particles per warp, upper half-warp idle -- does a half-empty warp
+    // occupy the 16-lane FP64 pipe for one pass instead of two?
+    if ((threadIdx.x & 31) >= 16) return;
+    const int k = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 16 + (threadIdx.x & 15);
+#else
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+#endif
     if (k >= a.K) return;
     SmemScratch sc{smem + threadIdx.x};
     const int ctrl = k / a.particles_per_ctrl;
@@ -218,7 +225,11 @@ extern "C" int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a
     MJB_REQUIRE(a->state && a->mean && a->costs, "mjb_rollout_reacher: state, mean and costs are required");
     MJB_CUDA(cudaSetDevice(m->device));
     const int block = MJB_ROLLOUT_BLOCK;
+#ifdef MJB_HALFWARP
+    const int grid = (2 * a->K + block - 1) / block;
+#else
     const int grid = (a->K + block - 1) / block;
+#endif
     cudaStream_t s = (cudaStream_t)stream;
     const bool extra = a->qv_traj || a->next_obs || a->ncon || a->closed_loop;
     const bool fused = a->noise_cov != nullptr;

@@ -44,6 +44,38 @@ def emit(name, ms, K, H, n_ctrl=1, **kw):
 
 
 states = synthetic_states(compiled, 16, seed=1)
+ONLY = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else ""
+if ONLY in ("", "fullsize"):
+    # the other controllers at the north-star size K=65536, H=32: one GPU, eager + graph
+    from mjmpc_b200.control import RandomShooting
+    K, H = 65536, 32
+    kw = dict(horizon=H, num_particles=K, gamma=1.0, n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=123, **R7)
+    mk = {
+        "MPPI": lambda: MPPI(init_cov=1.0, base_action='null', lam=0.2, step_size=1.0, alpha=1, **kw),
+        "CEM full-cov": lambda: CEM(init_cov=1.0, base_action='null', elite_frac=0.2, step_size=1.0, beta=0.0, cov_type='full', **kw),
+        "CEM diag-cov": lambda: CEM(init_cov=1.0, base_action='null', elite_frac=0.2, step_size=1.0, beta=0.0, cov_type='diagonal', **kw),
+        "RandomShooting": lambda: RandomShooting(init_cov=1.0, base_action='null', step_size=1.0, **kw),
+        "PFMPC": lambda: PFMPC(cov_shift=0.05, cov_resample=1.0, base_action='null', lam=0.2, **kw),
+        "DMD-MPC diag-cov": lambda: DMDMPC(init_cov=0.1, beta=0.3, base_action='null', lam=0.2, step_size=1.0, update_cov=True,
+                                           cov_type='diagonal', **kw),
+    }
+    for name, f in mk.items():
+        env = GpuReacherVecEnv(compiled)
+        c = f()
+        c.set_sim_state_fn, c.rollout_fn = env.set_env_state, env.rollout_fn
+        for graph in (False, True):
+            if graph and name == "PFMPC":
+                continue                                 # r comes from Python's random module every step: eager only
+            try:
+                ms = timed(c, states, steps=60, warmup=5, graph=graph)
+                emit("fullsize %s K=65536 H=32 (%s)" % (name, "cuda graph" if graph else "eager"), ms, K, H)
+            except Exception as e:              # a config that cannot run is a finding, not a crash of the sweep
+                print(json.dumps(dict(config="fullsize " + name, graph=graph, error=repr(e)[:300])), flush=True)
+        env.close()
+        del c, env
+        torch.cuda.empty_cache()
+    if ONLY:
+        sys.exit(0)
 # configs[0]
 env = GpuReacherVecEnv(compiled)
 c = MPPI(horizon=16, init_cov=1.0, base_action='null', lam=0.2, num_particles=32, step_size=1.0, alpha=1, gamma=1.0, n_iters=1,

@@ -18,7 +18,8 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "gpurun_variants")
 VARIANTS = {
     "default": [],
-    "no_repair": ["MJB_NO_REPAIR"],      # without the rank-one repair of a misjudged limit row (chain_dynamics.cuh)
+    "no_repair": ["MJB_NO_REPAIR"],
+    "halfwarp": ["MJB_HALFWARP"],        # 16 particles per warp (lone-warp regime probe: FP64 pipe passes per warp instruction)      # without the rank-one repair of a misjudged limit row (chain_dynamics.cuh)
 }
 
 
