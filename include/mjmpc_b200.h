@@ -79,6 +79,13 @@ typedef struct {
     int closed_loop;
 } mjb_rollout_args;
 int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a, void* stream);
+/* Largest per-launch particle count that takes the ROLE-SPLIT instantiation of the rollout kernel (four warps
+ * per 32 particles: bias forces | mass matrix + Euler solve | constraint rows + Newton | controls + cost; for
+ * the latency-bound small launches of sharded controllers -- the reference's small per-worker batches,
+ * subproc_vec_env.py:161-186).  Larger launches, and launches that ask for observations, closed-loop control or
+ * in-kernel noise, run one thread per particle.  Returns the previous value; a negative argument only queries.
+ * Default 8192, the measured cross-over (or the MJB_SPLIT_MAX_K environment variable); 0 switches the split kernel off. */
+int mjb_rollout_split_max_k(int new_value);
 
 /* ---- K9 pendulum rollout: replaces PendulumEnv.step (mjmpc/envs/basic/pendulum.py:33-50) under
  * GymEnvWrapper.rollout.  state: (n_ctrl, 2) theta, thetadot; mean (n_ctrl, H, 1); d_action = 1.

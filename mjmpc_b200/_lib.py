@@ -63,7 +63,7 @@ def lib():
 EXPORTS = [
     "mjb_last_error", "mjb_version", "mjb_device_info", "mjb_fp64_peak",
     "mjb_model_create", "mjb_model_update", "mjb_model_n_instances", "mjb_model_destroy",
-    "mjb_rollout_reacher",
+    "mjb_rollout_reacher", "mjb_rollout_split_max_k",
 ]
 
 

@@ -63,20 +63,25 @@ extern "C" int mjb_model_update(mjb_model* m, int first, int n, const double* ho
         mjb_derive_params(P);
     }
     m->fits_sawyer = 1;
-    for (int i = 0; i < m->n_instances; i++) m->fits_sawyer &= mjb_params_fit_sawyer(m->h_params + (size_t)i * CH_NDEV);
+    m->uniform_frame_skip = 1;
+    for (int i = 0; i < m->n_instances; i++) {
+        m->fits_sawyer &= mjb_params_fit_sawyer(m->h_params + (size_t)i * CH_NDEV);
+        m->uniform_frame_skip &= m->h_params[(size_t)i * CH_NDEV + CS_FRAME_SKIP] == m->h_params[CS_FRAME_SKIP];
+    }
     MJB_CUDA(cudaSetDevice(m->device));
     cudaStream_t s = (cudaStream_t)stream;
     MJB_CUDA(cudaMemcpyAsync(m->d_params + (size_t)first * CH_NDEV, m->h_params + (size_t)first * CH_NDEV,
                              sizeof(double) * CH_NDEV * n, cudaMemcpyHostToDevice, s));
     MJB_CUDA(cudaStreamSynchronize(s));
     m->serial = ++g_serial;
-    return MJB_OK;
+    return mjb::const_bank_on_update(m);
 }
 
 extern "C" int mjb_model_n_instances(const mjb_model* m) { return m ? m->n_instances : 0; }
 
 extern "C" int mjb_model_destroy(mjb_model* m) {
     if (!m) return MJB_OK;
+    mjb::const_bank_release(m);
     cudaFree(m->d_params);
     free(m->h_params);
     free(m);

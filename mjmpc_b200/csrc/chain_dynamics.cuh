@@ -162,6 +162,35 @@ MJB_HD void sincos_joint(double x, double& s, double& c) {
     c = ((k + 1) & 2) ? -b : b;
 }
 
+// sin / cos of q + dq from sin / cos of q by the angle-addition formulas, sin(dq) and cos(dq) - 1 from their Taylor
+// series (to dq^13 and dq^14: truncation below 2e-17 for |dq| <= 0.25 rad, one integration step of a joint slower
+// than 25 rad/s).  21 FP64 instructions instead of the 41 of sincos_joint and no range reduction; each update
+// rounds s and c once more, so the pair drifts from the exact values by O(updates x 1e-16) -- the role-split
+// rollout uses it (64 updates per horizon: < 1e-14), callers fall back to sincos_joint beyond 0.25 rad.
+MJB_HD void sincos_advance(double dq, double& s, double& c) {
+    const double z = dq * dq;
+    const double S = z * fma(z, fma(z, fma(z, fma(z, fma(z, 1.60590438368216146e-10, -2.50521083854417188e-08),
+                                                   2.75573192239858907e-06), -1.98412698412698413e-04),
+                                    8.33333333333333333e-03), -1.66666666666666667e-01);          // sin(dq)/dq - 1
+    const double C = z * fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, -1.14707455977297247e-11, 2.08767569878680990e-09),
+                                                          -2.75573192239858907e-07), 2.48015873015873016e-05),
+                                           -1.38888888888888889e-03), 4.16666666666666667e-02), -0.5);   // cos(dq) - 1
+    const double sd = fma(dq, S, dq);
+    const double s0 = s;
+    s = s0 + fma(c, sd, s0 * C);
+    c = c + fma(-s0, sd, c * C);
+}
+// exact re-evaluation of all seven pairs, out of line (rare path of the callers of sincos_advance):
+// io[0..7) angles in, io[7..14) sin, io[14..21) cos out
+MJB_NOINLINE void sincos_all(double* io) {
+#pragma unroll 1
+    for (int j = 0; j < 7; j++) {
+        double s, c;
+        sincos_joint(io[j], s, c);
+        io[7 + j] = s; io[14 + j] = c;
+    }
+}
+
 // Structure of the reference's arm (sawyer.xml:15-59): axes z,y,x,y,x,y,x; after merging the two
 // welded bodies, link offsets are (x,0,0) or 0 and COMs are on the link x axis (or at the origin),
 // so inertias about the link origin stay diagonal for links 1..6.  Bit k of a mask = component k.
@@ -646,7 +675,8 @@ MJB_NOINLINE void chol_solve7(double (*A)[7], double* x) {      // SPD solve, lo
         for (int k = i + 1; k < 7; k++) t -= A[k][i] * x[k]; x[i] = t / A[i][i]; }
 }
 
-MJB_NOINLINE void constrained_solve_slow(double* w) {
+// force_only (role-split rollout): w[49..56) <- the constraint force J'lambda, no Euler solve.
+MJB_NOINLINE void constrained_solve_slow(double* w, int force_only = 0) {
     const double *M49 = w, *f = w + 49, *hd = w + 56, *D = w + 63, *b = w + 70, *sg = w + 77, *Jc = w + 84;
     const double Dc = w[91], arefc = w[92];
     double a[7], A[7][7], x[7], jar[8], jp[8], Dr[8];
@@ -726,6 +756,16 @@ MJB_NOINLINE void constrained_solve_slow(double* w) {
     #pragma unroll 1
     for (int j = 0; j < 7; j++) jc += Jc[j] * a[j];
     const double lc = (Dc > 0.0 && jc < 0.0) ? -Dc * jc : 0.0;
+    if (force_only) {
+        #pragma unroll 1
+        for (int i = 0; i < 7; i++) {
+            const double r = sg[i] * (a[i] - b[i]);
+            x[i] = ((D[i] > 0.0 && r < 0.0) ? D[i] * (b[i] - a[i]) : 0.0) + lc * Jc[i];
+        }
+        #pragma unroll 1
+        for (int j = 0; j < 7; j++) w[49 + j] = x[j];
+        return;
+    }
     #pragma unroll 1
     for (int i = 0; i < 7; i++) {
         const double r = sg[i] * (a[i] - b[i]);
@@ -751,7 +791,9 @@ MJB_NOINLINE void constrained_solve_slow(double* w) {
 // increment and a right-hand-side increment:
 //     Newton:  H = M + diag(dadd),  rhs = f + radd,   dadd = D on the active rows, radd = D b
 //     Euler:   H = M + diag(h B),   rhs = f + fc,     fc = D (b - a) on the active rows
-template <class T, class P, class S>
+// REPAIR = false: without the rank-one repair (a wrong first guess costs another factor/solve trip instead; measured
+// round 2: within 2 % either way at every launch size, kept as a compile-time switch for experiments).
+template <class T, bool REPAIR = true, class P, class S>
 MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], const double (&sn)[7],
                           const double (&cs)[7]) {
     double f[7];
@@ -845,6 +887,7 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
                 // the joint-space constraint force D_j (b_j - a_j); otherwise a plain active-set (unit Newton) step
                 bool ok = (actx == act) & (con_x == con_on);
 #ifndef MJB_NO_REPAIR
+                if constexpr (REPAIR) {
                 // One limit row misjudged (98 % of the wrong guesses; measured on the host): repair the solution
                 // by a rank-one update on the factor at hand instead of a new factor/solve trip.  With
                 // H z = e_j:  (H + s D_j e_j e_j') x' = rhs + s rho_j e_j  has  x' = x + alpha z,
@@ -854,7 +897,7 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
                 // like any other; a warp whose lanes all settle here skips the third trip the wrong guess cost
                 // (64 % of warp-substeps on the bench workload).
                 const unsigned fm = actx ^ act;
-                if (!ok && R.Dc == 0.0 && (fm & (fm - 1u)) == 0u) {
+                if (REPAIR && !ok && R.Dc == 0.0 && (fm & (fm - 1u)) == 0u) {
                     MJB_STAT(4);
                     double z[7];
 #pragma unroll
@@ -880,6 +923,7 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
                     for (int j = 0; j < 7; j++) actx |= (sflip(x[j], R.sgn(j)) < R.bs[j]) ? (1u << j) : 0u;
                     ok = actx == act;
                     if (ok) MJB_STAT(5);
+                }
                 }
 #endif
 #pragma unroll
@@ -926,6 +970,130 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
 #pragma unroll
     for (int j = 0; j < 7; j++) { qd[j] += h * x[j]; q[j] += h * qd[j]; }
     return any;
+}
+
+// The Newton half of chain_substep on its own, for the role-split rollout (rollout_reacher_split.cuh): the
+// constraint force J'lambda at the minimiser -- what the loop above hands to its Euler trip as `radd` -- from the
+// smooth force f, the rows R and M in the scratch (SC_M; SC_JC / SC_M2 when the contact row exists).  Same
+// operations in the same order as chain_substep: first guess f_j / M_jj, factor/solve trips on M + diag(D_active),
+// rank-one repair of a single misjudged row, slow path after 6 unsettled trips.
+template <class T, class P, class S>
+MJB_HD void constraint_force(const P& prm, S& sc, const double (&f)[7], const Rows& R, double (&fc)[7]) {
+    double dadd[7], radd[7], x[7];
+    unsigned act = 0;
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        const double bm = R.bs[j] * sc.ld(sc_m(j, j));
+        const bool on = sflip(f[j], R.sgn(j)) < bm;
+        act |= on ? (1u << j) : 0u;
+        dadd[j] = on ? R.D[j] : 0.0;
+        radd[j] = sflip(dadd[j] * R.bs[j], R.sgn(j));
+    }
+    int moff = 0;
+    bool con_on = false;
+    if (R.Dc > 0.0) {
+#pragma unroll 1
+        for (int i = 0; i < 7; i++) {
+            const double ji = R.Dc * sc.ld(SC_JC + i);
+#pragma unroll 1
+            for (int j = 0; j <= i; j++)
+                sc.st(SC_M2 + i * (i + 1) / 2 + j, sc.ld(SC_M + i * (i + 1) / 2 + j) + ji * sc.ld(SC_JC + j));
+        }
+        con_on = R.arefc > 0.0;
+        if (con_on) {
+            moff = SC_M2 - SC_M;
+#pragma unroll
+            for (int j = 0; j < 7; j++) radd[j] += R.Dc * R.arefc * sc.ld(SC_JC + j);
+        }
+    }
+    bool slow = false;
+    int iters = 0, again;
+#pragma unroll 1
+    do {
+        double H[7][7], dinv[7];
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+#pragma unroll
+            for (int j = 0; j < i; j++) H[i][j] = sc.ld(moff + sc_m(i, j));
+            H[i][i] = sc.ld(moff + sc_m(i, i)) + dadd[i];
+            x[i] = f[i] + radd[i];
+        }
+        ldl7(H, dinv);
+        ldl7_solve(H, dinv, x);
+        unsigned actx = 0;
+#pragma unroll
+        for (int j = 0; j < 7; j++) actx |= (sflip(x[j], R.sgn(j)) < R.bs[j]) ? (1u << j) : 0u;
+        bool con_x = false;
+        double jcx = 0.0;
+        if (R.Dc > 0.0) {
+            jcx = -R.arefc;
+#pragma unroll
+            for (int j = 0; j < 7; j++) jcx += sc.ld(SC_JC + j) * x[j];
+            con_x = jcx < 0.0;
+        }
+        bool ok = (actx == act) & (con_x == con_on);
+#ifndef MJB_NO_REPAIR
+        const unsigned fm = actx ^ act;
+        if (!ok && R.Dc == 0.0 && (fm & (fm - 1u)) == 0u) {
+            double z[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) z[j] = ((fm >> j) & 1u) ? 1.0 : 0.0;
+            ldl7_solve(H, dinv, z);
+            double Dj = 0.0, wj = 0.0, zj = 0.0;
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                const bool b = (fm >> j) & 1u;
+                Dj = b ? R.D[j] : Dj;
+                wj = b ? sflip(R.bs[j] - sflip(x[j], R.sgn(j)), R.sgn(j)) : wj;
+                zj = b ? z[j] : zj;
+            }
+            const bool on = (actx & fm) != 0u;
+            const double sD = on ? Dj : -Dj;
+            const double alpha = sD * wj * rcp_pos(fma(sD, zj, 1.0));
+#pragma unroll
+            for (int j = 0; j < 7; j++) x[j] = fma(alpha, z[j], x[j]);
+            act ^= fm;
+            actx = 0;
+#pragma unroll
+            for (int j = 0; j < 7; j++) actx |= (sflip(x[j], R.sgn(j)) < R.bs[j]) ? (1u << j) : 0u;
+            ok = actx == act;
+        }
+#endif
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const double De = ((actx >> j) & 1u) ? R.D[j] : 0.0;
+            dadd[j] = De;
+            radd[j] = sflip(De * (R.bs[j] - (ok ? sflip(x[j], R.sgn(j)) : 0.0)), R.sgn(j));
+        }
+        if (con_x) {
+            const double lc = ok ? -R.Dc * jcx : R.Dc * R.arefc;
+#pragma unroll
+            for (int j = 0; j < 7; j++) radd[j] += lc * sc.ld(SC_JC + j);
+        }
+        act = actx;
+        con_on = con_x;
+        moff = con_on ? SC_M2 - SC_M : 0;
+        again = ok ? 0 : 1;
+        if (!ok && ++iters > 6) { slow = true; again = 0; }
+    } while (again);
+    if (slow) {
+        double w[93];
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+#pragma unroll
+            for (int k = 0; k <= j; k++) w[j * 7 + k] = sc.ld(sc_m(j, k));
+            w[49 + j] = f[j]; w[56 + j] = prm[CH_HDAMP + j];
+            w[63 + j] = R.D[j]; w[70 + j] = R.D[j] > 0.0 ? sflip(R.bs[j], R.sgn(j)) : 0.0;
+            w[77 + j] = ((R.below >> j) & 1u) ? 1.0 : -1.0;
+            w[84 + j] = R.Dc > 0.0 ? sc.ld(SC_JC + j) : 0.0;
+        }
+        w[91] = R.Dc; w[92] = R.arefc;
+        constrained_solve_slow(w, 1);
+#pragma unroll
+        for (int j = 0; j < 7; j++) radd[j] = w[49 + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 7; j++) fc[j] = radd[j];
 }
 
 // Motor torque of joint j under control u: gear * clip(u, ctrlrange) (MuJoCo mj_fwdActuation with

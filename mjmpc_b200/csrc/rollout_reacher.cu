@@ -3,6 +3,8 @@
 // env-copy loop: GymEnvWrapper.rollout (mjmpc/envs/gym_env_wrapper.py:125-153) ->
 // Reacher7DOFEnv.step (mjmpc/envs/basic/reacher_env.py:29-39) -> MuJoCo mj_step x frame_skip,
 // fanned out by SubprocVecEnv.rollout (mjmpc/envs/vec_env/subproc_vec_env.py:161-186).
+#include <stdlib.h>
+#include <mutex>
 #include <type_traits>
 #include "chain_dynamics.cuh"
 #include "philox_noise.cuh"
@@ -61,14 +63,7 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
         if (threadIdx.x == 0) noise_chol<7>(a.noise_cov, Lsh);
         __syncthreads();
     }
-#ifdef MJB_HALFWARP
-    // experiment (tools/k1_variants.py): 16 particles per warp, upper half-warp idle -- does a half-empty warp
-    // occupy the 16-lane FP64 pipe for one pass instead of two?
-    if ((threadIdx.x & 31) >= 16) return;
-    const int k = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 16 + (threadIdx.x & 15);
-#else
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-#endif
     if (k >= a.K) return;
     SmemScratch sc{smem + threadIdx.x};
     const int ctrl = k / a.particles_per_ctrl;
@@ -214,7 +209,81 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
 
 }  // namespace mjb
 
+#include "rollout_reacher_split.cuh"
+
 #ifndef MJB_HOST_EMU
+namespace mjb {
+// owner of the per-device constant bank (see common.h)
+static std::mutex g_bank_mutex;
+static const mjb_model* g_bank_owner[64] = {nullptr};
+static unsigned long long g_bank_serial[64] = {0};
+
+static int bank_upload(const mjb_model* m, cudaStream_t s) {
+    MJB_CUDA(cudaSetDevice(m->device));
+    MJB_CUDA(cudaMemcpyToSymbolAsync(c_params, m->h_params, sizeof(double) * CH_NDEV, 0, cudaMemcpyHostToDevice, s));
+    g_bank_serial[m->device & 63] = m->serial;
+    return MJB_OK;
+}
+// true: this launch may read the model from the constant bank
+static int bank_claim(const mjb_model* m, int K, cudaStream_t s, bool* use_const) {
+    *use_const = false;
+    if (m->n_instances != 1) return MJB_OK;
+    std::lock_guard<std::mutex> lock(g_bank_mutex);
+    const int dev = m->device & 63;
+    if (g_bank_owner[dev] == nullptr && K >= 64) {
+        g_bank_owner[dev] = m;
+        g_bank_serial[dev] = 0;
+    }
+    if (g_bank_owner[dev] != m) return MJB_OK;
+    if (g_bank_serial[dev] != m->serial) {
+        const int rc = bank_upload(m, s);       // first launch of the owner (stream-ordered before the kernel)
+        if (rc != MJB_OK) return rc;
+    }
+    *use_const = true;
+    return MJB_OK;
+}
+int const_bank_on_update(mjb_model* m) {
+    std::lock_guard<std::mutex> lock(g_bank_mutex);
+    const int dev = m->device & 63;
+    if (g_bank_owner[dev] != m) return MJB_OK;
+    // kernels (or graph replays) of the owner may be in flight on any stream: drain, then replace the constants
+    MJB_CUDA(cudaSetDevice(m->device));
+    MJB_CUDA(cudaDeviceSynchronize());
+    const int rc = bank_upload(m, nullptr);
+    if (rc != MJB_OK) return rc;
+    MJB_CUDA(cudaStreamSynchronize(nullptr));
+    return MJB_OK;
+}
+void const_bank_release(const mjb_model* m) {
+    std::lock_guard<std::mutex> lock(g_bank_mutex);
+    const int dev = m->device & 63;
+    if (g_bank_owner[dev] == m) { g_bank_owner[dev] = nullptr; g_bank_serial[dev] = 0; }
+}
+// particles per launch up to which the role-split kernel is used (4 warps per 32 particles; measured cross-over,
+// DESIGN 4.2); MJB_SPLIT_MAX_K overrides it (0 = never)
+static int g_split_max_k = -1;
+static int split_max_k() {
+    if (g_split_max_k < 0) {
+        const char* e = getenv("MJB_SPLIT_MAX_K");
+        g_split_max_k = e ? atoi(e) : 8192;
+    }
+    return g_split_max_k;
+}
+}  // namespace mjb
+
+#ifdef MJB_SPLIT_TIMING
+extern "C" int mjb_split_profile(unsigned long long* out32) {
+    MJB_CUDA(cudaMemcpyFromSymbol(out32, mjb::g_split_prof, sizeof(unsigned long long) * 32));
+    return MJB_OK;
+}
+#endif
+
+extern "C" int mjb_rollout_split_max_k(int new_value) {
+    const int old = mjb::split_max_k();
+    if (new_value >= 0) mjb::g_split_max_k = new_value;
+    return old;
+}
+
 extern "C" int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a, void* stream) {
     MJB_REQUIRE(m && a, "mjb_rollout_reacher: null handle");
     MJB_REQUIRE(a->K >= 1 && a->H >= 1, "mjb_rollout_reacher: K and H must be positive (K=%d H=%d)", a->K, a->H);
@@ -225,26 +294,47 @@ extern "C" int mjb_rollout_reacher(const mjb_model* m, const mjb_rollout_args* a
     MJB_REQUIRE(a->state && a->mean && a->costs, "mjb_rollout_reacher: state, mean and costs are required");
     MJB_CUDA(cudaSetDevice(m->device));
     const int block = MJB_ROLLOUT_BLOCK;
-#ifdef MJB_HALFWARP
-    const int grid = (2 * a->K + block - 1) / block;
-#else
     const int grid = (a->K + block - 1) / block;
-#endif
     cudaStream_t s = (cudaStream_t)stream;
     const bool extra = a->qv_traj || a->next_obs || a->ncon || a->closed_loop;
     const bool fused = a->noise_cov != nullptr;
     MJB_REQUIRE(!(fused && a->closed_loop), "mjb_rollout_reacher: closed-loop rollouts take an explicit noise tensor");
     MJB_REQUIRE(!(fused && a->noise), "mjb_rollout_reacher: pass either a noise tensor or in-kernel noise parameters, not both");
-    const bool use_const = m->n_instances == 1;
-    if (use_const) {
-        // constant bank is per device; re-upload only when another model (or an updated one) was there
-        static unsigned long long owner[64] = {0};
-        const int dev = m->device & 63;
-        if (owner[dev] != m->serial) {
-            if (owner[dev] != 0) MJB_CUDA(cudaDeviceSynchronize());   // kernels of the previous owner may still read it
-            MJB_CUDA(cudaMemcpyToSymbolAsync(mjb::c_params, m->h_params, sizeof(double) * CH_NDEV, 0, cudaMemcpyHostToDevice, s));
-            owner[dev] = m->serial;
+    bool use_const = false;
+    {
+        const int rc = mjb::bank_claim(m, a->K, s, &use_const);
+        if (rc != MJB_OK) return rc;
+    }
+    // small launches: four warps per 32 particles (rollout_reacher_split.cuh); it has no observation / closed-loop /
+    // fused-noise instantiations
+    if (a->K <= mjb::split_max_k() && !fused && !a->closed_loop && !a->next_obs && m->uniform_frame_skip) {
+        // 32 particles per block while that leaves every SM at most one block, else 64 (two warps per role in lock step)
+        int sm_count = 148;
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, m->device);
+        const bool wide = (a->K + 31) / 32 > sm_count;
+        const int lanes = wide ? 64 : 32;
+        const int sgrid = (a->K + lanes - 1) / lanes;
+        const size_t sbytes = sizeof(double) * mjb::SX_NSLOT * lanes;
+        const bool sx = a->qv_traj || a->ncon;
+#define MJB_SLAUNCH4(T, P, E, L)                                                                                          \
+    do {                                                                                                                  \
+        MJB_CUDA(cudaFuncSetAttribute(mjb::rollout_reacher_split_kernel<mjb::T, mjb::P, E, L>,                              \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * mjb::SX_NSLOT * L))); \
+        mjb::rollout_reacher_split_kernel<mjb::T, mjb::P, E, L><<<sgrid, 4 * L, sbytes, s>>>(m->d_params, m->n_instances, *a); \
+    } while (0)
+#define MJB_SLAUNCH3(T, P, E) do { if (wide) MJB_SLAUNCH4(T, P, E, 64); else MJB_SLAUNCH4(T, P, E, 32); } while (0)
+#define MJB_SLAUNCH(T, P) do { if (sx) MJB_SLAUNCH3(T, P, true); else MJB_SLAUNCH3(T, P, false); } while (0)
+        if (m->fits_sawyer) {
+            if (use_const) MJB_SLAUNCH(SawyerTraits, ConstParams);
+            else MJB_SLAUNCH(SawyerTraits, GlobalParams);
+        } else {
+            MJB_SLAUNCH(DenseTraits, GlobalParams);
         }
+#undef MJB_SLAUNCH4
+#undef MJB_SLAUNCH3
+#undef MJB_SLAUNCH
+        MJB_CUDA(cudaGetLastError());
+        return MJB_OK;
     }
 #define MJB_LAUNCH4(T, P, E, F) mjb::rollout_reacher_kernel<mjb::T, mjb::P, E, F><<<grid, block, 0, s>>>(m->d_params, m->n_instances, *a)
 #define MJB_LAUNCH(T, P)                                                    \

@@ -142,6 +142,8 @@ typedef struct {
     double hand[3];
     int nefc;
     double qacc[MAXV];
+    /* constraint rows of the last step, for row-by-row checks against oracle/efc_ref.py */
+    double efc_J[MAXROW][MAXV], efc_aref[MAXROW], efc_D[MAXROW], efc_force[MAXROW], qfrc_constraint[MAXV];
 } ora_data;
 
 static double impedance(const double* solimp, double pos, double margin) {
@@ -375,9 +377,15 @@ static void ora_step(const ora_model* m, ora_data* d, double* q, double* v, cons
         for (int r = 0; r < nr; r++) {
             double s = -aref[r];
             for (int k = 0; k < nv; k++) s += J[r][k] * a[k];
+            d->efc_force[r] = s < 0.0 ? -D[r] * s : 0.0;
             if (s < 0.0) for (int k = 0; k < nv; k++) fc[k] += J[r][k] * (-D[r] * s);
         }
     }
+    for (int r = 0; r < nr; r++) {
+        d->efc_aref[r] = aref[r]; d->efc_D[r] = D[r];
+        for (int k = 0; k < nv; k++) d->efc_J[r][k] = J[r][k];
+    }
+    for (int k = 0; k < nv; k++) d->qfrc_constraint[k] = fc[k];
     /* --- mj_Euler: implicit in joint damping --- */
     double A[MAXV][MAXV], qa[MAXV];
     for (int i = 0; i < nv; i++) {
@@ -440,6 +448,20 @@ int ora_substep(const ora_model* m, double* q, double* v, const double* u, doubl
     ora_data d;
     ora_step(m, &d, q, v, u);
     if (qacc_out) for (int j = 0; j < m->nv; j++) qacc_out[j] = d.qacc[j];
+    return d.nefc;
+}
+
+/* one mj_step, also handing back the constraint rows: J (nefc, nv), aref, D, efc_force (nefc each; room for
+ * 2 nv + 1 rows) and qfrc_constraint (nv).  Returns nefc. */
+int ora_substep_efc(const ora_model* m, double* q, double* v, const double* u, double* qacc_out, double* J_out,
+                    double* aref_out, double* D_out, double* force_out, double* qfrc_out) {
+    ora_data d;
+    ora_step(m, &d, q, v, u);
+    for (int j = 0; j < m->nv; j++) { qacc_out[j] = d.qacc[j]; qfrc_out[j] = d.qfrc_constraint[j]; }
+    for (int r = 0; r < d.nefc; r++) {
+        aref_out[r] = d.efc_aref[r]; D_out[r] = d.efc_D[r]; force_out[r] = d.efc_force[r];
+        for (int k = 0; k < m->nv; k++) J_out[r * m->nv + k] = d.efc_J[r][k];
+    }
     return d.nefc;
 }
 

@@ -29,6 +29,7 @@ def lib():
         L = C.CDLL(build())
         L.ora_model_create.restype = C.c_void_p
         L.ora_substep.restype = C.c_int
+        L.ora_substep_efc.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -79,6 +80,16 @@ class OracleModel:
         qacc = np.zeros(self.nv)
         n = lib().ora_substep(C.c_void_p(self.h), _p(q), _p(v), _p(u), _p(qacc))
         return q, v, qacc, n
+
+    def substep_efc(self, q, v, u):
+        """One mj_step plus its constraint rows: dict(q, v, qacc, J, aref, D, force, qfrc_constraint)."""
+        nv = self.nv
+        q = np.array(q, np.float64); v = np.array(v, np.float64); u = np.ascontiguousarray(u, np.float64)
+        qacc, qfrc = np.zeros(nv), np.zeros(nv)
+        J, aref, D, force = np.zeros((2 * nv + 1, nv)), np.zeros(2 * nv + 1), np.zeros(2 * nv + 1), np.zeros(2 * nv + 1)
+        n = lib().ora_substep_efc(C.c_void_p(self.h), _p(q), _p(v), _p(u), _p(qacc), _p(J), _p(aref), _p(D), _p(force),
+                                  _p(qfrc))
+        return dict(q=q, v=v, qacc=qacc, J=J[:n], aref=aref[:n], D=D[:n], force=force[:n], qfrc_constraint=qfrc)
 
 
 def _solref_kb(tree):

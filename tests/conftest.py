@@ -73,3 +73,15 @@ def synthetic_state(compiled_model, seed=0):
     qv = rng.normal(0, 0.5, 7)
     tgt = rng.uniform([-.3, -.2, -.25], [.3, .2, .25])
     return dict(qp=qp, qv=qv, qa=np.zeros(7), target_pos=tgt, timestep=0)
+
+
+@pytest.fixture
+def split_switch():
+    """`split_switch(v)`: the role-split rollout kernel takes launches of up to v particles for the rest of this test
+    (0 pins the thread-per-particle kernel); the library default is restored afterwards."""
+    import ctypes as C
+    from mjmpc_b200 import _lib
+    L = _lib.lib()
+    old = L.mjb_rollout_split_max_k(C.c_int(-1))
+    yield lambda v: L.mjb_rollout_split_max_k(C.c_int(v))
+    L.mjb_rollout_split_max_k(C.c_int(old))

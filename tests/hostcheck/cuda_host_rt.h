@@ -22,6 +22,8 @@ inline cudaError_t props_(cudaDeviceProp* p) {
 #define cudaMemcpyToSymbolAsync(sym, src, n, off, kind, s) (std::memcpy((char*)&(sym) + (off), (src), (n)), (void)(s), cudaSuccess)
 #define cudaStreamSynchronize(s) ((void)(s), cudaSuccess)
 #define cudaDeviceSynchronize() cudaSuccess
+#define cudaFuncSetAttribute(...) cudaSuccess
+#define cudaFuncAttributeMaxDynamicSharedMemorySize 8
 #define cudaSetDevice(d) ((void)(d), cudaSuccess)
 #define cudaGetDeviceProperties(p, d) emu::props_(p)
 #define cudaDeviceGetAttribute(v, a, d) (*(v) = ((a) == cudaDevAttrMultiProcessorCount ? 148 : 1965000), cudaSuccess)

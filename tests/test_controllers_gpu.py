@@ -521,9 +521,11 @@ def test_batched_independent_instances_match_single_controllers(compiled_model):
 
 
 @pytest.mark.parametrize("graph", [False, True])
-def test_fused_noise_controller_equals_two_kernel_path(compiled_model, graph):
-    """optimize() with the noise drawn inside the rollout kernel == optimize() with a materialised noise tensor."""
+def test_fused_noise_controller_equals_two_kernel_path(compiled_model, graph, split_switch):
+    """optimize() with the noise drawn inside the rollout kernel == optimize() with a materialised noise tensor
+    (bit for bit: one kernel instantiation, so the small-launch instantiations are switched off)."""
     from conftest import synthetic_state
+    split_switch(0)
     from mjmpc_b200.control import MPPI
     from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
     states = [synthetic_state(compiled_model, 50 + s) for s in range(4)]

@@ -76,7 +76,7 @@ def test_closed_loop_linear_rollout_matches_oracle(case):
     Wb = np.zeros((21, 7)); Wb[20] = [0.3, -0.2, 0.1, 0.0, 0.2, -0.1, 0.05]
     a = env.rollout_device(K, H, torch.from_numpy(Wb).cuda(), torch.from_numpy(noise).cuda(), closed_loop=True)
     b = env.rollout_device(K, H, torch.from_numpy(np.tile(Wb[20], (H, 1))).cuda(), torch.from_numpy(noise).cuda(),
-                           want_ncon=True)
+                           want_obs=True)                 # observations: the thread-per-particle trajectory instantiation
     assert torch.equal(a["costs"], b["costs"]) and torch.equal(a["actions"], b["actions"])
     env.close()
 

@@ -19,7 +19,7 @@ VDIR = os.path.join(ROOT, "gpurun_variants")
 VARIANTS = {
     "default": [],
     "no_repair": ["MJB_NO_REPAIR"],
-    "halfwarp": ["MJB_HALFWARP"],        # 16 particles per warp (lone-warp regime probe: FP64 pipe passes per warp instruction)      # without the rank-one repair of a misjudged limit row (chain_dynamics.cuh)
+    "fake_small": ["MJB_FAKE_SMALL"],    # footprint probe, WRONG physics: no bias forces, first-order sin/cos (hot loop ~28 KB instead of 39)      # without the rank-one repair of a misjudged limit row (chain_dynamics.cuh)
 }
 
 
