@@ -35,8 +35,9 @@ K_GLOBAL, HORIZON, D_ACTION = 65536, 32, 7
 FLOP_PER_PARTICLE_STEP = 5340.0          # BASELINE.md section 4 / SURVEY 8(d): the contract figure
 MPPI_PARAMS = dict(horizon=HORIZON, init_cov=1.0, filter_coeffs=[0.25, 0.8, 0.0], gamma=1.0, n_iters=1,
                    step_size=1.0, lam=0.2, alpha=1, base_action='null')     # reacher_7dof-v0.yml:20-30 + :5
-KERNELS_PER_STEP = 9     # noise, rollout, softmax {prep, traj_cost, weighted_reduce, decode_min, chunk_sum}, combine, shift
-#                          (counted inside the host emulation by tests/test_zz_native_step_gpu.py)
+KERNELS_PER_STEP = 4     # noise, rollout, trajectory costs, weighted reduction + update tail (last block: partial vector,
+#                          [peer exchange,] combine, next action, shift) -- counted inside the host emulation by
+#                          tests/test_zz_native_step_gpu.py; the same four are what the CUDA graph captures
 
 
 def synthetic_states(compiled, n, seed=0):
@@ -142,7 +143,7 @@ def run_reference(args):
     # bounded sample: as many particles per MPC iteration as keep the whole run near a minute on ~16 cores
     # (one iteration costs ~40 us per particle: numpy noise + C rollout on all cores + numpy update); the full
     # K = 65536 when the driver asks for few steps
-    budget = 60.0 / (40e-6 * max(1, args.steps + args.warmup))
+    budget = 150.0 / (40e-6 * max(1, args.steps + args.warmup))
     k_sample = 2048
     while k_sample * 2 <= min(K_GLOBAL, budget):
         k_sample *= 2
@@ -155,7 +156,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "mpc_hz_at_full_K": value / (K_GLOBAL * HORIZON),
-        "config": workload_config(args.gpus),
+        "config": dict(workload_config(args.gpus), particles_simulated_per_step=k_sample,
+                       sample_note=("every timed step simulates %d of the workload's %d particles (the metric is per "
+                                    "particle-step); the full %d when steps + warmup <= ~57" % (k_sample, K_GLOBAL, K_GLOBAL))),
         "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cb.cores, "kind": "port",
                          "sample": "%d of %d particles x H=%d per MPC iteration (numpy generate_noise + C oracle "
                                    "rollout on %d threads + numpy MPPI update); mujoco_py itself cannot run here"
@@ -277,6 +280,10 @@ def run_own(args):
     tf, pms = C.c_double(), C.c_double()
     _lib.check(L.mjb_fp64_peak(local_rank, 8, 2048, C.byref(tf), C.byref(pms)))
     achieved = kl * HORIZON * FLOP_PER_PARTICLE_STEP / (k1_ms * 1e-3) / 1e12
+    smc, khz = C.c_int(), C.c_int()
+    _lib.check(L.mjb_device_info(local_rank, C.byref(smc), C.byref(khz), None, None))
+    sm_count, clk_ghz = smc.value, khz.value / 1e6
+    peak_nominal = 64 * 2 * sm_count * clk_ghz / 1e3          # TFLOP/s
     # DRAM traffic of that kernel from the committed `ncu --set full` capture (per launch, K=65536, one GPU)
     traffic, traffic_src = None, None
     try:
@@ -315,6 +322,75 @@ def run_own(args):
         breakdown["eager_path"] = "mjb_softmax_mpc_step" if getattr(ctrl, "_fused_blocks", None) else "step by step"
     except Exception as e:          # pragma: no cover
         breakdown["error"] = repr(e)[:200]
+    # ---- the HBM-bound kernels against the measured copy bandwidth: K2 (noise: 56 B written per particle-step) and
+    # K4 (softmax update: 8 B of cost + 56 B of action read per particle-step = 1 800 B per particle at H = 32)
+    hbm_gbs, hbm_src = 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_gbs, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    extra_rooflines = []
+    try:
+        nbytes = kl * HORIZON * D_ACTION * 8
+        gbs = nbytes / (breakdown["noise_ms"] * 1e-3) / 1e9
+        extra_rooflines.append({"kernel": "noise_kernel<7> (K2)", "bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s",
+                                "frac": gbs / hbm_gbs, "algorithmic_bytes": nbytes, "ms_per_launch": breakdown["noise_ms"]})
+        sa, ca, _, _, keep = ctrl._softmax_blocks(out["costs"], out["actions"], ctrl.lam)
+        act = torch.empty(D_ACTION, dtype=torch.float64, device="cuda")
+        if world == 1:          # (with peers the update waits for every rank: timed inside the step only)
+            upd = lambda: _lib.check(L.mjb_softmax_update_fused(C.byref(sa), C.byref(ca), None, C.c_int(0), C.c_ulonglong(0),
+                                                                _lib.ptr(act), C.c_int(0), C.c_int(0), C.c_double(0.0),
+                                                                _lib.stream_ptr()))
+            saved_mean = ctrl._mean.clone()
+            upd()
+            torch.cuda.synchronize()
+            ns.record()
+            for _ in range(reps):
+                upd()
+            ne.record()
+            torch.cuda.synchronize()
+            ctrl._mean.copy_(saved_mean)
+            upd_ms = ns.elapsed_time(ne) / reps
+            ubytes = kl * (HORIZON * 8 + HORIZON * D_ACTION * 8 + 8)
+            breakdown["update_ms"] = upd_ms
+            extra_rooflines.append({"kernel": "traj_cost_kernel + softmax_reduce_tail_kernel (K3/K4 and the update tail: 2 launches)",
+                                    "bound": "hbm", "achieved": ubytes / (upd_ms * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
+                                    "frac": ubytes / (upd_ms * 1e-3) / 1e9 / hbm_gbs, "algorithmic_bytes": ubytes,
+                                    "ms_per_launch": upd_ms})
+        del keep
+    except Exception as e:          # pragma: no cover
+        breakdown["roofline_error"] = repr(e)[:200]
+
+    # ---- sharded step vs the same step on ONE GPU (N > 1, outside the timed region): every rank runs the sharded
+    # step, rank 0 also runs an unsharded controller on the same state / seed / step counter and compares
+    sharded_parity = None
+    if world > 1:
+        try:
+            ctrl.disable_cuda_graph()
+            ctrl.reset()
+            ctrl.num_steps = 0
+            st0 = states[3]
+            a_sh, _ = ctrl.optimize(st0)
+            m_sh = ctrl.mean_action.copy()
+            if rank == 0:
+                env1 = GpuReacherVecEnv(compiled, device=local_rank)
+                p1 = dict(params)
+                p1.update(shard=ShardContext())
+                c1 = MPCPolicy("mppi", p1).controller
+                c1.set_sim_state_fn, c1.rollout_fn = env1.set_env_state, env1.rollout_fn
+                a_1, _ = c1.optimize(st0)
+                m_1 = c1.mean_action
+                rel = lambda x, y: float(np.abs(x - y).max() / max(1e-300, np.abs(y).max()))
+                mr = max(rel(a_sh, a_1), rel(m_sh, m_1))
+                sharded_parity = {"max_rel": mr, "ok": bool(mr < 1e-9), "tolerance": 1e-9,
+                                  "what": "action and updated mean sequence of one MPPI step, %d ranks x %d particles vs one GPU x %d "
+                                          "(same seed, state and step counter; the small shards run the role-split rollout "
+                                          "kernel, the single GPU the thread-per-particle one)" % (world, kl, K_GLOBAL)}
+                env1.close()
+        except Exception as e:          # pragma: no cover
+            sharded_parity = {"error": repr(e)[:300], "ok": False}
+        barrier()
     px = getattr(ctrl, "_px", {})
     exchange = ("none (single GPU)" if world == 1 else
                 "nvlink peer-memory exchange fused into the combine kernel" if any(v is not None for v in px.values())
@@ -351,7 +427,11 @@ def run_own(args):
                      "algorithmic_hbm_bytes": kl * HORIZON * 120,
                      "ms_per_launch": k1_ms, "particles_per_launch": kl,
                      "flop_per_particle_step": FLOP_PER_PARTICLE_STEP,
-                     "peak_source": "mjb_fp64_peak microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)"},
+                     "peak_source": "mjb_fp64_peak microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                     "peak_nominal": peak_nominal, "frac_nominal": achieved / peak_nominal,
+                     "peak_nominal_source": "64 DFMA/clk/SM x %d SMs x %.3f GHz (max SM clock) x 2 FLOP" % (sm_count, clk_ghz)},
+        "rooflines_other": extra_rooflines, "hbm_peak_source": hbm_src,
+        "sharded_parity": sharded_parity,
         "breakdown": breakdown,
         "clocks": clocks,
         "cpu_baseline": cpu,

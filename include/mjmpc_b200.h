@@ -210,6 +210,18 @@ int mjb_softmax_combine(const mjb_combine_args* a, void* stream);
  * seq = 1, 2, 3, ... must advance identically on every rank. */
 int mjb_softmax_exchange_combine(const mjb_combine_args* a, const double* local_partial, void* const* peer_bufs_dev,
                                  int rank, unsigned long long seq, void* stream);
+/* The whole update of the softmax controllers after a rollout -- phase 1, the peer exchange (n_shards > 1),
+ * phase 2, next action, hot-start shift -- in two launches (three with the control cost): the last block of the
+ * weighted reduction to finish runs everything that follows it.  Replaces, bit for bit, the sequence
+ * mjb_softmax_partials -> mjb_softmax_combine | mjb_softmax_exchange_combine -> (action_out <- mean[0]) ->
+ * mjb_shift_mean -> mjb_cov_add_diag, i.e. MPPI._update_distribution (mppi.py:69-97) / DMDMPC._update_distribution
+ * (gaussian_dmd.py:65-91) + _get_next_action (olgaussian_mpc.py:69-78) + _shift (:116-129, gaussian_dmd.py:106-113).
+ * a->scratch[0] holds the "blocks done" counter: zero the scratch buffer once after allocating it.  action_out
+ * (d,) device or NULL; shift: 0 / 1; base_action: MJB_BASE_NULL or MJB_BASE_REPEAT; cov_shift_beta != 0:
+ * cov += beta I after the shift. */
+int mjb_softmax_update_fused(const mjb_softmax_args* a, const mjb_combine_args* c, void* const* peer_bufs_dev, int rank,
+                             unsigned long long seq, double* action_out, int shift, int base_action,
+                             double cov_shift_beta, void* stream);
 /* normalised weights w_k = exp(-(total_k - m)/lam)/S for one t-row of `total`; m,S from stats. */
 int mjb_softmax_weights(const double* total, int K, const double* stats, int t, double lam, double* w_out,
                         void* stream);

@@ -201,7 +201,7 @@ BASE_ACTIONS = {"null": 0, "repeat": 1, "random": 2}
 
 EXPORTS += [
     "mjb_rollout_pendulum", "mjb_rollout_lqr", "mjb_generate_noise", "mjb_cost_to_go",
-    "mjb_softmax_scratch_doubles", "mjb_softmax_partial_doubles", "mjb_softmax_partials",
+    "mjb_softmax_scratch_doubles", "mjb_softmax_partial_doubles", "mjb_softmax_partials", "mjb_softmax_update_fused",
     "mjb_softmax_combine", "mjb_softmax_exchange_combine", "mjb_softmax_weights",
     "mjb_select_elites", "mjb_argmin", "mjb_elite_scratch_doubles", "mjb_elite_moments1",
     "mjb_elite_moments2", "mjb_elite_combine", "mjb_blend_best",

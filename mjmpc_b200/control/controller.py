@@ -147,6 +147,9 @@ class Controller(ABC):
 
     # ---- CUDA-graph replay of the step (launch-bound at small K per GPU) --------------------------
     def _graph_body(self):
+        action = self._fused_step(None, True)       # MPPI / DMD-MPC: the 4-launch native step is what gets captured
+        if action is not None:
+            return action
         for _ in range(self.n_iters):
             trajectory = self.generate_rollouts(None)
             self._update_distribution(trajectory)

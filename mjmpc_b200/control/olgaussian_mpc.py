@@ -113,11 +113,11 @@ class OLGaussianMPC(Controller):
     def local_particles(self):
         return self.shard.local_range(self.num_particles)[1] * self.batch_size
 
-    def _buf(self, name, shape, dtype=torch.float64):
+    def _buf(self, name, shape, dtype=torch.float64, zero=False):
         key = (name, tuple(shape), dtype)
         b = self._buffers.get(key)
         if b is None:
-            b = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            b = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
             self._buffers[key] = b
         return b
 
@@ -264,7 +264,8 @@ class OLGaussianMPC(Controller):
             if qvals is not None:
                 a.qvals = qvals.data_ptr(); a.q_sk, a.q_st = qvals.stride()
         total = self._buf("total", (T, kl))
-        scratch = self._buf("sm_scratch", (int(L.mjb_softmax_scratch_doubles(kl, H, d, cov_mode)),))
+        # zero once: scratch[0] is the "blocks done" counter of mjb_softmax_update_fused (it resets itself)
+        scratch = self._buf("sm_scratch", (int(L.mjb_softmax_scratch_doubles(kl, H, d, cov_mode)),), zero=True)
         partials = self._buf("sm_partials", (P,))
         a.total, a.scratch, a.partials = total.data_ptr(), scratch.data_ptr(), partials.data_ptr()
         stats = self._buf("sm_stats", (2 + 2 * T,))

@@ -64,11 +64,11 @@ class PFMPC(Controller):
     def _graphable(self):
         return False          # the resampler's r comes from Python's random module every step
 
-    def _buf(self, name, shape, dtype=torch.float64):
+    def _buf(self, name, shape, dtype=torch.float64, zero=False):
         key = (name, tuple(shape), dtype)
         b = self._buffers.get(key)
         if b is None:
-            b = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            b = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
             self._buffers[key] = b
         return b
 
@@ -128,7 +128,7 @@ class PFMPC(Controller):
         a.gamma_seq = g.ctypes.data
         a.lam = float(self.lam)
         total = self._buf("total", (1, kl))
-        scratch = self._buf("sm_scratch", (int(L.mjb_softmax_scratch_doubles(kl, H, d, 0)),))
+        scratch = self._buf("sm_scratch", (int(L.mjb_softmax_scratch_doubles(kl, H, d, 0)),), zero=True)
         P = L.mjb_softmax_partial_doubles(H, d, 0, 0)
         partials = self._buf("sm_partials", (P,))
         a.total, a.scratch, a.partials = total.data_ptr(), scratch.data_ptr(), partials.data_ptr()

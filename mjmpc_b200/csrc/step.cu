@@ -58,19 +58,13 @@ extern "C" int mjb_softmax_mpc_step(const mjb_mpc_step_args* a, void* stream) {
             MJB_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
             forked = true;
         }
-        if ((rc = mjb_softmax_partials(a->softmax, stream)) != MJB_OK) return rc;
-        if (c->n_shards == 1) rc = mjb_softmax_combine(c, stream);
-        else rc = mjb_softmax_exchange_combine(c, a->softmax->partials, a->peer_bufs_dev, a->rank, a->seq + (unsigned long long)it, stream);
+        // the whole update tail rides in the last block of the weighted reduction; after the last iteration it
+        // also hands out the next action and shifts the mean sequence (4 launches per MPPI iteration in all)
+        const bool final_it = it == a->n_iters - 1;
+        rc = mjb_softmax_update_fused(a->softmax, c, a->peer_bufs_dev, a->rank, a->seq + (unsigned long long)it,
+                                      final_it ? a->action_out : nullptr, final_it ? a->shift : 0, a->base_action,
+                                      final_it && a->shift ? a->cov_shift_beta : 0.0, stream);
         if (rc != MJB_OK) return rc;
-    }
-    if (a->action_out)
-        MJB_CUDA(cudaMemcpyAsync(a->action_out, c->mean, sizeof(double) * c->d, cudaMemcpyDeviceToDevice, s));
-    if (a->shift) {
-        if ((rc = mjb_shift_mean(c->mean, c->H, c->d, a->base_action, nullptr, stream)) != MJB_OK) return rc;
-        if (a->cov_shift_beta != 0.0) {
-            MJB_REQUIRE(c->cov, "mjb_softmax_mpc_step: cov_shift_beta needs the covariance");
-            if ((rc = mjb_cov_add_diag(c->cov, c->d, a->cov_shift_beta, nullptr, stream)) != MJB_OK) return rc;
-        }
     }
     if (forked) MJB_CUDA(cudaStreamWaitEvent(s, ev_join[dev], 0));
     return MJB_OK;

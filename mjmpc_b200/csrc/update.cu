@@ -57,10 +57,16 @@ __global__ void cost_to_go_kernel(const double* __restrict__ c, long long sk, lo
 }
 
 // ------------------------------------------------------------------------------ softmax phase 1
-// scratch layout (doubles): [0, MAXH) encoded minima | [MAXH, MAXH + H*d) u_n | then block partials
+// scratch layout (doubles): [0] "blocks done" counter of the fused update (zero once, resets itself) | [MAXH, MAXH + H*d) u_n |
+// block partials H*nchunks*NACC | block minima T*nb (nb = blocks of traj_cost_kernel)
+__host__ __device__ inline long long sm_off_partials(int H, int d) { return MJB_MAXH + (long long)H * d; }
+__host__ __device__ inline int sm_nb(int K) { return (K + MJB_RB - 1) / MJB_RB; }
+__host__ __device__ inline int sm_nchunks(int K) { return (K + MJB_CHUNK - 1) / MJB_CHUNK; }
+__host__ __device__ inline long long sm_off_bmin(int K, int H, int d, int NACC) {
+    return sm_off_partials(H, d) + (long long)H * sm_nchunks(K) * NACC;
+}
+// only with the control cost (MPPI alpha == 0): u_n = mean @ inv(cov)
 __global__ void softmax_prep_kernel(mjb_softmax_args a, int T) {
-    unsigned long long* menc = (unsigned long long*)a.scratch;
-    for (int i = threadIdx.x; i < T; i += blockDim.x) menc[i] = enc_key(INFINITY);
     if (!a.control_cost) return;
     // u_n = mean @ inv(cov)   (mppi.py:106); inverse by Gauss-Jordan with partial pivoting on a d x 2d tableau
     __shared__ double A[MJB_MAXD][2 * MJB_MAXD];
@@ -93,13 +99,19 @@ __global__ void softmax_prep_kernel(mjb_softmax_args a, int T) {
 // per-particle trajectory cost (mppi.py:84-97 / gaussian_dmd.py:94-104) and its minimum over particles.
 // TD = true: MPPIQ's TD(lambda) return (mppiq.py:92-126) instead of the discounted cost-to-go; W is then
 // the (H-1)-entry weight sequence cumprod([1, gamma*td_lam, ...]) and G is unused.
-template <int D, bool TD>
-__global__ void __launch_bounds__(MJB_RB) traj_cost_kernel(mjb_softmax_args a, GammaSeq G, GammaSeq W, int T) {
+// T1: one weight row (not time-based): only the t = 0 entry of the cost-to-go is used, so the per-step divisions
+// and stores of the other rows are skipped (the accumulation S is the same sequence of operations).
+// Minimum: warp shuffle, then one value per block and row in bmin[row * nb + block] -- no atomics, nothing to reset.
+template <int D, bool TD, bool T1>
+__global__ void __launch_bounds__(MJB_RB) traj_cost_kernel(mjb_softmax_args a, GammaSeq G, GammaSeq W, int T, double* __restrict__ bmin) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long* menc = (unsigned long long*)a.scratch;
     const double* __restrict__ un = a.scratch + MJB_MAXH;
     const bool live = k < a.K;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double S = 0.0, Sc = 0.0, tot0 = INFINITY, qnext = 0.0;
+    double keep[MJB_MAXH / 32];          // lane l keeps the warp minimum of rows l, l + 32, ...
+#pragma unroll
+    for (int i = 0; i < MJB_MAXH / 32; i++) keep[i] = INFINITY;
     // costs are read 8 steps at a time ahead of the (sequential, reference-ordered) accumulation
     for (int tb = a.H - 1; tb >= 0; tb -= 8) {
         double cbuf[8], qbuf[8];
@@ -113,6 +125,7 @@ __global__ void __launch_bounds__(MJB_RB) traj_cost_kernel(mjb_softmax_args a, G
         for (int u = 0; u < 8; u++) {
             const int t = tb - u;
             if (t < 0) break;
+            const bool need = !T1 || t == 0;       // this row's trajectory cost is used
             double tot = INFINITY;
             if (live) {
                 const double c = cbuf[u];
@@ -132,52 +145,79 @@ __global__ void __launch_bounds__(MJB_RB) traj_cost_kernel(mjb_softmax_args a, G
                     if (t == a.H - 1) tot = q;
                     else {
                         const double td = __dsub_rn(__dadd_rn(ct, __dmul_rn(a.td_gamma, qnext)), q);
-                        double ctg;
+                        double ctg = 0.0;
                         if (W.raw) ctg = td;
-                        else { S = __dadd_rn(S, __dmul_rn(W.g[t], td)); ctg = __ddiv_rn(S, W.g[t]); }
+                        else { S = __dadd_rn(S, __dmul_rn(W.g[t], td)); if (need) ctg = __ddiv_rn(S, W.g[t]); }
                         tot = __dadd_rn(q, __dmul_rn(a.td_lam, ctg));
                     }
                     qnext = q;
                 } else {
-                    double ctg;
+                    double ctg = 0.0;
                     if (G.raw) ctg = c;
-                    else { S = __dadd_rn(S, __dmul_rn(G.g[t], c)); ctg = __ddiv_rn(S, G.g[t]); }
+                    else { S = __dadd_rn(S, __dmul_rn(G.g[t], c)); if (need) ctg = __ddiv_rn(S, G.g[t]); }
                     double ccg = 0.0;
                     if (a.control_cost) {
                         if (G.raw) ccg = cc;
-                        else { Sc = __dadd_rn(Sc, __dmul_rn(G.g[t], cc)); ccg = __ddiv_rn(Sc, G.g[t]); }
+                        else { Sc = __dadd_rn(Sc, __dmul_rn(G.g[t], cc)); if (need) ccg = __ddiv_rn(Sc, G.g[t]); }
                     }
                     tot = ctg + a.lam * ccg;
                 }
-                if (T > 1) a.total[(long long)t * a.K + k] = tot;
+                if (!T1) a.total[(long long)t * a.K + k] = tot;
                 tot0 = tot;
             }
-            if (T > 1) {
+            if (!T1) {
                 double mn = tot;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                if ((threadIdx.x & 31) == 0 && mn < INFINITY) atomicMin(&menc[t], enc_key(mn));
+#pragma unroll
+                for (int i = 0; i < MJB_MAXH / 32; i++) if ((t >> 5) == i && lane == (t & 31)) keep[i] = mn;
             }
         }
     }
-    if (T == 1) {
+    __shared__ double wmin[MJB_RB / 32][MJB_MAXH];
+    if (T1) {
         if (live) a.total[k] = tot0;
         double mn = tot0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        if ((threadIdx.x & 31) == 0 && mn < INFINITY) atomicMin(&menc[0], enc_key(mn));
+        if (lane == 0) wmin[wid][0] = mn;
+    } else {
+#pragma unroll
+        for (int i = 0; i < MJB_MAXH / 32; i++) if (lane + 32 * i < T) wmin[wid][lane + 32 * i] = keep[i];
+    }
+    __syncthreads();
+    for (int tr = threadIdx.x; tr < T; tr += blockDim.x) {
+        double m = wmin[0][tr];
+#pragma unroll
+        for (int w2 = 1; w2 < MJB_RB / 32; w2++) m = fmin(m, wmin[w2][tr]);
+        bmin[(long long)tr * gridDim.x + blockIdx.x] = m;
     }
 }
 
+// minimum of one row of block minima, by all threads of a block (every thread returns it)
+__device__ double row_min(const double* __restrict__ bmin, int nb, int tr) {
+    __shared__ double rm[MJB_RB / 32];
+    double m = INFINITY;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) m = fmin(m, bmin[(long long)tr * nb + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __syncthreads();                       // rm may still be read by a previous call
+    if ((threadIdx.x & 31) == 0) rm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = rm[0];
+    for (int w2 = 1; w2 < (int)(blockDim.x >> 5); w2++) m = fmin(m, rm[w2]);
+    return m;
+}
+
 // Generic weighted reduction over particles for one (chunk, t) tile.
-//   WMODE 0: w = exp(ninv*total - ninv*m)   1: w = flag (0/1)   2: w = 1
+//   WMODE 0: w = exp(ninv*total - ninv*m), m = row minimum from the block minima   1: w = flag (0/1)   2: w = 1
 //   CMODE 0: none  1: diag  2: full lower triangle of  w (delta-mu)(delta-mu)',  delta = a - mean[t]
-// block partial -> out[(t*nchunks + chunk)*NACC + c],  NACC = 1 + D + ncov
+// block partial -> out[(t*nchunks + chunk)*NACC + c],  NACC = 1 + D + ncov.  `stage`: >= 8 * NACC doubles of shared memory.
 template <int D, int WMODE, int CMODE>
-__global__ void __launch_bounds__(MJB_RB) weighted_reduce_kernel(
-    int K, int H, const double* __restrict__ total, int T, const unsigned long long* __restrict__ menc, double ninv,
+__device__ __forceinline__ void reduce_tile(
+    int K, int H, const double* __restrict__ total, int T, const double* __restrict__ bmin, int nb, double ninv,
     const unsigned char* __restrict__ flags, const double* __restrict__ actions, long long sk, long long st, long long sj,
-    const double* __restrict__ mean, const double* __restrict__ mu, double* __restrict__ out) {
+    const double* __restrict__ mean, const double* __restrict__ mu, double* __restrict__ out, double* stage) {
     constexpr int NC = CMODE == 0 ? 0 : (CMODE == 1 ? D : D * (D + 1) / 2);
     constexpr int NACC = 1 + D + NC;
     const int t = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
@@ -186,7 +226,7 @@ __global__ void __launch_bounds__(MJB_RB) weighted_reduce_kernel(
     for (int c = 0; c < NACC; c++) acc[c] = 0.0;
     double xmax = 0.0;
     const double* trow = nullptr;
-    if (WMODE == 0) { const int tr = T > 1 ? t : 0; xmax = ninv * dec_key(menc[tr]); trow = total + (long long)tr * K; }
+    if (WMODE == 0) { const int tr = T > 1 ? t : 0; xmax = ninv * row_min(bmin, nb, tr); trow = total + (long long)tr * K; }
     double mrow[D], murow[D];
 #pragma unroll
     for (int j = 0; j < D; j++) { mrow[j] = (CMODE != 0) ? mean[t * D + j] : 0.0; murow[j] = (CMODE != 0 && mu) ? mu[j] : 0.0; }
@@ -231,57 +271,85 @@ __global__ void __launch_bounds__(MJB_RB) weighted_reduce_kernel(
             }
         }
     }
-    __shared__ double sm[MJB_RB / 32][NACC];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < NACC; c++) {
         const double v = warp_sum(acc[c]);
-        if (lane == 0) sm[wid][c] = v;
+        if (lane == 0) stage[wid * NACC + c] = v;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < NACC; c += MJB_RB) {
         double s = 0.0;
 #pragma unroll
-        for (int w2 = 0; w2 < MJB_RB / 32; w2++) s += sm[w2][c];
+        for (int w2 = 0; w2 < MJB_RB / 32; w2++) s += stage[w2 * NACC + c];
         out[((long long)t * nchunks + chunk) * NACC + c] = s;
     }
 }
 
+template <int D, int WMODE, int CMODE>
+__global__ void __launch_bounds__(MJB_RB) weighted_reduce_kernel(
+    int K, int H, const double* __restrict__ total, int T, const double* __restrict__ bmin, int nb, double ninv,
+    const unsigned char* __restrict__ flags, const double* __restrict__ actions, long long sk, long long st, long long sj,
+    const double* __restrict__ mean, const double* __restrict__ mu, double* __restrict__ out) {
+    __shared__ double stage[(MJB_RB / 32) * (1 + MJB_MAXD + MJB_MAXD * (MJB_MAXD + 1) / 2)];
+    reduce_tile<D, WMODE, CMODE>(K, H, total, T, bmin, nb, ninv, flags, actions, sk, st, sj, mean, mu, out, stage);
+}
+
+// loads of values another block / another GPU wrote during this kernel: from L2, never from this SM's L1
+__device__ __forceinline__ double ld_cg(const double* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+
 // fixed-order sum over chunks: part[t*NACC + c] = sum_chunk blockpart[(t*nchunks+chunk)*NACC + c]
 // (eight loads issued before the first add: the one-load-per-add form paid one L2 round trip per chunk)
+__device__ __forceinline__ double chunk_sum_one(const double* __restrict__ p, int nchunks, int NACC) {
+    double s = 0.0;
+    int ch = 0;
+    for (; ch + 8 <= nchunks; ch += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = ld_cg(p + (long long)(ch + u) * NACC);
+#pragma unroll
+        for (int u = 0; u < 8; u++) s += v[u];
+    }
+    for (; ch < nchunks; ch++) s += ld_cg(p + (long long)ch * NACC);
+    return s;
+}
 __global__ void chunk_sum_kernel(const double* __restrict__ bp, int nchunks, int NACC, double* __restrict__ part) {
     const int t = blockIdx.x;
-    for (int c = threadIdx.x; c < NACC; c += blockDim.x) {
-        const double* __restrict__ p = bp + (long long)t * nchunks * NACC + c;
-        double s = 0.0;
-        int ch = 0;
-        for (; ch + 8 <= nchunks; ch += 8) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = p[(long long)(ch + u) * NACC];
-#pragma unroll
-            for (int u = 0; u < 8; u++) s += v[u];
-        }
-        for (; ch < nchunks; ch++) s += p[(long long)ch * NACC];
-        part[t * NACC + c] = s;
-    }
+    for (int c = threadIdx.x; c < NACC; c += blockDim.x)
+        part[t * NACC + c] = chunk_sum_one(bp + (long long)t * nchunks * NACC + c, nchunks, NACC);
 }
-__global__ void decode_min_kernel(const unsigned long long* menc, int T, double* out) {
-    for (int i = threadIdx.x; i < T; i += blockDim.x) out[i] = dec_key(menc[i]);
+// phase-1 epilogue of the step-by-step path, one block per row t: the row's chunk sums and (t < T) its minimum
+__global__ void __launch_bounds__(MJB_RB) softmax_finalize_kernel(const double* __restrict__ bp, int nchunks, int NACC, int T,
+                                                                  const double* __restrict__ bmin, int nb, double* __restrict__ part) {
+    const int t = blockIdx.x;
+    for (int c = threadIdx.x; c < NACC; c += blockDim.x)
+        part[T + t * NACC + c] = chunk_sum_one(bp + (long long)t * nchunks * NACC + c, nchunks, NACC);
+    if (t < T) {
+        const double m = row_min(bmin, nb, t);
+        if (threadIdx.x == 0) part[t] = m;
+    }
 }
 
 // ------------------------------------------------------------------------------ softmax phase 2
-__device__ void softmax_combine_body(const mjb_combine_args& a) {
+struct CombineSmem {
+    double mstar[MJB_MAXH];
+    double comb[MJB_MAXH][1 + MJB_MAXD + MJB_MAXD * (MJB_MAXD + 1) / 2];
+};
+__device__ void softmax_combine_body(const mjb_combine_args& a, CombineSmem& sm) {
     const int H = a.H, d = a.d, T = a.time_based ? H : 1;
     const int nc = a.cov_mode == MJB_COV_NONE ? 0 : (a.cov_mode == MJB_COV_DIAG ? d : d * (d + 1) / 2);
     const int NACC = 1 + d + nc, P = T + H * NACC;
     const double ninv = -1.0 / a.lam;
-    __shared__ double mstar[MJB_MAXH];
-    __shared__ double comb[MJB_MAXH][1 + MJB_MAXD + MJB_MAXD * (MJB_MAXD + 1) / 2];
     for (int tr = threadIdx.x; tr < T; tr += blockDim.x) {
         double m = INFINITY;
-        for (int r = 0; r < a.n_shards; r++) m = fmin(m, a.partials[(long long)r * P + tr]);
-        mstar[tr] = m;
+        for (int r = 0; r < a.n_shards; r++) m = fmin(m, ld_cg(a.partials + (long long)r * P + tr));
+        sm.mstar[tr] = m;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < H * NACC; i += blockDim.x) {
@@ -289,27 +357,27 @@ __device__ void softmax_combine_body(const mjb_combine_args& a) {
         double s = 0.0;
         for (int r = 0; r < a.n_shards; r++) {
             const double* p = a.partials + (long long)r * P;
-            const double scale = exp(ninv * p[tr] - ninv * mstar[tr]);   // <= 1: shard minimum vs global minimum
-            s += p[T + i] * scale;
+            const double scale = exp(ninv * ld_cg(p + tr) - ninv * sm.mstar[tr]);   // <= 1: shard minimum vs global minimum
+            s += ld_cg(p + T + i) * scale;
         }
-        comb[t][i % NACC] = s;
+        sm.comb[t][i % NACC] = s;
     }
     __syncthreads();
     // a.mean == NULL: statistics only (the _calc_val pass leaves the distribution untouched)
     for (int i = threadIdx.x; a.mean && i < H * d; i += blockDim.x) {
         const int t = i / d, j = i % d;
-        a.mean[i] = (1.0 - a.step_size) * a.mean[i] + a.step_size * (comb[t][1 + j] / comb[t][0]);
+        a.mean[i] = (1.0 - a.step_size) * a.mean[i] + a.step_size * (sm.comb[t][1 + j] / sm.comb[t][0]);
     }
     if (a.mean && a.cov_mode != MJB_COV_NONE) {
         for (int i = threadIdx.x; i < d * d; i += blockDim.x) {
             const int r = i / d, c = i % d;
             double upd = 0.0;
             if (a.cov_mode == MJB_COV_DIAG) {
-                if (r == c) { for (int t = 0; t < H; t++) upd += comb[t][1 + d + r] / comb[t][0]; upd /= H; }
+                if (r == c) { for (int t = 0; t < H; t++) upd += sm.comb[t][1 + d + r] / sm.comb[t][0]; upd /= H; }
             } else {
                 const int hi = r > c ? r : c, lo = r > c ? c : r;
                 const int idx = 1 + d + hi * (hi + 1) / 2 + lo;
-                for (int t = 0; t < H; t++) upd += comb[t][idx] / comb[t][0];
+                for (int t = 0; t < H; t++) upd += sm.comb[t][idx] / sm.comb[t][0];
                 upd /= H;
             }
             a.cov[i] = (1.0 - a.step_size) * a.cov[i] + a.step_size * upd;
@@ -317,49 +385,143 @@ __device__ void softmax_combine_body(const mjb_combine_args& a) {
     }
     if (a.stats) {
         if (threadIdx.x == 0) {
-            a.stats[0] = -a.lam * (ninv * mstar[0] + log(comb[0][0] / (double)a.K_global));
-            a.stats[1] = mstar[0];
+            a.stats[0] = -a.lam * (ninv * sm.mstar[0] + log(sm.comb[0][0] / (double)a.K_global));
+            a.stats[1] = sm.mstar[0];
         }
-        for (int tr = threadIdx.x; tr < T; tr += blockDim.x) a.stats[2 + tr] = comb[tr][0];
+        for (int tr = threadIdx.x; tr < T; tr += blockDim.x) a.stats[2 + tr] = sm.comb[tr][0];
         // minima for the other rows of a time-based weighting live after the normalisers
-        for (int tr = threadIdx.x; tr < T; tr += blockDim.x) a.stats[2 + T + tr] = mstar[tr];
+        for (int tr = threadIdx.x; tr < T; tr += blockDim.x) a.stats[2 + T + tr] = sm.mstar[tr];
     }
 }
 
-__global__ void softmax_combine_kernel(mjb_combine_args a) { softmax_combine_body(a); }
+__global__ void softmax_combine_kernel(mjb_combine_args a) {
+    __shared__ CombineSmem sm;
+    softmax_combine_body(a, sm);
+}
 
-// Fused exchange + combine over NVLink peer memory (one block per GPU).  Every rank owns a symmetric
-// buffer [2][world][P] doubles + [2][world] sequence flags, mapped into all peers.  The kernel
+// Exchange of the per-rank partial vectors over NVLink peer memory, by one block per GPU.  Every rank owns a
+// symmetric buffer [2][world][P] doubles + [2][world] sequence flags, mapped into all peers.  The block
 //   1. stores its partial vector straight into slot [parity][rank] of EVERY peer's buffer (P2P stores),
-//   2. publishes its sequence number in every peer's flag word (system-scope fence before it),
-//   3. spins until all `world` flags of its own buffer carry this sequence number,
-//   4. combines the `world` partial vectors in rank order -- the same code as the single-GPU combine --
-// so the 2 KB exchange costs one NVLink round trip inside the reduction epilogue instead of a separate
-// NCCL launch.  Two parity halves: a rank can be at most one exchange ahead of the slowest peer.
+//   2. publishes its sequence number in every peer's flag word (release at system scope after a system fence),
+//   3. spins (acquire at system scope) until all `world` flags of its own buffer carry this sequence number,
+// and returns the `world` partial vectors in rank order; the caller reads them with L1-bypassing loads (ld_cg).
+// Two parity halves: a rank can be at most one exchange ahead of the slowest peer.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+    *(volatile unsigned long long*)p = v;
+#endif
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+#else
+    return *(const volatile unsigned long long*)p;
+#endif
+}
+__device__ const double* exchange_partials(const double* __restrict__ local, int P, void* const* __restrict__ peers, int rank,
+                                           unsigned long long seq, int world) {
+    const int parity = (int)(seq & 1ull);
+    for (int r = 0; r < world; r++) {
+        double* dst = (double*)peers[r] + ((long long)parity * world + rank) * P;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) dst[i] = ld_cg(local + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world)
+        st_release_sys((unsigned long long*)((double*)peers[threadIdx.x] + 2ll * world * P) + parity * world + rank, seq);
+    double* mine = (double*)peers[rank];
+    if ((int)threadIdx.x < world) {
+        const unsigned long long* flag = (const unsigned long long*)(mine + 2ll * world * P) + parity * world + threadIdx.x;
+        while (ld_acquire_sys(flag) < seq) { __nanosleep(64); }
+    }
+    __threadfence_system();
+    __syncthreads();
+    return mine + (long long)parity * world * P;
+}
+
+// Fused exchange + combine (one block per GPU): the 2 KB exchange costs one NVLink round trip inside the reduction
+// epilogue instead of a separate NCCL launch.
 __global__ void __launch_bounds__(256) softmax_exchange_combine_kernel(mjb_combine_args a, const double* __restrict__ local,
                                                                         int P, void* const* __restrict__ peers, int rank,
                                                                         unsigned long long seq) {
-    const int world = a.n_shards, parity = (int)(seq & 1ull);
-    for (int r = 0; r < world; r++) {
-        double* dst = (double*)peers[r] + ((long long)parity * world + rank) * P;
-        for (int i = threadIdx.x; i < P; i += blockDim.x) dst[i] = local[i];
-    }
-    __threadfence_system();
+    __shared__ CombineSmem sm;
+    a.partials = exchange_partials(local, P, peers, rank, seq, a.n_shards);
+    softmax_combine_body(a, sm);
+}
+
+// ------------------------------------------------------------------------------ the whole update tail in one kernel
+// weighted reduction (WMODE 0) whose LAST block to finish also runs everything that used to follow it as separate
+// launches: chunk sums + row minima -> this rank's partial vector, [peer exchange,] combine, next action, shift of
+// the mean sequence, cov += beta I.  Same arithmetic in the same order as the separate kernels (bit-identical).
+struct TailArgs {
+    mjb_combine_args c;
+    double* partials;                    // this rank's partial vector (P doubles), written here
+    const double* bp;                    // block partials of the reduction
+    const double* bmin;
+    int nb, nch, NACC, T, P;
+    unsigned int* counter;               // blocks done; zero before the first launch, reset by the last block
+    void* const* peers; int rank; unsigned long long seq;      // c.n_shards > 1
+    double* action_out;                  // (d,) <- mean[0] after the update, before the shift; or NULL
+    int shift, base_action;
+    double cov_shift_beta;
+};
+
+__device__ void shift_mean_body(double* mean, int H, int d, int base, const double* rnd, double* buf) {
+    // single block: read everything, sync, write (rows overlap)
+    for (int i = threadIdx.x; i < H * d; i += blockDim.x) buf[i] = mean[i];
     __syncthreads();
-    if (threadIdx.x < world) {
-        volatile unsigned long long* flag =
-            (volatile unsigned long long*)((double*)peers[threadIdx.x] + 2ll * world * P) + parity * world + rank;
-        *flag = seq;
+    for (int i = threadIdx.x; i < H * d; i += blockDim.x) {
+        const int t = i / d, j = i % d;
+        double v;
+        if (t < H - 1) v = buf[(t + 1) * d + j];
+        else if (base == MJB_BASE_NULL) v = 0.0;
+        else if (base == MJB_BASE_REPEAT) v = H >= 2 ? buf[(H - 1) * d + j] : buf[j];   // mean[-2] after the shift
+        else v = rnd[j];
+        mean[i] = v;
     }
-    double* mine = (double*)peers[rank];
-    if (threadIdx.x < world) {
-        volatile unsigned long long* flag = (volatile unsigned long long*)(mine + 2ll * world * P) + parity * world + threadIdx.x;
-        while (*flag < seq) { __nanosleep(64); }
-    }
-    __threadfence_system();
+}
+
+template <int D, int CMODE>
+__global__ void __launch_bounds__(MJB_RB) softmax_reduce_tail_kernel(
+    int K, int H, const double* __restrict__ total, int T, const double* __restrict__ bmin, int nb, double ninv,
+    const double* __restrict__ actions, long long sk, long long st, long long sj, const double* __restrict__ mean,
+    double* __restrict__ out, TailArgs ta) {
+    __shared__ CombineSmem sm;           // the staging area of the reduction aliases it (dead before the tail starts)
+    __shared__ bool is_last;
+    reduce_tile<D, 0, CMODE>(K, H, total, T, bmin, nb, ninv, nullptr, actions, sk, st, sj, mean, nullptr, out, &sm.comb[0][0]);
+    __threadfence();
     __syncthreads();
-    a.partials = mine + (long long)parity * world * P;
-    softmax_combine_body(a);
+    if (threadIdx.x == 0) is_last = atomicAdd(ta.counter, 1u) == gridDim.x * gridDim.y - 1u;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // this rank's partial vector (the work of softmax_finalize_kernel)
+    for (int i = threadIdx.x; i < H * ta.NACC; i += blockDim.x) {
+        const int t = i / ta.NACC, c = i % ta.NACC;
+        ta.partials[ta.T + i] = chunk_sum_one(ta.bp + (long long)t * ta.nch * ta.NACC + c, ta.nch, ta.NACC);
+    }
+    for (int tr = 0; tr < ta.T; tr++) {
+        const double m = row_min(ta.bmin, ta.nb, tr);
+        if (threadIdx.x == 0) ta.partials[tr] = m;
+    }
+    __threadfence();
+    __syncthreads();
+    mjb_combine_args c = ta.c;
+    if (c.n_shards > 1) c.partials = exchange_partials(ta.partials, ta.P, ta.peers, ta.rank, ta.seq, c.n_shards);
+    else c.partials = ta.partials;
+    softmax_combine_body(c, sm);
+    __syncthreads();
+    if (ta.action_out) for (int j = threadIdx.x; j < c.d; j += blockDim.x) ta.action_out[j] = c.mean[j];
+    __syncthreads();
+    if (ta.shift) {
+        shift_mean_body(c.mean, H, c.d, ta.base_action, nullptr, &sm.comb[0][0]);
+        if (ta.cov_shift_beta != 0.0 && (int)threadIdx.x < c.d) c.cov[threadIdx.x * c.d + threadIdx.x] += ta.cov_shift_beta * 1.0;
+    }
+    if (threadIdx.x == 0) *ta.counter = 0u;
 }
 
 __global__ void softmax_weights_kernel(const double* __restrict__ total, int K, const double* __restrict__ stats, int T,
@@ -758,19 +920,8 @@ __global__ void sub_mean_batched_kernel(const double* __restrict__ x, long long 
 
 // ------------------------------------------------------------------------------ shifts
 __global__ void shift_mean_kernel(double* mean, int H, int d, int base, const double* rnd) {
-    // single block: read everything, sync, write (rows overlap)
     extern __shared__ double buf[];
-    for (int i = threadIdx.x; i < H * d; i += blockDim.x) buf[i] = mean[i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < H * d; i += blockDim.x) {
-        const int t = i / d, j = i % d;
-        double v;
-        if (t < H - 1) v = buf[(t + 1) * d + j];
-        else if (base == MJB_BASE_NULL) v = 0.0;
-        else if (base == MJB_BASE_REPEAT) v = H >= 2 ? buf[(H - 1) * d + j] : buf[j];   // mean[-2] after the shift
-        else v = rnd[j];
-        mean[i] = v;
-    }
+    shift_mean_body(mean, H, d, base, rnd, buf);
 }
 __global__ void cov_add_diag_kernel(double* cov, int d, double beta, const double* v) {
     if (threadIdx.x < d) cov[threadIdx.x * d + threadIdx.x] += beta * (v ? v[threadIdx.x] : 1.0);
@@ -798,9 +949,9 @@ __global__ void pf_shift_kernel(double* s, long long sk, long long st, long long
 
 template <int D>
 static int launch_reduce(int wmode, int cmode, dim3 grid, cudaStream_t s, int K, int H, const double* total, int T,
-                         const unsigned long long* menc, double ninv, const unsigned char* flags, const double* actions,
+                         const double* bmin, int nb, double ninv, const unsigned char* flags, const double* actions,
                          long long sk, long long st, long long sj, const double* mean, const double* mu, double* out) {
-#define MJB_L(W, C) weighted_reduce_kernel<D, W, C><<<grid, MJB_RB, 0, s>>>(K, H, total, T, menc, ninv, flags, actions, sk, st, sj, mean, mu, out)
+#define MJB_L(W, C) weighted_reduce_kernel<D, W, C><<<grid, MJB_RB, 0, s>>>(K, H, total, T, bmin, nb, ninv, flags, actions, sk, st, sj, mean, mu, out)
     if (wmode == 0 && cmode == 0) MJB_L(0, 0);
     else if (wmode == 0 && cmode == 1) MJB_L(0, 1);
     else if (wmode == 0 && cmode == 2) MJB_L(0, 2);
@@ -812,10 +963,10 @@ static int launch_reduce(int wmode, int cmode, dim3 grid, cudaStream_t s, int K,
     return MJB_OK;
 }
 static int dispatch_reduce(int d, int wmode, int cmode, dim3 grid, cudaStream_t s, int K, int H, const double* total, int T,
-                           const unsigned long long* menc, double ninv, const unsigned char* flags, const double* actions,
+                           const double* bmin, int nb, double ninv, const unsigned char* flags, const double* actions,
                            long long sk, long long st, long long sj, const double* mean, const double* mu, double* out) {
     switch (d) {
-#define MJB_CASE(D) case D: return launch_reduce<D>(wmode, cmode, grid, s, K, H, total, T, menc, ninv, flags, actions, sk, st, sj, mean, mu, out);
+#define MJB_CASE(D) case D: return launch_reduce<D>(wmode, cmode, grid, s, K, H, total, T, bmin, nb, ninv, flags, actions, sk, st, sj, mean, mu, out);
         MJB_CASE(1) MJB_CASE(2) MJB_CASE(3) MJB_CASE(4) MJB_CASE(5) MJB_CASE(6) MJB_CASE(7) MJB_CASE(8)
 #undef MJB_CASE
     }
@@ -842,51 +993,116 @@ extern "C" int mjb_cost_to_go(const double* costs, long long sk, long long st, c
 }
 
 extern "C" long long mjb_softmax_scratch_doubles(int K, int H, int d, int cov_mode) {
-    const long long NACC = 1 + d + ncov_of(d, cov_mode);
-    return MJB_MAXH + (long long)H * d + (long long)H * nchunks_of(K) * NACC + 64;
+    const int NACC = 1 + d + ncov_of(d, cov_mode);
+    return sm_off_bmin(K, H, d, NACC) + (long long)H * sm_nb(K) + 64;
 }
 extern "C" int mjb_softmax_partial_doubles(int H, int d, int time_based, int cov_mode) {
     return (time_based ? H : 1) + H * (1 + d + ncov_of(d, cov_mode));
 }
 
-extern "C" int mjb_softmax_partials(const mjb_softmax_args* a, void* stream) {
+namespace mjb {
+static int softmax_check(const mjb_softmax_args* a, const char* who) {
     MJB_REQUIRE(a && a->costs && a->actions && a->mean && a->gamma_seq && a->total && a->scratch && a->partials,
-                "mjb_softmax_partials: null pointer");
-    MJB_REQUIRE(a->K >= 1 && a->H >= 1, "mjb_softmax_partials: bad shape K=%d H=%d", a->K, a->H);
+                "%s: null pointer", who);
+    MJB_REQUIRE(a->K >= 1 && a->H >= 1, "%s: bad shape K=%d H=%d", who, a->K, a->H);
     MJB_REQUIRE(a->d >= 1 && a->d <= MJB_MAXD, "d_action=%d not in 1..%d", a->d, MJB_MAXD);
     MJB_REQUIRE(a->lam > 0.0, "lam must be positive");
     MJB_REQUIRE(!a->control_cost || a->cov, "control cost needs cov");
     MJB_REQUIRE(!(a->time_based && a->cov_mode != MJB_COV_NONE), "time-based weights have no covariance update");
     if (a->cov_mode < 0 || a->cov_mode > 2)
         return set_error(MJB_EINVAL, "Unidentified covariance type in update_distribution");   // gaussian_dmd.py:85
-    MJB_REQUIRE(a->returns == MJB_RETURNS_CTG || a->returns == MJB_RETURNS_TD_LAMBDA, "mjb_softmax_partials: unknown returns mode %d", a->returns);
+    MJB_REQUIRE(a->returns == MJB_RETURNS_CTG || a->returns == MJB_RETURNS_TD_LAMBDA, "%s: unknown returns mode %d", who, a->returns);
     const bool td = a->returns == MJB_RETURNS_TD_LAMBDA;
     MJB_REQUIRE(!td || a->H == 1 || a->td_weight_seq, "TD(lambda) returns need td_weight_seq");
     MJB_REQUIRE(!(td && a->cov_mode != MJB_COV_NONE), "TD(lambda) returns have no covariance update");
+    return MJB_OK;
+}
+// [u_n when the control cost is on,] trajectory costs + block minima
+static int launch_traj_cost(const mjb_softmax_args* a, cudaStream_t s) {
+    const bool td = a->returns == MJB_RETURNS_TD_LAMBDA;
     GammaSeq G, W;
     int rc = load_gamma(G, a->gamma_seq, a->H);
     if (rc) return rc;
     W.raw = 0;
     if (td && a->H > 1) { rc = load_gamma(W, a->td_weight_seq, a->H - 1); if (rc) return rc; }
+    const int T = a->time_based ? a->H : 1;
+    const int NACC = 1 + a->d + ncov_of(a->d, a->cov_mode);
+    if (a->control_cost) softmax_prep_kernel<<<1, 128, 0, s>>>(*a, T);
+    double* bmin = a->scratch + sm_off_bmin(a->K, a->H, a->d, NACC);
+    const int tgrid = sm_nb(a->K);
+    switch (a->d) {
+#define MJB_TC(D, TDV, T1V) traj_cost_kernel<D, TDV, T1V><<<tgrid, MJB_RB, 0, s>>>(*a, G, W, T, bmin)
+#define MJB_CASE(D) case D: if (td) { if (T == 1) MJB_TC(D, true, true); else MJB_TC(D, true, false); } \
+                            else { if (T == 1) MJB_TC(D, false, true); else MJB_TC(D, false, false); } break;
+        MJB_CASE(1) MJB_CASE(2) MJB_CASE(3) MJB_CASE(4) MJB_CASE(5) MJB_CASE(6) MJB_CASE(7) MJB_CASE(8)
+#undef MJB_CASE
+#undef MJB_TC
+    }
+    return MJB_OK;
+}
+}  // namespace mjb
+
+extern "C" int mjb_softmax_partials(const mjb_softmax_args* a, void* stream) {
+    int rc = softmax_check(a, "mjb_softmax_partials");
+    if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int T = a->time_based ? a->H : 1;
     const int NACC = 1 + a->d + ncov_of(a->d, a->cov_mode);
-    const int nch = nchunks_of(a->K);
-    softmax_prep_kernel<<<1, 128, 0, s>>>(*a, T);
-    const int tgrid = (a->K + MJB_RB - 1) / MJB_RB;
+    const int nch = nchunks_of(a->K), nb = sm_nb(a->K);
+    rc = launch_traj_cost(a, s);
+    if (rc) return rc;
+    double* bp = a->scratch + sm_off_partials(a->H, a->d);
+    const double* bmin = a->scratch + sm_off_bmin(a->K, a->H, a->d, NACC);
+    rc = dispatch_reduce(a->d, 0, a->cov_mode, dim3(nch, a->H), s, a->K, a->H, a->total, T, bmin, nb, -1.0 / a->lam, nullptr,
+                         a->actions, a->act_sk, a->act_st, a->act_sj, a->mean, nullptr, bp);
+    if (rc) return rc;
+    softmax_finalize_kernel<<<a->H, MJB_RB, 0, s>>>(bp, nch, NACC, T, bmin, nb, a->partials);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+// The whole softmax update -- phase 1, [peer exchange,] phase 2, next action, hot-start shift -- in TWO launches
+// (three with the control cost): trajectory costs, then the weighted reduction whose last block runs the tail.
+// Same results as mjb_softmax_partials + mjb_softmax_combine / mjb_softmax_exchange_combine + mjb_shift_mean +
+// mjb_cov_add_diag, bit for bit.  a->scratch[0] is the "blocks done" counter: zero it once after allocating.
+extern "C" int mjb_softmax_update_fused(const mjb_softmax_args* a, const mjb_combine_args* c, void* const* peer_bufs_dev,
+                                        int rank, unsigned long long seq, double* action_out, int shift, int base_action,
+                                        double cov_shift_beta, void* stream) {
+    int rc = softmax_check(a, "mjb_softmax_update_fused");
+    if (rc) return rc;
+    MJB_REQUIRE(c && c->mean, "mjb_softmax_update_fused: the combine must apply the update (mean is NULL)");
+    MJB_REQUIRE(c->H == a->H && c->d == a->d && c->time_based == a->time_based && c->cov_mode == a->cov_mode,
+                "mjb_softmax_update_fused: softmax / combine shapes disagree");
+    MJB_REQUIRE(c->n_shards >= 1 && c->n_shards <= MJB_RB && (c->n_shards == 1 || peer_bufs_dev),
+                "mjb_softmax_update_fused: %d shards need the peer-memory exchange buffers", c->n_shards);
+    MJB_REQUIRE(c->cov_mode == MJB_COV_NONE || c->cov, "covariance update needs cov");
+    MJB_REQUIRE(base_action == MJB_BASE_NULL || base_action == MJB_BASE_REPEAT || !shift,
+                "mjb_softmax_update_fused: base_action 'random' needs a host-drawn row; use the separate entry points");
+    MJB_REQUIRE(cov_shift_beta == 0.0 || c->cov, "mjb_softmax_update_fused: cov_shift_beta needs the covariance");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int T = a->time_based ? a->H : 1;
+    const int NACC = 1 + a->d + ncov_of(a->d, a->cov_mode);
+    const int nch = nchunks_of(a->K), nb = sm_nb(a->K);
+    rc = launch_traj_cost(a, s);
+    if (rc) return rc;
+    double* bp = a->scratch + sm_off_partials(a->H, a->d);
+    const double* bmin = a->scratch + sm_off_bmin(a->K, a->H, a->d, NACC);
+    TailArgs ta;
+    ta.c = *c;
+    ta.partials = a->partials; ta.bp = bp; ta.bmin = bmin;
+    ta.nb = nb; ta.nch = nch; ta.NACC = NACC; ta.T = T; ta.P = T + a->H * NACC;
+    ta.counter = (unsigned int*)a->scratch;
+    ta.peers = peer_bufs_dev; ta.rank = rank; ta.seq = seq;
+    ta.action_out = action_out; ta.shift = shift; ta.base_action = base_action; ta.cov_shift_beta = cov_shift_beta;
+    const dim3 grid(nch, a->H);
+    const double ninv = -1.0 / a->lam;
     switch (a->d) {
-#define MJB_CASE(D) case D: if (td) traj_cost_kernel<D, true><<<tgrid, MJB_RB, 0, s>>>(*a, G, W, T); \
-                            else traj_cost_kernel<D, false><<<tgrid, MJB_RB, 0, s>>>(*a, G, W, T); break;
+#define MJB_RT(D, C) softmax_reduce_tail_kernel<D, C><<<grid, MJB_RB, 0, s>>>(a->K, a->H, a->total, T, bmin, nb, ninv, a->actions, a->act_sk, a->act_st, a->act_sj, a->mean, bp, ta)
+#define MJB_CASE(D) case D: if (a->cov_mode == 0) MJB_RT(D, 0); else if (a->cov_mode == 1) MJB_RT(D, 1); else MJB_RT(D, 2); break;
         MJB_CASE(1) MJB_CASE(2) MJB_CASE(3) MJB_CASE(4) MJB_CASE(5) MJB_CASE(6) MJB_CASE(7) MJB_CASE(8)
 #undef MJB_CASE
+#undef MJB_RT
     }
-    double* bp = a->scratch + MJB_MAXH + (long long)a->H * a->d;
-    rc = dispatch_reduce(a->d, 0, a->cov_mode, dim3(nch, a->H), s, a->K, a->H, a->total, T,
-                         (const unsigned long long*)a->scratch, -1.0 / a->lam, nullptr, a->actions, a->act_sk, a->act_st,
-                         a->act_sj, a->mean, nullptr, bp);
-    if (rc) return rc;
-    decode_min_kernel<<<1, 128, 0, s>>>((const unsigned long long*)a->scratch, T, a->partials);
-    chunk_sum_kernel<<<a->H, 64, 0, s>>>(bp, nch, NACC, a->partials + T);
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;
 }
@@ -941,7 +1157,7 @@ static int elite_moments(const mjb_elite_args* a, int pass, void* stream) {
     const int NACC = 1 + a->d + (pass == 1 ? 0 : a->d * (a->d + 1) / 2);
     double* bp = a->scratch;
     double* part = a->scratch + (long long)a->H * nch * NACC;
-    int rc = dispatch_reduce(a->d, 1, cmode, dim3(nch, a->H), s, a->K, a->H, nullptr, 1, nullptr, 0.0, a->flags, a->actions,
+    int rc = dispatch_reduce(a->d, 1, cmode, dim3(nch, a->H), s, a->K, a->H, nullptr, 1, nullptr, 0, 0.0, a->flags, a->actions,
                              a->act_sk, a->act_st, a->act_sj, a->mean, a->mu, bp);
     if (rc) return rc;
     chunk_sum_kernel<<<a->H, 64, 0, s>>>(bp, nch, NACC, part);
@@ -1004,7 +1220,7 @@ extern "C" int mjb_particle_mean(const double* x, long long sk, long long st, lo
     const int nch = nchunks_of(K), NACC = 1 + d;
     double* bp = scratch;
     double* part = scratch + (long long)H * nch * NACC;
-    int rc = dispatch_reduce(d, 2, 0, dim3(nch, H), s, K, H, nullptr, 1, nullptr, 0.0, nullptr, x, sk, st, sj, nullptr, nullptr, bp);
+    int rc = dispatch_reduce(d, 2, 0, dim3(nch, H), s, K, H, nullptr, 1, nullptr, 0, 0.0, nullptr, x, sk, st, sj, nullptr, nullptr, bp);
     if (rc) return rc;
     chunk_sum_kernel<<<H, 64, 0, s>>>(bp, nch, NACC, part);
     particle_mean_pack_kernel<<<1, 256, 0, s>>>(part, H, d, K, out);

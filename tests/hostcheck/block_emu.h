@@ -209,7 +209,8 @@ static inline double __dadd_rn(double a, double b) { return a + b; }     // comp
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
-static inline void __threadfence_system() {}
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __nanosleep(unsigned) {}
 template <class T> static inline T __ldg(const T* p) { return *p; }
 #define cudaGetLastError() cudaSuccess

@@ -1,7 +1,8 @@
-// TEST HARNESS (CPU): runs the product's simple one-thread-per-particle KERNELS -- the actual sources
-// noise.cu (K2) and rollout_reacher.cu (K1 wrapper: noise prefetch, fused noise, trajectory / observation
-// outputs, closed-loop policy) -- on the host, one simulated thread after another, so that changes made
-// without a GPU at hand are executed before they reach one.  Not a product path and not a CUDA emulator:
+// TEST HARNESS (CPU): runs the product's one-thread-per-particle rollout KERNEL -- the actual source
+// rollout_reacher.cu (K1 wrapper: noise prefetch, fused noise, trajectory / observation outputs, closed-loop
+// policy) -- on the host, one simulated thread after another, so that changes made without a GPU at hand are
+// executed before they reach one.  (The noise kernel K2 became a cooperating-thread kernel in round 2: it runs on
+// the block emulator, libmjmpc_b200_emu.so, like the update kernels.)  Not a product path and not a CUDA emulator:
 // it only covers kernels whose threads do not communicate (thread 0's shared-memory prologue runs first
 // because threads are simulated in index order); MUFU approximations are replaced by libm.
 #include <cmath>
@@ -29,21 +30,7 @@ static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((ui
 #define __launch_bounds__(...)
 #endif
 
-#include "../../mjmpc_b200/csrc/noise.cu"
 #include "../../mjmpc_b200/csrc/rollout_reacher.cu"
-
-// ---- K2 ------------------------------------------------------------------------------------------------
-extern "C" int emu_generate_noise(const mjb_noise_args* a) {
-    if (a->d != 7 && a->d != 1) return 1;
-    const unsigned block = 128, grid = (a->K + block - 1) / block;
-    blockDim = {block, 1, 1}; gridDim = {grid, 1, 1};
-    for (unsigned b = 0; b < grid; b++)
-        for (unsigned t = 0; t < block; t++) {
-            blockIdx = {b, 0, 0}; threadIdx = {t, 0, 0};
-            if (a->d == 7) mjb::noise_kernel<7>(*a); else mjb::noise_kernel<1>(*a);
-        }
-    return 0;
-}
 
 // ---- K1 ------------------------------------------------------------------------------------------------
 // params167: n_inst x MJB_MODEL_NPARAM host blocks.  One instance: constant-bank instantiation (as the library

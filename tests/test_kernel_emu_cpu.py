@@ -6,6 +6,7 @@ GPU; only the special-function-unit approximations are replaced by libm.  The GP
 checks on the device."""
 import ctypes as C
 import os
+import sys
 import subprocess
 
 import numpy as np
@@ -22,7 +23,12 @@ def emu():
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", cuda_inc, "-o", so,
                            os.path.join(d, "kernel_emu.cpp"), "-lm"])
-    return C.CDLL(so)
+    L = C.CDLL(so)
+    # K2 is a cooperating-thread kernel: it runs on the block emulator build of the whole C ABI
+    sys.path.insert(0, d)
+    import gen_lib_emu
+    L.block_emu = C.CDLL(gen_lib_emu.build())
+    return L
 
 
 def _vp(a):
@@ -77,7 +83,7 @@ def _noise(emu, cov, b, K, H, seed, step=0, k_offset=0, K_global=None, zero_last
         a.out_sk, a.out_st, a.out_sj = 1, d * K, K
         view = out.transpose(2, 0, 1)
     a.out = _vp(out)
-    assert emu.emu_generate_noise(C.byref(a)) == 0
+    assert emu.block_emu.mjb_generate_noise(C.byref(a), None) == 0
     _Guard.check()
     return view
 
