@@ -172,7 +172,7 @@ def workload_config(n_gpus):
     return {"workload": "MPPI reacher_7dof-v0 K=65536 H=32 n_iters=1 (BASELINE.json configs[2])",
             "num_particles": K_GLOBAL, "horizon": HORIZON, "d_action": D_ACTION,
             "particles_per_gpu": K_GLOBAL // n_gpus, "sharding": "particles, contiguous blocks, %d rank(s)" % n_gpus,
-            "noise": "Philox4x32-10 + covariance factor + AR filter kernel (K2), new stream every step", "start_states": "synthetic, SURVEY 8(d), sphere >= 2 cm above the table, new state every step",
+            "noise": "Philox4x32-10 + covariance factor + AR filter kernel (K2), new stream every step, drawn one step ahead on a side stream", "start_states": "synthetic, SURVEY 8(d), sphere >= 2 cm above the table, new state every step",
             "l2": "per-step working set (noise + actions + costs = 251 MB at N=1) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -206,7 +206,7 @@ def run_own(args):
                   action_highs=env.action_highs, num_particles=K_GLOBAL, seed=123, device=local_rank, shard=shard)
     policy = MPCPolicy("mppi", params)
     ctrl = policy.controller
-    ctrl.overlap_noise = bool(args.overlap_noise)
+    ctrl.overlap_noise = not args.no_overlap_noise
     ctrl.set_sim_state_fn = env.set_env_state
     ctrl.rollout_fn = env.rollout_fn
     states = synthetic_states(compiled, 64, seed=0)
@@ -421,7 +421,7 @@ def run_own(args):
                 "h2d_bytes_per_step": 17 * 8, "d2h_bytes_per_step": 7 * 8,
                 "api": "MPCPolicy.get_action(state_dict) -> (action ndarray, value)"},
         "gpu_launches": KERNELS_PER_STEP * args.steps, "cuda_graph": bool(graphed), "exchange": exchange,
-        "overlap_noise": bool(args.overlap_noise),
+        "overlap_noise": bool(ctrl.overlap_noise),
         "roofline": {"kernel": "rollout_reacher_kernel (K1)", "bound": "fp64", "achieved": achieved, "peak": tf.value,
                      "unit": "TFLOP/s", "frac": achieved / tf.value, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_hbm_bytes": kl * HORIZON * 120,
@@ -462,15 +462,14 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=0,
                     help="particles per MPC iteration of the CPU sample (default: 32768 for cpu_baseline; sized to the step count for --impl reference)")
     ap.add_argument("--watchdog", type=int, default=600, help="abort if the whole run exceeds this many seconds")
-    ap.add_argument("--overlap-noise", action="store_true",
-                    help="eager native step only (use with --no-graph, or N > 1): draw the next step's noise on a side stream")
+    ap.add_argument("--overlap-noise", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--no-overlap-noise", action="store_true",
+                    help="draw every step's noise in line instead of on a side stream during the previous step's rollout")
     ap.add_argument("--backend", default="nccl", help="torch.distributed backend for N > 1 (the driver's runs: nccl)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.overlap_noise:
-        args.no_graph = True          # the overlap lives in the eager native step; a replayed graph would ignore it
     _watchdog(args.watchdog)
     if args.impl == "reference":
         run_reference(args)

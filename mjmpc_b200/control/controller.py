@@ -49,6 +49,7 @@ class Controller(ABC):
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         self.shard = shard if shard is not None else ShardContext()
         self._graph = None            # captured CUDA graph of one MPC step (enable_cuda_graph)
+        self._graphs = []             # two of them alternate when the next step's noise is drawn during the rollout
         self._step_d = torch.zeros(1, dtype=torch.int64, device=self.device)   # device mirror of num_steps
 
     # ---- abstract surface (controller.py:80-143,203-205) -----------------------------------
@@ -104,6 +105,10 @@ class Controller(ABC):
     def optimize(self, state, calc_val=False, hotstart=True):
         if self._graph is not None and not calc_val and hotstart:
             return self._optimize_graphed(state), 0.0
+        if self._graph is not None:
+            # an eager step while a graph is active: the noise kernels read the device step counter that only
+            # a replay fills -- keep it current, or this step would reuse the previous step's noise
+            self._step_d.fill_(self.num_steps)
         if not calc_val:
             action = self._fused_step(state, hotstart)       # the whole step in one native call, when it can be
             if action is not None:
@@ -132,6 +137,8 @@ class Controller(ABC):
         if self._graph is not None and hotstart:
             self._replay(state)
             return self._graph_action
+        if self._graph is not None:
+            self._step_d.fill_(self.num_steps)
         action = self._fused_step(state, hotstart)
         if action is not None:
             self.num_steps += 1
@@ -146,7 +153,12 @@ class Controller(ABC):
         return action
 
     # ---- CUDA-graph replay of the step (launch-bound at small K per GPU) --------------------------
-    def _graph_body(self):
+    def _graph_body(self, parity=0):
+        blk = self.__dict__.get("_fused_blocks")
+        if blk is not None and "ready" in blk:
+            # overlapped noise: this graph reads noise tensor `parity` (already drawn) and draws the next step's
+            # noise into the other one
+            blk["ready"] = (parity, self.num_steps)
         action = self._fused_step(None, True)       # MPPI / DMD-MPC: the 4-launch native step is what gets captured
         if action is not None:
             return action
@@ -183,24 +195,45 @@ class Controller(ABC):
             for _ in range(2):
                 self._graph_body()
         torch.cuda.current_stream().wait_stream(side)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._graph_action = self._graph_body()
+        # with overlapped noise (two noise tensors) two graphs alternate; otherwise one
+        blk = self.__dict__.get("_fused_blocks")
+        n_graphs = 2 if (blk is not None and "ready" in blk) else 1
+        graphs = []
+        for parity in range(n_graphs):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_action = self._graph_body(parity)
+            graphs.append(g)
         for k, v in saved.items():
             getattr(self, k).copy_(v)
         self.num_steps = steps
-        self._graph = g
+        self._graphs, self._graph_parity, self._graph_ready = graphs, 0, None
+        self._graph = graphs[0]
+        if blk is not None and "ready" in blk:
+            blk["ready"] = None
         return True
 
     def disable_cuda_graph(self):
         self._graph = None
+        self._graphs = []
         self._noise_step = None
+        blk = self.__dict__.get("_fused_blocks")
+        if blk is not None and "ready" in blk:
+            blk["ready"] = None
 
     def _replay(self, state):
         if state is not None:
             self._set_sim_state_fn(copy.deepcopy(state))
         self._step_d.fill_(self.num_steps)
-        self._graph.replay()
+        if len(self._graphs) == 2:
+            p = self._graph_parity
+            if self._graph_ready != (p, self.num_steps):
+                # this step's noise is not in tensor p yet (first replay, or eager steps in between): draw it now
+                self._draw_step_noise(p, self.num_steps)
+            self._graphs[p].replay()
+            self._graph_parity, self._graph_ready = 1 - p, (1 - p, self.num_steps + 1)
+        else:
+            self._graph.replay()
         self.num_steps += 1
 
     def _optimize_graphed(self, state):

@@ -31,15 +31,17 @@ template <int D>
 __global__ void __launch_bounds__(MJB_NZ_THREADS) noise_kernel(mjb_noise_args a) {
     __shared__ double L[MJB_MAXD][MJB_MAXD];
     __shared__ double sh[MJB_NZ_TT][D][MJB_NZ_KP];      // shaped normals (L z) of the pass
-    if (threadIdx.x == 0) noise_chol<D>(a.cov, L);
+    if (threadIdx.x == 0) noise_chol<D>(a.cov, L);      // ~2 us of dependent sqrt / divide: once per (persistent) block
     __syncthreads();
-    const long long kb = (long long)blockIdx.x * MJB_NZ_KP;
     Philox ph{(unsigned)a.seed, (unsigned)(a.seed >> 32)};
     // counter = (global particle, step counter, t, stream id << 8 | pair index); key = seed
-    const unsigned step_ctr = a.step_ptr ? (unsigned)(*a.step_ptr) : (unsigned)a.offset;
+    const unsigned step_ctr = (a.step_ptr ? (unsigned)(*a.step_ptr) : 0u) + (unsigned)a.offset;
     const unsigned tag_hi = (unsigned)(a.offset >> 32) << 8;
     // phase-2 identity of this thread: particle kl2, dimension j2 (threads beyond 32 * D idle in phase 2)
     const int kl2 = threadIdx.x % MJB_NZ_KP, j2 = threadIdx.x / MJB_NZ_KP;
+    const long long ntiles = (a.K + MJB_NZ_KP - 1) / MJB_NZ_KP;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long kb = tile * MJB_NZ_KP;
     const long long k2 = kb + kl2;
     const bool act2 = j2 < D && k2 < a.K;
     const bool zero_seq = a.zero_last && (a.k_offset + k2) == a.K_global - 1;
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(MJB_NZ_THREADS) noise_kernel(mjb_noise_args a)
         }
         __syncthreads();
     }
+    }
 }
 
 }  // namespace mjb
@@ -91,7 +94,11 @@ extern "C" int mjb_generate_noise(const mjb_noise_args* a, void* stream) {
     MJB_REQUIRE(a->d >= 1 && a->d <= MJB_MAXD, "mjb_generate_noise: d=%d not in 1..%d", a->d, MJB_MAXD);
     MJB_REQUIRE(!a->zero_last || a->neg_mean, "mjb_generate_noise: zero_last needs the mean sequence");
     if (a->K == 0) return MJB_OK;
-    const int block = MJB_NZ_THREADS, grid = (a->K + MJB_NZ_KP - 1) / MJB_NZ_KP;
+    // persistent blocks striding over the 32-particle tiles: 4 resident blocks per SM's worth at most
+    static int sms = 0;
+    if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess) sms = 148;
+    const long long ntiles = ((long long)a->K + MJB_NZ_KP - 1) / MJB_NZ_KP;
+    const int block = MJB_NZ_THREADS, grid = (int)(ntiles < 4ll * sms ? ntiles : 4ll * sms);
     cudaStream_t s = (cudaStream_t)stream;
     switch (a->d) {
 #define MJB_CASE(D) case D: mjb::noise_kernel<D><<<grid, block, 0, s>>>(*a); break;

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(MJB_ROLLOUT_BLOCK, MJB_OCC) rollout_reacher_ke
     // fused noise: Philox keyed like mjb_generate_noise
     const unsigned long long gk = FUSED ? (unsigned long long)(a.noise_k_offset + k) : 0ull;
     const Philox ph{(unsigned)a.noise_seed, (unsigned)(a.noise_seed >> 32)};
-    const unsigned step_ctr = FUSED ? (a.noise_step_ptr ? (unsigned)(*a.noise_step_ptr) : (unsigned)a.noise_offset) : 0u;
+    const unsigned step_ctr = FUSED ? (a.noise_step_ptr ? (unsigned)(*a.noise_step_ptr) : 0u) + (unsigned)a.noise_offset : 0u;
     const unsigned tag_hi = (unsigned)(a.noise_offset >> 32) << 8;
     const bool zero_seq = FUSED && a.noise_zero_last && (long long)gk == a.noise_K_global - 1;
     if constexpr (FUSED) {

@@ -112,17 +112,19 @@ __global__ void __launch_bounds__(MJB_RB) traj_cost_kernel(mjb_softmax_args a, G
     double keep[MJB_MAXH / 32];          // lane l keeps the warp minimum of rows l, l + 32, ...
 #pragma unroll
     for (int i = 0; i < MJB_MAXH / 32; i++) keep[i] = INFINITY;
-    // costs are read 8 steps at a time ahead of the (sequential, reference-ordered) accumulation
-    for (int tb = a.H - 1; tb >= 0; tb -= 8) {
-        double cbuf[8], qbuf[8];
+    // costs are read PF steps at a time ahead of the (sequential, reference-ordered) accumulation: the kernel is one
+    // load latency per batch long (32 steps in flight when only the t = 0 row is needed: one batch at H = 32)
+    constexpr int PF = (T1 && !TD) ? 32 : 8;
+    for (int tb = a.H - 1; tb >= 0; tb -= PF) {
+        double cbuf[PF], qbuf[TD ? PF : 1];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < PF; u++) {
             const int t = tb - u;
             cbuf[u] = (live && t >= 0) ? a.costs[k * a.costs_sk + t * a.costs_st] : 0.0;
             if (TD) qbuf[u] = (live && t >= 0 && a.qvals) ? a.qvals[k * a.q_sk + t * a.q_st] : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < PF; u++) {
             const int t = tb - u;
             if (t < 0) break;
             const bool need = !T1 || t == 0;       // this row's trajectory cost is used
@@ -309,6 +311,13 @@ __device__ __forceinline__ double ld_cg(const double* p) {
 __device__ __forceinline__ double chunk_sum_one(const double* __restrict__ p, int nchunks, int NACC) {
     double s = 0.0;
     int ch = 0;
+    for (; ch + 32 <= nchunks; ch += 32) {          // K = 65536: all 32 chunks of a row in flight at once
+        double v[32];
+#pragma unroll
+        for (int u = 0; u < 32; u++) v[u] = ld_cg(p + (long long)(ch + u) * NACC);
+#pragma unroll
+        for (int u = 0; u < 32; u++) s += v[u];
+    }
     for (; ch + 8 <= nchunks; ch += 8) {
         double v[8];
 #pragma unroll

@@ -543,3 +543,46 @@ def test_fused_noise_controller_equals_two_kernel_path(compiled_model, graph, sp
         env.close()
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
+
+
+def test_graph_replay_mixed_with_eager_calls_and_a_plant_model(compiled_model):
+    """(1) with a graph active, optimize(hotstart=False) / calc_val=True take the eager path and must
+    draw the noise of THEIR step (the device step counter only a replay used to fill), so a mixed sequence equals
+    the all-eager one; (2) a plant with a DIFFERENT model stepping between replays must not change what the
+    planner's captured kernels read (the constant bank belongs to the planner's model)."""
+    from conftest import synthetic_state
+    from mjmpc_b200.control import MPPI
+    from mjmpc_b200.envs.gpu_reacher_env import GpuReacherEnv
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    from mjmpc_b200.envs.model import randomized_copy
+    K, H = 1024, 10
+    states = [synthetic_state(compiled_model, 30 + s) for s in range(5)]
+    heavy, _, _ = randomized_copy(compiled_model, dict(body_mass={"r_forearm_link": [0.0, 0.8], "r_wrist_roll_link": [0.0, 0.8]}),
+                                  np.random.RandomState(1))
+    outs = []
+    for graphed in (False, True):
+        env = GpuReacherVecEnv(compiled_model)
+        c = MPPI(horizon=H, num_particles=K, gamma=0.99, n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=4, init_cov=1.0,
+                 base_action='null', lam=0.2, step_size=0.9, alpha=1, **_common())
+        c.set_sim_state_fn, c.rollout_fn = env.set_env_state, env.rollout_fn
+        plant = GpuReacherEnv(heavy) if graphed else None           # the plant only exists (and steps) in the graphed run
+        if graphed:
+            assert c.enable_cuda_graph(states[0])
+        acts = []
+        for i, st in enumerate(states):
+            if i == 2:
+                a, v = c.optimize(st, calc_val=True)                # eager even when a graph is active
+            elif i == 3:
+                a, v = c.optimize(st, hotstart=False)
+            else:
+                a, v = c.optimize(st)
+            acts.append(a)
+            if plant is not None:
+                plant.set_env_state(st)
+                plant.step(a)                                       # another model's K=1 launch between two replays
+        outs.append((np.stack(acts), c.mean_action))
+        env.close()
+        if plant is not None:
+            plant.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
