@@ -700,6 +700,142 @@ __global__ void __launch_bounds__(1024) select_elites_kernel(const double* __res
     }
 }
 
+#if defined(__CUDACC__)
+// The same selection by a thread-block CLUSTER of 8 CTAs (sm_100a): every CTA keeps its eighth of the keys in shared
+// memory (up to 16 384 keys = 128 KB per CTA), so the eight radix passes never touch L2 again; the per-pass
+// histograms of the eight CTAs are summed through distributed shared memory behind cluster barriers, every CTA
+// picks the bin redundantly.  One launch, ~10 us at K = 65 536 against ~250 us for the one-block form above (eight
+// passes of 64 dependent L2 loads per thread).  Ties at the threshold go to the LOWER index, ids ascending.
+#define MJB_SEL_NC 8
+#define MJB_SEL_MAXKEYS 16384
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <class T> __device__ __forceinline__ T ld_dsmem(const T* p, unsigned rank);
+template <> __device__ __forceinline__ unsigned ld_dsmem<unsigned>(const unsigned* p, unsigned rank) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p), ra, v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(ra) : "memory");
+    return v;
+}
+template <> __device__ __forceinline__ long long ld_dsmem<long long>(const long long* p, unsigned rank) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p), ra;
+    long long v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.s64 %0, [%1];" : "=l"(v) : "r"(ra) : "memory");
+    return v;
+}
+// exclusive prefix of one value per thread over the block (1024 threads); returns the prefix, *total = block sum
+// (in every thread)
+__device__ long long block_excl_scan(long long x, long long* total) {
+    __shared__ long long wsum[32], s_total;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    __syncthreads();
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        long long w = wsum[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += y; }
+        wsum[lane] = winc - w;                   // exclusive prefix of the warp sums
+        if (lane == 31) s_total = winc;
+    }
+    __syncthreads();
+    *total = s_total;
+    return wsum[wid] + inc - x;
+}
+__global__ void __cluster_dims__(MJB_SEL_NC, 1, 1) __launch_bounds__(1024)
+select_elites_cluster_kernel(const double* __restrict__ v, long long K, long long E, unsigned char* __restrict__ flags,
+                             long long* __restrict__ ids) {
+    extern __shared__ unsigned long long keys[];
+    __shared__ unsigned hist[256], tot[256];
+    __shared__ unsigned long long s_prefix, s_want;
+    __shared__ long long s_cnt[2];               // this CTA's keys equal to the threshold / elite keys
+    const int tid = threadIdx.x;
+    const unsigned rank = cluster_rank();
+    const long long per = (K + MJB_SEL_NC - 1) / MJB_SEL_NC;
+    const long long lo = (long long)rank * per;
+    const int n = (int)(lo >= K ? 0 : (lo + per <= K ? per : K - lo));
+    for (int i = tid; i < n; i += 1024) keys[i] = enc_key(v[lo + i]);
+    if (tid == 0) { s_prefix = 0; s_want = (unsigned long long)E; }
+    __syncthreads();
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        for (int i0 = 0; i0 < n; i0 += 1024) {
+            const int i = i0 + tid;
+            const bool in = i < n && ((keys[i] & himask) == prefix);
+            // warp-aggregate: costs share their exponent byte, so whole warps hit one bin
+            const unsigned b = in ? (unsigned)(keys[i] >> shift) & 255u : 256u;
+            const unsigned peers = __match_any_sync(0xffffffffu, b);
+            if (in && (tid & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[b], (unsigned)__popc(peers));
+        }
+        __syncthreads();
+        cluster_sync_all();                      // every CTA's histogram of this pass is complete
+        if (tid < 256) {
+            unsigned sum = 0;
+#pragma unroll
+            for (unsigned r = 0; r < MJB_SEL_NC; r++) sum += ld_dsmem(&hist[tid], r);
+            tot[tid] = sum;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // bin holding the `want`-th smallest key: lane l owns bins 8l .. 8l+7
+            unsigned long long part = 0;
+#pragma unroll
+            for (int b = 0; b < 8; b++) part += tot[8 * tid + b];
+            unsigned long long inc = part;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += y; }
+            const unsigned long long want = s_want;
+            const unsigned hit = __ballot_sync(0xffffffffu, inc >= want);
+            const int owner = __ffs(hit) - 1;
+            if (tid == owner) {
+                unsigned long long cum = inc - part;
+                int b = 0;
+                for (; b < 8; b++) { if (cum + tot[8 * tid + b] >= want) break; cum += tot[8 * tid + b]; }
+                s_want = want - cum;
+                s_prefix = prefix | ((unsigned long long)(8 * tid + b) << shift);
+            }
+        }
+        __syncthreads();
+        cluster_sync_all();                      // nobody still reads my histogram when the next pass clears it
+    }
+    const unsigned long long thr = s_prefix;     // key of the E-th smallest value
+    const long long need_eq = (long long)s_want; // how many keys equal to it are elite (lowest indices first)
+    // ordered pass: thread t owns the contiguous keys [t*c, (t+1)*c) of this CTA
+    const int c = (n + 1023) / 1024, a0 = tid * c < n ? tid * c : n, a1 = a0 + c < n ? a0 + c : n;
+    long long neq = 0, nlt = 0;
+    for (int i = a0; i < a1; i++) { neq += keys[i] == thr; nlt += keys[i] < thr; }
+    long long tot_eq, tot_lt;
+    const long long eq_before_cta = block_excl_scan(neq, &tot_eq);
+    const long long lt_before_cta = block_excl_scan(nlt, &tot_lt);
+    if (tid == 0) { s_cnt[0] = tot_eq; s_cnt[1] = tot_lt; }
+    __syncthreads();
+    cluster_sync_all();
+    long long eq_base = 0, lt_base = 0;
+    for (unsigned r = 0; r < rank; r++) { eq_base += ld_dsmem(&s_cnt[0], r); lt_base += ld_dsmem(&s_cnt[1], r); }
+    long long eq_before = eq_base + eq_before_cta;
+    // ids position of this thread's first elite: elites before it = keys below the threshold + admitted ties
+    long long o = (lt_base + lt_before_cta) + (eq_before < need_eq ? eq_before : need_eq);
+    for (int i = a0; i < a1; i++) {
+        const unsigned long long key = keys[i];
+        bool e = key < thr;
+        if (key == thr) { e = eq_before < need_eq; eq_before++; }
+        flags[lo + i] = e ? 1 : 0;
+        if (e && ids) ids[o++] = lo + i;
+    }
+    cluster_sync_all();                          // no CTA exits while a peer may still read its shared memory
+}
+#endif  // __CUDACC__
+
 __global__ void __launch_bounds__(1024) argmin_kernel(const double* __restrict__ v, long long K, long long* out_idx,
                                                      double* out_val) {
     __shared__ unsigned long long sk[1024];
@@ -1139,6 +1275,18 @@ extern "C" int mjb_select_elites(const double* ctg0, long long K_global, long lo
     (void)scratch;
     MJB_REQUIRE(ctg0 && flags, "mjb_select_elites: null pointer");
     MJB_REQUIRE(K_global >= 1 && num_elite >= 1 && num_elite <= K_global, "num_elite=%lld must be in 1..K=%lld", num_elite, K_global);
+#if defined(__CUDACC__)
+    if (K_global <= (long long)MJB_SEL_NC * MJB_SEL_MAXKEYS && K_global >= 4096) {
+        // keys resident in the shared memory of an 8-CTA cluster (one launch, no L2 re-reads)
+        const long long per = (K_global + MJB_SEL_NC - 1) / MJB_SEL_NC;
+        const size_t smem = sizeof(unsigned long long) * (size_t)per;
+        MJB_CUDA(cudaFuncSetAttribute(select_elites_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(unsigned long long) * MJB_SEL_MAXKEYS)));
+        select_elites_cluster_kernel<<<MJB_SEL_NC, 1024, smem, (cudaStream_t)stream>>>(ctg0, K_global, num_elite, flags, ids);
+        MJB_CUDA(cudaGetLastError());
+        return MJB_OK;
+    }
+#endif
     select_elites_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ctg0, K_global, num_elite, flags, ids);
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;

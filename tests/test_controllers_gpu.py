@@ -213,6 +213,29 @@ def test_elite_select_negative_and_large():
     np.testing.assert_array_equal(ids.cpu().numpy(), np.sort(np.argsort(v, kind="stable")[:E]))
 
 
+@pytest.mark.parametrize("K", [4096, 65536, 70001, 131072, 131073])
+def test_elite_select_cluster_path_heavy_ties_and_ragged_sizes(K):
+    """4096 <= K <= 131072 takes the 8-CTA cluster kernel (keys in distributed shared memory); 131073 the one-block
+    kernel.  Quantised costs: thousands of ties at the threshold, ties go to the lower index, ids ascending; every
+    num_elite from 1 to K-ish, including thresholds inside a tie group that spans CTA boundaries."""
+    import torch
+    from mjmpc_b200 import _lib
+    rng = np.random.default_rng(K)
+    v = np.round(rng.normal(0, 3, K), 1)             # ~100 distinct values
+    v[rng.integers(0, K, 50)] = -0.0
+    t = torch.from_numpy(v).cuda()
+    order = np.argsort(np.where(v == 0.0, 0.0, v), kind="stable")
+    for E in (1, 17, K // 5, K // 2 + 3, K - 1, K):
+        flags = torch.zeros(K, dtype=torch.uint8, device="cuda")
+        ids = torch.full((E,), -1, dtype=torch.int64, device="cuda")
+        _lib.check(_lib.lib().mjb_select_elites(_lib.ptr(t), _lib.c_ll(K), _lib.c_ll(E), _lib.ptr(flags), _lib.ptr(ids), None,
+                                                _lib.stream_ptr()))
+        want = np.sort(order[:E])
+        np.testing.assert_array_equal(ids.cpu().numpy(), want)
+        f = flags.cpu().numpy()
+        assert f.sum() == E and f[want].all()
+
+
 def test_pfmpc_resampling_bit_exact():
     from mjmpc_b200.control import PFMPC
     import torch
