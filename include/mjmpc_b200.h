@@ -304,9 +304,11 @@ int mjb_blend_best(const double* actions, long long sk, long long st, long long 
                    long long k_offset, int K, int H, int d, double step_size, double* mean, void* stream);
 
 /* ---- K7 systematic resampling: PFMPC._resampling (particle_filter_controller.py:159-174).
- * Sequential FP64 prefix sum c_i (the reference's accumulation order, so indices are bit-exact),
- * idx[m] = first i with c_i >= r + m/M (clamped to M-1).  r = random.uniform(0, 1/M) from the host. */
-int mjb_resample_indices(const double* weights, long long M, double r, double* cumsum_scratch /* (M,) */,
+ * idx[m] = first i with c_i >= r + m/M (clamped to M-1), c_i the SEQUENTIAL FP64 prefix sum of the reference's
+ * accumulation order, so indices are bit-exact.  M >= 4096: a parallel prefix sum whose indices are certified
+ * against the rounding distance 4 M 2^-53 sum(w) to the bin edges; the sequential scan only re-runs when a sample
+ * cannot be certified.  r = random.uniform(0, 1/M) from the host. */
+int mjb_resample_indices(const double* weights, long long M, double r, double* cumsum_scratch /* (M + 2,) */,
                          long long* idx_out, void* stream);
 /* out[m] = in[idx[m]] for (K,H,d) tensors by strides */
 int mjb_gather_particles(const double* in, long long in_sk, long long in_st, long long in_sj, const long long* idx,

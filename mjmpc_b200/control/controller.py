@@ -259,8 +259,10 @@ class Controller(ABC):
         (horizon, num_particles) reset the distribution."""
         reshape = False
         for k, v in params.items():
-            if not hasattr(self, k):
+            if not hasattr(self, k) or callable(getattr(self, k)) and k != "seed":
                 raise ValueError("unknown controller parameter %r" % k)
+            if k == "seed":
+                continue                      # `seed` is a method (controller.py:277-279): re-seeded below
             if k in ("horizon", "num_particles", "d_action") and getattr(self, k) != v:
                 reshape = True
             setattr(self, k, v)

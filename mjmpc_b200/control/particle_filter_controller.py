@@ -254,7 +254,7 @@ class PFMPC(Controller):
         H, d = self.horizon, self.d_action
         r = random.uniform(0.0, 1.0 / M * 1.0)
         allw = self.shard.all_gather(weights.contiguous()).reshape(-1)
-        cs = self._buf("cumsum", (M,))
+        cs = self._buf("cumsum", (M + 2,))
         idx = self._buf("resample_idx", (M,), torch.int64)
         _lib.check(L.mjb_resample_indices(_lib.ptr(allw), _lib.c_ll(M), C.c_double(r), _lib.ptr(cs), _lib.ptr(idx),
                                           _lib.stream_ptr()))

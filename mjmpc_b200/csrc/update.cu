@@ -961,6 +961,96 @@ __global__ void resample_search_kernel(const double* __restrict__ cs, long long 
     }
     idx[m] = res;
 }
+// Parallel form of the same resampling, exact by certification.  The reference compares a SEQUENTIALLY accumulated
+// FP64 prefix sum with u_m = r + m/M; a parallel scan rounds differently, but both sums of M non-negative terms stay
+// within gamma_M * S (S = total weight) of the exact prefix, so they differ by at most eps = 4 M 2^-53 S.  An index
+// found in the parallel prefix is therefore the reference's index whenever u_m is more than eps away from the two
+// neighbouring prefix values; only if some u_m is closer (probability ~1e-6 per particle) the flag goes up and the
+// two sequential kernels below re-do the whole resampling in the reference's order.  Bit-exact always, ~15 us
+// instead of ~300 (65 536 dependent additions on one thread) in all but one call in a few dozen.
+// aux: [0] flag (as unsigned), [1] eps
+__global__ void __launch_bounds__(1024) par_cumsum_kernel(const double* __restrict__ w, long long M, double* __restrict__ cs,
+                                                          double* __restrict__ aux) {
+    __shared__ double wsum[32], s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long c = (M + 1023) / 1024, a0 = tid * c < M ? tid * c : M, a1 = a0 + c < M ? a0 + c : M;
+    double loc = 0.0;
+    for (long long i = a0; i < a1; i++) loc += w[i];
+    double inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const double x = wsum[lane];
+        double winc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double y = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += y; }
+        wsum[lane] = winc - x;
+        if (lane == 31) s_total = winc;
+    }
+    __syncthreads();
+    double run = wsum[wid] + (inc - loc);
+    for (long long i = a0; i < a1; i++) { run += w[i]; cs[i] = run; }
+    if (tid == 0) {
+        *(unsigned int*)aux = 0u;
+        aux[1] = 4.0 * (double)M * 1.1102230246251565e-16 * s_total;
+    }
+}
+__global__ void resample_search_certified_kernel(const double* __restrict__ cs, long long M, double r,
+                                                 long long* __restrict__ idx, double* __restrict__ aux) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const double eps = aux[1];
+    const double u = __dadd_rn(r, __ddiv_rn((double)m, (double)M));       // r + m*1.0/M*1.0
+    long long res;
+    bool sure = true;
+    if (!(0.0 < u)) res = M - 1;                                          // loop never runs: act_seq[-1]
+    else {
+        long long lo = 0, hi = M;                                         // first i with cs[i] >= u
+        while (lo < hi) { const long long mid = (lo + hi) >> 1; if (cs[mid] >= u) hi = mid; else lo = mid + 1; }
+        if (lo < M) sure = (cs[lo] - u > eps) && (lo == 0 || u - cs[lo - 1] > eps);
+        else sure = u - cs[M - 1] > eps;
+        res = lo < M ? lo : M - 1;
+    }
+    idx[m] = res;
+    if (!sure) atomicOr((unsigned int*)aux, 1u);
+}
+__global__ void __launch_bounds__(256) seq_cumsum_if_kernel(const double* __restrict__ w, long long M, double* __restrict__ cs,
+                                                            const double* __restrict__ aux) {
+    if (*(const unsigned int*)aux == 0u) return;
+    __shared__ double tile[2048];
+    __shared__ double carry;
+    if (threadIdx.x == 0) carry = 0.0;
+    for (long long base = 0; base < M; base += 2048) {
+        const int n = (int)(M - base < 2048 ? M - base : 2048);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = w[base + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double c = carry;
+            for (int i = 0; i < n; i++) { c = __dadd_rn(c, tile[i]); tile[i] = c; }   // reference order: c += w[i]
+            carry = c;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) cs[base + i] = tile[i];
+    }
+}
+__global__ void resample_search_if_kernel(const double* __restrict__ cs, long long M, double r, long long* __restrict__ idx,
+                                          const double* __restrict__ aux) {
+    if (*(const unsigned int*)aux == 0u) return;
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const double u = __dadd_rn(r, __ddiv_rn((double)m, (double)M));
+    long long res;
+    if (!(0.0 < u)) res = M - 1;
+    else {
+        long long lo = 0, hi = M;
+        while (lo < hi) { const long long mid = (lo + hi) >> 1; if (cs[mid] >= u) hi = mid; else lo = mid + 1; }
+        res = lo < M ? lo : M - 1;
+    }
+    idx[m] = res;
+}
 __global__ void gather_kernel(const double* __restrict__ in, long long isk, long long ist, long long isj,
                               const long long* __restrict__ idx, int K, int H, int d, double* __restrict__ out,
                               long long osk, long long ost, long long osj) {
@@ -1347,8 +1437,19 @@ extern "C" int mjb_resample_indices(const double* weights, long long M, double r
                                     long long* idx_out, void* stream) {
     MJB_REQUIRE(weights && cumsum_scratch && idx_out && M >= 1, "mjb_resample_indices: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
-    seq_cumsum_kernel<<<1, 256, 0, s>>>(weights, M, cumsum_scratch);
-    resample_search_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(cumsum_scratch, M, r, idx_out);
+    if (M < 4096) {            // small sets: the sequential scan is already short
+        seq_cumsum_kernel<<<1, 256, 0, s>>>(weights, M, cumsum_scratch);
+        resample_search_kernel<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(cumsum_scratch, M, r, idx_out);
+    } else {
+        // parallel prefix + certified search; the sequential pair runs only when a sample sits within the rounding
+        // distance of a bin edge (scratch: M doubles of prefix + 2 of flag / eps)
+        double* aux = cumsum_scratch + M;
+        const unsigned g = (unsigned)((M + 255) / 256);
+        par_cumsum_kernel<<<1, 1024, 0, s>>>(weights, M, cumsum_scratch, aux);
+        resample_search_certified_kernel<<<g, 256, 0, s>>>(cumsum_scratch, M, r, idx_out, aux);
+        seq_cumsum_if_kernel<<<1, 256, 0, s>>>(weights, M, cumsum_scratch, aux);
+        resample_search_if_kernel<<<g, 256, 0, s>>>(cumsum_scratch, M, r, idx_out, aux);
+    }
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;
 }

@@ -192,12 +192,14 @@ template <class T, class S> T shfl(T v, S src_of_lane) {
 static inline void __syncthreads() { emu::yield_at(emu::AT_BLOCK); }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int o) { return emu::shfl(v, [o](int l) { return l + o; }); }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int o) { return emu::shfl(v, [o](int l) { return l ^ o; }); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int o) { return emu::shfl(v, [o](int l) { return l - o < 0 ? l : l - o; }); }
 static inline unsigned __activemask() { return 1u << (emu::linear_tid() & 31); }
 template <class T> static inline unsigned __match_any_sync(unsigned, T) { return 1u << (emu::linear_tid() & 31); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
     unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
     while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}

@@ -275,6 +275,35 @@ def test_resample_skewed_weights():
     np.testing.assert_array_equal(cs.cpu().numpy(), np.cumsum(g["w"]))           # sequential order
 
 
+@pytest.mark.parametrize("M", [4096, 8192, 65536])
+@pytest.mark.parametrize("kind", ["softmax", "uniform_edges", "sparse", "dyadic_edges"])
+def test_resample_certified_parallel_path_is_bit_exact(M, kind):
+    """M >= 4096: parallel prefix sum + certified search, with the sequential scan as the fall-back for samples that sit
+    within the rounding distance of a bin edge.  `uniform_edges` / `dyadic_edges` put EVERY sample on an edge (r = 0,
+    equal weights: u_m == c_{m-1} up to rounding), so the fall-back decides all of them; the answer must be the
+    reference's (sequential np.cumsum order) in every case."""
+    import ctypes as C
+    import torch
+    from mjmpc_b200 import _lib
+    from oracle import control_np as O
+    rng = np.random.default_rng(M)
+    if kind == "softmax":
+        c = np.abs(rng.normal(2.0, 1.0, M)); w = np.exp(-(c - c.min()) / 0.2); w /= w.sum(); r = rng.uniform(0, 1.0 / M)
+    elif kind == "uniform_edges":
+        w = np.full(M, 1.0 / M); r = 0.0
+    elif kind == "dyadic_edges":
+        w = np.full(M, 1.0 / M); w[::2] *= 1.5; w[1::2] *= 0.5; r = 0.5 / M
+    else:
+        w = np.zeros(M); w[rng.integers(0, M, 5)] = rng.uniform(0.1, 1.0, 5); w /= w.sum(); r = rng.uniform(0, 1.0 / M)
+    want = O.pf_resample_with_r(w, r) % M
+    wt = torch.from_numpy(w).cuda()
+    cs = torch.empty(M + 2, dtype=torch.float64, device="cuda")
+    idx = torch.empty(M, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.lib().mjb_resample_indices(_lib.ptr(wt), _lib.c_ll(M), C.c_double(float(r)), _lib.ptr(cs), _lib.ptr(idx),
+                                               _lib.stream_ptr()))
+    np.testing.assert_array_equal(idx.cpu().numpy(), want)
+
+
 @pytest.mark.parametrize("K,gamma", [(32, 1.0), (257, 0.97), (4096, 0.9)])
 def test_pf_update_batched_kernel(K, gamma):
     """mjb_pf_update_batched per instance against the numpy restatement: weights 1e-10, resampling indices

@@ -121,7 +121,7 @@ def test_systematic_resampling_indices_bit_exact(L, K, lam, rfrac, s):
     r = rfrac / K
     want = O.pf_resample_with_r(w, r)
     guard = Guard()
-    w = guard(w); cs = guard(np.zeros(K)); got = guard(np.zeros(K, np.int64))
+    w = guard(w); cs = guard(np.zeros(K + 2)); got = guard(np.zeros(K, np.int64))
     ok(L, L.mjb_resample_indices(vp(w), C.c_longlong(K), C.c_double(r), vp(cs), vp(got), None))
     guard.check()
     np.testing.assert_array_equal(got, want % K)            # the reference's index -1 (r = 0) is the last particle
