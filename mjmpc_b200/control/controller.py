@@ -208,6 +208,7 @@ class Controller(ABC):
             getattr(self, k).copy_(v)
         self.num_steps = steps
         self._graphs, self._graph_parity, self._graph_ready = graphs, 0, None
+        self._graph_state_gen = getattr(getattr(self._rollout_fn, "backend", None), "state_generation", 0)
         self._graph = graphs[0]
         if blk is not None and "ready" in blk:
             blk["ready"] = None
@@ -224,6 +225,10 @@ class Controller(ABC):
     def _replay(self, state):
         if state is not None:
             self._set_sim_state_fn(copy.deepcopy(state))
+        backend = getattr(self._rollout_fn, "backend", None)
+        if backend is not None and getattr(backend, "state_generation", 0) != self._graph_state_gen:
+            raise _lib.MjbError("the rollout backend reallocated its state buffer (different number of states) after "
+                                "enable_cuda_graph(): call enable_cuda_graph again")
         self._step_d.fill_(self.num_steps)
         if len(self._graphs) == 2:
             p = self._graph_parity

@@ -8,6 +8,7 @@
 // launches (interpreter, ctypes marshalling, tensor bookkeeping: ~0.3 ms per step from Python against
 // ~0.04 ms here), which is what bounds a step that cannot replay a CUDA graph -- the sharded multi-GPU step,
 // whose exchange kernel waits on peers -- once a GPU's share of the particles is small.
+#include <mutex>
 #include "common.h"
 
 extern "C" int mjb_softmax_mpc_step(const mjb_mpc_step_args* a, void* stream) {
@@ -28,6 +29,10 @@ extern "C" int mjb_softmax_mpc_step(const mjb_mpc_step_args* a, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     bool forked = false;
+    // per-device side stream and fork / join events, created once under a lock (controllers of several threads --
+    // logical ranks in tests -- may step concurrently).  Steps that share a device share them: two controllers
+    // forking at the same time only add a false dependency between their side-stream launches.
+    static std::mutex side_mutex;
     static cudaStream_t side[64] = {nullptr};
     static cudaEvent_t ev_fork[64] = {nullptr}, ev_join[64] = {nullptr};
     const int dev = a->model->device & 63;
@@ -39,6 +44,7 @@ extern "C" int mjb_softmax_mpc_step(const mjb_mpc_step_args* a, void* stream) {
         // and on a lowest-priority stream, so that the rollout's blocks take the SMs first and the noise blocks
         // fill what they leave; joined before returning.
         MJB_REQUIRE(a->noise_next->out != a->rollout->noise, "mjb_softmax_mpc_step: noise_next would overwrite the tensor this step reads");
+        std::lock_guard<std::mutex> lock(side_mutex);
         if (!side[dev]) {
             MJB_CUDA(cudaSetDevice(a->model->device));
             int lo = 0, hi = 0;
@@ -50,13 +56,21 @@ extern "C" int mjb_softmax_mpc_step(const mjb_mpc_step_args* a, void* stream) {
         MJB_CUDA(cudaEventRecord(ev_fork[dev], s));
         MJB_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
     }
+    // an error after the fork must not leave side-stream work unjoined
+    auto fail = [&](int code) {
+        if (forked) cudaStreamWaitEvent(s, ev_join[dev], 0);
+        return code;
+    };
     for (int it = 0; it < a->n_iters; it++) {
-        if (a->noise && (rc = mjb_generate_noise(a->noise, stream)) != MJB_OK) return rc;
-        if ((rc = mjb_rollout_reacher(a->model, a->rollout, stream)) != MJB_OK) return rc;
+        if (a->noise && (rc = mjb_generate_noise(a->noise, stream)) != MJB_OK) return fail(rc);
+        if ((rc = mjb_rollout_reacher(a->model, a->rollout, stream)) != MJB_OK) return fail(rc);
         if (a->noise_next && it == 0) {
-            if ((rc = mjb_generate_noise(a->noise_next, (void*)side[dev])) != MJB_OK) return rc;
+            std::lock_guard<std::mutex> lock(side_mutex);
+            rc = mjb_generate_noise(a->noise_next, (void*)side[dev]);
+            // joined even when the launch failed: the side stream still waits on this step's fork event
             MJB_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
             forked = true;
+            if (rc != MJB_OK) return fail(rc);
         }
         // the whole update tail rides in the last block of the weighted reduction; after the last iteration it
         // also hands out the next action and shifts the mean sequence (4 launches per MPPI iteration in all)
@@ -64,7 +78,7 @@ extern "C" int mjb_softmax_mpc_step(const mjb_mpc_step_args* a, void* stream) {
         rc = mjb_softmax_update_fused(a->softmax, c, a->peer_bufs_dev, a->rank, a->seq + (unsigned long long)it,
                                       final_it ? a->action_out : nullptr, final_it ? a->shift : 0, a->base_action,
                                       final_it && a->shift ? a->cov_shift_beta : 0.0, stream);
-        if (rc != MJB_OK) return rc;
+        if (rc != MJB_OK) return fail(rc);
     }
     if (forked) MJB_CUDA(cudaStreamWaitEvent(s, ev_join[dev], 0));
     return MJB_OK;

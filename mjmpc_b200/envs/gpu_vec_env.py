@@ -94,6 +94,7 @@ class GpuReacherVecEnv:
         self._state_host = torch.zeros(1, _lib.STATE_DIM, dtype=torch.float64).pin_memory()
         self._state = torch.zeros(1, _lib.STATE_DIM, dtype=torch.float64, device=self.device)
         self._h2d_done = None
+        self.state_generation = 0          # bumped whenever the device state buffer is reallocated
         self.action_lows = -np.ones(7)
         self.action_highs = np.ones(7)
 
@@ -118,10 +119,7 @@ class GpuReacherVecEnv:
                 rows = np.stack([_state_vector(s) for s in state_dicts])
         else:
             rows = _state_vector(state_dicts)[None]
-        if self._state_host.shape[0] != rows.shape[0]:
-            self._state_host = torch.zeros(rows.shape[0], _lib.STATE_DIM, dtype=torch.float64).pin_memory()
-            self._state = torch.zeros(rows.shape[0], _lib.STATE_DIM, dtype=torch.float64, device=self.device)
-            self._h2d_done = None
+        self._resize_state(rows.shape[0])
         if self._h2d_done is not None:
             self._h2d_done.synchronize()       # the previous asynchronous copy must have left the pinned buffer
         self._state_host.copy_(torch.from_numpy(rows))
@@ -134,9 +132,21 @@ class GpuReacherVecEnv:
         """Device-resident (n_ctrl, 17) states (no host round trip).  Copied into the persistent state
         buffer so that a captured CUDA graph of the MPC step keeps reading the right address."""
         state = state.reshape(-1, _lib.STATE_DIM)
-        if state.shape[0] != self._state.shape[0]:
-            self._state = torch.zeros(state.shape[0], _lib.STATE_DIM, dtype=torch.float64, device=self.device)
+        self._resize_state(state.shape[0])
         self._state.copy_(state)
+
+    def _resize_state(self, n_rows):
+        """Host and device state buffers always change size together.  The device buffer's address is baked into
+        captured CUDA graphs and cached argument blocks of the controllers, so a resize bumps `state_generation`
+        (controllers compare it and drop their graph / blocks)."""
+        if self._state.shape[0] == n_rows and self._state_host.shape[0] == n_rows:
+            return
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()
+        self._state_host = torch.zeros(n_rows, _lib.STATE_DIM, dtype=torch.float64).pin_memory()
+        self._state = torch.zeros(n_rows, _lib.STATE_DIM, dtype=torch.float64, device=self.device)
+        self._h2d_done = None
+        self.state_generation += 1
 
     def reset(self):
         pass

@@ -567,6 +567,10 @@ def randomized_copy(cm: CompiledModel, param_dict: dict, rng: np.random.RandomSt
             elif param_id in ("dof_frictionloss", "geom_size", "geom_friction", "sensor_noise"):
                 if noise_scale != 0.0 or bias_scale != 0.0:
                     raise ValueError("dynamics field %s is not modelled by the GPU rollout" % param_id)
+                # the reference still draws for such an entry (gym_env_wrapper.py:406-408: one uniform per element of the
+                # field -- geom_size and geom_friction are 3-vectors): consume the same draws, or every parameter
+                # listed after it would get a different value than the reference's worker with this seed
+                rng.uniform(size=3 if param_id in ("geom_size", "geom_friction") else None)
                 continue
             else:
                 raise ValueError("Unknown dynamics field")
