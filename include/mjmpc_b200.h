@@ -137,6 +137,11 @@ typedef struct {
     const double* neg_mean;      /* (H,d) mean sequence, needed when zero_last */
     double* out;                 /* (K,H,d) by strides */
     long long out_sk, out_st, out_sj;
+    /* batched controller instances with their OWN covariance (CEM with batch_size > 1): particle k draws from
+     * cov + ((k_offset + k) / particles_per_cov) * cov_stride.  cov_stride == 0 (default): one covariance for all.
+     * particles_per_cov must be a multiple of 32 (one covariance per 32-particle tile). */
+    long long cov_stride;
+    int particles_per_cov;
 } mjb_noise_args;
 int mjb_generate_noise(const mjb_noise_args* a, void* stream);
 
@@ -302,6 +307,35 @@ int mjb_elite_combine(const mjb_elite_combine_args* a, void* stream);
 /* mean <- (1-step)*mean + step*actions[best] (random_shooting.py:61-62); best_index device (1,) */
 int mjb_blend_best(const double* actions, long long sk, long long st, long long sj, const long long* best_index,
                    long long k_offset, int K, int H, int d, double step_size, double* mean, void* stream);
+
+/* Batched update of many small independent controller instances (one thread block each, no cross-instance
+ * reduction), the RandomShooting / CEM counterpart of mjb_mppi_update_batched: instance c owns particles
+ * [c*K, (c+1)*K), mean row c and (CEM) covariance c.
+ *   mode MJB_INST_RS:        mean <- (1-step) mean + step actions[argmin ctg0]      (random_shooting.py:52-62)
+ *   mode MJB_INST_CEM_DIAG / MJB_INST_CEM_FULL:  elite set = num_elite smallest ctg0 (ties -> lower index);
+ *        cov <- (1-step) cov + step (diag(np.var) | np.cov) of the elite deltas pooled over (elite, t), deltas taken
+ *        from the mean BEFORE its update; mean <- (1-step) mean + step mean(elite actions)      (cem.py:65-86)
+ * ids out: (n_ctrl, num_elite) elite indices within the instance, ascending (RS: (n_ctrl,) the argmin); value out:
+ * (n_ctrl,) mean cost-to-go (cem.py:107-113, random_shooting.py:65-69); either may be NULL.  apply == 0: values /
+ * ids only, mean and cov untouched.  K <= 4096. */
+#define MJB_INST_RS 0
+#define MJB_INST_CEM_DIAG 1
+#define MJB_INST_CEM_FULL 2
+typedef struct {
+    int n_ctrl, K, H, d, mode, apply;
+    long long num_elite;
+    const double* costs; long long costs_sk, costs_st;       /* (n_ctrl*K, H) */
+    const double* actions; long long act_sk, act_st, act_sj; /* (n_ctrl*K, H, d) */
+    double* mean;                /* (n_ctrl, H, d) in/out */
+    double* cov;                 /* (n_ctrl, d, d) in/out (CEM modes) */
+    const double* gamma_seq;     /* (H,) HOST */
+    double step_size;
+    long long* ids;
+    double* value;
+} mjb_instances_args;
+int mjb_instances_update_batched(const mjb_instances_args* a, void* stream);
+/* cov[c] += beta * diag(v) for n stacked (d,d) covariances (CEM._shift, cem.py:89-95, batched instances) */
+int mjb_cov_add_diag_batched(double* cov, int n, int d, double beta, const double* v, void* stream);
 
 /* ---- K7 systematic resampling: PFMPC._resampling (particle_filter_controller.py:159-174).
  * idx[m] = first i with c_i >= r + m/M (clamped to M-1), c_i the SEQUENTIAL FP64 prefix sum of the reference's

@@ -120,7 +120,22 @@ class NoiseArgs(C.Structure):
         ("cov", C.c_void_p), ("beta0", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double),
         ("zero_last", C.c_int), ("neg_mean", C.c_void_p),
         ("out", C.c_void_p), ("out_sk", c_ll), ("out_st", c_ll), ("out_sj", c_ll),
+        ("cov_stride", c_ll), ("particles_per_cov", C.c_int),
     ]
+
+
+class InstancesArgs(C.Structure):
+    _fields_ = [
+        ("n_ctrl", C.c_int), ("K", C.c_int), ("H", C.c_int), ("d", C.c_int), ("mode", C.c_int), ("apply", C.c_int),
+        ("num_elite", c_ll),
+        ("costs", C.c_void_p), ("costs_sk", c_ll), ("costs_st", c_ll),
+        ("actions", C.c_void_p), ("act_sk", c_ll), ("act_st", c_ll), ("act_sj", c_ll),
+        ("mean", C.c_void_p), ("cov", C.c_void_p), ("gamma_seq", C.c_void_p),
+        ("step_size", C.c_double), ("ids", C.c_void_p), ("value", C.c_void_p),
+    ]
+
+
+INST_RS, INST_CEM_DIAG, INST_CEM_FULL = 0, 1, 2
 
 
 class SoftmaxArgs(C.Structure):
@@ -202,6 +217,7 @@ BASE_ACTIONS = {"null": 0, "repeat": 1, "random": 2}
 EXPORTS += [
     "mjb_rollout_pendulum", "mjb_rollout_lqr", "mjb_generate_noise", "mjb_cost_to_go",
     "mjb_softmax_scratch_doubles", "mjb_softmax_partial_doubles", "mjb_softmax_partials", "mjb_softmax_update_fused",
+    "mjb_instances_update_batched", "mjb_cov_add_diag_batched",
     "mjb_softmax_combine", "mjb_softmax_exchange_combine", "mjb_softmax_weights",
     "mjb_select_elites", "mjb_argmin", "mjb_elite_scratch_doubles", "mjb_elite_moments1",
     "mjb_elite_moments2", "mjb_elite_combine", "mjb_blend_best",

@@ -48,6 +48,9 @@ class CEM(OLGaussianMPC):
             raise ValueError('Unidentified covariance type in update_distribution')
         L = _lib.lib()
         costs, actions = self._traj(trajectories)
+        if self.batch_size > 1:
+            self._batched_update(costs, actions, apply=True)
+            return
         k0, kl = self.shard.local_range(self.num_particles)
         H, d = self.horizon, self.d_action
         flags, ids = self._select(self._ctg0(costs))
@@ -75,14 +78,42 @@ class CEM(OLGaussianMPC):
         c.partial2, c.mean, c.cov = all2.data_ptr(), self._mean.data_ptr(), self._cov.data_ptr()
         _lib.check(L.mjb_elite_combine(C.byref(c), _lib.stream_ptr()))
 
+    _per_instance_cov = True          # batched instances adapt their own covariance
+
+    def _batched_update(self, costs, actions, apply):
+        """batch_size independent instances: one thread block per instance does cost-to-go, elite selection and
+        both moments (cem.py:65-86); every instance keeps its own covariance.  elite_ids: (batch_size, num_elite)."""
+        a = _lib.InstancesArgs()
+        a.n_ctrl, a.K, a.H, a.d = self.batch_size, self.num_particles, self.horizon, self.d_action
+        a.mode, a.apply = (_lib.INST_CEM_FULL if self.cov_type == 'full' else _lib.INST_CEM_DIAG), int(apply)
+        a.num_elite = self.num_elite
+        a.costs = costs.data_ptr(); a.costs_sk, a.costs_st = costs.stride()
+        a.actions = actions.data_ptr(); a.act_sk, a.act_st, a.act_sj = actions.stride()
+        a.mean, a.cov = self._mean.data_ptr(), self._cov.data_ptr()
+        g = np.ascontiguousarray(self.gamma_seq.reshape(-1))
+        a.gamma_seq = g.ctypes.data
+        a.step_size = float(self.step_size)
+        ids = self._buf("elite_ids_b", (self.batch_size, self.num_elite), torch.int64)
+        value = self._buf("batched_value", (self.batch_size,))
+        a.ids, a.value = ids.data_ptr(), value.data_ptr()
+        _lib.check(_lib.lib().mjb_instances_update_batched(C.byref(a), _lib.stream_ptr()))
+        self.elite_ids = ids
+        return value
+
     def _shift(self):
         """cem.py:89-95: shift the mean and grow the covariance by beta*diag(init_cov)."""
         super()._shift()
+        if self.batch_size > 1:
+            _lib.check(_lib.lib().mjb_cov_add_diag_batched(_lib.ptr(self._cov), C.c_int(self.batch_size), C.c_int(self.d_action),
+                                                           C.c_double(self.beta), _lib.ptr(self._init_cov_d), _lib.stream_ptr()))
+            return
         _lib.check(_lib.lib().mjb_cov_add_diag(_lib.ptr(self._cov), C.c_int(self.d_action), C.c_double(self.beta),
                                                _lib.ptr(self._init_cov_d), _lib.stream_ptr()))
 
     def _calc_val(self, trajectories):
         """cem.py:107-112: mean cost-to-go."""
-        costs, _ = self._traj(trajectories)
+        costs, actions = self._traj(trajectories)
+        if self.batch_size > 1:
+            return self._batched_update(costs, actions, apply=False).cpu().numpy()
         s = self.shard.all_gather(self._ctg0(costs).sum().reshape(1)).sum()
         return float(s.item()) / self.num_particles

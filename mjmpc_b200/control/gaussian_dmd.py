@@ -40,7 +40,30 @@ class DMDMPC(OLGaussianMPC):
     def _update_distribution(self, trajectories):
         """gaussian_dmd.py:65-91."""
         costs, actions = self._traj(trajectories)
+        if self.batch_size > 1:
+            self._batched_update(costs, actions, apply=True)
+            return
         self._softmax_update(costs, actions, self.lam, cov_mode=self._cov_mode())
+
+    def _batched_update(self, costs, actions, apply):
+        """batch_size independent instances with a fixed covariance: the exponential-utility weighted mean is
+        MPPI's without the control cost (gaussian_dmd.py:94-104 == mppi.py:84-97 at alpha = 1), one thread block per
+        instance (mjb_mppi_update_batched)."""
+        if self.update_cov:
+            raise NotImplementedError("batched DMD-MPC instances are implemented for update_cov=False")
+        a = _lib.MppiBatchedArgs()
+        a.n_ctrl, a.K, a.H, a.d = self.batch_size, self.num_particles, self.horizon, self.d_action
+        a.costs = costs.data_ptr(); a.costs_sk, a.costs_st = costs.stride()
+        a.actions = actions.data_ptr(); a.act_sk, a.act_st, a.act_sj = actions.stride()
+        mean = self._mean if apply else self._mean.clone()
+        a.mean, a.cov = mean.data_ptr(), self._cov.data_ptr()
+        g = np.ascontiguousarray(self.gamma_seq.reshape(-1))
+        a.gamma_seq = g.ctypes.data
+        a.lam, a.step_size, a.control_cost = float(self.lam), float(self.step_size), 0
+        value = self._buf("batched_value", (self.batch_size,))
+        a.value = value.data_ptr()
+        _lib.check(_lib.lib().mjb_mppi_update_batched(C.byref(a), _lib.stream_ptr()))
+        return value
 
     def _softmax_spec(self):
         return dict(lam=float(self.lam), control_cost=False, time_based=False, cov_mode=self._cov_mode(),
@@ -56,5 +79,7 @@ class DMDMPC(OLGaussianMPC):
     def _calc_val(self, trajectories):
         """gaussian_dmd.py:126-139."""
         costs, actions = self._traj(trajectories)
+        if self.batch_size > 1:
+            return self._batched_update(costs, actions, apply=False).cpu().numpy()
         stats = self._softmax_update(costs, actions, self.lam, apply=False)
         return float(stats[0].item())

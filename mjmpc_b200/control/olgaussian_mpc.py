@@ -66,8 +66,8 @@ class OLGaussianMPC(Controller):
         # kernel).  Under CUDA-graph replay two graphs alternate (read tensor A / write B, read B / write A).
         self.overlap_noise = True
         self._mean = self._mean_from(self.init_mean)
-        self._cov = self._to_device(np.diag(self.init_cov)).contiguous()
         self._init_cov_d = self._to_device(self.init_cov)
+        self._cov = self._cov_from_init()
         self._buffers = {}
         self._noise_step = None       # device step counter while a CUDA graph is active
 
@@ -100,7 +100,9 @@ class OLGaussianMPC(Controller):
     @cov_action.setter
     def cov_action(self, value):
         self.disable_cuda_graph()
-        self._cov = self._to_device(value).reshape(self.d_action, self.d_action).contiguous()
+        v = self._to_device(value)
+        shape = (self.batch_size, self.d_action, self.d_action) if self._cov.dim() == 3 else (self.d_action, self.d_action)
+        self._cov = v.expand(shape).contiguous().clone() if v.dim() < len(shape) else v.reshape(shape).contiguous()
 
     # ---- sharding ----------------------------------------------------------------------------------
     def set_instance_offset(self, first_instance: int):
@@ -113,6 +115,17 @@ class OLGaussianMPC(Controller):
     @property
     def local_particles(self):
         return self.shard.local_range(self.num_particles)[1] * self.batch_size
+
+    # batched instances of a controller that ADAPTS its covariance (CEM) keep one covariance per instance
+    _per_instance_cov = False
+
+    def _cov_from_init(self):
+        c = self._to_device(np.diag(self.init_cov)).contiguous()
+        if self._per_instance_cov and self.batch_size > 1:
+            if self.num_particles % 32 != 0:
+                raise ValueError("batched instances with their own covariance need num_particles in multiples of 32")
+            c = c.reshape(1, self.d_action, self.d_action).repeat(self.batch_size, 1, 1).contiguous()
+        return c
 
     def _buf(self, name, shape, dtype=torch.float64, zero=False):
         key = (name, tuple(shape), dtype)
@@ -147,7 +160,8 @@ class OLGaussianMPC(Controller):
             self._cov, self.filter_coeffs, (kl, self.horizon), self.seed_val,
             step=self._noise_step if self._noise_step is not None else self.num_steps,
             k_offset=k0, K_global=self._particle_id_offset + self.num_particles * self.batch_size,
-            zero_last=self.use_zero_control_seq, mean=self._mean)
+            zero_last=self.use_zero_control_seq, mean=self._mean,
+            particles_per_cov=self.num_particles if self._cov.dim() == 3 else 0)
 
     def sample_noise(self):
         spec = self.noise_spec()
@@ -192,7 +206,7 @@ class OLGaussianMPC(Controller):
         self.disable_cuda_graph()
         self.num_steps = 0
         self._mean = self._mean_from(np.zeros((self.horizon, self.d_action)))
-        self._cov = self._to_device(np.diag(self.init_cov)).contiguous()
+        self._cov = self._cov_from_init()
         self.gamma_seq = np.cumprod([1.0] + [self.gamma] * (self.horizon - 1)).reshape(1, self.horizon)
         self._buffers = {}
         self.__dict__.pop("_fused_blocks", None)

@@ -27,6 +27,9 @@ class RandomShooting(OLGaussianMPC):
         """random_shooting.py:52-62: mean <- (1-step)*mean + step*actions[argmin cost-to-go]."""
         L = _lib.lib()
         costs, actions = self._traj(trajectories)
+        if self.batch_size > 1:
+            self._batched_update(costs, actions, apply=True)
+            return
         k0, kl = self.shard.local_range(self.num_particles)
         H, d = self.horizon, self.d_action
         ctg0 = self._ctg0(costs).contiguous()
@@ -56,8 +59,29 @@ class RandomShooting(OLGaussianMPC):
                                     _lib.c_ll(0), C.c_int(self.shard.world_size), C.c_int(H), C.c_int(d),
                                     C.c_double(self.step_size), _lib.ptr(self._mean), _lib.stream_ptr()))
 
+    def _batched_update(self, costs, actions, apply):
+        """batch_size independent instances: one thread block per instance (argmin + blend), no reduction across
+        instances; best_id holds one index per instance (within the instance's particle block)."""
+        a = _lib.InstancesArgs()
+        a.n_ctrl, a.K, a.H, a.d = self.batch_size, self.num_particles, self.horizon, self.d_action
+        a.mode, a.apply = _lib.INST_RS, int(apply)
+        a.costs = costs.data_ptr(); a.costs_sk, a.costs_st = costs.stride()
+        a.actions = actions.data_ptr(); a.act_sk, a.act_st, a.act_sj = actions.stride()
+        a.mean = self._mean.data_ptr()
+        g = np.ascontiguousarray(self.gamma_seq.reshape(-1))
+        a.gamma_seq = g.ctypes.data
+        a.step_size = float(self.step_size)
+        ids = self._buf("rs_ids_b", (self.batch_size,), torch.int64)
+        value = self._buf("batched_value", (self.batch_size,))
+        a.ids, a.value = ids.data_ptr(), value.data_ptr()
+        _lib.check(_lib.lib().mjb_instances_update_batched(C.byref(a), _lib.stream_ptr()))
+        self.best_id = ids
+        return value
+
     def _calc_val(self, trajectories):
         """random_shooting.py:65-69."""
-        costs, _ = self._traj(trajectories)
+        costs, actions = self._traj(trajectories)
+        if self.batch_size > 1:
+            return self._batched_update(costs, actions, apply=False).cpu().numpy()
         s = self.shard.all_gather(self._ctg0(costs).sum().reshape(1)).sum()
         return float(s.item()) / self.num_particles

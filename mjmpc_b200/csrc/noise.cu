@@ -31,8 +31,10 @@ template <int D>
 __global__ void __launch_bounds__(MJB_NZ_THREADS) noise_kernel(mjb_noise_args a) {
     __shared__ double L[MJB_MAXD][MJB_MAXD];
     __shared__ double sh[MJB_NZ_TT][D][MJB_NZ_KP];      // shaped normals (L z) of the pass
-    if (threadIdx.x == 0) noise_chol<D>(a.cov, L);      // ~2 us of dependent sqrt / divide: once per (persistent) block
-    __syncthreads();
+    if (a.cov_stride == 0) {
+        if (threadIdx.x == 0) noise_chol<D>(a.cov, L);  // ~2 us of dependent sqrt / divide: once per (persistent) block
+        __syncthreads();
+    }
     Philox ph{(unsigned)a.seed, (unsigned)(a.seed >> 32)};
     // counter = (global particle, step counter, t, stream id << 8 | pair index); key = seed
     const unsigned step_ctr = (a.step_ptr ? (unsigned)(*a.step_ptr) : 0u) + (unsigned)a.offset;
@@ -42,6 +44,11 @@ __global__ void __launch_bounds__(MJB_NZ_THREADS) noise_kernel(mjb_noise_args a)
     const long long ntiles = (a.K + MJB_NZ_KP - 1) / MJB_NZ_KP;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long kb = tile * MJB_NZ_KP;
+    if (a.cov_stride != 0) {                            // batched instances with their own covariance: one factor per tile
+        __syncthreads();
+        if (threadIdx.x == 0) noise_chol<D>(a.cov + ((a.k_offset + kb) / a.particles_per_cov) * a.cov_stride, L);
+        __syncthreads();
+    }
     const long long k2 = kb + kl2;
     const bool act2 = j2 < D && k2 < a.K;
     const bool zero_seq = a.zero_last && (a.k_offset + k2) == a.K_global - 1;
@@ -93,6 +100,8 @@ extern "C" int mjb_generate_noise(const mjb_noise_args* a, void* stream) {
     MJB_REQUIRE(a->K >= 0 && a->H >= 1, "mjb_generate_noise: bad shape K=%d H=%d", a->K, a->H);
     MJB_REQUIRE(a->d >= 1 && a->d <= MJB_MAXD, "mjb_generate_noise: d=%d not in 1..%d", a->d, MJB_MAXD);
     MJB_REQUIRE(!a->zero_last || a->neg_mean, "mjb_generate_noise: zero_last needs the mean sequence");
+    MJB_REQUIRE(a->cov_stride == 0 || (a->particles_per_cov >= 32 && a->particles_per_cov % 32 == 0 && a->k_offset % 32 == 0),
+                "mjb_generate_noise: per-instance covariances need particles_per_cov (and k_offset) in multiples of 32");
     if (a->K == 0) return MJB_OK;
     // persistent blocks striding over the 32-particle tiles: 4 resident blocks per SM's worth at most
     static int sms = 0;

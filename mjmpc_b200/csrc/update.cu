@@ -929,6 +929,142 @@ __global__ void blend_best_kernel(const double* __restrict__ actions, long long 
         mean[i] = (1.0 - step) * mean[i] + step * actions[b * sk + (i / d) * st + (i % d) * sj];
 }
 
+// ------------------------------------------------------------------------------ batched RandomShooting / CEM instances
+// one block of 256 threads per instance; dynamic shared memory: K cost-to-go values + K flags
+__global__ void __launch_bounds__(256) instances_batched_kernel(mjb_instances_args a, GammaSeq G) {
+    extern __shared__ double sh[];
+    __shared__ unsigned hist[256];
+    __shared__ unsigned long long s_prefix, s_want;
+    __shared__ long long s_scan[256];
+    __shared__ double red[256], mu[MJB_MAXD];
+    __shared__ long long redi[256];
+    const int c = blockIdx.x, K = a.K, H = a.H, D = a.d, tid = threadIdx.x, nt = blockDim.x;
+    unsigned char* flag = (unsigned char*)(sh + K);
+    double* mean = a.mean + (long long)c * H * D;
+    const long long kbase = (long long)c * K;
+    // cost-to-go at t = 0 in the reference's operation order
+    double vsum = 0.0;
+    for (int k = tid; k < K; k += nt) {
+        double S = 0.0, ctg = 0.0;
+        for (int t = H - 1; t >= 0; t--) {
+            const double cst = a.costs[(kbase + k) * a.costs_sk + t * a.costs_st];
+            if (G.raw) ctg = cst;
+            else { S = __dadd_rn(S, __dmul_rn(G.g[t], cst)); ctg = __ddiv_rn(S, G.g[t]); }
+        }
+        sh[k] = ctg;
+        vsum += ctg;
+    }
+    red[tid] = vsum;
+    __syncthreads();
+    for (int s2 = nt / 2; s2 > 0; s2 >>= 1) { if (tid < s2) red[tid] += red[tid + s2]; __syncthreads(); }
+    if (a.value && tid == 0) a.value[c] = red[0] / (double)K;
+    __syncthreads();
+    if (a.mode == MJB_INST_RS) {
+        // argmin, first occurrence
+        unsigned long long bk = ~0ull; long long bi = -1;
+        for (int k = tid; k < K; k += nt) { const unsigned long long key = enc_key(sh[k]); if (key < bk) { bk = key; bi = k; } }
+        ((unsigned long long*)red)[tid] = bk; redi[tid] = bi;
+        __syncthreads();
+        for (int s2 = nt / 2; s2 > 0; s2 >>= 1) {
+            if (tid < s2) {
+                const unsigned long long ok = ((unsigned long long*)red)[tid + s2]; const long long oi = redi[tid + s2];
+                const unsigned long long mk = ((unsigned long long*)red)[tid];
+                if (oi >= 0 && (ok < mk || (ok == mk && (redi[tid] < 0 || oi < redi[tid])))) { ((unsigned long long*)red)[tid] = ok; redi[tid] = oi; }
+            }
+            __syncthreads();
+        }
+        const long long best = redi[0];
+        if (a.ids && tid == 0) a.ids[c] = best;
+        if (a.apply)
+            for (int i = tid; i < H * D; i += nt)
+                mean[i] = (1.0 - a.step_size) * mean[i] + a.step_size * a.actions[(kbase + best) * a.act_sk + (i / D) * a.act_st + (i % D) * a.act_sj];
+        return;
+    }
+    // ---- CEM: radix select of the num_elite smallest keys, ties to the lower index
+    if (tid == 0) { s_prefix = 0; s_want = (unsigned long long)a.num_elite; }
+    __syncthreads();
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        hist[tid] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix, himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        for (int k = tid; k < K; k += nt) {
+            const unsigned long long key = enc_key(sh[k]);
+            if ((key & himask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long want = s_want, cum = 0;
+            int b = 0;
+            for (; b < 256; b++) { if (cum + hist[b] >= want) break; cum += hist[b]; }
+            s_want = want - cum;
+            s_prefix = prefix | ((unsigned long long)b << shift);
+        }
+        __syncthreads();
+    }
+    const unsigned long long thr = s_prefix;
+    const long long need_eq = (long long)s_want;
+    const int per = (K + nt - 1) / nt, lo = tid * per < K ? tid * per : K, hi = lo + per < K ? lo + per : K;
+    long long neq = 0;
+    for (int k = lo; k < hi; k++) neq += enc_key(sh[k]) == thr;
+    s_scan[tid] = neq;
+    __syncthreads();
+    if (tid == 0) { long long cc = 0; for (int i = 0; i < nt; i++) { const long long x = s_scan[i]; s_scan[i] = cc; cc += x; } }
+    __syncthreads();
+    long long eq_before = s_scan[tid], nel = 0;
+    __syncthreads();
+    for (int k = lo; k < hi; k++) {
+        const unsigned long long key = enc_key(sh[k]);
+        bool e = key < thr;
+        if (key == thr) { e = eq_before < need_eq; eq_before++; }
+        flag[k] = e ? 1 : 0;
+        nel += e;
+    }
+    s_scan[tid] = nel;
+    __syncthreads();
+    if (tid == 0) { long long cc = 0; for (int i = 0; i < nt; i++) { const long long x = s_scan[i]; s_scan[i] = cc; cc += x; } }
+    __syncthreads();
+    if (a.ids) { long long o = s_scan[tid]; for (int k = lo; k < hi; k++) if (flag[k]) a.ids[(long long)c * a.num_elite + o++] = k; }
+    if (!a.apply) return;
+    const double E = (double)a.num_elite, n = E * (double)H;
+    // pooled mean of the elite deltas (delta = action - old mean), per dimension, particles in index order
+    if (tid < D) {
+        double s2 = 0.0;
+        for (int k = 0; k < K; k++) if (flag[k])
+            for (int t = 0; t < H; t++) s2 += a.actions[(kbase + k) * a.act_sk + t * a.act_st + tid * a.act_sj] - mean[t * D + tid];
+        mu[tid] = s2 / n;
+    }
+    __syncthreads();
+    // covariance update: np.var (ddof 0) on the diagonal, or np.cov (ddof 1) in full
+    double* cov = a.cov + (long long)c * D * D;
+    for (int i = tid; i < D * D; i += nt) {
+        const int r = i / D, q = i % D;
+        double upd = 0.0;
+        if (a.mode == MJB_INST_CEM_FULL || r == q) {
+            double s2 = 0.0;
+            for (int k = 0; k < K; k++) if (flag[k])
+                for (int t = 0; t < H; t++) {
+                    const double dr = a.actions[(kbase + k) * a.act_sk + t * a.act_st + r * a.act_sj] - mean[t * D + r] - mu[r];
+                    const double dq = a.actions[(kbase + k) * a.act_sk + t * a.act_st + q * a.act_sj] - mean[t * D + q] - mu[q];
+                    s2 += dr * dq;
+                }
+            upd = a.mode == MJB_INST_CEM_FULL ? s2 / (n - 1.0) : s2 / n;
+        }
+        cov[i] = (1.0 - a.step_size) * cov[i] + a.step_size * upd;
+    }
+    __syncthreads();                                     // every delta above used the OLD mean
+    for (int i = tid; i < H * D; i += nt) {
+        const int t = i / D, j = i % D;
+        double s2 = 0.0;
+        for (int k = 0; k < K; k++) if (flag[k]) s2 += a.actions[(kbase + k) * a.act_sk + t * a.act_st + j * a.act_sj];
+        mean[i] = (1.0 - a.step_size) * mean[i] + a.step_size * (s2 / E);
+    }
+}
+__global__ void cov_add_diag_batched_kernel(double* cov, int n, int d, double beta, const double* v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * d) { const int c = i / d, j = i % d; cov[(long long)c * d * d + j * d + j] += beta * (v ? v[j] : 1.0); }
+}
+
 // ------------------------------------------------------------------------------ PFMPC resampling
 __global__ void __launch_bounds__(256) seq_cumsum_kernel(const double* __restrict__ w, long long M, double* __restrict__ cs) {
     __shared__ double tile[2048];
@@ -1590,6 +1726,33 @@ extern "C" int mjb_softmax_exchange_combine(const mjb_combine_args* a, const dou
     MJB_REQUIRE(rank >= 0 && rank < a->n_shards && seq >= 1, "mjb_softmax_exchange_combine: bad rank / sequence number");
     const int P = mjb_softmax_partial_doubles(a->H, a->d, a->time_based, a->cov_mode);
     softmax_exchange_combine_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*a, local_partial, P, peer_bufs_dev, rank, seq);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_instances_update_batched(const mjb_instances_args* a, void* stream) {
+    MJB_REQUIRE(a && a->costs && a->actions && a->gamma_seq, "mjb_instances_update_batched: null pointer");
+    MJB_REQUIRE(!a->apply || a->mean, "mjb_instances_update_batched: apply needs the mean");
+    MJB_REQUIRE(a->n_ctrl >= 1 && a->K >= 1 && a->K <= 4096 && a->H >= 1, "mjb_instances_update_batched: bad shape (K <= 4096)");
+    MJB_REQUIRE(a->d >= 1 && a->d <= MJB_MAXD, "d_action=%d not in 1..%d", a->d, MJB_MAXD);
+    MJB_REQUIRE(a->mode == MJB_INST_RS || a->mode == MJB_INST_CEM_DIAG || a->mode == MJB_INST_CEM_FULL, "mjb_instances_update_batched: unknown mode %d", a->mode);
+    if (a->mode != MJB_INST_RS) {
+        MJB_REQUIRE(a->num_elite >= 1 && a->num_elite <= a->K, "num_elite=%lld must be in 1..K=%d", a->num_elite, a->K);
+        MJB_REQUIRE(!a->apply || a->cov, "mjb_instances_update_batched: CEM needs the covariances");
+        MJB_REQUIRE(a->mode != MJB_INST_CEM_FULL || a->num_elite * a->H >= 2, "np.cov needs at least two elite samples");
+    }
+    GammaSeq G;
+    int rc = load_gamma(G, a->gamma_seq, a->H);
+    if (rc) return rc;
+    const size_t smem = sizeof(double) * a->K + (size_t)a->K + 8;
+    instances_batched_kernel<<<a->n_ctrl, 256, smem, (cudaStream_t)stream>>>(*a, G);
+    MJB_CUDA(cudaGetLastError());
+    return MJB_OK;
+}
+
+extern "C" int mjb_cov_add_diag_batched(double* cov, int n, int d, double beta, const double* v, void* stream) {
+    MJB_REQUIRE(cov && n >= 1 && d >= 1 && d <= MJB_MAXD, "mjb_cov_add_diag_batched: bad argument");
+    cov_add_diag_batched_kernel<<<(n * d + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cov, n, d, beta, v);
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;
 }

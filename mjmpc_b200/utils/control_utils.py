@@ -24,7 +24,8 @@ class NoiseSpec:
     place of the ``noise`` argument; ``materialize()`` produces the tensor it stands for."""
 
     def __init__(self, cov, filter_coeffs, shape, base_seed, step=0, stream_id=0, k_offset=0, K_global=None,
-                 zero_last=False, mean=None):
+                 zero_last=False, mean=None, particles_per_cov=0):
+        self.particles_per_cov = int(particles_per_cov)      # cov is (n_instances, d, d): particles per instance
         self.cov, self.filter_coeffs, self.shape = cov, [float(b) for b in filter_coeffs], tuple(shape)
         self.base_seed, self.step, self.stream_id = int(base_seed), step, int(stream_id)
         self.k_offset = int(k_offset)
@@ -35,7 +36,7 @@ class NoiseSpec:
         return generate_noise(self.cov, self.filter_coeffs, self.shape, self.base_seed, step=self.step,
                               stream_id=self.stream_id, k_offset=self.k_offset, K_global=self.K_global,
                               zero_last_mean=self.mean if self.zero_last else None, out=out,
-                              device=self.cov.device)
+                              device=self.cov.device, particles_per_cov=self.particles_per_cov)
 
     def fill(self, a):
         """Write the fused-noise fields of a ``RolloutArgs``."""
@@ -64,7 +65,7 @@ def particle_minor(K, H, d, device):
 
 
 def generate_noise(cov, filter_coeffs, shape, base_seed, *, step=0, stream_id=NOISE_STREAM_ROLLOUT,
-                   k_offset=0, K_global=None, zero_last_mean=None, out=None, device="cuda"):
+                   k_offset=0, K_global=None, zero_last_mean=None, out=None, device="cuda", particles_per_cov=0):
     """Correlated noise samples eps (K,H,d): N(0,cov) draws filtered along the horizon by
     eps[:,i] = b0*eps[:,i] + b1*eps[:,i-1] + b2*eps[:,i-2], i >= 2 (control_utils.py:24-34).
 
@@ -73,22 +74,25 @@ def generate_noise(cov, filter_coeffs, shape, base_seed, *, step=0, stream_id=NO
     one MPC step do in the reference).  ``k_offset``/``K_global`` place a shard inside the
     global particle range; ``zero_last_mean`` applies olgaussian_mpc.py:110-111."""
     a, keep = noise_args(cov, filter_coeffs, shape, base_seed, step=step, stream_id=stream_id, k_offset=k_offset,
-                         K_global=K_global, zero_last_mean=zero_last_mean, out=out, device=device)
+                         K_global=K_global, zero_last_mean=zero_last_mean, out=out, device=device,
+                         particles_per_cov=particles_per_cov)
     _lib.check(_lib.lib().mjb_generate_noise(C.byref(a), _lib.stream_ptr()))
     return keep["out"]
 
 
 def noise_args(cov, filter_coeffs, shape, base_seed, *, step=0, stream_id=NOISE_STREAM_ROLLOUT, k_offset=0,
-               K_global=None, zero_last_mean=None, out=None, device="cuda"):
+               K_global=None, zero_last_mean=None, out=None, device="cuda", particles_per_cov=0):
     """The ``mjb_noise_args`` block :func:`generate_noise` launches with, and the tensors it points into
     (``keep``: hold on to it for as long as the block is used)."""
     K, H = int(shape[0]), int(shape[1])
     cov = _dev(cov, device).contiguous()
-    d = cov.shape[0]
+    d = cov.shape[-1]
     if out is None:
         out = particle_minor(K, H, d, cov.device)
     a = _lib.NoiseArgs()
     a.K, a.H, a.d = K, H, d
+    if cov.dim() == 3:                      # (n_instances, d, d): batched controller instances with their own covariance
+        a.cov_stride, a.particles_per_cov = d * d, int(particles_per_cov)
     a.k_offset = int(k_offset)
     a.K_global = int(K_global if K_global is not None else k_offset + K)
     a.seed = int(base_seed) & 0xFFFFFFFFFFFFFFFF

@@ -638,3 +638,52 @@ def test_graph_replay_mixed_with_eager_calls_and_a_plant_model(compiled_model):
             plant.close()
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("name", ["rs", "dmd", "cem_full", "cem_diag"])
+def test_batched_rs_dmd_cem_instances_match_single_controllers(compiled_model, name):
+    """batch_size independent RandomShooting / DMD-MPC (fixed covariance) / CEM instances in lock step -- one rollout
+    launch, one thread block per instance for the update, CEM with one covariance per instance -- against separate
+    single-instance controllers fed the same Philox block, start state and randomised model (the sweeps of
+    examples/job_script.py:186-217 in miniature)."""
+    import torch
+    from conftest import synthetic_state
+    from mjmpc_b200.control import CEM, DMDMPC, RandomShooting
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    B, K, H = 6, 64, 10
+    kw = dict(horizon=H, num_particles=K, gamma=0.98, n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=31, **_common())
+    mk = {"rs": lambda **b: RandomShooting(init_cov=1.0, base_action='null', step_size=0.7, **kw, **b),
+          "dmd": lambda **b: DMDMPC(init_cov=0.5, beta=0.1, base_action='repeat', lam=0.2, step_size=0.8, update_cov=False, **kw, **b),
+          "cem_full": lambda **b: CEM(init_cov=1.0, base_action='null', elite_frac=0.25, step_size=0.8, beta=0.1, cov_type='full', **kw, **b),
+          "cem_diag": lambda **b: CEM(init_cov=1.0, base_action='repeat', elite_frac=0.1, step_size=0.6, beta=0.05, cov_type='diagonal', **kw, **b)}[name]
+    states = [[synthetic_state(compiled_model, 200 * s + b) for b in range(B)] for s in range(3)]
+    env = GpuReacherVecEnv(compiled_model, n_workers=B)
+    env.randomize_dynamics(dict(body_mass={"r_forearm_link": [0.3, 0.0]}, dof_damping={"r_elbow_flex_joint": [0.2, 0.1]}), base_seed=5)
+    cb = mk(batch_size=B)
+    cb.set_sim_state_fn, cb.rollout_fn = env.set_env_state, env.rollout_fn
+    acts_b = np.stack([cb.optimize(st)[0] for st in states])
+    assert acts_b.shape == (3, B, 7)
+    ids_b = (cb.elite_ids if name.startswith("cem") else cb.best_id if name == "rs" else torch.zeros(B)).cpu().numpy().copy()
+    mean_b, cov_b = cb.mean_action.copy(), cb.cov_action.copy()
+    vals = cb._calc_val(cb.generate_rollouts(states[0]))          # statistics only: the distribution stays as it is
+    assert vals.shape == (B,) and np.all(np.isfinite(vals))
+    np.testing.assert_array_equal(cb.mean_action, mean_b)
+    np.testing.assert_array_equal(cb.cov_action, cov_b)
+    if name.startswith("cem"):
+        assert cb.cov_action.shape == (B, 7, 7)
+    for b in (0, 3, B - 1):
+        single_env = GpuReacherVecEnv(env._worker_models[b], n_workers=1)
+        c = mk(batch_size=1)
+        c._particle_id_offset = b * K
+        c.set_sim_state_fn, c.rollout_fn = single_env.set_env_state, single_env.rollout_fn
+        acts = np.stack([c.optimize(st[b])[0] for st in states])
+        np.testing.assert_allclose(acts_b[:, b], acts, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(cb.mean_action[b], c.mean_action, rtol=1e-9, atol=1e-12)
+        if name.startswith("cem"):
+            np.testing.assert_allclose(cb.cov_action[b], c.cov_action, rtol=1e-9, atol=1e-13)
+            np.testing.assert_array_equal(ids_b[b], c.elite_ids.cpu().numpy())
+        if name == "rs":
+            assert int(ids_b[b]) == int(c.best_id.item())
+        single_env.close()
+    assert np.abs(acts_b[:, 0] - acts_b[:, 1]).max() > 1e-3
+    env.close()
