@@ -23,33 +23,55 @@ compiled = compile_model(reacher7dof_spec())
 R7 = dict(d_state=25, d_obs=20, d_action=7, action_lows=-np.ones(7), action_highs=np.ones(7))
 
 
+WORLD, RANK, LOCAL = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+if WORLD > 1:
+    # torchrun: the full-size lines with the particles sharded over the ranks (device time, max over ranks)
+    import torch.distributed as dist
+    torch.cuda.set_device(LOCAL)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
+
+
 def timed(ctrl, states, steps=200, warmup=10, graph=True, set_state=None):
     if graph:
         ctrl.enable_cuda_graph(states[0])
     for i in range(warmup):
         ctrl.step_device(states[i % len(states)])
     torch.cuda.synchronize()
+    if WORLD > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
         ctrl.step_device(states[(warmup + i) % len(states)])
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps
+    ms = e0.elapsed_time(e1) / steps
+    if WORLD > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
 
 def emit(name, ms, K, H, n_ctrl=1, **kw):
+    if RANK != 0:
+        return
+    kw.setdefault("n_gpus", WORLD)
     print(json.dumps(dict(config=name, ms_per_step=ms, mpc_hz=1e3 / ms * n_ctrl, particle_steps_per_s=K * H * n_ctrl / (ms * 1e-3),
                           num_particles=K, horizon=H, instances=n_ctrl, **kw)), flush=True)
 
 
 states = synthetic_states(compiled, 16, seed=1)
 ONLY = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else ""
+if WORLD > 1:
+    ONLY = "fullsize"
 if ONLY in ("", "fullsize"):
     # the other controllers at the north-star size K=65536, H=32: one GPU, eager + graph
     from mjmpc_b200.control import RandomShooting
     K, H = 65536, 32
-    kw = dict(horizon=H, num_particles=K, gamma=1.0, n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=123, **R7)
+    from mjmpc_b200.utils.shard import ShardContext
+    kw = dict(horizon=H, num_particles=K, gamma=1.0, n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=123,
+              shard=ShardContext(RANK, WORLD), device=LOCAL, **R7)
     mk = {
         "MPPI": lambda: MPPI(init_cov=1.0, base_action='null', lam=0.2, step_size=1.0, alpha=1, **kw),
         "CEM full-cov": lambda: CEM(init_cov=1.0, base_action='null', elite_frac=0.2, step_size=1.0, beta=0.0, cov_type='full', **kw),
@@ -58,14 +80,16 @@ if ONLY in ("", "fullsize"):
         "PFMPC": lambda: PFMPC(cov_shift=0.05, cov_resample=1.0, base_action='null', lam=0.2, **kw),
         "DMD-MPC diag-cov": lambda: DMDMPC(init_cov=0.1, beta=0.3, base_action='null', lam=0.2, step_size=1.0, update_cov=True,
                                            cov_type='diagonal', **kw),
+        "DMD-MPC full-cov": lambda: DMDMPC(init_cov=0.1, beta=0.3, base_action='null', lam=0.2, step_size=1.0, update_cov=True,
+                                           cov_type='full', **kw),
     }
     for name, f in mk.items():
-        env = GpuReacherVecEnv(compiled)
+        env = GpuReacherVecEnv(compiled, device=LOCAL)
         c = f()
         c.set_sim_state_fn, c.rollout_fn = env.set_env_state, env.rollout_fn
         for graph in (False, True):
-            if graph and name == "PFMPC":
-                continue                                 # r comes from Python's random module every step: eager only
+            if graph and (name == "PFMPC" or WORLD > 1):
+                continue                                 # PFMPC: r comes from Python's random module every step; sharded steps launch eagerly
             try:
                 ms = timed(c, states, steps=60, warmup=5, graph=graph)
                 emit("fullsize %s K=65536 H=32 (%s)" % (name, "cuda graph" if graph else "eager"), ms, K, H)
@@ -74,6 +98,9 @@ if ONLY in ("", "fullsize"):
         env.close()
         del c, env
         torch.cuda.empty_cache()
+    if WORLD > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if ONLY:
         sys.exit(0)
 # configs[0]
