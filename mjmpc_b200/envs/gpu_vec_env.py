@@ -265,6 +265,32 @@ class GpuReacherVecEnv:
         info = [{"total_time": time.time() - start_t}] * self.n_workers
         return obs, np.ascontiguousarray(rew), act, done, info, nobs
 
+    def rollout_cl(self, policy, batch_size, horizon, mode='mean', noise=None):
+        """The reference's closed-loop rollout (gym_env_wrapper.py:255-325) for LINEAR(-Gaussian) policies: ``policy``
+        exposes its (d_obs + 1, 7) weight matrix as ``policy.weights`` (numpy or tensor; last row = bias) and the
+        whole batch runs inside the rollout kernel, ``u_t = W' [obs_t; 1] (+ noise[b, t])``.  Returns the reference's
+        7-tuple ``(obs, act, act_infos, rew, done, next_obs, info)`` as numpy arrays.  Policies that are general torch
+        modules (the reference's NN controllers) are outside the sampling-MPC path and raise."""
+        W = getattr(policy, "weights", None)
+        if W is None:
+            raise NotImplementedError("rollout_cl on the GPU evaluates linear policies (policy.weights); general torch "
+                                      "policies are outside the sampling-MPC path")
+        if mode not in ("mean", "sample"):
+            raise ValueError("mode must be 'mean' or 'sample'")
+        start_t = time.time()
+        W = self._to_device(W).reshape(_lib.OBS_DIM + 1, 7)
+        if noise is None:
+            noise = torch.zeros((batch_size, horizon, 7), dtype=torch.float64, device=self.device)
+        out = self.rollout_device(batch_size, horizon, W, self._to_device(noise), want_obs=True, closed_loop=True)
+        nobs = out["next_observations"].cpu().numpy()
+        obs = np.empty_like(nobs)
+        obs[:, 1:] = nobs[:, :-1]
+        obs[:, 0] = self._first_obs(batch_size)
+        act = np.ascontiguousarray(out["actions"].cpu().numpy())
+        rew = -np.ascontiguousarray(out["costs"].cpu().numpy())
+        info = {'total_time': time.time() - start_t, 'inference_time': 0.0}
+        return obs, act, [], rew, np.zeros((batch_size, horizon)), nobs, info
+
     def _first_obs(self, K):
         # observation at the set state: forward kinematics on the host (FK only, no dynamics)
         from .model import forward_kinematics
@@ -282,10 +308,16 @@ class GpuReacherVecEnv:
             if mode not in ("open_loop", "closed_loop_linear"):
                 raise NotImplementedError("mode %r does not run on the GPU rollout" % (mode,))
             host = not isinstance(noise, (torch.Tensor, NoiseSpec)) and not isinstance(mean, torch.Tensor)
+            closed = mode == "closed_loop_linear"
             out = self.rollout_device(num_particles, horizon, self._to_device(mean), self._to_device(noise),
-                                      want_obs=self.return_observations or host,
-                                      closed_loop=(mode == "closed_loop_linear"))
+                                      want_obs=self.return_observations or host or closed, closed_loop=closed)
             if not host:
+                if closed:
+                    # closed-loop controllers read the observation the policy saw first (clgaussian_mpc.py:105):
+                    # observations[:, t] = observation before step t, as in the reference's dict
+                    nobs = out["next_observations"]
+                    first = torch.from_numpy(self._first_obs(nobs.shape[0])).to(nobs.device)
+                    out["observations"] = torch.cat([first[:, None, :], nobs[:, :-1]], dim=1)
                 return out
             # unmodified reference controllers: numpy in, numpy out, reference dict keys
             nobs = out["next_observations"].cpu().numpy()

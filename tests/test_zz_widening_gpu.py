@@ -255,3 +255,66 @@ def test_example_driver_runs_the_pendulum_config():
                         "--n_episodes", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     assert "Avg. reward" in r.stdout
+
+
+def test_clgaussian_mpc_subclass_and_rollout_cl():
+    """the reference's CLGaussianMPC surface (clgaussian_mpc.py:10-145) on the in-kernel linear
+    policy, through a minimal subclass that supplies the missing update rule (a cost-weighted average of per-particle
+    bias perturbations -- just enough to exercise optimize()), and GymEnvWrapper.rollout_cl's 7-tuple
+    (gym_env_wrapper.py:255-325) for a linear policy, both against the CPU oracle's closed-loop restatement."""
+    import torch
+    from conftest import synthetic_state
+    from mjmpc_b200.control import CLGaussianMPC
+    from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv
+    from mjmpc_b200.envs.model import compile_model, reacher7dof_spec
+    from oracle import mjstep
+    cm = compile_model(reacher7dof_spec())
+    om = mjstep.OracleModel(cm.tree)
+    env = GpuReacherVecEnv(cm)
+    K, H = 128, 8
+    W0 = _linear_policy(2)
+
+    class BiasCL(CLGaussianMPC):
+        def _update_distribution(self, traj):
+            costs = traj["costs"].sum(dim=1)
+            w = torch.softmax(-(costs - costs.min()) / 0.5, dim=0)
+            delta = (traj["actions"][:, 0] * w[:, None]).sum(0) - traj["actions"][:, 0].mean(0)
+            self._weights[-1] += 0.1 * delta                     # nudge the bias row only
+
+    c = BiasCL(d_state=25, d_obs=20, d_action=7, action_lows=-np.ones(7), action_highs=np.ones(7), horizon=H, init_cov=0.3,
+               init_mean=W0, num_particles=K, gamma=0.99, n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=3)
+    c.set_sim_state_fn, c.rollout_fn = env.set_env_state, env.rollout_fn
+    st = synthetic_state(cm, 6)
+    traj = c.generate_rollouts(st)
+    noise = c.sample_noise().cpu().numpy()
+    ref = mjstep.rollout(om, st["qp"], st["qv"], st["target_pos"], None, np.ascontiguousarray(noise), want_obs=True,
+                         nthreads=4, policy_w=W0)
+    np.testing.assert_allclose(traj["costs"].cpu().numpy(), ref["costs"], rtol=1e-8)
+    np.testing.assert_allclose(traj["actions"].cpu().numpy(), ref["actions"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(traj["observations"][:, 1:].cpu().numpy(), ref["next_observations"][:, :-1], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(c.curr_obs[:14], np.concatenate([st["qp"], st["qv"]]))
+    action, value = c.optimize(st)
+    want = c.mean_weights.T @ np.append(c.curr_obs, 1.0)             # clgaussian_mpc.py:63
+    np.testing.assert_allclose(action, want, rtol=1e-12)
+    assert c.num_steps == 1 and not np.array_equal(c.mean_weights[-1], W0[-1]) and np.array_equal(c.mean_weights[:-1], W0[:-1])
+    with pytest.raises(NotImplementedError):
+        c.get_optimal_value(st)                                     # _calc_val raises, as in the reference
+    c.reset()
+    np.testing.assert_array_equal(c.mean_weights, W0)
+    with pytest.raises(TypeError):
+        CLGaussianMPC(d_state=25, d_obs=20, d_action=7, action_lows=None, action_highs=None, horizon=H, init_cov=0.3,
+                      init_mean=W0, num_particles=K, gamma=0.99, n_iters=1, filter_coeffs=[1, 0, 0])   # abstract, as in the reference
+
+    # rollout_cl: the reference's closed-loop rollout signature for a linear policy
+    class LinearPolicy:
+        weights = W0
+    env.set_env_state(st)
+    obs, act, act_infos, rew, done, next_obs, info = env.rollout_cl(LinearPolicy(), K, H, mode='mean', noise=noise)
+    np.testing.assert_allclose(rew, -ref["costs"], rtol=1e-8)
+    np.testing.assert_allclose(act, ref["actions"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(next_obs, ref["next_observations"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(obs[:, 1:], next_obs[:, :-1])
+    assert obs.shape == (K, H, 20) and done.shape == (K, H) and "total_time" in info
+    with pytest.raises(NotImplementedError):
+        env.rollout_cl(object(), K, H)
+    env.close()
