@@ -222,9 +222,16 @@ class Controller(ABC):
         if blk is not None and "ready" in blk:
             blk["ready"] = None
 
+    def _set_state(self, state):
+        """The reference hands set_sim_state_fn a deep copy (olgaussian_mpc.py:107: a simulator may keep or mutate
+        what it is given).  This package's own backends copy the state into their device buffer and keep nothing:
+        they get the state as it is (a deepcopy of a state dict is ~10 us of every get_action call)."""
+        own = getattr(getattr(self._rollout_fn, "backend", None), "set_env_state", None)
+        self._set_sim_state_fn(state if own is not None and own == self._set_sim_state_fn else copy.deepcopy(state))
+
     def _replay(self, state):
         if state is not None:
-            self._set_sim_state_fn(copy.deepcopy(state))
+            self._set_state(state)
         backend = getattr(self._rollout_fn, "backend", None)
         if backend is not None and getattr(backend, "state_generation", 0) != self._graph_state_gen:
             raise _lib.MjbError("the rollout backend reallocated its state buffer (different number of states) after "

@@ -322,7 +322,7 @@ class OLGaussianMPC(Controller):
         if self.shard.world_size > 1 and px is None:
             return None                 # NCCL all-gather between the two phases: host work inside the step
         if state is not None:
-            self._set_sim_state_fn(copy.deepcopy(state))
+            self._set_state(state)
         overlap = bool(self.overlap_noise) and spec["cov_mode"] == _lib.COV_NONE and not self.use_zero_control_seq
         key = (self._mean.data_ptr(), self._cov.data_ptr(), backend._state.data_ptr(), backend.model.handle.value,
                kl, H, self.n_iters, tuple(sorted(spec.items())), self.step_size, self.base_action, hotstart,
