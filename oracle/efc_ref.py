@@ -8,7 +8,7 @@ and no pre-computed constant with either:
     (``inertiafromgeom``: density 1000, sphere / capsule inertia, parallel axis) -- it does NOT import
     ``mjmpc_b200.envs.model`` / ``mjcf`` and does not take their ``dof_invweight0`` / ``con_invweight`` / ``K`` / ``B``;
   * M(q) comes from geometric Jacobians (sum_b m Jv'Jv + Jw' R I R' Jw + armature), the Coriolis / centrifugal
-    bias from the Christoffel form with dM/dq by torch autograd -- no recursion, no spatial algebra;
+    bias from the Christoffel form with dM/dq by complex-step differentiation -- no recursion, no spatial algebra;
   * qpos0 constants as ``mj_setConst`` documents them: dof_invweight0 = diag(M(qpos0)^-1), body_invweight0
     (translation) = tr(Jcom M0^-1 Jcom')/3;
   * rows as ``mj_instantiateLimit`` / ``mj_instantiateContact`` / ``mj_makeImpedance`` / ``mj_referenceConstraint``

@@ -6,7 +6,9 @@
  * --impl reference legs may load this library, and only as the checker / the timed
  * CPU baseline.  The product path (mjmpc_b200/csrc) never links or calls it.
  *
- * PARITY UNPINNED for the dynamics: the arithmetic of this path lives in MuJoCo 2.0
+ * PARITY UNPINNED AGAINST MuJoCo ITSELF for the dynamics (pinned instead, rows / forces / steps / rollouts, against
+ * the independent second restatement oracle/efc_ref.py: tests/test_efc_pin.py, tests/golden/efc_pin.npz).
+ * The arithmetic of this path lives in MuJoCo 2.0
  * (closed binary, reached through mujoco-py>=2.0,<2.1 and mjrl's MujocoEnv), none of
  * which is under /root/reference or installed here.  The reference ships no golden
  * vectors for it.  This file restates MuJoCo's published algorithm (mj_step for a

@@ -1,6 +1,7 @@
 """ctypes front-end of ``oracle/mjstep.c`` (TEST INFRASTRUCTURE -- see oracle/__init__.py).
 
-PARITY UNPINNED for the MuJoCo dynamics (no MuJoCo binary, no golden vectors in the
+PARITY UNPINNED AGAINST MuJoCo ITSELF (pinned against the independent restatement oracle/efc_ref.py,
+tests/test_efc_pin.py) for the MuJoCo dynamics (no MuJoCo binary, no golden vectors in the
 reference); see the header of mjstep.c.
 """
 from __future__ import annotations
