@@ -24,6 +24,7 @@ def pytest_configure(config):
 # under MJB_TEST_EMU=1 only.  _EMU_SLOW: tests too slow for the default CPU suite (MJB_TEST_EMU_ALL=1 keeps them)
 _EMU_IMPOSSIBLE = {
     "test_cuda_graph_step_equals_eager": "CUDA graphs are not emulated",
+    "test_graph_replay_mixed_with_eager_calls_and_a_plant_model": "CUDA graphs are not emulated",
     "test_fused_noise_controller_equals_two_kernel_path[True]": "CUDA graphs are not emulated",
     "test_example_driver_runs": "child process without the emulation shim",      # (prefix: both driver tests)
     "test_multigpu_gpu.py": "needs real NCCL ranks",

@@ -129,3 +129,66 @@ def test_split_threshold_selects_the_kernel(compiled_model, split_switch):
         outs.append(env.rollout_device(K, H, mean, noise)["costs"].cpu().numpy().copy())
     env.close()
     np.testing.assert_allclose(outs[0], outs[1], rtol=1e-12)
+
+
+def test_split_rollout_on_random_hard_states(compiled_model, split_switch):
+    """The hard-state fuzz of the thread-per-particle kernel (tests/test_kernel_emu_cpu.py) for the role-split one:
+    joints up to 0.2 rad beyond their limits, joint speeds up to ~6 rad/s, torque-saturating noise, the arm driven towards the table, randomised masses / inertias / damping, against the C
+    oracle within 1e-8 on the whole trajectory."""
+    from hypothesis import HealthCheck, assume, given, settings
+    from hypothesis import strategies as hst
+    from mjmpc_b200.envs.model import randomized_copy, table_clearance
+    lo, hi = compiled_model.tree.jnt_range[:, 0], compiled_model.tree.jnt_range[:, 1]
+    split_switch(1 << 20)
+    seen = dict(cases=0, constrained=0, fast=0)
+
+    @settings(deadline=None, max_examples=24, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(s=hst.integers(0, 2 ** 31 - 1), beyond=hst.sampled_from([0.0, 0.05, 0.2]), vstd=hst.sampled_from([0.5, 2.0, 6.0]),
+           nscale=hst.sampled_from([0.3, 1.0, 3.0]), table=hst.booleans(), rand_model=hst.booleans())
+    def run(s, beyond, vstd, nscale, table, rand_model):
+        rng = np.random.default_rng(s)
+        cm = compiled_model
+        if rand_model:
+            cm, _, _ = randomized_copy(compiled_model, dict(
+                body_mass={"r_forearm_link": [0.3, 0.0], "r_wrist_roll_link": [0.3, 0.0], "r_upper_arm_link": [0.3, 0.0]},
+                body_inertia={"r_upper_arm_link": [0.2, 0.0]},
+                dof_damping={"r_elbow_flex_joint": [0.3, 0.0], "r_shoulder_lift_joint": [0.3, 0.0]}),
+                np.random.RandomState(s % 100000), {})
+        qp = rng.uniform(lo - beyond, hi + beyond)
+        H = 6
+        mean = np.zeros((H, 7))
+        if table:
+            qp[1] = rng.uniform(0.3, 0.5); qp[3] = rng.uniform(-0.4, 0.0); qp[5] = rng.uniform(-0.5, 0.0)
+            mean[:, 1] = 1.0
+        assume(table_clearance(cm.tree, qp) > -0.02)
+        st = dict(qp=qp, qv=rng.normal(0, vstd, 7), target_pos=rng.uniform([-.3, -.2, -.25], [.3, .2, .25]))
+        K = 40
+        noise = nscale * reference_noise(K, H, 7, s % 1000)
+        got, models = _gpu_rollout(cm, st, K, H, noise, mean)
+        ref = _oracle(models, st, mean, noise)
+        assert np.isfinite(got["qv"]).all()
+        scale = np.abs(ref["qv"]).max(axis=(0, 1))
+        assert (np.abs(got["qv"] - ref["qv"]).max(axis=(0, 1)) / scale).max() < TRAJ_RTOL
+        np.testing.assert_allclose(got["costs"], ref["costs"], rtol=1e-8)
+        np.testing.assert_array_equal(got["ncon"], ref["ncon"])
+        seen["cases"] += 1
+        seen["constrained"] += int((ref["ncon"] > 0).any())
+
+    run()
+    assert seen["cases"] >= 15 and seen["constrained"] >= 8, seen
+
+
+def test_split_rollout_fast_joint_takes_the_exact_sincos_fallback(compiled_model, split_switch):
+    """A joint that turns by more than 0.25 rad in one substep (40 rad/s on the shoulder pan, 30 on the wrist roll)
+    is outside the Taylor range of the angle-addition update: the kernel re-evaluates sin / cos exactly.  Two env
+    steps from inside the ranges (the centrifugal load drives other joints into their limits on the way)."""
+    split_switch(1 << 20)
+    qv = np.zeros(7); qv[0] = 40.0; qv[6] = -30.0
+    st = dict(qp=np.array([-1.8, 0.3, 0.0, -1.0, 0.0, -0.5, 1.3]), qv=qv, target_pos=np.array([.1, .1, .1]))
+    K, H = 33, 2
+    mean = np.zeros((H, 7))
+    noise = 0.5 * reference_noise(K, H, 7, 3)
+    got, models = _gpu_rollout(compiled_model, st, K, H, noise, mean)
+    ref = _oracle(models, st, mean, noise)
+    assert np.abs(ref["qv"][:, 0, 7]).min() > 25.0
+    _assert_parity(got, ref)
