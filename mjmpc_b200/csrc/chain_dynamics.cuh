@@ -977,10 +977,20 @@ MJB_HD bool chain_substep(const P& prm, S& sc, double (&q)[7], double (&qd)[7], 
 // smooth force f, the rows R and M in the scratch (SC_M; SC_JC / SC_M2 when the contact row exists).  Same
 // operations in the same order as chain_substep: first guess f_j / M_jj, factor/solve trips on M + diag(D_active),
 // rank-one repair of a single misjudged row, slow path after 6 unsettled trips.
+// factor_only (warp-uniform): the caller is the warp that needs the factor of M + hB for the Euler solve; it runs
+// through the SAME load / factor instructions as the Newton warp next to it (one copy of that code to fetch for
+// both) and leaves with (H, dinv) = LDL'(M + hB).  H / dinv are the caller's arrays for that reason.
 template <class T, class P, class S>
-MJB_HD void constraint_force(const P& prm, S& sc, const double (&f)[7], const Rows& R, double (&fc)[7]) {
+MJB_HD void constraint_force(const P& prm, S& sc, const double (&f)[7], const Rows& R, double (&fc)[7], double (&H)[7][7],
+                             double (&dinv)[7], bool factor_only = false) {
     double dadd[7], radd[7], x[7];
     unsigned act = 0;
+    int moff = 0;
+    bool con_on = false;
+    if (factor_only) {
+#pragma unroll
+        for (int j = 0; j < 7; j++) { dadd[j] = prm[CH_HDAMP + j]; radd[j] = 0.0; }
+    } else {
 #pragma unroll
     for (int j = 0; j < 7; j++) {
         const double bm = R.bs[j] * sc.ld(sc_m(j, j));
@@ -989,9 +999,8 @@ MJB_HD void constraint_force(const P& prm, S& sc, const double (&f)[7], const Ro
         dadd[j] = on ? R.D[j] : 0.0;
         radd[j] = sflip(dadd[j] * R.bs[j], R.sgn(j));
     }
-    int moff = 0;
-    bool con_on = false;
-    if (R.Dc > 0.0) {
+    }
+    if (!factor_only && R.Dc > 0.0) {
 #pragma unroll 1
         for (int i = 0; i < 7; i++) {
             const double ji = R.Dc * sc.ld(SC_JC + i);
@@ -1010,15 +1019,16 @@ MJB_HD void constraint_force(const P& prm, S& sc, const double (&f)[7], const Ro
     int iters = 0, again;
 #pragma unroll 1
     do {
-        double H[7][7], dinv[7];
 #pragma unroll
         for (int i = 0; i < 7; i++) {
 #pragma unroll
             for (int j = 0; j < i; j++) H[i][j] = sc.ld(moff + sc_m(i, j));
             H[i][i] = sc.ld(moff + sc_m(i, i)) + dadd[i];
-            x[i] = f[i] + radd[i];
         }
         ldl7(H, dinv);
+        if (factor_only) return;
+#pragma unroll
+        for (int i = 0; i < 7; i++) x[i] = f[i] + radd[i];
         ldl7_solve(H, dinv, x);
         unsigned actx = 0;
 #pragma unroll

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(4 * LANES, 64 / LANES) rollout_reacher_split_k
             // ---------------------------------------------------------------- phase A
             bool any = false;
             Rows R;
+            R.Dc = 0.0; R.arefc = 0.0; R.below = 0u;       // (only role 2 fills and reads the rows)
             if (role == 0) {
                 double f[7];
                 chain_mass_bias<T, 1>(prm, scp, sn, cs, v, f);
@@ -163,24 +164,20 @@ __global__ void __launch_bounds__(4 * LANES, 64 / LANES) rollout_reacher_split_k
             MJB_TSTAMP(0);
             MJB_TSYNC(1);
             // ---------------------------------------------------------------- phase B
-            if (role == 1) {
-#pragma unroll
-                for (int i = 0; i < 7; i++) {
-#pragma unroll
-                    for (int j = 0; j < i; j++) Hf[i][j] = sc.ld(sc_m(i, j));
-                    Hf[i][i] = sc.ld(sc_m(i, i)) + prm[CH_HDAMP + i];
-                }
-                ldl7(Hf, dinv);
-            } else if (role == 2) {
+            if (role == 1 || role == 2) {
+                // roles 1 and 2 run through ONE copy of the load / factor code: role 1 leaves it with the factor of
+                // M + hB (kept in Hf / dinv until phase C), role 2 goes on with the Newton solve
                 double fc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                if (any) {
+                if (role == 1 || any) {
                     double f[7];
 #pragma unroll
-                    for (int j = 0; j < 7; j++) f[j] = sc.ld(SX_F + j);
-                    constraint_force<T>(prm, sc, f, R, fc);
+                    for (int j = 0; j < 7; j++) f[j] = role == 2 ? sc.ld(SX_F + j) : 0.0;
+                    constraint_force<T>(prm, sc, f, R, fc, Hf, dinv, role == 1);
                 }
+                if (role == 2) {
 #pragma unroll
-                for (int j = 0; j < 7; j++) sc.st(SX_FC + j, fc[j]);
+                    for (int j = 0; j < 7; j++) sc.st(SX_FC + j, fc[j]);
+                }
             } else if (role == 3 && last && t + 1 < a.H) {
                 step_controls(t + 1);      // role 0 read SC_U in phase A; the next read is after two barriers
             }

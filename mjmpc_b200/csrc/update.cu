@@ -797,6 +797,7 @@ select_elites_cluster_kernel(const double* __restrict__ v, long long K, long lon
             const unsigned long long want = s_want;
             const unsigned hit = __ballot_sync(0xffffffffu, inc >= want);
             const int owner = __ffs(hit) - 1;
+            __syncwarp();                            // every lane has read s_want before the owner overwrites it
             if (tid == owner) {
                 unsigned long long cum = inc - part;
                 int b = 0;
