@@ -50,6 +50,7 @@ class Controller(ABC):
         self.shard = shard if shard is not None else ShardContext()
         self._graph = None            # captured CUDA graph of one MPC step (enable_cuda_graph)
         self._graphs = []             # two of them alternate when the next step's noise is drawn during the rollout
+        self._graphs_io = []          # the same with state H2D / step counter / action D2H captured (get_action)
         self._step_d = torch.zeros(1, dtype=torch.int64, device=self.device)   # device mirror of num_steps
 
     # ---- abstract surface (controller.py:80-143,203-205) -----------------------------------
@@ -153,7 +154,15 @@ class Controller(ABC):
         return action
 
     # ---- CUDA-graph replay of the step (launch-bound at small K per GPU) --------------------------
-    def _graph_body(self, parity=0):
+    def _graph_body(self, parity=0, host_io=False):
+        if host_io:
+            # graphs of get_action(): the state and the step counter come from pinned host memory and the action
+            # goes back to it INSIDE the graph -- per call the host writes 18 numbers, replays and synchronises
+            self._rollout_fn.backend.graph_state_copy()
+            self._step_d.copy_(self._step_host, non_blocking=True)
+            action = self._graph_body(parity)
+            self._action_host.copy_(action, non_blocking=True)
+            return action
         blk = self.__dict__.get("_fused_blocks")
         if blk is not None and "ready" in blk:
             # overlapped noise: this graph reads noise tensor `parity` (already drawn) and draws the next step's
@@ -204,6 +213,19 @@ class Controller(ABC):
             with torch.cuda.graph(g):
                 self._graph_action = self._graph_body(parity)
             graphs.append(g)
+        # a second set with the host I/O captured (this package's reacher backend, one state)
+        backend = getattr(self._rollout_fn, "backend", None)
+        self._graphs_io = []
+        if hasattr(backend, "graph_state_copy") and backend._state_host.shape[0] == 1:
+            self._step_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+            self._step_host[0] = self.num_steps
+            self._action_host = torch.zeros(self.d_action, dtype=torch.float64).pin_memory()
+            self._action_host_np = self._action_host.numpy()
+            for parity in range(n_graphs):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._graph_body(parity, host_io=True)
+                self._graphs_io.append(g)
         for k, v in saved.items():
             getattr(self, k).copy_(v)
         self.num_steps = steps
@@ -217,6 +239,7 @@ class Controller(ABC):
     def disable_cuda_graph(self):
         self._graph = None
         self._graphs = []
+        self._graphs_io = []
         self._noise_step = None
         blk = self.__dict__.get("_fused_blocks")
         if blk is not None and "ready" in blk:
@@ -226,8 +249,12 @@ class Controller(ABC):
         """The reference hands set_sim_state_fn a deep copy (olgaussian_mpc.py:107: a simulator may keep or mutate
         what it is given).  This package's own backends copy the state into their device buffer and keep nothing:
         they get the state as it is (a deepcopy of a state dict is ~10 us of every get_action call)."""
-        own = getattr(getattr(self._rollout_fn, "backend", None), "set_env_state", None)
-        self._set_sim_state_fn(state if own is not None and own == self._set_sim_state_fn else copy.deepcopy(state))
+        backend = getattr(self._rollout_fn, "backend", None)
+        own = getattr(backend, "set_env_state", None)
+        if own is None or own != self._set_sim_state_fn:
+            self._set_sim_state_fn(copy.deepcopy(state))
+        elif not (hasattr(backend, "set_env_state_fast") and backend.set_env_state_fast(state)):
+            self._set_sim_state_fn(state)
 
     def _replay(self, state):
         if state is not None:
@@ -249,6 +276,20 @@ class Controller(ABC):
         self.num_steps += 1
 
     def _optimize_graphed(self, state):
+        backend = getattr(self._rollout_fn, "backend", None)
+        if self._graphs_io and state is not None and backend.state_generation == self._graph_state_gen \
+                and backend.set_env_state == self._set_sim_state_fn and backend.write_state_host(state):
+            # host state in, host action out, everything in between inside one graph replay
+            self._step_host[0] = self.num_steps
+            p = self._graph_parity if len(self._graphs_io) == 2 else 0
+            if len(self._graphs_io) == 2 and self._graph_ready != (p, self.num_steps):
+                self._draw_step_noise(p, self.num_steps)
+            self._graphs_io[p].replay()
+            if len(self._graphs_io) == 2:
+                self._graph_parity, self._graph_ready = 1 - p, (1 - p, self.num_steps + 1)
+            self.num_steps += 1
+            torch.cuda.current_stream().synchronize()
+            return self._action_host_np.copy()
         self._replay(state)
         return self._graph_action.cpu().numpy().copy()
 

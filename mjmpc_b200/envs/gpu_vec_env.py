@@ -128,6 +128,49 @@ class GpuReacherVecEnv:
             self._h2d_done = torch.cuda.Event()
         self._h2d_done.record()
 
+    # ---- host I/O inside a captured graph (Controller.enable_cuda_graph) -----------------------------------------
+    def write_state_host(self, state) -> bool:
+        """Write ONE reacher state (dict or (17,) vector) straight into the pinned host buffer, without launching
+        anything: the captured graph of the MPC step copies the buffer to the device itself (graph_state_copy).
+        False when this state does not fit the fast path (several states, device tensors)."""
+        if self._state_host.shape[0] != 1 or isinstance(state, (list, tuple, torch.Tensor)):
+            return False
+        if isinstance(state, np.ndarray) and state.ndim != 1:
+            return False
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()       # an earlier asynchronous set_env_state copy must have left the buffer
+        hv = self._state_host_np
+        if isinstance(state, dict):
+            hv[0, 0:7] = state["qp"]
+            hv[0, 7:14] = state["qv"]
+            hv[0, 14:17] = state["target_pos"]
+        else:
+            hv[0, :] = state
+        return True
+
+    def set_env_state_fast(self, state) -> bool:
+        """set_env_state for ONE state dict / (17,) vector without the numpy / torch conversions of the general path
+        (about 10 us of every eager get_action)."""
+        if not self.write_state_host(state):
+            return False
+        self._state.copy_(self._state_host, non_blocking=True)
+        if self._h2d_done is None:
+            self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record()
+        return True
+
+    def graph_state_copy(self):
+        """Pinned host state buffer -> device state buffer on the current stream (capturable)."""
+        self._state.copy_(self._state_host, non_blocking=True)
+
+    @property
+    def _state_host_np(self):
+        v = self.__dict__.get("_state_host_view")
+        if v is None or v[0] is not self._state_host:
+            v = (self._state_host, self._state_host.numpy())
+            self.__dict__["_state_host_view"] = v
+        return v[1]
+
     def set_env_state_device(self, state: torch.Tensor):
         """Device-resident (n_ctrl, 17) states (no host round trip).  Copied into the persistent state
         buffer so that a captured CUDA graph of the MPC step keeps reading the right address."""
