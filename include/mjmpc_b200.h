@@ -119,6 +119,39 @@ typedef struct {
 } mjb_lqr_args;
 int mjb_rollout_lqr(const mjb_lqr_args* a, void* stream);
 
+/* ---- K11 runtime-parameterised TREE rollout: replaces MuJoCo's mj_step under
+ * gym.envs.mujoco.MujocoEnv.do_simulation for the reference's hinge / slide models with a forward-progress reward --
+ * SwimmerEnv.step (mjmpc/envs/basic/swimmer.py:10-19: 'swimmer.xml', frame_skip 4) and the same shape of step in
+ * HalfCheetahEnv.step (half_cheetah.py:10-19) -- inside GymEnvWrapper.rollout (mjmpc/envs/gym_env_wrapper.py:123-153).
+ *   reward_t = w_fwd * (q[fwd_dof] after - before) / (frame_skip * timestep) - w_ctrl * |a_t|^2,  cost = -reward
+ *   a_t = mean[t] + noise[k, t] (recorded unclipped, wrapper :150; MuJoCo clamps the control to ctrlrange)
+ *   observation = (qpos[obs_qpos_start:], qvel)   (swimmer.py:21-24: 2; half_cheetah.py:21-25: 1)
+ * The model is the link-per-dof block compiled from MJCF by mjmpc_b200/envs/mjcf_tree.py (layout: csrc/tree_model.h,
+ * reported by mjb_tree_layout): link_params (nv, LK_STRIDE) doubles, link_ints (nv, LI_STRIDE) ints, globals
+ * (TG_STRIDE) doubles, HOST pointers, copied.  Dynamics: hinge / slide joints with any axis, anchor and body
+ * orientation, several joints per body, gravity, joint springs / dampers / armature, mj_passive's inertia-box fluid
+ * forces (option density / viscosity), soft joint limits (solreflimit / solimplimit), motors with ctrlrange, mj_Euler.
+ * No contacts, frictionloss, tendons, free / ball joints (the compiler rejects such models). */
+typedef struct mjb_tree_model mjb_tree_model;
+mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* link_params, const int* link_ints,
+                                      const double* globals, int device);   /* NULL + mjb_last_error on failure */
+void mjb_tree_model_destroy(mjb_tree_model* m);
+void mjb_tree_layout(int* out34);   /* the 34 layout constants of csrc/tree_model.h, in declaration order */
+typedef struct {
+    int K, H, frame_skip, particles_per_ctrl;
+    int fwd_dof, obs_qpos_start;
+    double w_fwd, w_ctrl;
+    const double* state;            /* (n_ctrl, 2 nv): qpos, qvel (swimmer.py:33-49 get / set_env_state) */
+    const double* mean;             /* (n_ctrl, H, nu) */
+    const double* noise; long long noise_sk, noise_st, noise_sj;     /* (K, H, nu) any strides, or NULL */
+    double* costs; long long costs_sk, costs_st;
+    double* actions; long long act_sk, act_st, act_sj;               /* or NULL */
+    double* states_out;             /* (K, H, 2 nv) row-major, state AFTER each env step, or NULL */
+    double* next_obs;               /* (K, H, 2 nv - obs_qpos_start) row-major, or NULL */
+    int* nefc;                      /* (K,) limit rows summed over the rollout's substeps, or NULL */
+} mjb_tree_rollout_args;
+int mjb_rollout_tree(const mjb_tree_model* m, const mjb_tree_rollout_args* a, void* stream);
+
 /* ---- K2 noise: replaces generate_noise (mjmpc/utils/control_utils.py:24-34) and the
  * use_zero_control_seq overwrite (mjmpc/control/olgaussian_mpc.py:110-111).  Philox4x32-10 keyed by
  * `seed`, counters (k_offset + k, low32(offset), t, high32(offset) << 8 | pair): results do not

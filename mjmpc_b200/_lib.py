@@ -112,6 +112,18 @@ class LqrArgs(C.Structure):
     ]
 
 
+class TreeRolloutArgs(C.Structure):
+    _fields_ = [
+        ("K", C.c_int), ("H", C.c_int), ("frame_skip", C.c_int), ("particles_per_ctrl", C.c_int),
+        ("fwd_dof", C.c_int), ("obs_qpos_start", C.c_int), ("w_fwd", C.c_double), ("w_ctrl", C.c_double),
+        ("state", C.c_void_p), ("mean", C.c_void_p),
+        ("noise", C.c_void_p), ("noise_sk", c_ll), ("noise_st", c_ll), ("noise_sj", c_ll),
+        ("costs", C.c_void_p), ("costs_sk", c_ll), ("costs_st", c_ll),
+        ("actions", C.c_void_p), ("act_sk", c_ll), ("act_st", c_ll), ("act_sj", c_ll),
+        ("states_out", C.c_void_p), ("next_obs", C.c_void_p), ("nefc", C.c_void_p),
+    ]
+
+
 class NoiseArgs(C.Structure):
     _fields_ = [
         ("K", C.c_int), ("H", C.c_int), ("d", C.c_int),
@@ -215,7 +227,8 @@ RETURNS_CTG, RETURNS_TD_LAMBDA = 0, 1
 BASE_ACTIONS = {"null": 0, "repeat": 1, "random": 2}
 
 EXPORTS += [
-    "mjb_rollout_pendulum", "mjb_rollout_lqr", "mjb_generate_noise", "mjb_cost_to_go",
+    "mjb_rollout_pendulum", "mjb_rollout_lqr", "mjb_tree_model_create", "mjb_tree_model_destroy", "mjb_tree_layout",
+    "mjb_rollout_tree", "mjb_generate_noise", "mjb_cost_to_go",
     "mjb_softmax_scratch_doubles", "mjb_softmax_partial_doubles", "mjb_softmax_partials", "mjb_softmax_update_fused",
     "mjb_instances_update_batched", "mjb_cov_add_diag_batched",
     "mjb_softmax_combine", "mjb_softmax_exchange_combine", "mjb_softmax_weights",
@@ -228,5 +241,10 @@ EXPORTS += [
 
 
 def _setup_restypes(L):
+    L.mjb_tree_model_create.restype = C.c_void_p
+    L.mjb_tree_model_destroy.restype = None
+    L.mjb_tree_model_destroy.argtypes = [C.c_void_p]
+    L.mjb_tree_layout.restype = None
+    L.mjb_rollout_tree.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mjb_softmax_scratch_doubles.restype = c_ll
     L.mjb_elite_scratch_doubles.restype = c_ll

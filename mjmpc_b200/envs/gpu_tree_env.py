@@ -1,0 +1,223 @@
+"""GPU rollout backend for MJCF hinge / slide trees with a forward-progress reward: the
+reference's ``Swimmer-v0`` (``mjmpc/envs/__init__.py:11-14``, ``mjmpc/envs/basic/swimmer.py``).  Same adaptor
+surface as :class:`GpuReacherVecEnv` / :class:`GpuPendulumVecEnv` (set_env_state / rollout / rollout_fn), plus the
+single-instance plant with the reference env's reset / step / get_obs / get_env_state / set_env_state."""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+
+from .. import _lib
+from . import mjcf_tree
+
+
+class DeviceTreeModel:
+    """Device copy of a compiled tree (``mjb_tree_model``)."""
+
+    def __init__(self, model: mjcf_tree.TreeModel, device: int = 0):
+        L = _lib.lib()
+        layout = (C.c_int * 34)()
+        L.mjb_tree_layout(layout)
+        mine = [mjcf_tree.LK_RFIX, mjcf_tree.LK_OFF, mjcf_tree.LK_AXIS, mjcf_tree.LK_MASS, mjcf_tree.LK_COM, mjcf_tree.LK_IC,
+                mjcf_tree.LK_RIN, mjcf_tree.LK_BOX, mjcf_tree.LK_ARM, mjcf_tree.LK_DAMP, mjcf_tree.LK_STIFF, mjcf_tree.LK_SREF,
+                mjcf_tree.LK_LO, mjcf_tree.LK_HI, mjcf_tree.LK_INVW, mjcf_tree.LK_SOLK, mjcf_tree.LK_SOLB, mjcf_tree.LK_SOLIMP,
+                mjcf_tree.LK_GEAR, mjcf_tree.LK_CLO, mjcf_tree.LK_CHI, mjcf_tree.LK_STRIDE, mjcf_tree.LI_PARENT,
+                mjcf_tree.LI_TYPE, mjcf_tree.LI_LIMITED, mjcf_tree.LI_ACT, mjcf_tree.LI_BODY, mjcf_tree.LI_STRIDE,
+                mjcf_tree.G_DT, mjcf_tree.G_GRAV, mjcf_tree.G_RHO, mjcf_tree.G_VISC, mjcf_tree.G_STRIDE, mjcf_tree.MAX_LINKS]
+        if list(layout) != mine:
+            raise _lib.MjbError("parameter layout of mjcf_tree.py and csrc/tree_model.h differ")
+        P, I, G = mjcf_tree.pack_links(model)
+        self.nv, self.nu = model.nv, model.nu
+        self._keep = (np.ascontiguousarray(P), np.ascontiguousarray(I, np.int32), np.ascontiguousarray(G))
+        self.handle = C.c_void_p(L.mjb_tree_model_create(
+            C.c_int(model.nv), C.c_int(model.nu), self._keep[0].ctypes.data_as(C.c_void_p),
+            self._keep[1].ctypes.data_as(C.c_void_p), self._keep[2].ctypes.data_as(C.c_void_p), C.c_int(device)))
+        if not self.handle:
+            raise _lib.MjbError(L.mjb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.lib().mjb_tree_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GpuTreeVecEnv:
+    """Batched rollouts of one compiled tree.  ``fwd_dof`` / ``w_fwd`` / ``w_ctrl`` / ``obs_qpos_start`` describe the
+    env on top of the model (swimmer.py:10-24: dof 0, 1, 1e-4, 2; half_cheetah.py:10-25: dof 0, 1, 0.1, 1)."""
+
+    def __init__(self, model: mjcf_tree.TreeModel, frame_skip: int, fwd_dof: int = 0, w_fwd: float = 1.0,
+                 w_ctrl: float = 1e-4, obs_qpos_start: int = 2, device: int = 0):
+        if not torch.cuda.is_available():
+            raise _lib.MjbError("GpuTreeVecEnv needs a CUDA device (there is no CPU fallback)")
+        self.model = model
+        self.device = torch.device("cuda", device)
+        self.dmodel = DeviceTreeModel(model, device)
+        self.frame_skip, self.fwd_dof, self.w_fwd, self.w_ctrl = int(frame_skip), int(fwd_dof), float(w_fwd), float(w_ctrl)
+        self.obs_qpos_start = int(obs_qpos_start)
+        self.nv = model.nv
+        self.d_action, self.d_state, self.d_obs = model.nu, 2 * model.nv, 2 * model.nv - self.obs_qpos_start
+        self.dt = model.timestep * self.frame_skip
+        self._state = torch.zeros(1, 2 * self.nv, dtype=torch.float64, device=self.device)
+        lim = np.where(model.act_ctrllimited[:, None], model.act_ctrlrange, np.array([[-1.0, 1.0]]))
+        self.action_lows, self.action_highs = lim[:, 0].copy(), lim[:, 1].copy()
+
+    @classmethod
+    def swimmer(cls, device: int = 0, **model_kwargs):
+        """``Swimmer-v0``: swimmer.py:7 (frame_skip 4), :10-19 (reward), :21-24 (observation)."""
+        model = mjcf_tree.compile_mjcf_string(mjcf_tree.swimmer_mjcf(**model_kwargs), allow_contacts="ignore")
+        return cls(model, frame_skip=4, fwd_dof=0, w_fwd=1.0, w_ctrl=1e-4, obs_qpos_start=2, device=device)
+
+    # ---- state (swimmer.py:33-49: {'qpos', 'qvel'})
+    def set_env_state(self, state_dicts):
+        if not isinstance(state_dicts, (list, tuple)):
+            state_dicts = [state_dicts]
+        rows = np.stack([np.concatenate([np.asarray(s["qpos"], float).reshape(self.nv),
+                                         np.asarray(s["qvel"], float).reshape(self.nv)]) for s in state_dicts])
+        self._state = torch.from_numpy(rows).to(self.device)
+
+    def set_env_state_device(self, state: torch.Tensor):
+        self._state = state.reshape(-1, 2 * self.nv).to(self.device, torch.float64).contiguous()
+
+    def reset(self):
+        pass
+
+    def close(self):
+        self.dmodel.close()
+
+    # ---- rollouts
+    def rollout_device(self, num_particles, horizon, mean, noise, want_states=False, want_obs=False, want_nefc=False):
+        """``mean`` (n_ctrl, H, nu) or (H, nu); ``noise`` (K, H, nu) any strides or None.  Costs / actions come back in
+        the particle-minor layout the update kernels read (like ``GpuReacherVecEnv.rollout_device``)."""
+        K, H, nu = int(num_particles), int(horizon), self.d_action
+        n_ctrl = self._state.shape[0]
+        mean = mean.reshape(-1, H, nu)
+        if mean.shape[0] != n_ctrl:
+            raise ValueError("mean has %d controller rows but %d states are set" % (mean.shape[0], n_ctrl))
+        if K % n_ctrl != 0:
+            raise ValueError("Number of particles must be divisible by number of controllers")
+        mean = mean.contiguous()
+        dev = self.device
+        costs = torch.empty((H, K), dtype=torch.float64, device=dev).t()
+        actions = torch.empty((H, nu, K), dtype=torch.float64, device=dev).permute(2, 0, 1)
+        a = _lib.TreeRolloutArgs()
+        a.K, a.H, a.frame_skip, a.particles_per_ctrl = K, H, self.frame_skip, K // n_ctrl
+        a.fwd_dof, a.obs_qpos_start, a.w_fwd, a.w_ctrl = self.fwd_dof, self.obs_qpos_start, self.w_fwd, self.w_ctrl
+        a.state, a.mean = self._state.data_ptr(), mean.data_ptr()
+        if noise is not None:
+            if tuple(noise.shape) != (K, H, nu):
+                raise ValueError("noise must have shape (K,H,%d)" % nu)
+            a.noise = noise.data_ptr()
+            a.noise_sk, a.noise_st, a.noise_sj = noise.stride()
+        a.costs = costs.data_ptr()
+        a.costs_sk, a.costs_st = costs.stride()
+        a.actions = actions.data_ptr()
+        a.act_sk, a.act_st, a.act_sj = actions.stride()
+        out = dict(costs=costs, actions=actions)
+        if want_states:
+            out["states"] = torch.empty((K, H, 2 * self.nv), dtype=torch.float64, device=dev)
+            a.states_out = out["states"].data_ptr()
+        if want_obs:
+            out["next_observations"] = torch.empty((K, H, self.d_obs), dtype=torch.float64, device=dev)
+            a.next_obs = out["next_observations"].data_ptr()
+        if want_nefc:
+            out["nefc"] = torch.empty((K,), dtype=torch.int32, device=dev)
+            a.nefc = out["nefc"].data_ptr()
+        self._keepalive = (mean, noise)
+        _lib.check(_lib.lib().mjb_rollout_tree(self.dmodel.handle, C.byref(a), _lib.stream_ptr()))
+        return out
+
+    def _to_device(self, x):
+        if x is None or isinstance(x, torch.Tensor):
+            return x
+        return torch.from_numpy(np.ascontiguousarray(x, np.float64)).to(self.device)
+
+    def _first_obs(self):
+        s = self._state[0].cpu().numpy()
+        return np.concatenate([s[self.obs_qpos_start:self.nv], s[self.nv:]])
+
+    def rollout(self, num_particles, horizon, mean, noise, mode="open_loop"):
+        """Reference signature and return value (gym_env_wrapper.py:80-156): numpy
+        ``(obs, rew, act, done, info, next_obs)``; ``obs[:, t]`` is the observation before step t."""
+        if mode != "open_loop":
+            raise NotImplementedError("mode %r does not run on the GPU tree rollout" % (mode,))
+        start_t = time.time()
+        out = self.rollout_device(num_particles, horizon, self._to_device(mean), self._to_device(noise), want_obs=True)
+        nobs = out["next_observations"].cpu().numpy()
+        obs = np.concatenate([np.broadcast_to(self._first_obs(), (nobs.shape[0], 1, self.d_obs)), nobs[:, :-1]], axis=1)
+        rew = -np.ascontiguousarray(out["costs"].cpu().numpy())
+        act = np.ascontiguousarray(out["actions"].cpu().numpy())
+        return obs, rew, act, np.zeros_like(rew), {"total_time": time.time() - start_t}, nobs
+
+    @property
+    def rollout_fn(self):
+        def fn(num_particles, horizon, mean, noise, mode="open_loop"):
+            if mode != "open_loop":
+                raise NotImplementedError("only mode='open_loop' runs on the GPU tree rollout")
+            host = not isinstance(noise, torch.Tensor) and not isinstance(mean, torch.Tensor)
+            out = self.rollout_device(num_particles, horizon, self._to_device(mean), self._to_device(noise))
+            if host:
+                return {k: np.ascontiguousarray(v.cpu().numpy()) for k, v in out.items()}
+            return out
+        fn.backend = self
+        return fn
+
+
+class GpuSwimmerEnv:
+    """The PLANT for ``Swimmer-v0`` (``mjmpc/envs/basic/swimmer.py:5-49``): one swimmer advanced by the kernel the
+    planner rolls out (K = 1, H = 1)."""
+    _max_episode_steps = 1000
+
+    def __init__(self, device: int = 0, seed=None, **model_kwargs):
+        self.sim = GpuTreeVecEnv.swimmer(device=device, **model_kwargs)
+        self.d_obs, self.d_state, self.d_action = self.sim.d_obs, self.sim.d_state, self.sim.d_action
+        self.action_lows, self.action_highs = self.sim.action_lows, self.sim.action_highs
+        self.np_random = np.random.RandomState(seed)
+        self.nv = self.sim.nv
+        self.init_qpos, self.init_qvel = np.zeros(self.nv), np.zeros(self.nv)
+        self.qpos, self.qvel = self.init_qpos.copy(), self.init_qvel.copy()
+        self.dt = self.sim.dt
+
+    def reset(self, seed=None):
+        """swimmer.py:26-31 reset_model: init + U(-0.1, 0.1) on qpos and qvel."""
+        if seed is not None:
+            self.np_random = np.random.RandomState(seed)
+        self.qpos = self.init_qpos + self.np_random.uniform(low=-.1, high=.1, size=self.nv)
+        self.qvel = self.init_qvel + self.np_random.uniform(low=-.1, high=.1, size=self.nv)
+        return self.get_obs()
+
+    def get_obs(self):
+        return np.concatenate([self.qpos[2:], self.qvel])          # swimmer.py:21-24
+
+    def get_env_state(self):
+        return {'qpos': self.qpos.copy(), 'qvel': self.qvel.copy()}
+
+    def set_env_state(self, state_dict):
+        self.qpos = np.asarray(state_dict['qpos'], float).reshape(self.nv).copy()
+        self.qvel = np.asarray(state_dict['qvel'], float).reshape(self.nv).copy()
+
+    def step(self, a):
+        """swimmer.py:10-19."""
+        a = np.asarray(a, np.float64).reshape(1, self.d_action)
+        self.sim.set_env_state(self.get_env_state())
+        out = self.sim.rollout_device(1, 1, torch.as_tensor(a, device=self.sim.device), None, want_states=True)
+        s = out["states"][0, 0].cpu().numpy()
+        xbefore = self.qpos[0]
+        self.qpos, self.qvel = s[:self.nv].copy(), s[self.nv:].copy()
+        reward_fwd = (self.qpos[0] - xbefore) / self.dt
+        reward_ctrl = -1e-4 * float(np.square(a).sum())
+        return self.get_obs(), -float(out["costs"][0, 0].item()), False, dict(reward_fwd=reward_fwd, reward_ctrl=reward_ctrl)
+
+    def evaluate_success(self, trajectories):
+        return 0.0
+
+    def close(self):
+        self.sim.close()

@@ -1,0 +1,571 @@
+"""MJCF-subset compiler for the runtime-parameterised tree rollout kernel (``csrc/rollout_tree.cu``).
+
+SURVEY §8(f-3): the reference's other MuJoCo models (``mjmpc/envs/assets/xml/swimmer.xml``,
+``half_cheetah.xml``) go through MuJoCo's own XML compiler inside ``mujoco_py`` (``gym.envs.mujoco.MujocoEnv``,
+reference ``mjmpc/envs/basic/swimmer.py:7``).  This module restates the part of that compiler a kinematic tree of
+hinge / slide joints needs and lowers the result to the kernel's parameter block.
+
+Subset (anything else raises ``UnsupportedMjcf`` -- an unsupported model is rejected, never simulated wrongly):
+  compiler   angle radian|degree, coordinate local, inertiafromgeom true|auto|false (+ <inertial>), settotalmass
+  option     timestep, gravity, density, viscosity, integrator Euler (wind must be zero)
+  default    nested classes for joint / geom / motor / site; ``childclass`` and ``class`` attributes
+  body       pos, quat | axisangle | euler; any number of hinge / slide joints per body, any axis, any anchor
+  joint      type hinge|slide, pos, axis, range + limited, damping, armature, stiffness + springref, ref = 0,
+             solreflimit / solimplimit
+  geom       sphere, capsule (fromto or size + pos/quat/axisangle), cylinder, box, plane (ignored): mass properties
+  actuator   motor: joint, gear (first component), ctrlrange + ctrllimited
+Not in the subset: contacts (a model whose geoms can collide is accepted only with ``allow_contacts="ignore"``, and
+says so in ``TreeModel.ignored``), frictionloss, tendons, equality constraints, free / ball joints, RK4.
+
+MuJoCo semantics restated here [EXT, MuJoCo 2.0 documentation: "XML reference", "Computation"]:
+  * geom mass properties at density 1000 unless given; body frame = first-moment / parallel-axis composition of its
+    geoms; the body inertial frame is the geom frame for a single geom, else the principal axes;
+  * bodies without joints are welded into their parent; world-fixed bodies drop out;
+  * dof_invweight0[i] = (M(qpos0)^-1)_ii  (hinge / slide: one dof per joint), the regulariser scale of limit rows;
+  * solref (timeconst, dampratio) -> (K, B) with timeconst clamped to 2 * timestep (REFSAFE).
+"""
+from __future__ import annotations
+
+import math
+import xml.etree.ElementTree as ET
+from dataclasses import dataclass, field
+from typing import Dict, List
+
+import numpy as np
+
+
+class UnsupportedMjcf(ValueError):
+    pass
+
+
+HINGE, SLIDE = 0, 1
+
+
+def _f(s, n=None):
+    v = np.array([float(x) for x in str(s).split()], float)
+    if n is not None and v.size != n:
+        raise UnsupportedMjcf("expected %d numbers, got %r" % (n, s))
+    return v
+
+
+def quat_to_mat(q):
+    q = np.asarray(q, float)
+    q = q / np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def axisangle_to_mat(axis, angle):
+    a = np.asarray(axis, float)
+    a = a / np.linalg.norm(a)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + math.sin(angle) * K + (1 - math.cos(angle)) * (K @ K)
+
+
+def _z_to(v):
+    """Rotation taking the z axis onto unit vector v (MuJoCo's fromto / zaxis convention: minimal rotation)."""
+    v = np.asarray(v, float) / np.linalg.norm(v)
+    z = np.array([0.0, 0.0, 1.0])
+    c = float(z @ v)
+    ax = np.cross(z, v)
+    s = np.linalg.norm(ax)
+    if s < 1e-12:
+        return np.eye(3) if c > 0 else np.diag([1.0, -1.0, -1.0])
+    return axisangle_to_mat(ax / s, math.atan2(s, c))
+
+
+@dataclass
+class TreeModel:
+    """MuJoCo-style compiled model of a hinge / slide tree (world = body 0 is implicit: parent -1 = world)."""
+    name: str
+    timestep: float
+    gravity: np.ndarray
+    density: float
+    viscosity: float
+    # bodies that move (welded bodies already merged), topological order
+    body_parent: np.ndarray       # (nb,) int, -1 = world
+    body_pos: np.ndarray          # (nb, 3) in the parent body frame
+    body_mat: np.ndarray          # (nb, 3, 3) body frame in the parent body frame
+    body_mass: np.ndarray         # (nb,)
+    body_ipos: np.ndarray         # (nb, 3) centre of mass in the body frame
+    body_imat: np.ndarray         # (nb, 3, 3) inertial frame in the body frame (columns = principal axes)
+    body_inertia: np.ndarray      # (nb, 3) principal moments
+    body_names: List[str]
+    # joints = dofs
+    jnt_type: np.ndarray          # (nv,) HINGE | SLIDE
+    jnt_body: np.ndarray          # (nv,)
+    jnt_pos: np.ndarray           # (nv, 3) anchor, body frame
+    jnt_axis: np.ndarray          # (nv, 3) unit, body frame
+    jnt_limited: np.ndarray       # (nv,) bool
+    jnt_range: np.ndarray         # (nv, 2)
+    jnt_damping: np.ndarray
+    jnt_armature: np.ndarray
+    jnt_stiffness: np.ndarray
+    jnt_springref: np.ndarray
+    jnt_solref: np.ndarray        # (nv, 2)
+    jnt_solimp: np.ndarray        # (nv, 5)
+    jnt_names: List[str]
+    # actuators
+    act_dof: np.ndarray           # (nu,)
+    act_gear: np.ndarray
+    act_ctrllimited: np.ndarray
+    act_ctrlrange: np.ndarray     # (nu, 2)
+    dof_invweight0: np.ndarray = None
+    ignored: List[str] = field(default_factory=list)
+
+    @property
+    def nv(self):
+        return int(self.jnt_type.size)
+
+    @property
+    def nb(self):
+        return int(self.body_parent.size)
+
+    @property
+    def nu(self):
+        return int(self.act_dof.size)
+
+
+# ------------------------------------------------------------------------------------------------ defaults
+class _Defaults:
+    """MJCF default classes: a class inherits its enclosing class; elements merge attribute-wise."""
+
+    def __init__(self, root):
+        self.cls: Dict[str, Dict[str, Dict[str, str]]] = {"main": {}}
+        for d in root.findall("default"):
+            self._read(d, "main", top=True)
+
+    def _read(self, node, parent, top=False):
+        name = node.get("class", "main" if top else None)
+        if name is None:
+            raise UnsupportedMjcf("nested <default> without class")
+        table = {k: dict(v) for k, v in self.cls.get(parent, {}).items()} if name != "main" else self.cls["main"]
+        for e in node:
+            if e.tag == "default":
+                continue
+            table.setdefault(e.tag, {}).update(e.attrib)
+        self.cls[name] = table
+        for d in node.findall("default"):
+            self._read(d, name)
+
+    def resolve(self, elem, childclass):
+        cls = elem.get("class", childclass or "main")
+        if cls not in self.cls:
+            raise UnsupportedMjcf("unknown default class %r" % cls)
+        a = dict(self.cls[cls].get(elem.tag, {}))
+        a.update({k: v for k, v in elem.attrib.items() if k != "class"})
+        return a
+
+
+# ------------------------------------------------------------------------------------------------ geoms
+def _geom_mass_props(a, angle_scale):
+    """(mass, centre, inertia about the centre, frame) of one geom in the body frame."""
+    kind = a.get("type", "sphere")
+    if kind == "plane":
+        return None
+    size = _f(a.get("size", "0"))
+    R = _orientation(a, angle_scale)
+    pos = _f(a.get("pos", "0 0 0"), 3)
+    if "fromto" in a:
+        if kind not in ("capsule", "cylinder", "box"):
+            raise UnsupportedMjcf("fromto on a %s" % kind)
+        ft = _f(a["fromto"], 6)
+        pos = 0.5 * (ft[:3] + ft[3:])
+        half = 0.5 * float(np.linalg.norm(ft[3:] - ft[:3]))
+        R = _z_to(ft[3:] - ft[:3])
+        size = np.array([size[0], half]) if kind != "box" else np.array([size[0], size[0], half])
+    r = float(size[0])
+    if kind == "sphere":
+        vol = 4.0 / 3.0 * math.pi * r ** 3
+        unit = np.full(3, 0.4 * r * r)
+    elif kind == "capsule":
+        h = 2.0 * float(size[1])
+        vc, vs = math.pi * r * r * h, 4.0 / 3.0 * math.pi * r ** 3
+        vol = vc + vs
+        axial = (0.5 * vc * r * r + 0.4 * vs * r * r) / vol
+        trans = (vc * (3 * r * r + h * h) / 12.0 + vs * (0.4 * r * r + 0.25 * h * h + 0.375 * r * h)) / vol
+        unit = np.array([trans, trans, axial])
+    elif kind == "cylinder":
+        h = 2.0 * float(size[1])
+        vol = math.pi * r * r * h
+        unit = np.array([(3 * r * r + h * h) / 12.0, (3 * r * r + h * h) / 12.0, 0.5 * r * r])
+    elif kind == "box":
+        x, y, z = (2.0 * size[:3]).tolist()
+        vol = x * y * z
+        unit = np.array([(y * y + z * z) / 12.0, (x * x + z * z) / 12.0, (x * x + y * y) / 12.0])
+    else:
+        raise UnsupportedMjcf("geom type %s" % kind)
+    mass = float(a["mass"]) if "mass" in a else float(a.get("density", "1000")) * vol
+    return mass, pos, R @ np.diag(mass * unit) @ R.T, R
+
+
+def _orientation(a, angle_scale):
+    if "quat" in a:
+        return quat_to_mat(_f(a["quat"], 4))
+    if "axisangle" in a:
+        v = _f(a["axisangle"], 4)
+        return axisangle_to_mat(v[:3], v[3] * angle_scale)
+    if "euler" in a:
+        e = _f(a["euler"], 3) * angle_scale        # default eulerseq "xyz", intrinsic
+        R = np.eye(3)
+        for ax, ang in zip(np.eye(3), e):
+            R = R @ axisangle_to_mat(ax, ang)
+        return R
+    if "zaxis" in a:
+        return _z_to(_f(a["zaxis"], 3))
+    if "xyaxes" in a:
+        raise UnsupportedMjcf("xyaxes orientation")
+    return np.eye(3)
+
+
+# ------------------------------------------------------------------------------------------------ compile
+def compile_mjcf(path: str, allow_contacts: str = "error") -> TreeModel:
+    """Compile an MJCF file."""
+    return compile_mjcf_root(ET.parse(path).getroot(), allow_contacts)
+
+
+def compile_mjcf_string(text: str, allow_contacts: str = "error") -> TreeModel:
+    return compile_mjcf_root(ET.fromstring(text), allow_contacts)
+
+
+def compile_mjcf_root(root, allow_contacts: str = "error") -> TreeModel:
+    comp = root.find("compiler")
+    comp = dict(comp.attrib) if comp is not None else {}
+    if comp.get("coordinate", "local") != "local":
+        raise UnsupportedMjcf("coordinate=global")
+    angle_scale = 1.0 if comp.get("angle", "degree") == "radian" else math.pi / 180.0
+    from_geom = comp.get("inertiafromgeom", "auto")
+    opt = root.find("option")
+    opt = dict(opt.attrib) if opt is not None else {}
+    if opt.get("integrator", "Euler") != "Euler":
+        raise UnsupportedMjcf("integrator %s" % opt["integrator"])
+    if "wind" in opt and np.any(_f(opt["wind"]) != 0):
+        raise UnsupportedMjcf("wind")
+    for tag in ("tendon", "equality", "contact", "sensor", "keyframe"):
+        if root.find(tag) is not None and len(root.find(tag)):
+            raise UnsupportedMjcf("<%s>" % tag)
+    timestep = float(opt.get("timestep", "0.002"))
+    defaults = _Defaults(root)
+    ignored: List[str] = []
+
+    raw = []     # every body of the file: dict(parent, pos, mat, joints, parts, name)
+
+    def walk(e, parent, childclass):
+        for be in e.findall("body"):
+            cc = be.get("childclass", childclass)
+            joints = []
+            for je in be.findall("joint"):
+                a = defaults.resolve(je, cc)
+                kind = a.get("type", "hinge")
+                if kind not in ("hinge", "slide"):
+                    raise UnsupportedMjcf("joint type %s" % kind)
+                if float(a.get("frictionloss", "0")) != 0.0:
+                    raise UnsupportedMjcf("frictionloss")
+                if float(a.get("ref", "0")) != 0.0:
+                    raise UnsupportedMjcf("joint ref")
+                axis = _f(a.get("axis", "0 0 1"), 3)
+                rng = _f(a.get("range", "0 0"), 2) * (angle_scale if kind == "hinge" else 1.0)
+                joints.append(dict(
+                    name=a.get("name", "joint%d" % (len(raw) * 8 + len(joints))), type=HINGE if kind == "hinge" else SLIDE,
+                    pos=_f(a.get("pos", "0 0 0"), 3), axis=axis / np.linalg.norm(axis),
+                    limited=a.get("limited", "false") == "true", range=rng,
+                    damping=float(a.get("damping", "0")), armature=float(a.get("armature", "0")),
+                    stiffness=float(a.get("stiffness", "0")),
+                    springref=float(a.get("springref", "0")) * (angle_scale if kind == "hinge" else 1.0),
+                    solref=_f(a.get("solreflimit", "0.02 1"), 2),
+                    solimp=_solimp(a.get("solimplimit"))))
+            if be.find("freejoint") is not None:
+                raise UnsupportedMjcf("free joint")
+            parts, collides = [], False
+            for ge in be.findall("geom"):
+                a = defaults.resolve(ge, cc)
+                mp = _geom_mass_props(a, angle_scale)
+                if mp is not None:
+                    parts.append(mp)
+                if int(a.get("contype", "1")) != 0 or int(a.get("conaffinity", "1")) != 0:
+                    collides = True
+            inertial = be.find("inertial")
+            if inertial is not None and from_geom != "true":
+                a = inertial.attrib
+                if "fullinertia" in a:
+                    raise UnsupportedMjcf("fullinertia")
+                Ri = _orientation(a, angle_scale)
+                parts = [(float(a["mass"]), _f(a["pos"], 3), Ri @ np.diag(_f(a["diaginertia"], 3)) @ Ri.T, Ri)]
+            elif from_geom == "false":
+                parts = []
+            raw.append(dict(parent=parent, pos=_f(be.get("pos", "0 0 0"), 3), mat=_orientation(be.attrib, angle_scale),
+                            joints=joints, parts=parts, name=be.get("name", "body%d" % len(raw)), collides=collides))
+            walk(be, len(raw) - 1, cc)
+
+    wb = root.find("worldbody")
+    walk(wb, -1, None)
+
+    # contacts: the subset has none.  A pair can collide when (contype_a & conaffinity_b) | (contype_b & conaffinity_a)
+    # and the bodies are not parent and child; with several colliding geoms on non-adjacent bodies the model is outside
+    # the subset unless the caller accepts dropping them.
+    n_coll = sum(1 for b in raw if b["collides"])
+    world_coll = any(int(defaults.resolve(g, None).get("contype", "1")) != 0 or
+                     int(defaults.resolve(g, None).get("conaffinity", "1")) != 0 for g in wb.findall("geom"))
+    if n_coll > 2 or (world_coll and n_coll > 0):
+        msg = "%d bodies carry colliding geoms%s" % (n_coll, " and so does the world" if world_coll else "")
+        if allow_contacts != "ignore":
+            raise UnsupportedMjcf("contacts are outside the subset: " + msg + " (allow_contacts='ignore' drops them)")
+        ignored.append("contacts dropped: " + msg)
+
+    # ---- weld joint-less bodies into their parents; drop world-fixed ones
+    nraw = len(raw)
+    frame_parent = [None] * nraw      # index of the moving body this raw body belongs to (-1 = world)
+    frame_pos = [None] * nraw         # its frame expressed in that moving body's frame
+    frame_mat = [None] * nraw
+    moving = []
+    for i, b in enumerate(raw):
+        p = b["parent"]
+        if p < 0:
+            hp, hpos, hmat = -1, b["pos"], b["mat"]
+        else:
+            hp = frame_parent[p] if not raw[p]["joints"] else p
+            if raw[p]["joints"]:
+                hpos, hmat = b["pos"], b["mat"]
+            else:
+                hpos, hmat = frame_pos[p] + frame_mat[p] @ b["pos"], frame_mat[p] @ b["mat"]
+        if b["joints"]:
+            moving.append(i)
+            b["host_parent"], b["host_pos"], b["host_mat"] = hp, hpos, hmat
+            frame_parent[i], frame_pos[i], frame_mat[i] = i, np.zeros(3), np.eye(3)
+        else:
+            frame_parent[i], frame_pos[i], frame_mat[i] = hp, hpos, hmat
+    index = {r: k for k, r in enumerate(moving)}
+    nb = len(moving)
+    if nb == 0:
+        raise UnsupportedMjcf("no joints")
+    parts_of = {r: [] for r in moving}
+    fluid = float(opt.get("density", "0")) > 0 or float(opt.get("viscosity", "0")) > 0
+    for i, b in enumerate(raw):
+        host = frame_parent[i]
+        if host < 0:
+            continue
+        if fluid and host != i and b["parts"]:
+            # MuJoCo keeps a welded body as a body of its own, with its own inertia box in mj_passive's fluid model
+            raise UnsupportedMjcf("body %r is welded to %r in a fluid (per-body inertia boxes)" % (b["name"], raw[host]["name"]))
+        for (m, c, I, R) in b["parts"]:
+            parts_of[host].append((m, frame_pos[i] + frame_mat[i] @ c, frame_mat[i] @ I @ frame_mat[i].T, frame_mat[i] @ R))
+
+    body_parent = np.array([index.get(raw[r]["host_parent"], -1) for r in moving], int)
+    body_pos = np.array([raw[r]["host_pos"] for r in moving])
+    body_mat = np.array([raw[r]["host_mat"] for r in moving])
+    mass, ipos, imat, inertia = np.zeros(nb), np.zeros((nb, 3)), np.zeros((nb, 3, 3)), np.zeros((nb, 3))
+    for k, r in enumerate(moving):
+        ps = parts_of[r]
+        m = sum(p[0] for p in ps)
+        if m <= 0:
+            imat[k] = np.eye(3)
+            continue
+        c = sum(p[0] * p[1] for p in ps) / m
+        I = np.zeros((3, 3))
+        for (mi, ci, Ii, _) in ps:
+            d = ci - c
+            I += Ii + mi * ((d @ d) * np.eye(3) - np.outer(d, d))
+        mass[k], ipos[k] = m, c
+        if len(ps) == 1:
+            imat[k] = ps[0][3]
+            inertia[k] = np.diag(ps[0][3].T @ I @ ps[0][3])
+        else:
+            w, V = np.linalg.eigh(I)
+            order = np.argsort(-w)                   # MuJoCo sorts principal moments in decreasing order
+            V = V[:, order]
+            if np.linalg.det(V) < 0:
+                V[:, 2] = -V[:, 2]
+            imat[k], inertia[k] = V, w[order]
+    if "settotalmass" in comp:
+        s = float(comp["settotalmass"]) / mass.sum()
+        mass, inertia = mass * s, inertia * s
+
+    J = [(index[r], j) for r in moving for j in raw[r]["joints"]]
+    nv = len(J)
+    names = [j["name"] for _, j in J]
+    act_dof, gear, cl, cr = [], [], [], []
+    act = root.find("actuator")
+    for me in (list(act) if act is not None else []):
+        if me.tag != "motor":
+            raise UnsupportedMjcf("actuator %s" % me.tag)
+        a = defaults.resolve(me, None)
+        if a.get("joint") not in names:
+            raise UnsupportedMjcf("motor on unknown joint %r" % a.get("joint"))
+        act_dof.append(names.index(a["joint"]))
+        gear.append(_f(a.get("gear", "1"))[0])
+        cl.append(a.get("ctrllimited", "false") == "true")
+        cr.append(_f(a.get("ctrlrange", "0 0"), 2))
+    model = TreeModel(
+        name=root.get("model", "model"), timestep=timestep, gravity=_f(opt.get("gravity", "0 0 -9.81"), 3),
+        density=float(opt.get("density", "0")), viscosity=float(opt.get("viscosity", "0")),
+        body_parent=body_parent, body_pos=body_pos, body_mat=body_mat, body_mass=mass, body_ipos=ipos, body_imat=imat,
+        body_inertia=inertia, body_names=[raw[r]["name"] for r in moving],
+        jnt_type=np.array([j["type"] for _, j in J], int), jnt_body=np.array([b for b, _ in J], int),
+        jnt_pos=np.array([j["pos"] for _, j in J]), jnt_axis=np.array([j["axis"] for _, j in J]),
+        jnt_limited=np.array([j["limited"] for _, j in J], bool), jnt_range=np.array([j["range"] for _, j in J]),
+        jnt_damping=np.array([j["damping"] for _, j in J]), jnt_armature=np.array([j["armature"] for _, j in J]),
+        jnt_stiffness=np.array([j["stiffness"] for _, j in J]), jnt_springref=np.array([j["springref"] for _, j in J]),
+        jnt_solref=np.array([j["solref"] for _, j in J]), jnt_solimp=np.array([j["solimp"] for _, j in J]),
+        jnt_names=names, act_dof=np.array(act_dof, int), act_gear=np.array(gear, float),
+        act_ctrllimited=np.array(cl, bool), act_ctrlrange=np.array(cr, float).reshape(-1, 2), ignored=ignored)
+    M0 = mass_matrix(model, np.zeros(nv))
+    model.dof_invweight0 = np.diag(np.linalg.inv(M0)).copy()
+    return model
+
+
+def _solimp(s):
+    v = np.array([0.9, 0.95, 0.001, 0.5, 2.0])
+    if s is not None:
+        g = _f(s)
+        v[:g.size] = g
+    return v
+
+
+# ------------------------------------------------------------------------------------------------ qpos0 quantities
+def kinematics(model: TreeModel, q):
+    """Body frames (origin, rotation), joint anchors and axes in the world frame (MuJoCo's mj_kinematics order:
+    the joints of a body act one after the other on the body frame)."""
+    nb = model.nb
+    xpos, xmat = np.zeros((nb, 3)), np.zeros((nb, 3, 3))
+    anchor, axis = np.zeros((model.nv, 3)), np.zeros((model.nv, 3))
+    for b in range(nb):
+        p = model.body_parent[b]
+        Pp, Rp = (np.zeros(3), np.eye(3)) if p < 0 else (xpos[p], xmat[p])
+        pos, R = Pp + Rp @ model.body_pos[b], Rp @ model.body_mat[b]
+        for j in np.nonzero(model.jnt_body == b)[0]:
+            anchor[j], axis[j] = pos + R @ model.jnt_pos[j], R @ model.jnt_axis[j]
+            if model.jnt_type[j] == SLIDE:
+                pos = pos + axis[j] * q[j]
+            else:
+                R = R @ axisangle_to_mat(model.jnt_axis[j], q[j])
+                pos = anchor[j] - R @ model.jnt_pos[j]
+        xpos[b], xmat[b] = pos, R
+    return xpos, xmat, anchor, axis
+
+
+def mass_matrix(model: TreeModel, q):
+    """M(q) from geometric Jacobians (used once, at qpos0, for dof_invweight0)."""
+    xpos, xmat, anchor, axis = kinematics(model, q)
+    nv = model.nv
+    M = np.diag(model.jnt_armature.astype(float))
+    for b in range(model.nb):
+        if model.body_mass[b] <= 0:
+            continue
+        com = xpos[b] + xmat[b] @ model.body_ipos[b]
+        Ri = xmat[b] @ model.body_imat[b]
+        Iw = Ri @ np.diag(model.body_inertia[b]) @ Ri.T
+        Jv, Jw = np.zeros((3, nv)), np.zeros((3, nv))
+        a = b
+        while a >= 0:
+            for j in np.nonzero(model.jnt_body == a)[0]:
+                if model.jnt_type[j] == SLIDE:
+                    Jv[:, j] = axis[j]
+                else:
+                    Jv[:, j], Jw[:, j] = np.cross(axis[j], com - anchor[j]), axis[j]
+            a = model.body_parent[a]
+        M += model.body_mass[b] * Jv.T @ Jv + Jw.T @ Iw @ Jw
+    return M
+
+
+def solref_to_kb(solref, solimp, timestep):
+    tc = max(float(solref[0]), 2.0 * timestep)
+    dr, dmax = float(solref[1]), float(solimp[1])
+    return 1.0 / max(1e-15, dmax * dmax * tc * tc * dr * dr), 2.0 / max(1e-15, dmax * tc)
+
+
+# ------------------------------------------------------------------------------------------------ kernel parameters
+# One LINK per dof (a body with several joints becomes a run of links, all but the last massless).  Per link, doubles:
+LK_RFIX, LK_OFF, LK_AXIS, LK_MASS, LK_COM, LK_IC, LK_RIN, LK_BOX = 0, 9, 12, 15, 16, 19, 25, 34
+LK_ARM, LK_DAMP, LK_STIFF, LK_SREF, LK_LO, LK_HI, LK_INVW, LK_SOLK, LK_SOLB, LK_SOLIMP = 37, 38, 39, 40, 41, 42, 43, 44, 45, 46
+LK_GEAR, LK_CLO, LK_CHI, LK_STRIDE = 51, 52, 53, 54
+# per link, ints: parent link, joint type, limited, actuator index (-1 = none), carries a body
+LI_PARENT, LI_TYPE, LI_LIMITED, LI_ACT, LI_BODY, LI_STRIDE = 0, 1, 2, 3, 4, 5
+# globals (doubles): timestep, gravity[3], density, viscosity
+G_DT, G_GRAV, G_RHO, G_VISC, G_STRIDE = 0, 1, 4, 5, 6
+MAX_LINKS = 12
+
+
+def pack_links(model: TreeModel):
+    """Lower the body / joint tree to the kernel's link arrays (see ``csrc/tree_model.h`` for the same offsets)."""
+    nv = model.nv
+    if nv > MAX_LINKS:
+        raise UnsupportedMjcf("%d dofs > %d" % (nv, MAX_LINKS))
+    P = np.zeros((nv, LK_STRIDE))
+    I = np.zeros((nv, LI_STRIDE), np.int32)
+    last_of_body = {}
+    for j in range(nv):
+        last_of_body[int(model.jnt_body[j])] = j
+    first_seen = set()
+    for j in range(nv):
+        b = int(model.jnt_body[j])
+        if b not in first_seen:                       # first joint of its body: hangs off the parent body's last link
+            first_seen.add(b)
+            pb = int(model.body_parent[b])
+            if pb < 0:
+                parent, base = -1, np.zeros(3)
+            else:
+                parent, base = last_of_body[pb], model.jnt_pos[last_of_body[pb]]
+            Rfix = model.body_mat[b]
+            off = model.body_pos[b] - base + Rfix @ model.jnt_pos[j]
+        else:                                          # next joint of the same body
+            parent, Rfix, off = j - 1, np.eye(3), model.jnt_pos[j] - model.jnt_pos[j - 1]
+        P[j, LK_RFIX:LK_RFIX + 9] = Rfix.reshape(9)
+        P[j, LK_OFF:LK_OFF + 3] = off
+        P[j, LK_AXIS:LK_AXIS + 3] = model.jnt_axis[j]
+        I[j, LI_PARENT], I[j, LI_TYPE], I[j, LI_LIMITED], I[j, LI_ACT] = parent, model.jnt_type[j], model.jnt_limited[j], -1
+        if last_of_body[b] == j and model.body_mass[b] > 0:
+            I[j, LI_BODY] = 1
+            P[j, LK_MASS] = model.body_mass[b]
+            P[j, LK_COM:LK_COM + 3] = model.body_ipos[b] - model.jnt_pos[j]
+            Rin = model.body_imat[b]
+            Ic = Rin @ np.diag(model.body_inertia[b]) @ Rin.T
+            P[j, LK_IC:LK_IC + 6] = [Ic[0, 0], Ic[1, 1], Ic[2, 2], Ic[0, 1], Ic[0, 2], Ic[1, 2]]
+            P[j, LK_RIN:LK_RIN + 9] = Rin.T.reshape(9)           # rows = inertial axes in link coordinates
+            In = model.body_inertia[b]
+            P[j, LK_BOX:LK_BOX + 3] = [math.sqrt(max(1e-15, In[1] + In[2] - In[0]) / model.body_mass[b] * 6.0),
+                                       math.sqrt(max(1e-15, In[0] + In[2] - In[1]) / model.body_mass[b] * 6.0),
+                                       math.sqrt(max(1e-15, In[0] + In[1] - In[2]) / model.body_mass[b] * 6.0)]
+        K, B = solref_to_kb(model.jnt_solref[j], model.jnt_solimp[j], model.timestep)
+        P[j, LK_ARM], P[j, LK_DAMP], P[j, LK_STIFF], P[j, LK_SREF] = (model.jnt_armature[j], model.jnt_damping[j],
+                                                                      model.jnt_stiffness[j], model.jnt_springref[j])
+        P[j, LK_LO], P[j, LK_HI], P[j, LK_INVW], P[j, LK_SOLK], P[j, LK_SOLB] = (model.jnt_range[j, 0], model.jnt_range[j, 1],
+                                                                               model.dof_invweight0[j], K, B)
+        P[j, LK_SOLIMP:LK_SOLIMP + 5] = model.jnt_solimp[j]
+    for a in range(model.nu):
+        j = int(model.act_dof[a])
+        if I[j, LI_ACT] >= 0:
+            raise UnsupportedMjcf("two motors on one joint")
+        I[j, LI_ACT] = a
+        P[j, LK_GEAR] = model.act_gear[a]
+        lo, hi = (model.act_ctrlrange[a] if model.act_ctrllimited[a] else (-np.inf, np.inf))
+        P[j, LK_CLO], P[j, LK_CHI] = lo, hi
+    G = np.zeros(G_STRIDE)
+    G[G_DT], G[G_GRAV:G_GRAV + 3], G[G_RHO], G[G_VISC] = model.timestep, model.gravity, model.density, model.viscosity
+    return P, I, G
+
+
+# ------------------------------------------------------------------------------------------------ shipped models
+def swimmer_mjcf(radii=(0.07, 0.065, 0.06, 0.055, 0.05), half_length=0.15, spacing=0.3, joint_range=1.5, gear=20.0,
+                 timestep=0.005, viscosity=0.000894, density=1000.0, height=0.03) -> str:
+    """MJCF text of the reference's ``Swimmer-v0`` model (``mjmpc/envs/assets/xml/swimmer.xml``), physics only: a
+    torso on two slides and a hinge (planar base) followed by ``len(radii) - 1`` capsule links on limited z hinges
+    with geared motors, in a fluid.  ``/root/reference`` does not travel to the GPU box, so the model is restated
+    as this parameter list; tests/test_tree_cpu.py compares its compilation with the reference file's."""
+    n = len(radii)
+    geom = '<geom type="capsule" pos="%g 0 0" quat="0.707 0 -0.707 0" size="%g %g"/>'
+    parts = ['<mujoco model="swimmer"><compiler inertiafromgeom="true" angle="radian"/>',
+             '<default><joint limited="true" range="%g %g"/><motor ctrllimited="true" ctrlrange="-1 1"/></default>'
+             % (-joint_range, joint_range),
+             '<option timestep="%g" viscosity="%g" density="%g"/>' % (timestep, viscosity, density),
+             '<worldbody><body name="torso" pos="0 0 %g">' % height,
+             '<joint type="slide" axis="1 0 0" limited="false"/><joint type="slide" axis="0 1 0" limited="false"/>',
+             '<joint type="hinge" axis="0 0 1" limited="false"/>', geom % (half_length, radii[0], half_length)]
+    for i in range(1, n):
+        parts.append('<body name="link%d" pos="%g 0 0"><joint name="j%d" type="hinge" axis="0 0 1"/>' % (i, spacing, i))
+        parts.append(geom % (half_length, radii[i], half_length))
+    parts.append("</body>" * n + "</worldbody><actuator>")
+    parts += ['<motor joint="j%d" gear="%g"/>' % (i, gear) for i in range(1, n)]
+    parts.append("</actuator></mujoco>")
+    return "".join(parts)

@@ -1,0 +1,180 @@
+"""SURVEY §8 f-3 on the CPU: the MJCF-subset compiler, the C oracle of the tree kernel (oracle/tree_step.c) against
+the committed vectors of the independent restatement (oracle/tree_ref.py -> tests/golden/tree_pin.npz), closed forms
+for the fluid model and energy, and the rejection of models outside the subset."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from mjmpc_b200.envs import mjcf_tree as T
+from oracle.tree_step import TreeOracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIX = os.path.join(HERE, "fixtures")
+REF_XML = "/root/reference/mjmpc/envs/assets/xml"
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF_XML), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(os.path.join(HERE, "golden", "tree_pin.npz"))
+
+
+def _model(name):
+    if name == "swimmer":
+        return T.compile_mjcf_string(T.swimmer_mjcf(), allow_contacts="ignore")
+    return T.compile_mjcf(os.path.join(FIX, name + ".xml"))
+
+
+def _rel(a, b):
+    b = np.asarray(b, float)
+    return float(np.abs(np.asarray(a, float) - b).max() / (1.0 + np.abs(b).max()))
+
+
+@pytest.mark.parametrize("name", ["swimmer", "tree3d", "tree3d_weld"])
+def test_c_oracle_and_compiled_constants_match_the_independent_restatement(g, name):
+    m = _model(name)
+    np.testing.assert_allclose(m.dof_invweight0, g[name + "_invweight0"], rtol=1e-10)
+    if name != "tree3d_weld":                       # the compiler merges the welded body, tree_ref keeps it
+        np.testing.assert_allclose(m.body_mass, g[name + "_mass"], rtol=1e-13)
+        np.testing.assert_allclose(np.sort(m.body_inertia, axis=1), np.sort(g[name + "_inertia"], axis=1), rtol=1e-12)
+    o = TreeOracle(m, T.solref_to_kb)
+    n = len(g[name + "_q"])
+    assert int((g[name + "_nefc"] > 0).sum()) >= 25
+    worst = {}
+    for i in range(n):
+        r = o.substep(g[name + "_q"][i], g[name + "_v"][i], g[name + "_u"][i])
+        assert r["nefc"] == int(g[name + "_nefc"][i])
+        for k in ("M", "bias", "passive", "actuation", "constraint", "qacc"):
+            worst[k] = max(worst.get(k, 0.0), _rel(r[k], g[name + "_" + k][i]))
+        worst["q"] = max(worst.get("q", 0.0), _rel(r["q"], g[name + "_q2"][i]))
+        worst["v"] = max(worst.get("v", 0.0), _rel(r["v"], g[name + "_v2"][i]))
+    assert max(worst.values()) < 1e-10, worst
+
+
+def test_swimmer_rollout_and_reward_match_the_independent_restatement(g):
+    m = _model("swimmer")
+    o = TreeOracle(m, T.solref_to_kb)
+    acts = g["swimmer_roll_actions"]
+    r = o.rollout(g["swimmer_roll_state0"], acts, np.zeros((1,) + acts.shape), frame_skip=4)
+    assert _rel(r["states"][0], g["swimmer_roll_states"]) < 1e-10
+    assert _rel(-r["costs"][0], g["swimmer_roll_rewards"]) < 1e-9          # swimmer.py:10-19
+
+
+@needs_ref
+def test_generated_swimmer_equals_the_reference_file():
+    """The parameter list in swimmer_mjcf() IS mjmpc/envs/assets/xml/swimmer.xml as far as the physics goes."""
+    a = _model("swimmer")
+    b = T.compile_mjcf(os.path.join(REF_XML, "swimmer.xml"), allow_contacts="ignore")
+    for f in ("body_parent", "body_pos", "body_mat", "body_mass", "body_ipos", "body_imat", "body_inertia", "jnt_type",
+              "jnt_body", "jnt_pos", "jnt_axis", "jnt_limited", "jnt_damping", "jnt_armature", "jnt_stiffness", "act_dof",
+              "act_gear", "act_ctrlrange", "gravity", "dof_invweight0"):
+        np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f)
+    np.testing.assert_array_equal(a.jnt_range[a.jnt_limited], b.jnt_range[b.jnt_limited])
+    assert (a.timestep, a.density, a.viscosity) == (b.timestep, b.density, b.viscosity) == (0.005, 1000.0, 0.000894)
+    with pytest.raises(T.UnsupportedMjcf, match="contacts"):
+        T.compile_mjcf(os.path.join(REF_XML, "swimmer.xml"))             # non-adjacent capsules may touch: opt-in only
+    assert b.ignored and "contacts dropped" in b.ignored[0]
+
+
+@needs_ref
+def test_half_cheetah_is_rejected_not_simulated_wrongly():
+    """half_cheetah.xml needs ground contact with friction cones: outside the subset, and the compiler says so."""
+    with pytest.raises(T.UnsupportedMjcf, match="contacts"):
+        T.compile_mjcf(os.path.join(REF_XML, "half_cheetah.xml"))
+    m = T.compile_mjcf(os.path.join(REF_XML, "half_cheetah.xml"), allow_contacts="ignore")   # the tree itself compiles
+    assert m.nv == 9 and m.nu == 6 and abs(m.body_mass.sum() - 14.0) < 1e-12                # settotalmass
+    assert list(m.jnt_type[:3]) == [T.SLIDE, T.SLIDE, T.HINGE] and m.jnt_stiffness[3] == 240.0
+
+
+@pytest.mark.parametrize("bad,why", [
+    ('<joint type="ball"/>', "joint type"), ('<joint type="hinge" frictionloss="0.1"/>', "frictionloss"),
+    ('<freejoint/>', "free joint"), ('<joint type="hinge" ref="0.3"/>', "joint ref")])
+def test_unsupported_elements_raise(bad, why):
+    xml = ('<mujoco><compiler angle="radian"/><worldbody><body>%s<geom type="sphere" size="0.1" contype="0" conaffinity="0"/>'
+           '</body></worldbody></mujoco>' % bad)
+    with pytest.raises(T.UnsupportedMjcf, match=why):
+        T.compile_mjcf_string(xml)
+    for opt, why2 in (('integrator="RK4"', "integrator"), ('wind="1 0 0"', "wind")):
+        with pytest.raises(T.UnsupportedMjcf, match=why2):
+            T.compile_mjcf_string('<mujoco><option %s/><worldbody><body><joint/><geom size="0.1" contype="0" conaffinity="0"/>'
+                                  '</body></worldbody></mujoco>' % opt)
+
+
+def test_welded_body_in_a_fluid_is_rejected():
+    xml = open(os.path.join(FIX, "tree3d_weld.xml")).read().replace('density="0" viscosity="0"', 'density="10" viscosity="0"')
+    with pytest.raises(T.UnsupportedMjcf, match="welded"):
+        T.compile_mjcf_string(xml)
+
+
+def _slider(rho, mu, r=0.05, half=0.2):
+    return ('<mujoco><compiler angle="radian" inertiafromgeom="true"/><option timestep="0.001" gravity="0 0 0" density="%g" '
+            'viscosity="%g"/><worldbody><body><joint type="slide" axis="1 0 0"/><joint type="hinge" axis="0 0 1"/>'
+            '<geom type="capsule" size="%g %g" contype="0" conaffinity="0"/></body></worldbody></mujoco>' % (rho, mu, r, half))
+
+
+def test_fluid_forces_closed_form():
+    """One capsule (axis = z) sliding along x and spinning about z: mj_passive's inertia-box model by hand."""
+    rho, mu, r, half = 700.0, 0.3, 0.05, 0.2
+    m = T.compile_mjcf_string(_slider(rho, mu, r, half))
+    o = TreeOracle(m, T.solref_to_kb)
+    hh = 2 * half
+    mc, ms = 1000 * math.pi * r * r * hh, 1000 * 4 / 3 * math.pi * r ** 3
+    mass = mc + ms
+    It = mc * (3 * r * r + hh * hh) / 12 + ms * (0.4 * r * r + 0.25 * hh * hh + 0.375 * r * hh)
+    Ia = 0.5 * mc * r * r + 0.4 * ms * r * r
+    bx = by = math.sqrt((It + Ia - It) / mass * 6)
+    bz = math.sqrt((2 * It - Ia) / mass * 6)
+    d = (bx + by + bz) / 3
+    vx, wz = 1.7, -2.3
+    fx = -3 * math.pi * d * mu * vx - 0.5 * rho * by * bz * abs(vx) * vx
+    tz = -math.pi * d ** 3 * mu * wz - rho * bz * (bx ** 4 + by ** 4) * abs(wz) * wz / 64
+    res = o.substep(np.zeros(2), np.array([vx, wz]), np.zeros(0))
+    np.testing.assert_allclose(res["passive"], [fx, tz], rtol=1e-12)
+    np.testing.assert_allclose(res["qacc"], [fx / mass, tz / Ia], rtol=1e-12)
+
+
+def test_pendulum_energy_is_conserved_to_first_order():
+    xml = ('<mujoco><compiler angle="radian" inertiafromgeom="true"/><option timestep="0.0005"/><worldbody><body pos="0 0 1">'
+           '<joint type="hinge" axis="0 1 0"/><geom type="capsule" fromto="0 0 0 0.4 0 0" size="0.03" contype="0" '
+           'conaffinity="0"/><body pos="0.4 0 0"><joint type="hinge" axis="0 1 0"/><geom type="capsule" fromto="0 0 0 0.3 0 0" '
+           'size="0.02" contype="0" conaffinity="0"/></body></body></worldbody></mujoco>')
+    m = T.compile_mjcf_string(xml)
+    o = TreeOracle(m, T.solref_to_kb)
+
+    def energy(q, v):
+        xpos, xmat, _, _ = T.kinematics(m, q)
+        pe = sum(-m.body_mass[b] * (m.gravity @ (xpos[b] + xmat[b] @ m.body_ipos[b])) for b in range(m.nb))
+        return 0.5 * v @ T.mass_matrix(m, q) @ v + pe
+    q, v = np.array([0.3, -0.5]), np.array([0.0, 0.0])
+    e0 = energy(q, v)
+    for _ in range(2000):                                  # 1 s of a double pendulum falling under gravity
+        r = o.substep(q, v, np.zeros(0))
+        q, v = r["q"], r["v"]
+    assert np.abs(v).max() > 1.0                           # it really moved
+    assert abs(energy(q, v) - e0) < 2e-3 * abs(e0 - energy(np.array([math.pi / 2, 0.0]), np.zeros(2)))
+
+
+def test_kernel_layout_matches_the_python_packer():
+    """csrc/tree_model.h and mjcf_tree.py agree (host-only call into the library, no GPU work)."""
+    import ctypes as C
+    from mjmpc_b200 import _lib
+    try:
+        L = _lib.lib()
+    except _lib.MjbError:
+        pytest.skip("extension not built")
+    out = (C.c_int * 34)()
+    L.mjb_tree_layout(out)
+    assert list(out)[:4] == [T.LK_RFIX, T.LK_OFF, T.LK_AXIS, T.LK_MASS]
+    assert out[21] == T.LK_STRIDE and out[27] == T.LI_STRIDE and out[32] == T.G_STRIDE and out[33] == T.MAX_LINKS
+
+
+def test_pack_links_shapes_and_topology():
+    m = _model("tree3d")
+    P, I, G = T.pack_links(m)
+    assert P.shape == (7, T.LK_STRIDE) and I.shape == (7, T.LI_STRIDE) and G.shape == (T.G_STRIDE,)
+    assert list(I[:, T.LI_PARENT]) == [-1, 0, 1, 2, 3, 1, 5]            # two branches off the base's last link
+    assert list(I[:, T.LI_BODY]) == [0, 1, 0, 1, 1, 1, 1]               # massless links of the multi-joint bodies
+    sw = T.pack_links(_model("swimmer"))[1]
+    assert list(sw[:, T.LI_PARENT]) == [-1, 0, 1, 2, 3, 4, 5] and list(sw[:, T.LI_ACT]) == [-1, -1, -1, 0, 1, 2, 3]

@@ -1,0 +1,160 @@
+"""K11: the runtime-parameterised tree rollout kernel against the CPU oracle (oracle/tree_step.c),
+through the C ABI (mjb_tree_model_create / mjb_rollout_tree) and through the reference-facing env surface.
+Tolerance: 1e-8 relative on costs / states over whole rollouts (FP64 on both sides, different formulations; the
+measured agreement is ~1e-12), the bar SURVEY §8(c) sets for the MuJoCo dynamics."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mjmpc_b200.envs import mjcf_tree as T
+from mjmpc_b200.envs.gpu_tree_env import GpuSwimmerEnv, GpuTreeVecEnv
+from oracle.tree_step import TreeOracle
+
+pytestmark = pytest.mark.gpu
+FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures")
+TOL = 1e-8
+
+
+def _rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / (1.0 + np.abs(np.asarray(b)).max()))
+
+
+def _compare(env, oracle, state, mean, noise, nthreads=8):
+    K, H, nu = noise.shape
+    nv = env.nv
+    env.set_env_state({"qpos": state[:nv], "qvel": state[nv:]})
+    out = env.rollout_device(K, H, torch.as_tensor(mean, device=env.device), torch.as_tensor(noise, device=env.device),
+                             want_states=True, want_obs=True, want_nefc=True)
+    ref = oracle.rollout(state, mean, noise, env.frame_skip, env.fwd_dof, env.w_fwd, env.w_ctrl, nthreads=nthreads)
+    costs, states = out["costs"].cpu().numpy(), out["states"].cpu().numpy()
+    assert np.array_equal(out["actions"].cpu().numpy(), ref["actions"])          # mean + noise, recorded unclipped
+    assert _rel(states, ref["states"]) < TOL
+    assert _rel(costs, ref["costs"]) < TOL
+    obs = out["next_observations"].cpu().numpy()
+    s = env.obs_qpos_start
+    assert np.array_equal(obs[..., :nv - s], states[..., s:nv]) and np.array_equal(obs[..., nv - s:], states[..., nv:])
+    return int(out["nefc"].cpu().numpy().sum()), ref["nefc"], _rel(states, ref["states"])
+
+
+@pytest.fixture(scope="module")
+def swimmer():
+    env = GpuTreeVecEnv.swimmer()
+    yield env, TreeOracle(env.model, T.solref_to_kb)
+    env.close()
+
+
+def test_swimmer_rollout_matches_oracle(swimmer):
+    env, oracle = swimmer
+    rng = np.random.default_rng(0)
+    K, H = 192, 12
+    state = np.concatenate([rng.uniform(-.1, .1, 7), rng.uniform(-.1, .1, 7)])
+    mean = rng.normal(0, 0.3, (H, 4))
+    noise = rng.normal(0, 0.6, (K, H, 4))
+    noise[0] = 0.0
+    nefc, nefc_ref, err = _compare(env, oracle, state, mean, noise)
+    assert nefc == nefc_ref
+    assert err < 1e-10
+
+
+def test_swimmer_limits_binding(swimmer):
+    """Controls pinned at the clamp drive the joints into their soft limits: most substeps carry limit rows."""
+    env, oracle = swimmer
+    rng = np.random.default_rng(1)
+    K, H = 64, 40
+    state = np.zeros(14)
+    state[3:7] = [1.3, -1.4, 1.45, -1.2]
+    mean = np.tile(np.array([2.0, -2.0, 2.0, -2.0]), (H, 1))          # beyond ctrlrange: clamped to +-1 inside
+    noise = rng.normal(0, 0.2, (K, H, 4))
+    nefc, nefc_ref, _ = _compare(env, oracle, state, mean, noise)
+    assert nefc == nefc_ref and nefc > K * H            # limits really bind
+
+
+def test_swimmer_ragged_and_single_particle(swimmer):
+    env, oracle = swimmer
+    rng = np.random.default_rng(2)
+    for K, H in ((1, 1), (77, 3), (130, 2)):
+        state = rng.uniform(-.3, .3, 14)
+        _compare(env, oracle, state, rng.normal(0, 0.5, (H, 4)), rng.normal(0, 0.5, (K, H, 4)), nthreads=2)
+
+
+@pytest.mark.parametrize("fixture", ["tree3d.xml", "tree3d_weld.xml"])
+def test_branched_3d_tree_matches_oracle(fixture):
+    """The run-time-topology instantiation: branches, skew axes, anchors off the body origin, rotated frames, slides
+    under hinges, gravity, springs, dampers (implicit Euler), armature, per-joint solref / solimp, a fluid or a weld."""
+    model = T.compile_mjcf(os.path.join(FIX, fixture))
+    env = GpuTreeVecEnv(model, frame_skip=3, fwd_dof=1, w_fwd=0.7, w_ctrl=0.05, obs_qpos_start=1)
+    oracle = TreeOracle(model, T.solref_to_kb)
+    rng = np.random.default_rng(3)
+    K, H = 96, 10
+    state = np.concatenate([rng.uniform(-.4, .4, 7), rng.normal(0, 1.0, 7)])
+    nefc, nefc_ref, _ = _compare(env, oracle, state, rng.normal(0, 0.5, (H, 4)), rng.normal(0, 1.0, (K, H, 4)))
+    assert nefc == nefc_ref and nefc > 0
+    env.close()
+
+
+def test_batched_controllers_share_one_launch(swimmer):
+    env, oracle = swimmer
+    rng = np.random.default_rng(4)
+    n_ctrl, per, H = 3, 32, 5
+    states = rng.uniform(-.2, .2, (n_ctrl, 14))
+    env.set_env_state([{"qpos": s[:7], "qvel": s[7:]} for s in states])
+    mean = rng.normal(0, 0.3, (n_ctrl, H, 4))
+    noise = rng.normal(0, 0.5, (n_ctrl * per, H, 4))
+    out = env.rollout_device(n_ctrl * per, H, torch.as_tensor(mean, device=env.device),
+                             torch.as_tensor(noise, device=env.device))
+    for c in range(n_ctrl):
+        ref = oracle.rollout(states[c], mean[c], noise[c * per:(c + 1) * per], 4)
+        assert _rel(out["costs"][c * per:(c + 1) * per].cpu().numpy(), ref["costs"]) < TOL
+
+
+def test_reference_rollout_signature(swimmer):
+    """GymEnvWrapper.rollout's return value (gym_env_wrapper.py:80-156): obs[:, 0] is the observation of the set state."""
+    env, oracle = swimmer
+    rng = np.random.default_rng(5)
+    state = rng.uniform(-.1, .1, 14)
+    env.set_env_state({"qpos": state[:7], "qvel": state[7:]})
+    K, H = 16, 4
+    mean, noise = rng.normal(0, 0.3, (H, 4)), rng.normal(0, 0.3, (K, H, 4))
+    obs, rew, act, done, info, nobs = env.rollout(K, H, mean, noise)
+    ref = oracle.rollout(state, mean, noise, 4)
+    assert obs.shape == (K, H, 12) and rew.shape == (K, H) and act.shape == (K, H, 4) and not done.any()
+    assert np.allclose(obs[:, 0], np.concatenate([state[2:7], state[7:]]))
+    assert np.array_equal(obs[:, 1:], nobs[:, :-1])
+    assert _rel(rew, -ref["costs"]) < TOL
+    with pytest.raises(NotImplementedError):
+        env.rollout(K, H, mean, noise, mode="closed_loop_linear")
+
+
+def test_mppi_swims_forward():
+    """MPPI on the plant (swimmer.py reward = forward velocity): the planner makes the swimmer advance along +x."""
+    from mjmpc_b200.control import MPPI
+    plant = GpuSwimmerEnv(seed=0)
+    sim = GpuTreeVecEnv.swimmer()
+    H, K = 20, 256
+    ctrl = MPPI(d_state=14, d_obs=12, d_action=4, action_lows=sim.action_lows, action_highs=sim.action_highs, horizon=H,
+                init_cov=0.5, base_action="null", num_particles=K, lam=0.05, step_size=1.0, alpha=0, gamma=1.0, n_iters=1,
+                set_sim_state_fn=sim.set_env_state, rollout_fn=sim.rollout_fn, sample_mode="mean", batch_size=1, seed=0,
+                filter_coeffs=[1.0, 0.0, 0.0])
+    plant.reset(seed=0)
+    x0 = plant.qpos[0]
+    total = 0.0
+    for _ in range(60):
+        a, _ = ctrl.optimize(plant.get_env_state())
+        _, r, _, info = plant.step(a)
+        total += r
+    assert plant.qpos[0] - x0 > 0.15, (plant.qpos[0] - x0, total)
+    assert np.all(np.abs(plant.qpos[3:]) < 1.7)
+    plant.close(); sim.close()
+
+
+def test_bad_arguments_are_rejected(swimmer):
+    env, _ = swimmer
+    with pytest.raises(ValueError):
+        env.rollout_device(8, 2, torch.zeros(2, 4, dtype=torch.float64, device=env.device),
+                           torch.zeros(8, 2, 3, dtype=torch.float64, device=env.device))
+    env.set_env_state([{"qpos": np.zeros(7), "qvel": np.zeros(7)}] * 3)
+    with pytest.raises(ValueError):
+        env.rollout_device(8, 2, torch.zeros(3, 2, 4, dtype=torch.float64, device=env.device), None)   # 8 % 3 != 0
+    env.set_env_state({"qpos": np.zeros(7), "qvel": np.zeros(7)})
