@@ -18,6 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mjmpc_b200.envs.gpu_reacher_env import GpuContinualReacherEnv, GpuReacherEnv          # noqa: E402
 from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv            # noqa: E402
 from mjmpc_b200.envs.gpu_pendulum import GpuPendulumEnv, GpuPendulumVecEnv    # noqa: E402
+from mjmpc_b200.envs.gpu_tree_env import GpuSwimmerEnv, GpuTreeVecEnv          # noqa: E402
 from mjmpc_b200.policies import MPCPolicy                           # noqa: E402
 
 
@@ -39,7 +40,7 @@ def load_policy_params(exp_params, controller_name, env):
 
 
 def main():
-    parser = argparse.ArgumentParser(description='Run an MPC algorithm on the GPU backend (reacher_7dof-v0, continual_reacher-v0, SimplePendulum-v0)')
+    parser = argparse.ArgumentParser(description='Run an MPC algorithm on the GPU backend (reacher_7dof-v0, continual_reacher-v0, SimplePendulum-v0, Swimmer-v0)')
     parser.add_argument('--config', type=str, required=True, help='yaml file with experiment parameters')
     parser.add_argument('--dyn_randomize_config', type=str, help='yaml file with dynamics randomization parameters')
     parser.add_argument('--controller', type=str, default='mppi', help='controller to run')
@@ -54,11 +55,12 @@ def main():
             dynamics_rand_params = yaml.load(file, Loader=yaml.FullLoader)
     # env name -> (plant, planner's rollout backend)                                mjmpc/envs/__init__.py:5-35
     plants = {'reacher_7dof-v0': (GpuReacherEnv, GpuReacherVecEnv), 'continual_reacher-v0': (GpuContinualReacherEnv, GpuReacherVecEnv),
-              'SimplePendulum-v0': (GpuPendulumEnv, GpuPendulumVecEnv)}
+              'SimplePendulum-v0': (GpuPendulumEnv, GpuPendulumVecEnv), 'Swimmer-v0': (GpuSwimmerEnv, GpuTreeVecEnv.swimmer)}
     if exp_params['env_name'] not in plants:
         raise NotImplementedError("only %s have a GPU plant; see DESIGN.md section 6" % sorted(plants))
     plant_cls, sim_cls = plants[exp_params['env_name']]
     reacher = sim_cls is GpuReacherVecEnv
+    swimmer = exp_params['env_name'] == 'Swimmer-v0'
     env = plant_cls()
     policy_params, num_cpu = load_policy_params(exp_params, args.controller, env)
     n_episodes = args.n_episodes or exp_params['n_episodes']
@@ -92,11 +94,13 @@ def main():
             obs, reward, done, info = env.step(action)
             ep_rewards[i] += reward
             infos.append(info.get('goal_achieved', False))
-            dists.append(np.linalg.norm(obs[17:20]) if reacher else abs(np.arctan2(obs[1], obs[0])))
+            dists.append(np.linalg.norm(obs[17:20]) if reacher else env.qpos[0] if swimmer else abs(np.arctan2(obs[1], obs[0])))
         trajectories.append(dict(env_infos=dict(goal_achieved=np.array(infos))))
         if reacher:
             print('episode %d: reward %.2f, hand-target distance %.3f -> %.3f, goal steps %d'
                   % (i, ep_rewards[i], dists[0], dists[-1], int(np.sum(infos))))
+        elif swimmer:
+            print('episode %d: reward %.2f, x position %.3f -> %.3f m' % (i, ep_rewards[i], dists[0], dists[-1]))
         else:
             print('episode %d: reward %.2f, |angle from upright| %.3f -> %.3f rad' % (i, ep_rewards[i], dists[0], dists[-1]))
     dt = time.time() - t0

@@ -67,6 +67,7 @@ class GpuTreeVecEnv:
         self.d_action, self.d_state, self.d_obs = model.nu, 2 * model.nv, 2 * model.nv - self.obs_qpos_start
         self.dt = model.timestep * self.frame_skip
         self._state = torch.zeros(1, 2 * self.nv, dtype=torch.float64, device=self.device)
+        self.state_generation = 0        # bumped when the state buffer is reallocated (captured CUDA graphs go stale)
         lim = np.where(model.act_ctrllimited[:, None], model.act_ctrlrange, np.array([[-1.0, 1.0]]))
         self.action_lows, self.action_highs = lim[:, 0].copy(), lim[:, 1].copy()
 
@@ -82,10 +83,17 @@ class GpuTreeVecEnv:
             state_dicts = [state_dicts]
         rows = np.stack([np.concatenate([np.asarray(s["qpos"], float).reshape(self.nv),
                                          np.asarray(s["qvel"], float).reshape(self.nv)]) for s in state_dicts])
-        self._state = torch.from_numpy(rows).to(self.device)
+        self.set_env_state_device(torch.from_numpy(rows))
 
     def set_env_state_device(self, state: torch.Tensor):
-        self._state = state.reshape(-1, 2 * self.nv).to(self.device, torch.float64).contiguous()
+        """(n_ctrl, 2 nv) rows of qpos, qvel.  The buffer is persistent while the row count stays the same, so a
+        captured CUDA graph of the controller step keeps reading the right memory."""
+        state = state.reshape(-1, 2 * self.nv)
+        if state.shape == self._state.shape:
+            self._state.copy_(state)
+        else:
+            self._state = state.to(self.device, torch.float64).contiguous().clone()
+            self.state_generation += 1
 
     def reset(self):
         pass

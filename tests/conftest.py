@@ -23,7 +23,7 @@ def pytest_configure(config):
 # `-m gpu` tests the host emulation cannot run (no CUDA graphs, no shim in child processes, no NCCL): skipped
 # under MJB_TEST_EMU=1 only.  _EMU_SLOW: tests too slow for the default CPU suite (MJB_TEST_EMU_ALL=1 keeps them)
 _EMU_IMPOSSIBLE = {
-    "test_cuda_graph_step_equals_eager": "CUDA graphs are not emulated",
+    "test_cuda_graph_step_equals_eager": "CUDA graphs are not emulated",      # (prefix: the reacher and the swimmer test)
     "test_graph_replay_mixed_with_eager_calls_and_a_plant_model": "CUDA graphs are not emulated",
     "test_fused_noise_controller_equals_two_kernel_path[True]": "CUDA graphs are not emulated",
     "test_example_driver_runs": "child process without the emulation shim",      # (prefix: both driver tests)

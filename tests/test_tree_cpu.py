@@ -156,6 +156,24 @@ def test_pendulum_energy_is_conserved_to_first_order():
     assert abs(energy(q, v) - e0) < 2e-3 * abs(e0 - energy(np.array([math.pi / 2, 0.0]), np.zeros(2)))
 
 
+def test_linear_momentum_drift_is_first_order_in_the_timestep():
+    """No fluid, planar base on two slides: x / y momentum (the slides' generalised momenta) is conserved by the
+    continuous dynamics whatever the joint torques and limit forces do; semi-implicit Euler drifts O(h)."""
+    drift = []
+    for h, n in ((0.005, 100), (0.0005, 1000)):
+        m = T.compile_mjcf_string(T.swimmer_mjcf(density=0.0, viscosity=0.0, timestep=h), allow_contacts="ignore")
+        o = TreeOracle(m, T.solref_to_kb)
+        rng = np.random.default_rng(0)
+        q, v = rng.uniform(-.3, .3, 7), rng.normal(0, 1, 7)
+        u = np.array([1, -1, .5, -.7])
+        p0 = (T.mass_matrix(m, q) @ v)[:2].copy()
+        for t in range(n):
+            r = o.substep(q, v, u * np.sin(40 * h * t))
+            q, v = r["q"], r["v"]
+        drift.append(np.abs((T.mass_matrix(m, q) @ v)[:2] - p0).max())
+    assert drift[0] > 1.0 and 7.0 < drift[0] / drift[1] < 13.0, drift
+
+
 def test_kernel_layout_matches_the_python_packer():
     """csrc/tree_model.h and mjcf_tree.py agree (host-only call into the library, no GPU work)."""
     import ctypes as C

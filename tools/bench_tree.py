@@ -1,0 +1,69 @@
+"""Secondary measurement (not the driver's bench contract): the tree rollout kernel (K11) and the MPPI
+step on the reference's Swimmer-v0 model.  One JSON line per size: kernel time by CUDA events, particle-steps/s
+(one particle-step = frame_skip 4 substeps + reward), the MPC step through the controller (CUDA graph), and the CPU
+oracle (oracle/tree_step.c, all host threads) on a bounded sample of the same workload.
+    python tools/bench_tree.py [--sizes 4096,65536] [--horizon 32]"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from mjmpc_b200.control import MPPI
+from mjmpc_b200.envs import mjcf_tree as T
+from mjmpc_b200.envs.gpu_tree_env import GpuTreeVecEnv
+
+sizes = [int(x) for x in (sys.argv[sys.argv.index("--sizes") + 1] if "--sizes" in sys.argv else "4096,65536").split(",")]
+H = int(sys.argv[sys.argv.index("--horizon") + 1]) if "--horizon" in sys.argv else 32
+rng = np.random.default_rng(0)
+env = GpuTreeVecEnv.swimmer()
+state = dict(qpos=rng.uniform(-.1, .1, 7), qvel=rng.uniform(-.1, .1, 7))
+env.set_env_state(state)
+for K in sizes:
+    mean = torch.as_tensor(rng.normal(0, 0.3, (H, 4)), device=env.device)
+    noise = torch.as_tensor(rng.normal(0, 0.5, (K, H, 4)), device=env.device)
+    for _ in range(3):
+        out = env.rollout_device(K, H, mean, noise)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        out = env.rollout_device(K, H, mean, noise)
+    e1.record()
+    torch.cuda.synchronize()
+    k_ms = e0.elapsed_time(e1) / reps
+    c = MPPI(d_state=14, d_obs=12, d_action=4, action_lows=env.action_lows, action_highs=env.action_highs, horizon=H,
+             init_cov=0.4, base_action="null", num_particles=K, lam=0.1, step_size=1.0, alpha=1, gamma=1.0, n_iters=1,
+             set_sim_state_fn=env.set_env_state, rollout_fn=env.rollout_fn, seed=3, filter_coeffs=[0.25, 0.8, 0.0])
+    c.enable_cuda_graph(state)
+    for _ in range(5):
+        c.step_device(state)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(50):
+        c.step_device(state)
+    e1.record()
+    torch.cuda.synchronize()
+    step_ms = e0.elapsed_time(e1) / 50
+    t0 = time.perf_counter()
+    for _ in range(50):
+        c.optimize(state)
+    e2e_ms = (time.perf_counter() - t0) / 50 * 1e3
+    # CPU oracle on a bounded sample
+    from oracle.tree_step import TreeOracle
+    o = TreeOracle(env.model, T.solref_to_kb)
+    ks = min(K, 2048)
+    nz = noise[:ks].cpu().numpy()
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    ref = o.rollout(np.concatenate([state["qpos"], state["qvel"]]), mean.cpu().numpy(), nz, 4, nthreads=min(cores, 64))
+    cpu_s = time.perf_counter() - t0
+    err = float(np.abs(out["costs"][:ks].cpu().numpy() - ref["costs"]).max() / (1 + np.abs(ref["costs"]).max()))
+    print(json.dumps(dict(config="Swimmer-v0 tree rollout + MPPI", num_particles=K, horizon=H, frame_skip=4,
+                          rollout_kernel_ms=k_ms, particle_steps_per_s=K * H / (k_ms * 1e-3), mpc_step_ms=step_ms,
+                          mpc_hz=1e3 / step_ms, e2e_ms=e2e_ms, rel_err_vs_oracle=err,
+                          cpu_oracle=dict(particle_steps_per_s=ks * H / cpu_s, cores=min(cores, 64), sample="%d particles x %d steps" % (ks, H)))),
+          flush=True)
