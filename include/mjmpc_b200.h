@@ -134,9 +134,16 @@ int mjb_rollout_lqr(const mjb_lqr_args* a, void* stream);
  * No contacts, frictionloss, tendons, free / ball joints (the compiler rejects such models). */
 typedef struct mjb_tree_model mjb_tree_model;
 mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* link_params, const int* link_ints,
-                                      const double* globals, int device);   /* NULL + mjb_last_error on failure */
+                                      const double* globals, const double* planar_params, const int* planar_anc,
+                                      const double* planar_gravity, int device);   /* NULL + mjb_last_error on failure */
 void mjb_tree_model_destroy(mjb_tree_model* m);
-void mjb_tree_layout(int* out34);   /* the 34 layout constants of csrc/tree_model.h, in declaration order */
+void mjb_tree_layout(int* out45);   /* the 45 layout constants of csrc/tree_model.h + rollout_tree_planar.cuh, in order */
+/* PLANAR MECHANISMS (all hinge axes parallel, all slides perpendicular to them -- swimmer.xml and half_cheetah.xml are):
+ * with the three planar blocks of mjcf_tree.pack_planar -- planar_params (nv, PK_STRIDE), planar_anc (nv) ancestor bit
+ * masks, planar_gravity (2); NULL otherwise -- rollouts of 7- and 9-dof models run the planar instantiation (3-vectors
+ * in place of spatial 6-vectors, everything in registers).  Same results to rounding; mjb_tree_use_planar(0) forces
+ * the general instantiation (tests compare the two), a negative argument only queries; returns the previous value. */
+int mjb_tree_use_planar(int on);
 typedef struct {
     int K, H, frame_skip, particles_per_ctrl;
     int fwd_dof, obs_qpos_start;

@@ -228,7 +228,7 @@ BASE_ACTIONS = {"null": 0, "repeat": 1, "random": 2}
 
 EXPORTS += [
     "mjb_rollout_pendulum", "mjb_rollout_lqr", "mjb_tree_model_create", "mjb_tree_model_destroy", "mjb_tree_layout",
-    "mjb_rollout_tree", "mjb_generate_noise", "mjb_cost_to_go",
+    "mjb_rollout_tree", "mjb_tree_use_planar", "mjb_generate_noise", "mjb_cost_to_go",
     "mjb_softmax_scratch_doubles", "mjb_softmax_partial_doubles", "mjb_softmax_partials", "mjb_softmax_update_fused",
     "mjb_instances_update_batched", "mjb_cov_add_diag_batched",
     "mjb_softmax_combine", "mjb_softmax_exchange_combine", "mjb_softmax_weights",

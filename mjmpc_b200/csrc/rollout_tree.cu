@@ -21,12 +21,15 @@
 // swimmer is a serial chain of 7 dofs); <run-time nv <= 12, any tree> with the per-link state in local memory.
 #include "common.h"
 #include "tree_model.h"
+#include <stdlib.h>
 
 struct mjb_tree_model {
-    int device, nv, nu, serial;
+    int device, nv, nu, serial, planar;
     double* d_lk;   // nv x LK_STRIDE
     int* d_li;      // nv x LI_STRIDE
     double* d_g;    // TG_STRIDE
+    double* d_pk;   // planar mechanisms: nv x PK_STRIDE, then the in-plane gravity (2)
+    int* d_anc;     // planar mechanisms: ancestor bit masks (nv)
 };
 
 namespace mjb {
@@ -61,6 +64,33 @@ TR_HD void symv(double* r, const double* S, const double* v) {        // S = xx 
     r[0] = x; r[1] = y; r[2] = z;
 }
 
+// sin / cos of a joint angle: two-term Cody-Waite reduction by pi/2 and the fdlibm kernel polynomials (~1 ulp for
+// |x| < 1e5 rad; the same routine as the reacher kernel's).  Beyond that an out-of-line call of the library routine:
+// its huge-argument path is ~100 instructions per call site and would sit 5-9 times in the unrolled loops.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+void sincos_far(double x, double* s, double* c) { sincos(x, s, c); }
+TR_HD void sincos_lean(double x, double* s, double* c) {
+    if (fabs(x) > 1e5) { sincos_far(x, s, c); return; }
+    const double kd = rint(x * 6.36619772367581382433e-01);
+    double r = fma(kd, -1.57079632673412561417e+00, x);
+    r = fma(kd, -6.07710050650619224932e-11, r);
+    const double z = r * r;
+    const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08),
+                                                2.75573137070700676789e-06), -1.98412698298579493134e-04),
+                                 8.33333333332248946124e-03), -1.66666666666666324348e-01);
+    const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09),
+                                                -2.75573143513906633035e-07), 2.48015872894767294178e-05),
+                                 -1.38888888888741095749e-03), 4.16666666666666019037e-02);
+    const double sr = fma(z * r, ps, r);
+    const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const int k = (int)kd;
+    const double a = (k & 1) ? cr : sr, b = (k & 1) ? sr : cr;
+    *s = (k & 2) ? -a : a;
+    *c = ((k + 1) & 2) ? -b : b;
+}
+
 TR_HD double impedance(const double* si, double dist) {
     if (si[0] == si[1] || si[2] <= 1e-15) return 0.5 * (si[0] + si[1]);
     const double x = fabs(dist / si[2]);
@@ -73,6 +103,11 @@ TR_HD double impedance(const double* si, double dist) {
     else y = 1.0 - pow(1.0 - x, si[4]) / pow(1.0 - si[3], si[4] - 1.0);
     return si[0] + y * (si[1] - si[0]);
 }
+
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+double impedance_call(const double* si, double dist) { return impedance(si, dist); }     // one out-of-line copy (pow paths)
 
 // In-place Cholesky solve of the dense SPD system A x = b (lower triangle of A used and overwritten).
 template <int N> TR_HD void chol_solve(int n, double (*A)[N], double* b) {
@@ -99,16 +134,130 @@ template <int N> TR_HD void chol_solve(int n, double (*A)[N], double* b) {
     }
 }
 
-// One mj_step.  NV > 0: compile-time dof count (loops unroll); NV == 0: run-time nv <= MJB_TREE_MAX_LINKS.
-// SERIAL: link i hangs off link i - 1.  u: controls (nu).  q, v advanced in place.  Returns the number of limit rows.
-template <int NV, bool SERIAL>
+// Soft joint limits, the constrained solve and mj_Euler for given M and f = qfrc_smooth (damping included); q, v
+// advanced in place.  Kept out of line: the planar kernel only comes here on substeps that have a limit row, and
+// one copy serves every instantiation.  Returns the number of limit rows.
+template <int N>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+int limits_solve_integrate(int nv, const double* lk, const int* li, double h, double (*M)[N], double* f, bool damped,
+                           double* q, double* v) {
+    // ---- joint-limit rows
+    int nr = 0, rdof[N];
+    double rs[N], aref[N], D[N];
+    for (int i = 0; i < N; i++) {
+        if (i >= nv) break;
+        if (!li[i * LI_STRIDE + LI_LIMITED]) continue;
+        const double* L = lk + i * LK_STRIDE;
+        const double dlo = q[i] - L[LK_LO], dhi = L[LK_HI] - q[i];
+        if (dlo < 0.0 || dhi < 0.0) {
+            const double side = dlo < 0.0 ? 1.0 : -1.0, dist = dlo < 0.0 ? dlo : dhi;
+            const double imp = impedance(L + LK_SOLIMP, dist);
+            const double Rr = fmax(1e-15, (1.0 - imp) * L[LK_INVW] / imp);
+            rdof[nr] = i; rs[nr] = side; D[nr] = 1.0 / Rr;
+            aref[nr] = -L[LK_SOLB] * (side * v[i]) - L[LK_SOLK] * imp * dist;
+            nr++;
+        }
+    }
+
+    // ---- one solver loop, one factorisation site.  phase 0: unconstrained acceleration (this is mj_Euler's solve when
+    // no row exists); phase 1: Newton on the active set with an exact line search; phase 2: mj_Euler's solve, implicit in
+    // joint damping, with the constraint force on the right-hand side.
+    double A[N][N], b[N], a0[N], fc[N];
+    unsigned act = 0;
+    int phase = 0;
+    for (int i = 0; i < nv; i++) fc[i] = 0.0;
+    for (int iter = 0; iter < 48; iter++) {
+        for (int i = 0; i < nv; i++) {
+            b[i] = f[i] + (phase == 2 ? fc[i] : 0.0);
+            for (int j = 0; j <= i; j++) A[i][j] = M[i][j];
+            if (phase == 2 || (phase == 0 && nr == 0)) A[i][i] += h * lk[i * LK_STRIDE + LK_DAMP];
+        }
+        if (phase == 1)
+            for (int rr = 0; rr < nr; rr++)
+                if (act >> rr & 1) { A[rdof[rr]][rdof[rr]] += D[rr]; b[rdof[rr]] += rs[rr] * D[rr] * aref[rr]; }
+        chol_solve<N>(nv, A, b);
+        if (phase == 2 || nr == 0) break;
+        bool converged = false;
+        if (phase == 0) {
+            for (int i = 0; i < nv; i++) a0[i] = b[i];
+            for (int rr = 0; rr < nr; rr++) if (rs[rr] * a0[rdof[rr]] - aref[rr] < 0.0) act |= 1u << rr;
+            phase = 1;
+            converged = act == 0;
+        } else {
+            unsigned act1 = 0;
+            for (int rr = 0; rr < nr; rr++) if (rs[rr] * b[rdof[rr]] - aref[rr] < 0.0) act1 |= 1u << rr;
+            if (act1 == act) {
+                for (int i = 0; i < nv; i++) a0[i] = b[i];
+                converged = true;
+            } else {
+                // the set changes along the step: exact minimiser of the piecewise quadratic on the ray a0 + t (b - a0)
+                double pdir[N], g0 = 0.0, h0 = 0.0;
+                for (int i = 0; i < nv; i++) pdir[i] = b[i] - a0[i];
+                for (int i = 0; i < nv; i++) {
+                    double Mp = 0.0, Ma = -f[i];
+                    for (int k = 0; k < nv; k++) { Mp += M[i][k] * pdir[k]; Ma += M[i][k] * a0[k]; }
+                    g0 += pdir[i] * Ma; h0 += pdir[i] * Mp;
+                }
+                double res[N], Jp[N], tcur = 0.0, tstar = 1.0;
+                for (int rr = 0; rr < nr; rr++) { res[rr] = rs[rr] * a0[rdof[rr]] - aref[rr]; Jp[rr] = rs[rr] * pdir[rdof[rr]]; }
+                for (int seg = 0; seg <= nr; seg++) {
+                    double tnext = TR_BIG;
+                    for (int rr = 0; rr < nr; rr++)
+                        if (Jp[rr] != 0.0) { const double tb = -res[rr] / Jp[rr]; if (tb > tcur && tb < tnext) tnext = tb; }
+                    const double tmid = tnext >= TR_BIG ? tcur + 1.0 : 0.5 * (tcur + tnext);
+                    double c0 = g0, c1 = h0;
+                    for (int rr = 0; rr < nr; rr++)
+                        if (res[rr] + tmid * Jp[rr] < 0.0) { c0 += D[rr] * res[rr] * Jp[rr]; c1 += D[rr] * Jp[rr] * Jp[rr]; }
+                    const double t = -c0 / c1;
+                    if (t <= tnext || tnext >= TR_BIG) { tstar = t < tcur ? tcur : t; break; }
+                    tcur = tnext;
+                }
+                for (int i = 0; i < nv; i++) a0[i] += tstar * pdir[i];
+                act = 0;
+                for (int rr = 0; rr < nr; rr++) if (rs[rr] * a0[rdof[rr]] - aref[rr] < 0.0) act |= 1u << rr;
+            }
+        }
+        if (converged) {
+            for (int rr = 0; rr < nr; rr++) {
+                const double sres = rs[rr] * a0[rdof[rr]] - aref[rr];
+                if (sres < 0.0) fc[rdof[rr]] += rs[rr] * (-D[rr] * sres);
+            }
+            if (!damped) { for (int i = 0; i < nv; i++) b[i] = a0[i]; break; }
+            phase = 2;
+        }
+    }
+    for (int i = 0; i < N; i++) {
+        if (i >= nv) break;
+        v[i] += h * b[i];
+        q[i] += h * v[i];
+    }
+    return nr;
+}
+
+}  // namespace tree
+}  // namespace mjb
+#include "rollout_tree_planar.cuh"
+namespace mjb {
+namespace tree {
+
+// One mj_step.  NV > 0: compile-time dof count; NV == 0: run-time nv <= MJB_TREE_MAX_LINKS.  SERIAL: link i hangs
+// off link i - 1 (the parent's frame and velocity ride in registers instead of per-link arrays).  UNROLL: per-link
+// loops unrolled.  u: controls (nu).  q, v advanced in place.  Returns the number of limit rows.
+//
+// All spatial vectors are world-oriented and refer to the point O = origin of link 0, so handing a wrench or an
+// inertia to the parent is a plain addition and an entry of M is one 6-vector dot product.
+template <int NV, bool SERIAL, bool UNROLL>
 TR_HD int substep(const double* lk, const int* li, const double* g, int nv_rt, double* q, double* v, const double* u) {
     constexpr int N = NV > 0 ? NV : MJB_TREE_MAX_LINKS;
-    constexpr int UNR = NV > 0 ? NV : 1;      // per-link loops unroll only when the dof count is a compile-time constant
+    constexpr int NS = SERIAL ? 1 : N;                      // slots for what a child needs from its parent
+    constexpr int UNR = (NV > 0 && UNROLL) ? NV : 1;
     const int nv = NV > 0 ? NV : nv_rt;
     const double h = g[TG_DT], rho = g[TG_RHO], visc = g[TG_VISC];
-    double R[N][9], r[N][3], w[N][3], vl[N][3], aa[N][3], al[N][3], fl[N][3], fn[N][3];
-    double cm[N], ch[N][3], cI[N][6], M[N][N], f[N];
+    double Rw[NS][9], pw[NS][3], V[NS][6], Ab[NS][6];
+    double S[N][6], F[N][6], cm[N], ch[N][3], cI[N][6], M[N][N], f[N];
+    double O[3] = {0.0, 0.0, 0.0};
 
     // ---- pass 1: root -> leaves
 #pragma unroll(UNR)
@@ -117,82 +266,129 @@ TR_HD int substep(const double* lk, const int* li, const double* g, int nv_rt, d
         const double* L = lk + i * LK_STRIDE;
         const int* I = li + i * LI_STRIDE;
         const int p = SERIAL ? i - 1 : I[LI_PARENT];
+        const int ps = SERIAL ? 0 : (p < 0 ? 0 : p), is = SERIAL ? 0 : i;
         const bool hinge = I[LI_TYPE] == MJB_TREE_HINGE;
         const double* a = L + LK_AXIS;
+        // parent frame, velocity, bias acceleration (world: identity at -O, at rest, accelerating against gravity)
+        double Rp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pp[3] = {-O[0], -O[1], -O[2]};
+        double Vp[6] = {0, 0, 0, 0, 0, 0}, Ap[6] = {0, 0, 0, -g[TG_GRAV], -g[TG_GRAV + 1], -g[TG_GRAV + 2]};
+        if (p >= 0) {
+#pragma unroll
+            for (int x = 0; x < 9; x++) Rp[x] = Rw[ps][x];
+#pragma unroll
+            for (int x = 0; x < 3; x++) pp[x] = pw[ps][x];
+#pragma unroll
+            for (int x = 0; x < 6; x++) { Vp[x] = V[ps][x]; Ap[x] = Ab[ps][x]; }
+        }
+        // link frame: R = Rp Rfix Rjoint, origin = pp + Rp (off [+ Rfix a q])
+        double Rl[9], ol[3] = {L[LK_OFF], L[LK_OFF + 1], L[LK_OFF + 2]};
         if (hinge) {
-            double s, c;
-            sincos(q[i], &s, &c);
-            const double t = 1.0 - c;
-            const double J[9] = {c + t * a[0] * a[0],        t * a[0] * a[1] - s * a[2], t * a[0] * a[2] + s * a[1],
-                                 t * a[0] * a[1] + s * a[2], c + t * a[1] * a[1],        t * a[1] * a[2] - s * a[0],
-                                 t * a[0] * a[2] - s * a[1], t * a[1] * a[2] + s * a[0], c + t * a[2] * a[2]};
+            double sn, cs;
+            sincos_lean(q[i], &sn, &cs);
+            const double t = 1.0 - cs;
+            const double J[9] = {cs + t * a[0] * a[0],        t * a[0] * a[1] - sn * a[2], t * a[0] * a[2] + sn * a[1],
+                                 t * a[0] * a[1] + sn * a[2], cs + t * a[1] * a[1],        t * a[1] * a[2] - sn * a[0],
+                                 t * a[0] * a[2] - sn * a[1], t * a[1] * a[2] + sn * a[0], cs + t * a[2] * a[2]};
+            if (I[LI_BODY] & 2) {                               // Rfix = identity
 #pragma unroll
-            for (int x = 0; x < 3; x++)
+                for (int x = 0; x < 9; x++) Rl[x] = J[x];
+            } else {
 #pragma unroll
-                for (int y = 0; y < 3; y++)
-                    R[i][3 * x + y] = L[LK_RFIX + 3 * x] * J[y] + L[LK_RFIX + 3 * x + 1] * J[3 + y] + L[LK_RFIX + 3 * x + 2] * J[6 + y];
-            r[i][0] = L[LK_OFF]; r[i][1] = L[LK_OFF + 1]; r[i][2] = L[LK_OFF + 2];
+                for (int x = 0; x < 3; x++)
+#pragma unroll
+                    for (int y = 0; y < 3; y++)
+                        Rl[3 * x + y] = L[LK_RFIX + 3 * x] * J[y] + L[LK_RFIX + 3 * x + 1] * J[3 + y] + L[LK_RFIX + 3 * x + 2] * J[6 + y];
+            }
         } else {
             double d[3];
 #pragma unroll
-            for (int x = 0; x < 9; x++) R[i][x] = L[LK_RFIX + x];
+            for (int x = 0; x < 9; x++) Rl[x] = L[LK_RFIX + x];
             mv(d, L + LK_RFIX, a);
 #pragma unroll
-            for (int x = 0; x < 3; x++) r[i][x] = L[LK_OFF + x] + d[x] * q[i];
+            for (int x = 0; x < 3; x++) ol[x] += d[x] * q[i];
         }
-        double wp[3] = {0, 0, 0}, vp[3] = {0, 0, 0}, ap[3] = {0, 0, 0}, lp[3] = {-g[TG_GRAV], -g[TG_GRAV + 1], -g[TG_GRAV + 2]};
-        if (p >= 0) {
+        double R[9], pos[3], aw[3];
 #pragma unroll
-            for (int x = 0; x < 3; x++) { wp[x] = w[p][x]; vp[x] = vl[p][x]; ap[x] = aa[p][x]; lp[x] = al[p][x]; }
+        for (int x = 0; x < 3; x++)
+#pragma unroll
+            for (int y = 0; y < 3; y++) R[3 * x + y] = Rp[3 * x] * Rl[y] + Rp[3 * x + 1] * Rl[3 + y] + Rp[3 * x + 2] * Rl[6 + y];
+        mv(pos, Rp, ol);
+#pragma unroll
+        for (int x = 0; x < 3; x++) pos[x] += pp[x];
+        if (i == 0) {                                           // the reference point: everything below is relative to it
+#pragma unroll
+            for (int x = 0; x < 3; x++) { O[x] = pos[x]; pos[x] = 0.0; }
         }
-        double t1[3], t2[3];
-        cross(t1, wp, r[i]);
-        cross(t2, ap, r[i]);
+        mv(aw, R, a);
+        // motion axis about O, velocity, bias acceleration
+        double Si[6];
+        if (hinge) { Si[0] = aw[0]; Si[1] = aw[1]; Si[2] = aw[2]; cross(Si + 3, pos, aw); }
+        else { Si[0] = 0.0; Si[1] = 0.0; Si[2] = 0.0; Si[3] = aw[0]; Si[4] = aw[1]; Si[5] = aw[2]; }
+        double Sd[6], t1[3], t2[3];
+        cross(Sd, Vp, Si);
+        cross(t1, Vp, Si + 3);
+        cross(t2, Vp + 3, Si);
 #pragma unroll
-        for (int x = 0; x < 3; x++) { t1[x] += vp[x]; t2[x] += lp[x]; }
-        mtv(w[i], R[i], wp);
-        mtv(vl[i], R[i], t1);
-        mtv(aa[i], R[i], ap);
-        mtv(al[i], R[i], t2);
-        const double sj[3] = {a[0] * v[i], a[1] * v[i], a[2] * v[i]};
-        if (hinge) {
-            cross(t1, w[i], sj);
-            cross(t2, vl[i], sj);
+        for (int x = 0; x < 3; x++) Sd[3 + x] = t1[x] + t2[x];
+        double Vi[6], Ai[6];
 #pragma unroll
-            for (int x = 0; x < 3; x++) { aa[i][x] += t1[x]; al[i][x] += t2[x]; w[i][x] += sj[x]; }
-        } else {
-            cross(t1, w[i], sj);
+        for (int x = 0; x < 6; x++) { Vi[x] = Vp[x] + Si[x] * v[i]; Ai[x] = Ap[x] + Sd[x] * v[i]; S[i][x] = Si[x]; }
 #pragma unroll
-            for (int x = 0; x < 3; x++) { al[i][x] += t1[x]; vl[i][x] += sj[x]; }
-        }
-        // link wrench and its own inertia as the seed of the composite
-        if (I[LI_BODY]) {
+        for (int x = 0; x < 9; x++) Rw[is][x] = R[x];
+#pragma unroll
+        for (int x = 0; x < 3; x++) pw[is][x] = pos[x];
+#pragma unroll
+        for (int x = 0; x < 6; x++) { V[is][x] = Vi[x]; Ab[is][x] = Ai[x]; }
+        // link wrench about O and its inertia as the seed of the composite
+        if (I[LI_BODY] & 1) {
             const double m = L[LK_MASS];
-            const double* c = L + LK_COM;
             const double* Ic = L + LK_IC;
-            double vc[3], hl[3], hn[3], ac[3], t3[3];
-            cross(vc, w[i], c);
-            cross(ac, aa[i], c);
+            double c[3], hh[3], Io[6];
+            mv(c, R, L + LK_COM);
 #pragma unroll
-            for (int x = 0; x < 3; x++) { vc[x] += vl[i][x]; ac[x] += al[i][x]; hl[x] = m * vc[x]; fl[i][x] = m * ac[x]; }
-            symv(hn, Ic, w[i]);
-            cross(t3, c, hl);
+            for (int x = 0; x < 3; x++) { c[x] += pos[x]; hh[x] = m * c[x]; }
+            {   // R Ic R' + m (|c|^2 1 - c c')
+                double RS[9];
 #pragma unroll
-            for (int x = 0; x < 3; x++) hn[x] += t3[x];
-            symv(fn[i], Ic, aa[i]);
-            cross(t3, c, fl[i]);
-            cross(t1, w[i], hn);
-            cross(t2, vl[i], hl);
+                for (int x = 0; x < 3; x++) {
+                    RS[3 * x] = R[3 * x] * Ic[0] + R[3 * x + 1] * Ic[3] + R[3 * x + 2] * Ic[4];
+                    RS[3 * x + 1] = R[3 * x] * Ic[3] + R[3 * x + 1] * Ic[1] + R[3 * x + 2] * Ic[5];
+                    RS[3 * x + 2] = R[3 * x] * Ic[4] + R[3 * x + 1] * Ic[5] + R[3 * x + 2] * Ic[2];
+                }
+                const double cc = dot(c, c);
+                Io[0] = RS[0] * R[0] + RS[1] * R[1] + RS[2] * R[2] + m * (cc - c[0] * c[0]);
+                Io[1] = RS[3] * R[3] + RS[4] * R[4] + RS[5] * R[5] + m * (cc - c[1] * c[1]);
+                Io[2] = RS[6] * R[6] + RS[7] * R[7] + RS[8] * R[8] + m * (cc - c[2] * c[2]);
+                Io[3] = RS[0] * R[3] + RS[1] * R[4] + RS[2] * R[5] - m * c[0] * c[1];
+                Io[4] = RS[0] * R[6] + RS[1] * R[7] + RS[2] * R[8] - m * c[0] * c[2];
+                Io[5] = RS[3] * R[6] + RS[4] * R[7] + RS[5] * R[8] - m * c[1] * c[2];
+            }
+            double mn[3], ml[3], fn[3], fl[3], t3[3];
+            symv(mn, Io, Vi);                       // momentum (angular about O, linear)
+            cross(t3, hh, Vi + 3);
+            cross(ml, Vi, hh);
 #pragma unroll
-            for (int x = 0; x < 3; x++) fn[i][x] += t3[x] + t1[x] + t2[x];
-            cross(t1, w[i], hl);
+            for (int x = 0; x < 3; x++) { mn[x] += t3[x]; ml[x] += m * Vi[3 + x]; }
+            symv(fn, Io, Ai);                       // I A
+            cross(t3, hh, Ai + 3);
+            cross(fl, Ai, hh);
 #pragma unroll
-            for (int x = 0; x < 3; x++) fl[i][x] += t1[x];
+            for (int x = 0; x < 3; x++) { fn[x] += t3[x]; fl[x] += m * Ai[3 + x]; }
+            cross(t1, Vi, mn);                      // + V x* (I V)
+            cross(t2, Vi + 3, ml);
+            cross(t3, Vi, ml);
+#pragma unroll
+            for (int x = 0; x < 3; x++) { fn[x] += t1[x] + t2[x]; fl[x] += t3[x]; }
             if (rho > 0.0 || visc > 0.0) {
                 const double* B = L + LK_BOX;
-                double lw[3], lv[3], lT[3] = {0, 0, 0}, lF[3] = {0, 0, 0}, T[3], F[3];
-                mv(lw, L + LK_RIN, w[i]);
-                mv(lv, L + LK_RIN, vc);
+                double vc[3], bw[3], bv[3], lw[3], lv[3], lT[3] = {0, 0, 0}, lF[3] = {0, 0, 0}, T[3], Fo[3];
+                cross(vc, Vi, c);
+#pragma unroll
+                for (int x = 0; x < 3; x++) vc[x] += Vi[3 + x];
+                mtv(bw, R, Vi);
+                mtv(bv, R, vc);
+                mv(lw, L + LK_RIN, bw);
+                mv(lv, L + LK_RIN, bv);
                 if (visc > 0.0) {
                     const double PI = 3.14159265358979323846, d = (B[0] + B[1] + B[2]) / 3.0;
 #pragma unroll
@@ -208,28 +404,30 @@ TR_HD int substep(const double* lk, const int* li, const double* g, int nv_rt, d
                     lT[1] -= rho * b1 * (q0 + q2) * fabs(lw[1]) * lw[1] / 64.0;
                     lT[2] -= rho * b2 * (q0 + q1) * fabs(lw[2]) * lw[2] / 64.0;
                 }
-                mtv(T, L + LK_RIN, lT);
-                mtv(F, L + LK_RIN, lF);
-                cross(t1, c, F);
+                mtv(bw, L + LK_RIN, lT);
+                mtv(bv, L + LK_RIN, lF);
+                mv(T, R, bw);
+                mv(Fo, R, bv);
+                cross(t1, c, Fo);
 #pragma unroll
-                for (int x = 0; x < 3; x++) { fl[i][x] -= F[x]; fn[i][x] -= T[x] + t1[x]; }
+                for (int x = 0; x < 3; x++) { fl[x] -= Fo[x]; fn[x] -= T[x] + t1[x]; }
             }
-            const double cc = dot(c, c);
             cm[i] = m;
 #pragma unroll
-            for (int x = 0; x < 3; x++) ch[i][x] = m * c[x];
-            cI[i][0] = Ic[0] + m * (cc - c[0] * c[0]); cI[i][1] = Ic[1] + m * (cc - c[1] * c[1]); cI[i][2] = Ic[2] + m * (cc - c[2] * c[2]);
-            cI[i][3] = Ic[3] - m * c[0] * c[1]; cI[i][4] = Ic[4] - m * c[0] * c[2]; cI[i][5] = Ic[5] - m * c[1] * c[2];
+            for (int x = 0; x < 3; x++) { ch[i][x] = hh[x]; F[i][x] = fn[x]; F[i][3 + x] = fl[x]; }
+#pragma unroll
+            for (int x = 0; x < 6; x++) cI[i][x] = Io[x];
         } else {
             cm[i] = 0.0;
 #pragma unroll
-            for (int x = 0; x < 3; x++) { fl[i][x] = 0.0; fn[i][x] = 0.0; ch[i][x] = 0.0; }
+            for (int x = 0; x < 3; x++) ch[i][x] = 0.0;
 #pragma unroll
-            for (int x = 0; x < 6; x++) cI[i][x] = 0.0;
+            for (int x = 0; x < 6; x++) { cI[i][x] = 0.0; F[i][x] = 0.0; }
         }
     }
 
     // ---- pass 2: leaves -> root
+    bool damped = false;
 #pragma unroll(UNR)
     for (int ii = 0; ii < N; ii++) {
         const int i = (NV > 0 ? NV : nv) - 1 - ii;
@@ -237,187 +435,74 @@ TR_HD int substep(const double* lk, const int* li, const double* g, int nv_rt, d
         const double* L = lk + i * LK_STRIDE;
         const int* I = li + i * LI_STRIDE;
         const int p = SERIAL ? i - 1 : I[LI_PARENT];
-        const bool hinge = I[LI_TYPE] == MJB_TREE_HINGE;
-        const double* a = L + LK_AXIS;
-        // generalised force of the link wrench (bias + gravity - fluid), passive joint forces, actuation
-        double tau = hinge ? dot(a, fn[i]) : dot(a, fl[i]);
+        const double* Si = S[i];
+        const double tau = Si[0] * F[i][0] + Si[1] * F[i][1] + Si[2] * F[i][2] + Si[3] * F[i][3] + Si[4] * F[i][4] + Si[5] * F[i][5];
         double act = 0.0;
         if (I[LI_ACT] >= 0) act = L[LK_GEAR] * fmin(fmax(u[I[LI_ACT]], L[LK_CLO]), L[LK_CHI]);
         f[i] = act - L[LK_STIFF] * (q[i] - L[LK_SREF]) - L[LK_DAMP] * v[i] - tau;
-        // column i of M: momentum of the composite under unit joint velocity, walked down to the root
-        double Fl[3], Fn[3];
-        if (hinge) { cross(Fl, a, ch[i]); symv(Fn, cI[i], a); }
-        else { Fl[0] = cm[i] * a[0]; Fl[1] = cm[i] * a[1]; Fl[2] = cm[i] * a[2]; cross(Fn, ch[i], a); }
-        M[i][i] = (hinge ? dot(a, Fn) : dot(a, Fl)) + L[LK_ARM];
-#pragma unroll(UNR)
-        for (int jj = 0; jj < N; jj++) if (jj < i) { M[i][jj] = 0.0; }
+        damped = damped || L[LK_DAMP] != 0.0;
+        // momentum of the composite under unit joint velocity; its projections on the ancestors' axes are column i of M
+        double mn[3], ml[3], t3[3];
+        symv(mn, cI[i], Si);
+        cross(t3, ch[i], Si + 3);
+        cross(ml, Si, ch[i]);
+#pragma unroll
+        for (int x = 0; x < 3; x++) { mn[x] += t3[x]; ml[x] += cm[i] * Si[3 + x]; }
         int j = i;
 #pragma unroll(UNR)
         for (int step = 0; step < N; step++) {
-            const int pj = SERIAL ? j - 1 : li[j * LI_STRIDE + LI_PARENT];
-            if (pj < 0) break;
-            double t1[3], t2[3];
-            mv(t1, R[j], Fl);
-            mv(t2, R[j], Fn);
-            cross(Fn, r[j], t1);
-#pragma unroll
-            for (int x = 0; x < 3; x++) { Fl[x] = t1[x]; Fn[x] += t2[x]; }
-            j = pj;
-            const double* aj = lk + j * LK_STRIDE + LK_AXIS;
-            M[i][j] = li[j * LI_STRIDE + LI_TYPE] == MJB_TREE_HINGE ? dot(aj, Fn) : dot(aj, Fl);
+            if (j < 0) break;
+            const double* Sj = S[j];
+            const double e = Sj[0] * mn[0] + Sj[1] * mn[1] + Sj[2] * mn[2] + Sj[3] * ml[0] + Sj[4] * ml[1] + Sj[5] * ml[2];
+            M[i][j] = e;
+            M[j][i] = e;
+            j = SERIAL ? j - 1 : li[j * LI_STRIDE + LI_PARENT];
         }
+        M[i][i] += L[LK_ARM];
         if (p >= 0) {
-            // hand wrench and composite inertia to the parent
-            double F[3], T[3], t1[3], hp[3];
-            mv(F, R[i], fl[i]);
-            mv(T, R[i], fn[i]);
-            cross(t1, r[i], F);
 #pragma unroll
-            for (int x = 0; x < 3; x++) { fl[p][x] += F[x]; fn[p][x] += T[x] + t1[x]; }
-            mv(hp, R[i], ch[i]);
-            // rotate the inertia: R S R'
-            const double* S = cI[i];
-            const double* Q = R[i];
-            double RS[9];
+            for (int x = 0; x < 6; x++) { F[p][x] += F[i][x]; cI[p][x] += cI[i][x]; }
 #pragma unroll
-            for (int x = 0; x < 3; x++) {
-                RS[3 * x] = Q[3 * x] * S[0] + Q[3 * x + 1] * S[3] + Q[3 * x + 2] * S[4];
-                RS[3 * x + 1] = Q[3 * x] * S[3] + Q[3 * x + 1] * S[1] + Q[3 * x + 2] * S[5];
-                RS[3 * x + 2] = Q[3 * x] * S[4] + Q[3 * x + 1] * S[5] + Q[3 * x + 2] * S[2];
-            }
-            const double m = cm[i];
-            const double* o = r[i];
-            const double oo = dot(o, o), oh = dot(o, hp);
-            const double Ixx = RS[0] * Q[0] + RS[1] * Q[1] + RS[2] * Q[2], Iyy = RS[3] * Q[3] + RS[4] * Q[4] + RS[5] * Q[5];
-            const double Izz = RS[6] * Q[6] + RS[7] * Q[7] + RS[8] * Q[8], Ixy = RS[0] * Q[3] + RS[1] * Q[4] + RS[2] * Q[5];
-            const double Ixz = RS[0] * Q[6] + RS[1] * Q[7] + RS[2] * Q[8], Iyz = RS[3] * Q[6] + RS[4] * Q[7] + RS[5] * Q[8];
-            cI[p][0] += Ixx + m * (oo - o[0] * o[0]) + 2.0 * (oh - o[0] * hp[0]);
-            cI[p][1] += Iyy + m * (oo - o[1] * o[1]) + 2.0 * (oh - o[1] * hp[1]);
-            cI[p][2] += Izz + m * (oo - o[2] * o[2]) + 2.0 * (oh - o[2] * hp[2]);
-            cI[p][3] += Ixy - m * o[0] * o[1] - o[0] * hp[1] - hp[0] * o[1];
-            cI[p][4] += Ixz - m * o[0] * o[2] - o[0] * hp[2] - hp[0] * o[2];
-            cI[p][5] += Iyz - m * o[1] * o[2] - o[1] * hp[2] - hp[1] * o[2];
-            cm[p] += m;
-#pragma unroll
-            for (int x = 0; x < 3; x++) ch[p][x] += hp[x] + m * o[x];
+            for (int x = 0; x < 3; x++) ch[p][x] += ch[i][x];
+            cm[p] += cm[i];
         }
     }
-    // symmetric fill (M[i][j] set for j < i)
+    if (!SERIAL) {
+        // dofs on different branches do not couple: M[i][j] was only written along ancestor chains
 #pragma unroll(UNR)
-    for (int i = 0; i < N; i++)
-#pragma unroll(UNR)
-        for (int j = 0; j < N; j++) if (j > i && j < nv) M[i][j] = M[j][i];
-
-    // ---- joint-limit rows
-    int nr = 0, rdof[N];
-    double rs[N], aref[N], D[N];
-    bool damped = false;
-#pragma unroll(UNR)
-    for (int i = 0; i < N; i++) {
-        if (i >= nv) break;
-        const double* L = lk + i * LK_STRIDE;
-        damped = damped || L[LK_DAMP] != 0.0;
-        if (!li[i * LI_STRIDE + LI_LIMITED]) continue;
-        const double dlo = q[i] - L[LK_LO], dhi = L[LK_HI] - q[i];
-        if (dlo < 0.0 || dhi < 0.0) {
-            const double side = dlo < 0.0 ? 1.0 : -1.0, dist = dlo < 0.0 ? dlo : dhi;
-            const double imp = impedance(L + LK_SOLIMP, dist);
-            const double Rr = fmax(1e-15, (1.0 - imp) * L[LK_INVW] / imp);
-            rdof[nr] = i; rs[nr] = side; D[nr] = 1.0 / Rr;
-            aref[nr] = -L[LK_SOLB] * (side * v[i]) - L[LK_SOLK] * imp * dist;
-            nr++;
-        }
-    }
-    double A[N][N], qa[N];
-    if (nr > 0) {
-        double a0[N];
-        for (int i = 0; i < nv; i++) { a0[i] = f[i]; for (int j = 0; j <= i; j++) A[i][j] = M[i][j]; }
-        chol_solve<N>(nv, A, a0);                       // unconstrained acceleration
-        double fc[N];
-        unsigned act = 0;
-        for (int rr = 0; rr < nr; rr++) if (rs[rr] * a0[rdof[rr]] - aref[rr] < 0.0) act |= 1u << rr;
-        for (int iter = 0; iter < 40 && (act || iter); iter++) {
-            // minimiser of the quadratic that holds on the current active set
-            double a1[N];
-            for (int i = 0; i < nv; i++) { a1[i] = f[i]; for (int j = 0; j <= i; j++) A[i][j] = M[i][j]; }
-            for (int rr = 0; rr < nr; rr++)
-                if (act >> rr & 1) { A[rdof[rr]][rdof[rr]] += D[rr]; a1[rdof[rr]] += rs[rr] * D[rr] * aref[rr]; }
-            chol_solve<N>(nv, A, a1);
-            unsigned act1 = 0;
-            for (int rr = 0; rr < nr; rr++) if (rs[rr] * a1[rdof[rr]] - aref[rr] < 0.0) act1 |= 1u << rr;
-            if (act1 == act) { for (int i = 0; i < nv; i++) a0[i] = a1[i]; break; }
-            // the set changes along the step: exact minimiser of the piecewise quadratic on the ray a0 + t (a1 - a0)
-            double p[N], g0 = 0.0, h0 = 0.0;
-            for (int i = 0; i < nv; i++) p[i] = a1[i] - a0[i];
-            for (int i = 0; i < nv; i++) {
-                double Mp = 0.0, Ma = -f[i];
-                for (int k = 0; k < nv; k++) { Mp += M[i][k] * p[k]; Ma += M[i][k] * a0[k]; }
-                g0 += p[i] * Ma; h0 += p[i] * Mp;
-            }
-            double res[N], Jp[N], tcur = 0.0;
-            for (int rr = 0; rr < nr; rr++) { res[rr] = rs[rr] * a0[rdof[rr]] - aref[rr]; Jp[rr] = rs[rr] * p[rdof[rr]]; }
-            double tstar = 1.0;
-            for (int seg = 0; seg <= nr; seg++) {
-                // next breakpoint after tcur
-                double tnext = TR_BIG;
-                for (int rr = 0; rr < nr; rr++)
-                    if (Jp[rr] != 0.0) { const double tb = -res[rr] / Jp[rr]; if (tb > tcur && tb < tnext) tnext = tb; }
-                const double tmid = tnext >= TR_BIG ? tcur + 1.0 : 0.5 * (tcur + tnext);
-                double c0 = g0, c1 = h0;
-                for (int rr = 0; rr < nr; rr++)
-                    if (res[rr] + tmid * Jp[rr] < 0.0) { c0 += D[rr] * res[rr] * Jp[rr]; c1 += D[rr] * Jp[rr] * Jp[rr]; }
-                const double t = -c0 / c1;
-                if (t <= tnext || tnext >= TR_BIG) { tstar = t < tcur ? tcur : t; break; }
-                tcur = tnext;
-            }
-            for (int i = 0; i < nv; i++) a0[i] += tstar * p[i];
-            act = 0;
-            for (int rr = 0; rr < nr; rr++) if (rs[rr] * a0[rdof[rr]] - aref[rr] < 0.0) act |= 1u << rr;
-        }
-        for (int i = 0; i < nv; i++) fc[i] = 0.0;
-        for (int rr = 0; rr < nr; rr++) {
-            const double s = rs[rr] * a0[rdof[rr]] - aref[rr];
-            if (s < 0.0) fc[rdof[rr]] += rs[rr] * (-D[rr] * s);
-        }
-        if (!damped) {
-            for (int i = 0; i < nv; i++) qa[i] = a0[i];
-        } else {
-            for (int i = 0; i < nv; i++) f[i] += fc[i];
-        }
-    }
-    if (nr == 0 || damped) {
-        // ---- mj_Euler, implicit in joint damping
-#pragma unroll
         for (int i = 0; i < N; i++) {
             if (i >= nv) break;
-            qa[i] = f[i];
-#pragma unroll(UNR)
-            for (int j = 0; j < N; j++) if (j <= i) A[i][j] = M[i][j];
-            A[i][i] += h * lk[i * LK_STRIDE + LK_DAMP];
+            for (int j = 0; j < i; j++) {
+                bool anc = false;
+                for (int k = li[i * LI_STRIDE + LI_PARENT]; k >= 0; k = li[k * LI_STRIDE + LI_PARENT]) anc = anc || k == j;
+                if (!anc) { M[i][j] = 0.0; M[j][i] = 0.0; }
+            }
         }
-        chol_solve<N>(nv, A, qa);
     }
-#pragma unroll(UNR)
-    for (int i = 0; i < N; i++) {
-        if (i >= nv) break;
-        v[i] += h * qa[i];
-        q[i] += h * v[i];
-    }
-    return nr;
+
+    return limits_solve_integrate<N>(nv, lk, li, h, M, f, damped, q, v);
 }
 
-template <int NV, bool SERIAL>
+// PLANAR: the planar instantiation (rollout_tree_planar.cuh; NV > 0), else the general 3-D one.
+template <int NV, bool SERIAL, bool PLANAR>
 __global__ void __launch_bounds__(64) rollout_tree_kernel(const double* __restrict__ g_lk, const int* __restrict__ g_li,
-                                                          const double* __restrict__ g_g, int nv_rt, int nu,
+                                                          const double* __restrict__ g_g, const double* __restrict__ g_pk,
+                                                          const int* __restrict__ g_anc, int nv_rt, int nu,
                                                           mjb_tree_rollout_args a) {
     constexpr int N = NV > 0 ? NV : MJB_TREE_MAX_LINKS;
     __shared__ double s_lk[N * LK_STRIDE];
     __shared__ int s_li[N * LI_STRIDE];
     __shared__ double s_g[TG_STRIDE];
+    __shared__ double s_pk[PLANAR ? N * PK_STRIDE + 2 : 1];
+    __shared__ int s_anc[PLANAR ? N : 1];
     const int nv = NV > 0 ? NV : nv_rt;
     for (int i = threadIdx.x; i < nv * LK_STRIDE; i += blockDim.x) s_lk[i] = g_lk[i];
     for (int i = threadIdx.x; i < nv * LI_STRIDE; i += blockDim.x) s_li[i] = g_li[i];
     if (threadIdx.x < TG_STRIDE) s_g[threadIdx.x] = g_g[threadIdx.x];
+    if (PLANAR) {
+        for (int i = threadIdx.x; i < nv * PK_STRIDE + 2; i += blockDim.x) s_pk[i] = g_pk[i];
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) s_anc[i] = g_anc[i];
+    }
     __syncthreads();
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.K) return;
@@ -441,9 +526,28 @@ __global__ void __launch_bounds__(64) rollout_tree_kernel(const double* __restri
             a2 += x * x;
             if (a.actions) a.actions[k * a.act_sk + t * a.act_st + j * a.act_sj] = x;     // unclipped (wrapper :150)
         }
-        const double before = q[a.fwd_dof];
-        for (int s = 0; s < a.frame_skip; s++) nefc += substep<NV, SERIAL>(s_lk, s_li, s_g, nv, q, v, u);
-        const double reward = a.w_fwd * (q[a.fwd_dof] - before) * inv_dt - a.w_ctrl * a2;
+        double uf[PLANAR ? N : 1];
+        if constexpr (PLANAR) {
+            // actuator force per dof (mj_fwdActuation: the control clamped to ctrlrange, times the gear), held over the substeps
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                const int ai = s_li[i * LI_STRIDE + LI_ACT];
+                double c = 0.0;
+#pragma unroll
+                for (int j = 0; j < N; j++) if (j == ai) c = u[j];
+                uf[i] = ai >= 0 ? s_lk[i * LK_STRIDE + LK_GEAR] * fmin(fmax(c, s_lk[i * LK_STRIDE + LK_CLO]), s_lk[i * LK_STRIDE + LK_CHI]) : 0.0;
+            }
+        }
+        double before = 0.0, after = 0.0;           // (selects, not q[fwd_dof]: a run-time index would push q out of registers)
+#pragma unroll
+        for (int i = 0; i < N; i++) if (i == a.fwd_dof) before = q[i];
+        for (int s = 0; s < a.frame_skip; s++) {
+            if constexpr (PLANAR) nefc += planar_substep<NV, SERIAL>(s_lk, s_li, s_pk, s_anc, s_g, s_pk + NV * PK_STRIDE, q, v, uf);
+            else nefc += substep<NV, SERIAL, false>(s_lk, s_li, s_g, nv, q, v, u);
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) if (i == a.fwd_dof) after = q[i];
+        const double reward = a.w_fwd * (after - before) * inv_dt - a.w_ctrl * a2;
         a.costs[k * a.costs_sk + t * a.costs_st] = -reward;
         if (a.states_out) {
             double* so = a.states_out + (k * a.H + t) * 2 * nv;
@@ -466,10 +570,23 @@ __global__ void __launch_bounds__(64) rollout_tree_kernel(const double* __restri
 }  // namespace mjb
 
 #ifndef MJB_HOST_EMU
+namespace {
+template <class T> bool upload(T** dst, const T* src, size_t n) {
+    return cudaMalloc(dst, sizeof(T) * n) == cudaSuccess &&
+           cudaMemcpyAsync(*dst, src, sizeof(T) * n, cudaMemcpyHostToDevice, 0) == cudaSuccess;
+}
+int g_use_planar = 1;
+}  // namespace
+
 extern "C" mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* link_params, const int* link_ints,
-                                                 const double* globals, int device) {
+                                                 const double* globals, const double* planar_params,
+                                                 const int* planar_anc, const double* planar_gravity, int device) {
     if (nv < 1 || nv > MJB_TREE_MAX_LINKS || nu < 0 || nu > nv || !link_params || !link_ints || !globals) {
         mjb::set_error(MJB_EINVAL, "mjb_tree_model_create: 1 <= nv <= %d, nu <= nv, non-null blocks", MJB_TREE_MAX_LINKS);
+        return nullptr;
+    }
+    if ((planar_params != nullptr) != (planar_anc != nullptr) || (planar_params != nullptr) != (planar_gravity != nullptr)) {
+        mjb::set_error(MJB_EINVAL, "mjb_tree_model_create: the three planar blocks come together or not at all");
         return nullptr;
     }
     int serial = 1;
@@ -481,16 +598,20 @@ extern "C" mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* l
         if (act >= nu) { mjb::set_error(MJB_EINVAL, "mjb_tree_model_create: link %d names actuator %d of %d", i, act, nu); return nullptr; }
     }
     if (cudaSetDevice(device) != cudaSuccess) { mjb::set_error(MJB_ECUDA, "mjb_tree_model_create: cudaSetDevice(%d) failed", device); return nullptr; }
-    mjb_tree_model* m = new mjb_tree_model{device, nv, nu, serial, nullptr, nullptr, nullptr};
-    if (cudaMalloc(&m->d_lk, sizeof(double) * nv * LK_STRIDE) != cudaSuccess || cudaMalloc(&m->d_li, sizeof(int) * nv * LI_STRIDE) != cudaSuccess ||
-        cudaMalloc(&m->d_g, sizeof(double) * TG_STRIDE) != cudaSuccess ||
-        cudaMemcpyAsync(m->d_lk, link_params, sizeof(double) * nv * LK_STRIDE, cudaMemcpyHostToDevice, 0) != cudaSuccess ||
-        cudaMemcpyAsync(m->d_li, link_ints, sizeof(int) * nv * LI_STRIDE, cudaMemcpyHostToDevice, 0) != cudaSuccess ||
-        cudaMemcpyAsync(m->d_g, globals, sizeof(double) * TG_STRIDE, cudaMemcpyHostToDevice, 0) != cudaSuccess ||
-        cudaStreamSynchronize(0) != cudaSuccess) {
+    mjb_tree_model* m = new mjb_tree_model{device, nv, nu, serial, planar_params != nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ok = upload(&m->d_lk, link_params, (size_t)nv * LK_STRIDE) && upload(&m->d_li, link_ints, (size_t)nv * LI_STRIDE) &&
+              upload(&m->d_g, globals, (size_t)TG_STRIDE);
+    if (ok && m->planar) {
+        double pk[MJB_TREE_MAX_LINKS * PK_STRIDE + 2];
+        for (int i = 0; i < nv * PK_STRIDE; i++) pk[i] = planar_params[i];
+        pk[nv * PK_STRIDE] = planar_gravity[0];
+        pk[nv * PK_STRIDE + 1] = planar_gravity[1];
+        ok = upload(&m->d_pk, pk, (size_t)nv * PK_STRIDE + 2) && upload(&m->d_anc, planar_anc, (size_t)nv);
+        ok = ok && cudaStreamSynchronize(0) == cudaSuccess;      // pk lives on this stack frame
+    }
+    if (!ok || cudaStreamSynchronize(0) != cudaSuccess) {
         mjb::set_error(MJB_ECUDA, "mjb_tree_model_create: device allocation / upload failed");
-        cudaFree(m->d_lk); cudaFree(m->d_li); cudaFree(m->d_g);
-        delete m;
+        mjb_tree_model_destroy(m);
         return nullptr;
     }
     return m;
@@ -499,13 +620,22 @@ extern "C" mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* l
 extern "C" void mjb_tree_model_destroy(mjb_tree_model* m) {
     if (!m) return;
     cudaFree(m->d_lk); cudaFree(m->d_li); cudaFree(m->d_g);
+    if (m->d_pk) cudaFree(m->d_pk);
+    if (m->d_anc) cudaFree(m->d_anc);
     delete m;
+}
+
+extern "C" int mjb_tree_use_planar(int on) {
+    const int old = g_use_planar;
+    if (on >= 0) g_use_planar = on != 0;
+    return old;
 }
 
 extern "C" void mjb_tree_layout(int* out) {
     const int v[] = {LK_RFIX, LK_OFF, LK_AXIS, LK_MASS, LK_COM, LK_IC, LK_RIN, LK_BOX, LK_ARM, LK_DAMP, LK_STIFF, LK_SREF, LK_LO,
                      LK_HI, LK_INVW, LK_SOLK, LK_SOLB, LK_SOLIMP, LK_GEAR, LK_CLO, LK_CHI, LK_STRIDE, LI_PARENT, LI_TYPE,
-                     LI_LIMITED, LI_ACT, LI_BODY, LI_STRIDE, TG_DT, TG_GRAV, TG_RHO, TG_VISC, TG_STRIDE, MJB_TREE_MAX_LINKS};
+                     LI_LIMITED, LI_ACT, LI_BODY, LI_STRIDE, TG_DT, TG_GRAV, TG_RHO, TG_VISC, TG_STRIDE, MJB_TREE_MAX_LINKS,
+                     PK_OFF, PK_DIR, PK_MASS, PK_COM, PK_INN, PK_CLIN, PK_KV1, PK_KV2, PK_E, PK_AK, PK_STRIDE};
     for (unsigned i = 0; i < sizeof(v) / sizeof(v[0]); i++) out[i] = v[i];
 }
 
@@ -518,10 +648,16 @@ extern "C" int mjb_rollout_tree(const mjb_tree_model* m, const mjb_tree_rollout_
                 "mjb_rollout_tree: fwd_dof / obs_qpos_start out of range");
     const int blocks = (a->K + 63) / 64;
     cudaStream_t st = (cudaStream_t)stream;
-    if (m->nv == 7 && m->serial)
-        mjb::tree::rollout_tree_kernel<7, true><<<blocks, 64, 0, st>>>(m->d_lk, m->d_li, m->d_g, m->nv, m->nu, *a);
-    else
-        mjb::tree::rollout_tree_kernel<0, false><<<blocks, 64, 0, st>>>(m->d_lk, m->d_li, m->d_g, m->nv, m->nu, *a);
+    using namespace mjb::tree;
+    const bool planar = m->planar && g_use_planar;
+#define MJB_TREE_LAUNCH(NV, SERIAL, PLANAR) \
+    rollout_tree_kernel<NV, SERIAL, PLANAR><<<blocks, 64, 0, st>>>(m->d_lk, m->d_li, m->d_g, m->d_pk, m->d_anc, m->nv, m->nu, *a)
+    if (planar && m->nv == 7 && m->serial) MJB_TREE_LAUNCH(7, true, true);
+    else if (planar && m->nv == 7) MJB_TREE_LAUNCH(7, false, true);
+    else if (planar && m->nv == 9) MJB_TREE_LAUNCH(9, false, true);
+    else if (m->nv == 7 && m->serial) MJB_TREE_LAUNCH(7, true, false);
+    else MJB_TREE_LAUNCH(0, false, false);
+#undef MJB_TREE_LAUNCH
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;
 }

@@ -28,6 +28,7 @@ enum {
     LK_STRIDE = 54
 };
 // per link, ints
+// LI_BODY: bit 0 = the link carries a body, bit 1 = LK_RFIX is the identity
 enum { LI_PARENT = 0, LI_TYPE = 1, LI_LIMITED = 2, LI_ACT = 3, LI_BODY = 4, LI_STRIDE = 5 };
 // globals, doubles
 enum { TG_DT = 0, TG_GRAV = 1, TG_RHO = 4, TG_VISC = 5, TG_STRIDE = 6 };

@@ -19,22 +19,31 @@ class DeviceTreeModel:
 
     def __init__(self, model: mjcf_tree.TreeModel, device: int = 0):
         L = _lib.lib()
-        layout = (C.c_int * 34)()
+        layout = (C.c_int * 45)()
         L.mjb_tree_layout(layout)
         mine = [mjcf_tree.LK_RFIX, mjcf_tree.LK_OFF, mjcf_tree.LK_AXIS, mjcf_tree.LK_MASS, mjcf_tree.LK_COM, mjcf_tree.LK_IC,
                 mjcf_tree.LK_RIN, mjcf_tree.LK_BOX, mjcf_tree.LK_ARM, mjcf_tree.LK_DAMP, mjcf_tree.LK_STIFF, mjcf_tree.LK_SREF,
                 mjcf_tree.LK_LO, mjcf_tree.LK_HI, mjcf_tree.LK_INVW, mjcf_tree.LK_SOLK, mjcf_tree.LK_SOLB, mjcf_tree.LK_SOLIMP,
                 mjcf_tree.LK_GEAR, mjcf_tree.LK_CLO, mjcf_tree.LK_CHI, mjcf_tree.LK_STRIDE, mjcf_tree.LI_PARENT,
                 mjcf_tree.LI_TYPE, mjcf_tree.LI_LIMITED, mjcf_tree.LI_ACT, mjcf_tree.LI_BODY, mjcf_tree.LI_STRIDE,
-                mjcf_tree.G_DT, mjcf_tree.G_GRAV, mjcf_tree.G_RHO, mjcf_tree.G_VISC, mjcf_tree.G_STRIDE, mjcf_tree.MAX_LINKS]
+                mjcf_tree.G_DT, mjcf_tree.G_GRAV, mjcf_tree.G_RHO, mjcf_tree.G_VISC, mjcf_tree.G_STRIDE, mjcf_tree.MAX_LINKS,
+                mjcf_tree.PK_OFF, mjcf_tree.PK_DIR, mjcf_tree.PK_MASS, mjcf_tree.PK_COM, mjcf_tree.PK_INN, mjcf_tree.PK_CLIN,
+                mjcf_tree.PK_KV1, mjcf_tree.PK_KV2, mjcf_tree.PK_E, mjcf_tree.PK_AK, mjcf_tree.PK_STRIDE]
         if list(layout) != mine:
             raise _lib.MjbError("parameter layout of mjcf_tree.py and csrc/tree_model.h differ")
         P, I, G = mjcf_tree.pack_links(model)
         self.nv, self.nu = model.nv, model.nu
+        planar = mjcf_tree.pack_planar(model)
+        self.planar = planar is not None
         self._keep = (np.ascontiguousarray(P), np.ascontiguousarray(I, np.int32), np.ascontiguousarray(G))
+        pk = [None, None, None]
+        if planar is not None:
+            self._keep += (np.ascontiguousarray(planar[0]), np.ascontiguousarray(planar[1], np.int32), np.ascontiguousarray(planar[2]))
+            pk = [k.ctypes.data_as(C.c_void_p) for k in self._keep[3:]]
         self.handle = C.c_void_p(L.mjb_tree_model_create(
             C.c_int(model.nv), C.c_int(model.nu), self._keep[0].ctypes.data_as(C.c_void_p),
-            self._keep[1].ctypes.data_as(C.c_void_p), self._keep[2].ctypes.data_as(C.c_void_p), C.c_int(device)))
+            self._keep[1].ctypes.data_as(C.c_void_p), self._keep[2].ctypes.data_as(C.c_void_p), pk[0], pk[1], pk[2],
+            C.c_int(device)))
         if not self.handle:
             raise _lib.MjbError(L.mjb_last_error().decode())
 

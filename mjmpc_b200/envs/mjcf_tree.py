@@ -480,7 +480,7 @@ def solref_to_kb(solref, solimp, timestep):
 LK_RFIX, LK_OFF, LK_AXIS, LK_MASS, LK_COM, LK_IC, LK_RIN, LK_BOX = 0, 9, 12, 15, 16, 19, 25, 34
 LK_ARM, LK_DAMP, LK_STIFF, LK_SREF, LK_LO, LK_HI, LK_INVW, LK_SOLK, LK_SOLB, LK_SOLIMP = 37, 38, 39, 40, 41, 42, 43, 44, 45, 46
 LK_GEAR, LK_CLO, LK_CHI, LK_STRIDE = 51, 52, 53, 54
-# per link, ints: parent link, joint type, limited, actuator index (-1 = none), carries a body
+# per link, ints: parent link, joint type, limited, actuator index (-1 = none), flags (1: carries a body, 2: Rfix = I)
 LI_PARENT, LI_TYPE, LI_LIMITED, LI_ACT, LI_BODY, LI_STRIDE = 0, 1, 2, 3, 4, 5
 # globals (doubles): timestep, gravity[3], density, viscosity
 G_DT, G_GRAV, G_RHO, G_VISC, G_STRIDE = 0, 1, 4, 5, 6
@@ -515,8 +515,10 @@ def pack_links(model: TreeModel):
         P[j, LK_OFF:LK_OFF + 3] = off
         P[j, LK_AXIS:LK_AXIS + 3] = model.jnt_axis[j]
         I[j, LI_PARENT], I[j, LI_TYPE], I[j, LI_LIMITED], I[j, LI_ACT] = parent, model.jnt_type[j], model.jnt_limited[j], -1
+        if np.array_equal(Rfix, np.eye(3)):
+            I[j, LI_BODY] |= 2                          # flag: the kernel skips the multiplication by Rfix
         if last_of_body[b] == j and model.body_mass[b] > 0:
-            I[j, LI_BODY] = 1
+            I[j, LI_BODY] |= 1
             P[j, LK_MASS] = model.body_mass[b]
             P[j, LK_COM:LK_COM + 3] = model.body_ipos[b] - model.jnt_pos[j]
             Rin = model.body_imat[b]
@@ -544,6 +546,71 @@ def pack_links(model: TreeModel):
     G = np.zeros(G_STRIDE)
     G[G_DT], G[G_GRAV:G_GRAV + 3], G[G_RHO], G[G_VISC] = model.timestep, model.gravity, model.density, model.viscosity
     return P, I, G
+
+
+# ------------------------------------------------------------------------------------------------ planar mechanisms
+# A tree whose hinge axes are all parallel (to n) and whose slides are all perpendicular to n moves in a plane: the
+# reference's swimmer (n = z) and half-cheetah (n = y) both do.  The kernel has a planar instantiation with 3-vectors
+# (omega; vx, vy) in place of spatial 6-vectors; the reduction is exact for any inertia tensor (only n'I n enters the
+# in-plane equations) and for mj_passive's inertia-box fluid model (the projections of the inertial axes on the plane
+# turn with the body, their components along n are constant).  Per link, doubles (frames are WORLD-ALIGNED at q = 0):
+PK_OFF, PK_DIR, PK_MASS, PK_COM, PK_INN, PK_CLIN, PK_KV1, PK_KV2, PK_E, PK_AK, PK_STRIDE = 0, 2, 4, 5, 7, 8, 9, 10, 11, 17, 20
+# PK_DIR: hinge: (sign of the axis along n, 0); slide: unit direction in the plane.  PK_E: the three inertial axes
+# projected on the plane (x0 y0 x1 y1 x2 y2); PK_AK: 1/2 rho * face area seen along each inertial axis.
+# per link, ints: bit mask of the link's ancestors
+PKG_GRAV, PKG_STRIDE = 0, 2           # planar globals: gravity projected on the plane
+
+
+def pack_planar(model: TreeModel, tol: float = 1e-12):
+    """Planar parameter block (P, anc, G) of a planar mechanism, or None."""
+    nv = model.nv
+    hinges = np.nonzero(model.jnt_type == HINGE)[0]
+    if hinges.size == 0:
+        return None
+    xpos, xmat, anchor, axis = kinematics(model, np.zeros(nv))
+    n = axis[hinges[0]]
+    sign = np.zeros(nv)
+    for j in range(nv):
+        c = float(axis[j] @ n)
+        if model.jnt_type[j] == HINGE:
+            if abs(abs(c) - 1.0) > tol:
+                return None
+            sign[j] = 1.0 if c > 0 else -1.0
+        elif abs(c) > tol:
+            return None
+    k = int(np.argmin(np.abs(n)))
+    ex = np.eye(3)[k] - n[k] * n
+    ex /= np.linalg.norm(ex)
+    ey = np.cross(n, ex)
+    plane = lambda w: np.array([ex @ w, ey @ w])
+    _, I, _ = pack_links(model)
+    P = np.zeros((nv, PK_STRIDE))
+    anc = np.zeros(nv, np.int32)
+    last_of_body = {int(model.jnt_body[j]): j for j in range(nv)}
+    for j in range(nv):
+        p = int(I[j, LI_PARENT])
+        anc[j] = 0 if p < 0 else (anc[p] | (1 << p))
+        P[j, PK_OFF:PK_OFF + 2] = plane(anchor[j] - (anchor[p] if p >= 0 else 0.0))
+        P[j, PK_DIR:PK_DIR + 2] = (sign[j], 0.0) if model.jnt_type[j] == HINGE else plane(axis[j])
+        b = int(model.jnt_body[j])
+        if last_of_body[b] == j and model.body_mass[b] > 0:
+            m = model.body_mass[b]
+            Ri = xmat[b] @ model.body_imat[b]                    # columns: inertial axes in the world at q = 0
+            In = model.body_inertia[b]
+            P[j, PK_MASS] = m
+            P[j, PK_COM:PK_COM + 2] = plane(xpos[b] + xmat[b] @ model.body_ipos[b] - anchor[j])
+            P[j, PK_INN] = float(n @ Ri @ np.diag(In) @ Ri.T @ n)
+            box = np.sqrt(np.maximum(1e-15, np.array([In[1] + In[2] - In[0], In[0] + In[2] - In[1], In[0] + In[1] - In[2]])) / m * 6.0)
+            d = box.sum() / 3.0
+            nk = Ri.T @ n
+            quart = np.array([box[1] ** 4 + box[2] ** 4, box[0] ** 4 + box[2] ** 4, box[0] ** 4 + box[1] ** 4])
+            P[j, PK_CLIN] = 3.0 * math.pi * d * model.viscosity
+            P[j, PK_KV1] = math.pi * d ** 3 * model.viscosity * float(nk @ nk)
+            P[j, PK_KV2] = model.density * float(np.sum(box * quart * np.abs(nk) ** 3)) / 64.0
+            for a in range(3):
+                P[j, PK_E + 2 * a:PK_E + 2 * a + 2] = plane(Ri[:, a])
+            P[j, PK_AK:PK_AK + 3] = 0.5 * model.density * np.array([box[1] * box[2], box[0] * box[2], box[0] * box[1]])
+    return P, anc, plane(model.gravity)
 
 
 # ------------------------------------------------------------------------------------------------ shipped models

@@ -94,6 +94,93 @@ def test_branched_3d_tree_matches_oracle(fixture):
     env.close()
 
 
+def _planar_switch(on):
+    from mjmpc_b200 import _lib
+    return _lib.lib().mjb_tree_use_planar(int(on))
+
+
+def test_planar_and_general_instantiations_agree(swimmer):
+    """swimmer.xml is a planar mechanism: the planar instantiation (3-vectors, registers) and the general 3-D one are
+    two formulations of the same step; both are held to the oracle above, here to each other."""
+    env, oracle = swimmer
+    assert env.dmodel.planar
+    rng = np.random.default_rng(11)
+    K, H = 128, 16
+    state = np.concatenate([rng.uniform(-.2, .2, 7), rng.uniform(-.5, .5, 7)])
+    state[3:7] = [1.2, -1.3, 0.4, 1.45]                                     # some joints near / into their limits
+    env.set_env_state({"qpos": state[:7], "qvel": state[7:]})
+    mean = torch.as_tensor(rng.normal(0, 0.6, (H, 4)), device=env.device)
+    noise = torch.as_tensor(rng.normal(0, 0.8, (K, H, 4)), device=env.device)
+    outs = []
+    for on in (1, 0):
+        old = _planar_switch(on)
+        try:
+            o = env.rollout_device(K, H, mean, noise, want_states=True, want_nefc=True)
+            outs.append({k: v.cpu().numpy().copy() for k, v in o.items()})
+        finally:
+            _planar_switch(old)
+    assert _rel(outs[0]["states"], outs[1]["states"]) < 1e-9 and _rel(outs[0]["costs"], outs[1]["costs"]) < 1e-9
+    assert np.array_equal(outs[0]["nefc"], outs[1]["nefc"]) and outs[0]["nefc"].sum() > 0
+    ref = oracle.rollout(state, mean.cpu().numpy(), noise.cpu().numpy(), 4)
+    for o in outs:
+        assert _rel(o["states"], ref["states"]) < TOL
+
+
+@pytest.mark.parametrize("n_axis", ["0 1 0", "0.6 0 0.8"])
+def test_planar_branched_mechanism_matches_oracle(n_axis):
+    """A half-cheetah-shaped planar tree (two legs off a torso on slide / slide / hinge, plane normal n, gravity in the
+    plane, springs, dampers, armature, limits, a fluid; no contacts): 9 dofs, branched -- the <9, tree> planar
+    instantiation with run-time parents, against the oracle and against the general instantiation."""
+    n = np.array([float(x) for x in n_axis.split()])
+    ex = np.cross(n, [0.0, 0.0, 1.0]) if abs(n[2]) < 0.9 else np.array([1.0, 0.0, 0.0])
+    ex = ex / np.linalg.norm(ex)
+    ez = np.cross(ex, n)
+    v = lambda a, b: "%.12g %.12g %.12g" % tuple(a * ex + b * ez)          # a point / direction of the plane
+
+    def leg(name, x, sgn):
+        return ('<body name="%sthigh" pos="%s"><joint name="%sthigh" axis="%s" range="-.6 .9" stiffness="24" damping="0.6"/>'
+                '<geom type="capsule" fromto="0 0 0 %s" size="0.046"/>'
+                '<body name="%sshin" pos="%s"><joint name="%sshin" axis="%s" range="-.8 .8" stiffness="18" damping="0.45"/>'
+                '<geom type="capsule" fromto="0 0 0 %s" size="0.04"/>'
+                '<body name="%sfoot" pos="%s"><joint name="%sfoot" axis="%s" range="-.4 .7" stiffness="12" damping="0.3"/>'
+                '<geom type="capsule" fromto="0 0 0 %s" size="0.035"/></body></body></body>'
+                % (name, v(x, 0), name, n_axis, v(sgn * .1, -.25), name, v(sgn * .1, -.25), name, n_axis, v(-sgn * .14, -.2),
+                   name, v(-sgn * .14, -.2), name, n_axis, v(sgn * .12, -.05)))
+    xml = ('<mujoco model="planar9"><compiler angle="radian" inertiafromgeom="true"/>'
+           '<default><joint armature="0.1" limited="true"/><geom contype="0" conaffinity="0"/>'
+           '<motor ctrllimited="true" ctrlrange="-1 1"/></default>'
+           '<option timestep="0.01" gravity="%s" density="30" viscosity="0.01"/><worldbody><body name="torso" pos="%s">'
+           '<joint name="rx" type="slide" axis="%s" limited="false" armature="0"/>'
+           '<joint name="rz" type="slide" axis="%s" limited="false" armature="0"/>'
+           '<joint name="ry" type="hinge" axis="%s" limited="false" armature="0"/>'
+           '<geom type="capsule" fromto="%s %s" size="0.046"/>%s%s</body></worldbody><actuator>%s</actuator></mujoco>'
+           % (v(0.3, -9.81), v(0, .7), v(1, 0), v(0, 1), n_axis, v(-.5, 0), v(.5, 0), leg("b", -.5, 1.0), leg("f", .5, -1.0),
+              "".join('<motor joint="%s" gear="%d"/>' % (j, g) for j, g in
+                      (("bthigh", 12), ("bshin", 9), ("bfoot", 6), ("fthigh", 12), ("fshin", 6), ("ffoot", 3)))))
+    model = T.compile_mjcf_string(xml)
+    assert model.nv == 9 and T.pack_planar(model) is not None
+    env = GpuTreeVecEnv(model, frame_skip=5, fwd_dof=0, w_fwd=1.0, w_ctrl=0.1, obs_qpos_start=1)      # half_cheetah.py:7-25
+    assert env.dmodel.planar
+    oracle = TreeOracle(model, T.solref_to_kb)
+    rng = np.random.default_rng(5)
+    K, H = 96, 8
+    state = np.concatenate([rng.uniform(-.3, .3, 9), rng.normal(0, 1.0, 9)])
+    mean, noise = rng.normal(0, 0.5, (H, 6)), rng.normal(0, 1.0, (K, H, 6))
+    nefc, nefc_ref, _ = _compare(env, oracle, state, mean, noise)
+    assert nefc == nefc_ref and nefc > 0
+    old = _planar_switch(0)
+    try:
+        _compare(env, oracle, state, mean, noise)
+    finally:
+        _planar_switch(old)
+    env.close()
+
+
+def test_non_planar_models_take_the_general_instantiation():
+    model = T.compile_mjcf(os.path.join(FIX, "tree3d.xml"))
+    assert T.pack_planar(model) is None
+
+
 def test_batched_controllers_share_one_launch(swimmer):
     env, oracle = swimmer
     rng = np.random.default_rng(4)

@@ -19,6 +19,10 @@ sizes = [int(x) for x in (sys.argv[sys.argv.index("--sizes") + 1] if "--sizes" i
 H = int(sys.argv[sys.argv.index("--horizon") + 1]) if "--horizon" in sys.argv else 32
 rng = np.random.default_rng(0)
 env = GpuTreeVecEnv.swimmer()
+if "--no-planar" in sys.argv:           # the general 3-D instantiation instead of the planar one
+    from mjmpc_b200 import _lib
+    _lib.lib().mjb_tree_use_planar(0)
+INST = "general" if "--no-planar" in sys.argv else "planar"
 state = dict(qpos=rng.uniform(-.1, .1, 7), qvel=rng.uniform(-.1, .1, 7))
 env.set_env_state(state)
 for K in sizes:
@@ -62,7 +66,7 @@ for K in sizes:
     ref = o.rollout(np.concatenate([state["qpos"], state["qvel"]]), mean.cpu().numpy(), nz, 4, nthreads=min(cores, 64))
     cpu_s = time.perf_counter() - t0
     err = float(np.abs(out["costs"][:ks].cpu().numpy() - ref["costs"]).max() / (1 + np.abs(ref["costs"]).max()))
-    print(json.dumps(dict(config="Swimmer-v0 tree rollout + MPPI", num_particles=K, horizon=H, frame_skip=4,
+    print(json.dumps(dict(config="Swimmer-v0 tree rollout + MPPI", instantiation=INST, num_particles=K, horizon=H, frame_skip=4,
                           rollout_kernel_ms=k_ms, particle_steps_per_s=K * H / (k_ms * 1e-3), mpc_step_ms=step_ms,
                           mpc_hz=1e3 / step_ms, e2e_ms=e2e_ms, rel_err_vs_oracle=err,
                           cpu_oracle=dict(particle_steps_per_s=ks * H / cpu_s, cores=min(cores, 64), sample="%d particles x %d steps" % (ks, H)))),
