@@ -135,14 +135,11 @@ template <int N> TR_HD void chol_solve(int n, double (*A)[N], double* b) {
 }
 
 // Soft joint limits, the constrained solve and mj_Euler for given M and f = qfrc_smooth (damping included); q, v
-// advanced in place.  Kept out of line: the planar kernel only comes here on substeps that have a limit row, and
-// one copy serves every instantiation.  Returns the number of limit rows.
+// advanced in place.  The general instantiation inlines it; the planar one calls the out-of-line copy below, and only
+// for the rare active set that its own in-register iteration does not settle.  Returns the number of limit rows.
 template <int N>
-#if defined(__CUDACC__)
-__host__ __device__ __noinline__
-#endif
-int limits_solve_integrate(int nv, const double* lk, const int* li, double h, double (*M)[N], double* f, bool damped,
-                           double* q, double* v) {
+TR_HD int limits_solve_integrate_inl(int nv, const double* lk, const int* li, double h, double (*M)[N], double* f, bool damped,
+                                     double* q, double* v) {
     // ---- joint-limit rows
     int nr = 0, rdof[N];
     double rs[N], aref[N], D[N];
@@ -234,6 +231,14 @@ int limits_solve_integrate(int nv, const double* lk, const int* li, double h, do
         q[i] += h * v[i];
     }
     return nr;
+}
+template <int N>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+int limits_solve_integrate(int nv, const double* lk, const int* li, double h, double (*M)[N], double* f, bool damped,
+                           double* q, double* v) {
+    return limits_solve_integrate_inl<N>(nv, lk, li, h, M, f, damped, q, v);
 }
 
 }  // namespace tree
@@ -480,7 +485,7 @@ TR_HD int substep(const double* lk, const int* li, const double* g, int nv_rt, d
         }
     }
 
-    return limits_solve_integrate<N>(nv, lk, li, h, M, f, damped, q, v);
+    return limits_solve_integrate_inl<N>(nv, lk, li, h, M, f, damped, q, v);
 }
 
 // PLANAR: the planar instantiation (rollout_tree_planar.cuh; NV > 0), else the general 3-D one.

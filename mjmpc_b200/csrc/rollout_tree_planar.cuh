@@ -10,7 +10,9 @@
 // the body) and their constant components along n (mjmpc_b200/envs/mjcf_tree.py: pack_planar).
 // Link frames are world-aligned at q = 0.  Parents are run-time data: a child picks its parent's state with predicated
 // selects over the links before it (static register indexing), or i - 1 when SERIAL.
-// Substeps without a limit row factor M + hB in registers; the others hand M and f to limits_solve_integrate.
+// The constrained solve and mj_Euler share one unrolled factorisation in registers, iterated over the active set of
+// limit rows; an active set that does not settle within 10 iterations goes to limits_solve_integrate (Newton with an
+// exact line search, out of line).
 #pragma once
 
 enum { PK_OFF = 0, PK_DIR = 2, PK_MASS = 4, PK_COM = 5, PK_INN = 7, PK_CLIN = 8, PK_KV1 = 9, PK_KV2 = 10, PK_E = 11, PK_AK = 17,
