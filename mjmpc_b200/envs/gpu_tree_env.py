@@ -233,6 +233,11 @@ class GpuSwimmerEnv:
         reward_ctrl = -1e-4 * float(np.square(a).sum())
         return self.get_obs(), -float(out["costs"][0, 0].item()), False, dict(reward_fwd=reward_fwd, reward_ctrl=reward_ctrl)
 
+    def self_clearance(self):
+        """Smallest gap between non-adjacent capsules in the current pose: positive = inside the contact-free subset
+        the kernel simulates (MuJoCo would generate a capsule-capsule contact below zero)."""
+        return mjcf_tree.self_clearance(self.sim.model, self.qpos)
+
     def evaluate_success(self, trajectories):
         return 0.0
 

@@ -114,6 +114,7 @@ class TreeModel:
     act_ctrlrange: np.ndarray     # (nu, 2)
     dof_invweight0: np.ndarray = None
     ignored: List[str] = field(default_factory=list)
+    shapes: list = field(default_factory=list)     # colliding capsules / spheres: (body, end 0, end 1, radius), body frame
 
     @property
     def nv(self):
@@ -278,7 +279,7 @@ def compile_mjcf_root(root, allow_contacts: str = "error") -> TreeModel:
                     solimp=_solimp(a.get("solimplimit"))))
             if be.find("freejoint") is not None:
                 raise UnsupportedMjcf("free joint")
-            parts, collides = [], False
+            parts, collides, shapes = [], False, []
             for ge in be.findall("geom"):
                 a = defaults.resolve(ge, cc)
                 mp = _geom_mass_props(a, angle_scale)
@@ -286,6 +287,16 @@ def compile_mjcf_root(root, allow_contacts: str = "error") -> TreeModel:
                     parts.append(mp)
                 if int(a.get("contype", "1")) != 0 or int(a.get("conaffinity", "1")) != 0:
                     collides = True
+                    if mp is not None and a.get("type", "sphere") in ("capsule", "sphere"):
+                        # the colliding shape as a segment + radius (a sphere is a segment of length 0): what
+                        # self_clearance() needs to say whether a configuration is inside the contact-free subset
+                        size = _f(a.get("size", "0"))
+                        if "fromto" in a:
+                            ft = _f(a["fromto"], 6)
+                            shapes.append((ft[:3], ft[3:], float(size[0])))
+                        else:
+                            half = float(size[1]) if a.get("type") == "capsule" else 0.0
+                            shapes.append((mp[1] - mp[3][:, 2] * half, mp[1] + mp[3][:, 2] * half, float(size[0])))
             inertial = be.find("inertial")
             if inertial is not None and from_geom != "true":
                 a = inertial.attrib
@@ -296,7 +307,8 @@ def compile_mjcf_root(root, allow_contacts: str = "error") -> TreeModel:
             elif from_geom == "false":
                 parts = []
             raw.append(dict(parent=parent, pos=_f(be.get("pos", "0 0 0"), 3), mat=_orientation(be.attrib, angle_scale),
-                            joints=joints, parts=parts, name=be.get("name", "body%d" % len(raw)), collides=collides))
+                            joints=joints, parts=parts, name=be.get("name", "body%d" % len(raw)), collides=collides,
+                            shapes=shapes))
             walk(be, len(raw) - 1, cc)
 
     wb = root.find("worldbody")
@@ -352,6 +364,11 @@ def compile_mjcf_root(root, allow_contacts: str = "error") -> TreeModel:
         for (m, c, I, R) in b["parts"]:
             parts_of[host].append((m, frame_pos[i] + frame_mat[i] @ c, frame_mat[i] @ I @ frame_mat[i].T, frame_mat[i] @ R))
 
+    shapes = []          # (moving body, end 0, end 1, radius) in the body frame
+    for i, b in enumerate(raw):
+        if frame_parent[i] >= 0:
+            for (p0, p1, rad) in b["shapes"]:
+                shapes.append((index[frame_parent[i]], frame_pos[i] + frame_mat[i] @ p0, frame_pos[i] + frame_mat[i] @ p1, rad))
     body_parent = np.array([index.get(raw[r]["host_parent"], -1) for r in moving], int)
     body_pos = np.array([raw[r]["host_pos"] for r in moving])
     body_mat = np.array([raw[r]["host_mat"] for r in moving])
@@ -409,7 +426,8 @@ def compile_mjcf_root(root, allow_contacts: str = "error") -> TreeModel:
         jnt_stiffness=np.array([j["stiffness"] for _, j in J]), jnt_springref=np.array([j["springref"] for _, j in J]),
         jnt_solref=np.array([j["solref"] for _, j in J]), jnt_solimp=np.array([j["solimp"] for _, j in J]),
         jnt_names=names, act_dof=np.array(act_dof, int), act_gear=np.array(gear, float),
-        act_ctrllimited=np.array(cl, bool), act_ctrlrange=np.array(cr, float).reshape(-1, 2), ignored=ignored)
+        act_ctrllimited=np.array(cl, bool), act_ctrlrange=np.array(cr, float).reshape(-1, 2), ignored=ignored,
+        shapes=shapes)
     M0 = mass_matrix(model, np.zeros(nv))
     model.dof_invweight0 = np.diag(np.linalg.inv(M0)).copy()
     return model
@@ -467,6 +485,45 @@ def mass_matrix(model: TreeModel, q):
             a = model.body_parent[a]
         M += model.body_mass[b] * Jv.T @ Jv + Jw.T @ Iw @ Jw
     return M
+
+
+def _segment_distance(p1, q1, p2, q2):
+    """Distance between segments p1-q1 and p2-q2 (closest points by clamping, Ericson 5.1.9)."""
+    d1, d2, r = q1 - p1, q2 - p2, p1 - p2
+    a, e, f = d1 @ d1, d2 @ d2, d2 @ r
+    if a <= 1e-18 and e <= 1e-18:
+        return float(np.linalg.norm(r))
+    if a <= 1e-18:
+        s, t = 0.0, min(max(f / e, 0.0), 1.0)
+    else:
+        c = d1 @ r
+        if e <= 1e-18:
+            t, s = 0.0, min(max(-c / a, 0.0), 1.0)
+        else:
+            b = d1 @ d2
+            den = a * e - b * b
+            s = min(max((b * f - c * e) / den, 0.0), 1.0) if den > 1e-18 else 0.0
+            t = (b * s + f) / e
+            if t < 0.0:
+                t, s = 0.0, min(max(-c / a, 0.0), 1.0)
+            elif t > 1.0:
+                t, s = 1.0, min(max((b - c) / a, 0.0), 1.0)
+    return float(np.linalg.norm(p1 + d1 * s - p2 - d2 * t))
+
+
+def self_clearance(model: TreeModel, q) -> float:
+    """Smallest gap between colliding shapes of bodies that are not parent and child (MuJoCo filters those pairs):
+    positive = the configuration is inside the contact-free subset the kernel simulates.  inf without such pairs."""
+    xpos, xmat, _, _ = kinematics(model, np.asarray(q, float))
+    world = [(b, xpos[b] + xmat[b] @ p0, xpos[b] + xmat[b] @ p1, r) for (b, p0, p1, r) in model.shapes]
+    best = np.inf
+    for i in range(len(world)):
+        for j in range(i + 1, len(world)):
+            bi, bj = world[i][0], world[j][0]
+            if bi == bj or model.body_parent[bi] == bj or model.body_parent[bj] == bi:
+                continue
+            best = min(best, _segment_distance(world[i][1], world[i][2], world[j][1], world[j][2]) - world[i][3] - world[j][3])
+    return best
 
 
 def solref_to_kb(solref, solimp, timestep):

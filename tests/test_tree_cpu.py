@@ -174,6 +174,22 @@ def test_linear_momentum_drift_is_first_order_in_the_timestep():
     assert drift[0] > 1.0 and 7.0 < drift[0] / drift[1] < 13.0, drift
 
 
+def test_self_clearance_marks_the_contact_free_subset():
+    """swimmer.xml's non-adjacent capsules only touch when three consecutive joints fold beyond ~1.4 rad to the same
+    side; the compiler drops those contacts and self_clearance() says when a pose would have needed them."""
+    m = _model("swimmer")
+    assert len(m.shapes) == 5
+    q = np.zeros(7)
+    assert abs(T.self_clearance(m, q) - (0.3 - 0.07 - 0.06)) < 1e-12         # torso and link 2, end to end
+    q[3:6] = 1.5
+    assert T.self_clearance(m, q) < 0.0
+    q[3:6] = 1.3
+    assert T.self_clearance(m, q) > 0.1
+    q[3:7] = [1.5, 1.5, -1.5, -1.5]
+    assert T.self_clearance(m, q) > 0.1
+    assert T.self_clearance(_model("tree3d"), np.zeros(7)) == np.inf          # contype = conaffinity = 0
+
+
 def test_kernel_layout_matches_the_python_packer():
     """csrc/tree_model.h and mjcf_tree.py agree (host-only call into the library, no GPU work)."""
     import ctypes as C

@@ -226,13 +226,18 @@ def test_mppi_swims_forward():
                 filter_coeffs=[1.0, 0.0, 0.0])
     plant.reset(seed=0)
     x0 = plant.qpos[0]
-    total = 0.0
+    total, clear = 0.0, []
     for _ in range(60):
         a, _ = ctrl.optimize(plant.get_env_state())
         _, r, _, info = plant.step(a)
         total += r
+        clear.append(plant.self_clearance())
     assert plant.qpos[0] - x0 > 0.15, (plant.qpos[0] - x0, total)
     assert np.all(np.abs(plant.qpos[3:]) < 1.7)
+    # KNOWN LIMIT of the contact-free subset: this gait curls the swimmer up until non-adjacent capsules
+    # overlap (about a third of the steps), where MuJoCo would add capsule-capsule contacts; the plant reports it
+    clear = np.array(clear)
+    assert np.isfinite(clear).all() and clear.max() > 0.1 and clear.min() > -0.13
     plant.close(); sim.close()
 
 
