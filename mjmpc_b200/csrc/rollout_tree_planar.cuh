@@ -114,7 +114,7 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
             if (dlo < 0.0 || dhi < 0.0) {
                 const double side = dlo < 0.0 ? 1.0 : -1.0, dist = dlo < 0.0 ? dlo : dhi;
                 const double imp = impedance_call(L + LK_SOLIMP, dist);
-                rD[i] = 1.0 / fmax(1e-15, (1.0 - imp) * L[LK_INVW] / imp);
+                rD[i] = fmin(1e15, imp / ((1.0 - imp) * L[LK_INVW]));       // 1 / max(1e-15, (1 - imp) invweight / imp)
                 rS[i] = side;
                 rA[i] = -L[LK_SOLB] * (side * v[i]) - L[LK_SOLK] * imp * dist;
                 rows |= 1u << i;
@@ -153,8 +153,9 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
     }
 
     // Constrained solve + mj_Euler around ONE factorisation in registers.  phase 0: active-set iterations on
-    // M + sum_active D e e' (the first one, with the empty set, is the unconstrained acceleration; a set that reproduces
-    // itself is the exact minimiser of the convex piecewise-quadratic problem); phase 2: mj_Euler's solve, implicit in joint
+    // M + sum_active D e e' (a set that reproduces itself is the exact minimiser of the convex piecewise-quadratic
+    // problem, whatever set the iteration started from: the first guess comes from the decoupled accelerations
+    // f_i / M_ii, which is right for most rows and saves the unconstrained solve); phase 2: mj_Euler's solve, implicit in joint
     // damping, with the constraint force on the right-hand side.  No row: phase 2 at once.  A set that keeps changing
     // (it can cycle without a line search) goes to the out-of-line Newton solver with its exact line search.
     double A[NV][NV], b[NV], fc[NV];
@@ -162,7 +163,10 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
     int phase = rows ? 0 : 2;
     bool done = false;
 #pragma unroll
-    for (int i = 0; i < NV; i++) fc[i] = 0.0;
+    for (int i = 0; i < NV; i++) {
+        fc[i] = 0.0;
+        if ((rows >> i & 1) && rS[i] * f[i] < rA[i] * M[i][i]) act |= 1u << i;      // M_ii > 0
+    }
 #pragma unroll 1
     for (int it = 0; it < 10 && !done; it++) {
 #pragma unroll
