@@ -67,10 +67,10 @@ def main():
     base_seed = exp_params['seed']
     ep_length = exp_params['max_ep_length']
 
-    sim_env = GpuReacherVecEnv(n_workers=num_cpu) if reacher else sim_cls()
+    sim_env = GpuReacherVecEnv(n_workers=num_cpu) if reacher else sim_cls(n_workers=num_cpu) if swimmer else sim_cls()
     if dynamics_rand_params is not None:
-        if not reacher:
-            raise NotImplementedError("dynamics randomisation is implemented for the reacher model")
+        if not hasattr(sim_env, "randomize_dynamics"):
+            raise NotImplementedError("dynamics randomisation is implemented for the reacher and the MJCF-tree models")
         default_params, randomized_params = sim_env.randomize_dynamics(dynamics_rand_params, base_seed=base_seed)
         print('Randomized params (worker 0) = {}'.format(randomized_params[0]))
 

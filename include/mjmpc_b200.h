@@ -135,7 +135,11 @@ int mjb_rollout_lqr(const mjb_lqr_args* a, void* stream);
 typedef struct mjb_tree_model mjb_tree_model;
 mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* link_params, const int* link_ints,
                                       const double* globals, const double* planar_params, const int* planar_anc,
-                                      const double* planar_gravity, int device);   /* NULL + mjb_last_error on failure */
+                                      const double* planar_gravity, int n_instances, int device);
+                                      /* NULL + mjb_last_error on failure.  n_instances > 1: link_params (n, nv, LK_STRIDE) and
+                                       * planar_params (n, nv, PK_STRIDE) hold one model per worker -- the perturbed copies of
+                                       * randomize_dynamics (subproc_vec_env.py:304-312, gym_env_wrapper.py:367-416): same topology,
+                                       * different masses / inertias / dampings */
 void mjb_tree_model_destroy(mjb_tree_model* m);
 void mjb_tree_layout(int* out45);   /* the 45 layout constants of csrc/tree_model.h + rollout_tree_planar.cuh, in order */
 /* PLANAR MECHANISMS (all hinge axes parallel, all slides perpendicular to them -- swimmer.xml and half_cheetah.xml are):
@@ -146,6 +150,7 @@ void mjb_tree_layout(int* out45);   /* the 45 layout constants of csrc/tree_mode
 int mjb_tree_use_planar(int on);
 typedef struct {
     int K, H, frame_skip, particles_per_ctrl;
+    int particles_per_model;        /* K / number of workers: particle k runs model k / particles_per_model (K for one model) */
     int fwd_dof, obs_qpos_start;
     double w_fwd, w_ctrl;
     const double* state;            /* (n_ctrl, 2 nv): qpos, qvel (swimmer.py:33-49 get / set_env_state) */

@@ -115,6 +115,7 @@ class LqrArgs(C.Structure):
 class TreeRolloutArgs(C.Structure):
     _fields_ = [
         ("K", C.c_int), ("H", C.c_int), ("frame_skip", C.c_int), ("particles_per_ctrl", C.c_int),
+        ("particles_per_model", C.c_int),
         ("fwd_dof", C.c_int), ("obs_qpos_start", C.c_int), ("w_fwd", C.c_double), ("w_ctrl", C.c_double),
         ("state", C.c_void_p), ("mean", C.c_void_p),
         ("noise", C.c_void_p), ("noise_sk", c_ll), ("noise_st", c_ll), ("noise_sj", c_ll),

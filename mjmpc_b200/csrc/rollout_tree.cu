@@ -24,11 +24,11 @@
 #include <stdlib.h>
 
 struct mjb_tree_model {
-    int device, nv, nu, serial, planar;
-    double* d_lk;   // nv x LK_STRIDE
+    int device, nv, nu, serial, planar, n_inst;
+    double* d_lk;   // n_inst x nv x LK_STRIDE (per-worker models of randomize_dynamics share topology and globals)
     int* d_li;      // nv x LI_STRIDE
     double* d_g;    // TG_STRIDE
-    double* d_pk;   // planar mechanisms: nv x PK_STRIDE, then the in-plane gravity (2)
+    double* d_pk;   // planar mechanisms: n_inst x (nv x PK_STRIDE, then the in-plane gravity (2))
     int* d_anc;     // planar mechanisms: ancestor bit masks (nv)
 };
 
@@ -501,16 +501,21 @@ __global__ void __launch_bounds__(64) rollout_tree_kernel(const double* __restri
     __shared__ double s_pk[PLANAR ? N * PK_STRIDE + 2 : 1];
     __shared__ int s_anc[PLANAR ? N : 1];
     const int nv = NV > 0 ? NV : nv_rt;
+    // blocks are model-uniform: instance = block / blocks-per-model (one model: the plain particle numbering)
+    const int bpm = (a.particles_per_model + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int inst = blockIdx.x / bpm, local = (blockIdx.x % bpm) * blockDim.x + threadIdx.x;
+    g_lk += (long long)inst * nv * LK_STRIDE;
     for (int i = threadIdx.x; i < nv * LK_STRIDE; i += blockDim.x) s_lk[i] = g_lk[i];
     for (int i = threadIdx.x; i < nv * LI_STRIDE; i += blockDim.x) s_li[i] = g_li[i];
     if (threadIdx.x < TG_STRIDE) s_g[threadIdx.x] = g_g[threadIdx.x];
     if (PLANAR) {
+        g_pk += (long long)inst * (nv * PK_STRIDE + 2);
         for (int i = threadIdx.x; i < nv * PK_STRIDE + 2; i += blockDim.x) s_pk[i] = g_pk[i];
         for (int i = threadIdx.x; i < nv; i += blockDim.x) s_anc[i] = g_anc[i];
     }
     __syncthreads();
-    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= a.K) return;
+    const long long k = (long long)inst * a.particles_per_model + local;
+    if (local >= a.particles_per_model || k >= a.K) return;
     const int ctrl = (int)(k / a.particles_per_ctrl);
     const double* s0 = a.state + (long long)ctrl * 2 * nv;
     const double* mean = a.mean + (long long)ctrl * a.H * nu;
@@ -585,9 +590,10 @@ int g_use_planar = 1;
 
 extern "C" mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* link_params, const int* link_ints,
                                                  const double* globals, const double* planar_params,
-                                                 const int* planar_anc, const double* planar_gravity, int device) {
-    if (nv < 1 || nv > MJB_TREE_MAX_LINKS || nu < 0 || nu > nv || !link_params || !link_ints || !globals) {
-        mjb::set_error(MJB_EINVAL, "mjb_tree_model_create: 1 <= nv <= %d, nu <= nv, non-null blocks", MJB_TREE_MAX_LINKS);
+                                                 const int* planar_anc, const double* planar_gravity, int n_instances,
+                                                 int device) {
+    if (nv < 1 || nv > MJB_TREE_MAX_LINKS || nu < 0 || nu > nv || !link_params || !link_ints || !globals || n_instances < 1) {
+        mjb::set_error(MJB_EINVAL, "mjb_tree_model_create: 1 <= nv <= %d, nu <= nv, n_instances >= 1, non-null blocks", MJB_TREE_MAX_LINKS);
         return nullptr;
     }
     if ((planar_params != nullptr) != (planar_anc != nullptr) || (planar_params != nullptr) != (planar_gravity != nullptr)) {
@@ -603,16 +609,21 @@ extern "C" mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* l
         if (act >= nu) { mjb::set_error(MJB_EINVAL, "mjb_tree_model_create: link %d names actuator %d of %d", i, act, nu); return nullptr; }
     }
     if (cudaSetDevice(device) != cudaSuccess) { mjb::set_error(MJB_ECUDA, "mjb_tree_model_create: cudaSetDevice(%d) failed", device); return nullptr; }
-    mjb_tree_model* m = new mjb_tree_model{device, nv, nu, serial, planar_params != nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool ok = upload(&m->d_lk, link_params, (size_t)nv * LK_STRIDE) && upload(&m->d_li, link_ints, (size_t)nv * LI_STRIDE) &&
+    mjb_tree_model* m = new mjb_tree_model{device, nv, nu, serial, planar_params != nullptr, n_instances,
+                                           nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ok = upload(&m->d_lk, link_params, (size_t)n_instances * nv * LK_STRIDE) && upload(&m->d_li, link_ints, (size_t)nv * LI_STRIDE) &&
               upload(&m->d_g, globals, (size_t)TG_STRIDE);
     if (ok && m->planar) {
-        double pk[MJB_TREE_MAX_LINKS * PK_STRIDE + 2];
-        for (int i = 0; i < nv * PK_STRIDE; i++) pk[i] = planar_params[i];
-        pk[nv * PK_STRIDE] = planar_gravity[0];
-        pk[nv * PK_STRIDE + 1] = planar_gravity[1];
-        ok = upload(&m->d_pk, pk, (size_t)nv * PK_STRIDE + 2) && upload(&m->d_anc, planar_anc, (size_t)nv);
-        ok = ok && cudaStreamSynchronize(0) == cudaSuccess;      // pk lives on this stack frame
+        const size_t stride = (size_t)nv * PK_STRIDE + 2;
+        double* pk = (double*)malloc(sizeof(double) * stride * n_instances);
+        for (int n = 0; n < n_instances && pk; n++) {
+            for (int i = 0; i < nv * PK_STRIDE; i++) pk[n * stride + i] = planar_params[(size_t)n * nv * PK_STRIDE + i];
+            pk[n * stride + nv * PK_STRIDE] = planar_gravity[0];
+            pk[n * stride + nv * PK_STRIDE + 1] = planar_gravity[1];
+        }
+        ok = pk && upload(&m->d_pk, pk, stride * n_instances) && upload(&m->d_anc, planar_anc, (size_t)nv);
+        ok = ok && cudaStreamSynchronize(0) == cudaSuccess;      // pk is freed right here
+        free(pk);
     }
     if (!ok || cudaStreamSynchronize(0) != cudaSuccess) {
         mjb::set_error(MJB_ECUDA, "mjb_tree_model_create: device allocation / upload failed");
@@ -651,7 +662,9 @@ extern "C" int mjb_rollout_tree(const mjb_tree_model* m, const mjb_tree_rollout_
                 "Number of particles must be divisible by number of controllers");
     MJB_REQUIRE(a->fwd_dof >= 0 && a->fwd_dof < m->nv && a->obs_qpos_start >= 0 && a->obs_qpos_start <= m->nv,
                 "mjb_rollout_tree: fwd_dof / obs_qpos_start out of range");
-    const int blocks = (a->K + 63) / 64;
+    MJB_REQUIRE(a->particles_per_model >= 1 && a->K % a->particles_per_model == 0 && a->K / a->particles_per_model <= m->n_inst,
+                "Number of particles must be divisible by number of cpus");      /* (subproc_vec_env.py:140-141) */
+    const int blocks = (a->K / a->particles_per_model) * ((a->particles_per_model + 63) / 64);
     cudaStream_t st = (cudaStream_t)stream;
     using namespace mjb::tree;
     const bool planar = m->planar && g_use_planar;

@@ -15,9 +15,12 @@ from . import mjcf_tree
 
 
 class DeviceTreeModel:
-    """Device copy of a compiled tree (``mjb_tree_model``)."""
+    """Device copy of one compiled tree or of several perturbed copies of it (``mjb_tree_model``)."""
 
-    def __init__(self, model: mjcf_tree.TreeModel, device: int = 0):
+    def __init__(self, models, device: int = 0):
+        if isinstance(models, mjcf_tree.TreeModel):
+            models = [models]
+        model = models[0]
         L = _lib.lib()
         layout = (C.c_int * 45)()
         L.mjb_tree_layout(layout)
@@ -31,19 +34,21 @@ class DeviceTreeModel:
                 mjcf_tree.PK_KV1, mjcf_tree.PK_KV2, mjcf_tree.PK_E, mjcf_tree.PK_AK, mjcf_tree.PK_STRIDE]
         if list(layout) != mine:
             raise _lib.MjbError("parameter layout of mjcf_tree.py and csrc/tree_model.h differ")
-        P, I, G = mjcf_tree.pack_links(model)
-        self.nv, self.nu = model.nv, model.nu
-        planar = mjcf_tree.pack_planar(model)
-        self.planar = planar is not None
-        self._keep = (np.ascontiguousarray(P), np.ascontiguousarray(I, np.int32), np.ascontiguousarray(G))
+        packs = [mjcf_tree.pack_links(m) for m in models]
+        planars = [mjcf_tree.pack_planar(m) for m in models]
+        self.planar = all(p is not None for p in planars)
+        self.nv, self.nu, self.n_instances = model.nv, model.nu, len(models)
+        self._keep = (np.ascontiguousarray(np.stack([p[0] for p in packs])), np.ascontiguousarray(packs[0][1], np.int32),
+                      np.ascontiguousarray(packs[0][2]))
         pk = [None, None, None]
-        if planar is not None:
-            self._keep += (np.ascontiguousarray(planar[0]), np.ascontiguousarray(planar[1], np.int32), np.ascontiguousarray(planar[2]))
+        if self.planar:
+            self._keep += (np.ascontiguousarray(np.stack([p[0] for p in planars])), np.ascontiguousarray(planars[0][1], np.int32),
+                           np.ascontiguousarray(planars[0][2]))
             pk = [k.ctypes.data_as(C.c_void_p) for k in self._keep[3:]]
         self.handle = C.c_void_p(L.mjb_tree_model_create(
             C.c_int(model.nv), C.c_int(model.nu), self._keep[0].ctypes.data_as(C.c_void_p),
             self._keep[1].ctypes.data_as(C.c_void_p), self._keep[2].ctypes.data_as(C.c_void_p), pk[0], pk[1], pk[2],
-            C.c_int(device)))
+            C.c_int(len(models)), C.c_int(device)))
         if not self.handle:
             raise _lib.MjbError(L.mjb_last_error().decode())
 
@@ -64,12 +69,16 @@ class GpuTreeVecEnv:
     env on top of the model (swimmer.py:10-24: dof 0, 1, 1e-4, 2; half_cheetah.py:10-25: dof 0, 1, 0.1, 1)."""
 
     def __init__(self, model: mjcf_tree.TreeModel, frame_skip: int, fwd_dof: int = 0, w_fwd: float = 1.0,
-                 w_ctrl: float = 1e-4, obs_qpos_start: int = 2, device: int = 0):
+                 w_ctrl: float = 1e-4, obs_qpos_start: int = 2, device: int = 0, n_workers: int = 1):
         if not torch.cuda.is_available():
             raise _lib.MjbError("GpuTreeVecEnv needs a CUDA device (there is no CPU fallback)")
         self.model = model
+        self.n_workers = int(n_workers)          # the reference's num_cpu: one (possibly perturbed) model per worker
+        self._worker_models = [model] * self.n_workers
+        self._defaults = [dict() for _ in range(self.n_workers)]
+        self._device_index = device
         self.device = torch.device("cuda", device)
-        self.dmodel = DeviceTreeModel(model, device)
+        self.dmodel = DeviceTreeModel(self._worker_models, device)
         self.frame_skip, self.fwd_dof, self.w_fwd, self.w_ctrl = int(frame_skip), int(fwd_dof), float(w_fwd), float(w_ctrl)
         self.obs_qpos_start = int(obs_qpos_start)
         self.nv = model.nv
@@ -81,10 +90,26 @@ class GpuTreeVecEnv:
         self.action_lows, self.action_highs = lim[:, 0].copy(), lim[:, 1].copy()
 
     @classmethod
-    def swimmer(cls, device: int = 0, **model_kwargs):
+    def swimmer(cls, device: int = 0, n_workers: int = 1, **model_kwargs):
         """``Swimmer-v0``: swimmer.py:7 (frame_skip 4), :10-19 (reward), :21-24 (observation)."""
         model = mjcf_tree.compile_mjcf_string(mjcf_tree.swimmer_mjcf(**model_kwargs), allow_contacts="ignore")
-        return cls(model, frame_skip=4, fwd_dof=0, w_fwd=1.0, w_ctrl=1e-4, obs_qpos_start=2, device=device)
+        return cls(model, frame_skip=4, fwd_dof=0, w_fwd=1.0, w_ctrl=1e-4, obs_qpos_start=2, device=device, n_workers=n_workers)
+
+    def randomize_dynamics(self, param_dict, base_seed, worker_offset=0):
+        """Per-worker model perturbation, worker i seeded with base_seed + i * 12345 (subproc_vec_env.py:304-312 ->
+        gym_env_wrapper.py:367-416); particle k of a rollout runs the model of worker k // (K / n_workers).  Replaces
+        the device model (a CUDA graph captured before this call must be captured again)."""
+        defaults, randomized = [], []
+        for i in range(self.n_workers):
+            rng = np.random.RandomState(base_seed + (worker_offset + i) * 12345)
+            m, d, r = mjcf_tree.randomized_copy(self.model, param_dict, rng, self._defaults[i])
+            self._worker_models[i] = m
+            defaults.append(d)
+            randomized.append(r)
+        self.dmodel.close()
+        self.dmodel = DeviceTreeModel(self._worker_models, self._device_index)
+        self.state_generation += 1
+        return defaults, randomized
 
     # ---- state (swimmer.py:33-49: {'qpos', 'qvel'})
     def set_env_state(self, state_dicts):
@@ -121,12 +146,15 @@ class GpuTreeVecEnv:
             raise ValueError("mean has %d controller rows but %d states are set" % (mean.shape[0], n_ctrl))
         if K % n_ctrl != 0:
             raise ValueError("Number of particles must be divisible by number of controllers")
+        if K % self.n_workers != 0:
+            raise AssertionError("Number of particles must be divisible by number of cpus")
         mean = mean.contiguous()
         dev = self.device
         costs = torch.empty((H, K), dtype=torch.float64, device=dev).t()
         actions = torch.empty((H, nu, K), dtype=torch.float64, device=dev).permute(2, 0, 1)
         a = _lib.TreeRolloutArgs()
         a.K, a.H, a.frame_skip, a.particles_per_ctrl = K, H, self.frame_skip, K // n_ctrl
+        a.particles_per_model = K // self.n_workers
         a.fwd_dof, a.obs_qpos_start, a.w_fwd, a.w_ctrl = self.fwd_dof, self.obs_qpos_start, self.w_fwd, self.w_ctrl
         a.state, a.mean = self._state.data_ptr(), mean.data_ptr()
         if noise is not None:

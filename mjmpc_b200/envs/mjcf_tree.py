@@ -605,6 +605,44 @@ def pack_links(model: TreeModel):
     return P, I, G
 
 
+# ------------------------------------------------------------------------------------------------ domain randomisation
+def randomized_copy(model: TreeModel, param_dict: dict, rng: np.random.RandomState, defaults: dict = None):
+    """(model', defaults, randomized): the named fields perturbed as the reference does (gym_env_wrapper.py:367-416):
+    ``biased = (1 + bias) * default``, ``value ~ U(biased * (1 - noise), biased * (1 + noise))``, written into the model
+    arrays (qpos0 constants such as dof_invweight0 are NOT recomputed -- neither does mujoco_py).  Fields of this model
+    family: body_mass, body_inertia (the principal moments), dof_damping; dof_frictionloss / geom_* / sensor_noise do not
+    exist in the subset: a non-zero request raises, a zero one still consumes the reference's random draws."""
+    import copy
+    m = copy.deepcopy(model)
+    defaults = {} if defaults is None else defaults
+    randomized = {}
+    for param_id, entries in param_dict.items():
+        defaults.setdefault(param_id, {})
+        randomized.setdefault(param_id, {})
+        for name, (noise_scale, bias_scale) in entries.items():
+            if param_id == "body_mass":
+                idx, field_ = m.body_names.index(name), m.body_mass
+            elif param_id == "body_inertia":
+                idx, field_ = m.body_names.index(name), m.body_inertia
+            elif param_id == "dof_damping":
+                idx, field_ = m.jnt_names.index(name), m.jnt_damping
+            elif param_id in ("dof_frictionloss", "geom_size", "geom_friction", "sensor_noise"):
+                if noise_scale != 0.0 or bias_scale != 0.0:
+                    raise ValueError("dynamics field %s is not modelled by the GPU rollout" % param_id)
+                rng.uniform(size=3 if param_id in ("geom_size", "geom_friction") else None)
+                continue
+            else:
+                raise ValueError("Unknown dynamics field")
+            if name not in defaults[param_id]:
+                defaults[param_id][name] = copy.deepcopy(field_[idx])
+            cur = copy.deepcopy(defaults[param_id][name])
+            biased = (1.0 + bias_scale) * cur
+            val = rng.uniform(biased - biased * noise_scale, biased + biased * noise_scale)
+            field_[idx] = val
+            randomized[param_id][name] = val
+    return m, defaults, randomized
+
+
 # ------------------------------------------------------------------------------------------------ planar mechanisms
 # A tree whose hinge axes are all parallel (to n) and whose slides are all perpendicular to n moves in a plane: the
 # reference's swimmer (n = z) and half-cheetah (n = y) both do.  The kernel has a planar instantiation with 3-vectors

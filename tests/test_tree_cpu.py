@@ -102,6 +102,39 @@ def test_unsupported_elements_raise(bad, why):
                                   '</body></worldbody></mujoco>' % opt)
 
 
+def test_compiler_geometry_rules_closed_forms():
+    """Mass properties of every geom type, degree angles, nested default classes, class / childclass, <inertial>."""
+    xml = ('<mujoco><compiler inertiafromgeom="auto"/>'                                   # angle: degrees by default
+           '<default><geom contype="0" conaffinity="0" density="500"/><joint damping="0.2"/>'
+           '<default class="a"><joint range="-90 90" limited="true"/><default class="b"><joint armature="0.3"/></default></default>'
+           '</default><worldbody>'
+           '<body name="box" childclass="a"><joint name="j0" axis="0 0 1"/><geom type="box" size="0.1 0.2 0.3"/>'
+           '<body name="cyl" pos="1 0 0" euler="0 0 90"><joint name="j1" class="b" type="slide" axis="1 0 0" range="-1 2"/>'
+           '<geom type="cylinder" size="0.1 0.25" axisangle="1 0 0 90"/>'
+           '<body name="given" pos="0 1 0"><joint name="j2" class="main" axis="0 1 0"/>'
+           '<inertial pos="0.1 0 0" mass="2.5" diaginertia="0.3 0.2 0.1"/><geom type="sphere" size="0.5"/></body></body></body>'
+           '</worldbody></mujoco>')
+    m = T.compile_mjcf_string(xml)
+    assert m.nv == 3 and list(m.jnt_type) == [T.HINGE, T.SLIDE, T.HINGE]
+    # box 0.2 x 0.4 x 0.6 at density 500
+    mb = 500 * 0.2 * 0.4 * 0.6
+    np.testing.assert_allclose(m.body_mass[0], mb, rtol=1e-14)
+    np.testing.assert_allclose(m.body_inertia[0], mb / 12 * np.array([0.4 ** 2 + 0.6 ** 2, 0.2 ** 2 + 0.6 ** 2, 0.2 ** 2 + 0.4 ** 2]), rtol=1e-13)
+    # cylinder r 0.1, length 0.5, its axis turned from z to -y by the 90 degree axisangle
+    mc = 500 * math.pi * 0.01 * 0.5
+    np.testing.assert_allclose(m.body_mass[1], mc, rtol=1e-14)
+    np.testing.assert_allclose(m.body_inertia[1], [mc * (3 * 0.01 + 0.25) / 12] * 2 + [0.5 * mc * 0.01], rtol=1e-13)
+    np.testing.assert_allclose(np.abs(m.body_imat[1][:, 2]), [0, 1, 0], atol=1e-15)
+    np.testing.assert_allclose(m.body_mat[1], [[0, -1, 0], [1, 0, 0], [0, 0, 1]], atol=1e-15)        # euler 0 0 90 degrees
+    # <inertial> wins over the geom under inertiafromgeom="auto"
+    np.testing.assert_allclose([m.body_mass[2], *m.body_ipos[2], *m.body_inertia[2]], [2.5, 0.1, 0, 0, 0.3, 0.2, 0.1])
+    # defaults: class a (range in degrees for the hinge, limited), class b inherits a and adds armature; slide ranges are lengths
+    np.testing.assert_allclose(m.jnt_range[0], [-math.pi / 2, math.pi / 2], rtol=1e-15)
+    np.testing.assert_allclose(m.jnt_range[1], [-1, 2])
+    assert list(m.jnt_limited) == [True, True, False] and list(m.jnt_armature) == [0.0, 0.3, 0.0]
+    assert list(m.jnt_damping) == [0.2, 0.2, 0.2]
+
+
 def test_welded_body_in_a_fluid_is_rejected():
     xml = open(os.path.join(FIX, "tree3d_weld.xml")).read().replace('density="0" viscosity="0"', 'density="10" viscosity="0"')
     with pytest.raises(T.UnsupportedMjcf, match="welded"):

@@ -181,6 +181,39 @@ def test_non_planar_models_take_the_general_instantiation():
     assert T.pack_planar(model) is None
 
 
+@pytest.mark.parametrize("per_worker", [4, 96])
+def test_per_worker_randomised_models(per_worker):
+    """randomize_dynamics (subproc_vec_env.py:304-312, gym_env_wrapper.py:367-416): every worker's particles run that
+    worker's perturbed model -- against one oracle model per worker; the reference's rule and seeding on the host."""
+    n_workers, H = 5, 6
+    env = GpuTreeVecEnv.swimmer(n_workers=n_workers)
+    spec = dict(body_mass={"torso": [0.3, 0.1], "link3": [0.2, 0.0]}, body_inertia={"link1": [0.2, -0.1]},
+                dof_damping={"j2": [0.0, 0.0]}, geom_friction={"x": [0.0, 0.0]})
+    d, r = env.randomize_dynamics(spec, base_seed=7)
+    rng0 = np.random.RandomState(7 + 2 * 12345)
+    m0 = float(env.model.body_mass[0]) * 1.1
+    assert abs(r[2]["body_mass"]["torso"] - rng0.uniform(m0 - 0.3 * m0, m0 + 0.3 * m0)) < 1e-15
+    assert d[0]["body_mass"]["torso"] == env.model.body_mass[0] and len({x["body_mass"]["torso"] for x in r}) == n_workers
+    K = n_workers * per_worker
+    rng = np.random.default_rng(8)
+    state = rng.uniform(-.2, .2, 14)
+    env.set_env_state({"qpos": state[:7], "qvel": state[7:]})
+    mean, noise = rng.normal(0, 0.4, (H, 4)), rng.normal(0, 0.6, (K, H, 4))
+    out = env.rollout_device(K, H, torch.as_tensor(mean, device=env.device), torch.as_tensor(noise, device=env.device),
+                             want_states=True)
+    states = out["states"].cpu().numpy()
+    for w in range(n_workers):
+        sl = slice(w * per_worker, (w + 1) * per_worker)
+        ref = TreeOracle(env._worker_models[w], T.solref_to_kb).rollout(state, mean, noise[sl], 4)
+        assert _rel(states[sl], ref["states"]) < TOL
+    assert _rel(states[:per_worker], states[per_worker:2 * per_worker]) > 1e-6           # the models really differ
+    with pytest.raises(AssertionError, match="divisible by number of cpus"):
+        env.rollout_device(K + 1, H, torch.zeros(H, 4, dtype=torch.float64, device=env.device), None)
+    with pytest.raises(ValueError):
+        env.randomize_dynamics(dict(dof_frictionloss={"j1": [0.1, 0.0]}), base_seed=1)
+    env.close()
+
+
 def test_batched_controllers_share_one_launch(swimmer):
     env, oracle = swimmer
     rng = np.random.default_rng(4)
