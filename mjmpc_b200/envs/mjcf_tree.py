@@ -434,10 +434,14 @@ def compile_mjcf_root(root, allow_contacts: str = "error") -> TreeModel:
 
 
 def _solimp(s):
+    """solimp (d0, dmax, width, midpoint, power) with MuJoCo's clamps [EXT: getsolparam]: impedances and the midpoint
+    into [mjMINIMP, mjMAXIMP] = [0.0001, 0.9999], width >= 0, power >= 1 (half_cheetah.xml asks for d0 = 0)."""
     v = np.array([0.9, 0.95, 0.001, 0.5, 2.0])
     if s is not None:
         g = _f(s)
         v[:g.size] = g
+    v[0], v[1], v[3] = (min(0.9999, max(0.0001, x)) for x in (v[0], v[1], v[3]))
+    v[2], v[4] = max(0.0, v[2]), max(1.0, v[4])
     return v
 
 

@@ -38,6 +38,14 @@ def _v(s):
     return np.array([float(x) for x in s.split()])
 
 
+def _clamp_solimp(v):
+    """MuJoCo clamps the impedances and the midpoint to [1e-4, 1 - 1e-4], the width to >= 0, the power to >= 1."""
+    v = np.array(v, float)
+    v[[0, 1, 3]] = np.clip(v[[0, 1, 3]], 1e-4, 1 - 1e-4)
+    v[2], v[4] = max(0.0, v[2]), max(1.0, v[4])
+    return v
+
+
 # ------------------------------------------------------------------------------------------------ quaternions
 def qmul(a, b):
     return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3],
@@ -149,8 +157,8 @@ def read_model(xml_path: str) -> dict:
                                    damping=float(a.get("damping", "0")), armature=float(a.get("armature", "0")),
                                    stiffness=float(a.get("stiffness", "0")), springref=float(a.get("springref", "0")),
                                    solref=_v(a.get("solreflimit", "0.02 1")),
-                                   solimp=np.concatenate([_v(a["solimplimit"]), [0.9, 0.95, 0.001, 0.5, 2.0][len(_v(a["solimplimit"])):]])
-                                   if "solimplimit" in a else np.array([0.9, 0.95, 0.001, 0.5, 2.0]),
+                                   solimp=_clamp_solimp(np.concatenate([_v(a["solimplimit"]), [0.9, 0.95, 0.001, 0.5, 2.0][len(_v(a["solimplimit"])):]])
+                                                        if "solimplimit" in a else np.array([0.9, 0.95, 0.001, 0.5, 2.0])),
                                    name=a.get("name", "")))
             if len(geoms) != 1:
                 raise ValueError("tree_ref reads one geom per body")       # principal-axis composition not needed here

@@ -135,6 +135,33 @@ def test_compiler_geometry_rules_closed_forms():
     assert list(m.jnt_damping) == [0.2, 0.2, 0.2]
 
 
+def test_solimp_is_clamped_like_mujoco_and_both_restatements_agree(tmp_path):
+    """half_cheetah.xml's joints ask for solimplimit="0 .8 .03": MuJoCo clamps d0 to 1e-4 (a zero impedance would make
+    the regulariser infinite).  The C oracle and the independent restatement agree on such a model."""
+    from oracle import tree_ref
+    xml = ('<mujoco><compiler angle="radian" inertiafromgeom="true"/><option timestep="0.01" gravity="0 0 -9.81"/>'
+           '<default><joint limited="true" solimplimit="0 .8 .03" solreflimit=".02 1" armature="0.1" damping="0.01" stiffness="8"/>'
+           '<geom contype="0" conaffinity="0"/></default><worldbody><body pos="0 0 1">'
+           '<joint name="a" axis="0 1 0" range="-.5 .7"/><geom type="capsule" fromto="0 0 0 0.3 0 -0.2" size="0.05"/>'
+           '<body pos="0.3 0 -0.2"><joint name="b" axis="0 1 0" range="-.4 .4"/><geom type="capsule" fromto="0 0 0 -0.1 0 -0.3" size="0.04"/>'
+           '</body></body></worldbody><actuator><motor joint="a" gear="30"/><motor joint="b" gear="10"/></actuator></mujoco>')
+    f = tmp_path / "m.xml"
+    f.write_text(xml)
+    m = T.compile_mjcf(str(f))
+    np.testing.assert_allclose(m.jnt_solimp[0], [1e-4, 0.8, 0.03, 0.5, 2.0])
+    o, rm = TreeOracle(m, T.solref_to_kb), tree_ref.read_model(str(f))
+    rng = np.random.default_rng(0)
+    hit = 0
+    for _ in range(20):
+        q, v, u = rng.uniform(-.9, .9, 2), rng.normal(0, 2, 2), rng.normal(0, 1, 2)
+        a = o.substep(q, v, u)
+        q2, v2, info = tree_ref.step(rm, q, v, u)
+        assert a["nefc"] == info["nefc"]
+        hit += a["nefc"] > 0
+        assert _rel(a["q"], q2) < 1e-11 and _rel(a["v"], v2) < 1e-10 and _rel(a["constraint"], info["constraint"]) < 1e-10
+    assert hit >= 8
+
+
 def test_welded_body_in_a_fluid_is_rejected():
     xml = open(os.path.join(FIX, "tree3d_weld.xml")).read().replace('density="0" viscosity="0"', 'density="10" viscosity="0"')
     with pytest.raises(T.UnsupportedMjcf, match="welded"):
