@@ -115,6 +115,7 @@ class TreeModel:
     dof_invweight0: np.ndarray = None
     ignored: List[str] = field(default_factory=list)
     shapes: list = field(default_factory=list)     # colliding capsules / spheres: (body, end 0, end 1, radius), body frame
+    contacts: list = field(default_factory=list)   # candidate contact pairs (allow_contacts="model"), see compile_mjcf_root
 
     @property
     def nv(self):
@@ -202,6 +203,33 @@ def _geom_mass_props(a, angle_scale):
     return mass, pos, R @ np.diag(mass * unit) @ R.T, R
 
 
+def _collision_record(a, mp, angle_scale):
+    """What collision detection needs from one geom, or None when it cannot collide (contype = conaffinity = 0)."""
+    ct, ca = int(a.get("contype", "1")), int(a.get("conaffinity", "1"))
+    if ct == 0 and ca == 0:
+        return None
+    kind = a.get("type", "sphere")
+    size = _f(a.get("size", "0"))
+    rec = dict(kind=kind, contype=ct, conaffinity=ca, condim=int(a.get("condim", "3")),
+               friction=float(_f(a.get("friction", "1 0.005 0.0001"))[0]), solref=_f(a.get("solref", "0.02 1"), 2),
+               solimp=_solimp(a.get("solimp")), margin=float(a.get("margin", "0")), gap=float(a.get("gap", "0")),
+               name=a.get("name", ""))
+    if kind == "plane":
+        R = _orientation(a, angle_scale)
+        rec.update(p0=_f(a.get("pos", "0 0 0"), 3), p1=R[:, 2].copy(), radius=0.0)     # a point of the plane, its normal
+    elif kind in ("capsule", "sphere"):
+        if "fromto" in a:
+            ft = _f(a["fromto"], 6)
+            rec.update(p0=ft[:3], p1=ft[3:], radius=float(size[0]))
+        else:
+            half = float(size[1]) if kind == "capsule" else 0.0
+            rec.update(p0=mp[1] - mp[3][:, 2] * half, p1=mp[1] + mp[3][:, 2] * half, radius=float(size[0]))
+    else:
+        rec.update(p0=None, p1=None, radius=0.0)            # a colliding shape the subset has no detection for
+    rec["com"] = None
+    return rec
+
+
 def _orientation(a, angle_scale):
     if "quat" in a:
         return quat_to_mat(_f(a["quat"], 4))
@@ -285,18 +313,10 @@ def compile_mjcf_root(root, allow_contacts: str = "error") -> TreeModel:
                 mp = _geom_mass_props(a, angle_scale)
                 if mp is not None:
                     parts.append(mp)
-                if int(a.get("contype", "1")) != 0 or int(a.get("conaffinity", "1")) != 0:
+                rec = _collision_record(a, mp, angle_scale)
+                if rec is not None:
                     collides = True
-                    if mp is not None and a.get("type", "sphere") in ("capsule", "sphere"):
-                        # the colliding shape as a segment + radius (a sphere is a segment of length 0): what
-                        # self_clearance() needs to say whether a configuration is inside the contact-free subset
-                        size = _f(a.get("size", "0"))
-                        if "fromto" in a:
-                            ft = _f(a["fromto"], 6)
-                            shapes.append((ft[:3], ft[3:], float(size[0])))
-                        else:
-                            half = float(size[1]) if a.get("type") == "capsule" else 0.0
-                            shapes.append((mp[1] - mp[3][:, 2] * half, mp[1] + mp[3][:, 2] * half, float(size[0])))
+                    shapes.append(rec)
             inertial = be.find("inertial")
             if inertial is not None and from_geom != "true":
                 a = inertial.attrib
@@ -306,6 +326,10 @@ def compile_mjcf_root(root, allow_contacts: str = "error") -> TreeModel:
                 parts = [(float(a["mass"]), _f(a["pos"], 3), Ri @ np.diag(_f(a["diaginertia"], 3)) @ Ri.T, Ri)]
             elif from_geom == "false":
                 parts = []
+            mtot = sum(p_[0] for p_ in parts)
+            own_com = sum(p_[0] * p_[1] for p_ in parts) / mtot if mtot > 0 else np.zeros(3)
+            for rec in shapes:
+                rec["com"] = own_com                       # body_invweight0 is taken at the centre of mass of the geom's own body
             raw.append(dict(parent=parent, pos=_f(be.get("pos", "0 0 0"), 3), mat=_orientation(be.attrib, angle_scale),
                             joints=joints, parts=parts, name=be.get("name", "body%d" % len(raw)), collides=collides,
                             shapes=shapes))
@@ -314,17 +338,10 @@ def compile_mjcf_root(root, allow_contacts: str = "error") -> TreeModel:
     wb = root.find("worldbody")
     walk(wb, -1, None)
 
-    # contacts: the subset has none.  A pair can collide when (contype_a & conaffinity_b) | (contype_b & conaffinity_a)
-    # and the bodies are not parent and child; with several colliding geoms on non-adjacent bodies the model is outside
-    # the subset unless the caller accepts dropping them.
-    n_coll = sum(1 for b in raw if b["collides"])
-    world_coll = any(int(defaults.resolve(g, None).get("contype", "1")) != 0 or
-                     int(defaults.resolve(g, None).get("conaffinity", "1")) != 0 for g in wb.findall("geom"))
-    if n_coll > 2 or (world_coll and n_coll > 0):
-        msg = "%d bodies carry colliding geoms%s" % (n_coll, " and so does the world" if world_coll else "")
-        if allow_contacts != "ignore":
-            raise UnsupportedMjcf("contacts are outside the subset: " + msg + " (allow_contacts='ignore' drops them)")
-        ignored.append("contacts dropped: " + msg)
+    world_shapes = [r for r in (_collision_record(defaults.resolve(g, None), None, angle_scale) if
+                                defaults.resolve(g, None).get("type", "sphere") == "plane" else
+                                _collision_record(defaults.resolve(g, None), _geom_mass_props(defaults.resolve(g, None), angle_scale),
+                                                  angle_scale) for g in wb.findall("geom")) if r is not None]
 
     # ---- weld joint-less bodies into their parents; drop world-fixed ones
     nraw = len(raw)
@@ -364,11 +381,53 @@ def compile_mjcf_root(root, allow_contacts: str = "error") -> TreeModel:
         for (m, c, I, R) in b["parts"]:
             parts_of[host].append((m, frame_pos[i] + frame_mat[i] @ c, frame_mat[i] @ I @ frame_mat[i].T, frame_mat[i] @ R))
 
-    shapes = []          # (moving body, end 0, end 1, radius) in the body frame
+    geoms = []           # colliding geoms: record + moving body (-1 = world) with coordinates in that body's frame
+    for rec in world_shapes:
+        geoms.append(dict(rec, body=-1))
     for i, b in enumerate(raw):
-        if frame_parent[i] >= 0:
-            for (p0, p1, rad) in b["shapes"]:
-                shapes.append((index[frame_parent[i]], frame_pos[i] + frame_mat[i] @ p0, frame_pos[i] + frame_mat[i] @ p1, rad))
+        fp, fm = (frame_pos[i], frame_mat[i])
+        for rec in b["shapes"]:
+            g = dict(rec, body=index[frame_parent[i]] if frame_parent[i] >= 0 else -1)
+            if rec["p0"] is not None:
+                g["p0"] = fp + fm @ rec["p0"]
+                g["p1"] = fm @ rec["p1"] if rec["kind"] == "plane" else fp + fm @ rec["p1"]
+                g["com"] = fp + fm @ rec["com"]
+            geoms.append(g)
+    shapes = [(g["body"], g["p0"], g["p1"], g["radius"]) for g in geoms if g["body"] >= 0 and g["kind"] in ("capsule", "sphere")]
+    bp = [index.get(raw[r]["host_parent"], -1) for r in moving]
+    pairs = []
+    for i in range(len(geoms)):
+        for j in range(i + 1, len(geoms)):
+            a, b = geoms[i], geoms[j]
+            if a["body"] == b["body"]:
+                continue                                         # same rigid assembly (or both fixed to the world)
+            if a["body"] >= 0 and b["body"] >= 0 and (bp[a["body"]] == b["body"] or bp[b["body"]] == a["body"]):
+                continue                                         # parent and child (the world is nobody's filtered parent)
+            if not ((a["contype"] & b["conaffinity"]) or (b["contype"] & a["conaffinity"])):
+                continue
+            pairs.append((a, b) if (a["kind"] == "plane" or b["kind"] != "plane") else (b, a))    # the plane is geom 1
+    contacts = []
+    if pairs:
+        msg = "%d geom pairs can collide" % len(pairs)
+        if allow_contacts == "error":
+            raise UnsupportedMjcf("contacts are outside the default subset: " + msg +
+                                  " (allow_contacts='ignore' drops them, 'model' keeps plane / capsule / sphere pairs)")
+        if allow_contacts == "ignore":
+            ignored.append("contacts dropped: " + msg)
+        else:
+            for a, b in pairs:
+                ok = a["kind"] in ("plane", "capsule", "sphere") and b["kind"] in ("capsule", "sphere") and \
+                    (a["kind"] != "plane" or a["body"] < 0)
+                if not ok:
+                    raise UnsupportedMjcf("no collision detection for a %s against a %s" % (a["kind"], b["kind"]))
+                if a["condim"] != 3 or b["condim"] != 3 or a["margin"] or b["margin"] or a["gap"] or b["gap"]:
+                    raise UnsupportedMjcf("contacts: condim 3, margin 0, gap 0 only")
+                if not (np.array_equal(a["solref"], b["solref"]) and np.array_equal(a["solimp"], b["solimp"])):
+                    raise UnsupportedMjcf("contacts: geoms with different solref / solimp (solmix) are not supported")
+                contacts.append(dict(kind="plane" if a["kind"] == "plane" else "capsule", body1=a["body"], body2=b["body"],
+                                     a0=a["p0"], a1=a["p1"], ra=a["radius"], b0=b["p0"], b1=b["p1"], rb=b["radius"],
+                                     com1=a.get("com"), com2=b.get("com"), mu=max(a["friction"], b["friction"]),
+                                     solref=a["solref"].copy(), solimp=a["solimp"].copy()))
     body_parent = np.array([index.get(raw[r]["host_parent"], -1) for r in moving], int)
     body_pos = np.array([raw[r]["host_pos"] for r in moving])
     body_mat = np.array([raw[r]["host_mat"] for r in moving])
@@ -427,9 +486,21 @@ def compile_mjcf_root(root, allow_contacts: str = "error") -> TreeModel:
         jnt_solref=np.array([j["solref"] for _, j in J]), jnt_solimp=np.array([j["solimp"] for _, j in J]),
         jnt_names=names, act_dof=np.array(act_dof, int), act_gear=np.array(gear, float),
         act_ctrllimited=np.array(cl, bool), act_ctrlrange=np.array(cr, float).reshape(-1, 2), ignored=ignored,
-        shapes=shapes)
+        shapes=shapes, contacts=contacts)
     M0 = mass_matrix(model, np.zeros(nv))
-    model.dof_invweight0 = np.diag(np.linalg.inv(M0)).copy()
+    Minv = np.linalg.inv(M0)
+    model.dof_invweight0 = np.diag(Minv).copy()
+    if contacts:
+        # body_invweight0 (translational) = tr(Jp M^-1 Jp') / 3 at the centre of mass of the geom's body, qpos0 (mj_setConst)
+        xpos, xmat, anchor, axis = kinematics(model, np.zeros(nv))
+        for c in contacts:
+            w = 0.0
+            for body, com in ((c["body1"], c["com1"]), (c["body2"], c["com2"])):
+                if body < 0:
+                    continue
+                Jp = point_jacobian(model, body, xpos[body] + xmat[body] @ com, anchor, axis)
+                w += float(np.trace(Jp @ Minv @ Jp.T)) / 3.0
+            c["invweight"] = w
     return model
 
 
@@ -465,6 +536,17 @@ def kinematics(model: TreeModel, q):
                 pos = anchor[j] - R @ model.jnt_pos[j]
         xpos[b], xmat[b] = pos, R
     return xpos, xmat, anchor, axis
+
+
+def point_jacobian(model: TreeModel, body: int, point, anchor, axis):
+    """Translational Jacobian (3, nv) of a world point moving with ``body``."""
+    Jp = np.zeros((3, model.nv))
+    a = body
+    while a >= 0:
+        for j in np.nonzero(model.jnt_body == a)[0]:
+            Jp[:, j] = axis[j] if model.jnt_type[j] == SLIDE else np.cross(axis[j], point - anchor[j])
+        a = model.body_parent[a]
+    return Jp
 
 
 def mass_matrix(model: TreeModel, q):

@@ -80,7 +80,7 @@ def qmat(q):
 
 
 # ------------------------------------------------------------------------------------------------ model
-def read_model(xml_path: str) -> dict:
+def read_model(xml_path: str, contacts: bool = False) -> dict:
     root = ET.parse(xml_path).getroot()
     comp = root.find("compiler").attrib if root.find("compiler") is not None else {}
     deg = comp.get("angle", "degree") != "radian"
@@ -148,6 +148,10 @@ def read_model(xml_path: str) -> dict:
                 else:
                     raise ValueError(kind)
                 geoms.append((m, pos, quat, I))
+                coll = dict(r=r, half=half, contype=int(a.get("contype", "1")), conaffinity=int(a.get("conaffinity", "1")),
+                            mu=_v(a.get("friction", "1 0.005 0.0001"))[0], solref=_v(a.get("solref", "0.02 1")),
+                            solimp=_clamp_solimp(np.concatenate([_v(a.get("solimp", "0.9 0.95 0.001")), [0.5, 2.0]])[:5]
+                                                 if len(_v(a.get("solimp", "0.9 0.95 0.001"))) < 5 else _v(a["solimp"])))
             joints = []
             for je in be.findall("joint"):
                 a = attrs(je, c2)
@@ -164,7 +168,7 @@ def read_model(xml_path: str) -> dict:
                 raise ValueError("tree_ref reads one geom per body")       # principal-axis composition not needed here
             m, c, gq, I = geoms[0]
             bodies.append(dict(parent=parent, pos=_v(be.get("pos", "0 0 0")), quat=orient(be.attrib), joints=joints,
-                               mass=m, ipos=c, iquat=gq, inertia=I))
+                               mass=m, ipos=c, iquat=gq, inertia=I, coll=coll))
             walk(be, len(bodies) - 1, c2)
 
     walk(root.find("worldbody"), -1, None)
@@ -178,7 +182,29 @@ def read_model(xml_path: str) -> dict:
     model = dict(bodies=bodies, dofs=dofs, motors=motors, nv=len(dofs), h=float(opt.get("timestep", "0.002")),
                  gravity=_v(opt.get("gravity", "0 0 -9.81")), rho=float(opt.get("density", "0")),
                  mu=float(opt.get("viscosity", "0")))
-    model["invweight0"] = np.diag(np.linalg.inv(mass_matrix(model, np.zeros(model["nv"])))).copy()
+    Minv0 = np.linalg.inv(mass_matrix(model, np.zeros(model["nv"])))
+    model["invweight0"] = np.diag(Minv0).copy()
+    # contacts (read only when asked: read_model(..., contacts=True)): world planes and the bodies' capsules / spheres
+    model["planes"], model["pairs"] = [], []
+    if contacts:
+        for ge in root.find("worldbody").findall("geom"):
+            a = attrs(ge, None)
+            if a.get("type", "sphere") == "plane" and (int(a.get("contype", "1")) or int(a.get("conaffinity", "1"))):
+                model["planes"].append(dict(point=_v(a.get("pos", "0 0 0")), normal=qrot(orient(a), np.array([0.0, 0, 1])),
+                                            contype=int(a.get("contype", "1")), conaffinity=int(a.get("conaffinity", "1")),
+                                            mu=_v(a.get("friction", "1 0.005 0.0001"))[0]))
+        Jv0, _, _ = jacobians(model, np.zeros(model["nv"]))
+        bw = [np.trace(Jv0[b] @ Minv0 @ Jv0[b].T) / 3.0 for b in range(len(bodies))]       # body_invweight0, translational
+        can = lambda x, y: bool((x["contype"] & y["conaffinity"]) or (y["contype"] & x["conaffinity"]))
+        for b, body in enumerate(bodies):
+            for pl in model["planes"]:
+                if can(pl, body["coll"]):
+                    model["pairs"].append(dict(plane=pl, b2=b, mu=max(pl["mu"], body["coll"]["mu"]), invw=bw[b]))
+            for b1 in range(b):
+                o = bodies[b1]
+                if body["parent"] == b1 or o["parent"] == b or not can(o["coll"], body["coll"]):
+                    continue
+                model["pairs"].append(dict(plane=None, b1=b1, b2=b, mu=max(o["coll"]["mu"], body["coll"]["mu"]), invw=bw[b1] + bw[b]))
     return model
 
 
@@ -363,6 +389,151 @@ def solve_rows(M, f, rows):
     raise RuntimeError("no consistent active set")
 
 
+def _material_point_jacobian(model, q, body, world_point):
+    """d/dq of the world position of the point of ``body`` that currently sits at ``world_point`` (complex step)."""
+    def frames(qq):
+        pos, quat = [], []
+        k = 0
+        for bd in model["bodies"]:
+            p = bd["parent"]
+            P, Q = (np.zeros(3), np.array([1.0, 0, 0, 0])) if p < 0 else (pos[p], quat[p])
+            P = P + qrot(Q, bd["pos"])
+            Q = qmul(Q, bd["quat"])
+            for j in bd["joints"]:
+                anchor, axis = P + qrot(Q, j["pos"]), qrot(Q, j["axis"])
+                if j["type"] == "slide":
+                    P = P + axis * qq[k]
+                else:
+                    Q = qmul(Q, qaxis(j["axis"], qq[k]))
+                    P = anchor - qrot(Q, j["pos"])
+                k += 1
+            pos.append(P)
+            quat.append(Q)
+        return pos, quat
+    pos, quat = frames(np.asarray(q, float))
+    qc = np.array([quat[body][0], *(-quat[body][1:])])
+    local = qrot(qc, world_point - pos[body])
+    J = np.zeros((3, model["nv"]))
+    for i in range(model["nv"]):
+        qq = np.array(q, complex)
+        qq[i] += 1e-30j
+        P, Q = frames(qq)
+        J[:, i] = np.imag(P[body] + qrot(Q[body], local)) / 1e-30
+    return J
+
+
+def _closest_points(c1, a1, c2, a2):
+    """Closest points of segments c1 + x1 a1, c2 + x2 a2, x in [-1, 1]: interior stationary point, else the best of the
+    four edges (each a point-to-segment projection) -- not MuJoCo's sequential clamping, the same points in general position."""
+    best = None
+    def consider(x1, x2):
+        nonlocal best
+        d = np.linalg.norm(c1 + x1 * a1 - c2 - x2 * a2)
+        if best is None or d < best[0]:
+            best = (d, x1, x2)
+    A = np.array([[a1 @ a1, -a1 @ a2], [-a1 @ a2, a2 @ a2]])
+    rhs = np.array([-(c1 - c2) @ a1, (c1 - c2) @ a2])
+    if abs(np.linalg.det(A)) > 1e-14:
+        x = np.linalg.solve(A, rhs)
+        if np.all(np.abs(x) <= 1):
+            consider(x[0], x[1])
+    for x1 in (-1.0, 1.0):
+        p = c1 + x1 * a1
+        x2 = np.clip((p - c2) @ a2 / max(a2 @ a2, 1e-300), -1, 1) if a2 @ a2 > 0 else 0.0
+        consider(x1, x2)
+    for x2 in (-1.0, 1.0):
+        p = c2 + x2 * a2
+        x1 = np.clip((p - c1) @ a1 / max(a1 @ a1, 1e-300), -1, 1) if a1 @ a1 > 0 else 0.0
+        consider(x1, x2)
+    return best[1], best[2]
+
+
+def contact_rows(model, q, v):
+    """Pyramidal rows of every active contact: 4 per contact (n +- mu t1, n +- mu t2), R = 2 mu^2 (1 - imp)/imp (1 + mu^2) w."""
+    if not model["pairs"]:
+        return []
+    com, iq, _, _ = forward(model, np.asarray(q, float))
+    rows = []
+    for pr in model["pairs"]:
+        b2 = model["bodies"][pr["b2"]]
+        c2, z2 = com[pr["b2"]], qrot(iq[pr["b2"]], np.array([0.0, 0, 1]))          # one geom per body: geom frame = inertial frame
+        r2, a2 = b2["coll"]["r"], z2 * b2["coll"]["half"]
+        found = []
+        if pr["plane"] is not None:
+            n = pr["plane"]["normal"]
+            for end in ((1.0, -1.0) if b2["coll"]["half"] > 0 else (0.0,)):
+                p = c2 + end * a2
+                dist = (p - pr["plane"]["point"]) @ n - r2
+                if dist < 0:
+                    found.append((dist, p - n * (r2 + 0.5 * dist), n, a2 if b2["coll"]["half"] > 0 else None))
+            solref, solimp = b2["coll"]["solref"], b2["coll"]["solimp"]
+            bodies = (None, pr["b2"])
+        else:
+            b1 = model["bodies"][pr["b1"]]
+            c1, z1 = com[pr["b1"]], qrot(iq[pr["b1"]], np.array([0.0, 0, 1]))
+            r1, a1 = b1["coll"]["r"], z1 * b1["coll"]["half"]
+            x1, x2 = _closest_points(c1, a1, c2, a2)
+            p1, p2 = c1 + x1 * a1, c2 + x2 * a2
+            cd = np.linalg.norm(p2 - p1)
+            dist = cd - r1 - r2
+            if dist < 0 and cd > 1e-15:
+                n = (p2 - p1) / cd
+                found.append((dist, p1 + n * (r1 + 0.5 * dist), n, None))
+            solref, solimp = b2["coll"]["solref"], b2["coll"]["solimp"]
+            bodies = (pr["b1"], pr["b2"])
+        tc, dr, dmax = max(solref[0], 2 * model["h"]), solref[1], solimp[1]
+        Kk, Bb = 1.0 / (dmax * dmax * tc * tc * dr * dr), 2.0 / (dmax * tc)
+        for dist, pos, n, pref in found:
+            y = None
+            if pref is not None:
+                y = pref - (pref @ n) * n
+                y = None if np.linalg.norm(y) < 1e-12 else y
+            if y is None:
+                y = np.array([0.0, 1, 0]) if -0.5 < n[1] < 0.5 else np.array([0.0, 0, 1])
+                y = y - (y @ n) * n
+            t1 = y / np.linalg.norm(y)
+            t2 = np.cross(n, t1)
+            Jd = _material_point_jacobian(model, q, bodies[1], pos)
+            if bodies[0] is not None:
+                Jd = Jd - _material_point_jacobian(model, q, bodies[0], pos)
+            imp = impedance(solimp, dist)
+            mu = pr["mu"]
+            R = 2 * mu * mu * max(MINVAL, (1 - imp) / imp * (1 + mu * mu) * pr["invw"])
+            for t, sg in ((t1, 1.0), (t1, -1.0), (t2, 1.0), (t2, -1.0)):
+                Jr = (n + sg * mu * t) @ Jd
+                rows.append(dict(J=Jr, D=1.0 / R, aref=-Bb * (Jr @ v) - Kk * imp * dist, dist=dist))
+    return rows
+
+
+def solve_dense_rows(M, f, rows):
+    """Enumerate active sets of dense rows (identical rows switch together: they have the same residual)."""
+    groups = []
+    for r in rows:
+        for g in groups:
+            if np.allclose(g[0]["J"], r["J"], rtol=0, atol=1e-14) and g[0]["aref"] == r["aref"]:
+                g.append(r)
+                break
+        else:
+            groups.append([r])
+    for active in itertools.product((False, True), repeat=len(groups)):
+        H, rhs = M.copy(), f.copy()
+        for g, on in zip(groups, active):
+            if on:
+                for r in g:
+                    H += r["D"] * np.outer(r["J"], r["J"])
+                    rhs += r["D"] * r["aref"] * r["J"]
+        a = np.linalg.solve(H, rhs)
+        res = [g[0]["J"] @ a - g[0]["aref"] for g in groups]
+        if all((x < 0) == on for x, on in zip(res, active)):
+            fc = np.zeros_like(f)
+            for g, x, on in zip(groups, res, active):
+                if on:
+                    for r in g:
+                        fc += r["J"] * (-r["D"] * x)
+            return a, fc
+    raise RuntimeError("no consistent active set")
+
+
 def step(model, q, v, u):
     """One mj_step; returns (q', v', info)."""
     q, v = np.asarray(q, float), np.asarray(v, float)
@@ -377,8 +548,13 @@ def step(model, q, v, u):
         act[mtr["dof"]] += mtr["gear"] * min(max(ui, mtr["range"][0]), mtr["range"][1])
     f = passive + act - bias
     rows = limit_rows(model, q, v)
+    crows = contact_rows(model, q, v) if model.get("pairs") else []
     fc = np.zeros(model["nv"])
-    if rows:
+    if crows:
+        dense = [dict(J=r["sign"] * np.eye(model["nv"])[r["dof"]], D=r["D"], aref=r["aref"]) for r in rows] + crows
+        _, fc = solve_dense_rows(M, f, dense)
+        rows = dense
+    elif rows:
         _, fc = solve_rows(M, f, rows)
     qacc = np.linalg.solve(M + model["h"] * np.diag(damp), f + fc)
     v2 = v + model["h"] * qacc

@@ -32,6 +32,8 @@
 
 #define TMAXB 12
 #define TMAXV 12
+#define TMAXC 24                 /* candidate contact pairs */
+#define TMAXROW (TMAXV + 8 * TMAXC)
 #define MJMINVAL 1e-15
 #define MJPI 3.14159265358979323846
 
@@ -46,12 +48,18 @@ typedef struct {
     int act_dof[TMAXV];
     double gear[TMAXV], ctrlrange[TMAXV][2];
     double timestep, gravity[3], density, viscosity;
+    /* candidate contact pairs (mjcf_tree.compile_mjcf(..., allow_contacts="model")): kind 0 capsule / sphere against
+     * capsule / sphere (segments a0-a1, b0-b1 in their body frames), kind 1 world plane (point a0, normal a1) against the
+     * two end spheres of segment b0-b1 */
+    int ncon, ckind[TMAXC], cbody1[TMAXC], cbody2[TMAXC];
+    double ca0[TMAXC][3], ca1[TMAXC][3], cra[TMAXC], cb0[TMAXC][3], cb1[TMAXC][3], crb[TMAXC];
+    double cmu[TMAXC], cK[TMAXC], cB[TMAXC], csolimp[TMAXC][5], cinvw[TMAXC];
 } tree_model;
 
 typedef struct {
     double M[TMAXV][TMAXV], bias[TMAXV], passive[TMAXV], actuation[TMAXV], constraint[TMAXV], qacc[TMAXV];
     double xpos[TMAXB][3], xmat[TMAXB][9];
-    int nefc;
+    int nefc, ncontact;
 } tree_data;
 
 static void cross3(double* r, const double* a, const double* b) {
@@ -318,9 +326,10 @@ static void tree_step(const tree_model* m, tree_data* d, double* q, double* v, c
     }
     double f[TMAXV];
     for (int j = 0; j < nv; j++) f[j] = d->passive[j] + d->actuation[j] - d->bias[j];
-    /* --- joint-limit rows: J = +-e_j --- */
-    int nr = 0, rdof[TMAXV];
-    double rs[TMAXV], aref[TMAXV], D[TMAXV];
+    /* --- constraint rows (dense): joint limits J = +-e_j, then four pyramid rows per contact --- */
+    int nr = 0;
+    static __thread double J[TMAXROW][TMAXV];
+    double aref[TMAXROW], D[TMAXROW];
     for (int j = 0; j < nv; j++) {
         if (!m->jlimited[j]) continue;
         for (int side = -1; side <= 1; side += 2) {
@@ -329,62 +338,181 @@ static void tree_step(const tree_model* m, tree_data* d, double* q, double* v, c
                 const double imp = impedance(m->solimp[j], dist);
                 double R = (1.0 - imp) * m->invweight0[j] / imp;
                 if (R < MJMINVAL) R = MJMINVAL;
-                rdof[nr] = j; rs[nr] = -side; D[nr] = 1.0 / R;
+                for (int k = 0; k < nv; k++) J[nr][k] = 0.0;
+                J[nr][j] = -side; D[nr] = 1.0 / R;
                 aref[nr] = -m->solB[j] * (-side * v[j]) - m->solK[j] * imp * dist;
                 nr++;
             }
+        }
+    }
+    d->ncontact = 0;
+    for (int c = 0; c < m->ncon; c++) {
+        /* up to two contacts per candidate: world positions of the sphere centres that touch, normal from geom 1 to geom 2 */
+        double cpos[2][3], cnrm[2][3], cdist[2], tpref[3] = {0, 0, 0};
+        int nc = 0;
+        const int b1 = m->cbody1[c], b2 = m->cbody2[c];
+        double q0[3], q1[3], t[3];
+        mv3(t, d->xmat[b2], m->cb0[c]); for (int k = 0; k < 3; k++) q0[k] = d->xpos[b2][k] + t[k];
+        mv3(t, d->xmat[b2], m->cb1[c]); for (int k = 0; k < 3; k++) q1[k] = d->xpos[b2][k] + t[k];
+        if (m->ckind[c] == 1) {
+            /* mjc_PlaneCapsule: a sphere test at each end; the first tangent follows the capsule axis */
+            const double* n = m->ca1[c];
+            for (int k = 0; k < 3; k++) tpref[k] = q1[k] - q0[k];
+            for (int e = 0; e < 2; e++) {
+                const double* p = e ? q0 : q1;               /* MuJoCo tests pos + axis first */
+                double rel[3];
+                for (int k = 0; k < 3; k++) rel[k] = p[k] - m->ca0[c][k];
+                const double dist = dot3(rel, n) - m->crb[c];
+                if (dist < 0.0) {
+                    for (int k = 0; k < 3; k++) { cnrm[nc][k] = n[k]; cpos[nc][k] = p[k] - n[k] * (m->crb[c] + 0.5 * dist); }
+                    cdist[nc++] = dist;
+                }
+                if (m->cb0[c][0] == m->cb1[c][0] && m->cb0[c][1] == m->cb1[c][1] && m->cb0[c][2] == m->cb1[c][2]) break;  /* a sphere */
+            }
+        } else {
+            /* mjc_CapsuleCapsule (general position) / mjc_SphereCapsule: closest points of the two segments, then sphere-sphere */
+            double p0[3], p1[3];
+            mv3(t, d->xmat[b1], m->ca0[c]); for (int k = 0; k < 3; k++) p0[k] = d->xpos[b1][k] + t[k];
+            mv3(t, d->xmat[b1], m->ca1[c]); for (int k = 0; k < 3; k++) p1[k] = d->xpos[b1][k] + t[k];
+            double c1[3], c2[3], ax1[3], ax2[3], dif[3];
+            for (int k = 0; k < 3; k++) {
+                c1[k] = 0.5 * (p0[k] + p1[k]); c2[k] = 0.5 * (q0[k] + q1[k]);
+                ax1[k] = 0.5 * (p1[k] - p0[k]); ax2[k] = 0.5 * (q1[k] - q0[k]); dif[k] = c1[k] - c2[k];
+            }
+            const double ma = dot3(ax1, ax1), mb = -dot3(ax1, ax2), mc = dot3(ax2, ax2), u = -dot3(ax1, dif), w = dot3(ax2, dif);
+            const double det = ma * mc - mb * mb;
+            double x1 = 0.0, x2 = 0.0;
+            if (fabs(det) >= MJMINVAL) {
+                x1 = (mc * u - mb * w) / det; x2 = (ma * w - mb * u) / det;
+                if (x1 > 1) { x1 = 1; x2 = (w - mb) / mc; } else if (x1 < -1) { x1 = -1; x2 = (w + mb) / mc; }
+                if (x2 > 1) { x2 = 1; x1 = (u - mb) / ma; if (x1 > 1) x1 = 1; else if (x1 < -1) x1 = -1; }
+                else if (x2 < -1) { x2 = -1; x1 = (u + mb) / ma; if (x1 > 1) x1 = 1; else if (x1 < -1) x1 = -1; }
+            } else {
+                /* a sphere against a segment, or parallel segments (one contact at the clamped projection of the centres) */
+                if (ma > MJMINVAL) { x1 = u / ma; if (x1 > 1) x1 = 1; else if (x1 < -1) x1 = -1; }
+                if (mc > MJMINVAL) { x2 = (w - mb * x1) / mc; if (x2 > 1) x2 = 1; else if (x2 < -1) x2 = -1; }
+            }
+            double v1[3], v2[3], dd[3];
+            for (int k = 0; k < 3; k++) { v1[k] = c1[k] + ax1[k] * x1; v2[k] = c2[k] + ax2[k] * x2; dd[k] = v2[k] - v1[k]; }
+            const double cd = sqrt(dot3(dd, dd)), dist = cd - m->cra[c] - m->crb[c];
+            if (dist < 0.0 && cd > MJMINVAL) {
+                for (int k = 0; k < 3; k++) { cnrm[0][k] = dd[k] / cd; cpos[0][k] = v1[k] + cnrm[0][k] * (m->cra[c] + 0.5 * dist); }
+                cdist[0] = dist; nc = 1;
+            }
+        }
+        for (int e = 0; e < nc; e++) {
+            const double* n = cnrm[e];
+            /* contact frame: normal, first tangent from the preferred axis (plane-capsule) or mju_makeFrame's default */
+            double t1[3], t2[3], y[3] = {0, 0, 0};
+            double pref = dot3(tpref, tpref);
+            if (pref > MJMINVAL) { for (int k = 0; k < 3; k++) y[k] = tpref[k]; }
+            else if (n[1] > -0.5 && n[1] < 0.5) y[1] = 1.0; else y[2] = 1.0;
+            double yn = dot3(y, n);
+            for (int k = 0; k < 3; k++) t1[k] = y[k] - yn * n[k];
+            double tn = sqrt(dot3(t1, t1));
+            if (tn < 1e-12) {            /* preferred axis along the normal: fall back to the default rule */
+                y[0] = y[1] = y[2] = 0.0;
+                if (n[1] > -0.5 && n[1] < 0.5) y[1] = 1.0; else y[2] = 1.0;
+                yn = dot3(y, n);
+                for (int k = 0; k < 3; k++) t1[k] = y[k] - yn * n[k];
+                tn = sqrt(dot3(t1, t1));
+            }
+            for (int k = 0; k < 3; k++) t1[k] /= tn;
+            cross3(t2, n, t1);
+            /* Jacobian difference of the contact point: body 2 minus body 1 */
+            double Jn[TMAXV], Jt1[TMAXV], Jt2[TMAXV];
+            for (int j = 0; j < nv; j++) {
+                double col[3] = {0, 0, 0};
+                for (int s2 = 0; s2 < 2; s2++) {
+                    const int body = s2 ? b2 : b1;
+                    if (body < 0) continue;
+                    int anc = m->jbody[j] == body;
+                    for (int a = m->parent[body]; a >= 0 && !anc; a = m->parent[a]) if (a == m->jbody[j]) anc = 1;
+                    if (!anc) continue;
+                    double jc[3];
+                    if (m->jtype[j] == 1) { for (int k = 0; k < 3; k++) jc[k] = axis[j][k]; }
+                    else { double rr[3]; for (int k = 0; k < 3; k++) rr[k] = cpos[e][k] - anchor[j][k]; cross3(jc, axis[j], rr); }
+                    for (int k = 0; k < 3; k++) col[k] += s2 ? jc[k] : -jc[k];
+                }
+                Jn[j] = dot3(n, col); Jt1[j] = dot3(t1, col); Jt2[j] = dot3(t2, col);
+            }
+            const double mu = m->cmu[c], imp = impedance(m->csolimp[c], cdist[e]);
+            double R0 = (1.0 - imp) * ((1.0 + mu * mu) * m->cinvw[c]) / imp;
+            if (R0 < MJMINVAL) R0 = MJMINVAL;
+            const double Rpy = 2.0 * mu * mu * R0;
+            for (int k = 0; k < 4; k++) {
+                const double sg = (k & 1) ? -mu : mu;
+                const double* Jt = k < 2 ? Jt1 : Jt2;
+                double vel = 0.0;
+                for (int j = 0; j < nv; j++) { J[nr][j] = Jn[j] + sg * Jt[j]; vel += J[nr][j] * v[j]; }
+                D[nr] = 1.0 / Rpy;
+                aref[nr] = -m->cB[c] * vel - m->cK[c] * imp * cdist[e];
+                nr++;
+            }
+            d->ncontact++;
         }
     }
     d->nefc = nr;
     double fc[TMAXV];
     for (int j = 0; j < nv; j++) fc[j] = 0.0;
     if (nr > 0) {
+        /* exact minimiser of the convex piecewise-quadratic constraint problem: Newton with an exact line search */
         double a[TMAXV], A[TMAXV][TMAXV];
         for (int i = 0; i < nv; i++) { a[i] = f[i]; for (int j = 0; j < nv; j++) A[i][j] = d->M[i][j]; }
         chol_solve(nv, A, a);
-        for (int iter = 0; iter < 100; iter++) {
-            double jar[TMAXV], g[TMAXV], fn = 0, gn = 0;
-            int act[TMAXV];
-            for (int r = 0; r < nr; r++) { jar[r] = rs[r] * a[rdof[r]] - aref[r]; act[r] = jar[r] < 0.0; }
-            for (int i = 0; i < nv; i++) {
-                double s = -f[i];
-                for (int k = 0; k < nv; k++) s += d->M[i][k] * a[k];
-                g[i] = s;
+        for (int iter = 0; iter < 200; iter++) {
+            double jar[TMAXROW], g[TMAXV], fn = 0, gn = 0;
+            int act[TMAXROW];
+            for (int r = 0; r < nr; r++) {
+                double s2 = -aref[r];
+                for (int k = 0; k < nv; k++) s2 += J[r][k] * a[k];
+                jar[r] = s2; act[r] = s2 < 0.0;
             }
-            for (int r = 0; r < nr; r++) if (act[r]) g[rdof[r]] += D[r] * jar[r] * rs[r];
-            for (int i = 0; i < nv; i++) { gn += g[i] * g[i]; fn += f[i] * f[i]; }
+            for (int i = 0; i < nv; i++) {
+                double s2 = -f[i];
+                for (int k = 0; k < nv; k++) s2 += d->M[i][k] * a[k];
+                for (int r = 0; r < nr; r++) if (act[r]) s2 += D[r] * jar[r] * J[r][i];
+                g[i] = s2; gn += s2 * s2; fn += f[i] * f[i];
+            }
             if (sqrt(gn) <= 1e-15 * (1.0 + sqrt(fn))) break;
-            double p[TMAXV], Jp[TMAXV];
-            for (int i = 0; i < nv; i++) { p[i] = -g[i]; for (int j = 0; j < nv; j++) A[i][j] = d->M[i][j]; }
-            for (int r = 0; r < nr; r++) if (act[r]) A[rdof[r]][rdof[r]] += D[r];
+            double p[TMAXV], Jp[TMAXROW];
+            for (int i = 0; i < nv; i++) {
+                p[i] = -g[i];
+                for (int j = 0; j < nv; j++) {
+                    double s2 = d->M[i][j];
+                    for (int r = 0; r < nr; r++) if (act[r]) s2 += D[r] * J[r][i] * J[r][j];
+                    A[i][j] = s2;
+                }
+            }
             chol_solve(nv, A, p);
             double g0 = 0, h0 = 0;
             for (int i = 0; i < nv; i++) {
-                double s = 0, gi = -f[i];
-                for (int k = 0; k < nv; k++) { s += d->M[i][k] * p[k]; gi += d->M[i][k] * a[k]; }
-                g0 += p[i] * gi; h0 += p[i] * s;
+                double s2 = 0, gi = -f[i];
+                for (int k = 0; k < nv; k++) { s2 += d->M[i][k] * p[k]; gi += d->M[i][k] * a[k]; }
+                g0 += p[i] * gi; h0 += p[i] * s2;
             }
-            for (int r = 0; r < nr; r++) Jp[r] = rs[r] * p[rdof[r]];
-            double bp[TMAXV + 2];
+            for (int r = 0; r < nr; r++) { double s2 = 0; for (int k = 0; k < nv; k++) s2 += J[r][k] * p[k]; Jp[r] = s2; }
+            double bp[TMAXROW + 2];
             int nbp = 0;
             bp[nbp++] = 0.0;
-            for (int r = 0; r < nr; r++) if (Jp[r] != 0.0) { double t = -jar[r] / Jp[r]; if (t > 0.0) bp[nbp++] = t; }
+            for (int r = 0; r < nr; r++) if (Jp[r] != 0.0) { double tb = -jar[r] / Jp[r]; if (tb > 0.0) bp[nbp++] = tb; }
             for (int i = 1; i < nbp; i++) { double x = bp[i]; int k = i - 1; while (k >= 0 && bp[k] > x) { bp[k + 1] = bp[k]; k--; } bp[k + 1] = x; }
             double tstar = 1.0;
-            for (int s = 0; s < nbp; s++) {
-                const double lo = bp[s], hi = (s + 1 < nbp) ? bp[s + 1] : INFINITY;
+            for (int s2 = 0; s2 < nbp; s2++) {
+                const double lo = bp[s2], hi = (s2 + 1 < nbp) ? bp[s2 + 1] : INFINITY;
                 const double mid = isinf(hi) ? lo + 1.0 : 0.5 * (lo + hi);
                 double c0 = g0, c1 = h0;
                 for (int r = 0; r < nr; r++)
                     if (jar[r] + mid * Jp[r] < 0.0) { c0 += D[r] * jar[r] * Jp[r]; c1 += D[r] * Jp[r] * Jp[r]; }
-                const double t = -c0 / c1;
-                if (t <= hi || s + 1 == nbp) { tstar = t < lo ? lo : t; break; }
+                const double tt = -c0 / c1;
+                if (tt <= hi || s2 + 1 == nbp) { tstar = tt < lo ? lo : tt; break; }
             }
             for (int i = 0; i < nv; i++) a[i] += tstar * p[i];
         }
         for (int r = 0; r < nr; r++) {
-            const double s = rs[r] * a[rdof[r]] - aref[r];
-            if (s < 0.0) fc[rdof[r]] += rs[r] * (-D[r] * s);
+            double s2 = -aref[r];
+            for (int k = 0; k < nv; k++) s2 += J[r][k] * a[k];
+            if (s2 < 0.0) for (int k = 0; k < nv; k++) fc[k] += J[r][k] * (-D[r] * s2);
         }
     }
     for (int k = 0; k < nv; k++) d->constraint[k] = fc[k];
@@ -431,6 +559,19 @@ tree_model* tree_model_create(int nb, int nv, int nu, const int* parent, const d
     m->timestep = timestep; m->density = density; m->viscosity = viscosity;
     for (int k = 0; k < 3; k++) m->gravity[k] = gravity[k];
     return m;
+}
+int tree_model_set_contacts(tree_model* m, int ncon, const int* kind, const int* body1, const int* body2, const double* a0,
+                            const double* a1, const double* ra, const double* b0, const double* b1, const double* rb,
+                            const double* mu, const double* K, const double* B, const double* solimp, const double* invw) {
+    if (ncon > TMAXC) return -1;
+    m->ncon = ncon;
+    for (int c = 0; c < ncon; c++) {
+        m->ckind[c] = kind[c]; m->cbody1[c] = body1[c]; m->cbody2[c] = body2[c];
+        for (int k = 0; k < 3; k++) { m->ca0[c][k] = a0[3 * c + k]; m->ca1[c][k] = a1[3 * c + k]; m->cb0[c][k] = b0[3 * c + k]; m->cb1[c][k] = b1[3 * c + k]; }
+        m->cra[c] = ra[c]; m->crb[c] = rb[c]; m->cmu[c] = mu[c]; m->cK[c] = K[c]; m->cB[c] = B[c]; m->cinvw[c] = invw[c];
+        for (int k = 0; k < 5; k++) m->csolimp[c][k] = solimp[5 * c + k];
+    }
+    return 0;
 }
 void tree_model_free(tree_model* m) { free(m); }
 

@@ -61,6 +61,17 @@ class TreeOracle:
             C.c_double(model.timestep), _p(k[24]), C.c_double(model.density), C.c_double(model.viscosity)))
         if not self.h:
             raise ValueError("model too large for the oracle")
+        cs = getattr(model, "contacts", [])
+        if cs:
+            z3 = np.zeros(3)
+            kb = np.array([solref_to_kb(c["solref"], c["solimp"], model.timestep) for c in cs])
+            arr = [i([1 if c["kind"] == "plane" else 0 for c in cs]), i([c["body1"] for c in cs]), i([c["body2"] for c in cs]),
+                   f([c["a0"] for c in cs]), f([c["a1"] for c in cs]), f([c["ra"] for c in cs]), f([c["b0"] for c in cs]),
+                   f([c["b1"] for c in cs]), f([c["rb"] for c in cs]), f([c["mu"] for c in cs]), f(kb[:, 0]), f(kb[:, 1]),
+                   f([c["solimp"] for c in cs]), f([c["invweight"] for c in cs])]
+            self._keep += arr
+            if L.tree_model_set_contacts(self.h, ci(len(cs)), _p(arr[0], ci), _p(arr[1], ci), _p(arr[2], ci), *[_p(a) for a in arr[3:]]):
+                raise ValueError("too many contact candidates for the oracle")
 
     def __del__(self):
         if getattr(self, "h", None):
