@@ -135,18 +135,24 @@ int mjb_rollout_lqr(const mjb_lqr_args* a, void* stream);
 typedef struct mjb_tree_model mjb_tree_model;
 mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* link_params, const int* link_ints,
                                       const double* globals, const double* planar_params, const int* planar_anc,
-                                      const double* planar_gravity, int n_instances, int device);
+                                      const double* planar_gravity, int n_contacts, const int* contact_ints,
+                                      const double* contact_params, int n_instances, int device);
                                       /* NULL + mjb_last_error on failure.  n_instances > 1: link_params (n, nv, LK_STRIDE) and
                                        * planar_params (n, nv, PK_STRIDE) hold one model per worker -- the perturbed copies of
                                        * randomize_dynamics (subproc_vec_env.py:304-312, gym_env_wrapper.py:367-416): same topology,
                                        * different masses / inertias / dampings */
 void mjb_tree_model_destroy(mjb_tree_model* m);
-void mjb_tree_layout(int* out45);   /* the 45 layout constants of csrc/tree_model.h + rollout_tree_planar.cuh, in order */
+void mjb_tree_layout(int* out59);   /* the 59 layout constants of csrc/tree_model.h + rollout_tree_planar.cuh, in order */
 /* PLANAR MECHANISMS (all hinge axes parallel, all slides perpendicular to them -- swimmer.xml and half_cheetah.xml are):
  * with the three planar blocks of mjcf_tree.pack_planar -- planar_params (nv, PK_STRIDE), planar_anc (nv) ancestor bit
  * masks, planar_gravity (2); NULL otherwise -- rollouts of 7- and 9-dof models run the planar instantiation (3-vectors
  * in place of spatial 6-vectors, everything in registers).  Same results to rounding; mjb_tree_use_planar(0) forces
- * the general instantiation (tests compare the two), a negative argument only queries; returns the previous value. */
+ * the general instantiation (tests compare the two), a negative argument only queries; returns the previous value.
+ * CONTACTS (planar mechanisms only): n_contacts candidate pairs from mjcf_tree.pack_planar_contacts -- contact_ints
+ * (n, 3): kind, link 1 (-1 = world), link 2; contact_params (n, CT_STRIDE) -- world plane against the end spheres of a
+ * capsule (half_cheetah.xml's floor) and capsule against capsule (swimmer.xml's non-adjacent links): MuJoCo's
+ * mjc_PlaneCapsule / mjc_CapsuleCapsule detection, condim-3 pyramidal friction rows (n +- mu t), R = 2 mu^2 (1 - imp) / imp
+ * (1 + mu^2)(invweight_1 + invweight_2), solved with the limit rows by Newton with an exact line search. */
 int mjb_tree_use_planar(int on);
 typedef struct {
     int K, H, frame_skip, particles_per_ctrl;

@@ -30,6 +30,9 @@ struct mjb_tree_model {
     double* d_g;    // TG_STRIDE
     double* d_pk;   // planar mechanisms: n_inst x (nv x PK_STRIDE, then the in-plane gravity (2))
     int* d_anc;     // planar mechanisms: ancestor bit masks (nv)
+    int ncand;      // planar mechanisms with contacts: candidate pairs (rollout_tree_planar.cuh)
+    int* d_cti;     // ncand x CTI_STRIDE
+    double* d_ctd;  // ncand x CT_STRIDE
 };
 
 namespace mjb {
@@ -492,7 +495,8 @@ TR_HD int substep(const double* lk, const int* li, const double* g, int nv_rt, d
 template <int NV, bool SERIAL, bool PLANAR>
 __global__ void __launch_bounds__(64) rollout_tree_kernel(const double* __restrict__ g_lk, const int* __restrict__ g_li,
                                                           const double* __restrict__ g_g, const double* __restrict__ g_pk,
-                                                          const int* __restrict__ g_anc, int nv_rt, int nu,
+                                                          const int* __restrict__ g_anc, int ncand, const int* __restrict__ g_cti,
+                                                          const double* __restrict__ g_ctd, int nv_rt, int nu,
                                                           mjb_tree_rollout_args a) {
     constexpr int N = NV > 0 ? NV : MJB_TREE_MAX_LINKS;
     __shared__ double s_lk[N * LK_STRIDE];
@@ -500,6 +504,8 @@ __global__ void __launch_bounds__(64) rollout_tree_kernel(const double* __restri
     __shared__ double s_g[TG_STRIDE];
     __shared__ double s_pk[PLANAR ? N * PK_STRIDE + 2 : 1];
     __shared__ int s_anc[PLANAR ? N : 1];
+    __shared__ int s_cti[PLANAR ? MJB_TREE_MAX_CAND * CTI_STRIDE : 1];
+    __shared__ double s_ctd[PLANAR ? MJB_TREE_MAX_CAND * CT_STRIDE : 1];
     const int nv = NV > 0 ? NV : nv_rt;
     // blocks are model-uniform: instance = block / blocks-per-model (one model: the plain particle numbering)
     const int bpm = (a.particles_per_model + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -512,6 +518,8 @@ __global__ void __launch_bounds__(64) rollout_tree_kernel(const double* __restri
         g_pk += (long long)inst * (nv * PK_STRIDE + 2);
         for (int i = threadIdx.x; i < nv * PK_STRIDE + 2; i += blockDim.x) s_pk[i] = g_pk[i];
         for (int i = threadIdx.x; i < nv; i += blockDim.x) s_anc[i] = g_anc[i];
+        for (int i = threadIdx.x; i < ncand * CTI_STRIDE; i += blockDim.x) s_cti[i] = g_cti[i];
+        for (int i = threadIdx.x; i < ncand * CT_STRIDE; i += blockDim.x) s_ctd[i] = g_ctd[i];
     }
     __syncthreads();
     const long long k = (long long)inst * a.particles_per_model + local;
@@ -552,7 +560,7 @@ __global__ void __launch_bounds__(64) rollout_tree_kernel(const double* __restri
 #pragma unroll
         for (int i = 0; i < N; i++) if (i == a.fwd_dof) before = q[i];
         for (int s = 0; s < a.frame_skip; s++) {
-            if constexpr (PLANAR) nefc += planar_substep<NV, SERIAL>(s_lk, s_li, s_pk, s_anc, s_g, s_pk + NV * PK_STRIDE, q, v, uf);
+            if constexpr (PLANAR) nefc += planar_substep<NV, SERIAL>(s_lk, s_li, s_pk, s_anc, s_g, s_pk + NV * PK_STRIDE, ncand, s_cti, s_ctd, q, v, uf);
             else nefc += substep<NV, SERIAL, false>(s_lk, s_li, s_g, nv, q, v, u);
         }
 #pragma unroll
@@ -590,7 +598,8 @@ int g_use_planar = 1;
 
 extern "C" mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* link_params, const int* link_ints,
                                                  const double* globals, const double* planar_params,
-                                                 const int* planar_anc, const double* planar_gravity, int n_instances,
+                                                 const int* planar_anc, const double* planar_gravity, int n_contacts,
+                                                 const int* contact_ints, const double* contact_params, int n_instances,
                                                  int device) {
     if (nv < 1 || nv > MJB_TREE_MAX_LINKS || nu < 0 || nu > nv || !link_params || !link_ints || !globals || n_instances < 1) {
         mjb::set_error(MJB_EINVAL, "mjb_tree_model_create: 1 <= nv <= %d, nu <= nv, n_instances >= 1, non-null blocks", MJB_TREE_MAX_LINKS);
@@ -598,6 +607,12 @@ extern "C" mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* l
     }
     if ((planar_params != nullptr) != (planar_anc != nullptr) || (planar_params != nullptr) != (planar_gravity != nullptr)) {
         mjb::set_error(MJB_EINVAL, "mjb_tree_model_create: the three planar blocks come together or not at all");
+        return nullptr;
+    }
+    if (n_contacts < 0 || n_contacts > MJB_TREE_MAX_CAND || (n_contacts > 0 && (!planar_params || !contact_ints || !contact_params)) ||
+        (n_contacts > 0 && nv != 7 && nv != 9)) {
+        mjb::set_error(MJB_ENOTIMPL, "mjb_tree_model_create: contacts run in the planar instantiation only (planar mechanism of 7 or "
+                       "9 dofs, at most %d candidate pairs)", MJB_TREE_MAX_CAND);
         return nullptr;
     }
     int serial = 1;
@@ -610,7 +625,7 @@ extern "C" mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* l
     }
     if (cudaSetDevice(device) != cudaSuccess) { mjb::set_error(MJB_ECUDA, "mjb_tree_model_create: cudaSetDevice(%d) failed", device); return nullptr; }
     mjb_tree_model* m = new mjb_tree_model{device, nv, nu, serial, planar_params != nullptr, n_instances,
-                                           nullptr, nullptr, nullptr, nullptr, nullptr};
+                                           nullptr, nullptr, nullptr, nullptr, nullptr, n_contacts, nullptr, nullptr};
     bool ok = upload(&m->d_lk, link_params, (size_t)n_instances * nv * LK_STRIDE) && upload(&m->d_li, link_ints, (size_t)nv * LI_STRIDE) &&
               upload(&m->d_g, globals, (size_t)TG_STRIDE);
     if (ok && m->planar) {
@@ -624,6 +639,8 @@ extern "C" mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* l
         ok = pk && upload(&m->d_pk, pk, stride * n_instances) && upload(&m->d_anc, planar_anc, (size_t)nv);
         ok = ok && cudaStreamSynchronize(0) == cudaSuccess;      // pk is freed right here
         free(pk);
+        if (ok && n_contacts > 0)
+            ok = upload(&m->d_cti, contact_ints, (size_t)n_contacts * CTI_STRIDE) && upload(&m->d_ctd, contact_params, (size_t)n_contacts * CT_STRIDE);
     }
     if (!ok || cudaStreamSynchronize(0) != cudaSuccess) {
         mjb::set_error(MJB_ECUDA, "mjb_tree_model_create: device allocation / upload failed");
@@ -638,6 +655,8 @@ extern "C" void mjb_tree_model_destroy(mjb_tree_model* m) {
     cudaFree(m->d_lk); cudaFree(m->d_li); cudaFree(m->d_g);
     if (m->d_pk) cudaFree(m->d_pk);
     if (m->d_anc) cudaFree(m->d_anc);
+    if (m->d_cti) cudaFree(m->d_cti);
+    if (m->d_ctd) cudaFree(m->d_ctd);
     delete m;
 }
 
@@ -651,7 +670,8 @@ extern "C" void mjb_tree_layout(int* out) {
     const int v[] = {LK_RFIX, LK_OFF, LK_AXIS, LK_MASS, LK_COM, LK_IC, LK_RIN, LK_BOX, LK_ARM, LK_DAMP, LK_STIFF, LK_SREF, LK_LO,
                      LK_HI, LK_INVW, LK_SOLK, LK_SOLB, LK_SOLIMP, LK_GEAR, LK_CLO, LK_CHI, LK_STRIDE, LI_PARENT, LI_TYPE,
                      LI_LIMITED, LI_ACT, LI_BODY, LI_STRIDE, TG_DT, TG_GRAV, TG_RHO, TG_VISC, TG_STRIDE, MJB_TREE_MAX_LINKS,
-                     PK_OFF, PK_DIR, PK_MASS, PK_COM, PK_INN, PK_CLIN, PK_KV1, PK_KV2, PK_E, PK_AK, PK_STRIDE};
+                     PK_OFF, PK_DIR, PK_MASS, PK_COM, PK_INN, PK_CLIN, PK_KV1, PK_KV2, PK_E, PK_AK, PK_STRIDE,
+                     CT_A, CT_HA, CT_RA, CT_B, CT_HB, CT_RB, CT_MU, CT_K, CT_BB, CT_SOLIMP, CT_INVW, CT_STRIDE, CTI_STRIDE, MJB_TREE_MAX_CAND};
     for (unsigned i = 0; i < sizeof(v) / sizeof(v[0]); i++) out[i] = v[i];
 }
 
@@ -667,9 +687,11 @@ extern "C" int mjb_rollout_tree(const mjb_tree_model* m, const mjb_tree_rollout_
     const int blocks = (a->K / a->particles_per_model) * ((a->particles_per_model + 63) / 64);
     cudaStream_t st = (cudaStream_t)stream;
     using namespace mjb::tree;
+    MJB_REQUIRE(m->ncand == 0 || g_use_planar, "mjb_rollout_tree: a model with contacts runs in the planar instantiation only");
     const bool planar = m->planar && g_use_planar;
 #define MJB_TREE_LAUNCH(NV, SERIAL, PLANAR) \
-    rollout_tree_kernel<NV, SERIAL, PLANAR><<<blocks, 64, 0, st>>>(m->d_lk, m->d_li, m->d_g, m->d_pk, m->d_anc, m->nv, m->nu, *a)
+    rollout_tree_kernel<NV, SERIAL, PLANAR><<<blocks, 64, 0, st>>>(m->d_lk, m->d_li, m->d_g, m->d_pk, m->d_anc, m->ncand, m->d_cti, m->d_ctd, \
+                                                               m->nv, m->nu, *a)
     if (planar && m->nv == 7 && m->serial) MJB_TREE_LAUNCH(7, true, true);
     else if (planar && m->nv == 7) MJB_TREE_LAUNCH(7, false, true);
     else if (planar && m->nv == 9) MJB_TREE_LAUNCH(9, false, true);

@@ -18,8 +18,101 @@
 enum { PK_OFF = 0, PK_DIR = 2, PK_MASS = 4, PK_COM = 5, PK_INN = 7, PK_CLIN = 8, PK_KV1 = 9, PK_KV2 = 10, PK_E = 11, PK_AK = 17,
        PK_STRIDE = 20 };
 
+// Contact candidates of a planar mechanism (mjcf_tree.pack_planar_contacts).  Per candidate, ints: kind (0 segment /
+// segment, 1 world plane / the two end spheres of a segment), link 1 (-1 = world), link 2; doubles (link frames
+// world-aligned at q = 0, relative to the link's anchor): segment A centre (2), half axis (2), radius -- for a plane:
+// a point (2, absolute) and the normal (2) -- segment B centre, half axis, radius, then mu, K, B, solimp (5),
+// body_invweight0 sum.
+enum { CT_A = 0, CT_HA = 2, CT_RA = 4, CT_B = 5, CT_HB = 7, CT_RB = 9, CT_MU = 10, CT_K = 11, CT_BB = 12, CT_SOLIMP = 13, CT_INVW = 18,
+       CT_STRIDE = 19, CTI_STRIDE = 3, MJB_TREE_MAX_CAND = 16, MJB_TREE_MAX_DENSE = 3 * 2 * MJB_TREE_MAX_CAND };
+
 namespace mjb {
 namespace tree {
+
+// Constrained solve + mj_Euler with DENSE rows (contacts) next to the joint-limit rows: Newton on the convex
+// piecewise-quadratic problem with an exact line search along every step (the oracle's algorithm), out of line.  Limit
+// rows come per dof (rD = 0: none): J = rS e_i; dense rows as (Jd, Dd, Ad)[nd].  M, f are clobbered.
+template <int NV>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#endif
+void dense_solve_integrate(const double* lk, double h, double (*M)[NV], double* f, bool damped, const double* rD, const double* rS,
+                           const double* rA, int nd, const double (*Jd)[NV], const double* Dd, const double* Ad, double* q, double* v) {
+    double A[NV][NV], a[NV], g[NV], p[NV], fc[NV];
+    double res[NV + MJB_TREE_MAX_DENSE], Jp[NV + MJB_TREE_MAX_DENSE];
+    for (int i = 0; i < NV; i++) { a[i] = f[i]; for (int j = 0; j <= i; j++) A[i][j] = M[i][j]; }
+    chol_solve<NV>(NV, A, a);
+    double fn = 0.0;
+    for (int i = 0; i < NV; i++) fn += f[i] * f[i];
+    for (int iter = 0; iter < 100; iter++) {
+        // residuals: rows 0..NV-1 are the limit rows (absent: rD = 0), NV.. the dense ones
+        for (int i = 0; i < NV; i++) res[i] = rD[i] > 0.0 ? rS[i] * a[i] - rA[i] : 1.0;
+        for (int r = 0; r < nd; r++) {
+            double sres = -Ad[r];
+            for (int k = 0; k < NV; k++) sres += Jd[r][k] * a[k];
+            res[NV + r] = sres;
+        }
+        double gn = 0.0;
+        for (int i = 0; i < NV; i++) {
+            double t = -f[i];
+            for (int k = 0; k < NV; k++) t += M[i][k] * a[k];
+            if (res[i] < 0.0) t += rD[i] * res[i] * rS[i];
+            for (int r = 0; r < nd; r++) if (res[NV + r] < 0.0) t += Dd[r] * res[NV + r] * Jd[r][i];
+            g[i] = t; gn += t * t;
+        }
+        if (sqrt(gn) <= 1e-15 * (1.0 + sqrt(fn))) break;
+        for (int i = 0; i < NV; i++) {
+            p[i] = -g[i];
+            for (int j = 0; j <= i; j++) {
+                double t = M[i][j];
+                for (int r = 0; r < nd; r++) if (res[NV + r] < 0.0) t += Dd[r] * Jd[r][i] * Jd[r][j];
+                A[i][j] = t;
+            }
+            if (res[i] < 0.0) A[i][i] += rD[i];
+        }
+        chol_solve<NV>(NV, A, p);
+        double g0 = 0.0, h0 = 0.0;
+        for (int i = 0; i < NV; i++) {
+            double Mp = 0.0, Ma = -f[i];
+            for (int k = 0; k < NV; k++) { Mp += M[i][k] * p[k]; Ma += M[i][k] * a[k]; }
+            g0 += p[i] * Ma; h0 += p[i] * Mp;
+        }
+        for (int i = 0; i < NV; i++) Jp[i] = rD[i] > 0.0 ? rS[i] * p[i] : 0.0;
+        for (int r = 0; r < nd; r++) { double t = 0.0; for (int k = 0; k < NV; k++) t += Jd[r][k] * p[k]; Jp[NV + r] = t; }
+        const int nrow = NV + nd;
+        double tcur = 0.0, tstar = 1.0;
+        for (int seg = 0; seg <= nrow; seg++) {
+            double tnext = TR_BIG;
+            for (int r = 0; r < nrow; r++)
+                if (Jp[r] != 0.0) { const double tb = -res[r] / Jp[r]; if (tb > tcur && tb < tnext) tnext = tb; }
+            const double tmid = tnext >= TR_BIG ? tcur + 1.0 : 0.5 * (tcur + tnext);
+            double c0 = g0, c1 = h0;
+            for (int r = 0; r < nrow; r++) {
+                const double Dr = r < NV ? rD[r] : Dd[r - NV];
+                if (Dr > 0.0 && res[r] + tmid * Jp[r] < 0.0) { c0 += Dr * res[r] * Jp[r]; c1 += Dr * Jp[r] * Jp[r]; }
+            }
+            const double t = -c0 / c1;
+            if (t <= tnext || tnext >= TR_BIG) { tstar = t < tcur ? tcur : t; break; }
+            tcur = tnext;
+        }
+        for (int i = 0; i < NV; i++) a[i] += tstar * p[i];
+    }
+    if (damped) {
+        for (int i = 0; i < NV; i++) fc[i] = rD[i] > 0.0 && rS[i] * a[i] - rA[i] < 0.0 ? rS[i] * (-rD[i] * (rS[i] * a[i] - rA[i])) : 0.0;
+        for (int r = 0; r < nd; r++) {
+            double sres = -Ad[r];
+            for (int k = 0; k < NV; k++) sres += Jd[r][k] * a[k];
+            if (sres < 0.0) for (int k = 0; k < NV; k++) fc[k] += Jd[r][k] * (-Dd[r] * sres);
+        }
+        for (int i = 0; i < NV; i++) {
+            a[i] = f[i] + fc[i];
+            for (int j = 0; j <= i; j++) A[i][j] = M[i][j];
+            A[i][i] += h * lk[i * LK_STRIDE + LK_DAMP];
+        }
+        chol_solve<NV>(NV, A, a);
+    }
+    for (int i = 0; i < NV; i++) { v[i] += h * a[i]; q[i] += h * v[i]; }
+}
 
 TR_HD double inv_sqrt(double x) {
 #if defined(__CUDA_ARCH__)
@@ -31,6 +124,7 @@ TR_HD double inv_sqrt(double x) {
 
 template <int NV, bool SERIAL>
 TR_HD int planar_substep(const double* lk, const int* li, const double* pk, const int* anc, const double* g, const double* gp,
+                         int ncand, const int* cti, const double* ctd,
                          double* q, double* v, const double* u /* per dof: gear * clamp(ctrl) */) {
     const double h = g[TG_DT];
     const bool fluid = g[TG_RHO] > 0.0 || g[TG_VISC] > 0.0;
@@ -149,6 +243,106 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
 #pragma unroll
             for (int j = 0; j < i; j++)
                 if (j == p) { Fw[j] += Fw[i]; Fx[j] += Fx[i]; Fy[j] += Fy[i]; cm[j] += cm[i]; chx[j] += chx[i]; chy[j] += chy[i]; cI[j] += cI[i]; }
+        }
+    }
+
+    // ---- contacts (models compiled with allow_contacts="model"): detection on the link frames, three rows per
+    // contact -- n + mu t, n - mu t and the pair n +- mu t_out merged into one row of twice the weight (t_out is normal
+    // to the plane of motion: both rows have the Jacobian of n) -- and the dense Newton, out of line
+    if (ncand > 0) {
+        double Jd[MJB_TREE_MAX_DENSE][NV], Dd[MJB_TREE_MAX_DENSE], Ad[MJB_TREE_MAX_DENSE];
+        int nd = 0, ncontact = 0;
+#pragma unroll 1
+        for (int cnd = 0; cnd < ncand; cnd++) {
+            const int* CI = cti + cnd * CTI_STRIDE;
+            const double* C = ctd + cnd * CT_STRIDE;
+            const int l1 = CI[1], l2 = CI[2];
+            double c1 = 1.0, s1 = 0.0, x1 = -Ox, y1 = -Oy, c2 = 1.0, s2 = 0.0, x2 = 0.0, y2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                if (j == l1) { c1 = cs[j]; s1 = sn[j]; x1 = px[j]; y1 = py[j]; }
+                if (j == l2) { c2 = cs[j]; s2 = sn[j]; x2 = px[j]; y2 = py[j]; }
+            }
+            const unsigned m1 = l1 < 0 ? 0u : ((SERIAL ? ((1u << l1) - 1u) : (unsigned)anc[l1]) | (1u << l1));
+            const unsigned m2 = (SERIAL ? ((1u << l2) - 1u) : (unsigned)anc[l2]) | (1u << l2);
+            // segment B in the world (relative to O)
+            const double bx = x2 + c2 * C[CT_B] - s2 * C[CT_B + 1], by = y2 + s2 * C[CT_B] + c2 * C[CT_B + 1];
+            const double hbx = c2 * C[CT_HB] - s2 * C[CT_HB + 1], hby = s2 * C[CT_HB] + c2 * C[CT_HB + 1];
+            double cpx[2], cpy[2], cnx[2], cny[2], cdist[2];
+            int nc = 0;
+            if (CI[0] == 1) {
+                const double nx = C[CT_HA], ny = C[CT_HA + 1];
+                const bool sphere = C[CT_HB] == 0.0 && C[CT_HB + 1] == 0.0;
+                for (int e = 0; e < (sphere ? 1 : 2); e++) {
+                    const double sg = sphere ? 0.0 : (e ? -1.0 : 1.0);
+                    const double ex = bx + sg * hbx, ey = by + sg * hby;
+                    const double dist = (ex + Ox - C[CT_A]) * nx + (ey + Oy - C[CT_A + 1]) * ny - C[CT_RB];
+                    if (dist < 0.0) {
+                        cnx[nc] = nx; cny[nc] = ny; cdist[nc] = dist;
+                        cpx[nc] = ex - nx * (C[CT_RB] + 0.5 * dist); cpy[nc] = ey - ny * (C[CT_RB] + 0.5 * dist);
+                        nc++;
+                    }
+                }
+            } else {
+                const double ax = x1 + c1 * C[CT_A] - s1 * C[CT_A + 1], ay = y1 + s1 * C[CT_A] + c1 * C[CT_A + 1];
+                const double hax = c1 * C[CT_HA] - s1 * C[CT_HA + 1], hay = s1 * C[CT_HA] + c1 * C[CT_HA + 1];
+                const double dfx = ax - bx, dfy = ay - by;
+                const double ma = hax * hax + hay * hay, mb = -(hax * hbx + hay * hby), mc = hbx * hbx + hby * hby;
+                const double uu = -(hax * dfx + hay * dfy), ww = hbx * dfx + hby * dfy;
+                const double det = ma * mc - mb * mb;
+                double t1 = 0.0, t2 = 0.0;
+                if (fabs(det) >= 1e-15) {                 // mjc_CapsuleCapsule, general position: sequential clamping
+                    t1 = (mc * uu - mb * ww) / det; t2 = (ma * ww - mb * uu) / det;
+                    if (t1 > 1.0) { t1 = 1.0; t2 = (ww - mb) / mc; } else if (t1 < -1.0) { t1 = -1.0; t2 = (ww + mb) / mc; }
+                    if (t2 > 1.0) { t2 = 1.0; t1 = fmin(1.0, fmax(-1.0, (uu - mb) / ma)); }
+                    else if (t2 < -1.0) { t2 = -1.0; t1 = fmin(1.0, fmax(-1.0, (uu + mb) / ma)); }
+                } else {                                  // a sphere against a segment, or parallel segments
+                    if (ma > 1e-15) t1 = fmin(1.0, fmax(-1.0, uu / ma));
+                    if (mc > 1e-15) t2 = fmin(1.0, fmax(-1.0, (ww - mb * t1) / mc));
+                }
+                const double v1x = ax + hax * t1, v1y = ay + hay * t1, ddx = bx + hbx * t2 - v1x, ddy = by + hby * t2 - v1y;
+                const double cd = sqrt(ddx * ddx + ddy * ddy), dist = cd - C[CT_RA] - C[CT_RB];
+                if (dist < 0.0 && cd > 1e-15) {
+                    cnx[0] = ddx / cd; cny[0] = ddy / cd; cdist[0] = dist;
+                    cpx[0] = v1x + cnx[0] * (C[CT_RA] + 0.5 * dist); cpy[0] = v1y + cny[0] * (C[CT_RA] + 0.5 * dist);
+                    nc = 1;
+                }
+            }
+            for (int e = 0; e < nc && nd + 3 <= MJB_TREE_MAX_DENSE; e++) {
+                const double nx = cnx[e], ny = cny[e], tx = -ny, ty = nx, mu = C[CT_MU];
+                const double imp = impedance_call(C + CT_SOLIMP, cdist[e]);
+                const double R0 = fmax(1e-15, (1.0 - imp) * ((1.0 + mu * mu) * C[CT_INVW]) / imp);
+                const double Dr = 1.0 / (2.0 * mu * mu * R0);
+                double vn = 0.0, vt = 0.0;
+#pragma unroll
+                for (int j = 0; j < NV; j++) {
+                    // velocity of the contact point per unit qdot_j: body 2 minus body 1
+                    const double sgn = ((m2 >> j & 1u) ? 1.0 : 0.0) - ((m1 >> j & 1u) ? 1.0 : 0.0);
+                    const double jx = sgn * (Sx[j] - Sw[j] * cpy[e]), jy = sgn * (Sy[j] + Sw[j] * cpx[e]);
+                    const double jn = nx * jx + ny * jy, jt = tx * jx + ty * jy;
+                    Jd[nd][j] = jn + mu * jt; Jd[nd + 1][j] = jn - mu * jt; Jd[nd + 2][j] = jn;
+                    vn += jn * v[j]; vt += jt * v[j];
+                }
+                const double pen = C[CT_K] * imp * cdist[e];
+                Dd[nd] = Dr; Dd[nd + 1] = Dr; Dd[nd + 2] = 2.0 * Dr;
+                Ad[nd] = -C[CT_BB] * (vn + mu * vt) - pen; Ad[nd + 1] = -C[CT_BB] * (vn - mu * vt) - pen; Ad[nd + 2] = -C[CT_BB] * vn - pen;
+                nd += 3;
+                ncontact++;
+            }
+        }
+        if (nd > 0) {
+            double Ml[NV][NV], fl[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++) {
+                fl[i] = f[i];
+#pragma unroll
+                for (int j = 0; j < NV; j++) Ml[i][j] = M[i][j];
+            }
+            dense_solve_integrate<NV>(lk, h, Ml, fl, damped, rD, rS, rA, nd, Jd, Dd, Ad, q, v);
+            int nr = 4 * ncontact;
+#pragma unroll
+            for (int i = 0; i < NV; i++) nr += rows >> i & 1;
+            return nr;
         }
     }
 

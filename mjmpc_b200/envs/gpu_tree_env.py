@@ -22,7 +22,7 @@ class DeviceTreeModel:
             models = [models]
         model = models[0]
         L = _lib.lib()
-        layout = (C.c_int * 45)()
+        layout = (C.c_int * 59)()
         L.mjb_tree_layout(layout)
         mine = [mjcf_tree.LK_RFIX, mjcf_tree.LK_OFF, mjcf_tree.LK_AXIS, mjcf_tree.LK_MASS, mjcf_tree.LK_COM, mjcf_tree.LK_IC,
                 mjcf_tree.LK_RIN, mjcf_tree.LK_BOX, mjcf_tree.LK_ARM, mjcf_tree.LK_DAMP, mjcf_tree.LK_STIFF, mjcf_tree.LK_SREF,
@@ -31,7 +31,10 @@ class DeviceTreeModel:
                 mjcf_tree.LI_TYPE, mjcf_tree.LI_LIMITED, mjcf_tree.LI_ACT, mjcf_tree.LI_BODY, mjcf_tree.LI_STRIDE,
                 mjcf_tree.G_DT, mjcf_tree.G_GRAV, mjcf_tree.G_RHO, mjcf_tree.G_VISC, mjcf_tree.G_STRIDE, mjcf_tree.MAX_LINKS,
                 mjcf_tree.PK_OFF, mjcf_tree.PK_DIR, mjcf_tree.PK_MASS, mjcf_tree.PK_COM, mjcf_tree.PK_INN, mjcf_tree.PK_CLIN,
-                mjcf_tree.PK_KV1, mjcf_tree.PK_KV2, mjcf_tree.PK_E, mjcf_tree.PK_AK, mjcf_tree.PK_STRIDE]
+                mjcf_tree.PK_KV1, mjcf_tree.PK_KV2, mjcf_tree.PK_E, mjcf_tree.PK_AK, mjcf_tree.PK_STRIDE,
+                mjcf_tree.CT_A, mjcf_tree.CT_HA, mjcf_tree.CT_RA, mjcf_tree.CT_B, mjcf_tree.CT_HB, mjcf_tree.CT_RB, mjcf_tree.CT_MU,
+                mjcf_tree.CT_K, mjcf_tree.CT_BB, mjcf_tree.CT_SOLIMP, mjcf_tree.CT_INVW, mjcf_tree.CT_STRIDE, mjcf_tree.CTI_STRIDE,
+                mjcf_tree.MAX_CAND]
         if list(layout) != mine:
             raise _lib.MjbError("parameter layout of mjcf_tree.py and csrc/tree_model.h differ")
         packs = [mjcf_tree.pack_links(m) for m in models]
@@ -45,10 +48,14 @@ class DeviceTreeModel:
             self._keep += (np.ascontiguousarray(np.stack([p[0] for p in planars])), np.ascontiguousarray(planars[0][1], np.int32),
                            np.ascontiguousarray(planars[0][2]))
             pk = [k.ctypes.data_as(C.c_void_p) for k in self._keep[3:]]
+        cti, ctd = mjcf_tree.pack_planar_contacts(model)          # raises for contacts the planar kernel cannot simulate
+        self.n_contacts = len(cti)
+        self._keep += (np.ascontiguousarray(cti, np.int32), np.ascontiguousarray(ctd))
         self.handle = C.c_void_p(L.mjb_tree_model_create(
             C.c_int(model.nv), C.c_int(model.nu), self._keep[0].ctypes.data_as(C.c_void_p),
             self._keep[1].ctypes.data_as(C.c_void_p), self._keep[2].ctypes.data_as(C.c_void_p), pk[0], pk[1], pk[2],
-            C.c_int(len(models)), C.c_int(device)))
+            C.c_int(len(cti)), self._keep[-2].ctypes.data_as(C.c_void_p) if len(cti) else None,
+            self._keep[-1].ctypes.data_as(C.c_void_p) if len(cti) else None, C.c_int(len(models)), C.c_int(device)))
         if not self.handle:
             raise _lib.MjbError(L.mjb_last_error().decode())
 
@@ -90,9 +97,11 @@ class GpuTreeVecEnv:
         self.action_lows, self.action_highs = lim[:, 0].copy(), lim[:, 1].copy()
 
     @classmethod
-    def swimmer(cls, device: int = 0, n_workers: int = 1, **model_kwargs):
-        """``Swimmer-v0``: swimmer.py:7 (frame_skip 4), :10-19 (reward), :21-24 (observation)."""
-        model = mjcf_tree.compile_mjcf_string(mjcf_tree.swimmer_mjcf(**model_kwargs), allow_contacts="ignore")
+    def swimmer(cls, device: int = 0, n_workers: int = 1, contacts: bool = True, **model_kwargs):
+        """``Swimmer-v0``: swimmer.py:7 (frame_skip 4), :10-19 (reward), :21-24 (observation).  ``contacts``: simulate the
+        capsule-capsule contacts between non-adjacent links (MuJoCo's default for this file) or drop them."""
+        model = mjcf_tree.compile_mjcf_string(mjcf_tree.swimmer_mjcf(**model_kwargs),
+                                              allow_contacts="model" if contacts else "ignore")
         return cls(model, frame_skip=4, fwd_dof=0, w_fwd=1.0, w_ctrl=1e-4, obs_qpos_start=2, device=device, n_workers=n_workers)
 
     def randomize_dynamics(self, param_dict, base_seed, worker_offset=0):

@@ -794,6 +794,56 @@ def pack_planar(model: TreeModel, tol: float = 1e-12):
     return P, anc, plane(model.gravity)
 
 
+# contact candidates of a planar mechanism (csrc/rollout_tree_planar.cuh): per candidate, doubles / ints
+CT_A, CT_HA, CT_RA, CT_B, CT_HB, CT_RB, CT_MU, CT_K, CT_BB, CT_SOLIMP, CT_INVW, CT_STRIDE, CTI_STRIDE, MAX_CAND = \
+    0, 2, 4, 5, 7, 9, 10, 11, 12, 13, 18, 19, 3, 16
+
+
+def pack_planar_contacts(model: TreeModel, tol: float = 1e-9):
+    """(ints (n, 3), doubles (n, CT_STRIDE)) for the planar kernel, or raises when the contacts do not live in the plane
+    of motion (shapes at different heights along the plane normal, a floor that is not perpendicular to the plane)."""
+    nv = model.nv
+    if not model.contacts:
+        return np.zeros((0, CTI_STRIDE), np.int32), np.zeros((0, CT_STRIDE))
+    if pack_planar(model) is None:
+        raise UnsupportedMjcf("contacts are only simulated for planar mechanisms")
+    if len(model.contacts) > MAX_CAND:
+        raise UnsupportedMjcf("%d contact candidates > %d" % (len(model.contacts), MAX_CAND))
+    xpos, xmat, anchor, axis = kinematics(model, np.zeros(nv))
+    hinges = np.nonzero(model.jnt_type == HINGE)[0]
+    n = axis[hinges[0]]
+    k = int(np.argmin(np.abs(n)))
+    ex = np.eye(3)[k] - n[k] * n
+    ex /= np.linalg.norm(ex)
+    ey = np.cross(n, ex)
+    plane = lambda w: np.array([ex @ w, ey @ w])
+    last = {int(model.jnt_body[j]): j for j in range(nv)}
+    I, D = np.zeros((len(model.contacts), CTI_STRIDE), np.int32), np.zeros((len(model.contacts), CT_STRIDE))
+    heights = []
+    for c, ct in enumerate(model.contacts):
+        l2 = last[ct["body2"]]
+        w0, w1 = (xpos[ct["body2"]] + xmat[ct["body2"]] @ ct[e] for e in ("b0", "b1"))
+        heights += [n @ w0, n @ w1]
+        D[c, CT_B:CT_B + 2], D[c, CT_HB:CT_HB + 2], D[c, CT_RB] = plane(0.5 * (w0 + w1) - anchor[l2]), plane(0.5 * (w1 - w0)), ct["rb"]
+        if ct["kind"] == "plane":
+            if abs(n @ ct["a1"]) > tol:
+                raise UnsupportedMjcf("a contact plane must be perpendicular to the plane of motion")
+            I[c] = (1, -1, l2)
+            D[c, CT_A:CT_A + 2], D[c, CT_HA:CT_HA + 2] = plane(ct["a0"]), plane(ct["a1"])
+        else:
+            l1 = last[ct["body1"]]
+            v0, v1 = (xpos[ct["body1"]] + xmat[ct["body1"]] @ ct[e] for e in ("a0", "a1"))
+            heights += [n @ v0, n @ v1]
+            I[c] = (0, l1, l2)
+            D[c, CT_A:CT_A + 2], D[c, CT_HA:CT_HA + 2], D[c, CT_RA] = plane(0.5 * (v0 + v1) - anchor[l1]), plane(0.5 * (v1 - v0)), ct["ra"]
+        K, B = solref_to_kb(ct["solref"], ct["solimp"], model.timestep)
+        D[c, CT_MU], D[c, CT_K], D[c, CT_BB], D[c, CT_INVW] = ct["mu"], K, B, ct["invweight"]
+        D[c, CT_SOLIMP:CT_SOLIMP + 5] = ct["solimp"]
+    if max(heights) - min(heights) > tol:
+        raise UnsupportedMjcf("colliding shapes at different heights along the plane normal")
+    return I, D
+
+
 # ------------------------------------------------------------------------------------------------ shipped models
 def swimmer_mjcf(radii=(0.07, 0.065, 0.06, 0.055, 0.05), half_length=0.15, spacing=0.3, joint_range=1.5, gear=20.0,
                  timestep=0.005, viscosity=0.000894, density=1000.0, height=0.03) -> str:

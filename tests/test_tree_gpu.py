@@ -40,7 +40,7 @@ def _compare(env, oracle, state, mean, noise, nthreads=8):
 
 @pytest.fixture(scope="module")
 def swimmer():
-    env = GpuTreeVecEnv.swimmer()
+    env = GpuTreeVecEnv.swimmer(contacts=False)          # the contact-free dynamics; contacts: the tests further down
     yield env, TreeOracle(env.model, T.solref_to_kb)
     env.close()
 
@@ -176,6 +176,52 @@ def test_planar_branched_mechanism_matches_oracle(n_axis):
     env.close()
 
 
+def _walker_xml(floor=True):
+    """A half-cheetah-shaped planar walker written for the tests: torso on slide x / slide z / hinge y, two 3-joint legs,
+    a floor it collides with (half_cheetah.xml's collision setup: body geoms contype 1 / conaffinity 0, floor
+    conaffinity 1, condim 3, friction 0.4, solimp "0 0.8 0.01"), springs, dampers, armature, limits."""
+    def leg(name, x, sgn):
+        return ('<body name="%sthigh" pos="%g 0 0"><joint name="%sthigh" axis="0 1 0" range="-.6 .9" stiffness="24" damping="0.6"/>'
+                '<geom name="%st" type="capsule" fromto="0 0 0 %g 0 -.25" size="0.046"/>'
+                '<body name="%sshin" pos="%g 0 -.25"><joint name="%sshin" axis="0 1 0" range="-.8 .8" stiffness="18" damping="0.45"/>'
+                '<geom name="%ss" type="capsule" fromto="0 0 0 %g 0 -.2" size="0.046"/>'
+                '<body name="%sfoot" pos="%g 0 -.2"><joint name="%sfoot" axis="0 1 0" range="-.4 .7" stiffness="12" damping="0.3"/>'
+                '<geom name="%sf" type="capsule" fromto="0 0 0 %g 0 -.05" size="0.046"/></body></body></body>'
+                % (name, x, name, name, sgn * .1, name, sgn * .1, name, name, -sgn * .14, name, -sgn * .14, name, name, sgn * .12))
+    return ('<mujoco model="walker"><compiler angle="radian" inertiafromgeom="true"/>'
+            '<default><joint armature="0.1" limited="true" solimplimit="0 .8 .03"/>'
+            '<geom contype="1" conaffinity="0" condim="3" friction=".4 .1 .1" solimp="0.0 0.8 0.01" solref="0.02 1"/>'
+            '<motor ctrllimited="true" ctrlrange="-1 1"/></default><option timestep="0.01" gravity="0 0 -9.81"/><worldbody>'
+            + ('<geom name="floor" type="plane" conaffinity="1" pos="0 0 0" size="40 40 40"/>' if floor else '') +
+            '<body name="torso" pos="0 0 .7"><joint name="rx" type="slide" axis="1 0 0" limited="false" armature="0"/>'
+            '<joint name="rz" type="slide" axis="0 0 1" limited="false" armature="0"/>'
+            '<joint name="ry" type="hinge" axis="0 1 0" limited="false" armature="0"/>'
+            '<geom name="torso" type="capsule" fromto="-.5 0 0 .5 0 0" size="0.046"/>%s%s</body></worldbody><actuator>%s</actuator></mujoco>'
+            % (leg("b", -.5, 1.0), leg("f", .5, -1.0),
+               "".join('<motor joint="%s" gear="%d"/>' % (j, g) for j, g in
+                       (("bthigh", 120), ("bshin", 90), ("bfoot", 60), ("fthigh", 120), ("fshin", 60), ("ffoot", 30)))))
+
+
+def test_planar_walker_on_a_floor_matches_oracle():
+    """Ground contact with friction cones (the half-cheetah's kind): plane against the end spheres of capsules, several
+    contacts at once, with limits, springs and implicit damping; dropped from 0.7 m, pushed by random torques."""
+    model = T.compile_mjcf_string(_walker_xml(), allow_contacts="model")
+    assert model.nv == 9 and len(model.contacts) == 7
+    env = GpuTreeVecEnv(model, frame_skip=5, fwd_dof=0, w_fwd=1.0, w_ctrl=0.1, obs_qpos_start=1)      # half_cheetah.py:7-25
+    oracle = TreeOracle(model, T.solref_to_kb)
+    rng = np.random.default_rng(31)
+    total = 0
+    for z0 in (0.0, -0.12, -0.2):
+        K, H = 64, 8
+        state = np.concatenate([rng.uniform(-.1, .1, 9), rng.normal(0, 0.5, 9)])
+        state[1] = z0                                     # torso height offset: feet above / at / into the floor
+        nefc, nefc_ref, _ = _compare(env, oracle, state, rng.normal(0, 0.3, (H, 6)), rng.normal(0, 0.7, (K, H, 6)))
+        assert nefc == nefc_ref
+        total += nefc
+    assert total > 64 * 8 * 5 * 8                          # the feet are on the floor most of the time
+    env.close()
+
+
 def test_non_planar_models_take_the_general_instantiation():
     model = T.compile_mjcf(os.path.join(FIX, "tree3d.xml"))
     assert T.pack_planar(model) is None
@@ -214,6 +260,37 @@ def test_per_worker_randomised_models(per_worker):
     env.close()
 
 
+def test_swimmer_self_contact_matches_oracle():
+    """swimmer.xml's non-adjacent capsules collide (MuJoCo's default): rollouts started from folded poses, where the
+    capsule-capsule contacts with their pyramidal friction rows act together with the joint limits."""
+    env = GpuTreeVecEnv.swimmer()                            # contacts on by default
+    assert env.dmodel.n_contacts == 6 and env.dmodel.planar
+    oracle = TreeOracle(env.model, T.solref_to_kb)
+    rng = np.random.default_rng(21)
+    total = 0
+    for trial in range(3):
+        K, H = 64, 6
+        state = np.concatenate([rng.uniform(-.2, .2, 7), rng.normal(0, 1.0, 7)])
+        sgn = 1.0 if trial != 1 else -1.0
+        state[3:7] = sgn * np.array([1.45, 1.5, 1.42, 0.3 if trial == 2 else 1.4])
+        assert T.self_clearance(env.model, state[:7]) < 0
+        nefc, nefc_ref, _ = _compare(env, oracle, state, rng.normal(0, 0.4, (H, 4)), rng.normal(0, 0.6, (K, H, 4)))
+        assert nefc == nefc_ref
+        total += nefc
+    assert total > 3 * 64 * 4 * 4                            # contacts (4 rows each) in most substeps
+    # away from contact the two models coincide
+    free = GpuTreeVecEnv.swimmer(contacts=False)
+    state = np.concatenate([rng.uniform(-.3, .3, 7), rng.normal(0, 0.5, 7)])
+    mean, noise = rng.normal(0, 0.2, (4, 4)), rng.normal(0, 0.2, (32, 4, 4))
+    outs = []
+    for e in (env, free):
+        e.set_env_state({"qpos": state[:7], "qvel": state[7:]})
+        outs.append(e.rollout_device(32, 4, torch.as_tensor(mean, device=e.device), torch.as_tensor(noise, device=e.device),
+                                     want_states=True)["states"].cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    env.close(); free.close()
+
+
 def test_batched_controllers_share_one_launch(swimmer):
     env, oracle = swimmer
     rng = np.random.default_rng(4)
@@ -250,8 +327,8 @@ def test_reference_rollout_signature(swimmer):
 def test_mppi_swims_forward():
     """MPPI on the plant (swimmer.py reward = forward velocity): the planner makes the swimmer advance along +x."""
     from mjmpc_b200.control import MPPI
-    plant = GpuSwimmerEnv(seed=0)
-    sim = GpuTreeVecEnv.swimmer()
+    plant = GpuSwimmerEnv(seed=0, contacts=False)
+    sim = GpuTreeVecEnv.swimmer(contacts=False)
     H, K = 20, 256
     ctrl = MPPI(d_state=14, d_obs=12, d_action=4, action_lows=sim.action_lows, action_highs=sim.action_highs, horizon=H,
                 init_cov=0.5, base_action="null", num_particles=K, lam=0.05, step_size=1.0, alpha=0, gamma=1.0, n_iters=1,
