@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mjmpc_b200.envs.gpu_reacher_env import GpuContinualReacherEnv, GpuReacherEnv          # noqa: E402
 from mjmpc_b200.envs.gpu_vec_env import GpuReacherVecEnv            # noqa: E402
 from mjmpc_b200.envs.gpu_pendulum import GpuPendulumEnv, GpuPendulumVecEnv    # noqa: E402
-from mjmpc_b200.envs.gpu_tree_env import GpuSwimmerEnv, GpuTreeVecEnv          # noqa: E402
+from mjmpc_b200.envs.gpu_tree_env import GpuHalfCheetahEnv, GpuSwimmerEnv, GpuTreeVecEnv          # noqa: E402
 from mjmpc_b200.policies import MPCPolicy                           # noqa: E402
 
 
@@ -40,7 +40,7 @@ def load_policy_params(exp_params, controller_name, env):
 
 
 def main():
-    parser = argparse.ArgumentParser(description='Run an MPC algorithm on the GPU backend (reacher_7dof-v0, continual_reacher-v0, SimplePendulum-v0, Swimmer-v0)')
+    parser = argparse.ArgumentParser(description='Run an MPC algorithm on the GPU backend (reacher_7dof-v0, continual_reacher-v0, SimplePendulum-v0, Swimmer-v0, HalfCheetah-v0)')
     parser.add_argument('--config', type=str, required=True, help='yaml file with experiment parameters')
     parser.add_argument('--dyn_randomize_config', type=str, help='yaml file with dynamics randomization parameters')
     parser.add_argument('--controller', type=str, default='mppi', help='controller to run')
@@ -55,12 +55,13 @@ def main():
             dynamics_rand_params = yaml.load(file, Loader=yaml.FullLoader)
     # env name -> (plant, planner's rollout backend)                                mjmpc/envs/__init__.py:5-35
     plants = {'reacher_7dof-v0': (GpuReacherEnv, GpuReacherVecEnv), 'continual_reacher-v0': (GpuContinualReacherEnv, GpuReacherVecEnv),
-              'SimplePendulum-v0': (GpuPendulumEnv, GpuPendulumVecEnv), 'Swimmer-v0': (GpuSwimmerEnv, GpuTreeVecEnv.swimmer)}
+              'SimplePendulum-v0': (GpuPendulumEnv, GpuPendulumVecEnv), 'Swimmer-v0': (GpuSwimmerEnv, GpuTreeVecEnv.swimmer),
+              'HalfCheetah-v0': (GpuHalfCheetahEnv, GpuTreeVecEnv.half_cheetah)}
     if exp_params['env_name'] not in plants:
         raise NotImplementedError("only %s have a GPU plant; see DESIGN.md section 6" % sorted(plants))
     plant_cls, sim_cls = plants[exp_params['env_name']]
     reacher = sim_cls is GpuReacherVecEnv
-    swimmer = exp_params['env_name'] == 'Swimmer-v0'
+    swimmer = exp_params['env_name'] in ('Swimmer-v0', 'HalfCheetah-v0')
     env = plant_cls()
     policy_params, num_cpu = load_policy_params(exp_params, args.controller, env)
     n_episodes = args.n_episodes or exp_params['n_episodes']

@@ -104,6 +104,13 @@ class GpuTreeVecEnv:
                                               allow_contacts="model" if contacts else "ignore")
         return cls(model, frame_skip=4, fwd_dof=0, w_fwd=1.0, w_ctrl=1e-4, obs_qpos_start=2, device=device, n_workers=n_workers)
 
+    @classmethod
+    def half_cheetah(cls, device: int = 0, n_workers: int = 1):
+        """``HalfCheetah-v0`` (mjmpc/envs/__init__.py:16-19): half_cheetah.py:7 (frame_skip 5), :10-19 (reward), :21-25
+        (observation = qpos[1:], qvel), with the ground contacts of half_cheetah.xml."""
+        model = mjcf_tree.compile_mjcf_string(mjcf_tree.half_cheetah_mjcf(), allow_contacts="model")
+        return cls(model, frame_skip=5, fwd_dof=0, w_fwd=1.0, w_ctrl=0.1, obs_qpos_start=1, device=device, n_workers=n_workers)
+
     def randomize_dynamics(self, param_dict, base_seed, worker_offset=0):
         """Per-worker model perturbation, worker i seeded with base_seed + i * 12345 (subproc_vec_env.py:304-312 ->
         gym_env_wrapper.py:367-416); particle k of a rollout runs the model of worker k // (K / n_workers).  Replaces
@@ -229,9 +236,17 @@ class GpuSwimmerEnv:
     """The PLANT for ``Swimmer-v0`` (``mjmpc/envs/basic/swimmer.py:5-49``): one swimmer advanced by the kernel the
     planner rolls out (K = 1, H = 1)."""
     _max_episode_steps = 1000
+    _ctrl_coeff = 1e-4
+
+    def _make_sim(self, device, **model_kwargs):
+        return GpuTreeVecEnv.swimmer(device=device, **model_kwargs)
+
+    def _reset_noise(self):
+        """swimmer.py:26-31: U(-0.1, 0.1) on qpos and on qvel."""
+        return self.np_random.uniform(low=-.1, high=.1, size=self.nv), self.np_random.uniform(low=-.1, high=.1, size=self.nv)
 
     def __init__(self, device: int = 0, seed=None, **model_kwargs):
-        self.sim = GpuTreeVecEnv.swimmer(device=device, **model_kwargs)
+        self.sim = self._make_sim(device, **model_kwargs)
         self.d_obs, self.d_state, self.d_action = self.sim.d_obs, self.sim.d_state, self.sim.d_action
         self.action_lows, self.action_highs = self.sim.action_lows, self.sim.action_highs
         self.np_random = np.random.RandomState(seed)
@@ -244,12 +259,12 @@ class GpuSwimmerEnv:
         """swimmer.py:26-31 reset_model: init + U(-0.1, 0.1) on qpos and qvel."""
         if seed is not None:
             self.np_random = np.random.RandomState(seed)
-        self.qpos = self.init_qpos + self.np_random.uniform(low=-.1, high=.1, size=self.nv)
-        self.qvel = self.init_qvel + self.np_random.uniform(low=-.1, high=.1, size=self.nv)
+        dq, dv = self._reset_noise()
+        self.qpos, self.qvel = self.init_qpos + dq, self.init_qvel + dv
         return self.get_obs()
 
     def get_obs(self):
-        return np.concatenate([self.qpos[2:], self.qvel])          # swimmer.py:21-24
+        return np.concatenate([self.qpos[self.sim.obs_qpos_start:], self.qvel])          # swimmer.py:21-24, half_cheetah.py:21-25
 
     def get_env_state(self):
         return {'qpos': self.qpos.copy(), 'qvel': self.qvel.copy()}
@@ -267,7 +282,7 @@ class GpuSwimmerEnv:
         xbefore = self.qpos[0]
         self.qpos, self.qvel = s[:self.nv].copy(), s[self.nv:].copy()
         reward_fwd = (self.qpos[0] - xbefore) / self.dt
-        reward_ctrl = -1e-4 * float(np.square(a).sum())
+        reward_ctrl = -self._ctrl_coeff * float(np.square(a).sum())
         return self.get_obs(), -float(out["costs"][0, 0].item()), False, dict(reward_fwd=reward_fwd, reward_ctrl=reward_ctrl)
 
     def self_clearance(self):
@@ -280,3 +295,15 @@ class GpuSwimmerEnv:
 
     def close(self):
         self.sim.close()
+
+
+class GpuHalfCheetahEnv(GpuSwimmerEnv):
+    """The PLANT for ``HalfCheetah-v0`` (``mjmpc/envs/basic/half_cheetah.py:5-51``)."""
+    _ctrl_coeff = 0.1
+
+    def _make_sim(self, device, **model_kwargs):
+        return GpuTreeVecEnv.half_cheetah(device=device, **model_kwargs)
+
+    def _reset_noise(self):
+        """half_cheetah.py:27-31: U(-0.1, 0.1) on qpos, 0.1 * N(0, 1) on qvel."""
+        return self.np_random.uniform(low=-.1, high=.1, size=self.nv), self.np_random.randn(self.nv) * .1

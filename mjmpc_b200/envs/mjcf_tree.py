@@ -867,3 +867,38 @@ def swimmer_mjcf(radii=(0.07, 0.065, 0.06, 0.055, 0.05), half_length=0.15, spaci
     parts += ['<motor joint="j%d" gear="%g"/>' % (i, gear) for i in range(1, n)]
     parts.append("</actuator></mujoco>")
     return "".join(parts)
+
+
+def half_cheetah_mjcf() -> str:
+    """MJCF text of the reference's ``HalfCheetah-v0`` model (``mjmpc/envs/assets/xml/half_cheetah.xml``), physics only:
+    a torso (two capsules) on slide x / slide z / hinge y, a back and a front leg of three spring-loaded, damped, limited
+    hinges each, geared motors, total mass set to 14, a floor the capsules collide with (friction 0.4, condim 3).  Restated
+    as a parameter list because ``/root/reference`` does not travel to the GPU box; tests/test_tree_cpu.py compares its
+    compilation with the reference file's."""
+    legs = [  # body, pos, joint range, stiffness, damping, geom axisangle-y, geom pos, geom half length, gear
+        [("bthigh", "-.5 0 0", "-.52 1.05", 240, 6, -3.8, ".1 0 -.13", .145, 120),
+         ("bshin", ".16 0 -.25", "-.785 .785", 180, 4.5, -2.03, "-.14 0 -.07", .15, 90),
+         ("bfoot", "-.28 0 -.14", "-.4 .785", 120, 3, -.27, ".03 0 -.097", .094, 60)],
+        [("fthigh", ".5 0 0", "-1 .7", 180, 4.5, .52, "-.07 0 -.12", .133, 120),
+         ("fshin", "-.14 0 -.24", "-1.2 .87", 120, 3, -.6, ".065 0 -.09", .106, 60),
+         ("ffoot", ".13 0 -.18", "-.5 .5", 60, 1.5, -.6, ".045 0 -.07", .07, 30)]]
+    parts = ['<mujoco model="cheetah"><compiler angle="radian" coordinate="local" inertiafromgeom="true" settotalmass="14"/>',
+             '<default><joint armature=".1" damping=".01" limited="true" solimplimit="0 .8 .03" solreflimit=".02 1" stiffness="8"/>',
+             '<geom conaffinity="0" condim="3" contype="1" friction=".4 .1 .1" solimp="0.0 0.8 0.01" solref="0.02 1"/>',
+             '<motor ctrllimited="true" ctrlrange="-1 1"/></default><option gravity="0 0 -9.81" timestep="0.01"/><worldbody>',
+             '<geom conaffinity="1" condim="3" name="floor" pos="0 0 0" size="40 40 40" type="plane"/><body name="torso" pos="0 0 .7">']
+    for name, axis, kind in (("rootx", "1 0 0", "slide"), ("rootz", "0 0 1", "slide"), ("rooty", "0 1 0", "hinge")):
+        parts.append('<joint armature="0" axis="%s" damping="0" limited="false" name="%s" pos="0 0 0" stiffness="0" type="%s"/>'
+                     % (axis, name, kind))
+    parts.append('<geom fromto="-.5 0 0 .5 0 0" name="torso" size="0.046" type="capsule"/>')
+    parts.append('<geom axisangle="0 1 0 .87" name="head" pos=".6 0 .1" size="0.046 .15" type="capsule"/>')
+    for leg in legs:
+        for name, pos, rng, k, d, ang, gpos, half, _ in leg:
+            parts.append('<body name="%s" pos="%s"><joint axis="0 1 0" damping="%g" name="%s" pos="0 0 0" range="%s" stiffness="%g" '
+                         'type="hinge"/><geom axisangle="0 1 0 %g" name="%s" pos="%s" size="0.046 %g" type="capsule"/>'
+                         % (name, pos, d, name, rng, k, ang, name, gpos, half))
+        parts.append("</body>" * 3)
+    parts.append("</body></worldbody><actuator>")
+    parts += ['<motor gear="%g" joint="%s" name="%s"/>' % (g, n, n) for leg in legs for (n, _, _, _, _, _, _, _, g) in leg]
+    parts.append("</actuator></mujoco>")
+    return "".join(parts)

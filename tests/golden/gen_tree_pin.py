@@ -22,16 +22,20 @@ from oracle import tree_ref  # noqa: E402
 
 MODELS = {"swimmer": "/root/reference/mjmpc/envs/assets/xml/swimmer.xml",
           "tree3d": os.path.join(ROOT, "tests", "fixtures", "tree3d.xml"),
-          "tree3d_weld": os.path.join(ROOT, "tests", "fixtures", "tree3d_weld.xml")}
+          "tree3d_weld": os.path.join(ROOT, "tests", "fixtures", "tree3d_weld.xml"),
+          # the contact half: the same swimmer with its capsule-capsule contacts (folded poses), a walker on a floor
+          "swimmer_contact": "/root/reference/mjmpc/envs/assets/xml/swimmer.xml",
+          "walker": os.path.join(ROOT, "tests", "fixtures", "planar_walker.xml")}
 
 
 def main():
     out = {}
     rng = np.random.default_rng(20260101)
     for name, xml in MODELS.items():
-        m = tree_ref.read_model(xml)
+        contact = name in ("swimmer_contact", "walker")
+        m = tree_ref.read_model(xml, contacts=contact)
         nv, nu = m["nv"], len(m["motors"])
-        n = 48
+        n = 24 if contact else 48
         Q, V, U = np.zeros((n, nv)), np.zeros((n, nv)), np.zeros((n, nu))
         keys = ("M", "bias", "passive", "actuation", "constraint", "qacc")
         rec = {k: [] for k in keys}
@@ -43,6 +47,12 @@ def main():
                     if j["limited"] and rng.random() < 0.5:
                         d = rng.uniform(0, 0.003 if i % 3 == 1 else 0.2)
                         q[k] = j["range"][0] - d if rng.random() < 0.5 else j["range"][1] + d
+            if name == "swimmer_contact":     # three or four joints folded to one side: non-adjacent capsules overlap
+                q[3:7] = rng.choice([-1.0, 1.0]) * rng.uniform(1.3, 1.6, 4)
+                if i % 4 == 0:
+                    q[6] = -q[6]
+            if name == "walker":              # feet at / into the floor (rest height of the feet is ~0.2 m above it)
+                q[:3] = [rng.uniform(-1, 1), rng.uniform(-0.3, -0.1), rng.uniform(-0.4, 0.4)]
             v = rng.normal(0, 2.0 if i % 2 else 0.2, nv)
             u = rng.normal(0, 1.2, nu)
             q2, v2, info = tree_ref.step(m, q, v, u)

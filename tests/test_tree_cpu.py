@@ -24,6 +24,10 @@ def g():
 def _model(name):
     if name == "swimmer":
         return T.compile_mjcf_string(T.swimmer_mjcf(), allow_contacts="ignore")
+    if name == "swimmer_contact":
+        return T.compile_mjcf_string(T.swimmer_mjcf(), allow_contacts="model")
+    if name == "walker":
+        return T.compile_mjcf(os.path.join(FIX, "planar_walker.xml"), allow_contacts="model")
     return T.compile_mjcf(os.path.join(FIX, name + ".xml"))
 
 
@@ -32,7 +36,7 @@ def _rel(a, b):
     return float(np.abs(np.asarray(a, float) - b).max() / (1.0 + np.abs(b).max()))
 
 
-@pytest.mark.parametrize("name", ["swimmer", "tree3d", "tree3d_weld"])
+@pytest.mark.parametrize("name", ["swimmer", "tree3d", "tree3d_weld", "swimmer_contact", "walker"])
 def test_c_oracle_and_compiled_constants_match_the_independent_restatement(g, name):
     m = _model(name)
     np.testing.assert_allclose(m.dof_invweight0, g[name + "_invweight0"], rtol=1e-10)
@@ -41,7 +45,9 @@ def test_c_oracle_and_compiled_constants_match_the_independent_restatement(g, na
         np.testing.assert_allclose(np.sort(m.body_inertia, axis=1), np.sort(g[name + "_inertia"], axis=1), rtol=1e-12)
     o = TreeOracle(m, T.solref_to_kb)
     n = len(g[name + "_q"])
-    assert int((g[name + "_nefc"] > 0).sum()) >= 25
+    assert int((g[name + "_nefc"] > 0).sum()) >= 20
+    if name in ("swimmer_contact", "walker"):            # four pyramid rows per contact on top of the limit rows
+        assert int((g[name + "_nefc"] >= 4).sum()) >= 14 and int(g[name + "_nefc"].max()) >= 10
     worst = {}
     for i in range(n):
         r = o.substep(g[name + "_q"][i], g[name + "_v"][i], g[name + "_u"][i])
@@ -79,13 +85,25 @@ def test_generated_swimmer_equals_the_reference_file():
 
 
 @needs_ref
-def test_half_cheetah_is_rejected_not_simulated_wrongly():
-    """half_cheetah.xml needs ground contact with friction cones: outside the subset, and the compiler says so."""
+def test_generated_half_cheetah_equals_the_reference_file():
+    """half_cheetah.xml: contacts must be asked for (the default refuses them), and the parameter list in
+    half_cheetah_mjcf() IS the reference file as far as the physics goes -- contact candidates included."""
     with pytest.raises(T.UnsupportedMjcf, match="contacts"):
         T.compile_mjcf(os.path.join(REF_XML, "half_cheetah.xml"))
-    m = T.compile_mjcf(os.path.join(REF_XML, "half_cheetah.xml"), allow_contacts="ignore")   # the tree itself compiles
-    assert m.nv == 9 and m.nu == 6 and abs(m.body_mass.sum() - 14.0) < 1e-12                # settotalmass
-    assert list(m.jnt_type[:3]) == [T.SLIDE, T.SLIDE, T.HINGE] and m.jnt_stiffness[3] == 240.0
+    a = T.compile_mjcf_string(T.half_cheetah_mjcf(), allow_contacts="model")
+    b = T.compile_mjcf(os.path.join(REF_XML, "half_cheetah.xml"), allow_contacts="model")
+    assert a.nv == 9 and a.nu == 6 and abs(a.body_mass.sum() - 14.0) < 1e-12                # settotalmass
+    assert list(a.jnt_type[:3]) == [T.SLIDE, T.SLIDE, T.HINGE] and a.jnt_stiffness[3] == 240.0
+    for f in ("body_parent", "body_pos", "body_mat", "body_mass", "body_ipos", "body_imat", "body_inertia", "jnt_type",
+              "jnt_body", "jnt_pos", "jnt_axis", "jnt_limited", "jnt_range", "jnt_damping", "jnt_armature", "jnt_stiffness",
+              "jnt_solimp", "jnt_solref", "act_dof", "act_gear", "act_ctrlrange", "gravity", "dof_invweight0"):
+        np.testing.assert_array_equal(getattr(a, f), getattr(b, f), err_msg=f)
+    assert len(a.contacts) == len(b.contacts) == 8                                          # floor x 8 capsules
+    for ca, cb in zip(a.contacts, b.contacts):
+        assert ca["kind"] == cb["kind"] == "plane" and ca["mu"] == cb["mu"] == 0.4
+        for k in ("a0", "a1", "b0", "b1", "rb", "solimp", "solref", "invweight", "body2"):
+            np.testing.assert_array_equal(ca[k], cb[k], err_msg=k)
+    assert T.pack_planar(a) is not None and T.pack_planar_contacts(a)[0].shape == (8, 3)
 
 
 @pytest.mark.parametrize("bad,why", [

@@ -176,30 +176,8 @@ def test_planar_branched_mechanism_matches_oracle(n_axis):
     env.close()
 
 
-def _walker_xml(floor=True):
-    """A half-cheetah-shaped planar walker written for the tests: torso on slide x / slide z / hinge y, two 3-joint legs,
-    a floor it collides with (half_cheetah.xml's collision setup: body geoms contype 1 / conaffinity 0, floor
-    conaffinity 1, condim 3, friction 0.4, solimp "0 0.8 0.01"), springs, dampers, armature, limits."""
-    def leg(name, x, sgn):
-        return ('<body name="%sthigh" pos="%g 0 0"><joint name="%sthigh" axis="0 1 0" range="-.6 .9" stiffness="24" damping="0.6"/>'
-                '<geom name="%st" type="capsule" fromto="0 0 0 %g 0 -.25" size="0.046"/>'
-                '<body name="%sshin" pos="%g 0 -.25"><joint name="%sshin" axis="0 1 0" range="-.8 .8" stiffness="18" damping="0.45"/>'
-                '<geom name="%ss" type="capsule" fromto="0 0 0 %g 0 -.2" size="0.046"/>'
-                '<body name="%sfoot" pos="%g 0 -.2"><joint name="%sfoot" axis="0 1 0" range="-.4 .7" stiffness="12" damping="0.3"/>'
-                '<geom name="%sf" type="capsule" fromto="0 0 0 %g 0 -.05" size="0.046"/></body></body></body>'
-                % (name, x, name, name, sgn * .1, name, sgn * .1, name, name, -sgn * .14, name, -sgn * .14, name, name, sgn * .12))
-    return ('<mujoco model="walker"><compiler angle="radian" inertiafromgeom="true"/>'
-            '<default><joint armature="0.1" limited="true" solimplimit="0 .8 .03"/>'
-            '<geom contype="1" conaffinity="0" condim="3" friction=".4 .1 .1" solimp="0.0 0.8 0.01" solref="0.02 1"/>'
-            '<motor ctrllimited="true" ctrlrange="-1 1"/></default><option timestep="0.01" gravity="0 0 -9.81"/><worldbody>'
-            + ('<geom name="floor" type="plane" conaffinity="1" pos="0 0 0" size="40 40 40"/>' if floor else '') +
-            '<body name="torso" pos="0 0 .7"><joint name="rx" type="slide" axis="1 0 0" limited="false" armature="0"/>'
-            '<joint name="rz" type="slide" axis="0 0 1" limited="false" armature="0"/>'
-            '<joint name="ry" type="hinge" axis="0 1 0" limited="false" armature="0"/>'
-            '<geom name="torso" type="capsule" fromto="-.5 0 0 .5 0 0" size="0.046"/>%s%s</body></worldbody><actuator>%s</actuator></mujoco>'
-            % (leg("b", -.5, 1.0), leg("f", .5, -1.0),
-               "".join('<motor joint="%s" gear="%d"/>' % (j, g) for j, g in
-                       (("bthigh", 120), ("bshin", 90), ("bfoot", 60), ("fthigh", 120), ("fshin", 60), ("ffoot", 30)))))
+def _walker_xml():
+    return open(os.path.join(FIX, "planar_walker.xml")).read()
 
 
 def test_planar_walker_on_a_floor_matches_oracle():
@@ -220,6 +198,49 @@ def test_planar_walker_on_a_floor_matches_oracle():
         total += nefc
     assert total > 64 * 8 * 5 * 8                          # the feet are on the floor most of the time
     env.close()
+
+
+def test_half_cheetah_rollouts_match_oracle():
+    """HalfCheetah-v0 (half_cheetah.py:7-25) on the reference's own model: the cheetah standing on its feet (the file's
+    initial pose penetrates the floor by a few mm), dropped, and thrown sideways; reward = forward speed - 0.1 |a|^2."""
+    env = GpuTreeVecEnv.half_cheetah()
+    assert env.nv == 9 and env.d_obs == 17 and env.frame_skip == 5 and env.dmodel.n_contacts == 8
+    oracle = TreeOracle(env.model, T.solref_to_kb)
+    rng = np.random.default_rng(41)
+    total = 0
+    for case in range(3):
+        K, H = 64, 8
+        state = np.concatenate([rng.uniform(-.1, .1, 9), 0.1 * rng.normal(0, 1.0, 9)])          # half_cheetah.py:27-31
+        if case == 1:
+            state[1] += 0.3                                   # in the air first
+        if case == 2:
+            state[2] = 1.2; state[9] = 2.0                    # pitched forward and moving: head and torso hit the floor
+        nefc, nefc_ref, _ = _compare(env, oracle, state, rng.normal(0, 0.3, (H, 6)), rng.normal(0, 0.7, (K, H, 6)))
+        assert nefc == nefc_ref
+        total += nefc
+    assert total > 10000                                   # contact rows in most substeps
+    env.close()
+
+
+def test_mppi_makes_the_cheetah_run():
+    from mjmpc_b200.control import MPPI
+    from mjmpc_b200.envs.gpu_tree_env import GpuHalfCheetahEnv
+    plant = GpuHalfCheetahEnv(seed=0)
+    sim = GpuTreeVecEnv.half_cheetah()
+    H, K = 16, 192
+    ctrl = MPPI(d_state=18, d_obs=17, d_action=6, action_lows=sim.action_lows, action_highs=sim.action_highs, horizon=H,
+                init_cov=0.3, base_action="null", num_particles=K, lam=0.05, step_size=1.0, alpha=0, gamma=1.0, n_iters=1,
+                set_sim_state_fn=sim.set_env_state, rollout_fn=sim.rollout_fn, sample_mode="mean", batch_size=1, seed=0,
+                filter_coeffs=[1.0, 0.0, 0.0])
+    plant.reset(seed=0)
+    x0 = plant.qpos[0]
+    for _ in range(40):
+        a, _ = ctrl.optimize(plant.get_env_state())
+        obs, r, done, info = plant.step(a)
+    assert obs.shape == (17,) and np.isfinite(plant.qpos).all()
+    assert plant.qpos[0] - x0 > 0.3, plant.qpos[0] - x0          # 2 s of control: it has moved forward
+    assert plant.qpos[1] > -0.45                                  # and has not fallen through the floor
+    plant.close(); sim.close()
 
 
 def test_non_planar_models_take_the_general_instantiation():
