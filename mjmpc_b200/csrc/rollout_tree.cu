@@ -491,8 +491,9 @@ TR_HD int substep(const double* lk, const int* li, const double* g, int nv_rt, d
     return limits_solve_integrate_inl<N>(nv, lk, li, h, M, f, damped, q, v);
 }
 
-// PLANAR: the planar instantiation (rollout_tree_planar.cuh; NV > 0), else the general 3-D one.
-template <int NV, bool SERIAL, bool PLANAR>
+// PLANAR: the planar instantiation (rollout_tree_planar.cuh; NV > 0), else the general 3-D one; CONTACTS: with the
+// contact candidates of the model (planar only).
+template <int NV, bool SERIAL, bool PLANAR, bool CONTACTS>
 __global__ void __launch_bounds__(64) rollout_tree_kernel(const double* __restrict__ g_lk, const int* __restrict__ g_li,
                                                           const double* __restrict__ g_g, const double* __restrict__ g_pk,
                                                           const int* __restrict__ g_anc, int ncand, const int* __restrict__ g_cti,
@@ -504,8 +505,8 @@ __global__ void __launch_bounds__(64) rollout_tree_kernel(const double* __restri
     __shared__ double s_g[TG_STRIDE];
     __shared__ double s_pk[PLANAR ? N * PK_STRIDE + 2 : 1];
     __shared__ int s_anc[PLANAR ? N : 1];
-    __shared__ int s_cti[PLANAR ? MJB_TREE_MAX_CAND * CTI_STRIDE : 1];
-    __shared__ double s_ctd[PLANAR ? MJB_TREE_MAX_CAND * CT_STRIDE : 1];
+    __shared__ int s_cti[CONTACTS ? MJB_TREE_MAX_CAND * CTI_STRIDE : 1];
+    __shared__ double s_ctd[CONTACTS ? MJB_TREE_MAX_CAND * CT_STRIDE : 1];
     const int nv = NV > 0 ? NV : nv_rt;
     // blocks are model-uniform: instance = block / blocks-per-model (one model: the plain particle numbering)
     const int bpm = (a.particles_per_model + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -518,8 +519,10 @@ __global__ void __launch_bounds__(64) rollout_tree_kernel(const double* __restri
         g_pk += (long long)inst * (nv * PK_STRIDE + 2);
         for (int i = threadIdx.x; i < nv * PK_STRIDE + 2; i += blockDim.x) s_pk[i] = g_pk[i];
         for (int i = threadIdx.x; i < nv; i += blockDim.x) s_anc[i] = g_anc[i];
-        for (int i = threadIdx.x; i < ncand * CTI_STRIDE; i += blockDim.x) s_cti[i] = g_cti[i];
-        for (int i = threadIdx.x; i < ncand * CT_STRIDE; i += blockDim.x) s_ctd[i] = g_ctd[i];
+        if (CONTACTS) {
+            for (int i = threadIdx.x; i < ncand * CTI_STRIDE; i += blockDim.x) s_cti[i] = g_cti[i];
+            for (int i = threadIdx.x; i < ncand * CT_STRIDE; i += blockDim.x) s_ctd[i] = g_ctd[i];
+        }
     }
     __syncthreads();
     const long long k = (long long)inst * a.particles_per_model + local;
@@ -560,7 +563,7 @@ __global__ void __launch_bounds__(64) rollout_tree_kernel(const double* __restri
 #pragma unroll
         for (int i = 0; i < N; i++) if (i == a.fwd_dof) before = q[i];
         for (int s = 0; s < a.frame_skip; s++) {
-            if constexpr (PLANAR) nefc += planar_substep<NV, SERIAL>(s_lk, s_li, s_pk, s_anc, s_g, s_pk + NV * PK_STRIDE, ncand, s_cti, s_ctd, q, v, uf);
+            if constexpr (PLANAR) nefc += planar_substep<NV, SERIAL, CONTACTS>(s_lk, s_li, s_pk, s_anc, s_g, s_pk + NV * PK_STRIDE, ncand, s_cti, s_ctd, q, v, uf);
             else nefc += substep<NV, SERIAL, false>(s_lk, s_li, s_g, nv, q, v, u);
         }
 #pragma unroll
@@ -689,14 +692,20 @@ extern "C" int mjb_rollout_tree(const mjb_tree_model* m, const mjb_tree_rollout_
     using namespace mjb::tree;
     MJB_REQUIRE(m->ncand == 0 || g_use_planar, "mjb_rollout_tree: a model with contacts runs in the planar instantiation only");
     const bool planar = m->planar && g_use_planar;
-#define MJB_TREE_LAUNCH(NV, SERIAL, PLANAR) \
-    rollout_tree_kernel<NV, SERIAL, PLANAR><<<blocks, 64, 0, st>>>(m->d_lk, m->d_li, m->d_g, m->d_pk, m->d_anc, m->ncand, m->d_cti, m->d_ctd, \
-                                                               m->nv, m->nu, *a)
-    if (planar && m->nv == 7 && m->serial) MJB_TREE_LAUNCH(7, true, true);
-    else if (planar && m->nv == 7) MJB_TREE_LAUNCH(7, false, true);
-    else if (planar && m->nv == 9) MJB_TREE_LAUNCH(9, false, true);
-    else if (m->nv == 7 && m->serial) MJB_TREE_LAUNCH(7, true, false);
-    else MJB_TREE_LAUNCH(0, false, false);
+#define MJB_TREE_LAUNCH(NV, SERIAL, PLANAR, CONTACTS) \
+    rollout_tree_kernel<NV, SERIAL, PLANAR, CONTACTS><<<blocks, 64, 0, st>>>(m->d_lk, m->d_li, m->d_g, m->d_pk, m->d_anc, m->ncand, m->d_cti, \
+                                                                         m->d_ctd, m->nv, m->nu, *a)
+    if (m->ncand > 0) {
+        // contacts: the two shapes the reference's models have (swimmer: 7 dofs in series; half-cheetah: 9, two legs)
+        if (m->nv == 7 && m->serial) MJB_TREE_LAUNCH(7, true, true, true);
+        else if (m->nv == 9) MJB_TREE_LAUNCH(9, false, true, true);
+        else return mjb::set_error(MJB_ENOTIMPL, "mjb_rollout_tree: contacts are instantiated for 7 dofs in series and for 9-dof trees");
+    }
+    else if (planar && m->nv == 7 && m->serial) MJB_TREE_LAUNCH(7, true, true, false);
+    else if (planar && m->nv == 7) MJB_TREE_LAUNCH(7, false, true, false);
+    else if (planar && m->nv == 9) MJB_TREE_LAUNCH(9, false, true, false);
+    else if (m->nv == 7 && m->serial) MJB_TREE_LAUNCH(7, true, false, false);
+    else MJB_TREE_LAUNCH(0, false, false, false);
 #undef MJB_TREE_LAUNCH
     MJB_CUDA(cudaGetLastError());
     return MJB_OK;

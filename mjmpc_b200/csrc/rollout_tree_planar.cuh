@@ -96,6 +96,16 @@ void dense_solve_integrate(const double* lk, double h, double (*M)[NV], double* 
             tcur = tnext;
         }
         for (int i = 0; i < NV; i++) a[i] += tstar * p[i];
+        // a full Newton step that crossed no breakpoint landed on the minimiser of the quadratic it was built from, and
+        // that quadratic still holds there: optimal (what remains of the gradient is rounding)
+        if (fabs(tstar - 1.0) < 1e-9 && tcur == 0.0) {
+            bool same = true;
+            for (int r = 0; r < nrow && same; r++) {
+                const double Dr = r < NV ? rD[r] : Dd[r - NV];
+                if (Dr > 0.0 && ((res[r] < 0.0) != (res[r] + tstar * Jp[r] < 0.0))) same = false;
+            }
+            if (same) break;
+        }
     }
     if (damped) {
         for (int i = 0; i < NV; i++) fc[i] = rD[i] > 0.0 && rS[i] * a[i] - rA[i] < 0.0 ? rS[i] * (-rD[i] * (rS[i] * a[i] - rA[i])) : 0.0;
@@ -122,7 +132,7 @@ TR_HD double inv_sqrt(double x) {
 #endif
 }
 
-template <int NV, bool SERIAL>
+template <int NV, bool SERIAL, bool CONTACTS>
 TR_HD int planar_substep(const double* lk, const int* li, const double* pk, const int* anc, const double* g, const double* gp,
                          int ncand, const int* cti, const double* ctd,
                          double* q, double* v, const double* u /* per dof: gear * clamp(ctrl) */) {
@@ -249,9 +259,9 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
     // ---- contacts (models compiled with allow_contacts="model"): detection on the link frames, three rows per
     // contact -- n + mu t, n - mu t and the pair n +- mu t_out merged into one row of twice the weight (t_out is normal
     // to the plane of motion: both rows have the Jacobian of n) -- and the dense Newton, out of line
-    if (ncand > 0) {
-        double Jd[MJB_TREE_MAX_DENSE][NV], Dd[MJB_TREE_MAX_DENSE], Ad[MJB_TREE_MAX_DENSE];
-        int nd = 0, ncontact = 0;
+    double Jd[CONTACTS ? MJB_TREE_MAX_DENSE : 1][NV], Dd[CONTACTS ? MJB_TREE_MAX_DENSE : 1], Ad[CONTACTS ? MJB_TREE_MAX_DENSE : 1];
+    int nd = 0, ncontact = 0;
+    if (CONTACTS) {
 #pragma unroll 1
         for (int cnd = 0; cnd < ncand; cnd++) {
             const int* CI = cti + cnd * CTI_STRIDE;
@@ -330,20 +340,6 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
                 ncontact++;
             }
         }
-        if (nd > 0) {
-            double Ml[NV][NV], fl[NV];
-#pragma unroll
-            for (int i = 0; i < NV; i++) {
-                fl[i] = f[i];
-#pragma unroll
-                for (int j = 0; j < NV; j++) Ml[i][j] = M[i][j];
-            }
-            dense_solve_integrate<NV>(lk, h, Ml, fl, damped, rD, rS, rA, nd, Jd, Dd, Ad, q, v);
-            int nr = 4 * ncontact;
-#pragma unroll
-            for (int i = 0; i < NV; i++) nr += rows >> i & 1;
-            return nr;
-        }
     }
 
     // Constrained solve + mj_Euler around ONE factorisation in registers.  phase 0: active-set iterations on
@@ -352,17 +348,22 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
     // f_i / M_ii, which is right for most rows and saves the unconstrained solve); phase 2: mj_Euler's solve, implicit in joint
     // damping, with the constraint force on the right-hand side.  No row: phase 2 at once.  A set that keeps changing
     // (it can cycle without a line search) goes to the out-of-line Newton solver with its exact line search.
+    // Dense rows (contacts) join the same iteration: active ones add D J J' to the matrix before it is factored -- the
+    // row comes from local memory, the matrix stays in registers -- first guess: the reference acceleration pushes apart.
     double A[NV][NV], b[NV], fc[NV];
     unsigned act = 0;
-    int phase = rows ? 0 : 2;
+    unsigned long long dact = 0;
+    int phase = (rows || nd) ? 0 : 2;
     bool done = false;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
         fc[i] = 0.0;
         if ((rows >> i & 1) && rS[i] * f[i] < rA[i] * M[i][i]) act |= 1u << i;      // M_ii > 0
     }
+    if (CONTACTS)
+        for (int r = 0; r < nd; r++) if (Ad[r] > 0.0) dact |= 1ull << r;
 #pragma unroll 1
-    for (int it = 0; it < 10 && !done; it++) {
+    for (int it = 0; it < (CONTACTS ? 16 : 10) && !done; it++) {
 #pragma unroll
         for (int i = 0; i < NV; i++) {
             const bool on = phase == 0 && (act >> i & 1);
@@ -370,6 +371,23 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
 #pragma unroll
             for (int j = 0; j < i; j++) A[i][j] = M[i][j];
             A[i][i] = M[i][i] + (phase == 2 ? h * lk[i * LK_STRIDE + LK_DAMP] : 0.0) + (on ? rD[i] : 0.0);
+        }
+        if (CONTACTS && phase == 0) {
+#pragma unroll 1
+            for (int r = 0; r < nd; r++) {
+                if (!(dact >> r & 1)) continue;
+                double jr[NV];
+#pragma unroll
+                for (int i = 0; i < NV; i++) jr[i] = Jd[r][i];
+                const double dr = Dd[r], da = dr * Ad[r];
+#pragma unroll
+                for (int i = 0; i < NV; i++) {
+                    const double di = dr * jr[i];
+                    b[i] += da * jr[i];
+#pragma unroll
+                    for (int j = 0; j <= i; j++) A[i][j] += di * jr[j];
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < NV; j++) {
@@ -405,13 +423,35 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
         unsigned na = 0;
 #pragma unroll
         for (int i = 0; i < NV; i++) if ((rows >> i & 1) && rS[i] * b[i] - rA[i] < 0.0) na |= 1u << i;
-        if (na == act) {
+        unsigned long long nda = 0;
+        if (CONTACTS) {
+#pragma unroll 1
+            for (int r = 0; r < nd; r++) {
+                double sres = -Ad[r];
+#pragma unroll
+                for (int i = 0; i < NV; i++) sres += Jd[r][i] * b[i];
+                if (sres < 0.0) nda |= 1ull << r;
+            }
+        }
+        if (na == act && nda == dact) {
             if (!damped) { done = true; break; }
 #pragma unroll
             for (int i = 0; i < NV; i++) fc[i] = (act >> i & 1) ? rS[i] * (-rD[i] * (rS[i] * b[i] - rA[i])) : 0.0;
+            if (CONTACTS) {
+#pragma unroll 1
+                for (int r = 0; r < nd; r++) {
+                    if (!(dact >> r & 1)) continue;
+                    double sres = -Ad[r];
+#pragma unroll
+                    for (int i = 0; i < NV; i++) sres += Jd[r][i] * b[i];
+#pragma unroll
+                    for (int i = 0; i < NV; i++) fc[i] += Jd[r][i] * (-Dd[r] * sres);
+                }
+            }
             phase = 2;
         } else {
             act = na;
+            dact = nda;
         }
     }
     if (!done) {
@@ -423,9 +463,16 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
 #pragma unroll
             for (int j = 0; j < NV; j++) Ml[i][j] = M[i][j];
         }
+        if (CONTACTS && nd > 0) {
+            dense_solve_integrate<NV>(lk, h, Ml, fl, damped, rD, rS, rA, nd, Jd, Dd, Ad, q, v);
+            int nrc = 4 * ncontact;
+#pragma unroll
+            for (int i = 0; i < NV; i++) nrc += rows >> i & 1;
+            return nrc;
+        }
         return limits_solve_integrate<NV>(NV, lk, li, h, Ml, fl, damped, q, v);
     }
-    int nr = 0;
+    int nr = 4 * ncontact;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
         v[i] += h * b[i];

@@ -18,16 +18,18 @@ from mjmpc_b200.envs.gpu_tree_env import GpuTreeVecEnv
 sizes = [int(x) for x in (sys.argv[sys.argv.index("--sizes") + 1] if "--sizes" in sys.argv else "4096,65536").split(",")]
 H = int(sys.argv[sys.argv.index("--horizon") + 1]) if "--horizon" in sys.argv else 32
 rng = np.random.default_rng(0)
-env = GpuTreeVecEnv.swimmer()
+MODEL = sys.argv[sys.argv.index("--model") + 1] if "--model" in sys.argv else "swimmer"      # swimmer | swimmer-nocontact | cheetah
+env = GpuTreeVecEnv.half_cheetah() if MODEL == "cheetah" else GpuTreeVecEnv.swimmer(contacts=MODEL == "swimmer")
 if "--no-planar" in sys.argv:           # the general 3-D instantiation instead of the planar one
     from mjmpc_b200 import _lib
     _lib.lib().mjb_tree_use_planar(0)
 INST = "general" if "--no-planar" in sys.argv else "planar"
-state = dict(qpos=rng.uniform(-.1, .1, 7), qvel=rng.uniform(-.1, .1, 7))
+nv, nu = env.nv, env.d_action
+state = dict(qpos=rng.uniform(-.1, .1, nv), qvel=rng.uniform(-.1, .1, nv))
 env.set_env_state(state)
 for K in sizes:
-    mean = torch.as_tensor(rng.normal(0, 0.3, (H, 4)), device=env.device)
-    noise = torch.as_tensor(rng.normal(0, 0.5, (K, H, 4)), device=env.device)
+    mean = torch.as_tensor(rng.normal(0, 0.3, (H, nu)), device=env.device)
+    noise = torch.as_tensor(rng.normal(0, 0.5, (K, H, nu)), device=env.device)
     for _ in range(3):
         out = env.rollout_device(K, H, mean, noise)
     torch.cuda.synchronize()
@@ -39,7 +41,7 @@ for K in sizes:
     e1.record()
     torch.cuda.synchronize()
     k_ms = e0.elapsed_time(e1) / reps
-    c = MPPI(d_state=14, d_obs=12, d_action=4, action_lows=env.action_lows, action_highs=env.action_highs, horizon=H,
+    c = MPPI(d_state=env.d_state, d_obs=env.d_obs, d_action=nu, action_lows=env.action_lows, action_highs=env.action_highs, horizon=H,
              init_cov=0.4, base_action="null", num_particles=K, lam=0.1, step_size=1.0, alpha=1, gamma=1.0, n_iters=1,
              set_sim_state_fn=env.set_env_state, rollout_fn=env.rollout_fn, seed=3, filter_coeffs=[0.25, 0.8, 0.0])
     c.enable_cuda_graph(state)
@@ -63,10 +65,11 @@ for K in sizes:
     nz = noise[:ks].cpu().numpy()
     cores = os.cpu_count() or 1
     t0 = time.perf_counter()
-    ref = o.rollout(np.concatenate([state["qpos"], state["qvel"]]), mean.cpu().numpy(), nz, 4, nthreads=min(cores, 64))
+    ref = o.rollout(np.concatenate([state["qpos"], state["qvel"]]), mean.cpu().numpy(), nz, env.frame_skip, env.fwd_dof, env.w_fwd,
+                    env.w_ctrl, nthreads=min(cores, 64))
     cpu_s = time.perf_counter() - t0
     err = float(np.abs(out["costs"][:ks].cpu().numpy() - ref["costs"]).max() / (1 + np.abs(ref["costs"]).max()))
-    print(json.dumps(dict(config="Swimmer-v0 tree rollout + MPPI", instantiation=INST, num_particles=K, horizon=H, frame_skip=4,
+    print(json.dumps(dict(config="%s tree rollout + MPPI" % {"cheetah": "HalfCheetah-v0"}.get(MODEL, "Swimmer-v0"), model=MODEL, instantiation=INST, num_particles=K, horizon=H, frame_skip=env.frame_skip,
                           rollout_kernel_ms=k_ms, particle_steps_per_s=K * H / (k_ms * 1e-3), mpc_step_ms=step_ms,
                           mpc_hz=1e3 / step_ms, e2e_ms=e2e_ms, rel_err_vs_oracle=err,
                           cpu_oracle=dict(particle_steps_per_s=ks * H / cpu_s, cores=min(cores, 64), sample="%d particles x %d steps" % (ks, H)))),
