@@ -130,8 +130,8 @@ int mjb_rollout_lqr(const mjb_lqr_args* a, void* stream);
  * reported by mjb_tree_layout): link_params (nv, LK_STRIDE) doubles, link_ints (nv, LI_STRIDE) ints, globals
  * (TG_STRIDE) doubles, HOST pointers, copied.  Dynamics: hinge / slide joints with any axis, anchor and body
  * orientation, several joints per body, gravity, joint springs / dampers / armature, mj_passive's inertia-box fluid
- * forces (option density / viscosity), soft joint limits (solreflimit / solimplimit), motors with ctrlrange, mj_Euler.
- * No contacts, frictionloss, tendons, free / ball joints (the compiler rejects such models). */
+ * forces (option density / viscosity), soft joint limits (solreflimit / solimplimit), motors with ctrlrange, mj_Euler,
+ * contacts of planar mechanisms (below).  No frictionloss, tendons, free / ball joints (the compiler rejects such models). */
 typedef struct mjb_tree_model mjb_tree_model;
 mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* link_params, const int* link_ints,
                                       const double* globals, const double* planar_params, const int* planar_anc,

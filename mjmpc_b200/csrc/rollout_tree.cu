@@ -14,6 +14,8 @@
 //   constraints              soft joint limits: rows +-e_j with MuJoCo's impedance / reference acceleration; the convex
 //                            problem  min 1/2 (a-a0)'M(a-a0) + sum 1/2 D min(0, J a - aref)^2  is solved exactly:
 //                            Newton on the active set with an exact piecewise-linear line search
+//                            contacts (planar instantiation): MuJoCo's plane-capsule / capsule-capsule detection on the
+//                            link frames, condim-3 pyramidal friction rows, solved with the limit rows
 //   mj_Euler                 implicit in joint damping: (M + h B) qacc = f + J'lambda
 // The model block (tree_model.h) is staged in shared memory once per block: link parameters are indexed with
 // run-time link numbers and every lane reads the same address (broadcast).

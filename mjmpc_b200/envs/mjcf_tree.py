@@ -14,8 +14,12 @@ Subset (anything else raises ``UnsupportedMjcf`` -- an unsupported model is reje
              solreflimit / solimplimit
   geom       sphere, capsule (fromto or size + pos/quat/axisangle), cylinder, box, plane (ignored): mass properties
   actuator   motor: joint, gear (first component), ctrlrange + ctrllimited
-Not in the subset: contacts (a model whose geoms can collide is accepted only with ``allow_contacts="ignore"``, and
-says so in ``TreeModel.ignored``), frictionloss, tendons, equality constraints, free / ball joints, RK4.
+  contacts   opt-in.  The default (``allow_contacts="error"``) refuses a model whose geoms can collide; ``"model"`` keeps
+             world-plane / capsule / sphere pairs as contact candidates (contype / conaffinity test, same-assembly and
+             parent-child filters, condim 3, margin = gap = 0, one solref / solimp per pair, friction = the larger of the
+             two) with ``body_invweight0`` -- simulated by the planar instantiation of the kernel; ``"ignore"`` drops
+             them and says so in ``TreeModel.ignored``
+Not in the subset: frictionloss, tendons, equality constraints, free / ball joints, RK4, boxes / meshes as colliders.
 
 MuJoCo semantics restated here [EXT, MuJoCo 2.0 documentation: "XML reference", "Computation"]:
   * geom mass properties at density 1000 unless given; body frame = first-moment / parallel-axis composition of its

@@ -16,6 +16,9 @@ no derivation with either (the counterpart of ``oracle/efc_ref.py`` for SURVEY Â
     back through the same Jacobians;
   * dof_invweight0 = diag(M(0)^-1); limit rows per ``mj_instantiateLimit`` / ``mj_makeImpedance`` /
     ``mj_referenceConstraint``; the convex problem solved by ENUMERATING active sets and keeping the KKT-consistent one;
+  * contacts (read_model(..., contacts=True)): its own candidate pairs and body_invweight0 (complex-step Jacobians), a TRUE
+    closest-point search between segments (not MuJoCo's sequential clamping: the same points in general position),
+    contact Jacobians by complex step of the material point, pyramidal rows, active-set enumeration over dense rows;
   * mj_Euler with implicit joint damping.
 
 Reference call sites: mjmpc/envs/basic/swimmer.py:7-24 (frame_skip 4, reward, observation),

@@ -24,6 +24,12 @@
  * Passive forces: joint springs / dampers and the inertia-box fluid model of mj_passive (viscous: -3 pi d mu v,
  * -pi d^3 mu w; quadratic drag: -1/2 rho A |v| v per box face, -rho b (c^4 + d^4)/64 |w| w), evaluated in the body's
  * inertial frame.  Soft joint limits as in oracle/mjstep.c: the convex problem is solved to machine precision.
+ * Contacts (tree_model_set_contacts; restated from the published engine source of MuJoCo 2.1 -- mjc_PlaneCapsule,
+ * mjc_CapsuleCapsule / mjraw_SphereSphere, mju_makeFrame, mj_instantiateContact, mj_diagApprox, mj_makeImpedance -- whose
+ * algorithms the 2.0 binary shares): plane against the two end spheres of a capsule (first tangent along the capsule),
+ * capsule against capsule (closest points by sequential clamping, then sphere-sphere; parallel axes: ONE contact at the
+ * clamped projection where MuJoCo makes up to two); condim 3, pyramidal cone: rows n +- mu t1, n +- mu t2 with
+ * diagApprox = (1 + mu^2)(invweight_1 + invweight_2), R = 2 mu^2 (1 - imp)/imp diagApprox for all four (impratio 1).
  */
 #include <math.h>
 #include <pthread.h>
