@@ -262,17 +262,19 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
     double Jd[CONTACTS ? MJB_TREE_MAX_DENSE : 1][NV], Dd[CONTACTS ? MJB_TREE_MAX_DENSE : 1], Ad[CONTACTS ? MJB_TREE_MAX_DENSE : 1];
     int nd = 0, ncontact = 0;
     if (CONTACTS) {
+        double lf[NV][4];
+#pragma unroll
+        for (int j = 0; j < NV; j++) { lf[j][0] = cs[j]; lf[j][1] = sn[j]; lf[j][2] = px[j]; lf[j][3] = py[j]; }
 #pragma unroll 1
         for (int cnd = 0; cnd < ncand; cnd++) {
             const int* CI = cti + cnd * CTI_STRIDE;
             const double* C = ctd + cnd * CT_STRIDE;
             const int l1 = CI[1], l2 = CI[2];
-            double c1 = 1.0, s1 = 0.0, x1 = -Ox, y1 = -Oy, c2 = 1.0, s2 = 0.0, x2 = 0.0, y2 = 0.0;
-#pragma unroll
-            for (int j = 0; j < NV; j++) {
-                if (j == l1) { c1 = cs[j]; s1 = sn[j]; x1 = px[j]; y1 = py[j]; }
-                if (j == l2) { c2 = cs[j]; s2 = sn[j]; x2 = px[j]; y2 = py[j]; }
-            }
+            // link frames by run-time link number: from the local-memory copy (a select chain over the register arrays
+            // cost 56 predicated moves per candidate)
+            double c1 = 1.0, s1 = 0.0, x1 = -Ox, y1 = -Oy;
+            if (l1 >= 0) { c1 = lf[l1][0]; s1 = lf[l1][1]; x1 = lf[l1][2]; y1 = lf[l1][3]; }
+            const double c2 = lf[l2][0], s2 = lf[l2][1], x2 = lf[l2][2], y2 = lf[l2][3];
             const unsigned m1 = l1 < 0 ? 0u : ((SERIAL ? ((1u << l1) - 1u) : (unsigned)anc[l1]) | (1u << l1));
             const unsigned m2 = (SERIAL ? ((1u << l2) - 1u) : (unsigned)anc[l2]) | (1u << l2);
             // segment B in the world (relative to O)
