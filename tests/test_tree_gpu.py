@@ -222,6 +222,36 @@ def test_half_cheetah_rollouts_match_oracle():
     env.close()
 
 
+@pytest.mark.parametrize("name", ["cheetah", "swimmer"])
+def test_contact_fuzz_one_state_per_particle(name):
+    """Violent random states, one per particle (each its own controller row), two env steps: bodies deep in the floor,
+    limbs folded through each other, joints beyond their limits, high speeds -- the active-set iteration (and its
+    fall-back) against the oracle's Newton, row counts included."""
+    env = GpuTreeVecEnv.half_cheetah() if name == "cheetah" else GpuTreeVecEnv.swimmer()
+    oracle = TreeOracle(env.model, T.solref_to_kb)
+    nv, nu, n, H = env.nv, env.d_action, 192, 2
+    rng = np.random.default_rng(123)
+    states = np.zeros((n, 2 * nv))
+    for i in range(n):
+        q, v = rng.uniform(-.4, .4, nv), rng.normal(0, 2.0, nv)
+        if name == "cheetah":
+            q[1], q[2], q[3:] = rng.uniform(-.45, 0.1), rng.uniform(-1.5, 1.5), rng.uniform(-1.2, 1.2, 6)
+        else:
+            q[3:] = rng.choice([-1, 1]) * rng.uniform(1.0, 1.65, 4) * rng.choice([1, 1, 1, -1], 4)
+        states[i] = np.concatenate([q, v])
+    env.set_env_state([dict(qpos=s[:nv], qvel=s[nv:]) for s in states])
+    mean = rng.normal(0, .5, (n, H, nu))
+    out = env.rollout_device(n, H, torch.as_tensor(mean, device=env.device), None, want_states=True, want_nefc=True)
+    st, nefc = out["states"].cpu().numpy(), out["nefc"].cpu().numpy()
+    rows = 0
+    for i in range(n):
+        ref = oracle.rollout(states[i], mean[i], np.zeros((1, H, nu)), env.frame_skip, env.fwd_dof, env.w_fwd, env.w_ctrl, nthreads=1)
+        assert _rel(st[i], ref["states"][0]) < TOL and int(nefc[i]) == ref["nefc"]
+        rows += ref["nefc"]
+    assert rows > (4 if name == "cheetah" else 1.5) * n * H * env.frame_skip       # rows per substep on average
+    env.close()
+
+
 def test_mppi_makes_the_cheetah_run():
     from mjmpc_b200.control import MPPI
     from mjmpc_b200.envs.gpu_tree_env import GpuHalfCheetahEnv
