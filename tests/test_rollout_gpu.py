@@ -135,6 +135,7 @@ def test_rollout_per_worker_models(compiled_model):
     env.randomize_dynamics(params, base_seed=5)
     env.set_env_state(st)
     noise = reference_noise(K, H, 7, 8)
+    noise[K // W] = noise[0]            # the first particle of worker 1 gets the controls of the first particle of worker 0
     mean = np.zeros((H, 7))
     out = env.rollout_device(K, H, torch.from_numpy(mean).cuda(), torch.from_numpy(noise).cuda(), want_traj=True)
     oms = [mjstep.OracleModel(m.tree) for m in env._worker_models]
@@ -142,8 +143,9 @@ def test_rollout_per_worker_models(compiled_model):
     got = out["qv"].cpu().numpy()
     scale = np.abs(ref["qv"]).max(axis=(0, 1))
     assert (np.abs(got - ref["qv"]).max(axis=(0, 1)) / scale).max() < TRAJ_RTOL
-    # and the models really differ between workers
-    assert np.abs(ref["qv"][0] - ref["qv"][K // W]).max() > 1e-6 or True
+    # and the models really differ between workers: same state, same controls, different trajectories
+    assert np.abs(ref["qv"][0] - ref["qv"][K // W]).max() > 1e-6
+    assert np.abs(got[0] - got[K // W]).max() > 1e-6
     env.close()
 
 
