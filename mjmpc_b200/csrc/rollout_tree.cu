@@ -614,12 +614,6 @@ extern "C" mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* l
         mjb::set_error(MJB_EINVAL, "mjb_tree_model_create: the three planar blocks come together or not at all");
         return nullptr;
     }
-    if (n_contacts < 0 || n_contacts > MJB_TREE_MAX_CAND || (n_contacts > 0 && (!planar_params || !contact_ints || !contact_params)) ||
-        (n_contacts > 0 && nv != 7 && nv != 9)) {
-        mjb::set_error(MJB_ENOTIMPL, "mjb_tree_model_create: contacts run in the planar instantiation only (planar mechanism of 7 or "
-                       "9 dofs, at most %d candidate pairs)", MJB_TREE_MAX_CAND);
-        return nullptr;
-    }
     int serial = 1;
     for (int i = 0; i < nv; i++) {
         const int p = link_ints[i * LI_STRIDE + LI_PARENT];
@@ -627,6 +621,12 @@ extern "C" mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* l
         if (p != i - 1) serial = 0;
         const int act = link_ints[i * LI_STRIDE + LI_ACT];
         if (act >= nu) { mjb::set_error(MJB_EINVAL, "mjb_tree_model_create: link %d names actuator %d of %d", i, act, nu); return nullptr; }
+    }
+    if (n_contacts < 0 || n_contacts > MJB_TREE_MAX_CAND || (n_contacts > 0 && (!planar_params || !contact_ints || !contact_params)) ||
+        (n_contacts > 0 && !((nv == 7 && serial) || nv == 9))) {
+        mjb::set_error(MJB_ENOTIMPL, "mjb_tree_model_create: contacts run in the planar instantiation only, for 7 dofs in series "
+                       "and for 9-dof trees (the shapes of the reference's models), at most %d candidate pairs", MJB_TREE_MAX_CAND);
+        return nullptr;
     }
     if (cudaSetDevice(device) != cudaSuccess) { mjb::set_error(MJB_ECUDA, "mjb_tree_model_create: cudaSetDevice(%d) failed", device); return nullptr; }
     mjb_tree_model* m = new mjb_tree_model{device, nv, nu, serial, planar_params != nullptr, n_instances,
@@ -690,6 +690,7 @@ extern "C" int mjb_rollout_tree(const mjb_tree_model* m, const mjb_tree_rollout_
     MJB_REQUIRE(a->particles_per_model >= 1 && a->K % a->particles_per_model == 0 && a->K / a->particles_per_model <= m->n_inst,
                 "Number of particles must be divisible by number of cpus");      /* (subproc_vec_env.py:140-141) */
     const int blocks = (a->K / a->particles_per_model) * ((a->particles_per_model + 63) / 64);
+    MJB_CUDA(cudaSetDevice(m->device));
     cudaStream_t st = (cudaStream_t)stream;
     using namespace mjb::tree;
     MJB_REQUIRE(m->ncand == 0 || g_use_planar, "mjb_rollout_tree: a model with contacts runs in the planar instantiation only");
@@ -699,9 +700,8 @@ extern "C" int mjb_rollout_tree(const mjb_tree_model* m, const mjb_tree_rollout_
                                                                          m->d_ctd, m->nv, m->nu, *a)
     if (m->ncand > 0) {
         // contacts: the two shapes the reference's models have (swimmer: 7 dofs in series; half-cheetah: 9, two legs)
-        if (m->nv == 7 && m->serial) MJB_TREE_LAUNCH(7, true, true, true);
-        else if (m->nv == 9) MJB_TREE_LAUNCH(9, false, true, true);
-        else return mjb::set_error(MJB_ENOTIMPL, "mjb_rollout_tree: contacts are instantiated for 7 dofs in series and for 9-dof trees");
+        if (m->nv == 7) MJB_TREE_LAUNCH(7, true, true, true);         // (mjb_tree_model_create admits nothing else)
+        else MJB_TREE_LAUNCH(9, false, true, true);
     }
     else if (planar && m->nv == 7 && m->serial) MJB_TREE_LAUNCH(7, true, true, false);
     else if (planar && m->nv == 7) MJB_TREE_LAUNCH(7, false, true, false);
