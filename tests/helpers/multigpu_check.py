@@ -84,6 +84,27 @@ def main():
         except AssertionError as e:
             ok = False
             print("multigpu %-6s FAIL on rank %d: %s" % (name, rank, str(e)[:300]), flush=True)
+    # the MJCF-tree backend under the same sharding: MPPI on Swimmer-v0, contacts on
+    from mjmpc_b200.envs.gpu_tree_env import GpuTreeVecEnv
+    rng = np.random.default_rng(3)
+    sw_state = dict(qpos=rng.uniform(-.1, .1, 7), qvel=rng.uniform(-.1, .1, 7))
+    res = []
+    for sh in (shard, ShardContext()):
+        env = GpuTreeVecEnv.swimmer(device=local)
+        c = MPPI(d_state=14, d_obs=12, d_action=4, action_lows=env.action_lows, action_highs=env.action_highs, horizon=H,
+                 num_particles=K, gamma=0.98, n_iters=1, filter_coeffs=[0.25, 0.8, 0.0], seed=5, device=local, init_cov=0.5,
+                 base_action='null', lam=0.1, step_size=0.9, alpha=0, shard=sh)
+        c.set_sim_state_fn, c.rollout_fn = env.set_env_state, env.rollout_fn
+        res.append((np.stack([c.optimize(sw_state)[0] for _ in range(3)]), c.mean_action))
+        env.close()
+    try:
+        np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-9, atol=1e-12)
+        if rank == 0:
+            print("multigpu %-6s ok (N=%d)" % ("tree", world), flush=True)
+    except AssertionError as e:
+        ok = False
+        print("multigpu %-6s FAIL on rank %d: %s" % ("tree", rank, str(e)[:300]), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

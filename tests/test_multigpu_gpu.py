@@ -19,5 +19,5 @@ def test_sharded_controllers_match_unsharded():
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "helpers", "multigpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    for name in ("mppi", "dmd", "cem", "rs", "pfmpc"):
+    for name in ("mppi", "dmd", "cem", "rs", "pfmpc", "tree"):
         assert "multigpu %-6s ok" % name in r.stdout, r.stdout[-2000:]

@@ -96,7 +96,7 @@ def test_two_rank_gloo_sharded_controllers_match_unsharded_on_the_host_emulation
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "helpers", "multigpu_check.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    for name in ("mppi", "dmd", "cem", "rs", "pfmpc"):
+    for name in ("mppi", "dmd", "cem", "rs", "pfmpc", "tree"):
         assert "multigpu %-6s ok" % name in r.stdout, r.stdout[-2000:]
 
 
