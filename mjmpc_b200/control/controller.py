@@ -114,7 +114,7 @@ class Controller(ABC):
             action = self._fused_step(state, hotstart)       # the whole step in one native call, when it can be
             if action is not None:
                 self.num_steps += 1
-                return action.cpu().numpy().copy(), 0.0
+                return self._to_host(action), 0.0
         for _ in range(self.n_iters):
             trajectory = self.generate_rollouts(copy.deepcopy(state))
             self._update_distribution(trajectory)
@@ -255,6 +255,20 @@ class Controller(ABC):
             self._set_sim_state_fn(copy.deepcopy(state))
         elif not (hasattr(backend, "set_env_state_fast") and backend.set_env_state_fast(state)):
             self._set_sim_state_fn(state)
+
+    def _to_host(self, action):
+        """(d,) device action -> numpy through a pinned staging buffer (torch's .cpu() allocates and copies through
+        pageable memory on every call; this is the read-back of every eager sharded step)."""
+        buf = self.__dict__.get("_eager_action_host")
+        if buf is None or buf.shape != action.shape:
+            try:
+                buf = torch.zeros(action.shape, dtype=action.dtype).pin_memory()
+            except RuntimeError:                      # no pinned memory (host emulation)
+                return action.cpu().numpy().copy()
+            self.__dict__["_eager_action_host"] = buf
+        buf.copy_(action, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return buf.numpy().copy()
 
     def _replay(self, state):
         if state is not None:
