@@ -63,7 +63,6 @@ class TreeOracle:
             raise ValueError("model too large for the oracle")
         cs = getattr(model, "contacts", [])
         if cs:
-            z3 = np.zeros(3)
             kb = np.array([solref_to_kb(c["solref"], c["solimp"], model.timestep) for c in cs])
             arr = [i([1 if c["kind"] == "plane" else 0 for c in cs]), i([c["body1"] for c in cs]), i([c["body2"] for c in cs]),
                    f([c["a0"] for c in cs]), f([c["a1"] for c in cs]), f([c["ra"] for c in cs]), f([c["b0"] for c in cs]),

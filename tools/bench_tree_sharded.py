@@ -65,7 +65,6 @@ for name, make in (("HalfCheetah-v0", GpuTreeVecEnv.half_cheetah), ("Swimmer-v0"
         c1 = controller(env1, ShardContext())
         ref = c1.optimize(state)[0]
         line["first_action_max_abs_diff_vs_unsharded"] = float(np.abs(first - ref).max())
-        line["ms_per_step_one_gpu_eager"] = timed_single = None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for _ in range(2):
             c1.step_device(state)
