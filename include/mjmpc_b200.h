@@ -142,7 +142,7 @@ mjb_tree_model* mjb_tree_model_create(int nv, int nu, const double* link_params,
                                        * randomize_dynamics (subproc_vec_env.py:304-312, gym_env_wrapper.py:367-416): same topology,
                                        * different masses / inertias / dampings */
 void mjb_tree_model_destroy(mjb_tree_model* m);
-void mjb_tree_layout(int* out59);   /* the 59 layout constants of csrc/tree_model.h + rollout_tree_planar.cuh, in order */
+void mjb_tree_layout(int* out60);   /* the 60 layout constants of csrc/tree_model.h + rollout_tree_planar.cuh, in order */
 /* PLANAR MECHANISMS (all hinge axes parallel, all slides perpendicular to them -- swimmer.xml and half_cheetah.xml are):
  * with the three planar blocks of mjcf_tree.pack_planar -- planar_params (nv, PK_STRIDE), planar_anc (nv) ancestor bit
  * masks, planar_gravity (2); NULL otherwise -- rollouts of 7- and 9-dof models run the planar instantiation (3-vectors

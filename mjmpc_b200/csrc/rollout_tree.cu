@@ -676,7 +676,8 @@ extern "C" void mjb_tree_layout(int* out) {
                      LK_HI, LK_INVW, LK_SOLK, LK_SOLB, LK_SOLIMP, LK_GEAR, LK_CLO, LK_CHI, LK_STRIDE, LI_PARENT, LI_TYPE,
                      LI_LIMITED, LI_ACT, LI_BODY, LI_STRIDE, TG_DT, TG_GRAV, TG_RHO, TG_VISC, TG_STRIDE, MJB_TREE_MAX_LINKS,
                      PK_OFF, PK_DIR, PK_MASS, PK_COM, PK_INN, PK_CLIN, PK_KV1, PK_KV2, PK_E, PK_AK, PK_STRIDE,
-                     CT_A, CT_HA, CT_RA, CT_B, CT_HB, CT_RB, CT_MU, CT_K, CT_BB, CT_SOLIMP, CT_INVW, CT_STRIDE, CTI_STRIDE, MJB_TREE_MAX_CAND};
+                     CT_A, CT_HA, CT_RA, CT_B, CT_HB, CT_RB, CT_MU, CT_K, CT_BB, CT_SOLIMP, CT_INVW, CT_BOUND, CT_STRIDE, CTI_STRIDE,
+                     MJB_TREE_MAX_CAND};
     for (unsigned i = 0; i < sizeof(v) / sizeof(v[0]); i++) out[i] = v[i];
 }
 

@@ -24,7 +24,8 @@ enum { PK_OFF = 0, PK_DIR = 2, PK_MASS = 4, PK_COM = 5, PK_INN = 7, PK_CLIN = 8,
 // a point (2, absolute) and the normal (2) -- segment B centre, half axis, radius, then mu, K, B, solimp (5),
 // body_invweight0 sum.
 enum { CT_A = 0, CT_HA = 2, CT_RA = 4, CT_B = 5, CT_HB = 7, CT_RB = 9, CT_MU = 10, CT_K = 11, CT_BB = 12, CT_SOLIMP = 13, CT_INVW = 18,
-       CT_STRIDE = 19, CTI_STRIDE = 3, MJB_TREE_MAX_CAND = 16, MJB_TREE_MAX_DENSE = 3 * 2 * MJB_TREE_MAX_CAND };
+       CT_BOUND = 19,       // |half axis A| + |half axis B| + radius A + radius B: centres farther apart than this cannot touch
+       CT_STRIDE = 20, CTI_STRIDE = 3, MJB_TREE_MAX_CAND = 16, MJB_TREE_MAX_DENSE = 3 * 2 * MJB_TREE_MAX_CAND };
 
 namespace mjb {
 namespace tree {
@@ -299,6 +300,7 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
                 const double ax = x1 + c1 * C[CT_A] - s1 * C[CT_A + 1], ay = y1 + s1 * C[CT_A] + c1 * C[CT_A + 1];
                 const double hax = c1 * C[CT_HA] - s1 * C[CT_HA + 1], hay = s1 * C[CT_HA] + c1 * C[CT_HA + 1];
                 const double dfx = ax - bx, dfy = ay - by;
+                if (dfx * dfx + dfy * dfy >= C[CT_BOUND] * C[CT_BOUND]) continue;      // bounding circles apart: no contact
                 const double ma = hax * hax + hay * hay, mb = -(hax * hbx + hay * hby), mc = hbx * hbx + hby * hby;
                 const double uu = -(hax * dfx + hay * dfy), ww = hbx * dfx + hby * dfy;
                 const double det = ma * mc - mb * mb;

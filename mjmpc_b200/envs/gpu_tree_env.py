@@ -22,7 +22,7 @@ class DeviceTreeModel:
             models = [models]
         model = models[0]
         L = _lib.lib()
-        layout = (C.c_int * 59)()
+        layout = (C.c_int * 60)()
         L.mjb_tree_layout(layout)
         mine = [mjcf_tree.LK_RFIX, mjcf_tree.LK_OFF, mjcf_tree.LK_AXIS, mjcf_tree.LK_MASS, mjcf_tree.LK_COM, mjcf_tree.LK_IC,
                 mjcf_tree.LK_RIN, mjcf_tree.LK_BOX, mjcf_tree.LK_ARM, mjcf_tree.LK_DAMP, mjcf_tree.LK_STIFF, mjcf_tree.LK_SREF,
@@ -33,7 +33,8 @@ class DeviceTreeModel:
                 mjcf_tree.PK_OFF, mjcf_tree.PK_DIR, mjcf_tree.PK_MASS, mjcf_tree.PK_COM, mjcf_tree.PK_INN, mjcf_tree.PK_CLIN,
                 mjcf_tree.PK_KV1, mjcf_tree.PK_KV2, mjcf_tree.PK_E, mjcf_tree.PK_AK, mjcf_tree.PK_STRIDE,
                 mjcf_tree.CT_A, mjcf_tree.CT_HA, mjcf_tree.CT_RA, mjcf_tree.CT_B, mjcf_tree.CT_HB, mjcf_tree.CT_RB, mjcf_tree.CT_MU,
-                mjcf_tree.CT_K, mjcf_tree.CT_BB, mjcf_tree.CT_SOLIMP, mjcf_tree.CT_INVW, mjcf_tree.CT_STRIDE, mjcf_tree.CTI_STRIDE,
+                mjcf_tree.CT_K, mjcf_tree.CT_BB, mjcf_tree.CT_SOLIMP, mjcf_tree.CT_INVW, mjcf_tree.CT_BOUND, mjcf_tree.CT_STRIDE,
+                mjcf_tree.CTI_STRIDE,
                 mjcf_tree.MAX_CAND]
         if list(layout) != mine:
             raise _lib.MjbError("parameter layout of mjcf_tree.py and csrc/tree_model.h differ")

@@ -799,8 +799,8 @@ def pack_planar(model: TreeModel, tol: float = 1e-12):
 
 
 # contact candidates of a planar mechanism (csrc/rollout_tree_planar.cuh): per candidate, doubles / ints
-CT_A, CT_HA, CT_RA, CT_B, CT_HB, CT_RB, CT_MU, CT_K, CT_BB, CT_SOLIMP, CT_INVW, CT_STRIDE, CTI_STRIDE, MAX_CAND = \
-    0, 2, 4, 5, 7, 9, 10, 11, 12, 13, 18, 19, 3, 16
+CT_A, CT_HA, CT_RA, CT_B, CT_HB, CT_RB, CT_MU, CT_K, CT_BB, CT_SOLIMP, CT_INVW, CT_BOUND, CT_STRIDE, CTI_STRIDE, MAX_CAND = \
+    0, 2, 4, 5, 7, 9, 10, 11, 12, 13, 18, 19, 20, 3, 16
 
 
 def pack_planar_contacts(model: TreeModel, tol: float = 1e-9):
@@ -840,6 +840,8 @@ def pack_planar_contacts(model: TreeModel, tol: float = 1e-9):
             heights += [n @ v0, n @ v1]
             I[c] = (0, l1, l2)
             D[c, CT_A:CT_A + 2], D[c, CT_HA:CT_HA + 2], D[c, CT_RA] = plane(0.5 * (v0 + v1) - anchor[l1]), plane(0.5 * (v1 - v0)), ct["ra"]
+            # centres farther apart than this cannot touch (a hair of slack for the rounding of the kernel's own centres)
+            D[c, CT_BOUND] = (np.linalg.norm(D[c, CT_HA:CT_HA + 2]) + np.linalg.norm(D[c, CT_HB:CT_HB + 2]) + ct["ra"] + ct["rb"]) * (1 + 1e-9)
         K, B = solref_to_kb(ct["solref"], ct["solimp"], model.timestep)
         D[c, CT_MU], D[c, CT_K], D[c, CT_BB], D[c, CT_INVW] = ct["mu"], K, B, ct["invweight"]
         D[c, CT_SOLIMP:CT_SOLIMP + 5] = ct["solimp"]

@@ -276,13 +276,13 @@ def test_kernel_layout_matches_the_python_packer():
         L = _lib.lib()
     except _lib.MjbError:
         pytest.skip("extension not built")
-    out = (C.c_int * 59)()
+    out = (C.c_int * 60)()
     L.mjb_tree_layout(out)
     assert list(out)[:4] == [T.LK_RFIX, T.LK_OFF, T.LK_AXIS, T.LK_MASS]
     assert out[21] == T.LK_STRIDE and out[27] == T.LI_STRIDE and out[32] == T.G_STRIDE and out[33] == T.MAX_LINKS
     assert list(out)[34:45] == [T.PK_OFF, T.PK_DIR, T.PK_MASS, T.PK_COM, T.PK_INN, T.PK_CLIN, T.PK_KV1, T.PK_KV2, T.PK_E, T.PK_AK, T.PK_STRIDE]
     assert list(out)[45:] == [T.CT_A, T.CT_HA, T.CT_RA, T.CT_B, T.CT_HB, T.CT_RB, T.CT_MU, T.CT_K, T.CT_BB, T.CT_SOLIMP, T.CT_INVW,
-                              T.CT_STRIDE, T.CTI_STRIDE, T.MAX_CAND]
+                              T.CT_BOUND, T.CT_STRIDE, T.CTI_STRIDE, T.MAX_CAND]
 
 
 def test_pack_links_shapes_and_topology():
