@@ -286,6 +286,8 @@ TR_HD int planar_substep(const double* lk, const int* li, const double* pk, cons
             if (CI[0] == 1) {
                 const double nx = C[CT_HA], ny = C[CT_HA + 1];
                 const bool sphere = C[CT_HB] == 0.0 && C[CT_HB + 1] == 0.0;
+                // the whole capsule above the plane: neither end sphere can touch
+                if ((bx + Ox - C[CT_A]) * nx + (by + Oy - C[CT_A + 1]) * ny - fabs(hbx * nx + hby * ny) - C[CT_RB] >= 0.0) continue;
                 for (int e = 0; e < (sphere ? 1 : 2); e++) {
                     const double sg = sphere ? 0.0 : (e ? -1.0 : 1.0);
                     const double ex = bx + sg * hbx, ey = by + sg * hby;
