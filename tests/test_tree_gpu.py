@@ -273,6 +273,28 @@ def test_mppi_makes_the_cheetah_run():
     plant.close(); sim.close()
 
 
+@pytest.mark.parametrize("n_links", [3, 8, 10])
+def test_other_dof_counts_run_the_general_instantiation(n_links):
+    """Swimmers of 3, 8 and 10 links (5, 10, 12 dofs: no planar instantiation for these sizes; 12 = the kernel's limit):
+    the run-time-size general instantiation against the oracle."""
+    radii = tuple(0.07 - 0.004 * i for i in range(n_links))
+    model = T.compile_mjcf_string(T.swimmer_mjcf(radii=radii), allow_contacts="ignore")
+    assert model.nv == n_links + 2 and model.nu == n_links - 1
+    env = GpuTreeVecEnv(model, frame_skip=4, fwd_dof=0, w_fwd=1.0, w_ctrl=1e-4, obs_qpos_start=2)
+    oracle = TreeOracle(model, T.solref_to_kb)
+    rng = np.random.default_rng(n_links)
+    K, H = 70, 5
+    state = np.concatenate([rng.uniform(-.3, .3, model.nv), rng.normal(0, 1.0, model.nv)])
+    state[3] = 1.55                                          # one joint beyond its limit from the start
+    nefc, nefc_ref, _ = _compare(env, oracle, state, rng.normal(0, 0.5, (H, model.nu)), rng.normal(0, 0.8, (K, H, model.nu)))
+    assert nefc == nefc_ref and nefc > 0
+    env.close()
+    if n_links == 10:
+        too_big = T.compile_mjcf_string(T.swimmer_mjcf(radii=radii + (0.03,)), allow_contacts="ignore")
+        with pytest.raises(T.UnsupportedMjcf, match="dofs"):
+            GpuTreeVecEnv(too_big, frame_skip=4)
+
+
 def test_non_planar_models_take_the_general_instantiation():
     model = T.compile_mjcf(os.path.join(FIX, "tree3d.xml"))
     assert T.pack_planar(model) is None
