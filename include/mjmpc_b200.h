@@ -152,7 +152,9 @@ void mjb_tree_layout(int* out60);   /* the 60 layout constants of csrc/tree_mode
  * (n, 3): kind, link 1 (-1 = world), link 2; contact_params (n, CT_STRIDE) -- world plane against the end spheres of a
  * capsule (half_cheetah.xml's floor) and capsule against capsule (swimmer.xml's non-adjacent links): MuJoCo's
  * mjc_PlaneCapsule / mjc_CapsuleCapsule detection, condim-3 pyramidal friction rows (n +- mu t), R = 2 mu^2 (1 - imp) / imp
- * (1 + mu^2)(invweight_1 + invweight_2), solved with the limit rows by Newton with an exact line search. */
+ * (1 + mu^2)(invweight_1 + invweight_2), solved with the limit rows: active-set iteration around one factorisation,
+ * Newton with an exact line search as the fall-back.  Instantiated for the two shapes of the reference's models (7 dofs
+ * in series, 9-dof trees); mjb_tree_model_create refuses contacts on anything else (MJB_ENOTIMPL). */
 int mjb_tree_use_planar(int on);
 typedef struct {
     int K, H, frame_skip, particles_per_ctrl;
@@ -166,7 +168,7 @@ typedef struct {
     double* actions; long long act_sk, act_st, act_sj;               /* or NULL */
     double* states_out;             /* (K, H, 2 nv) row-major, state AFTER each env step, or NULL */
     double* next_obs;               /* (K, H, 2 nv - obs_qpos_start) row-major, or NULL */
-    int* nefc;                      /* (K,) limit rows summed over the rollout's substeps, or NULL */
+    int* nefc;                      /* (K,) constraint rows (limits + 4 per contact) summed over the rollout's substeps, or NULL */
 } mjb_tree_rollout_args;
 int mjb_rollout_tree(const mjb_tree_model* m, const mjb_tree_rollout_args* a, void* stream);
 
