@@ -145,7 +145,7 @@ void mjb_tree_model_destroy(mjb_tree_model* m);
 void mjb_tree_layout(int* out60);   /* the 60 layout constants of csrc/tree_model.h + rollout_tree_planar.cuh, in order */
 /* PLANAR MECHANISMS (all hinge axes parallel, all slides perpendicular to them -- swimmer.xml and half_cheetah.xml are):
  * with the three planar blocks of mjcf_tree.pack_planar -- planar_params (nv, PK_STRIDE), planar_anc (nv) ancestor bit
- * masks, planar_gravity (2); NULL otherwise -- rollouts of 7- and 9-dof models run the planar instantiation (3-vectors
+ * masks, planar_gravity (2); NULL otherwise -- rollouts of models of 3 to 9 dofs run the planar instantiation (3-vectors
  * in place of spatial 6-vectors, everything in registers).  Same results to rounding; mjb_tree_use_planar(0) forces
  * the general instantiation (tests compare the two), a negative argument only queries; returns the previous value.
  * CONTACTS (planar mechanisms only): n_contacts candidate pairs from mjcf_tree.pack_planar_contacts -- contact_ints

@@ -707,6 +707,12 @@ extern "C" int mjb_rollout_tree(const mjb_tree_model* m, const mjb_tree_rollout_
     else if (planar && m->nv == 7 && m->serial) MJB_TREE_LAUNCH(7, true, true, false);
     else if (planar && m->nv == 7) MJB_TREE_LAUNCH(7, false, true, false);
     else if (planar && m->nv == 9) MJB_TREE_LAUNCH(9, false, true, false);
+    // other planar mechanisms of up to 8 dofs (n-link swimmers, hoppers, walkers without contacts): run-time parents
+    else if (planar && m->nv == 3) MJB_TREE_LAUNCH(3, false, true, false);
+    else if (planar && m->nv == 4) MJB_TREE_LAUNCH(4, false, true, false);
+    else if (planar && m->nv == 5) MJB_TREE_LAUNCH(5, false, true, false);
+    else if (planar && m->nv == 6) MJB_TREE_LAUNCH(6, false, true, false);
+    else if (planar && m->nv == 8) MJB_TREE_LAUNCH(8, false, true, false);
     else if (m->nv == 7 && m->serial) MJB_TREE_LAUNCH(7, true, false, false);
     else MJB_TREE_LAUNCH(0, false, false, false);
 #undef MJB_TREE_LAUNCH

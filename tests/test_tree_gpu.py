@@ -275,8 +275,9 @@ def test_mppi_makes_the_cheetah_run():
 
 @pytest.mark.parametrize("n_links", [3, 8, 10])
 def test_other_dof_counts_run_the_general_instantiation(n_links):
-    """Swimmers of 3, 8 and 10 links (5, 10, 12 dofs: no planar instantiation for these sizes; 12 = the kernel's limit):
-    the run-time-size general instantiation against the oracle."""
+    """Swimmers of 3, 8 and 10 links (5, 10, 12 dofs; 12 = the kernel's limit): the planar instantiation of a size other
+    than the reference models' (5) and the run-time-size general instantiation (10, 12; also 5 with the planar switch
+    off) against the oracle."""
     radii = tuple(0.07 - 0.004 * i for i in range(n_links))
     model = T.compile_mjcf_string(T.swimmer_mjcf(radii=radii), allow_contacts="ignore")
     assert model.nv == n_links + 2 and model.nu == n_links - 1
@@ -286,8 +287,14 @@ def test_other_dof_counts_run_the_general_instantiation(n_links):
     K, H = 70, 5
     state = np.concatenate([rng.uniform(-.3, .3, model.nv), rng.normal(0, 1.0, model.nv)])
     state[3] = 1.55                                          # one joint beyond its limit from the start
-    nefc, nefc_ref, _ = _compare(env, oracle, state, rng.normal(0, 0.5, (H, model.nu)), rng.normal(0, 0.8, (K, H, model.nu)))
+    mean, noise = rng.normal(0, 0.5, (H, model.nu)), rng.normal(0, 0.8, (K, H, model.nu))
+    nefc, nefc_ref, _ = _compare(env, oracle, state, mean, noise)
     assert nefc == nefc_ref and nefc > 0
+    old = _planar_switch(0)
+    try:
+        _compare(env, oracle, state, mean, noise)
+    finally:
+        _planar_switch(old)
     env.close()
     if n_links == 10:
         too_big = T.compile_mjcf_string(T.swimmer_mjcf(radii=radii + (0.03,)), allow_contacts="ignore")
