@@ -4,10 +4,12 @@
 """
 from __future__ import annotations
 
+import concurrent.futures
 import glob
 import os
 import subprocess
 import sys
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -39,12 +41,24 @@ def build(force: bool = False, verbose: bool = False, out: str = None, defines=(
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     target = out or LIB
-    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + sources()
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stderr)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+    # one nvcc per translation unit, in parallel (they are independent: no relocatable device code), then one link
+    with tempfile.TemporaryDirectory(prefix="mjb_build_") as tmp:
+        def compile_one(src):
+            obj = os.path.join(tmp, os.path.basename(src)[:-3] + ".o")
+            r = subprocess.run([nvcc] + flags + ["-c", "-o", obj, src], capture_output=True, text=True)
+            return src, obj, r
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            results = list(ex.map(compile_one, sources()))
+        for src, _, r in results:
+            if verbose:
+                sys.stderr.write(r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed on %s:\n%s" % (os.path.basename(src), r.stderr))
+        r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", target] + [o for _, o, _ in results],
+                           capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stderr)
     return target
 
 
