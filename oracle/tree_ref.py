@@ -83,8 +83,8 @@ def qmat(q):
 
 
 # ------------------------------------------------------------------------------------------------ model
-def read_model(xml_path: str, contacts: bool = False) -> dict:
-    root = ET.parse(xml_path).getroot()
+def read_model(xml_path: str, contacts: bool = False, text: str = None) -> dict:
+    root = ET.fromstring(text) if text is not None else ET.parse(xml_path).getroot()
     comp = root.find("compiler").attrib if root.find("compiler") is not None else {}
     deg = comp.get("angle", "degree") != "radian"
     opt = root.find("option").attrib if root.find("option") is not None else {}

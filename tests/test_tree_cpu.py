@@ -180,6 +180,31 @@ def test_solimp_is_clamped_like_mujoco_and_both_restatements_agree(tmp_path):
     assert hit >= 8
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_trees_both_restatements_agree(seed):
+    """Random 3-D trees (tests/helpers/random_tree.py: topology, axes, anchors, orientations, springs, dampers, limits with
+    random solref / solimp, motors, fluid or not): the compiler + C oracle against the independent restatement."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "helpers"))
+    from random_tree import random_tree_xml
+    from oracle import tree_ref
+    xml = random_tree_xml(seed)
+    m = T.compile_mjcf_string(xml)
+    o, rm = TreeOracle(m, T.solref_to_kb), tree_ref.read_model(None, text=xml)
+    np.testing.assert_allclose(m.dof_invweight0, rm["invweight0"], rtol=1e-9)
+    rng = np.random.default_rng(100 + seed)
+    rows = 0
+    for _ in range(4):
+        q, v, u = rng.uniform(-1, 1, m.nv), rng.normal(0, 2, m.nv), rng.normal(0, 1, m.nu)
+        a = o.substep(q, v, u)
+        q2, v2, info = tree_ref.step(rm, q, v, u)
+        assert a["nefc"] == info["nefc"]
+        rows += a["nefc"]
+        for k in ("M", "bias", "passive", "actuation", "constraint", "qacc"):
+            assert _rel(a[k], info[k]) < 1e-10, k
+        assert _rel(a["q"], q2) < 1e-11 and _rel(a["v"], v2) < 1e-10
+
+
 def test_welded_body_in_a_fluid_is_rejected():
     xml = open(os.path.join(FIX, "tree3d_weld.xml")).read().replace('density="0" viscosity="0"', 'density="10" viscosity="0"')
     with pytest.raises(T.UnsupportedMjcf, match="welded"):

@@ -302,6 +302,24 @@ def test_other_dof_counts_run_the_general_instantiation(n_links):
             GpuTreeVecEnv(too_big, frame_skip=4)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_trees_match_oracle(seed):
+    """Random 3-D trees (tests/helpers/random_tree.py) through the compiler and the general instantiation: rollouts vs the
+    oracle; limits are hit on the way (nefc compared)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers"))
+    from random_tree import random_tree_xml
+    model = T.compile_mjcf_string(random_tree_xml(seed))
+    env = GpuTreeVecEnv(model, frame_skip=2, fwd_dof=0, w_fwd=1.0, w_ctrl=0.01, obs_qpos_start=0)
+    oracle = TreeOracle(model, T.solref_to_kb)
+    rng = np.random.default_rng(200 + seed)
+    K, H = 48, 6
+    state = np.concatenate([rng.uniform(-.6, .6, model.nv), rng.normal(0, 1.0, model.nv)])
+    nefc, nefc_ref, _ = _compare(env, oracle, state, rng.normal(0, 0.5, (H, model.nu)), rng.normal(0, 1.0, (K, H, model.nu)))
+    assert nefc == nefc_ref
+    env.close()
+
+
 def test_non_planar_models_take_the_general_instantiation():
     model = T.compile_mjcf(os.path.join(FIX, "tree3d.xml"))
     assert T.pack_planar(model) is None
