@@ -4,21 +4,28 @@ dampers, armature, limits with random solref / solimp, motors, with or without a
 import numpy as np
 
 
-def random_tree_xml(seed: int) -> str:
+def random_tree_xml(seed: int, planar: bool = False) -> str:
+    """planar: every hinge axis along one random direction n, every slide perpendicular to it, body frames turned about n
+    only -- a planar mechanism in a tilted plane, with bodies, anchors and centres of mass OFF the plane and arbitrary
+    inertia tensors (the planar reduction must be exact for all of that); at most 9 dofs."""
     rng = np.random.default_rng(seed)
-    f = lambda v: " ".join("%.6g" % x for x in np.atleast_1d(v))
-    nbody = int(rng.integers(2, 7))
+    n = rng.normal(0, 1, 3)
+    n /= np.linalg.norm(n)
+    f = lambda v: " ".join(("%.17g" if planar else "%.6g") % x for x in np.atleast_1d(v))
+    nbody = int(rng.integers(2, 6 if planar else 7))
     fluid = rng.random() < 0.5
     opt = '<option timestep="%g" gravity="%s"%s/>' % (rng.choice([0.002, 0.005, 0.01]), f(rng.normal(0, 5, 3)),
                                                       ' density="%g" viscosity="%g"' % (rng.uniform(5, 500), rng.uniform(0, 0.05)) if fluid else "")
     bodies, joints, nv = [], [], 0
     parent = [-1] + [int(rng.integers(0, i)) for i in range(1, nbody)]
     for b in range(nbody):
-        nj = 1 if nv >= 10 else int(rng.integers(1, 3))
+        nj = 1 if nv >= (7 if planar else 10) else int(rng.integers(1, 3))
         js = ""
         for k in range(nj):
             kind = "slide" if rng.random() < 0.3 else "hinge"
             ax = rng.normal(0, 1, 3)
+            if planar:
+                ax = n * rng.choice([-1.0, 1.0]) if kind == "hinge" else ax - (ax @ n) * n
             ax /= np.linalg.norm(ax)
             name = "j%d_%d" % (b, k)
             lim = rng.random() < 0.6
@@ -37,6 +44,9 @@ def random_tree_xml(seed: int) -> str:
         else:
             geom = '<geom type="sphere" pos="%s" size="%g"/>' % (f(rng.normal(0, 0.1, 3)), rng.uniform(0.04, 0.08))
         q = rng.normal(0, 1, 4)
+        if planar:                                   # a turn about n
+            ang = rng.uniform(-np.pi, np.pi)
+            q = np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * n])
         bodies.append(dict(open='<body name="b%d" pos="%s" quat="%s">%s%s' % (b, f(rng.normal(0, 0.3, 3)), f(q / np.linalg.norm(q)), js, geom)))
     children = {i: [j for j in range(nbody) if parent[j] == i] for i in range(-1, nbody)}
 

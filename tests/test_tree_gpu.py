@@ -320,6 +320,33 @@ def test_random_trees_match_oracle(seed):
     env.close()
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_planar_mechanisms_both_instantiations(seed):
+    """Random planar mechanisms in a tilted plane whose bodies, anchors and centres of mass sit OFF the plane, with
+    arbitrary inertia tensors, gravity with a component along the normal, fluid or not: the planar reduction is exact --
+    planar and general instantiation against the oracle."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers"))
+    from random_tree import random_tree_xml
+    model = T.compile_mjcf_string(random_tree_xml(seed, planar=True))
+    assert model.nv <= 9 and T.pack_planar(model) is not None
+    env = GpuTreeVecEnv(model, frame_skip=2, fwd_dof=0, w_fwd=1.0, w_ctrl=0.01, obs_qpos_start=0)
+    assert env.dmodel.planar
+    oracle = TreeOracle(model, T.solref_to_kb)
+    rng = np.random.default_rng(300 + seed)
+    K, H = 48, 6
+    state = np.concatenate([rng.uniform(-.6, .6, model.nv), rng.normal(0, 1.0, model.nv)])
+    mean, noise = rng.normal(0, 0.5, (H, model.nu)), rng.normal(0, 1.0, (K, H, model.nu))
+    nefc, nefc_ref, _ = _compare(env, oracle, state, mean, noise)
+    assert nefc == nefc_ref
+    old = _planar_switch(0)
+    try:
+        _compare(env, oracle, state, mean, noise)
+    finally:
+        _planar_switch(old)
+    env.close()
+
+
 def test_non_planar_models_take_the_general_instantiation():
     model = T.compile_mjcf(os.path.join(FIX, "tree3d.xml"))
     assert T.pack_planar(model) is None
