@@ -835,6 +835,13 @@ def pack_planar_contacts(model: TreeModel, tol: float = 1e-9):
             I[c] = (1, -1, l2)
             D[c, CT_A:CT_A + 2], D[c, CT_HA:CT_HA + 2] = plane(ct["a0"]), plane(ct["a1"])
         else:
+            # MuJoCo orients the friction pyramid of a capsule-capsule contact by mju_makeFrame (first tangent from the world
+            # y or z axis), and a pyramid is not invariant under a turn about the normal.  When the plane of motion is a
+            # world coordinate plane the tangents come out in the plane / along its normal -- the three merged rows the kernel
+            # builds; in a tilted plane they would be a mixture, which is not implemented.  (Plane-capsule contacts take their
+            # first tangent from the capsule axis, which lies in the plane of motion whatever its orientation.)
+            if np.sort(np.abs(n))[1] > tol:
+                raise UnsupportedMjcf("capsule-capsule contacts need the plane of motion to be a world coordinate plane")
             l1 = last[ct["body1"]]
             v0, v1 = (xpos[ct["body1"]] + xmat[ct["body1"]] @ ct[e] for e in ("a0", "a1"))
             heights += [n @ v0, n @ v1]

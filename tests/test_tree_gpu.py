@@ -347,6 +347,35 @@ def test_random_planar_mechanisms_both_instantiations(seed):
     env.close()
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_random_planar_mechanisms_with_contacts(seed):
+    """Random 9-dof planar trees in the x-y, y-z and z-x planes whose capsules collide with each other (non-adjacent bodies)
+    and with a floor, random friction / solref / solimp: geometry unlike the swimmer's or the cheetah's through the same
+    contact code.  (In a TILTED plane MuJoCo's mju_makeFrame turns the friction pyramid of a capsule-capsule contact out of
+    the plane of motion; the compiler refuses that case -- checked at the end.)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "helpers"))
+    from random_tree import random_contact_mechanism_xml
+    model = T.compile_mjcf_string(random_contact_mechanism_xml(seed), allow_contacts="model")
+    assert model.nv == 9 and len(model.contacts) >= 5
+    env = GpuTreeVecEnv(model, frame_skip=3, fwd_dof=0, w_fwd=1.0, w_ctrl=0.01, obs_qpos_start=0)
+    assert env.dmodel.n_contacts == len(model.contacts)
+    oracle = TreeOracle(model, T.solref_to_kb)
+    rng = np.random.default_rng(400 + seed)
+    K, H = 48, 6
+    state = np.concatenate([rng.uniform(-.5, .5, 9), rng.normal(0, 1.0, 9)])
+    nefc, nefc_ref, _ = _compare(env, oracle, state, rng.normal(0, 0.5, (H, model.nu)), rng.normal(0, 1.0, (K, H, model.nu)))
+    assert nefc == nefc_ref and nefc > 0
+    env.close()
+    if seed == 0:
+        from random_tree import random_tree_xml
+        tilted = random_tree_xml(3, planar=True).replace('contype="0" conaffinity="0"', 'contype="1" conaffinity="1"')
+        m2 = T.compile_mjcf_string(tilted, allow_contacts="model")
+        if any(c["kind"] == "capsule" for c in m2.contacts):
+            with pytest.raises(T.UnsupportedMjcf):
+                T.pack_planar_contacts(m2)
+
+
 def test_non_planar_models_take_the_general_instantiation():
     model = T.compile_mjcf(os.path.join(FIX, "tree3d.xml"))
     assert T.pack_planar(model) is None
