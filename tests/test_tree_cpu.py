@@ -205,6 +205,25 @@ def test_random_trees_both_restatements_agree(seed):
         assert _rel(a["q"], q2) < 1e-11 and _rel(a["v"], v2) < 1e-10
 
 
+def test_capsule_contacts_in_a_tilted_plane_are_refused():
+    """mju_makeFrame takes the first tangent of a capsule-capsule contact from the world y / z axis: in a tilted plane of
+    motion the friction pyramid is turned out of the plane, which the planar kernel's three merged rows do not represent."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "helpers"))
+    from random_tree import random_contact_mechanism_xml, random_tree_xml
+    ok = T.compile_mjcf_string(random_contact_mechanism_xml(1), allow_contacts="model")       # a coordinate plane
+    assert T.pack_planar_contacts(ok)[0].shape[0] == len(ok.contacts) >= 5
+    found = False
+    for seed in range(6):
+        tilted = random_tree_xml(seed, planar=True).replace('contype="0" conaffinity="0"', 'contype="1" conaffinity="1"')
+        m = T.compile_mjcf_string(tilted, allow_contacts="model")
+        if any(c["kind"] == "capsule" for c in m.contacts):
+            found = True
+            with pytest.raises(T.UnsupportedMjcf, match="coordinate plane|heights"):
+                T.pack_planar_contacts(m)
+    assert found
+
+
 def test_welded_body_in_a_fluid_is_rejected():
     xml = open(os.path.join(FIX, "tree3d_weld.xml")).read().replace('density="0" viscosity="0"', 'density="10" viscosity="0"')
     with pytest.raises(T.UnsupportedMjcf, match="welded"):
